@@ -1,0 +1,114 @@
+/*
+ * pnnp_b200 — C ABI of the B200-native PNNP hot path (libpnnp_b200.so).
+ *
+ * The reference (fenghansen/PNNP) is pure Python and has no FFI; each entry point below
+ * names the reference function (file:line under the reference tree) it replaces.  The
+ * reference-side binding is a ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the name ends in
+ *     `_host`; the library never allocates or frees caller buffers;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream);
+ *   - return value 0 = ok, non-zero = error, message via pnnp_last_error() (thread-local);
+ *   - RNG state is (seed, offset), passed in; nothing is hidden in the library;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns an error.
+ */
+#ifndef PNNP_B200_H
+#define PNNP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNNP_ABI_VERSION 1
+
+/* noise_code letters of generate_noisy_obs (data_process/process.py:598-603) as bits */
+#define PNNP_CODE_P 0x01u /* 'p' Poisson shot noise (else Gaussian approximation)   */
+#define PNNP_CODE_G 0x02u /* 'g' Tukey-lambda read noise (else Gaussian sigGs)       */
+#define PNNP_CODE_R 0x04u /* 'r' per-(channel,row) banding noise                      */
+#define PNNP_CODE_Q 0x08u /* 'q' quantisation noise                                   */
+#define PNNP_CODE_D 0x10u /* 'd' per-channel bias                                     */
+#define PNNP_CODE_B 0x20u /* 'b' black frame: read/row/q/bias all zero                */
+
+/* arithmetic chain (which reference function's rounding sequence is reproduced) */
+#define PNNP_CHAIN_NUMPY 0 /* generate_noisy_obs   process.py:591-631 (NEP-50 promotion)   */
+#define PNNP_CHAIN_TORCH 1 /* generate_noisy_torch process.py:634-673 (float32 throughout) */
+
+/* per-crop flags: which python scalars were np.float64 ("strong") in the reference call */
+#define PNNP_F_K64 0x1u     /* K is np.float64 (sample_params)  → shot term is float64   */
+#define PNNP_F_RATIO64 0x2u /* ratio is np.float64                                         */
+#define PNNP_F_SIG64 0x4u   /* sigR is np.float64                                          */
+
+/* One row per crop (128 bytes).  Mirrors the dict returned by sample_params /
+ * sample_params_max (process.py:311-412): keys K sigTL sigR sigGs bias lam q ratio wp bl. */
+typedef struct pnnp_noise_params {
+    double K;       /* system gain                                  */
+    double sigTL;   /* Tukey-lambda scale                           */
+    double sigGs;   /* Gaussian read-noise sigma                    */
+    double sigR;    /* row-noise sigma                              */
+    double lam;     /* Tukey-lambda shape                           */
+    double q;       /* quantisation step (used by the torch chain)  */
+    double ratio;   /* exposure ratio                               */
+    double span;    /* wp - bl                                      */
+    double clip_lo; /* -bl / wp  (process.py:627)                   */
+    double bias[4]; /* per-channel bias ('d')                       */
+    uint32_t flags; /* PNNP_F_*                                     */
+    uint32_t reserved[5];
+} pnnp_noise_params;
+
+const char* pnnp_last_error(void);
+int pnnp_abi_version(void);
+/* number of kernels this library has launched in the calling process (for gpu_launches) */
+uint64_t pnnp_launch_count(void);
+
+/* P1 — raw2bayer(raw, wp, bl, norm, clip, bias)                 utils/isp_ops.py:84-96
+ * raw: n frames of H x W (uint16 or float32), out: n x 4 x H/2 x W/2 float32, plane order
+ * R(0,0) G1(0,1) B(1,1) G2(1,0).  black4_host[c] = bl + bias[c]; arithmetic in float64,
+ * rounded to float32 once, exactly like the reference. */
+int pnnp_pack_norm_u16(const uint16_t* raw, float* out, int n, int H, int W, double wp,
+                       const double* black4_host, int norm, int clip, void* stream);
+int pnnp_pack_norm_f32(const float* raw, float* out, int n, int H, int W, double wp,
+                       const double* black4_host, int norm, int clip, void* stream);
+
+/* P2 — bayer2raw(packed, wp, bl)                                utils/isp_ops.py:98-112
+ * packed: n x 4 x h x w float32 → raw: n x 2h x 2w uint16 (truncating cast). */
+int pnnp_unpack_quant(const float* packed, uint16_t* raw, int n, int h, int w, float wp, float bl,
+                      void* stream);
+
+/* N1-N3 / N4 — fused noise synthesis, Philox4x32-10 draws generated in-kernel.
+ * clean, noisy: n x c x h x w float32 (may alias);  table: n rows (device).
+ * clip: the reference's `clip` argument (0 → clip to [-bl/wp, 1], non-zero → [0, 1]).
+ * post_lo/post_hi: the caller's follow-up clamp, fused (syn_datasets.py:339-342,
+ * trainer_SID.py:481-485); pass -INF/+INF for none.
+ * crop i uses Philox key = seed, counter = (element index, stream, offset + i-independent) so
+ * results do not depend on grid shape or on how crops are sharded across GPUs:
+ * `crop_id0` is the global index of the first crop in this call. */
+int pnnp_noise_synth(const float* clean, float* noisy, const pnnp_noise_params* table, int n, int c,
+                     int h, int w, uint32_t code_bits, int chain, int ori, int clip, float post_lo,
+                     float post_hi, uint64_t seed, uint64_t offset, uint64_t crop_id0, void* stream);
+
+/* Same launch, but also writes the draws it used (any pointer may be NULL):
+ * d_shot  n*c*h*w f32 — Poisson counts ('p') or the standard-normal shot draw,
+ * d_read  n*c*h*w f32 — read-noise sample in DN (already scaled),
+ * d_rowz  n*c*h   f32 — standard-normal row draw,
+ * d_q     n*c*h*w f64 — numpy chain: U(-0.5,0.5) in DN; torch chain: U[0,1). */
+int pnnp_noise_synth_debug(const float* clean, float* noisy, const pnnp_noise_params* table, int n,
+                           int c, int h, int w, uint32_t code_bits, int chain, int ori, int clip,
+                           float post_lo, float post_hi, uint64_t seed, uint64_t offset,
+                           uint64_t crop_id0, float* d_shot, float* d_read, float* d_rowz,
+                           double* d_q, void* stream);
+
+/* Replay mode: identical arithmetic core, draws supplied by the caller (the reference's own
+ * draws in the parity tests) → bit-exact against generate_noisy_obs / generate_noisy_torch. */
+int pnnp_noise_synth_replay(const float* clean, float* noisy, const pnnp_noise_params* table, int n,
+                            int c, int h, int w, uint32_t code_bits, int chain, int ori, int clip,
+                            float post_lo, float post_hi, const float* d_shot, const float* d_read,
+                            const float* d_rowz, const double* d_q, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNNP_B200_H */

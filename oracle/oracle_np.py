@@ -253,12 +253,13 @@ def parse_noise_code(noise_code: str) -> dict:
 
 
 def tukeylambda_ppf(u, lam):
-    """SciPy's generic inverse-CDF sampling for tukeylambda (scipy/stats/_continuous_distns.py,
-    tukeylambda_gen._ppf): boxcox(u, lam) - boxcox1p(-u, lam); boxcox(x,l)=expm1(l*log x)/l."""
+    """SciPy's generic inverse-CDF sampling for tukeylambda (third-party, scipy 1.18.1,
+    stats/_continuous_distns.py tukeylambda_gen._ppf): boxcox(u, lam) - boxcox1p(-u, lam), i.e.
+    (u^lam - 1)/lam - ((1-u)^lam - 1)/lam.  We call the same scipy.special kernels so the float64
+    value — and therefore its float32 cast — is the one the reference gets."""
+    from scipy import special as sc
     u = np.asarray(u, dtype=F64)
-    if lam == 0:
-        return np.log(u) - np.log1p(-u)
-    return np.expm1(lam * np.log(u)) / lam - np.expm1(lam * np.log1p(-u)) / lam
+    return sc.boxcox(u, lam) - sc.boxcox1p(-u, lam)
 
 
 def is_f64_scalar(x) -> bool:

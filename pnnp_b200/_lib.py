@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in include/pnnp_b200.h.
+
+The product path has NO CPU fallback: if libpnnp_b200.so is missing, or an entry point
+returns non-zero, a RuntimeError is raised (the reference's trainers catch RuntimeError,
+trainer_LRID.py:131-135, so the error behaviour of a failed device op is preserved).
+"""
+import ctypes as C
+import os
+
+import torch  # noqa: F401  loads libcudart.so.12 into the process before our library resolves it
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpnnp_b200.so")
+
+
+class NoiseParamsRow(C.Structure):
+    """struct pnnp_noise_params (128 bytes)."""
+    _fields_ = [("K", C.c_double), ("sigTL", C.c_double), ("sigGs", C.c_double), ("sigR", C.c_double),
+                ("lam", C.c_double), ("q", C.c_double), ("ratio", C.c_double), ("span", C.c_double),
+                ("clip_lo", C.c_double), ("bias", C.c_double * 4), ("flags", C.c_uint32),
+                ("reserved", C.c_uint32 * 5)]
+
+
+assert C.sizeof(NoiseParamsRow) == 128
+
+CODE_P, CODE_G, CODE_R, CODE_Q, CODE_D, CODE_B = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+CHAIN_NUMPY, CHAIN_TORCH = 0, 1
+F_K64, F_RATIO64, F_SIG64 = 0x1, 0x2, 0x4
+
+_vp, _i, _u32, _u64, _f, _d = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_float, C.c_double
+
+# name -> (restype, argtypes); must list every symbol include/pnnp_b200.h declares
+SIGNATURES = {
+    "pnnp_last_error": (C.c_char_p, []),
+    "pnnp_abi_version": (_i, []),
+    "pnnp_launch_count": (_u64, []),
+    "pnnp_pack_norm_u16": (_i, [_vp, _vp, _i, _i, _i, _d, C.POINTER(C.c_double), _i, _i, _vp]),
+    "pnnp_pack_norm_f32": (_i, [_vp, _vp, _i, _i, _i, _d, C.POINTER(C.c_double), _i, _i, _vp]),
+    "pnnp_unpack_quant": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    "pnnp_noise_synth": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _f, _u64, _u64, _u64, _vp]),
+    "pnnp_noise_synth_debug": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _f, _u64, _u64, _u64,
+                                    _vp, _vp, _vp, _vp, _vp]),
+    "pnnp_noise_synth_replay": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _f,
+                                     _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"pnnp_b200: native library {LIB_PATH} is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or pnnp_b200/csrc/build.sh). "
+                "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError(f"pnnp_b200 {what} failed: {lib().pnnp_last_error().decode(errors='replace')}")
+
+
+def ptr(t) -> int:
+    """Device (or host) pointer of a torch tensor / None."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().pnnp_launch_count())
+
+
+def require_cuda(t, name="tensor"):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"pnnp_b200: {name} must be a CUDA tensor (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"pnnp_b200: {name} must be contiguous")

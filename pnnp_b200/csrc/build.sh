@@ -1,0 +1,20 @@
+#!/bin/bash
+# Builds libpnnp_b200.so (sm_100a) in-tree.  Usage: pnnp_b200/csrc/build.sh
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../libpnnp_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -cudart shared
+       --expt-relaxed-constexpr -Xptxas -v)
+mkdir -p "$HERE/_obj"
+pids=()
+for f in "$HERE"/*.cu; do
+  o="$HERE/_obj/$(basename "${f%.cu}").o"
+  if [[ ! -f "$o" || "$f" -nt "$o" || -n "$(find "$HERE" "$HERE/../../include" -name '*.h' -newer "$o" -o -name '*.cuh' -newer "$o")" ]]; then
+    ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+"$NVCC" -shared -cudart shared -o "$OUT" "$HERE"/_obj/*.o
+echo "built $OUT"

@@ -1,0 +1,264 @@
+// Device-side core of the fused noise synthesis: Philox4x32-10, the samplers, and the
+// deterministic arithmetic ("tail") shared by the Philox kernel and the replay kernel.
+//
+// Reference semantics: data_process/process.py:591-631 (generate_noisy_obs, NumPy chain) and
+// :634-673 (generate_noisy_torch, float32 chain).  The cast-by-cast specification this file is
+// written from is oracle/oracle_np.py::noisy_obs_tail_explicit / noisy_torch_tail.
+//
+// Every arithmetic step of the tails uses the *_rn intrinsics so that nvcc can never contract
+// a mul+add into an FMA: the reference rounds after every NumPy / torch op.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/pnnp_b200.h"
+
+namespace pnnp {
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw — SC'11).  Counter layout used by this library:
+//   key  = (seed_lo, seed_hi)
+//   ctr0 = index_lo            ctr1 = index_hi[15:0] | sub << 16 | stream << 24
+//   ctr2 = offset_lo           ctr3 = offset_hi
+// index = global element index (stream ELEM) or global (crop, channel, row) index (stream ROW).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+constexpr uint32_t kStreamElem = 0u, kStreamRow = 1u;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
+        const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += kPhiloxW0;
+        k.y += kPhiloxW1;
+    }
+    return c;
+}
+
+struct RngCtx {
+    uint2 key;
+    uint32_t off_lo, off_hi;
+    __device__ __forceinline__ uint4 block(uint64_t index, uint32_t stream, uint32_t sub) const {
+        const uint32_t c1 = (uint32_t)((index >> 32) & 0xFFFFu) | (sub << 16) | (stream << 24);
+        return philox4x32_10(make_uint4((uint32_t)index, c1, off_lo, off_hi), key);
+    }
+};
+
+// (0,1) with 24 random bits, exactly representable in float32
+__device__ __forceinline__ float u01_24(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+// [0,1) with 24 random bits (torch.rand's lattice)
+__device__ __forceinline__ float u01_24_closed0(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-8f; }
+// (0,1] ∩ float32 from all 32 bits: relative precision kept near 0 (tails)
+__device__ __forceinline__ float u01_32(uint32_t w) { return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// standard normal from two words (Box–Muller, cosine branch)
+__device__ __forceinline__ float normal_bm(uint32_t w0, uint32_t w1) {
+    const float u1 = u01_32(w0);
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
+    const float th = (u01_24_closed0(w1) - 0.5f) * 6.283185307179586f;
+    return r * __cosf(th);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tukey-lambda quantile  Q(u) = (u^lam - (1-u)^lam) / lam   (lam -> 0: logit)
+// u and 1-u are formed separately from the word so both tails keep relative precision.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tukey_lambda_ppf(uint32_t w, float lam, float inv_lam) {
+    const float a = u01_32(w), b = u01_32(~w);
+    const float la = __log2f(a), lb = __log2f(b);
+    if (fabsf(lam) < 1e-3f) {
+        const float xa = la * 0.6931471805599453f, xb = lb * 0.6931471805599453f;
+        const float d1 = xa - xb, d2 = xa * xa - xb * xb, d3 = xa * xa * xa - xb * xb * xb;
+        return d1 + lam * (0.5f * d2 + lam * 0.16666667f * d3);
+    }
+    return (exp2f(lam * la) - exp2f(lam * lb)) * inv_lam;
+}
+
+// ------------------------------------------------------------------------------------------
+// Poisson sampler.  lam < 10: inversion by sequential search on one uniform;
+// lam >= 10: Hörmann's transformed rejection with squeeze (PTRS, Insurance: Math. & Econ. 12, 1993).
+// Same two algorithms NumPy's legacy RandomState.poisson (the reference's sampler) chooses
+// between at the same threshold; the draws come from Philox instead of MT19937.
+// smem: s_inv[k] = 1/k (k = 1..63), s_lfact[k] = ln k! (k = 0..15)
+// ------------------------------------------------------------------------------------------
+constexpr int kInvTab = 64, kLfactTab = 16;
+
+__device__ __forceinline__ void init_poisson_tables(float* s_inv, float* s_lfact) {
+    for (int i = threadIdx.x; i < kInvTab; i += blockDim.x) s_inv[i] = i ? 1.0f / (float)i : 0.f;
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+        s_lfact[0] = 0.f;
+        for (int k = 1; k < kLfactTab; ++k) { acc += log((double)k); s_lfact[k] = (float)acc; }
+    }
+}
+
+__device__ __forceinline__ float poisson_small(float lam, uint32_t w, const float* s_inv) {
+    const float u = u01_24(w);
+    float p = __expf(-lam), F = p;
+    int k = 0;
+    while (u > F && k < kInvTab - 1) {
+        ++k;
+        p *= lam * s_inv[k];
+        F += p;
+    }
+    return (float)k;
+}
+
+__device__ __forceinline__ float poisson_ptrs(float lam, uint32_t w0, uint32_t w1, const RngCtx& rng,
+                                              uint64_t index, const float* s_lfact) {
+    const float slam = sqrtf(lam);
+    const float ln_lam = __logf(lam);
+    const float b = 0.931f + 2.53f * slam;
+    const float a = -0.059f + 0.02483f * b;
+    const float inv_alpha = 1.1239f + __fdividef(1.1328f, b - 3.4f);
+    const float vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
+    uint32_t wu = w0, wv = w1;
+    uint4 blk = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int t = 0; t < 64; ++t) {
+        if (t > 0) {
+            if (t & 1) { blk = rng.block(index, kStreamElem, 2u + (uint32_t)(t >> 1)); wu = blk.x; wv = blk.y; }
+            else       { wu = blk.z; wv = blk.w; }
+        }
+        const float U = u01_24(wu) - 0.5f;
+        const float V = u01_24(wv);
+        const float us = 0.5f - fabsf(U);
+        const float kf = floorf((__fdividef(2.0f * a, us) + b) * U + lam + 0.43f);
+        if (us >= 0.07f && V <= vr) return kf;
+        if (kf < 0.f || (us < 0.013f && V > us)) continue;
+        const float lhs = __logf(V * inv_alpha / (__fdividef(a, us * us) + b));
+        float rhs;
+        if (kf < (float)kLfactTab) {
+            rhs = -lam + kf * ln_lam - s_lfact[(int)kf];
+        } else {
+            // ln pmf in a cancellation-free form: k ln(lam/k) + (k - lam) - ln sqrt(2 pi k) - Stirling tail
+            const float ik = __fdividef(1.0f, kf);
+            rhs = kf * __logf(lam * ik) + (kf - lam) - 0.5f * __logf(6.283185307179586f * kf)
+                  - ik * (0.083333333f - 0.0027777778f * ik * ik);
+        }
+        if (lhs <= rhs) return kf;
+    }
+    return floorf(lam + 0.5f);   // unreachable in practice (rejection probability^64)
+}
+
+__device__ __forceinline__ float poisson_sample(float lam, uint32_t w0, uint32_t w1, const RngCtx& rng,
+                                                uint64_t index, const float* s_inv, const float* s_lfact) {
+    if (!(lam > 0.f)) return 0.f;
+    if (lam < 10.f) return poisson_small(lam, w0, s_inv);
+    return poisson_ptrs(lam, w0, w1, rng, index, s_lfact);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-crop parameters as the kernels hold them (one table row, read through L1 by every lane)
+// ------------------------------------------------------------------------------------------
+struct RowP {
+    double K, sigTL, sigGs, sigR, lam, q, ratio, span, lo;
+    uint32_t flags;
+};
+__device__ __forceinline__ RowP load_row_params(const pnnp_noise_params* t) {
+    RowP p;
+    p.K = t->K; p.sigTL = t->sigTL; p.sigGs = t->sigGs; p.sigR = t->sigR; p.lam = t->lam; p.q = t->q;
+    p.ratio = t->ratio; p.span = t->span; p.lo = t->clip_lo; p.flags = t->flags;
+    return p;
+}
+
+// Scale-in (process.py:593-595) and the Poisson rate / Gaussian-shot scale the reference forms.
+struct ScaleIn { float ysc32; double ysc64; };
+__device__ __forceinline__ ScaleIn scale_in_numpy(float y, const RowP& p) {
+    ScaleIn s;
+    const float y32 = __fmul_rn(y, (float)p.span);
+    if (p.flags & PNNP_F_RATIO64) { s.ysc64 = __ddiv_rn((double)y32, p.ratio); s.ysc32 = (float)s.ysc64; }
+    else { s.ysc32 = __fdiv_rn(y32, (float)p.ratio); s.ysc64 = (double)s.ysc32; }
+    return s;
+}
+__device__ __forceinline__ float poisson_rate_numpy(const ScaleIn& s, const RowP& p) {
+    // 1.0*y/K in K's precision (float64 if either side is float64); our sampler consumes float32
+    if (p.flags & (PNNP_F_K64 | PNNP_F_RATIO64)) return (float)(s.ysc64 / p.K);
+    return __fdiv_rn(s.ysc32, (float)p.K);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tail, NumPy chain.  d_shot = Poisson count (code P) or N(0,1) draw; d_read in DN;
+// d_rowz = N(0,1) row draw; d_q = U(-.5,.5) in DN (float64); bias_c = per-channel bias.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tail_numpy(float y, const RowP& p, uint32_t code, bool ori, bool clip01,
+                                            float d_shot, float d_read, float d_rowz, double d_q, double bias_c) {
+    const bool k64 = p.flags & PNNP_F_K64, r64 = p.flags & PNNP_F_RATIO64, s64 = p.flags & PNNP_F_SIG64;
+    const float span32 = (float)p.span;
+    const ScaleIn s = scale_in_numpy(y, p);
+    bool a64;
+    float a32 = 0.f;
+    double A = 0.0;
+    if (code & PNNP_CODE_P) {
+        if (k64) { A = __dmul_rn((double)d_shot, p.K); a64 = true; }
+        else     { a32 = __fmul_rn(d_shot, (float)p.K); a64 = false; }
+    } else if (k64 || r64) {
+        const double yy = s.ysc64;
+        const double t = __dsqrt_rn(fmax(__ddiv_rn(yy, p.K), 1e-10));
+        A = __dadd_rn(yy, __dmul_rn(__dmul_rn((double)d_shot, t), p.K));
+        a64 = true;
+    } else {
+        const float K32 = (float)p.K;
+        const float t = __fsqrt_rn(fmaxf(__fdiv_rn(s.ysc32, K32), 1e-10f));
+        a32 = __fadd_rn(s.ysc32, __fmul_rn(__fmul_rn(d_shot, t), K32));
+        a64 = false;
+    }
+    if (!(code & PNNP_CODE_B)) {
+        if (a64) A = __dadd_rn(A, (double)d_read); else a32 = __fadd_rn(a32, d_read);
+        if (code & PNNP_CODE_R) {
+            if (s64) {
+                if (!a64) { A = (double)a32; a64 = true; }
+                A = __dadd_rn(A, __dmul_rn((double)d_rowz, p.sigR));
+            } else {
+                const float row32 = __fmul_rn(d_rowz, (float)p.sigR);
+                if (a64) A = __dadd_rn(A, (double)row32); else a32 = __fadd_rn(a32, row32);
+            }
+        }
+        if (code & PNNP_CODE_Q) {
+            if (!a64) { A = (double)a32; a64 = true; }
+            A = __dadd_rn(A, d_q);
+        }
+        if (code & PNNP_CODE_D) {
+            if (!a64) { A = (double)a32; a64 = true; }
+            A = __dadd_rn(A, bias_c);
+        }
+    }
+    if (a64) {
+        double z = __ddiv_rn(A, p.span);
+        z = clip01 ? fmin(fmax(z, 0.0), 1.0) : fmin(fmax(z, p.lo), 1.0);
+        if (!ori) z = __dmul_rn(z, p.ratio);
+        return (float)z;
+    }
+    float z = __fdiv_rn(a32, span32);
+    z = clip01 ? fminf(fmaxf(z, 0.f), 1.f) : fminf(fmaxf(z, (float)p.lo), 1.f);
+    if (!ori) {
+        if (r64) return (float)__dmul_rn((double)z, p.ratio);
+        z = __fmul_rn(z, (float)p.ratio);
+    }
+    return z;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tail, torch chain (float32 throughout; d_q = U[0,1) draw, q = (u-0.5)*q*(wp-bl)).
+// 'b' zeroes only the read term there (process.py:652-661).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float scale_in_torch(float y, const RowP& p) {
+    return __fdiv_rn(__fmul_rn(y, (float)p.span), (float)p.ratio);
+}
+__device__ __forceinline__ float tail_torch(const RowP& p, uint32_t code, bool ori, bool clip01, float d_shot,
+                                            float d_read, float d_rowz, float d_qu) {
+    const float span32 = (float)p.span, K32 = (float)p.K, ratio32 = (float)p.ratio;
+    float acc = __fmul_rn(d_shot, K32);
+    acc = __fadd_rn(acc, (code & PNNP_CODE_B) ? 0.f : d_read);
+    if (code & PNNP_CODE_R) acc = __fadd_rn(acc, __fmul_rn(d_rowz, (float)p.sigR));
+    if (code & PNNP_CODE_Q)
+        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__fsub_rn(d_qu, 0.5f), (float)p.q), span32));
+    float z = __fdiv_rn(acc, span32);
+    z = clip01 ? fminf(fmaxf(z, 0.f), 1.f) : fminf(fmaxf(z, (float)p.lo), 1.f);
+    if (!ori) z = __fmul_rn(z, ratio32);
+    return z;
+}
+
+}  // namespace pnnp

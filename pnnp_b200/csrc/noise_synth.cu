@@ -1,0 +1,239 @@
+// Fused physics-based noise synthesis for packed Bayer crops (sm_100a).
+//
+// Replaces the per-crop Python loops around generate_noisy_obs / generate_noisy_torch
+// (data_process/process.py:591-673; callers data_process/syn_datasets.py:326-337 and
+// trainer_SID.py:449-462): one launch for all crops, one HBM read of the clean tensor and one
+// write of the noisy tensor (8 B per element), parameters from a small device table.
+//
+// Work decomposition: one warp per (crop, channel, row, 512-element segment).  Each lane owns
+// up to four float4 groups (128-bit coalesced loads/stores, lane-interleaved).  The row-noise
+// draw is keyed on the (crop, channel, row) index, so every lane of every warp that touches the
+// row computes the same value — a broadcast by construction, no shuffle needed.
+#include <cmath>
+#include <cstdio>
+#include "abi_common.h"
+#include "noise_core.cuh"
+
+namespace pnnp {
+
+struct SynthArgs {
+    const float* clean;
+    float* noisy;
+    const pnnp_noise_params* table;
+    int n, c, h, w;
+    uint32_t code;
+    int ori, clip;
+    float post_lo, post_hi;
+    uint64_t seed, offset, crop_id0;
+    // debug outputs / replay inputs (NULL when unused)
+    float* d_shot; float* d_read; float* d_rowz; double* d_q;
+};
+
+constexpr int kSeg = 512;          // elements per warp work unit
+constexpr int kThreads = 256;
+
+// One element, Philox mode.  Returns the noisy value; optionally records the draws.
+template <int CHAIN, bool DEBUG>
+__device__ __forceinline__ float synth_one(float y, uint64_t gidx, size_t lidx, int crop, int ch, const RowP& p,
+                                           const SynthArgs& a, const RngCtx& rng, float rowz, float lam_tl,
+                                           float inv_lam_tl, const float* s_inv, const float* s_lfact) {
+    const uint32_t code = a.code;
+    const uint4 w = rng.block(gidx, kStreamElem, 0u);
+    uint4 w2 = make_uint4(0, 0, 0, 0);
+    const bool need_normals = !(code & PNNP_CODE_P) || (!(code & PNNP_CODE_G) && !(code & PNNP_CODE_B));
+    if (need_normals) w2 = rng.block(gidx, kStreamElem, 1u);
+
+    float lam, d_shot;
+    ScaleIn s;
+    if (CHAIN == PNNP_CHAIN_NUMPY) { s = scale_in_numpy(y, p); lam = poisson_rate_numpy(s, p); }
+    else { s.ysc32 = scale_in_torch(y, p); s.ysc64 = 0.0; lam = __fdiv_rn(s.ysc32, (float)p.K); }
+    if (code & PNNP_CODE_P) d_shot = poisson_sample(lam, w.x, w.y, rng, gidx, s_inv, s_lfact);
+    else d_shot = normal_bm(w2.z, w2.w);
+
+    float d_read = 0.f;
+    if (!(code & PNNP_CODE_B)) {
+        if ((code & PNNP_CODE_G) && CHAIN == PNNP_CHAIN_NUMPY)
+            d_read = tukey_lambda_ppf(w.z, lam_tl, inv_lam_tl) * (float)p.sigTL;
+        else
+            d_read = normal_bm(w2.x, w2.y) * (float)p.sigGs;
+    }
+    float out;
+    double dq = 0.0;
+    if (CHAIN == PNNP_CHAIN_NUMPY) {
+        // numpy: uniform(-0.5, 0.5) is float64; (w + 0.5) * 2^-32 - 0.5 is exact in float64
+        if (code & PNNP_CODE_Q) dq = fma((double)w.w, 2.3283064365386963e-10, 1.1641532182693481e-10) - 0.5;
+        const double bias_c = (code & PNNP_CODE_D) ? a.table[crop].bias[ch & 3] : 0.0;
+        out = tail_numpy(y, p, code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, dq, bias_c);
+    } else {
+        const float qu = u01_24_closed0(w.w);
+        dq = (double)qu;
+        out = tail_torch(p, code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, qu);
+    }
+    out = fminf(fmaxf(out, a.post_lo), a.post_hi);
+    if (DEBUG) {
+        if (a.d_shot) a.d_shot[lidx] = d_shot;
+        if (a.d_read) a.d_read[lidx] = d_read;
+        if (a.d_q) a.d_q[lidx] = dq;
+    }
+    return out;
+}
+
+template <int CHAIN, bool DEBUG, int VEC>
+__global__ void __launch_bounds__(kThreads) noise_synth_kernel(const SynthArgs a) {
+    __shared__ float s_inv[kInvTab];
+    __shared__ float s_lfact[kLfactTab];
+    init_poisson_tables(s_inv, s_lfact);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const long long warps_total = (long long)gridDim.x * (kThreads / 32);
+    const long long warp_id = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int nseg = (a.w + kSeg - 1) / kSeg;
+    const long long rows = (long long)a.n * a.c * a.h;
+    const long long units = rows * nseg;
+    RngCtx rng;
+    rng.key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    rng.off_lo = (uint32_t)a.offset;
+    rng.off_hi = (uint32_t)(a.offset >> 32);
+    const size_t crop_elems = (size_t)a.c * a.h * a.w;
+
+    for (long long u = warp_id; u < units; u += warps_total) {
+        const long long row = u / nseg;
+        const int seg = (int)(u - row * nseg);
+        const int crop = (int)(row / ((long long)a.c * a.h));
+        const int ch = (int)((row / a.h) % a.c);
+        const RowP p = load_row_params(a.table + crop);
+        const float lam_tl = (float)p.lam;
+        const float inv_lam_tl = lam_tl != 0.f ? 1.0f / lam_tl : 0.f;
+        float rowz = 0.f;
+        if (a.code & PNNP_CODE_R) {
+            const uint64_t grow = a.crop_id0 * (uint64_t)a.c * a.h + (uint64_t)row;
+            const uint4 wr = rng.block(grow, kStreamRow, 0u);
+            rowz = normal_bm(wr.x, wr.y);
+            if (DEBUG && a.d_rowz && seg == 0 && lane == 0) a.d_rowz[row] = rowz;
+        }
+        const size_t row_base = (size_t)row * a.w;
+        const uint64_t g_base = a.crop_id0 * (uint64_t)crop_elems + (uint64_t)row_base;
+        const int x0 = seg * kSeg;
+        if (VEC == 4) {
+#pragma unroll 1
+            for (int j = 0; j < kSeg / 128; ++j) {
+                const int x = x0 + (j * 32 + lane) * 4;
+                if (x >= a.w) break;
+                const float4 y = __ldcs(reinterpret_cast<const float4*>(a.clean + row_base + x));
+                float4 o;
+                o.x = synth_one<CHAIN, DEBUG>(y.x, g_base + x + 0, row_base + x + 0, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
+                o.y = synth_one<CHAIN, DEBUG>(y.y, g_base + x + 1, row_base + x + 1, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
+                o.z = synth_one<CHAIN, DEBUG>(y.z, g_base + x + 2, row_base + x + 2, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
+                o.w = synth_one<CHAIN, DEBUG>(y.w, g_base + x + 3, row_base + x + 3, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
+                __stcs(reinterpret_cast<float4*>(a.noisy + row_base + x), o);
+            }
+        } else {
+#pragma unroll 1
+            for (int x = x0 + lane; x < min(a.w, x0 + kSeg); x += 32) {
+                const float y = a.clean[row_base + x];
+                a.noisy[row_base + x] = synth_one<CHAIN, DEBUG>(y, g_base + x, row_base + x, crop, ch, p, a, rng, rowz, lam_tl,
+                                                               inv_lam_tl, s_inv, s_lfact);
+            }
+        }
+    }
+}
+
+// Replay: same tails, draws read from memory.  One thread per element (test path, not tuned).
+template <int CHAIN>
+__global__ void noise_replay_kernel(const SynthArgs a) {
+    const size_t total = (size_t)a.n * a.c * a.h * a.w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / a.w;
+        const int crop = (int)(row / ((size_t)a.c * a.h));
+        const int ch = (int)((row / a.h) % a.c);
+        const RowP p = load_row_params(a.table + crop);
+        const float y = a.clean[i];
+        const float d_shot = a.d_shot ? a.d_shot[i] : 0.f;
+        const float d_read = a.d_read ? a.d_read[i] : 0.f;
+        const float rowz = a.d_rowz ? a.d_rowz[row] : 0.f;
+        const double dq = a.d_q ? a.d_q[i] : 0.0;
+        float out;
+        if (CHAIN == PNNP_CHAIN_NUMPY) {
+            const double bias_c = (a.code & PNNP_CODE_D) ? a.table[crop].bias[ch & 3] : 0.0;
+            out = tail_numpy(y, p, a.code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, dq, bias_c);
+        } else {
+            out = tail_torch(p, a.code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, (float)dq);
+        }
+        a.noisy[i] = fminf(fmaxf(out, a.post_lo), a.post_hi);
+    }
+}
+
+static int check_common(const SynthArgs& a, int chain, bool replay) {
+    if (!a.clean || !a.noisy || !a.table) return fail("noise_synth: null pointer");
+    if (a.n <= 0 || a.c <= 0 || a.h <= 0 || a.w <= 0) return fail("noise_synth: empty shape");
+    if (chain != PNNP_CHAIN_NUMPY && chain != PNNP_CHAIN_TORCH) return fail("noise_synth: unknown chain");
+    if (chain == PNNP_CHAIN_TORCH) {
+        // mirror the reference's failures (process.py:651,654,663)
+        if (!(a.code & PNNP_CODE_P)) return fail("generate_noisy_torch: shot noise without 'p' is unsupported by the reference");
+        if ((a.code & PNNP_CODE_G) && !(a.code & PNNP_CODE_B)) return fail("generate_noisy_torch: Tukey-lambda ('g') is NotImplemented in the reference");
+        if (a.code & PNNP_CODE_D) return fail("generate_noisy_torch: 'd' is unsupported by the reference");
+    }
+    if ((a.code & PNNP_CODE_D) && a.c > 4) return fail("noise_synth: 'd' needs c <= 4");
+    (void)replay;
+    return 0;
+}
+
+template <bool DEBUG>
+static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
+    if (int e = check_common(a, chain, false)) return e;
+    int dev = 0, sms = 0;
+    PNNP_CUDA(cudaGetDevice(&dev));
+    PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const bool vec = (a.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.clean) | reinterpret_cast<uintptr_t>(a.noisy)) % 16 == 0);
+    const int nseg = (a.w + kSeg - 1) / kSeg;
+    const long long units = (long long)a.n * a.c * a.h * nseg;
+    const long long want = (units + (kThreads / 32) - 1) / (kThreads / 32);
+    const int blocks = (int)std::min<long long>(want, (long long)sms * 8);   // 8 CTAs of 256 threads per SM = 64 warps
+#define PNNP_LAUNCH(CH, V) noise_synth_kernel<CH, DEBUG, V><<<blocks, kThreads, 0, st>>>(a)
+    if (chain == PNNP_CHAIN_NUMPY) { if (vec) PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 4); else PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 1); }
+    else                           { if (vec) PNNP_LAUNCH(PNNP_CHAIN_TORCH, 4); else PNNP_LAUNCH(PNNP_CHAIN_TORCH, 1); }
+#undef PNNP_LAUNCH
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pnnp
+
+using namespace pnnp;
+
+extern "C" int pnnp_noise_synth(const float* clean, float* noisy, const pnnp_noise_params* table, int n, int c,
+                                int h, int w, uint32_t code_bits, int chain, int ori, int clip, float post_lo,
+                                float post_hi, uint64_t seed, uint64_t offset, uint64_t crop_id0, void* stream) {
+    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, seed, offset, crop_id0,
+                nullptr, nullptr, nullptr, nullptr};
+    return launch_synth<false>(a, chain, (cudaStream_t)stream);
+}
+
+extern "C" int pnnp_noise_synth_debug(const float* clean, float* noisy, const pnnp_noise_params* table, int n,
+                                      int c, int h, int w, uint32_t code_bits, int chain, int ori, int clip,
+                                      float post_lo, float post_hi, uint64_t seed, uint64_t offset,
+                                      uint64_t crop_id0, float* d_shot, float* d_read, float* d_rowz,
+                                      double* d_q, void* stream) {
+    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, seed, offset, crop_id0,
+                d_shot, d_read, d_rowz, d_q};
+    return launch_synth<true>(a, chain, (cudaStream_t)stream);
+}
+
+extern "C" int pnnp_noise_synth_replay(const float* clean, float* noisy, const pnnp_noise_params* table, int n,
+                                       int c, int h, int w, uint32_t code_bits, int chain, int ori, int clip,
+                                       float post_lo, float post_hi, const float* d_shot, const float* d_read,
+                                       const float* d_rowz, const double* d_q, void* stream) {
+    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, 0, 0, 0,
+                const_cast<float*>(d_shot), const_cast<float*>(d_read), const_cast<float*>(d_rowz),
+                const_cast<double*>(d_q)};
+    if (int e = check_common(a, chain, true)) return e;
+    const size_t total = (size_t)n * c * h * w;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    if (chain == PNNP_CHAIN_NUMPY) noise_replay_kernel<PNNP_CHAIN_NUMPY><<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    else noise_replay_kernel<PNNP_CHAIN_TORCH><<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,57 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))   # tests are allowed to import the oracle
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+def decode_param(d):
+    """Inverse of oracle/make_golden.py::_jsonable — restores the exact python / numpy types."""
+    out = {}
+    for k, v in d.items():
+        if "nd" in v:
+            out[k] = np.array(v["nd"], dtype=v["dtype"])
+        elif "f64" in v:
+            out[k] = np.float64(float.fromhex(v["f64"]))
+        elif "pyf" in v:
+            out[k] = float.fromhex(v["pyf"])
+        else:
+            out[k] = int(v["pyi"])
+    return out
+
+
+@pytest.fixture(scope="session")
+def meta():
+    with open(os.path.join(GOLDEN, "meta.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    cache = {}
+
+    def load(name):
+        if name not in cache:
+            cache[name] = np.load(os.path.join(GOLDEN, name + ".npz"))
+        return cache[name]
+    return load

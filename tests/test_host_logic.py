@@ -1,0 +1,103 @@
+"""Product host logic that needs no GPU: parameter sampling, table packing, the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pnnp_b200 as P
+from pnnp_b200 import _lib
+from pnnp_b200.noise_params import fill_row
+from conftest import ROOT, decode_param
+
+
+def test_param_sampling_matches_reference_goldens(meta):
+    for case in meta["params"]:
+        np.random.seed(case["seed"])
+        got = getattr(P, case["fn"])(case["camera"], **case["kwargs"])
+        want = decode_param(case["out"])
+        assert got.keys() == want.keys()
+        for k in want:
+            assert type(got[k]) is type(want[k]), (case["fn"], case["camera"], case["kwargs"], k)
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), (case, k)
+
+
+def test_param_sampling_reference_errors():
+    for cam in ("IMX686", "NikonD850"):
+        with pytest.raises(KeyError, match="uReadk"):
+            P.sample_params(cam)
+    with pytest.raises(KeyError):
+        P.sample_params_max("SonyA7S2", iso=123)
+
+
+def test_noise_code_bits():
+    assert P.noise_code_bits("pgrq") == 0x0F and P.noise_code_bits("PR") == 0x05
+    assert P.noise_code_bits("pgrqdb") == 0x3F and P.noise_code_bits("") == 0
+
+
+def test_param_row_flags():
+    np.random.seed(0)
+    row = _lib.NoiseParamsRow()
+    fill_row(row, P.sample_params("SonyA7S2"))
+    assert row.flags == (_lib.F_K64 | _lib.F_SIG64) and row.span == 15871 and row.clip_lo == -512 / 16383
+    fill_row(row, P.sample_params_max("SonyA7S2", iso=1600))
+    assert row.flags == 0
+    fill_row(row, P.sample_params_max("IMX686", iso=6400))
+    assert row.flags == _lib.F_RATIO64 and list(row.bias) == [-0.08113494, -0.04906388, -0.9408157, -1.2048522]
+    fill_row(row, P.sample_params_max("IMX686"), torch_chain=True)
+    assert row.flags == 0 and row.clip_lo == float(np.float32(-64.0) / np.float32(1023.0))
+
+
+def test_error_mirroring_without_gpu():
+    p = {"K": 1.0, "sigTL": 1.0, "sigR": 1.0, "sigGs": 1.0, "bias": 0, "lam": 0.1, "q": 1e-3, "ratio": 2.0,
+         "wp": 1023, "bl": 64}
+    with pytest.raises(AttributeError):
+        P.generate_noisy_obs(np.zeros((4, 2, 2), np.float32), param=p, noise_code="pd")
+    import torch
+    t = torch.zeros(4, 2, 2)
+    with pytest.raises(TypeError):
+        P.generate_noisy_torch(t, param=p, noise_code="r")
+    with pytest.raises(NotImplementedError):
+        P.generate_noisy_torch(t, param=p, noise_code="pg")
+    with pytest.raises(TypeError):
+        P.generate_noisy_torch(t, param=p, noise_code="pd")
+
+
+def test_abi_exports_every_declared_symbol():
+    """The shared library loads and exports exactly what include/pnnp_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "pnnp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pnnp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 9
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().pnnp_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA tensor"):
+        P.generate_noisy_obs(np.zeros((4, 4, 4), np.float32),
+                             param={"K": 1.0, "sigTL": 1.0, "sigR": 1.0, "sigGs": 1.0, "bias": 0, "lam": 0.1,
+                                    "q": 1e-3, "ratio": 2.0, "wp": 1023, "bl": 64}, noise_code="p")
+    with pytest.raises(RuntimeError):
+        P.raw2bayer(np.zeros((4, 4), np.uint16))
+
+
+def test_product_never_imports_oracle():
+    """No import / include / dlopen of anything under oracle/ from the product package."""
+    pkg = os.path.join(ROOT, "pnnp_b200")
+    pat_py = re.compile(r"^\s*(import|from)\s+(oracle|oracle_np|ref_harness)\b|sys\.path.*oracle|CDLL\(.*oracle", re.M)
+    pat_c = re.compile(r"#\s*include\s*[\"<][^\">]*oracle")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            src_path = os.path.join(dp, fn)
+            if fn.endswith(".py"):
+                assert not pat_py.search(open(src_path).read()), fn
+            elif fn.endswith((".cu", ".cuh", ".h", ".sh")):
+                assert not pat_c.search(open(src_path).read()), fn
