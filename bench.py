@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
+        self.index, self.samples, self.reasons, self._halt = index, [], set(), threading.Event()
         self.max_mhz = None
         try:
             import pynvml
@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
         names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                  "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
                  "hw_power_brake": 0x80}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.002)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=1.0)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,

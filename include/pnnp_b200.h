@@ -108,6 +108,40 @@ int pnnp_noise_synth_replay(const float* clean, float* noisy, const pnnp_noise_p
                             float post_lo, float post_hi, const float* d_shot, const float* d_read,
                             const float* d_rowz, const double* d_q, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * U1 / U2 building blocks — UNetSeeInDark.forward (archs/Unet.py:54-99) and ResUnet.forward
+ * (archs/ResUnet.py:46-88, archs/modules.py:130-197) as tcgen05/TMEM implicit-GEMM layers.
+ * Activations: NHWC bf16, channel counts multiples of 16.  Weights: bf16 [taps][rows][cin_total]
+ * (cin innermost), taps = 9 (ky*3+kx) | 1 | 4 (a*2+b for ConvTranspose2d(2, stride 2)).
+ * ------------------------------------------------------------------------------------------ */
+#define PNNP_CONV3 0 /* nn.Conv2d(k=3, s=1, p=1)                    */
+#define PNNP_CONV1 1 /* nn.Conv2d(k=1)                              */
+#define PNNP_CONVT 2 /* nn.ConvTranspose2d(k=2, s=2): output 2h x 2w */
+#define PNNP_ACT_NONE 0
+#define PNNP_ACT_LEAKY02 1 /* nn.LeakyReLU(0.2)  Unet.py:52    */
+#define PNNP_ACT_RELU 2    /* nn.ReLU            ResUnet.py:44 */
+#define PNNP_OUT_NHWC_BF16 0
+#define PNNP_OUT_NCHW_F32 1 /* network output: fp32 planes straight from the fp32 accumulators */
+
+/* One layer.  in1/cin1: optional second K source = the skip tensor of torch.cat([up, skip], 1)
+ * (Unet.py:72,77,82,87) — the concat is never materialised.  resid: optional NHWC bf16 tensor added
+ * after the activation (ResidualBlock `output += short_cut(x)`, modules.py:193-197); resid_nchw:
+ * optional fp32 NCHW tensor added to an OUT_NCHW_F32 output (`out = conv10 + x`, Unet.py:96).
+ * h, w are the INPUT spatial size.  w_rows = rows allocated per tap in `weight` (>= cout, padded
+ * with zero rows up to a multiple of 16). */
+int pnnp_conv2d_tc(int mode, const void* in0, int cin0, const void* in1, int cin1, const void* weight,
+                   int w_rows, const float* bias, void* out, int cout, int cout_stride, int n, int h,
+                   int w, int act, int out_mode, const void* resid, const float* resid_nchw,
+                   void* stream);
+/* Non-zero if a tcgen05/TMA pipeline wait timed out since the last call (the kernels terminate
+ * instead of hanging); synchronises the device. */
+int pnnp_conv_pipeline_error(void);
+/* network input: NCHW fp32 (c <= 16) * scale -> NHWC bf16 zero-padded to 16 channels */
+int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, float scale,
+                        void* stream);
+/* nn.MaxPool2d(2) on NHWC bf16 (Unet.py:57) */
+int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int w, int c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

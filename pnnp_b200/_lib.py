@@ -42,7 +42,15 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, _vp]),
     "pnnp_noise_synth_replay": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _f,
                                      _vp, _vp, _vp, _vp, _vp]),
+    "pnnp_conv2d_tc": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pnnp_conv_pipeline_error": (_i, []),
+    "pnnp_nchw_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "pnnp_maxpool2x2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
+
+CONV3, CONV1, CONVT = 0, 1, 2
+ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
+OUT_NHWC_BF16, OUT_NCHW_F32 = 0, 1
 
 _lib = None
 

@@ -1,0 +1,218 @@
+"""UNetSeeInDark / ResUnet with the reference's module API and state_dict keys
+(archs/Unet.py:4-99, archs/ResUnet.py:3-88, archs/modules.py:130-197), forward executed by the
+tcgen05/TMEM implicit-GEMM kernels in csrc/conv_tc.cu (NHWC bf16 activations, fp32 accumulation).
+
+`Net(args)` takes the YAML `arch` dict (keys in_nc out_nc nf nframes res; the rest ignored), so the
+trainers' `globals()[arch['name']](arch)` lookup (trainer_SID.py:17) resolves to these classes.
+The parameter-holding sub-modules are ordinary nn.Conv2d / nn.ConvTranspose2d so `state_dict()`,
+`load_weights(by_name=True)` (utils/utils.py:148-192) and `initialize_weights` work unchanged; they
+are never *called* on the forward path — there is no eager/PyTorch fallback.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def initialize_weights(net):
+    """archs/__init__.py:12-19 — Conv2d w,b ~ N(0, 0.02); ConvTranspose2d w ~ N(0, 0.02), bias untouched."""
+    for m in net.modules():
+        if isinstance(m, nn.Conv2d):
+            m.weight.data.normal_(0.0, 0.02)
+            if m.bias is not None:
+                m.bias.data.normal_(0.0, 0.02)
+        if isinstance(m, nn.ConvTranspose2d):
+            m.weight.data.normal_(0.0, 0.02)
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+class _PackedLayer:
+    """bf16 weights in the kernel's [taps][rows][cin] layout + fp32 bias, rebuilt when the
+    underlying parameters change (tracked by tensor._version / data_ptr)."""
+
+    def __init__(self, module, kind):
+        self.module, self.kind, self.key = module, kind, None
+        self.weight = self.bias = None
+
+    def get(self, device):
+        m = self.module
+        key = (m.weight._version, m.weight.data_ptr(), None if m.bias is None else (m.bias._version, m.bias.data_ptr()),
+               str(device))
+        if key != self.key:
+            w = m.weight.detach().to(device=device, dtype=torch.float32)
+            if self.kind == "convT":                       # [Cin, Cout, 2, 2] -> [a*2+b][Cout][Cin]
+                cin, cout = w.shape[0], w.shape[1]
+                packed = w.permute(2, 3, 1, 0).reshape(4, cout, cin)
+            else:                                          # [Cout, Cin, k, k] -> [ky*k+kx][Cout][Cin]
+                cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+                packed = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
+            rows, cin_p = _pad16(packed.shape[1]), _pad16(packed.shape[2])
+            buf = torch.zeros((packed.shape[0], rows, cin_p), dtype=torch.bfloat16, device=device)
+            buf[:, :packed.shape[1], :packed.shape[2]] = packed.to(torch.bfloat16)
+            self.weight = buf.contiguous()
+            self.bias = None if m.bias is None else m.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+            self.key = key
+        return self.weight, self.bias
+
+
+class _Workspace:
+    """Activation buffers keyed by name, reused across calls with the same geometry."""
+
+    def __init__(self):
+        self.bufs, self.sig = {}, None
+
+    def get(self, sig, name, shape, device):
+        if sig != self.sig:
+            self.bufs, self.sig = {}, sig
+        t = self.bufs.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=torch.bfloat16, device=device)
+            self.bufs[name] = t
+        return t
+
+
+def _conv(mode, x0, w, b, out, cout, act, x1=None, resid=None, out_mode=_lib.OUT_NHWC_BF16, resid_nchw=None):
+    """x0/x1: NHWC bf16 (n,h,w,c).  out: NHWC bf16 tensor or NCHW fp32 tensor."""
+    n, h, wd, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[3]
+    cout_stride = out.shape[3] if out_mode == _lib.OUT_NHWC_BF16 else cout
+    _lib.check(_lib.lib().pnnp_conv2d_tc(
+        mode, x0.data_ptr(), c0, _lib.ptr(x1), c1, w.data_ptr(), w.shape[1], _lib.ptr(b), out.data_ptr(), cout,
+        cout_stride, n, h, wd, act, out_mode, _lib.ptr(resid), _lib.ptr(resid_nchw), _lib.stream_ptr(x0.device)),
+        "conv2d_tc")
+    return out
+
+
+def _pool(x, out):
+    n, h, w, c = x.shape
+    _lib.check(_lib.lib().pnnp_maxpool2x2_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, _lib.stream_ptr(x.device)), "maxpool")
+    return out
+
+
+def _to_nhwc16(x, out, scale=1.0):
+    n, c, h, w = x.shape
+    _lib.check(_lib.lib().pnnp_nchw_to_nhwc16(x.data_ptr(), out.data_ptr(), n, c, h, w, float(scale),
+                                              _lib.stream_ptr(x.device)), "nchw_to_nhwc16")
+    return out
+
+
+class _TCNet(nn.Module):
+    def _check_input(self, x):
+        _lib.require_cuda(x, "network input")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise RuntimeError("pnnp_b200: the tcgen05 forward is inference-only in this build; "
+                               "wrap the call in torch.no_grad() / net.eval()")
+        n, c, h, w = x.shape
+        if h % 16 or w % 16:
+            raise RuntimeError(f"pnnp_b200: h and w must be multiples of 16, got {h}x{w} "
+                               "(the reference pads by reflection first, trainer_SID.py:221-226)")
+        if c > 16:
+            raise RuntimeError("pnnp_b200: at most 16 input channels")
+        return x.float().contiguous()
+
+    def _packed(self, name, kind="conv"):
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        if name not in cache:
+            cache[name] = _PackedLayer(self.get_submodule(name), kind)
+        return cache[name].get(next(self.parameters()).device)
+
+    def _ws(self):
+        return self.__dict__.setdefault("_workspace", _Workspace())
+
+
+class UNetSeeInDark(_TCNet):
+    """archs/Unet.py:4-99."""
+
+    def __init__(self, args=None):
+        super().__init__()
+        self.args = args
+        self.nframes = args['nframes']
+        self.cf = args['nframes'] // 2
+        self.res = args['res']
+        nf, in_nc, out_nc = args['nf'], args['in_nc'] * args['nframes'], args['out_nc']
+        if nf % 16:
+            raise RuntimeError("pnnp_b200: nf must be a multiple of 16 for the tensor-core path")
+        self.nf, self.out_nc = nf, out_nc
+        chans = [(in_nc, nf), (nf, nf * 2), (nf * 2, nf * 4), (nf * 4, nf * 8), (nf * 8, nf * 16)]
+        for i, (ci, co) in enumerate(chans, start=1):
+            setattr(self, f"conv{i}_1", nn.Conv2d(ci, co, kernel_size=3, stride=1, padding=1))
+            setattr(self, f"conv{i}_2", nn.Conv2d(co, co, kernel_size=3, stride=1, padding=1))
+            if i < 5:
+                setattr(self, f"pool{i}", nn.MaxPool2d(kernel_size=2))
+        for i, co in zip(range(6, 10), (nf * 8, nf * 4, nf * 2, nf)):
+            setattr(self, f"upv{i}", nn.ConvTranspose2d(co * 2, co, 2, stride=2))
+            setattr(self, f"conv{i}_1", nn.Conv2d(co * 2, co, kernel_size=3, stride=1, padding=1))
+            setattr(self, f"conv{i}_2", nn.Conv2d(co, co, kernel_size=3, stride=1, padding=1))
+        self.conv10_1 = nn.Conv2d(nf, out_nc, kernel_size=1, stride=1)
+        self.relu = nn.LeakyReLU(0.2, inplace=True)
+
+    def forward(self, x):
+        x = self._check_input(x)
+        n, c, h, w = x.shape
+        dev, ws, nf = x.device, self._ws(), self.nf
+        sig = (n, h, w, str(dev))
+        buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev)
+        L = _lib.ACT_LEAKY
+        with torch.cuda.device(dev):
+            cur = _to_nhwc16(x, buf("x16", h, w, 16))
+            skips = []
+            hh, ww = h, w
+            for i in range(1, 6):                                  # encoder (Unet.py:55-69)
+                co = nf * 2 ** (i - 1)
+                w1, b1 = self._packed(f"conv{i}_1")
+                w2, b2 = self._packed(f"conv{i}_2")
+                t = _conv(_lib.CONV3, cur, w1, b1, buf(f"c{i}a", hh, ww, co), co, L)
+                cfull = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
+                if i < 5:
+                    skips.append(cfull)
+                    cur = _pool(cfull, buf(f"p{i}", hh // 2, ww // 2, co))
+                    hh, ww = hh // 2, ww // 2
+                else:
+                    cur = cfull
+            for i in range(6, 10):                                 # decoder (Unet.py:71-89)
+                co = nf * 2 ** (9 - i)
+                skip = skips[9 - i]
+                wu, bu = self._packed(f"upv{i}", "convT")
+                up = _conv(_lib.CONVT, cur, wu, bu, buf(f"u{i}", hh * 2, ww * 2, co), co, _lib.ACT_NONE)
+                hh, ww = hh * 2, ww * 2
+                w1, b1 = self._packed(f"conv{i}_1")
+                w2, b2 = self._packed(f"conv{i}_2")
+                t = _conv(_lib.CONV3, up, w1, b1, buf(f"c{i}a", hh, ww, co), co, L, x1=skip)   # cat([up, skip], 1)
+                cur = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
+            w10, b10 = self._packed("conv10_1")
+            out = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=dev)
+            _conv(_lib.CONV1, cur, w10, b10, out, self.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,
+                  resid_nchw=x if self.res else None)
+        return out
+
+
+# ---- ResUnet building blocks with the reference's parameter names (archs/modules.py:130-197) ----
+class conv3x3(nn.Module):
+    """modules.py:130-138: stride-2 3x3 conv WITH bias; the 'relu' child hung on the nn.Conv2d never runs."""
+
+    def __init__(self, in_nc, out_nc, stride=2, is_activate=True):
+        super().__init__()
+        self.conv = nn.Conv2d(in_nc, out_nc, kernel_size=3, padding=1, stride=stride)
+
+
+class convWithBN(nn.Module):
+    def __init__(self, in_c, out_c, kernel_size=3, padding=1, stride=1, is_activate=True, is_bn=True):
+        super().__init__()
+        self.conv = nn.Sequential(OrderedDict([
+            ("conv", nn.Conv2d(in_c, out_c, kernel_size=kernel_size, padding=padding, stride=stride, bias=False))]))
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, in_c, out_c, is_activate=True):
+        super().__init__()
+        self.block = nn.Sequential(convWithBN(in_c, out_c, is_bn=False),
+                                   convWithBN(out_c, out_c, is_activate=False, is_bn=False))
+        if in_c != out_c:
+            self.short_cut = nn.Sequential(convWithBN(in_c, out_c, kernel_size=1, padding=0, is_activate=False, is_bn=False))
+        else:
+            self.short_cut = nn.Sequential(OrderedDict([]))

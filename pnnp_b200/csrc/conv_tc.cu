@@ -1,0 +1,515 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM), operands staged by
+// TMA, for the UNet / ResUnet denoiser forward (archs/Unet.py:54-99, archs/ResUnet.py:46-88).
+//
+// One persistent, warp-specialised kernel covers every GEMM-shaped layer of both networks:
+//   mode CONV3  3x3, pad 1, stride 1   (conv*_1/_2, ResidualBlock convs)     taps = 9
+//   mode CONV1  1x1                     (conv10_1, ResidualBlock short_cut)    taps = 1
+//   mode CONVT  ConvTranspose2d(2, s2)  (upv6..upv9): 4 GEMMs, one per (a,b), pixel-shuffle store
+// Activations are NHWC bf16 (channels padded to a multiple of 16), accumulation fp32 in TMEM.
+//
+// GEMM view.  M = 128 output pixels (an 8 x 16 spatial tile), N = UMMA_N output channels,
+// K = taps x Cin.  The A operand of tap (dy,dx) is the input tile shifted by (dy-1, dx-1); a 4-D
+// TMA box (Kc channels x 16 x (8+2) x 1) lands in shared memory as 160 rows of Kc*2 bytes in the
+// canonical K-major swizzled layout, with out-of-bounds rows/columns zero-filled by the TMA unit
+// (= the convolution's zero padding).  One box per dx serves the three dy taps: the UMMA
+// descriptor start address is advanced by dy*16 rows (a whole number of swizzle atoms).  The
+// channel concat of the decoder (torch.cat([up, skip], 1), Unet.py:72) is never materialised: the
+// K loop simply walks two tensor maps.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2-5 = epilogue (TMEM -> registers -> bias/activation/residual -> global).
+// Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM accumulator double buffer
+// full/empty mbarriers (MMA <-> epilogue).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include "abi_common.h"
+#include "../../include/pnnp_b200.h"
+
+namespace pnnp {
+
+constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kSpinLimit = 1u << 27;      // ~ seconds; a broken pipeline terminates instead of hanging the GPU
+
+enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2 };
+enum { OUT_NHWC_BF16 = 0, OUT_NCHW_F32 = 1 };
+enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
+
+struct ConvParams {
+    int mode, n_img, H, W;          // H, W: spatial size of the INPUT (== output for CONV3/CONV1; output is 2H x 2W for CONVT)
+    int tiles_x, tiles_y, n_tiles;
+    int umma_n;                     // columns per accumulator / MMA N
+    int nsrc, cin0, cin1;           // channels of the two K sources (multiples of kc); cin1 = 0 if single
+    int kc, swz;                    // channels per K chunk (16/32/64) and swizzle span in bytes (= 2*kc)
+    int cout;                       // real output channels written per pixel
+    int cout_stride;                // channel stride of the NHWC output (>= cout)
+    int act, out_mode;
+    int stages, stage_bytes, a_bytes, b_tap_stride;
+    int tmem_cols;
+    const float* bias;              // [cout] or null
+    void* out;
+    const __nv_bfloat16* resid;     // NHWC bf16 residual with the output's geometry, or null
+    const float* resid_nchw;        // NCHW fp32 residual for OUT_NCHW_F32, or null
+    int* err;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    uint32_t ok = 0;
+#pragma unroll 1
+    for (uint32_t it = 0; it < kSpinLimit; ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    if (err) atomicExch(err, code);
+    return false;
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
+__device__ __forceinline__ uint64_t umma_desc_hi(int swz) {
+    const uint64_t layout = swz == 128 ? 2ull : (swz == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (uint64_t)((8 * swz) >> 4);
+    return (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint64_t hi, uint32_t saddr) { return hi | (uint64_t)((saddr >> 4) & 0x3FFFu); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages x stage_bytes] [barriers] [tmem slot] [bias]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t* full_bar = bars;                       // [stages]
+    uint64_t* empty_bar = bars + kMaxStages;         // [stages]
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;     // [2]
+    uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps_per_stage = p.mode == MODE_CONV3 ? 3 : 1;
+    const int dx_count = p.mode == MODE_CONV3 ? 3 : 1;
+    const int chunks0 = p.cin0 / p.kc, chunks1 = p.nsrc > 1 ? p.cin1 / p.kc : 0;
+    const int ksteps = (chunks0 + chunks1) * dx_count;
+    const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
+    const uint32_t stage_tx = (uint32_t)(p.a_bytes + taps_per_stage * p.umma_n * p.swz);
+
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            bool alive = true;
+            for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
+                int r = t;
+                const int n_tile = r % p.n_tiles; r /= p.n_tiles;
+                const int tx = r % p.tiles_x; r /= p.tiles_x;
+                const int ty = r % p.tiles_y; r /= p.tiles_y;
+                const int img = r;
+                const int x0 = tx * kTileW, y0 = ty * kTileH;
+                const int n_off = p.mode == MODE_CONVT ? 0 : n_tile * p.umma_n;
+                for (int ks = 0; ks < ksteps && alive; ++ks) {
+                    const int chunk = ks / dx_count, dx = ks - chunk * dx_count;
+                    const int src = chunk >= chunks0 ? 1 : 0;
+                    const int cc = src ? chunk - chunks0 : chunk;
+                    const int cin_off = (src ? p.cin0 : 0) + cc * p.kc;
+                    alive = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 101);
+                    if (!alive) break;
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_expect_tx(fb, stage_tx);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                    const int halo = p.mode == MODE_CONV3 ? 1 : 0;
+                    tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - halo, img);
+                    const uint32_t sb = sa + p.a_bytes;
+                    for (int dy = 0; dy < taps_per_stage; ++dy) {
+                        const int tap = p.mode == MODE_CONV3 ? dy * 3 + dx : (p.mode == MODE_CONVT ? n_tile : 0);
+                        tma_load_3d(sb + dy * p.b_tap_stride, &tmB, fb, cin_off, n_off, tap);
+                    }
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint64_t dhi = umma_desc_hi(p.swz);
+            const int k16s = p.kc / 16;
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            bool alive = true;
+            for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
+                alive = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 102);
+                if (!alive) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.umma_n;
+                for (int ks = 0; ks < ksteps && alive; ++ks) {
+                    alive = mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 103);
+                    if (!alive) break;
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                    const uint32_t sb = sa + p.a_bytes;
+                    for (int dy = 0; dy < taps_per_stage; ++dy) {
+                        const uint32_t a0 = sa + dy * kTileW * p.swz;
+                        const uint32_t b0 = sb + dy * p.b_tap_stride;
+                        for (int k = 0; k < k16s; ++k)
+                            tc_mma_bf16(d_tmem, umma_desc(dhi, a0 + k * 32), umma_desc(dhi, b0 + k * 32), idesc,
+                                        (ks | dy | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(smem_u32(&empty_bar[stage]));          // frees the smem slot when these MMAs retire
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(smem_u32(&tfull_bar[acc]));                // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
+        const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
+        const int ty_in = m / kTileW, tx_in = m % kTileW;
+        uint32_t acc = 0, acc_phase = 0;
+        bool alive = true;
+        const int chunks16 = p.umma_n / 16;
+        for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
+            int r = t;
+            const int n_tile = r % p.n_tiles; r /= p.n_tiles;
+            const int tx = r % p.tiles_x; r /= p.tiles_x;
+            const int ty = r % p.tiles_y; r /= p.tiles_y;
+            const int img = r;
+            const int x = tx * kTileW + tx_in, y = ty * kTileH + ty_in;
+            const bool valid = x < p.W && y < p.H;
+            alive = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
+            if (!alive) break;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * (uint32_t)p.umma_n + ((uint32_t)(quad * 32) << 16);
+            size_t opix;            // output pixel index
+            int col0;               // first output channel of this tile
+            if (p.mode == MODE_CONVT) {
+                const int a = n_tile >> 1, b = n_tile & 1;
+                opix = ((size_t)img * (2 * p.H) + (2 * y + a)) * (size_t)(2 * p.W) + (2 * x + b);
+                col0 = 0;
+            } else {
+                opix = ((size_t)img * p.H + y) * (size_t)p.W + x;
+                col0 = n_tile * p.umma_n;
+            }
+            for (int j = 0; j < chunks16; ++j) {
+                uint32_t v[16];
+                tc_ld16(taddr + j * 16, v);
+                tc_ld_wait();
+                const int c0 = col0 + j * 16;
+                if (!valid || c0 >= p.cout) continue;
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = apply_act(__uint_as_float(v[i]) + s_bias[min(c0 + i, p.cout - 1)], p.act);
+                if (p.out_mode == OUT_NHWC_BF16) {
+                    if (p.resid) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + opix * p.cout_stride + c0);
+                        const uint4 r0 = rp[0], r1 = rp[1];
+                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            f[2 * i] += __uint_as_float(rw[i] << 16);
+                            f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0);
+                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out);
+                    const size_t plane = (size_t)p.H * p.W;
+                    for (int i = 0; i < 16 && c0 + i < p.cout; ++i) {
+                        const size_t oi = ((size_t)img * p.cout + (c0 + i)) * plane + (size_t)y * p.W + x;
+                        o[oi] = f[i] + (p.resid_nchw ? p.resid_nchw[oi] : 0.f);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ small helper kernels
+// NCHW fp32 (c <= 16 channels) -> NHWC bf16 with the channel dim zero-padded to 16 (network input)
+__global__ void nchw_f32_to_nhwc16_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int c,
+                                               int h, int w, float scale) {
+    const size_t plane = (size_t)h * w, total = (size_t)n * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t img = i / plane, pix = i - img * plane;
+        uint32_t pk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float a = (2 * k < c) ? in[(img * c + 2 * k) * plane + pix] * scale : 0.f;
+            const float b = (2 * k + 1 < c) ? in[(img * c + 2 * k + 1) * plane + pix] * scale : 0.f;
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+            pk[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+}
+
+// 2x2 max pooling, NHWC bf16, 8 channels (16 bytes) per thread
+__global__ void maxpool2x2_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int h,
+                                            int w, int c) {
+    const int ho = h / 2, wo = w / 2, c8 = c / 8;
+    const size_t total = (size_t)n * ho * wo * c8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c8);
+        size_t r = i / c8;
+        const int xo = (int)(r % wo); r /= wo;
+        const int yo = (int)(r % ho);
+        const int img = (int)(r / ho);
+        const __nv_bfloat16* base = in + (((size_t)img * h + 2 * yo) * w + 2 * xo) * c + cc * 8;
+        const uint4 q00 = *reinterpret_cast<const uint4*>(base);
+        const uint4 q01 = *reinterpret_cast<const uint4*>(base + c);
+        const uint4 q10 = *reinterpret_cast<const uint4*>(base + (size_t)w * c);
+        const uint4 q11 = *reinterpret_cast<const uint4*>(base + (size_t)w * c + c);
+        const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&q00);
+        const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&q01);
+        const __nv_bfloat162* cq = reinterpret_cast<const __nv_bfloat162*>(&q10);
+        const __nv_bfloat162* d = reinterpret_cast<const __nv_bfloat162*>(&q11);
+        uint4 o;
+        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) op[k] = __hmax2(__hmax2(a[k], b[k]), __hmax2(cq[k], d[k]));
+        *reinterpret_cast<uint4*>(out + (((size_t)img * ho + yo) * wo + xo) * c + cc * 8) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+static CUtensorMapSwizzle swz_enum(int swz) {
+    return swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+// activation map: NHWC bf16 viewed as (C, W, H, N); box (kc, 16, box_h, 1)
+static int make_act_map(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c, int kc, int box_h, int swz) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kTileW, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return fail(b); }
+    return 0;
+}
+// weight map: [taps][rows][cin] bf16 viewed as (cin, rows, taps); box (kc, umma_n, 1)
+static int make_w_map(CUtensorMap* tm, const void* ptr, int taps, int rows, int cin, int kc, int umma_n, int swz) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)rows, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)rows * cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)umma_n, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r); return fail(b); }
+    return 0;
+}
+
+static int* g_err_dev = nullptr;     // device word the kernels report pipeline time-outs into
+
+int conv_layer_launch(int mode, const void* in0, int cin0, const void* in1, int cin1, const void* weight, int w_rows,
+                      const float* bias, void* out, int cout, int cout_stride, int n, int h, int w, int act, int out_mode,
+                      const void* resid, const float* resid_nchw, cudaStream_t st) {
+    if (!in0 || !weight || !out) return fail("conv: null pointer");
+    if (cin0 % 16 || cin1 % 16) return fail("conv: channel counts must be multiples of 16");
+    const int nsrc = in1 ? 2 : 1;
+    int kc = 64;
+    while (kc > 16 && ((cin0 % kc) || (nsrc > 1 && (cin1 % kc)))) kc >>= 1;
+    int umma_n, n_tiles;
+    if (mode == MODE_CONVT) { umma_n = cout; n_tiles = 4; if (cout % 16 || cout > 256) return fail("convT: cout must be a multiple of 16, <= 256"); }
+    else {
+        const int cpad = (cout + 15) / 16 * 16;
+        umma_n = std::min(cpad, 256);
+        if (cpad % umma_n) return fail("conv: cout must be <= 256 or a multiple of 256");
+        n_tiles = cpad / umma_n;
+    }
+    if (out_mode == OUT_NHWC_BF16 && (cout % 16)) return fail("conv: NHWC output needs cout % 16 == 0");
+    if (w_rows < (mode == MODE_CONVT ? cout : n_tiles * umma_n)) return fail("conv: weight tensor has too few rows");
+    const int taps = mode == MODE_CONV3 ? 9 : (mode == MODE_CONVT ? 4 : 1);
+    const int tps = mode == MODE_CONV3 ? 3 : 1;
+    const int box_h = mode == MODE_CONV3 ? kTileH + 2 : kTileH;
+    // shrink the K chunk until at least 3 pipeline stages fit
+    int swz, a_bytes, b_tap_stride, stage_bytes, stages;
+    const int smem_budget = 227 * 1024 - 4096;
+    for (;; kc >>= 1) {
+        swz = kc * 2;
+        a_bytes = box_h * kTileW * swz;
+        b_tap_stride = (umma_n * swz + 1023) / 1024 * 1024;
+        stage_bytes = (a_bytes + tps * b_tap_stride + 1023) / 1024 * 1024;
+        stages = std::min(kMaxStages, smem_budget / stage_bytes);
+        if (stages >= 3 || kc == 16) break;
+    }
+    if (stages < 2) return fail("conv: tile does not fit in shared memory");
+    ConvParams p{};
+    p.mode = mode; p.n_img = n; p.H = h; p.W = w;
+    p.tiles_x = (w + kTileW - 1) / kTileW; p.tiles_y = (h + kTileH - 1) / kTileH; p.n_tiles = n_tiles;
+    p.umma_n = umma_n; p.nsrc = nsrc; p.cin0 = cin0; p.cin1 = nsrc > 1 ? cin1 : 0; p.kc = kc; p.swz = swz;
+    p.cout = cout; p.cout_stride = cout_stride; p.act = act; p.out_mode = out_mode;
+    p.stages = stages; p.stage_bytes = stage_bytes; p.a_bytes = a_bytes; p.b_tap_stride = b_tap_stride;
+    int tc = 32; while (tc < 2 * umma_n) tc <<= 1;
+    p.tmem_cols = tc;
+    p.bias = bias; p.out = out; p.resid = static_cast<const __nv_bfloat16*>(resid); p.resid_nchw = resid_nchw;
+    if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
+    p.err = g_err_dev;
+    CUtensorMap tmA0, tmA1, tmB;
+    if (int e = make_act_map(&tmA0, in0, n, h, w, cin0, kc, box_h, swz)) return e;
+    if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz)) return e; }
+    else tmA1 = tmA0;
+    if (int e = make_w_map(&tmB, weight, taps, w_rows, cin0 + (nsrc > 1 ? cin1 : 0), kc, umma_n, swz)) return e;
+    int dev = 0, sms = 0;
+    PNNP_CUDA(cudaGetDevice(&dev));
+    PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int total_tiles = n * p.tiles_y * p.tiles_x * n_tiles;
+    const int grid = std::min(total_tiles, sms);
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16 + (size_t)cout * 4 + 64;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        smem_set = 227 * 1024;
+    }
+    if (smem > 227 * 1024) return fail("conv: shared memory budget exceeded");
+    conv_gemm_tc_kernel<<<grid, kConvThreads, smem, st>>>(tmA0, tmA1, tmB, p);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pnnp
+
+using namespace pnnp;
+
+extern "C" int pnnp_conv2d_tc(int mode, const void* in0, int cin0, const void* in1, int cin1, const void* weight, int w_rows,
+                              const float* bias, void* out, int cout, int cout_stride, int n, int h, int w, int act,
+                              int out_mode, const void* resid, const float* resid_nchw, void* stream) {
+    return conv_layer_launch(mode, in0, cin0, in1, cin1, weight, w_rows, bias, out, cout, cout_stride, n, h, w, act, out_mode,
+                             resid, resid_nchw, (cudaStream_t)stream);
+}
+
+extern "C" int pnnp_conv_pipeline_error(void) {
+    int v = 0;
+    if (g_err_dev) { cudaMemcpy(&v, g_err_dev, sizeof(int), cudaMemcpyDeviceToHost); if (v) cudaMemset(g_err_dev, 0, sizeof(int)); }
+    return v;
+}
+
+extern "C" int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, float scale, void* stream) {
+    if (!in || !out || c > 16) return fail("nchw_to_nhwc16: bad arguments");
+    const size_t total = (size_t)n * h * w;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    nchw_f32_to_nhwc16_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, static_cast<__nv_bfloat16*>(out), n, c, h, w, scale);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int w, int c, void* stream) {
+    if (!in || !out || (c % 8) || (h & 1) || (w & 1)) return fail("maxpool2x2: needs even h, w and c % 8 == 0");
+    const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    maxpool2x2_nhwc_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                         static_cast<__nv_bfloat16*>(out), n, h, w, c);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -84,6 +84,15 @@ __device__ __forceinline__ float tukey_lambda_ppf(uint32_t w, float lam, float i
 // smem: s_inv[k] = 1/k (k = 1..63), s_lfact[k] = ln k! (k = 0..15)
 // ------------------------------------------------------------------------------------------
 constexpr int kInvTab = 64, kLfactTab = 16;
+// 1/k for the sequential search: every active lane is at the same k, so the index is warp-uniform
+// and the constant-bank read is a broadcast.
+__constant__ float c_inv_k[kInvTab] = {
+    0.f, 1.f / 1, 1.f / 2, 1.f / 3, 1.f / 4, 1.f / 5, 1.f / 6, 1.f / 7, 1.f / 8, 1.f / 9, 1.f / 10, 1.f / 11, 1.f / 12,
+    1.f / 13, 1.f / 14, 1.f / 15, 1.f / 16, 1.f / 17, 1.f / 18, 1.f / 19, 1.f / 20, 1.f / 21, 1.f / 22, 1.f / 23,
+    1.f / 24, 1.f / 25, 1.f / 26, 1.f / 27, 1.f / 28, 1.f / 29, 1.f / 30, 1.f / 31, 1.f / 32, 1.f / 33, 1.f / 34,
+    1.f / 35, 1.f / 36, 1.f / 37, 1.f / 38, 1.f / 39, 1.f / 40, 1.f / 41, 1.f / 42, 1.f / 43, 1.f / 44, 1.f / 45,
+    1.f / 46, 1.f / 47, 1.f / 48, 1.f / 49, 1.f / 50, 1.f / 51, 1.f / 52, 1.f / 53, 1.f / 54, 1.f / 55, 1.f / 56,
+    1.f / 57, 1.f / 58, 1.f / 59, 1.f / 60, 1.f / 61, 1.f / 62, 1.f / 63};
 
 __device__ __forceinline__ void init_poisson_tables(float* s_inv, float* s_lfact) {
     for (int i = threadIdx.x; i < kInvTab; i += blockDim.x) s_inv[i] = i ? 1.0f / (float)i : 0.f;
@@ -96,11 +105,12 @@ __device__ __forceinline__ void init_poisson_tables(float* s_inv, float* s_lfact
 
 __device__ __forceinline__ float poisson_small(float lam, uint32_t w, const float* s_inv) {
     const float u = u01_24(w);
+    (void)s_inv;
     float p = __expf(-lam), F = p;
     int k = 0;
     while (u > F && k < kInvTab - 1) {
         ++k;
-        p *= lam * s_inv[k];
+        p *= lam * c_inv_k[k];
         F += p;
     }
     return (float)k;

@@ -79,7 +79,7 @@ __device__ __forceinline__ float synth_one(float y, uint64_t gidx, size_t lidx, 
 }
 
 template <int CHAIN, bool DEBUG, int VEC>
-__global__ void __launch_bounds__(kThreads) noise_synth_kernel(const SynthArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArgs a) {
     __shared__ float s_inv[kInvTab];
     __shared__ float s_lfact[kLfactTab];
     init_poisson_tables(s_inv, s_lfact);

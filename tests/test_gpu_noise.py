@@ -208,34 +208,37 @@ def test_gaussian_read_row_and_quant_stage_ks():
     _, d = P.synthesize_batch(y[:1], [p], "g", generator=P.PhiloxGenerator(9), debug=True)
     assert stats.kstest(d["shot"].cpu().numpy().reshape(-1).astype(np.float64), "norm").pvalue > 1e-3
     # independence of the four streams of one element block
-    c = np.corrcoef(np.stack([read, q, d["read"].cpu().numpy().reshape(-1)[: read.size]]))
-    assert np.abs(c - np.eye(3)).max() < 0.01
+    c = np.corrcoef(np.stack([read, q]))
+    assert np.abs(c - np.eye(2)).max() < 0.01
 
 
 def test_row_noise_is_constant_along_width_and_differs_across_rows():
     y = torch.zeros((2, 4, 64, 2128), device="cuda")      # 5 segments per row: same draw in each
-    p = _flat_param(1.0, sigR=4.0)
-    p["sigTL"] = np.float64(0.0)
-    out = P.synthesize_batch(y, [p, p], "gr", generator=P.PhiloxGenerator(2), ori=True)
+    p = _flat_param(1.0, sigR=4.0, sigGs=0.0)       # Poisson(0) = 0 and N(0, 0) = 0: only the row term is left
+    out = P.synthesize_batch(y, [p, p], "pr", generator=P.PhiloxGenerator(2), ori=True)
     o = out.cpu().numpy()
     assert np.all(o == o[..., :1]) and len(np.unique(o[..., 0])) == 2 * 4 * 64
 
 
 def test_end_to_end_matches_reference_statistics():
-    """Whole-function KS: product generate_noisy_obs vs the oracle's reference-order sampling."""
+    """Whole-function two-sample KS: product generate_noisy_obs vs the oracle's reference-order
+    sampling.  The pooled-residual KS uses 'pgq' (i.i.d. per pixel); with 'r' every pixel of a row
+    shares one draw, so pooled residuals are not independent and only moments are compared."""
     rs = np.random.RandomState(4)
     y = (rs.rand(4, 256, 256).astype(np.float32) ** 2)
     np.random.seed(9)
     p = O.sample_params("SonyA7S2")
-    np.random.seed(10)
-    want = O.generate_noisy_obs(y, param=p, noise_code="pgrq")
-    P.manual_seed(77)
-    got = P.generate_noisy_obs(y, param=p, noise_code="pgrq")
-    assert got.dtype == np.float32 and got.shape == want.shape
-    res_w, res_g = (want - y).reshape(-1), (got - y).reshape(-1)
-    assert stats.ks_2samp(res_w, res_g).pvalue > 1e-3
-    assert abs(res_g.mean() - res_w.mean()) < 4 * res_w.std() / np.sqrt(res_w.size) * 2
-    assert abs(res_g.std() / res_w.std() - 1) < 0.02
+    for code, do_ks in (("pgq", True), ("pgrq", False)):
+        np.random.seed(10)
+        want = O.generate_noisy_obs(y, param=p, noise_code=code)
+        P.manual_seed(77)
+        got = P.generate_noisy_obs(y, param=p, noise_code=code)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        res_w, res_g = (want - y).reshape(-1), (got - y).reshape(-1)
+        if do_ks:
+            assert stats.ks_2samp(res_w, res_g).pvalue > 1e-3
+            assert abs(res_g.mean() - res_w.mean()) < 8 * res_w.std() / np.sqrt(res_w.size)
+        assert abs(res_g.std() / res_w.std() - 1) < 0.02
     lo = -p["bl"] / p["wp"] * p["ratio"]
     assert got.min() >= np.float32(lo) - 1e-6
 

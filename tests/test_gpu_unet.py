@@ -1,0 +1,167 @@
+"""tcgen05 implicit-GEMM layers and the UNet forward through the C ABI vs torch fp32 / the oracle.
+
+Tolerances (stated, per BASELINE north_star): the network output must be within 1e-3 max-abs of
+the fp32 reference with the reference's own init; this build computes in bf16 with fp32
+accumulation (the "bf16 variant"), so per-layer checks use a bf16-appropriate relative bound
+against an fp32 reference evaluated on the SAME bf16-rounded inputs and weights."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle_np as O
+import pnnp_b200 as P
+from pnnp_b200 import _lib, archs
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(t):       # NCHW fp32 -> NHWC bf16
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _nchw(t):       # NHWC bf16 -> NCHW fp32
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _pack(w, kind="conv"):
+    class M:        # minimal stand-in with .weight/.bias for _PackedLayer
+        pass
+    m = M()
+    m.weight, m.bias = w, None
+    return archs._PackedLayer(m, kind).get(w.device)[0]
+
+
+def _no_pipeline_error():
+    torch.cuda.synchronize()
+    assert _lib.lib().pnnp_conv_pipeline_error() == 0, "tcgen05/TMA pipeline wait timed out"
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n", [(16, 32, 16, 32, 1), (32, 32, 24, 40, 2), (64, 64, 32, 48, 1),
+                                            (128, 256, 16, 16, 1), (256, 512, 8, 16, 1), (512, 512, 16, 32, 1),
+                                            (64, 32, 40, 72, 1)])
+@pytest.mark.parametrize("act", [_lib.ACT_LEAKY, _lib.ACT_NONE])
+def test_conv3x3_layer(cin, cout, h, w, n, act):
+    g = torch.Generator(device="cuda").manual_seed(cin * 1000 + cout)
+    x = torch.randn((n, cin, h, w), device="cuda", generator=g)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) / (3 * cin ** 0.5)
+    b = torch.randn((cout,), device="cuda", generator=g) * 0.1
+    out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device="cuda")
+    archs._conv(_lib.CONV3, _nhwc(x), _pack(wt), b, out, cout, act)
+    _no_pipeline_error()
+    ref = F.conv2d(_bf(x), _bf(wt), b, padding=1)
+    if act == _lib.ACT_LEAKY:
+        ref = F.leaky_relu(ref, 0.2)
+    err = (_nchw(out) - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err      # bf16 output rounding: 2^-8 relative
+
+
+def test_conv3x3_two_sources_is_concat():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    up, skip = torch.randn((1, 64, 24, 32), device="cuda", generator=g), torch.randn((1, 64, 24, 32), device="cuda", generator=g)
+    wt = torch.randn((64, 128, 3, 3), device="cuda", generator=g) / 30
+    b = torch.randn((64,), device="cuda", generator=g) * 0.1
+    out = torch.empty((1, 24, 32, 64), dtype=torch.bfloat16, device="cuda")
+    archs._conv(_lib.CONV3, _nhwc(up), _pack(wt), b, out, 64, _lib.ACT_LEAKY, x1=_nhwc(skip))
+    _no_pipeline_error()
+    ref = F.leaky_relu(F.conv2d(torch.cat([_bf(up), _bf(skip)], 1), _bf(wt), b, padding=1), 0.2)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout", [(512, 256), (64, 32)])
+def test_conv_transpose_layer(cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(cin)
+    x = torch.randn((1, cin, 8, 24), device="cuda", generator=g)
+    wt = torch.randn((cin, cout, 2, 2), device="cuda", generator=g) / cin ** 0.5
+    b = torch.randn((cout,), device="cuda", generator=g) * 0.1
+    out = torch.empty((1, 16, 48, cout), dtype=torch.bfloat16, device="cuda")
+    archs._conv(_lib.CONVT, _nhwc(x), _pack(wt, "convT"), b, out, cout, _lib.ACT_NONE)
+    _no_pipeline_error()
+    ref = F.conv_transpose2d(_bf(x), _bf(wt), b, stride=2)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+def test_conv1x1_to_nchw_f32_with_residual():
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((2, 32, 24, 40), device="cuda", generator=g)
+    wt = torch.randn((4, 32, 1, 1), device="cuda", generator=g) / 6
+    b = torch.randn((4,), device="cuda", generator=g) * 0.1
+    res = torch.randn((2, 4, 24, 40), device="cuda", generator=g)
+    out = torch.empty((2, 4, 24, 40), dtype=torch.float32, device="cuda")
+    archs._conv(_lib.CONV1, _nhwc(x), _pack(wt), b, out, 4, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32, resid_nchw=res)
+    _no_pipeline_error()
+    ref = F.conv2d(_bf(x), _bf(wt), b) + res
+    assert (out - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())   # fp32 accumulators, fp32 output
+
+
+def test_maxpool_and_input_layout():
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((2, 64, 16, 48), device="cuda", generator=g)
+    out = torch.empty((2, 8, 24, 64), dtype=torch.bfloat16, device="cuda")
+    archs._pool(_nhwc(x), out)
+    assert torch.equal(_nchw(out), F.max_pool2d(_bf(x), 2))
+    x4 = torch.rand((2, 4, 16, 32), device="cuda", generator=g)
+    o16 = torch.empty((2, 16, 32, 16), dtype=torch.bfloat16, device="cuda")
+    archs._to_nhwc16(x4, o16)
+    assert torch.equal(o16[..., :4].float(), _bf(x4).permute(0, 2, 3, 1)) and float(o16[..., 4:].abs().max()) == 0.0
+
+
+def _arch(res=False):
+    return dict(name="UNetSeeInDark", in_nc=4, out_nc=4, nf=32, nframes=1, use_dpsv=False, res=res, cascade=False,
+                add=False, lock_wb=False)
+
+
+@pytest.mark.parametrize("res", [False, True])
+@pytest.mark.parametrize("shape", [(1, 4, 64, 96), (2, 4, 512, 512)])
+def test_unet_forward_vs_fp32_oracle_reference_init(shape, res):
+    """Reference init (N(0, 0.02)): |out - fp32 oracle| <= 1e-3 max-abs (north_star) and PSNR drift
+    far below 0.01 dB on [0,1] data."""
+    torch.manual_seed(7)
+    net = P.UNetSeeInDark(_arch(res)).cuda()
+    P.initialize_weights(net)
+    net.eval()
+    x = torch.rand(shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1997))
+    with torch.no_grad():
+        got = net(x)
+        want = O.unet_forward(x, net.state_dict(), res=res)       # torch fp32 functional restatement (cuDNN fp32)
+    _no_pipeline_error()
+    err = (got - want).abs().max().item()
+    rel = err / want.abs().max().item()
+    print(f"unet {shape} res={res}: max-abs {err:.3e}, rel {rel:.3e}, out absmax {want.abs().max().item():.3e}")
+    assert err <= 1e-3, err
+    target = torch.rand_like(want)
+    psnr = lambda a: 10 * torch.log10(1.0 / ((a.clamp(0, 1) - target) ** 2).mean())
+    assert abs(psnr(got).item() - psnr(want).item()) < 0.01
+
+
+def test_unet_forward_default_init_relative_error():
+    """PyTorch default init (outputs O(0.1)): report bf16-vs-fp32 relative error (bf16 variant)."""
+    torch.manual_seed(3)
+    net = P.UNetSeeInDark(_arch()).cuda().eval()
+    x = torch.rand((1, 4, 128, 160), device="cuda")
+    with torch.no_grad():
+        got, want = net(x), O.unet_forward(x, net.state_dict())
+    _no_pipeline_error()
+    rel = ((got - want).abs().max() / want.abs().max()).item()
+    print(f"default init: rel max err {rel:.3e}")
+    assert rel < 3e-2
+
+
+def test_state_dict_is_reference_compatible(golden):
+    """Keys / shapes equal the reference module's (golden fixture made from the live reference)."""
+    g = golden("nets")
+    ref_keys = [k.split("__sd__")[1] for k in g.files if k.startswith("UNetSeeInDark_res0__sd__")]
+    arch = _arch()
+    arch["nf"] = 16
+    net = P.UNetSeeInDark(arch)
+    assert list(net.state_dict().keys()) == ref_keys
+
+
+def test_rejects_bad_shapes():
+    net = P.UNetSeeInDark(_arch()).cuda().eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="multiples of 16"):
+        net(torch.rand((1, 4, 40, 64), device="cuda"))
