@@ -1,16 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the pnnp_b200 hot path (driver contract: see the task brief).
+"""bench.py — benchmark of the pnnp_b200 hot path (driver contract: see the task brief).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
-Default workload (`synth64`) is BASELINE.json configs[1]: SonyA7S2 P-G/ELD noise synthesis
-(Poisson + Tukey-lambda + row + quantisation, noise_code 'pgrq') on 64 synthetic 4x512x512 packed
-crops per GPU.  A "step" is one fused-kernel pass over that batch.  Metric: raw megapixels / s
-(raw MP = packed elements / 1e6), whole-job aggregate over all ranks (weak scaling: every rank
-synthesises its own 64 crops; crop ids — and therefore Philox streams — are global).
-
-One JSON line on stdout (rank 0).  Keys beyond the base contract: roofline, cpu_baseline, e2e,
-gpu_launches, clocks.
+Workloads (BASELINE.json configs; raw MP = Bayer samples = packed elements / 1e6):
+  synth64      configs[1] (DEFAULT, the headline): SonyA7S2 P-G/ELD noise synthesis 'pgrq' on 64
+               synthetic 4x512x512 packed crops per GPU; one step = one fused-kernel pass. HBM roofline.
+  unet_sony    configs[0] on the GPU: UNetSeeInDark (PNNP.yml arch, reference init) eval forward on one
+               synthetic 4x1424x2128 frame per GPU per step. Tensor-core roofline.
+  imx686_eval  configs[3]: UNetSeeInDark eval on synthetic 4x1736x2312 frames, reflect-pad 4 -> net ->
+               crop (trainer_LRID.py:224-229), one frame per GPU per step.
+Every rank processes its own crops / frames (weak scaling, no data-path collective); crop ids — and so
+the Philox streams — are global.  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
@@ -22,32 +23,43 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "raw megapixels/sec (noise synthesis, 64x4x512x512 crops per GPU)"
 UNIT = "MP/s"
-N_CROPS, C, HW = 64, 4, 512
-ELEMS = N_CROPS * C * HW * HW                      # 67 108 864 packed elements per GPU per step
-ALGO_BYTES = ELEMS * 8                             # 4 B read + 4 B write per element
 NOISE_CODE = "pgrq"
+UNET_FLOP_PER_PIXEL = 92288.0          # BASELINE.md §3 (2 x MACs per raw pixel, UNetSeeInDark nf=32)
+ARCH = dict(name="UNetSeeInDark", in_nc=4, out_nc=4, nf=32, nframes=1, use_dpsv=False, res=False,
+            cascade=False, add=False, lock_wb=False)       # runfiles/SonyA7S2/PNNP.yml: arch
+
+WORKLOADS = {
+    "synth64": dict(metric="raw megapixels/sec (noise synthesis, 64x4x512x512 crops per GPU)", n=64, c=4, h=512, w=512,
+                    bound="hbm", dtype="f64",
+                    desc="synth64 (BASELINE configs[1]): SonyA7S2 'pgrq' noise synthesis, 64 crops of 4x512x512 per GPU, "
+                         "numpy (float64) chain, Philox4x32-10"),
+    "unet_sony": dict(metric="raw megapixels/sec (UNetSeeInDark eval forward, 4x1424x2128 frame per GPU)", n=1, c=4, h=1424,
+                      w=2128, bound="tensor", dtype="bf16",
+                      desc="unet_sony (BASELINE configs[0] on GPU): UNetSeeInDark nf=32 forward, one 4x1424x2128 frame, "
+                           "bf16 tcgen05 + fp32 accumulate"),
+    "imx686_eval": dict(metric="raw megapixels/sec (UNetSeeInDark eval, 4x1736x2312 frame per GPU, reflect-pad path)", n=1,
+                        c=4, h=1736, w=2312, bound="tensor", dtype="bf16",
+                        desc="imx686_eval (BASELINE configs[3]): reflect-pad 4 -> UNetSeeInDark -> crop on 4x1736x2312 frames"),
+}
 
 
-# ----------------------------------------------------------------------------------------------
-# helpers
 # ----------------------------------------------------------------------------------------------
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as fh:
             d = json.load(fh)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(workload):
     """DRAM bytes per launch of the dominant kernel from the committed ncu summary, if any."""
-    p = os.path.join(ROOT, "profiles", "noise_synth_traffic.json")
+    p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as fh:
-            return json.load(fh).get("dram_bytes_per_launch")
+            return json.load(fh).get(workload)
     return None
 
 
@@ -71,8 +83,7 @@ class ClockSampler(threading.Thread):
         if self.nv is None:
             return
         nv = self.nv
-        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
                  "hw_power_brake": 0x80}
         while not self._halt.is_set():
             try:
@@ -96,26 +107,21 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def synth_inputs(torch, device, rank):
-    """Synthetic dark-scene crops (u^2) and 64 parameter rows, as SURVEY §8d config 2 prescribes."""
-    import numpy as np
-    import pnnp_b200 as P
-    g = torch.Generator(device=device).manual_seed(1997 + rank)
-    clean = torch.rand((N_CROPS, C, HW, HW), device=device, generator=g) ** 2
-    np.random.seed(1997 + rank)
-    params = [P.sample_params("SonyA7S2") for _ in range(N_CROPS)]
-    return clean, params
-
-
 # ----------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference's generate_noisy_obs: same NumPy/SciPy calls)
+# CPU side: the oracle port of the reference algorithms (the reference is Python; /root/reference is
+# not on the GPU box).  Used ONLY as the reported baseline.
 # ----------------------------------------------------------------------------------------------
-def _cpu_one_crop(seed):
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import oracle_np as O
+    return O
+
+
+def _cpu_synth_one_crop(seed):
+    import numpy as np
+    O = _oracle()
     rs = np.random.RandomState(seed)
-    y = rs.rand(C, HW, HW).astype(np.float32) ** 2
+    y = rs.rand(4, 512, 512).astype(np.float32) ** 2
     np.random.seed(seed)
     p = O.sample_params("SonyA7S2")
     t0 = time.perf_counter()
@@ -123,57 +129,87 @@ def _cpu_one_crop(seed):
     return time.perf_counter() - t0
 
 
-def cpu_baseline_single(budget_s=12.0, max_crops=N_CROPS):
-    """One thread, sequential crops (NumPy/SciPy are single-threaded here), bounded by time."""
-    t_start, n, busy = time.perf_counter(), 0, 0.0
-    while n < max_crops and (time.perf_counter() - t_start) < budget_s:
-        busy += _cpu_one_crop(1000 + n)
-        n += 1
-    mp = n * C * HW * HW / 1e6
-    return {"value": mp / busy, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n} of {N_CROPS} crops (4x512x512, '{NOISE_CODE}'), sequential, oracle/oracle_np.py::generate_noisy_obs"}
+def _cpu_unet_frames(wl, frames, threads):
+    """reference init + torch CPU fp32 forward (oracle restatement of archs/Unet.py), `threads` threads."""
+    import torch
+    import torch.nn.functional as F
+    O = _oracle()
+    import pnnp_b200 as P
+    torch.set_num_threads(threads)
+    torch.manual_seed(1997)
+    net = P.UNetSeeInDark(ARCH)
+    P.initialize_weights(net)
+    sd = net.state_dict()
+    x = torch.rand((1, 4, wl["h"], wl["w"]))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(frames):
+            if wl["w"] % 16:
+                y = O.unet_forward(F.pad(x, (4, 4, 4, 4), mode="reflect"), sd)[..., 4:-4, 4:-4]
+            else:
+                y = O.unet_forward(x, sd)
+    return time.perf_counter() - t0
 
 
-def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port — the reference itself is
-    Python and /root/reference does not exist on the GPU box) on all host cores, one worker
-    process per core like the reference's DataLoader workers."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import multiprocessing as mp
+def cpu_baseline(name, wl):
     cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 64))
-    per_step = min(N_CROPS, workers)                       # bounded sample: one crop per worker per step
-    ctx = mp.get_context("fork")
-    with ctx.Pool(workers) as pool:
-        for w in range(args.warmup):
-            pool.map(_cpu_one_crop, [w * per_step + i for i in range(per_step)])
-        t0 = time.perf_counter()
-        for s in range(args.steps):
-            pool.map(_cpu_one_crop, [5000 + s * per_step + i for i in range(per_step)])
-        dt = time.perf_counter() - t0
-    mp_per_step = per_step * C * HW * HW / 1e6
-    value = mp_per_step * args.steps / dt
-    sample = f"{per_step} crops per step on {workers} worker processes (oracle port of generate_noisy_obs)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": "synth64: SonyA7S2 'pgrq' noise synthesis, 4x512x512 crops",
-                                            "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    if name == "synth64":
+        t_start, n, busy = time.perf_counter(), 0, 0.0
+        while n < 64 and (time.perf_counter() - t_start) < 12.0:
+            busy += _cpu_synth_one_crop(1000 + n)
+            n += 1
+        return {"value": n * 4 * 512 * 512 / 1e6 / busy, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{n} of 64 crops (4x512x512, '{NOISE_CODE}'), sequential, oracle_np.generate_noisy_obs "
+                          "(NumPy/SciPy are single-threaded)"}
+    dt = _cpu_unet_frames(wl, 1, cores)
+    return {"value": wl["c"] * wl["h"] * wl["w"] / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 frame 4x{wl['h']}x{wl['w']}, torch CPU fp32, {cores} threads, oracle_np.unet_forward"}
+
+
+def run_reference_arm(args, name, wl):
+    """--impl reference: the reference's CPU algorithm with all the host threads it can use."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    if name == "synth64":
+        import multiprocessing as mp
+        workers = max(1, min(cores, 64))
+        per_step = workers                                     # bounded sample: one crop per worker per step
+        with mp.get_context("fork").Pool(workers) as pool:
+            for w in range(args.warmup):
+                pool.map(_cpu_synth_one_crop, [w * per_step + i for i in range(per_step)])
+            t0 = time.perf_counter()
+            for s in range(args.steps):
+                pool.map(_cpu_synth_one_crop, [5000 + s * per_step + i for i in range(per_step)])
+            dt = time.perf_counter() - t0
+        mp_step = per_step * 4 * 512 * 512 / 1e6
+        sample = f"{per_step} crops per step on {workers} worker processes (oracle port of generate_noisy_obs)"
+        used = workers
+    else:
+        steps = min(args.steps, 3)                             # ~5 s per frame on 8 cores
+        _cpu_unet_frames(wl, min(args.warmup, 1), cores)
+        dt = _cpu_unet_frames(wl, steps, cores) * args.steps / steps
+        mp_step = wl["c"] * wl["h"] * wl["w"] / 1e6
+        sample = f"1 frame per step ({steps} timed, scaled to {args.steps}), torch CPU fp32 on {cores} threads"
+        used = cores
+    value = mp_step * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if name == "synth64" else "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_gpu_arm(args):
+def run_gpu_arm(args, name, wl):
     import numpy as np
     import torch
     import torch.distributed as dist
+    import torch.nn.functional as F
     import pnnp_b200 as P
     from pnnp_b200 import _lib
     from pnnp_b200.pipeline import HostSynthPipeline
@@ -193,15 +229,49 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    clean, params = synth_inputs(torch, device, rank)
-    table = P.ParamTable(params, device)
-    out = torch.empty_like(clean)
-    gen = P.PhiloxGenerator(1997)
-    crop0 = rank * N_CROPS
+    def allmax(v):
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step():
-        P.synthesize_batch(clean, None, NOISE_CODE, _lib.CHAIN_NUMPY, post_clip=(-float("inf"), 1.0),
-                           generator=gen, crop_id0=crop0, out=out, table=table)
+    n, c, h, w = wl["n"], wl["c"], wl["h"], wl["w"]
+    elems = n * c * h * w
+    gen = P.PhiloxGenerator(1997)
+    g = torch.Generator(device=device).manual_seed(1997 + rank)
+    if name == "synth64":
+        clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2      # dark-scene distribution
+        np.random.seed(1997 + rank)
+        params = [P.sample_params("SonyA7S2") for _ in range(n)]
+        table = P.ParamTable(params, device)
+        out = torch.empty_like(clean)
+        crop0 = rank * n
+
+        def step():
+            P.synthesize_batch(clean, None, NOISE_CODE, _lib.CHAIN_NUMPY, post_clip=(-float("inf"), 1.0),
+                               generator=gen, crop_id0=crop0, out=out, table=table)
+        algo = elems * 8.0                                                     # 4 B read + 4 B write per element
+        l2_note = "no flush: 268 MB in + 268 MB out per step exceed the 126 MB L2"
+        kernel = "noise_synth_kernel"
+    else:
+        torch.manual_seed(1997)
+        net = P.UNetSeeInDark(ARCH).to(device).eval()
+        P.initialize_weights(net)
+        frame = torch.rand((n, c, h, w), device=device, generator=g)
+        pad = (w % 16) != 0
+
+        def forward(x):
+            with torch.no_grad():
+                if pad:                                                        # trainer_LRID.py:224-229
+                    return net(F.pad(x, (4, 4, 4, 4), mode="reflect"))[..., 4:-4, 4:-4]
+                return net(x)
+
+        def step():
+            forward(frame)
+        hp, wp_ = (h + 8, w + 8) if pad else (h, w)
+        algo = UNET_FLOP_PER_PIXEL * n * c * hp * wp_                          # FLOPs on the padded extent (per RAW pixel)
+        l2_note = "no flush: level-1/2 activations (194 MB per tensor) exceed the 126 MB L2"
+        kernel = "conv_gemm_tc_kernel (all conv layers; share of step in profiles/)"
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -217,54 +287,63 @@ def run_gpu_arm(args):
     barrier()
     clocks = sampler.stop()
     launches = _lib.launch_count() - l0
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * ELEMS / 1e6 / (ms_step / 1e3)
+    ms_step = allmax(e0.elapsed_time(e1)) / args.steps
+    value = world * elems / 1e6 / (ms_step / 1e3)
 
-    # ---- end-to-end through the public host-buffer API (pinned host in, pinned host out)
-    pipe = HostSynthPipeline(N_CROPS, C, HW, HW, device)
-    host_in = torch.empty((N_CROPS, C, HW, HW), dtype=torch.float32).pin_memory()
-    host_in.copy_(clean.cpu())
-    host_out = torch.empty_like(host_in).pin_memory()
+    # ---- end-to-end through the public host-buffer API (pinned host in, host result out)
     e2e_steps = max(3, min(args.steps, 20))
+    if name == "synth64":
+        pipe = HostSynthPipeline(n, c, h, w, device)
+        host_in = torch.empty((n, c, h, w), dtype=torch.float32).pin_memory()
+        host_in.copy_(clean.cpu())
+        host_out = torch.empty_like(host_in).pin_memory()
+
+        def e2e_step():
+            pipe.run(host_in, host_out, params, NOISE_CODE, generator=gen, crop_id0=crop0, post_clip=(-float("inf"), 1.0))
+        h2d, d2h = elems * 4 + n * 128, elems * 4
+        api = "pnnp_b200.pipeline.HostSynthPipeline.run (pinned host crops in, pinned host noisy crops out)"
+    else:
+        host_in = torch.empty((n, c, h, w), dtype=torch.float32).pin_memory()
+        host_in.copy_(frame.cpu())
+        host_out = torch.empty_like(host_in).pin_memory()
+        dev_in = torch.empty_like(frame)
+
+        def e2e_step():
+            dev_in.copy_(host_in, non_blocking=True)
+            host_out.copy_(forward(dev_in), non_blocking=True)
+        h2d, d2h = elems * 4, elems * 4
+        api = "UNetSeeInDark.forward on a pinned host frame: H2D + forward + D2H of the denoised frame"
     for _ in range(2):
-        pipe.run(host_in, host_out, params, NOISE_CODE, generator=gen, crop_id0=crop0, post_clip=(-float("inf"), 1.0))
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        pipe.run(host_in, host_out, params, NOISE_CODE, generator=gen, crop_id0=crop0, post_clip=(-float("inf"), 1.0))
+        e2e_step()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * ELEMS / 1e6 / (float(te.item()) / e2e_steps)
+    e2e_value = world * elems / 1e6 / (allmax(time.perf_counter() - t0) / e2e_steps)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        achieved = ALGO_BYTES / (ms_step / 1e3) / 1e9
+        peaks, peak_src = measured_peaks()
+        if wl["bound"] == "hbm":
+            achieved, peak, unit = algo / (ms_step / 1e3) / 1e9, float(peaks["hbm_gbs"]), "GB/s"
+            which = "burst copy"
+        else:
+            achieved, unit = algo / (ms_step / 1e3) / 1e12, "TFLOP/s"
+            peak, which = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), "sustained cuBLAS bf16 (kernels timed inside a multi-kernel step)"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synth64 (BASELINE configs[1]): SonyA7S2 'pgrq' noise synthesis, 64 crops of "
-                                   "4x512x512 per GPU, numpy (float64) chain, Philox4x32-10",
-                       "crops_per_gpu": N_CROPS, "crop": [C, HW, HW], "noise_code": NOISE_CODE,
-                       "l2": "no flush: 268 MB in + 268 MB out per step exceed the 126 MB L2"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "noise_synth_kernel",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ELEMS * 4 + N_CROPS * 128,
-                    "d2h_bytes_per_step": ELEMS * 4, "api": "pnnp_b200.pipeline.HostSynthPipeline.run (pinned host in/out)",
+            "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": wl["desc"], "per_gpu_shape": [n, c, h, w], "l2": l2_note},
+            "roofline": {"bound": wl["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                         "traffic": ncu_traffic(name), "peak_source": f"{peak_src}, {which}", "kernel": kernel,
+                         "algorithmic_work_per_step": algo},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api,
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_single()
+            line["cpu_baseline"] = cpu_baseline(name, wl)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -276,16 +355,17 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pnnp_b200", choices=["pnnp_b200", "reference"])
-    ap.add_argument("--workload", default="synth64")
+    ap.add_argument("--workload", default="synth64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, args.workload, wl)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                                    "29533", os.path.abspath(__file__)] + sys.argv[1:])
-    run_gpu_arm(args)
+    run_gpu_arm(args, args.workload, wl)
 
 
 if __name__ == "__main__":

@@ -117,6 +117,7 @@ int pnnp_noise_synth_replay(const float* clean, float* noisy, const pnnp_noise_p
 #define PNNP_CONV3 0 /* nn.Conv2d(k=3, s=1, p=1)                    */
 #define PNNP_CONV1 1 /* nn.Conv2d(k=1)                              */
 #define PNNP_CONVT 2 /* nn.ConvTranspose2d(k=2, s=2): output 2h x 2w */
+#define PNNP_CONV3S2 3 /* nn.Conv2d(k=3, s=2, p=1): output h/2 x w/2 (ResUnet down-sampling, modules.py:130-138) */
 #define PNNP_ACT_NONE 0
 #define PNNP_ACT_LEAKY02 1 /* nn.LeakyReLU(0.2)  Unet.py:52    */
 #define PNNP_ACT_RELU 2    /* nn.ReLU            ResUnet.py:44 */
@@ -141,6 +142,16 @@ int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, 
                         void* stream);
 /* nn.MaxPool2d(2) on NHWC bf16 (Unet.py:57) */
 int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int w, int c, void* stream);
+
+/* E1 / E2 — eval boundary on the device (trainer_SID.py:231-248; IlluminanceCorrect,
+ * data_process/__init__.py:162-175; tensor2im + quality_assess, utils/visualization.py:9-31).
+ * dn, hr: n x c x h x w fp32 (network output, clean target).  dn is scaled by `scale` (the ratio when
+ * dst['ori'], else 1) and clamped to [0,1]; with brightness_correct the ELD gain <dn,hr>/<dn,dn> over
+ * hr != 1 is applied; both images go through x255 + clip.  Writes per frame (3 + c) doubles into
+ * `sums` (device): [num, den, sum of squared error, per-channel sums of the SSIM map over its
+ * (h-6)(w-6) valid centres].  PSNR = 10 log10(255^2 c h w / sse); SSIM = mean_c(sum_c / ((h-6)(w-6))). */
+int pnnp_eval_epilogue(const float* dn, const float* hr, int n, int c, int h, int w, float scale,
+                       int brightness_correct, double* sums, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ from .noise_params import (Dual_ISO_Cameras, HALF_CLIP, ParamTable, get_camera_n
 from .noise import (generate_noisy_obs, generate_noisy_torch, noise_code_bits, replay_batch,
                     synthesize_batch)
 from .rng import PhiloxGenerator, default_generator, manual_seed
-from .archs import UNetSeeInDark, initialize_weights
+from .archs import ResUnet, UNetSeeInDark, initialize_weights
 
 __all__ = [
     "raw2bayer", "bayer2raw", "bayer2rggb", "rggb2bayer",
@@ -20,5 +20,5 @@ __all__ = [
     "sample_params", "sample_params_max",
     "generate_noisy_obs", "generate_noisy_torch", "noise_code_bits", "replay_batch", "synthesize_batch",
     "PhiloxGenerator", "default_generator", "manual_seed",
-    "UNetSeeInDark", "initialize_weights",
+    "UNetSeeInDark", "ResUnet", "initialize_weights",
 ]

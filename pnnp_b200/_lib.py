@@ -46,9 +46,10 @@ SIGNATURES = {
     "pnnp_conv_pipeline_error": (_i, []),
     "pnnp_nchw_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "pnnp_maxpool2x2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "pnnp_eval_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
 }
 
-CONV3, CONV1, CONVT = 0, 1, 2
+CONV3, CONV1, CONVT, CONV3S2 = 0, 1, 2, 3
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 OUT_NHWC_BF16, OUT_NCHW_F32 = 0, 1
 

@@ -216,3 +216,75 @@ class ResidualBlock(nn.Module):
             self.short_cut = nn.Sequential(convWithBN(in_c, out_c, kernel_size=1, padding=0, is_activate=False, is_bn=False))
         else:
             self.short_cut = nn.Sequential(OrderedDict([]))
+
+
+class ResUnet(_TCNet):
+    """archs/ResUnet.py:3-88.  ResidualBlock(is_activate=False) = conv(no bias)+ReLU -> conv(no bias),
+    then `+= short_cut(x)` (identity, or a bias-free 1x1 conv when in != out); down-sampling is a
+    stride-2 3x3 conv with bias and no activation."""
+
+    def __init__(self, args=None):
+        super().__init__()
+        self.args = args
+        self.nframes = args['nframes']
+        self.cf = args['nframes'] // 2
+        self.res = args['res']
+        nf, in_nc, out_nc = args['nf'], args['in_nc'] * args['nframes'], args['out_nc']
+        if nf % 16:
+            raise RuntimeError("pnnp_b200: nf must be a multiple of 16 for the tensor-core path")
+        self.nf, self.out_nc = nf, out_nc
+        self.conv_in = nn.Conv2d(in_nc, nf, kernel_size=3, stride=1, padding=1)
+        for i in range(1, 6):
+            co = nf * 2 ** (i - 1)
+            setattr(self, f"conv{i}", ResidualBlock(co, co, is_activate=False))
+            if i < 5:
+                setattr(self, f"pool{i}", conv3x3(co, co * 2))
+        for i, co in zip(range(6, 10), (nf * 8, nf * 4, nf * 2, nf)):
+            setattr(self, f"upv{i}", nn.ConvTranspose2d(co * 2, co, 2, stride=2))
+            setattr(self, f"conv{i}", ResidualBlock(co * 2, co, is_activate=False))
+        self.conv10 = nn.Conv2d(nf, out_nc, kernel_size=1, stride=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x, noise_map=None):
+        x = self._check_input(x)
+        n, c, h, w = x.shape
+        dev, ws, nf = x.device, self._ws(), self.nf
+        sig = (n, h, w, str(dev))
+        buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev)
+
+        def block(i, src0, src1, hh, ww, co):
+            """ResidualBlock i on (src0 [, src1]) -> NHWC bf16 (modules.py:176-197)."""
+            w1, _ = self._packed(f"conv{i}.block.0.conv.conv")
+            w2, _ = self._packed(f"conv{i}.block.1.conv.conv")
+            t = _conv(_lib.CONV3, src0, w1, None, buf(f"b{i}a", hh, ww, co), co, _lib.ACT_RELU, x1=src1)
+            if src1 is None:
+                shortcut = src0                                        # identity (in_c == out_c)
+            else:
+                wsc, _ = self._packed(f"conv{i}.short_cut.0.conv.conv")
+                shortcut = _conv(_lib.CONV1, src0, wsc, None, buf(f"b{i}s", hh, ww, co), co, _lib.ACT_NONE, x1=src1)
+            return _conv(_lib.CONV3, t, w2, None, buf(f"b{i}", hh, ww, co), co, _lib.ACT_NONE, resid=shortcut)
+
+        with torch.cuda.device(dev):
+            x16 = _to_nhwc16(x, buf("x16", h, w, 16))
+            wi, bi = self._packed("conv_in")
+            cur = _conv(_lib.CONV3, x16, wi, bi, buf("cin", h, w, nf), nf, _lib.ACT_RELU)
+            skips, hh, ww = [], h, w
+            for i in range(1, 6):
+                co = nf * 2 ** (i - 1)
+                cur = block(i, cur, None, hh, ww, co)
+                if i < 5:
+                    skips.append(cur)
+                    wp, bp = self._packed(f"pool{i}.conv")
+                    cur = _conv(_lib.CONV3S2, cur, wp, bp, buf(f"d{i}", hh // 2, ww // 2, co * 2), co * 2, _lib.ACT_NONE)
+                    hh, ww = hh // 2, ww // 2
+            for i in range(6, 10):
+                co = nf * 2 ** (9 - i)
+                wu, bu = self._packed(f"upv{i}", "convT")
+                up = _conv(_lib.CONVT, cur, wu, bu, buf(f"u{i}", hh * 2, ww * 2, co), co, _lib.ACT_NONE)
+                hh, ww = hh * 2, ww * 2
+                cur = block(i, up, skips[9 - i], hh, ww, co)
+            w10, b10 = self._packed("conv10")
+            out = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=dev)
+            _conv(_lib.CONV1, cur, w10, b10, out, self.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,
+                  resid_nchw=x if self.res else None)
+        return out

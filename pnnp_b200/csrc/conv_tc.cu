@@ -35,12 +35,12 @@ constexpr int kConvThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSpinLimit = 1u << 27;      // ~ seconds; a broken pipeline terminates instead of hanging the GPU
 
-enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2 };
+enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2, MODE_CONV3S2 = 3 };
 enum { OUT_NHWC_BF16 = 0, OUT_NCHW_F32 = 1 };
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
 
 struct ConvParams {
-    int mode, n_img, H, W;          // H, W: spatial size of the INPUT (== output for CONV3/CONV1; output is 2H x 2W for CONVT)
+    int mode, n_img, H, W;          // H, W: tiled spatial grid = output size (CONV3/CONV1/CONV3S2) or input size (CONVT: output 2H x 2W)
     int tiles_x, tiles_y, n_tiles;
     int umma_n;                     // columns per accumulator / MMA N
     int nsrc, cin0, cin1;           // channels of the two K sources (multiples of kc); cin1 = 0 if single
@@ -68,16 +68,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-    uint32_t ok = 0;
+// Spin on an mbarrier phase.  Returns nothing on purpose: loop control of the callers must not depend
+// on inline-asm outputs, otherwise nvcc treats the whole role loop as divergent and wraps every
+// tcgen05.mma in an ELECT/R2UR waterfall.  A wait that exceeds kSpinLimit polls raises the global error
+// word; once it is set every later wait returns after a single poll, so a broken pipeline terminates
+// in bounded time instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    uint32_t ok = 0, it = 0;
 #pragma unroll 1
-    for (uint32_t it = 0; it < kSpinLimit; ++it) {
+    while (true) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return true;
+        if (ok) return;
+        if ((++it & 0x3FFu) == 0) {
+            if (*reinterpret_cast<volatile int*>(err) != 0) return;
+            if (it >= kSpinLimit) { atomicExch(err, code); return; }
+        }
     }
-    if (err) atomicExch(err, code);
-    return false;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -119,7 +131,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// All MMAs of one pipeline stage: TPS taps x K16S K-slices, fully unrolled; descriptors advance by adding
+// to the 14-bit start-address field (no carry out of the field: shared memory is < 256 KB).
+template <int TPS, int K16S>
+__device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc0, uint64_t bdesc0, uint32_t a_tap_stride,
+                                                 uint32_t b_tap_stride, uint32_t idesc, bool accumulate_first) {
+#pragma unroll
+    for (int dy = 0; dy < TPS; ++dy) {
+#pragma unroll
+        for (int k = 0; k < K16S; ++k) {
+            const uint64_t ad = adesc0 + (uint64_t)(dy * a_tap_stride + k * 2);     // k * 32 B
+            const uint64_t bd = bdesc0 + (uint64_t)(dy * b_tap_stride + k * 2);
+            tc_mma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || dy != 0 || k != 0) ? 1u : 0u);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ kernel
+template <int TPS, int K16S>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
@@ -135,8 +164,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int taps_per_stage = p.mode == MODE_CONV3 ? 3 : 1;
-    const int dx_count = p.mode == MODE_CONV3 ? 3 : 1;
+    constexpr int taps_per_stage = TPS;
+    const int dx_count = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : 1);   // pipeline stages per K chunk
     const int chunks0 = p.cin0 / p.kc, chunks1 = p.nsrc > 1 ? p.cin1 / p.kc : 0;
     const int ksteps = (chunks0 + chunks1) * dx_count;
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
@@ -160,74 +189,76 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Producer and MMA warps run their loops warp-uniformly (all 32 lanes take the same branches and
+    // hold the same values, so addresses/descriptors stay in uniform registers); only the TMA / MMA /
+    // commit instructions themselves are predicated on one elected lane.
     if (warp == 0) {
         // ============================== TMA producer ==============================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            bool alive = true;
-            for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
-                int r = t;
-                const int n_tile = r % p.n_tiles; r /= p.n_tiles;
-                const int tx = r % p.tiles_x; r /= p.tiles_x;
-                const int ty = r % p.tiles_y; r /= p.tiles_y;
-                const int img = r;
-                const int x0 = tx * kTileW, y0 = ty * kTileH;
-                const int n_off = p.mode == MODE_CONVT ? 0 : n_tile * p.umma_n;
-                for (int ks = 0; ks < ksteps && alive; ++ks) {
-                    const int chunk = ks / dx_count, dx = ks - chunk * dx_count;
-                    const int src = chunk >= chunks0 ? 1 : 0;
-                    const int cc = src ? chunk - chunks0 : chunk;
-                    const int cin_off = (src ? p.cin0 : 0) + cc * p.kc;
-                    alive = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 101);
-                    if (!alive) break;
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
+        uint32_t stage = 0, phase = 0;
+        const int halo = p.mode == MODE_CONV3 ? 1 : 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int r = t;
+            const int n_tile = r % p.n_tiles; r /= p.n_tiles;
+            const int tx = r % p.tiles_x; r /= p.tiles_x;
+            const int ty = r % p.tiles_y; r /= p.tiles_y;
+            const int img = r;
+            const int x0 = tx * kTileW, y0 = ty * kTileH;
+            const int n_off = p.mode == MODE_CONVT ? 0 : n_tile * p.umma_n;
+            int chunk = 0, dx = 0;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int src = chunk >= chunks0 ? 1 : 0;
+                const int cc = src ? chunk - chunks0 : chunk;
+                const int cin_off = (src ? p.cin0 : 0) + cc * p.kc;
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 101);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                const uint32_t sb = sa + p.a_bytes;
+                if (elect_one()) {
                     mbar_expect_tx(fb, stage_tx);
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                    const int halo = p.mode == MODE_CONV3 ? 1 : 0;
-                    tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - halo, img);
-                    const uint32_t sb = sa + p.a_bytes;
+                    if (p.mode == MODE_CONV3S2)      // stride 2: one box per tap, TMA element stride 2 in x and y
+                        tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx % 3) - 1, 2 * y0 + (dx / 3) - 1, img);
+                    else
+                        tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - halo, img);
                     for (int dy = 0; dy < taps_per_stage; ++dy) {
-                        const int tap = p.mode == MODE_CONV3 ? dy * 3 + dx : (p.mode == MODE_CONVT ? n_tile : 0);
+                        const int tap = p.mode == MODE_CONV3 ? dy * 3 + dx
+                                      : (p.mode == MODE_CONVT ? n_tile : (p.mode == MODE_CONV3S2 ? dx : 0));
                         tma_load_3d(sb + dy * p.b_tap_stride, &tmB, fb, cin_off, n_off, tap);
                     }
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++dx == dx_count) { dx = 0; ++chunk; }
+                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            const uint64_t dhi = umma_desc_hi(p.swz);
-            const int k16s = p.kc / 16;
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            bool alive = true;
-            for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
-                alive = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 102);
-                if (!alive) break;
+        // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        const uint64_t dhi = umma_desc_hi(p.swz);
+        const uint32_t a_tap_stride = (uint32_t)(kTileW * p.swz) >> 4;      // descriptor units (16 B)
+        const uint32_t b_tap_stride = (uint32_t)p.b_tap_stride >> 4;
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 102);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.umma_n;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 103);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.umma_n;
-                for (int ks = 0; ks < ksteps && alive; ++ks) {
-                    alive = mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 103);
-                    if (!alive) break;
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                    const uint32_t sb = sa + p.a_bytes;
-                    for (int dy = 0; dy < taps_per_stage; ++dy) {
-                        const uint32_t a0 = sa + dy * kTileW * p.swz;
-                        const uint32_t b0 = sb + dy * p.b_tap_stride;
-                        for (int k = 0; k < k16s; ++k)
-                            tc_mma_bf16(d_tmem, umma_desc(dhi, a0 + k * 32), umma_desc(dhi, b0 + k * 32), idesc,
-                                        (ks | dy | k) != 0 ? 1u : 0u);
-                    }
-                    tc_commit(smem_u32(&empty_bar[stage]));          // frees the smem slot when these MMAs retire
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                const uint64_t adesc0 = dhi | (uint64_t)((sa >> 4) & 0x3FFFu);
+                const uint64_t bdesc0 = dhi | (uint64_t)(((sa + p.a_bytes) >> 4) & 0x3FFFu);
+                if (elect_one()) {
+                    issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_tap_stride, idesc, ks != 0);
+                    tc_commit(smem_u32(&empty_bar[stage]));              // frees the smem slot when these MMAs retire
                 }
-                tc_commit(smem_u32(&tfull_bar[acc]));                // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                __syncwarp();
+                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete -> epilogue
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     } else {
         // ============================== epilogue (warps 2..5) ==============================
@@ -235,9 +266,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
         const int ty_in = m / kTileW, tx_in = m % kTileW;
         uint32_t acc = 0, acc_phase = 0;
-        bool alive = true;
         const int chunks16 = p.umma_n / 16;
-        for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             int r = t;
             const int n_tile = r % p.n_tiles; r /= p.n_tiles;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
@@ -245,8 +275,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const int img = r;
             const int x = tx * kTileW + tx_in, y = ty * kTileH + ty_in;
             const bool valid = x < p.W && y < p.H;
-            alive = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
-            if (!alive) break;
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * (uint32_t)p.umma_n + ((uint32_t)(quad * 32) << 16);
             size_t opix;            // output pixel index
@@ -379,13 +408,15 @@ static CUtensorMapSwizzle swz_enum(int swz) {
     return swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 // activation map: NHWC bf16 viewed as (C, W, H, N); box (kc, 16, box_h, 1)
-static int make_act_map(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c, int kc, int box_h, int swz) {
+static int make_act_map(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c, int kc, int box_h, int swz,
+                        int stride = 1) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kTileW, (cuuint32_t)box_h, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // with a traversal stride s the TMA unit loads boxDim/s elements per dimension
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(kTileW * stride), (cuuint32_t)(box_h * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -427,7 +458,10 @@ int conv_layer_launch(int mode, const void* in0, int cin0, const void* in1, int 
     }
     if (out_mode == OUT_NHWC_BF16 && (cout % 16)) return fail("conv: NHWC output needs cout % 16 == 0");
     if (w_rows < (mode == MODE_CONVT ? cout : n_tiles * umma_n)) return fail("conv: weight tensor has too few rows");
-    const int taps = mode == MODE_CONV3 ? 9 : (mode == MODE_CONVT ? 4 : 1);
+    const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : (mode == MODE_CONVT ? 4 : 1);
+    if (mode == MODE_CONV3S2 && (nsrc > 1 || (h & 1) || (w & 1))) return fail("stride-2 conv: single source, even h and w");
+    const int in_h = h, in_w = w;
+    if (mode == MODE_CONV3S2) { h /= 2; w /= 2; }        // tile over the OUTPUT grid
     const int tps = mode == MODE_CONV3 ? 3 : 1;
     const int box_h = mode == MODE_CONV3 ? kTileH + 2 : kTileH;
     // shrink the K chunk until at least 3 pipeline stages fit
@@ -454,7 +488,7 @@ int conv_layer_launch(int mode, const void* in0, int cin0, const void* in1, int 
     if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
     p.err = g_err_dev;
     CUtensorMap tmA0, tmA1, tmB;
-    if (int e = make_act_map(&tmA0, in0, n, h, w, cin0, kc, box_h, swz)) return e;
+    if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, mode == MODE_CONV3S2 ? 2 : 1)) return e;
     if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz)) return e; }
     else tmA1 = tmA0;
     if (int e = make_w_map(&tmB, weight, taps, w_rows, cin0 + (nsrc > 1 ? cin1 : 0), kc, umma_n, swz)) return e;
@@ -464,13 +498,21 @@ int conv_layer_launch(int mode, const void* in0, int cin0, const void* in1, int 
     const int total_tiles = n * p.tiles_y * p.tiles_x * n_tiles;
     const int grid = std::min(total_tiles, sms);
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16 + (size_t)cout * 4 + 64;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        smem_set = 227 * 1024;
-    }
     if (smem > 227 * 1024) return fail("conv: shared memory budget exceeded");
-    conv_gemm_tc_kernel<<<grid, kConvThreads, smem, st>>>(tmA0, tmA1, tmB, p);
+    static bool attr_done = false;
+#define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1) X(3, 2) X(3, 4) X(1, 1) X(1, 2) X(1, 4)
+    if (!attr_done) {
+#define X(T, K) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PNNP_FOR_EACH_CONV_VARIANT(X)
+#undef X
+        attr_done = true;
+    }
+    const int k16s = kc / 16;
+    bool launched = false;
+#define X(T, K) if (!launched && tps == T && k16s == K) { conv_gemm_tc_kernel<T, K><<<grid, kConvThreads, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
+    PNNP_FOR_EACH_CONV_VARIANT(X)
+#undef X
+    if (!launched) return fail("conv: no kernel variant for this (taps per stage, K chunk)");
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

@@ -1,0 +1,74 @@
+"""Synthetic stand-ins for the reference's eval datasets (real_datasets.py ELD_Dataset / SID_Dataset,
+phone_datasets.py IMX686_Dataset), which need 560 GB of RAW files that are out of scope here.
+
+Same constructor (`Dataset(yaml_dict)`), same item dict keys (lr hr ratio wb ccm name ISO
+ExposureTime) and the same sweep controls (`ratio_list`, `recheck_length`, `change_eval_ratio`).
+The clean frame is a seeded dark-scene frame; the noisy frame is produced ON THE DEVICE by the fused
+synthesis kernel from per-ISO calibrated parameters (sample_params_max(camera, ratio, iso)), i.e. the
+P1 -> S3 -> N1-N3 chain of the hot path.  Items carry host tensors for hr only; `lr` is filled by the
+trainer's preprocess on the GPU."""
+import numpy as np
+import torch
+
+from .noise_params import sample_params_max
+
+
+class _SyntheticEvalBase(torch.utils.data.Dataset):
+    default_frames = 10
+
+    def __init__(self, args=None):
+        self.args = dict(args)
+        self.H, self.W = self.args['H'], self.args['W']
+        self.h, self.w, self.c = self.H // 2, self.W // 2, 4
+        self.ratio_list = list(self.args.get('ratio_list', [100]))
+        self.iso_list = list(self.args.get('iso_list', [self.default_iso]))
+        self.n_scenes = int(self.args.get('synthetic_frames', self.default_frames))
+        self.recheck_length()
+
+    def recheck_length(self):
+        self.items = [(s, iso, r) for r in self.ratio_list for s in range(self.n_scenes) for iso in self.iso_list]
+        self.length = len(self.items)
+
+    def change_eval_ratio(self, ratio):
+        self.ratio_list = [ratio]
+        self.recheck_length()
+
+    def __len__(self):
+        return self.length
+
+    def clean_frame(self, scene):
+        g = torch.Generator().manual_seed(1997 + scene)
+        return torch.rand((self.c, self.h, self.w), generator=g) ** 2
+
+    def __getitem__(self, idx):
+        scene, iso, ratio = self.items[idx]
+        rs = np.random.RandomState(7919 * scene + iso)
+        state = np.random.get_state()
+        np.random.set_state(rs.get_state())
+        try:
+            iso_arg = iso if self.args['camera_type'] in ("SonyA7S2", "IMX686") and iso in self.legal_iso else None
+            param = sample_params_max(self.args['camera_type'], ratio=ratio, iso=iso_arg)
+        finally:
+            np.random.set_state(state)
+        hr = self.clean_frame(scene)
+        return {"hr": hr[None], "lr": hr[None].clone(), "ratio": np.float32(ratio), "wb": np.ones(4, np.float32),
+                "ccm": np.eye(3, dtype=np.float32), "name": f"{self.args.get('dstname', 'syn')}_s{scene:03d}_iso{iso}_x{ratio}",
+                "ISO": iso, "ExposureTime": 1.0, "param": param, "index": idx}
+
+
+class Synthetic_ELD_Dataset(_SyntheticEvalBase):
+    """ELD-shaped sweep: 10 scenes x iso_list, ratio_list [100, 200] (real_datasets.py:333-338)."""
+    default_frames, default_iso = 10, 1600
+    legal_iso = (50, 64, 80, 100, 125, 160, 200, 250, 320, 400, 500, 640, 800, 1000, 1250, 1600, 2000, 2500, 3200,
+                 4000, 5000, 6400, 8000, 10000, 12800, 16000, 20000, 25600)
+
+
+class Synthetic_SID_Dataset(Synthetic_ELD_Dataset):
+    """SID-shaped sweep: 40 frames per ratio (real_datasets.py:324)."""
+    default_frames = 40
+
+
+class Synthetic_IMX686_Dataset(_SyntheticEvalBase):
+    """LRID-shaped sweep: 9 scenes (phone_datasets.py:245), 4x1736x2312 frames."""
+    default_frames, default_iso = 9, 6400
+    legal_iso = (100, 6400)

@@ -1,0 +1,52 @@
+"""Eval entry points (trainer_SID.py / trainer_LRID.py equivalents) end to end on small synthetic frames."""
+import os
+import re
+
+import pytest
+import yaml
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_runfile(tmp_path, src, H, W, frames, name=None):
+    cfg = yaml.load(open(os.path.join(ROOT, src)), Loader=yaml.FullLoader)
+    for k in ("dst", "dst_train", "dst_eval", "dst_test"):
+        cfg[k]["H"], cfg[k]["W"] = H, W
+        cfg[k]["synthetic_frames"] = frames
+        if "iso_list" in cfg[k]:
+            cfg[k]["iso_list"] = cfg[k]["iso_list"][:1]
+    if name:
+        cfg["arch"]["name"] = name
+        cfg["model_name"] += "_" + name
+    cfg["fast_ckpt"] = str(tmp_path / "ckpt")
+    cfg["checkpoint"] = str(tmp_path / "saved")
+    p = tmp_path / "run.yml"
+    p.write_text(yaml.dump(cfg))
+    return str(p), cfg
+
+
+@pytest.mark.parametrize("arch", ["UNetSeeInDark", "ResUnet"])
+def test_sid_evaltest_entry_point(tmp_path, monkeypatch, arch):
+    from pnnp_b200 import trainer as T
+    monkeypatch.chdir(tmp_path)
+    runfile, cfg = _small_runfile(tmp_path, "runfiles/SonyA7S2/PNNP.yml", 256, 384, 2, arch)
+    res = T.main_sid(["-f", runfile, "--mode", "evaltest"])
+    assert set(res) == {"eval_x100", "eval_x200", "test_x100", "test_x250", "test_x300"}
+    for v in res.values():
+        assert v["frames"] == 2 and 0 < v["PSNR"] < 80 and -1 <= v["SSIM"] <= 1
+    text = open(tmp_path / "logs" / f"log_{cfg['model_name']}.log").read()
+    assert "ELD Datasets: Dgain=100" in text and "SID Datasets: Dgain=300" in text
+    assert re.search(r">>  Epoch -1: PSNR=\d+\.\d\d\npsnrs_lr=\d+\.\d\d, psnrs_dn=\d+\.\d\d\nssims_lr=-?\d\.\d{4}, ssims_dn=-?\d\.\d{4}", text)
+    assert os.path.exists(tmp_path / "metrics" / f"{cfg['model_name']}_metrics.pkl")
+    assert os.path.exists(os.path.join(cfg["fast_ckpt"], f"{cfg['model_name']}_last_model.pth"))
+
+
+def test_lrid_eval_entry_point_takes_reflect_pad_branch(tmp_path, monkeypatch):
+    from pnnp_b200 import trainer as T
+    monkeypatch.chdir(tmp_path)
+    runfile, cfg = _small_runfile(tmp_path, "runfiles/IMX686/PNNP.yml", 80, 112, 2)     # 40 x 56 packed: 56 % 16 != 0
+    res = T.main_lrid(["-f", runfile, "--mode", "eval"])
+    assert set(res) == {f"eval_x{r}" for r in (1, 2, 4, 8, 16)}
+    assert all(v["frames"] == 2 and v["PSNR"] > 0 for v in res.values())

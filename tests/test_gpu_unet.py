@@ -165,3 +165,54 @@ def test_rejects_bad_shapes():
     net = P.UNetSeeInDark(_arch()).cuda().eval()
     with torch.no_grad(), pytest.raises(RuntimeError, match="multiples of 16"):
         net(torch.rand((1, 4, 40, 64), device="cuda"))
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(32, 64, 32, 64), (64, 128, 16, 32), (256, 512, 32, 32), (32, 64, 24, 40)])
+def test_conv3x3_stride2_layer(cin, cout, h, w):
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    x = torch.randn((2, cin, h, w), device="cuda", generator=g)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) / (3 * cin ** 0.5)
+    b = torch.randn((cout,), device="cuda", generator=g) * 0.1
+    out = torch.empty((2, h // 2, w // 2, cout), dtype=torch.bfloat16, device="cuda")
+    archs._conv(_lib.CONV3S2, _nhwc(x), _pack(wt), b, out, cout, _lib.ACT_NONE)
+    _no_pipeline_error()
+    ref = F.conv2d(_bf(x), _bf(wt), b, padding=1, stride=2)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_residual_add_in_epilogue():
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((1, 64, 16, 32), device="cuda", generator=g)
+    wt = torch.randn((64, 64, 3, 3), device="cuda", generator=g) / 24
+    out = torch.empty((1, 16, 32, 64), dtype=torch.bfloat16, device="cuda")
+    xb = _nhwc(x)
+    archs._conv(_lib.CONV3, xb, _pack(wt), None, out, 64, _lib.ACT_NONE, resid=xb)
+    _no_pipeline_error()
+    ref = F.conv2d(_bf(x), _bf(wt), None, padding=1) + _bf(x)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 64, 96), (1, 4, 256, 512)])
+def test_resunet_forward_vs_fp32_oracle_reference_init(shape):
+    torch.manual_seed(11)
+    net = P.ResUnet(_arch()).cuda()
+    P.initialize_weights(net)
+    net.eval()
+    x = torch.rand(shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    with torch.no_grad():
+        got = net(x)
+        want = O.resunet_forward(x, net.state_dict())
+    _no_pipeline_error()
+    err = (got - want).abs().max().item()
+    print(f"resunet {shape}: max-abs {err:.3e}, rel {err / want.abs().max().item():.3e}")
+    assert err <= 1e-3, err
+
+
+def test_resunet_state_dict_is_reference_compatible(golden):
+    g = golden("nets")
+    ref_keys = [k.split("__sd__")[1] for k in g.files if k.startswith("ResUnet_res0__sd__")]
+    arch = _arch()
+    arch["nf"] = 16
+    net = P.ResUnet(arch)
+    assert list(net.state_dict().keys()) == ref_keys
+    assert sum(p.numel() for p in P.ResUnet(_arch()).parameters()) == 11075268
