@@ -69,7 +69,7 @@ class Base_Trainer():
         self.model_name, self.fast_ckpt = self.args['model_name'], self.args['fast_ckpt']
         self.model_dir = self.args['checkpoint']
         self.sample_dir = os.path.join(self.args['result_dir'], f"samples-{self.model_name}")
-        for d in (self.model_dir, './logs', f'./{self.fast_ckpt}', './metrics'):
+        for d in (self.model_dir, './logs', self.fast_ckpt, './metrics'):
             os.makedirs(d, exist_ok=True)
         self.logfile = f'./logs/log_{self.model_name}.log' if self.rank == 0 else None
 
