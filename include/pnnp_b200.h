@@ -134,6 +134,24 @@ int pnnp_conv2d_tc(int mode, const void* in0, int cin0, const void* in1, int cin
                    int w_rows, const float* bias, void* out, int cout, int cout_stride, int n, int h,
                    int w, int act, int out_mode, const void* resid, const float* resid_nchw,
                    void* stream);
+/* Descriptor form with the fused epilogue options.  pool_out: also write nn.MaxPool2d(2) of the output
+ * (NHWC bf16, h/2 x w/2; Unet.py:57-69).  head_*: fuse a following 1x1 conv with <= 4 output channels
+ * (conv10_1, Unet.py:93-98) — fp32 weights [head_cout][cout], output NCHW fp32 (+ resid_nchw); `out` may
+ * then be NULL so the intermediate activation is never written. */
+typedef struct pnnp_conv_desc {
+    int mode, act, out_mode;
+    int n, h, w;
+    const void* in0; int cin0;
+    const void* in1; int cin1;
+    const void* weight; int w_rows;
+    const float* bias;
+    void* out; int cout; int cout_stride;
+    const void* resid;
+    const float* resid_nchw;
+    void* pool_out;
+    const float* head_w; const float* head_b; float* head_out; int head_cout;
+} pnnp_conv_desc;
+int pnnp_conv2d_tc_ex(const pnnp_conv_desc* desc, void* stream);
 /* Non-zero if a tcgen05/TMA pipeline wait timed out since the last call (the kernels terminate
  * instead of hanging); synchronises the device. */
 int pnnp_conv_pipeline_error(void);

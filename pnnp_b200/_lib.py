@@ -23,6 +23,16 @@ class NoiseParamsRow(C.Structure):
 
 assert C.sizeof(NoiseParamsRow) == 128
 
+
+class ConvDesc(C.Structure):
+    """struct pnnp_conv_desc."""
+    _fields_ = [("mode", C.c_int), ("act", C.c_int), ("out_mode", C.c_int), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int),
+                ("in0", C.c_void_p), ("cin0", C.c_int), ("in1", C.c_void_p), ("cin1", C.c_int),
+                ("weight", C.c_void_p), ("w_rows", C.c_int), ("bias", C.c_void_p),
+                ("out", C.c_void_p), ("cout", C.c_int), ("cout_stride", C.c_int),
+                ("resid", C.c_void_p), ("resid_nchw", C.c_void_p), ("pool_out", C.c_void_p),
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_cout", C.c_int)]
+
 CODE_P, CODE_G, CODE_R, CODE_Q, CODE_D, CODE_B = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 CHAIN_NUMPY, CHAIN_TORCH = 0, 1
 F_K64, F_RATIO64, F_SIG64 = 0x1, 0x2, 0x4
@@ -43,6 +53,7 @@ SIGNATURES = {
     "pnnp_noise_synth_replay": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _f,
                                      _vp, _vp, _vp, _vp, _vp]),
     "pnnp_conv2d_tc": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pnnp_conv2d_tc_ex": (_i, [C.POINTER(ConvDesc), _vp]),
     "pnnp_conv_pipeline_error": (_i, []),
     "pnnp_nchw_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "pnnp_maxpool2x2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

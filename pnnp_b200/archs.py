@@ -76,15 +76,24 @@ class _Workspace:
         return t
 
 
-def _conv(mode, x0, w, b, out, cout, act, x1=None, resid=None, out_mode=_lib.OUT_NHWC_BF16, resid_nchw=None):
-    """x0/x1: NHWC bf16 (n,h,w,c).  out: NHWC bf16 tensor or NCHW fp32 tensor."""
+def _conv(mode, x0, w, b, out, cout, act, x1=None, resid=None, out_mode=_lib.OUT_NHWC_BF16, resid_nchw=None,
+          pool_out=None, head=None):
+    """x0/x1: NHWC bf16 (n,h,w,c).  out: NHWC bf16 tensor, NCHW fp32 tensor, or None with `head`.
+    pool_out: NHWC bf16 (n,h/2,w/2,cout) receiving the fused 2x2 max-pool.
+    head = (w fp32 [co2, cout], b fp32 [co2], out fp32 NCHW): fused 1x1 conv on the activated output."""
     n, h, wd, c0 = x0.shape
-    c1 = 0 if x1 is None else x1.shape[3]
-    cout_stride = out.shape[3] if out_mode == _lib.OUT_NHWC_BF16 else cout
-    _lib.check(_lib.lib().pnnp_conv2d_tc(
-        mode, x0.data_ptr(), c0, _lib.ptr(x1), c1, w.data_ptr(), w.shape[1], _lib.ptr(b), out.data_ptr(), cout,
-        cout_stride, n, h, wd, act, out_mode, _lib.ptr(resid), _lib.ptr(resid_nchw), _lib.stream_ptr(x0.device)),
-        "conv2d_tc")
+    d = _lib.ConvDesc()
+    d.mode, d.act, d.out_mode, d.n, d.h, d.w = mode, act, out_mode, n, h, wd
+    d.in0, d.cin0 = x0.data_ptr(), c0
+    d.in1, d.cin1 = (None, 0) if x1 is None else (x1.data_ptr(), x1.shape[3])
+    d.weight, d.w_rows, d.bias = w.data_ptr(), w.shape[1], _lib.ptr(b)
+    d.out, d.cout = _lib.ptr(out), cout
+    d.cout_stride = cout if (out is None or out_mode != _lib.OUT_NHWC_BF16) else out.shape[3]
+    d.resid, d.resid_nchw, d.pool_out = _lib.ptr(resid), _lib.ptr(resid_nchw), _lib.ptr(pool_out)
+    if head is not None:
+        hw, hb, hout = head
+        d.head_w, d.head_b, d.head_out, d.head_cout = hw.data_ptr(), hb.data_ptr(), hout.data_ptr(), hw.shape[0]
+    _lib.check(_lib.lib().pnnp_conv2d_tc_ex(d, _lib.stream_ptr(x0.device)), "conv2d_tc")
     return out
 
 
@@ -167,13 +176,12 @@ class UNetSeeInDark(_TCNet):
                 w1, b1 = self._packed(f"conv{i}_1")
                 w2, b2 = self._packed(f"conv{i}_2")
                 t = _conv(_lib.CONV3, cur, w1, b1, buf(f"c{i}a", hh, ww, co), co, L)
-                cfull = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
-                if i < 5:
-                    skips.append(cfull)
-                    cur = _pool(cfull, buf(f"p{i}", hh // 2, ww // 2, co))
-                    hh, ww = hh // 2, ww // 2
+                if i < 5:                                          # conv + LeakyReLU + MaxPool2d(2) in one epilogue
+                    pooled = buf(f"p{i}", hh // 2, ww // 2, co)
+                    skips.append(_conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L, pool_out=pooled))
+                    cur, hh, ww = pooled, hh // 2, ww // 2
                 else:
-                    cur = cfull
+                    cur = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
             for i in range(6, 10):                                 # decoder (Unet.py:71-89)
                 co = nf * 2 ** (9 - i)
                 skip = skips[9 - i]
@@ -183,11 +191,19 @@ class UNetSeeInDark(_TCNet):
                 w1, b1 = self._packed(f"conv{i}_1")
                 w2, b2 = self._packed(f"conv{i}_2")
                 t = _conv(_lib.CONV3, up, w1, b1, buf(f"c{i}a", hh, ww, co), co, L, x1=skip)   # cat([up, skip], 1)
-                cur = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
-            w10, b10 = self._packed("conv10_1")
+                if i < 9 or co > 64 or self.out_nc > 4:
+                    cur = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
             out = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=dev)
-            _conv(_lib.CONV1, cur, w10, b10, out, self.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,
-                  resid_nchw=x if self.res else None)
+            if co <= 64 and self.out_nc <= 4:
+                # conv9_2 + LeakyReLU + conv10_1 (+ x) in one kernel: conv9 never goes to HBM (Unet.py:90-98)
+                m10 = self.conv10_1
+                hw = m10.weight.detach().reshape(self.out_nc, co).float().contiguous()
+                _conv(_lib.CONV3, t, w2, b2, None, co, L, head=(hw, m10.bias.detach().float().contiguous(), out),
+                      resid_nchw=x if self.res else None)
+            else:
+                w10, b10 = self._packed("conv10_1")
+                _conv(_lib.CONV1, cur, w10, b10, out, self.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,
+                      resid_nchw=x if self.res else None)
         return out
 
 

@@ -25,13 +25,14 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "abi_common.h"
 #include "../../include/pnnp_b200.h"
 
 namespace pnnp {
 
 constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSpinLimit = 1u << 27;      // ~ seconds; a broken pipeline terminates instead of hanging the GPU
 
@@ -49,11 +50,18 @@ struct ConvParams {
     int cout_stride;                // channel stride of the NHWC output (>= cout)
     int act, out_mode;
     int stages, stage_bytes, a_bytes, b_tap_stride;
+    int b_resident;                 // all taps x K chunks of the weights stay in smem for the whole kernel
+    int b_res_bytes;
     int tmem_cols;
     const float* bias;              // [cout] or null
     void* out;
     const __nv_bfloat16* resid;     // NHWC bf16 residual with the output's geometry, or null
-    const float* resid_nchw;        // NCHW fp32 residual for OUT_NCHW_F32, or null
+    const float* resid_nchw;        // NCHW fp32 residual for OUT_NCHW_F32 / the fused head, or null
+    __nv_bfloat16* pool_out;        // optional fused 2x2 max-pool output (NHWC bf16, H/2 x W/2)
+    const float* head_w;            // optional fused 1x1 head: [head_cout][cout] fp32 weights
+    const float* head_b;            // [head_cout]
+    float* head_out;                // NCHW fp32, head_cout <= 4 planes
+    int head_cout;
     int* err;
 };
 
@@ -155,13 +163,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x stage_bytes] [barriers] [tmem slot] [bias]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint8_t* smem_bres = smem + (size_t)p.stages * p.stage_bytes;          // resident weights (1024-aligned), may be empty
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bres + p.b_res_bytes);
     uint64_t* full_bar = bars;                       // [stages]
     uint64_t* empty_bar = bars + kMaxStages;         // [stages]
     uint64_t* tfull_bar = bars + 2 * kMaxStages;     // [2]
     uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    uint64_t* bres_bar = bars + 2 * kMaxStages + 4;    // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+    float* s_head_w = s_bias + p.cout;            // [cout][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int taps_per_stage = TPS;
@@ -169,15 +180,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int chunks0 = p.cin0 / p.kc, chunks1 = p.nsrc > 1 ? p.cin1 / p.kc : 0;
     const int ksteps = (chunks0 + chunks1) * dx_count;
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
-    const uint32_t stage_tx = (uint32_t)(p.a_bytes + taps_per_stage * p.umma_n * p.swz);
+    const uint32_t stage_tx = (uint32_t)(p.a_bytes + (p.b_resident ? 0 : taps_per_stage * p.umma_n * p.swz));
+    const int taps_total = p.mode == MODE_CONV3 ? 9 : (p.mode == MODE_CONV3S2 ? 9 : 1);
 
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (p.head_out)
+        for (int i = threadIdx.x; i < 4 * p.cout; i += blockDim.x)      // [channel][4 outputs], zero beyond head_cout
+            s_head_w[i] = (i & 3) < p.head_cout ? p.head_w[(i & 3) * p.cout + (i >> 2)] : 0.f;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+        mbar_init(smem_u32(bres_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -196,6 +212,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         // ============================== TMA producer ==============================
         uint32_t stage = 0, phase = 0;
         const int halo = p.mode == MODE_CONV3 ? 1 : 0;
+        if (p.b_resident && elect_one()) {
+            // weights for every (K chunk, tap) once per CTA: layout [chunk][tap][umma_n rows x swz bytes]
+            const uint32_t bb = smem_u32(bres_bar);
+            mbar_expect_tx(bb, (uint32_t)((chunks0 + chunks1) * taps_total * p.umma_n * p.swz));
+            for (int ch = 0; ch < chunks0 + chunks1; ++ch)
+                for (int tap = 0; tap < taps_total; ++tap)
+                    tma_load_3d(smem_u32(smem_bres) + (ch * taps_total + tap) * p.b_tap_stride, &tmB, bb, ch * p.kc, 0, tap);
+        }
+        __syncwarp();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             int r = t;
             const int n_tile = r % p.n_tiles; r /= p.n_tiles;
@@ -203,7 +228,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const int ty = r % p.tiles_y; r /= p.tiles_y;
             const int img = r;
             const int x0 = tx * kTileW, y0 = ty * kTileH;
-            const int n_off = p.mode == MODE_CONVT ? 0 : n_tile * p.umma_n;
+            const int n_off = n_tile * p.umma_n;
             int chunk = 0, dx = 0;
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int src = chunk >= chunks0 ? 1 : 0;
@@ -219,9 +244,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx % 3) - 1, 2 * y0 + (dx / 3) - 1, img);
                     else
                         tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - halo, img);
-                    for (int dy = 0; dy < taps_per_stage; ++dy) {
+                    for (int dy = 0; dy < (p.b_resident ? 0 : taps_per_stage); ++dy) {
                         const int tap = p.mode == MODE_CONV3 ? dy * 3 + dx
-                                      : (p.mode == MODE_CONVT ? n_tile : (p.mode == MODE_CONV3S2 ? dx : 0));
+                                      : (p.mode == MODE_CONV3S2 ? dx : 0);
                         tma_load_3d(sb + dy * p.b_tap_stride, &tmB, fb, cin_off, n_off, tap);
                     }
                 }
@@ -238,8 +263,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const uint32_t a_tap_stride = (uint32_t)(kTileW * p.swz) >> 4;      // descriptor units (16 B)
         const uint32_t b_tap_stride = (uint32_t)p.b_tap_stride >> 4;
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0, p.err, 105);
+        const int dxc = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : 1);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 102);
+            int chunk = 0, dx = 0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.umma_n;
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -247,9 +275,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
                 const uint64_t adesc0 = dhi | (uint64_t)((sa >> 4) & 0x3FFFu);
-                const uint64_t bdesc0 = dhi | (uint64_t)(((sa + p.a_bytes) >> 4) & 0x3FFFu);
+                // resident layout [chunk][tap]: CONV3 stage dx uses taps dy*3+dx (stride 3 taps); S2 stage uses tap dx
+                const uint32_t sb = p.b_resident
+                    ? smem_u32(smem_bres) + (uint32_t)((chunk * taps_total + dx) * p.b_tap_stride)
+                    : sa + p.a_bytes;
+                const uint64_t bdesc0 = dhi | (uint64_t)((sb >> 4) & 0x3FFFu);
+                const uint32_t b_stride_eff = (p.b_resident && p.mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;
+                if (++dx == dxc) { dx = 0; ++chunk; }
                 if (elect_one()) {
-                    issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_tap_stride, idesc, ks != 0);
+                    issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
                     tc_commit(smem_u32(&empty_bar[stage]));              // frees the smem slot when these MMAs retire
                 }
                 __syncwarp();
@@ -262,12 +296,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
     } else {
         // ============================== epilogue (warps 2..5) ==============================
+        // Two epilogue groups of four warps: group g drains accumulator buffer g, i.e. every other tile of
+        // this CTA, so two tiles' epilogues overlap each other and the next tile's MMAs.
+        const int group = (warp - 2) >> 2;
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
         const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
         const int ty_in = m / kTileW, tx_in = m % kTileW;
-        uint32_t acc = 0, acc_phase = 0;
+        const uint32_t acc = (uint32_t)group;
+        uint32_t acc_phase = 0;
         const int chunks16 = p.umma_n / 16;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x + group * gridDim.x; t < total_tiles; t += 2 * gridDim.x) {
             int r = t;
             const int n_tile = r % p.n_tiles; r /= p.n_tiles;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
@@ -278,27 +316,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * (uint32_t)p.umma_n + ((uint32_t)(quad * 32) << 16);
-            size_t opix;            // output pixel index
-            int col0;               // first output channel of this tile
-            if (p.mode == MODE_CONVT) {
-                const int a = n_tile >> 1, b = n_tile & 1;
-                opix = ((size_t)img * (2 * p.H) + (2 * y + a)) * (size_t)(2 * p.W) + (2 * x + b);
-                col0 = 0;
-            } else {
-                opix = ((size_t)img * p.H + y) * (size_t)p.W + x;
-                col0 = n_tile * p.umma_n;
-            }
+            const int col_tile0 = n_tile * p.umma_n;     // first GEMM column of this tile
+            const size_t pix_in = ((size_t)img * p.H + y) * (size_t)p.W + x;
+            float head[4] = {0.f, 0.f, 0.f, 0.f};
             for (int j = 0; j < chunks16; ++j) {
                 uint32_t v[16];
                 tc_ld16(taddr + j * 16, v);
                 tc_ld_wait();
-                const int c0 = col0 + j * 16;
-                if (!valid || c0 >= p.cout) continue;
+                int c0 = col_tile0 + j * 16;              // output channel of v[0]
+                size_t opix = pix_in;
+                if (p.mode == MODE_CONVT) {               // GEMM column = (a*2+b)*cout + co  ->  pixel (2y+a, 2x+b)
+                    const int tap = c0 / p.cout;
+                    c0 -= tap * p.cout;
+                    opix = ((size_t)img * (2 * p.H) + (2 * y + (tap >> 1))) * (size_t)(2 * p.W) + (2 * x + (tap & 1));
+                }
+                if (c0 >= p.cout) continue;               // zero-padded weight rows (warp-uniform)
                 float f[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) f[i] = apply_act(__uint_as_float(v[i]) + s_bias[min(c0 + i, p.cout - 1)], p.act);
                 if (p.out_mode == OUT_NHWC_BF16) {
-                    if (p.resid) {
+                    if (p.resid && valid) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.resid + opix * p.cout_stride + c0);
                         const uint4 r0 = rp[0], r1 = rp[1];
                         const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -314,10 +351,41 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                         pk[i] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0);
-                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                } else {
+                    if (p.out && valid) {
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0);
+                        op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                    if (p.pool_out) {
+                        // fused nn.MaxPool2d(2): lanes l^1 hold the x-neighbour, l^16 the y-neighbour of the same tile
+                        // (a warp owns two 16-pixel tile rows); max of bf16-rounded values == rounding of the max
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+                            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+                            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o1));
+                            uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
+                            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, 16);
+                            a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
+                            pk[i] = *reinterpret_cast<uint32_t*>(&a);
+                        }
+                        if (valid && !(lane & 1) && !(lane & 16)) {
+                            const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
+                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pp * p.cout_stride + c0);
+                            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                    }
+                    if (p.head_out) {
+                        // fused 1x1 head (conv10_1, Unet.py:93): 4 dot products over this pixel's channels, fp32
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(&s_head_w[(c0 + i) * 4]);
+                            head[0] = fmaf(f[i], w4.x, head[0]); head[1] = fmaf(f[i], w4.y, head[1]);
+                            head[2] = fmaf(f[i], w4.z, head[2]); head[3] = fmaf(f[i], w4.w, head[3]);
+                        }
+                    }
+                } else if (valid) {
                     float* o = reinterpret_cast<float*>(p.out);
                     const size_t plane = (size_t)p.H * p.W;
                     for (int i = 0; i < 16 && c0 + i < p.cout; ++i) {
@@ -326,11 +394,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     }
                 }
             }
+            if (p.head_out && valid) {
+                const size_t plane = (size_t)p.H * p.W;
+                for (int o = 0; o < p.head_cout; ++o) {
+                    const size_t oi = ((size_t)img * p.head_cout + o) * plane + (size_t)y * p.W + x;
+                    p.head_out[oi] = head[o] + p.head_b[o] + (p.resid_nchw ? p.resid_nchw[oi] : 0.f);
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            acc_phase ^= 1;
         }
     }
     tc_fence_before();
@@ -440,24 +514,39 @@ static int make_w_map(CUtensorMap* tm, const void* ptr, int taps, int rows, int 
 
 static int* g_err_dev = nullptr;     // device word the kernels report pipeline time-outs into
 
-int conv_layer_launch(int mode, const void* in0, int cin0, const void* in1, int cin1, const void* weight, int w_rows,
-                      const float* bias, void* out, int cout, int cout_stride, int n, int h, int w, int act, int out_mode,
-                      const void* resid, const float* resid_nchw, cudaStream_t st) {
-    if (!in0 || !weight || !out) return fail("conv: null pointer");
+int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
+    const int mode = d.mode, cin0 = d.cin0, cin1 = d.cin1, cout = d.cout, cout_stride = d.cout_stride, n = d.n, act = d.act,
+              out_mode = d.out_mode, w_rows = d.w_rows;
+    int h = d.h, w = d.w;
+    const void *in0 = d.in0, *in1 = d.in1, *weight = d.weight, *resid = d.resid;
+    const float *bias = d.bias, *resid_nchw = d.resid_nchw;
+    void* out = d.out;
+    if (!in0 || !weight || (!out && !d.head_out)) return fail("conv: null pointer");
     if (cin0 % 16 || cin1 % 16) return fail("conv: channel counts must be multiples of 16");
     const int nsrc = in1 ? 2 : 1;
     int kc = 64;
     while (kc > 16 && ((cin0 % kc) || (nsrc > 1 && (cin1 % kc)))) kc >>= 1;
     int umma_n, n_tiles;
-    if (mode == MODE_CONVT) { umma_n = cout; n_tiles = 4; if (cout % 16 || cout > 256) return fail("convT: cout must be a multiple of 16, <= 256"); }
+    if (mode == MODE_CONVT) {
+        // one GEMM with N = 4*cout columns ((a*2+b)*cout + co), tiled by <= 256 columns
+        if (cout % 16) return fail("convT: cout must be a multiple of 16");
+        umma_n = std::min(4 * cout, 256);
+        if ((4 * cout) % umma_n) return fail("convT: 4*cout must be <= 256 or a multiple of 256");
+        n_tiles = 4 * cout / umma_n;
+    }
     else {
         const int cpad = (cout + 15) / 16 * 16;
         umma_n = std::min(cpad, 256);
         if (cpad % umma_n) return fail("conv: cout must be <= 256 or a multiple of 256");
         n_tiles = cpad / umma_n;
     }
+    if (d.pool_out && (mode == MODE_CONVT || out_mode != OUT_NHWC_BF16 || (h & 1) || (w & 1)))
+        return fail("conv: fused max-pool needs an NHWC bf16 output with even h, w");
+    if (d.head_out && (n_tiles != 1 || out_mode != OUT_NHWC_BF16 || d.head_cout < 1 || d.head_cout > 4 || mode == MODE_CONVT ||
+                       !d.head_w || !d.head_b || cout > 64))
+        return fail("conv: fused 1x1 head needs a single N tile, cout <= 64 and 1..4 head channels");
     if (out_mode == OUT_NHWC_BF16 && (cout % 16)) return fail("conv: NHWC output needs cout % 16 == 0");
-    if (w_rows < (mode == MODE_CONVT ? cout : n_tiles * umma_n)) return fail("conv: weight tensor has too few rows");
+    if (mode == MODE_CONVT ? (w_rows != cout) : (w_rows < n_tiles * umma_n)) return fail("conv: weight tensor has the wrong number of rows");
     const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : (mode == MODE_CONVT ? 4 : 1);
     if (mode == MODE_CONV3S2 && (nsrc > 1 || (h & 1) || (w & 1))) return fail("stride-2 conv: single source, even h and w");
     const int in_h = h, in_w = w;
@@ -465,15 +554,25 @@ int conv_layer_launch(int mode, const void* in0, int cin0, const void* in1, int 
     const int tps = mode == MODE_CONV3 ? 3 : 1;
     const int box_h = mode == MODE_CONV3 ? kTileH + 2 : kTileH;
     // shrink the K chunk until at least 3 pipeline stages fit
-    int swz, a_bytes, b_tap_stride, stage_bytes, stages;
-    const int smem_budget = 227 * 1024 - 4096;
+    int swz, a_bytes, b_tap_stride, stage_bytes, stages, b_resident = 0, b_res_bytes = 0;
+    const int smem_budget = 227 * 1024 - 4096 - cout * 20;
+    const int cin_total = cin0 + (nsrc > 1 ? cin1 : 0);
+    {
+        // weights resident in smem when all taps x chunks fit beside >= 3 A-only stages (single N tile, not convT)
+        const int swz_r = kc * 2, bts = (umma_n * swz_r + 1023) / 1024 * 1024;
+        const int res_bytes = (cin_total / kc) * taps * bts;
+        const int a_only = (box_h * kTileW * swz_r + 1023) / 1024 * 1024;
+        if (mode != MODE_CONVT && n_tiles == 1 && res_bytes + 3 * a_only <= smem_budget && !getenv("PNNP_NO_RESIDENT_W")) {
+            b_resident = 1; b_res_bytes = res_bytes;
+        }
+    }
     for (;; kc >>= 1) {
         swz = kc * 2;
         a_bytes = box_h * kTileW * swz;
         b_tap_stride = (umma_n * swz + 1023) / 1024 * 1024;
-        stage_bytes = (a_bytes + tps * b_tap_stride + 1023) / 1024 * 1024;
-        stages = std::min(kMaxStages, smem_budget / stage_bytes);
-        if (stages >= 3 || kc == 16) break;
+        stage_bytes = ((b_resident ? a_bytes : a_bytes + tps * b_tap_stride) + 1023) / 1024 * 1024;
+        stages = std::min(kMaxStages, (smem_budget - b_res_bytes) / stage_bytes);
+        if (stages >= 3 || kc == 16 || b_resident) break;
     }
     if (stages < 2) return fail("conv: tile does not fit in shared memory");
     ConvParams p{};
@@ -482,22 +581,26 @@ int conv_layer_launch(int mode, const void* in0, int cin0, const void* in1, int 
     p.umma_n = umma_n; p.nsrc = nsrc; p.cin0 = cin0; p.cin1 = nsrc > 1 ? cin1 : 0; p.kc = kc; p.swz = swz;
     p.cout = cout; p.cout_stride = cout_stride; p.act = act; p.out_mode = out_mode;
     p.stages = stages; p.stage_bytes = stage_bytes; p.a_bytes = a_bytes; p.b_tap_stride = b_tap_stride;
+    p.b_resident = b_resident; p.b_res_bytes = b_res_bytes;
     int tc = 32; while (tc < 2 * umma_n) tc <<= 1;
     p.tmem_cols = tc;
     p.bias = bias; p.out = out; p.resid = static_cast<const __nv_bfloat16*>(resid); p.resid_nchw = resid_nchw;
+    p.pool_out = static_cast<__nv_bfloat16*>(d.pool_out);
+    p.head_w = d.head_w; p.head_b = d.head_b; p.head_out = d.head_out; p.head_cout = d.head_out ? d.head_cout : 0;
     if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
     p.err = g_err_dev;
     CUtensorMap tmA0, tmA1, tmB;
     if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, mode == MODE_CONV3S2 ? 2 : 1)) return e;
     if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz)) return e; }
     else tmA1 = tmA0;
-    if (int e = make_w_map(&tmB, weight, taps, w_rows, cin0 + (nsrc > 1 ? cin1 : 0), kc, umma_n, swz)) return e;
+    if (mode == MODE_CONVT) { if (int e = make_w_map(&tmB, weight, 1, 4 * cout, cin0, kc, umma_n, swz)) return e; }
+    else if (int e = make_w_map(&tmB, weight, taps, w_rows, cin0 + (nsrc > 1 ? cin1 : 0), kc, umma_n, swz)) return e;
     int dev = 0, sms = 0;
     PNNP_CUDA(cudaGetDevice(&dev));
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int total_tiles = n * p.tiles_y * p.tiles_x * n_tiles;
     const int grid = std::min(total_tiles, sms);
-    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16 + (size_t)cout * 4 + 64;
+    const size_t smem = (size_t)stages * stage_bytes + b_res_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 16 + (size_t)cout * 4 * 5 + 64;
     if (smem > 227 * 1024) return fail("conv: shared memory budget exceeded");
     static bool attr_done = false;
 #define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1) X(3, 2) X(3, 4) X(1, 1) X(1, 2) X(1, 4)
@@ -525,8 +628,16 @@ using namespace pnnp;
 extern "C" int pnnp_conv2d_tc(int mode, const void* in0, int cin0, const void* in1, int cin1, const void* weight, int w_rows,
                               const float* bias, void* out, int cout, int cout_stride, int n, int h, int w, int act,
                               int out_mode, const void* resid, const float* resid_nchw, void* stream) {
-    return conv_layer_launch(mode, in0, cin0, in1, cin1, weight, w_rows, bias, out, cout, cout_stride, n, h, w, act, out_mode,
-                             resid, resid_nchw, (cudaStream_t)stream);
+    pnnp_conv_desc d{};
+    d.mode = mode; d.act = act; d.out_mode = out_mode; d.n = n; d.h = h; d.w = w;
+    d.in0 = in0; d.cin0 = cin0; d.in1 = in1; d.cin1 = cin1; d.weight = weight; d.w_rows = w_rows; d.bias = bias;
+    d.out = out; d.cout = cout; d.cout_stride = cout_stride; d.resid = resid; d.resid_nchw = resid_nchw;
+    return conv_layer_launch(d, (cudaStream_t)stream);
+}
+
+extern "C" int pnnp_conv2d_tc_ex(const pnnp_conv_desc* desc, void* stream) {
+    if (!desc) return fail("conv2d_tc_ex: null descriptor");
+    return conv_layer_launch(*desc, (cudaStream_t)stream);
 }
 
 extern "C" int pnnp_conv_pipeline_error(void) {

@@ -17,6 +17,9 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # fp32 references must be true fp32 (cuDNN / cuBLAS default to TF32 for fp32 convs / matmuls on this GPU)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

@@ -216,3 +216,25 @@ def test_resunet_state_dict_is_reference_compatible(golden):
     net = P.ResUnet(arch)
     assert list(net.state_dict().keys()) == ref_keys
     assert sum(p.numel() for p in P.ResUnet(_arch()).parameters()) == 11075268
+
+
+def test_fused_pool_and_head_epilogues():
+    """conv + LeakyReLU + MaxPool2d(2) and conv + LeakyReLU + 1x1 head (+ residual) fused in the epilogue."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn((2, 32, 24, 48), device="cuda", generator=g)
+    wt = torch.randn((32, 32, 3, 3), device="cuda", generator=g) / 17
+    b = torch.randn((32,), device="cuda", generator=g) * 0.1
+    out = torch.empty((2, 24, 48, 32), dtype=torch.bfloat16, device="cuda")
+    pooled = torch.empty((2, 12, 24, 32), dtype=torch.bfloat16, device="cuda")
+    archs._conv(_lib.CONV3, _nhwc(x), _pack(wt), b, out, 32, _lib.ACT_LEAKY, pool_out=pooled)
+    _no_pipeline_error()
+    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(out), 2))
+    hw = torch.randn((4, 32), device="cuda", generator=g) / 6
+    hb = torch.randn((4,), device="cuda", generator=g) * 0.1
+    res = torch.randn((2, 4, 24, 48), device="cuda", generator=g)
+    hout = torch.empty((2, 4, 24, 48), dtype=torch.float32, device="cuda")
+    archs._conv(_lib.CONV3, _nhwc(x), _pack(wt), b, None, 32, _lib.ACT_LEAKY, head=(hw, hb, hout), resid_nchw=res)
+    _no_pipeline_error()
+    act = F.leaky_relu(F.conv2d(_bf(x), _bf(wt), b, padding=1), 0.2)
+    ref = F.conv2d(act, hw.view(4, 32, 1, 1), hb) + res
+    assert (hout - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
