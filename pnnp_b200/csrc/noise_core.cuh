@@ -53,12 +53,44 @@ __device__ __forceinline__ float u01_24_closed0(uint32_t w) { return (float)(w >
 // (0,1] ∩ float32 from all 32 bits: relative precision kept near 0 (tails)
 __device__ __forceinline__ float u01_32(uint32_t w) { return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 
-// standard normal from two words (Box–Muller, cosine branch)
-__device__ __forceinline__ float normal_bm(uint32_t w0, uint32_t w1) {
-    const float u1 = u01_32(w0);
-    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
-    const float th = (u01_24_closed0(w1) - 0.5f) * 6.283185307179586f;
-    return r * __cosf(th);
+// ------------------------------------------------------------------------------------------
+// Standard normal by inversion of ONE 32-bit word: z = Phi^-1((w + 0.5) / 2^32).
+// The smaller tail probability p = (min(w, ~w) + 0.5) / 2^32 in (0, 0.5] is formed exactly, so both
+// tails keep relative precision down to 2^-33.  With t = -log2(4 p (1-p)):
+//   central (t < 8.25, p > ~8e-4): erfinv(x) = x * P7(t),  x = 1 - 2p
+//   tail                          : erfinv(x) = Q6(sqrt(t))
+// Coefficients: Chebyshev-node least-squares fits, tools/fit_normal_icdf.py (max |error| 1.3e-6 in z
+// for the float32 evaluation, checked there against scipy.special.ndtri).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float normal_icdf(uint32_t w) {
+    const bool lower = w < 0x80000000u;
+    const uint32_t m = lower ? w : ~w;
+    const float p = fmaf((float)m, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float t = -__log2f(4.0f * p * (1.0f - p));
+    float e;
+    if (t < 8.25f) {
+        float q = 2.674857846e-08f;
+        q = fmaf(q, t, -1.025935489e-06f);
+        q = fmaf(q, t, 1.418562169e-05f);
+        q = fmaf(q, t, -4.943624299e-05f);
+        q = fmaf(q, t, -7.453467697e-04f);
+        q = fmaf(q, t, 5.522758700e-03f);
+        q = fmaf(q, t, 1.608277857e-01f);
+        q = fmaf(q, t, 8.862264752e-01f);
+        e = q * (1.0f - 2.0f * p);
+    } else {
+        const float s = sqrtf(t);
+        float q = 7.718497727e-06f;
+        q = fmaf(q, s, -2.602138266e-04f);
+        q = fmaf(q, s, 3.719373606e-03f);
+        q = fmaf(q, s, -2.902236022e-02f);
+        q = fmaf(q, s, 1.309477687e-01f);
+        q = fmaf(q, s, 5.167053342e-01f);
+        q = fmaf(q, s, 1.426639557e-01f);
+        e = q;
+    }
+    const float z = 1.4142135623730951f * e;
+    return lower ? -z : z;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -77,15 +109,20 @@ __device__ __forceinline__ float tukey_lambda_ppf(uint32_t w, float lam, float i
 }
 
 // ------------------------------------------------------------------------------------------
-// Poisson sampler.  lam < 10: inversion by sequential search on one uniform;
-// lam >= 10: Hörmann's transformed rejection with squeeze (PTRS, Insurance: Math. & Econ. 12, 1993).
-// Same two algorithms NumPy's legacy RandomState.poisson (the reference's sampler) chooses
-// between at the same threshold; the draws come from Philox instead of MT19937.
-// smem: s_inv[k] = 1/k (k = 1..63), s_lfact[k] = ln k! (k = 0..15)
+// Poisson sampler: inversion of ONE uniform word (no rejection loop, no per-lane retry divergence).
+//   lam <  10 : exact inversion by sequential search of the CDF from k = 0 (the index k is
+//               warp-uniform, so 1/k comes from the constant bank as a broadcast);
+//   lam >= 10 : k = floor(Q(z)), z = Phi^-1(u), with the third-order Cornish-Fisher expansion of the
+//               Poisson quantile including the continuity correction (Giles, "Algorithm 955:
+//               approximation of the inverse Poisson CDF", ACM TOMS 42, 2016, eq. Q_N):
+//                 Q = lam + sqrt(lam) z + (1/3 + z^2/6) + (-z/36 - z^3/72)/sqrt(lam)
+//                       + (-8/405 + 7 z^2/810 + z^4/270)/lam
+//               Its CDF differs from the exact Poisson CDF by at most 4.7e-5 at lam = 10, 3.9e-6 at 32,
+//               < 1e-6 from 64 up (tests/test_poisson_model.py evaluates this against scipy on a grid);
+//               a KS test needs ~1e9 samples at one rate to see it.  NumPy's legacy sampler (the
+//               reference's) switches algorithm at the same lam = 10.
 // ------------------------------------------------------------------------------------------
-constexpr int kInvTab = 64, kLfactTab = 16;
-// 1/k for the sequential search: every active lane is at the same k, so the index is warp-uniform
-// and the constant-bank read is a broadcast.
+constexpr int kInvTab = 64;
 __constant__ float c_inv_k[kInvTab] = {
     0.f, 1.f / 1, 1.f / 2, 1.f / 3, 1.f / 4, 1.f / 5, 1.f / 6, 1.f / 7, 1.f / 8, 1.f / 9, 1.f / 10, 1.f / 11, 1.f / 12,
     1.f / 13, 1.f / 14, 1.f / 15, 1.f / 16, 1.f / 17, 1.f / 18, 1.f / 19, 1.f / 20, 1.f / 21, 1.f / 22, 1.f / 23,
@@ -93,19 +130,20 @@ __constant__ float c_inv_k[kInvTab] = {
     1.f / 35, 1.f / 36, 1.f / 37, 1.f / 38, 1.f / 39, 1.f / 40, 1.f / 41, 1.f / 42, 1.f / 43, 1.f / 44, 1.f / 45,
     1.f / 46, 1.f / 47, 1.f / 48, 1.f / 49, 1.f / 50, 1.f / 51, 1.f / 52, 1.f / 53, 1.f / 54, 1.f / 55, 1.f / 56,
     1.f / 57, 1.f / 58, 1.f / 59, 1.f / 60, 1.f / 61, 1.f / 62, 1.f / 63};
+constexpr float kPoissonSwitch = 10.0f;
 
-__device__ __forceinline__ void init_poisson_tables(float* s_inv, float* s_lfact) {
-    for (int i = threadIdx.x; i < kInvTab; i += blockDim.x) s_inv[i] = i ? 1.0f / (float)i : 0.f;
-    if (threadIdx.x == 0) {
-        double acc = 0.0;
-        s_lfact[0] = 0.f;
-        for (int k = 1; k < kLfactTab; ++k) { acc += log((double)k); s_lfact[k] = (float)acc; }
-    }
+__device__ __forceinline__ float poisson_large(float lam, uint32_t w) {
+    const float z = normal_icdf(w);
+    const float rs = rsqrtf(lam), s = lam * rs, z2 = z * z;
+    float x = fmaf(s, z, lam);
+    x += fmaf(z2, 0.16666667f, 0.33333334f);
+    x = fmaf(-z * fmaf(z2, 0.013888889f, 0.027777778f), rs, x);
+    x = fmaf(fmaf(z2, fmaf(z2, 0.0037037036f, 0.008641975f), -0.019753087f), rs * rs, x);
+    return fmaxf(floorf(x), 0.f);
 }
 
-__device__ __forceinline__ float poisson_small(float lam, uint32_t w, const float* s_inv) {
-    const float u = u01_24(w);
-    (void)s_inv;
+__device__ __forceinline__ float poisson_small(float lam, uint32_t w) {
+    const float u = fminf(u01_32(w), 0.99999994f);
     float p = __expf(-lam), F = p;
     int k = 0;
     while (u > F && k < kInvTab - 1) {
@@ -116,48 +154,9 @@ __device__ __forceinline__ float poisson_small(float lam, uint32_t w, const floa
     return (float)k;
 }
 
-__device__ __forceinline__ float poisson_ptrs(float lam, uint32_t w0, uint32_t w1, const RngCtx& rng,
-                                              uint64_t index, const float* s_lfact) {
-    const float slam = sqrtf(lam);
-    const float ln_lam = __logf(lam);
-    const float b = 0.931f + 2.53f * slam;
-    const float a = -0.059f + 0.02483f * b;
-    const float inv_alpha = 1.1239f + __fdividef(1.1328f, b - 3.4f);
-    const float vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
-    uint32_t wu = w0, wv = w1;
-    uint4 blk = make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-    for (int t = 0; t < 64; ++t) {
-        if (t > 0) {
-            if (t & 1) { blk = rng.block(index, kStreamElem, 2u + (uint32_t)(t >> 1)); wu = blk.x; wv = blk.y; }
-            else       { wu = blk.z; wv = blk.w; }
-        }
-        const float U = u01_24(wu) - 0.5f;
-        const float V = u01_24(wv);
-        const float us = 0.5f - fabsf(U);
-        const float kf = floorf((__fdividef(2.0f * a, us) + b) * U + lam + 0.43f);
-        if (us >= 0.07f && V <= vr) return kf;
-        if (kf < 0.f || (us < 0.013f && V > us)) continue;
-        const float lhs = __logf(V * inv_alpha / (__fdividef(a, us * us) + b));
-        float rhs;
-        if (kf < (float)kLfactTab) {
-            rhs = -lam + kf * ln_lam - s_lfact[(int)kf];
-        } else {
-            // ln pmf in a cancellation-free form: k ln(lam/k) + (k - lam) - ln sqrt(2 pi k) - Stirling tail
-            const float ik = __fdividef(1.0f, kf);
-            rhs = kf * __logf(lam * ik) + (kf - lam) - 0.5f * __logf(6.283185307179586f * kf)
-                  - ik * (0.083333333f - 0.0027777778f * ik * ik);
-        }
-        if (lhs <= rhs) return kf;
-    }
-    return floorf(lam + 0.5f);   // unreachable in practice (rejection probability^64)
-}
-
-__device__ __forceinline__ float poisson_sample(float lam, uint32_t w0, uint32_t w1, const RngCtx& rng,
-                                                uint64_t index, const float* s_inv, const float* s_lfact) {
+__device__ __forceinline__ float poisson_sample(float lam, uint32_t w) {
     if (!(lam > 0.f)) return 0.f;
-    if (lam < 10.f) return poisson_small(lam, w0, s_inv);
-    return poisson_ptrs(lam, w0, w1, rng, index, s_lfact);
+    return lam < kPoissonSwitch ? poisson_small(lam, w) : poisson_large(lam, w);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -32,40 +32,50 @@ struct SynthArgs {
 constexpr int kSeg = 512;          // elements per warp work unit
 constexpr int kThreads = 256;
 
-// One element, Philox mode.  Returns the noisy value; optionally records the draws.
-template <int CHAIN, bool DEBUG>
-__device__ __forceinline__ float synth_one(float y, uint64_t gidx, size_t lidx, int crop, int ch, const RowP& p,
-                                           const SynthArgs& a, const RngCtx& rng, float rowz, float lam_tl,
-                                           float inv_lam_tl, const float* s_inv, const float* s_lfact) {
-    const uint32_t code = a.code;
-    const uint4 w = rng.block(gidx, kStreamElem, 0u);
-    uint4 w2 = make_uint4(0, 0, 0, 0);
-    const bool need_normals = !(code & PNNP_CODE_P) || (!(code & PNNP_CODE_G) && !(code & PNNP_CODE_B));
-    if (need_normals) w2 = rng.block(gidx, kStreamElem, 1u);
+// Draw layout.  Elements are grouped in fours by GLOBAL element index g (crop_id0 * c*h*w + local index);
+// group G = g >> 2 owns three Philox blocks (sub = 0,1,2) = 12 words, and element e = g & 3 uses words
+// 3e, 3e+1, 3e+2 as (shot, read, quantisation).  Every draw is an inversion of exactly one word, so no
+// mode needs more than three words per element and nothing depends on thread/grid shape or on W % 4.
+struct GroupWords { uint32_t w[12]; };
+__device__ __forceinline__ GroupWords group_words(const RngCtx& rng, uint64_t group) {
+    GroupWords g;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const uint4 b = rng.block(group, kStreamElem, (uint32_t)s);
+        g.w[4 * s] = b.x; g.w[4 * s + 1] = b.y; g.w[4 * s + 2] = b.z; g.w[4 * s + 3] = b.w;
+    }
+    return g;
+}
 
+// One element given its three words.  Returns the noisy value; optionally records the draws.
+template <int CHAIN, bool DEBUG>
+__device__ __forceinline__ float synth_one(float y, uint32_t w_shot, uint32_t w_read, uint32_t w_q, size_t lidx, int crop,
+                                           int ch, const RowP& p, const SynthArgs& a, float rowz, float lam_tl,
+                                           float inv_lam_tl) {
+    const uint32_t code = a.code;
     float lam, d_shot;
     ScaleIn s;
     if (CHAIN == PNNP_CHAIN_NUMPY) { s = scale_in_numpy(y, p); lam = poisson_rate_numpy(s, p); }
     else { s.ysc32 = scale_in_torch(y, p); s.ysc64 = 0.0; lam = __fdiv_rn(s.ysc32, (float)p.K); }
-    if (code & PNNP_CODE_P) d_shot = poisson_sample(lam, w.x, w.y, rng, gidx, s_inv, s_lfact);
-    else d_shot = normal_bm(w2.z, w2.w);
+    if (code & PNNP_CODE_P) d_shot = poisson_sample(lam, w_shot);
+    else d_shot = normal_icdf(w_shot);
 
     float d_read = 0.f;
     if (!(code & PNNP_CODE_B)) {
         if ((code & PNNP_CODE_G) && CHAIN == PNNP_CHAIN_NUMPY)
-            d_read = tukey_lambda_ppf(w.z, lam_tl, inv_lam_tl) * (float)p.sigTL;
+            d_read = tukey_lambda_ppf(w_read, lam_tl, inv_lam_tl) * (float)p.sigTL;
         else
-            d_read = normal_bm(w2.x, w2.y) * (float)p.sigGs;
+            d_read = normal_icdf(w_read) * (float)p.sigGs;
     }
     float out;
     double dq = 0.0;
     if (CHAIN == PNNP_CHAIN_NUMPY) {
         // numpy: uniform(-0.5, 0.5) is float64; (w + 0.5) * 2^-32 - 0.5 is exact in float64
-        if (code & PNNP_CODE_Q) dq = fma((double)w.w, 2.3283064365386963e-10, 1.1641532182693481e-10) - 0.5;
+        if (code & PNNP_CODE_Q) dq = fma((double)w_q, 2.3283064365386963e-10, 1.1641532182693481e-10) - 0.5;
         const double bias_c = (code & PNNP_CODE_D) ? a.table[crop].bias[ch & 3] : 0.0;
         out = tail_numpy(y, p, code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, dq, bias_c);
     } else {
-        const float qu = u01_24_closed0(w.w);
+        const float qu = u01_24_closed0(w_q);
         dq = (double)qu;
         out = tail_torch(p, code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, qu);
     }
@@ -80,11 +90,6 @@ __device__ __forceinline__ float synth_one(float y, uint64_t gidx, size_t lidx, 
 
 template <int CHAIN, bool DEBUG, int VEC>
 __global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArgs a) {
-    __shared__ float s_inv[kInvTab];
-    __shared__ float s_lfact[kLfactTab];
-    init_poisson_tables(s_inv, s_lfact);
-    __syncthreads();
-
     const int lane = threadIdx.x & 31;
     const long long warps_total = (long long)gridDim.x * (kThreads / 32);
     const long long warp_id = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -107,9 +112,9 @@ __global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArg
         const float inv_lam_tl = lam_tl != 0.f ? 1.0f / lam_tl : 0.f;
         float rowz = 0.f;
         if (a.code & PNNP_CODE_R) {
+            // keyed on the global (crop, channel, row) index: identical in every lane / warp that touches the row
             const uint64_t grow = a.crop_id0 * (uint64_t)a.c * a.h + (uint64_t)row;
-            const uint4 wr = rng.block(grow, kStreamRow, 0u);
-            rowz = normal_bm(wr.x, wr.y);
+            rowz = normal_icdf(rng.block(grow, kStreamRow, 0u).x);
             if (DEBUG && a.d_rowz && seg == 0 && lane == 0) a.d_rowz[row] = rowz;
         }
         const size_t row_base = (size_t)row * a.w;
@@ -121,19 +126,26 @@ __global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArg
                 const int x = x0 + (j * 32 + lane) * 4;
                 if (x >= a.w) break;
                 const float4 y = __ldcs(reinterpret_cast<const float4*>(a.clean + row_base + x));
+                const GroupWords g = group_words(rng, (g_base + x) >> 2);       // (g_base + x) % 4 == 0 on this path
                 float4 o;
-                o.x = synth_one<CHAIN, DEBUG>(y.x, g_base + x + 0, row_base + x + 0, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
-                o.y = synth_one<CHAIN, DEBUG>(y.y, g_base + x + 1, row_base + x + 1, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
-                o.z = synth_one<CHAIN, DEBUG>(y.z, g_base + x + 2, row_base + x + 2, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
-                o.w = synth_one<CHAIN, DEBUG>(y.w, g_base + x + 3, row_base + x + 3, crop, ch, p, a, rng, rowz, lam_tl, inv_lam_tl, s_inv, s_lfact);
+                o.x = synth_one<CHAIN, DEBUG>(y.x, g.w[0], g.w[1], g.w[2], row_base + x + 0, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
+                o.y = synth_one<CHAIN, DEBUG>(y.y, g.w[3], g.w[4], g.w[5], row_base + x + 1, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
+                o.z = synth_one<CHAIN, DEBUG>(y.z, g.w[6], g.w[7], g.w[8], row_base + x + 2, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
+                o.w = synth_one<CHAIN, DEBUG>(y.w, g.w[9], g.w[10], g.w[11], row_base + x + 3, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
                 __stcs(reinterpret_cast<float4*>(a.noisy + row_base + x), o);
             }
         } else {
 #pragma unroll 1
             for (int x = x0 + lane; x < min(a.w, x0 + kSeg); x += 32) {
                 const float y = a.clean[row_base + x];
-                a.noisy[row_base + x] = synth_one<CHAIN, DEBUG>(y, g_base + x, row_base + x, crop, ch, p, a, rng, rowz, lam_tl,
-                                                               inv_lam_tl, s_inv, s_lfact);
+                const uint64_t gi = g_base + x;
+                const GroupWords g = group_words(rng, gi >> 2);
+                const int e = (int)(gi & 3);
+                uint32_t w0 = g.w[0], w1 = g.w[1], w2 = g.w[2];
+                if (e == 1) { w0 = g.w[3]; w1 = g.w[4]; w2 = g.w[5]; }
+                else if (e == 2) { w0 = g.w[6]; w1 = g.w[7]; w2 = g.w[8]; }
+                else if (e == 3) { w0 = g.w[9]; w1 = g.w[10]; w2 = g.w[11]; }
+                a.noisy[row_base + x] = synth_one<CHAIN, DEBUG>(y, w0, w1, w2, row_base + x, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
             }
         }
     }
@@ -185,7 +197,8 @@ static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
     int dev = 0, sms = 0;
     PNNP_CUDA(cudaGetDevice(&dev));
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const bool vec = (a.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.clean) | reinterpret_cast<uintptr_t>(a.noisy)) % 16 == 0);
+    const bool vec = (a.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.clean) | reinterpret_cast<uintptr_t>(a.noisy)) % 16 == 0) &&
+                     ((a.crop_id0 * (uint64_t)a.c * a.h * a.w) % 4 == 0);
     const int nseg = (a.w + kSeg - 1) / kSeg;
     const long long units = (long long)a.n * a.c * a.h * nseg;
     const long long want = (units + (kThreads / 32) - 1) / (kThreads / 32);

@@ -114,6 +114,8 @@ def test_philox_kernel_uses_the_replay_arithmetic(chain, code, w):
 
 
 def test_device_philox_words_match_cpu_philox():
+    """Element g uses words 3e..3e+2 (e = g & 3) of the three Philox blocks of group g >> 2; the
+    quantisation draw exposes word 3e+2 exactly: q = (w + 0.5) * 2^-32 - 0.5."""
     n, c, h, w = 2, 4, 8, 64
     y = _cuda(_mk(n, h, w, 5))
     np.random.seed(1)
@@ -124,10 +126,14 @@ def test_device_philox_words_match_cpu_philox():
     _, d = P.synthesize_batch(y, params, "pgrq", generator=gen, crop_id0=crop0, debug=True)
     q = d["q"].cpu().numpy().reshape(-1)
     words = np.round((q + 0.5) * 2.0 ** 32 - 0.5).astype(np.uint64)
-    idx = np.arange(n * c * h * w, dtype=np.uint64) + np.uint64(crop0 * c * h * w)
-    ctr = np.stack([idx & 0xFFFFFFFF, (idx >> 32) & 0xFFFF, np.full_like(idx, 7), np.zeros_like(idx)], -1).astype(np.uint32)
+    g = np.arange(n * c * h * w, dtype=np.uint64) + np.uint64(crop0 * c * h * w)
+    grp, e = g >> np.uint64(2), (g & np.uint64(3)).astype(np.int64)
+    slot = 3 * e + 2
+    sub, word = (slot // 4).astype(np.uint64), slot % 4
+    ctr = np.stack([grp & np.uint64(0xFFFFFFFF), ((grp >> np.uint64(32)) & np.uint64(0xFFFF)) | (sub << np.uint64(16)),
+                    np.full_like(grp, 7), np.zeros_like(grp)], -1).astype(np.uint32)
     ref = O.philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32))
-    assert np.array_equal(words, ref[:, 3].astype(np.uint64))
+    assert np.array_equal(words, ref[np.arange(g.size), word].astype(np.uint64))
 
 
 def test_shard_independence():
