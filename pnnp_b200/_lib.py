@@ -34,6 +34,7 @@ class ConvDesc(C.Structure):
                 ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_cout", C.c_int)]
 
 CODE_P, CODE_G, CODE_R, CODE_Q, CODE_D, CODE_B = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+CODE_UNIFORM_F64 = 0x100
 CHAIN_NUMPY, CHAIN_TORCH = 0, 1
 F_K64, F_RATIO64, F_SIG64 = 0x1, 0x2, 0x4
 

@@ -146,10 +146,16 @@ __device__ __forceinline__ float poisson_small(float lam, uint32_t w) {
     const float u = fminf(u01_32(w), 0.99999994f);
     float p = __expf(-lam), F = p;
     int k = 0;
-    while (u > F && k < kInvTab - 1) {
-        ++k;
-        p *= lam * c_inv_k[k];
-        F += p;
+#pragma unroll 1
+    while (u > F && k < kInvTab - 2) {          // two CDF terms per trip
+        p *= lam * c_inv_k[k + 1];
+        const float F1 = F + p;
+        p *= lam * c_inv_k[k + 2];
+        const float F2 = F1 + p;
+        const bool stop1 = !(u > F1);
+        k += stop1 ? 1 : 2;
+        F = stop1 ? F1 : F2;
+        if (stop1) break;
     }
     return (float)k;
 }
@@ -247,6 +253,35 @@ __device__ __forceinline__ float tail_numpy(float y, const RowP& p, uint32_t cod
         z = __fmul_rn(z, (float)p.ratio);
     }
     return z;
+}
+
+// ------------------------------------------------------------------------------------------
+// Correctly rounded division by a per-crop constant without the division subroutine (Markstein 1990):
+// with r = RN(1/b), q = RN(a r), rem = a - b q (exact in one FMA), RN(q + rem r) == RN(a / b).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float div_rn_by_const(float a, float b, float r) {
+    const float q = __fmul_rn(a, r);
+    return __fmaf_rn(__fmaf_rn(-b, q, a), r, q);
+}
+__device__ __forceinline__ double div_rn_by_const(double a, double b, double r) {
+    const double q = __dmul_rn(a, r);
+    return __fma_rn(__fma_rn(-b, q, a), r, q);
+}
+
+// Per-unit constants of the specialised ("fast") NumPy-chain path: noise_code 'p','g','r','q' only,
+// K / sigR np.float64 and ratio a python float (what sample_params returns), ori=False, clip=False.
+struct FastP {
+    float span32, ratio32, rratio32, invK32, sigTL32, lam_tl, inv_lam_tl;
+    double K, span, rspan, lo, ratio, row64;
+};
+__device__ __forceinline__ float tail_numpy_fast(const FastP& f, float cnt, float d_read, double d_q) {
+    double A = __dmul_rn((double)cnt, f.K);
+    A = __dadd_rn(A, (double)d_read);
+    A = __dadd_rn(A, f.row64);
+    A = __dadd_rn(A, d_q);
+    double z = div_rn_by_const(A, f.span, f.rspan);
+    z = fmin(fmax(z, f.lo), 1.0);
+    return (float)__dmul_rn(z, f.ratio);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -49,8 +49,6 @@ def synthesize_batch(clean, params, noise_code="p", chain=_lib.CHAIN_NUMPY, ori=
         table = ParamTable(params, clean.device, torch_chain=(chain == _lib.CHAIN_TORCH))
     if table.n < table_row0 + n:
         raise RuntimeError(f"pnnp_b200: {table.n} parameter rows for crops [{table_row0}, {table_row0 + n})")
-    if table.n != n and table_row0 == 0 and params is not None:
-        raise RuntimeError(f"pnnp_b200: {table.n} parameter rows for {n} crops")
     if out is None:
         out = torch.empty_like(clean)
     if seed_offset is None:
@@ -61,6 +59,8 @@ def synthesize_batch(clean, params, noise_code="p", chain=_lib.CHAIN_NUMPY, ori=
     tab_ptr = table.data_ptr() + 128 * table_row0
     lo, hi = (-math.inf, math.inf) if post_clip is None else post_clip
     bits = noise_code_bits(noise_code) if isinstance(noise_code, str) else int(noise_code)
+    if chain == _lib.CHAIN_NUMPY and getattr(table, "uniform_f64", False):
+        bits |= _lib.CODE_UNIFORM_F64
     L = _lib.lib()
     with torch.cuda.device(clean.device):
         st = _lib.stream_ptr(clean.device)

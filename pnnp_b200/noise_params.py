@@ -220,6 +220,7 @@ class ParamTable:
         self.host = host
         self.device = host.to(device, non_blocking=True)
         self.ratios = [float(r.ratio) for r in rows]
+        self.uniform_f64 = all(r.flags == (_lib.F_K64 | _lib.F_SIG64) for r in rows)
 
     def data_ptr(self):
         return self.device.data_ptr()

@@ -113,6 +113,24 @@ def test_philox_kernel_uses_the_replay_arithmetic(chain, code, w):
     assert not torch.equal(out, out3)
 
 
+def test_specialised_kernel_is_bit_identical_to_replay_at_scale():
+    """16 crops x 4x512x512 (16.8 M elements) through the branch-free instantiation (reciprocal-multiply
+    divisions with Markstein correction) == the generic replay kernel (IEEE divisions) on the same draws."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    y = torch.rand((16, 4, 512, 512), device="cuda", generator=g) ** 2
+    np.random.seed(12)
+    params = [P.sample_params("SonyA7S2") for _ in range(16)]
+    out, d = P.synthesize_batch(y, params, "pgrq", generator=P.PhiloxGenerator(5), debug=True)
+    rep = P.replay_batch(y, params, "pgrq", {"shot": d["shot"], "read": d["read"], "row_z": d["row_z"], "q": d["q"]})
+    assert torch.equal(out, rep)
+    # and the generic kernel (hint withheld) agrees with its own replay too
+    tab = P.ParamTable(params, y.device)
+    tab.uniform_f64 = False
+    out2, d2 = P.synthesize_batch(y[:2].contiguous(), None, "pgrq", generator=P.PhiloxGenerator(5), debug=True, table=tab)
+    rep2 = P.replay_batch(y[:2].contiguous(), params[:2], "pgrq", {"shot": d2["shot"], "read": d2["read"], "row_z": d2["row_z"], "q": d2["q"]})
+    assert torch.equal(out2, rep2)
+
+
 def test_device_philox_words_match_cpu_philox():
     """Element g uses words 3e..3e+2 (e = g & 3) of the three Philox blocks of group g >> 2; the
     quantisation draw exposes word 3e+2 exactly: q = (w + 0.5) * 2^-32 - 0.5."""
