@@ -121,6 +121,9 @@ int pnnp_noise_synth_replay(const float* clean, float* noisy, const pnnp_noise_p
 #define PNNP_CONV1 1 /* nn.Conv2d(k=1)                              */
 #define PNNP_CONVT 2 /* nn.ConvTranspose2d(k=2, s=2): output 2h x 2w */
 #define PNNP_CONV3S2 3 /* nn.Conv2d(k=3, s=2, p=1): output h/2 x w/2 (ResUnet down-sampling, modules.py:130-138) */
+/* 3x3 s1 p1 with the x-shift folded into N: weights [ky][kx*cout + co][cin], MMA N = 3*cout, the three
+ * kx partial sums are combined across neighbouring pixels in the epilogue (cout <= 80) */
+#define PNNP_CONV3X 4
 #define PNNP_ACT_NONE 0
 #define PNNP_ACT_LEAKY02 1 /* nn.LeakyReLU(0.2)  Unet.py:52    */
 #define PNNP_ACT_RELU 2    /* nn.ReLU            ResUnet.py:44 */

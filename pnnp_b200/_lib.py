@@ -61,7 +61,7 @@ SIGNATURES = {
     "pnnp_eval_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
 }
 
-CONV3, CONV1, CONVT, CONV3S2 = 0, 1, 2, 3
+CONV3, CONV1, CONVT, CONV3S2, CONV3X = 0, 1, 2, 3, 4
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 OUT_NHWC_BF16, OUT_NCHW_F32 = 0, 1
 

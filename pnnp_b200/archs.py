@@ -27,6 +27,10 @@ def initialize_weights(net):
             m.weight.data.normal_(0.0, 0.02)
 
 
+import os
+_X_MODE = os.environ.get("PNNP_NO_XMODE") is None
+
+
 def _pad16(c):
     return (c + 15) // 16 * 16
 
@@ -48,6 +52,9 @@ class _PackedLayer:
             if self.kind == "convT":                       # [Cin, Cout, 2, 2] -> [a*2+b][Cout][Cin]
                 cin, cout = w.shape[0], w.shape[1]
                 packed = w.permute(2, 3, 1, 0).reshape(4, cout, cin)
+            elif self.kind == "conv3x":                    # [Cout, Cin, 3, 3] -> [ky][kx*Cout + co][Cin]  (x-shift in N)
+                cout, cin = w.shape[0], w.shape[1]
+                packed = w.permute(2, 3, 0, 1).reshape(3, 3 * cout, cin)
             else:                                          # [Cout, Cin, k, k] -> [ky*k+kx][Cout][Cin]
                 cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
                 packed = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
@@ -126,9 +133,18 @@ class _TCNet(nn.Module):
 
     def _packed(self, name, kind="conv"):
         cache = self.__dict__.setdefault("_pack_cache", {})
-        if name not in cache:
-            cache[name] = _PackedLayer(self.get_submodule(name), kind)
-        return cache[name].get(next(self.parameters()).device)
+        if (name, kind) not in cache:
+            cache[(name, kind)] = _PackedLayer(self.get_submodule(name), kind)
+        return cache[(name, kind)].get(next(self.parameters()).device)
+
+    def _conv3(self, name, x0, out, cout, act, **kw):
+        """3x3 stride-1 conv layer `name`: the x-shift-in-N kernel mode for narrow layers (Cout <= 64, where a
+        128 x Cout MMA cannot amortise its A-operand read), the per-tap mode otherwise."""
+        if cout <= 64 and cout % 16 == 0 and kw.get("resid") is None and _X_MODE:
+            w, b = self._packed(name, "conv3x")
+            return _conv(_lib.CONV3X, x0, w, b, out, cout, act, **kw)
+        w, b = self._packed(name)
+        return _conv(_lib.CONV3, x0, w, b, out, cout, act, **kw)
 
     def _ws(self):
         return self.__dict__.setdefault("_workspace", _Workspace())
@@ -173,33 +189,29 @@ class UNetSeeInDark(_TCNet):
             hh, ww = h, w
             for i in range(1, 6):                                  # encoder (Unet.py:55-69)
                 co = nf * 2 ** (i - 1)
-                w1, b1 = self._packed(f"conv{i}_1")
-                w2, b2 = self._packed(f"conv{i}_2")
-                t = _conv(_lib.CONV3, cur, w1, b1, buf(f"c{i}a", hh, ww, co), co, L)
+                t = self._conv3(f"conv{i}_1", cur, buf(f"c{i}a", hh, ww, co), co, L)
                 if i < 5:                                          # conv + LeakyReLU + MaxPool2d(2) in one epilogue
                     pooled = buf(f"p{i}", hh // 2, ww // 2, co)
-                    skips.append(_conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L, pool_out=pooled))
+                    skips.append(self._conv3(f"conv{i}_2", t, buf(f"c{i}", hh, ww, co), co, L, pool_out=pooled))
                     cur, hh, ww = pooled, hh // 2, ww // 2
                 else:
-                    cur = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
+                    cur = self._conv3(f"conv{i}_2", t, buf(f"c{i}", hh, ww, co), co, L)
             for i in range(6, 10):                                 # decoder (Unet.py:71-89)
                 co = nf * 2 ** (9 - i)
                 skip = skips[9 - i]
                 wu, bu = self._packed(f"upv{i}", "convT")
                 up = _conv(_lib.CONVT, cur, wu, bu, buf(f"u{i}", hh * 2, ww * 2, co), co, _lib.ACT_NONE)
                 hh, ww = hh * 2, ww * 2
-                w1, b1 = self._packed(f"conv{i}_1")
-                w2, b2 = self._packed(f"conv{i}_2")
-                t = _conv(_lib.CONV3, up, w1, b1, buf(f"c{i}a", hh, ww, co), co, L, x1=skip)   # cat([up, skip], 1)
+                t = self._conv3(f"conv{i}_1", up, buf(f"c{i}a", hh, ww, co), co, L, x1=skip)   # cat([up, skip], 1)
                 if i < 9 or co > 64 or self.out_nc > 4:
-                    cur = _conv(_lib.CONV3, t, w2, b2, buf(f"c{i}", hh, ww, co), co, L)
+                    cur = self._conv3(f"conv{i}_2", t, buf(f"c{i}", hh, ww, co), co, L)
             out = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=dev)
             if co <= 64 and self.out_nc <= 4:
                 # conv9_2 + LeakyReLU + conv10_1 (+ x) in one kernel: conv9 never goes to HBM (Unet.py:90-98)
                 m10 = self.conv10_1
                 hw = m10.weight.detach().reshape(self.out_nc, co).float().contiguous()
-                _conv(_lib.CONV3, t, w2, b2, None, co, L, head=(hw, m10.bias.detach().float().contiguous(), out),
-                      resid_nchw=x if self.res else None)
+                self._conv3("conv9_2", t, None, co, L, head=(hw, m10.bias.detach().float().contiguous(), out),
+                            resid_nchw=x if self.res else None)
             else:
                 w10, b10 = self._packed("conv10_1")
                 _conv(_lib.CONV1, cur, w10, b10, out, self.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,

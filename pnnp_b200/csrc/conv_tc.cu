@@ -36,7 +36,8 @@ constexpr int kConvThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 ep
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSpinLimit = 1u << 27;      // ~ seconds; a broken pipeline terminates instead of hanging the GPU
 
-enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2, MODE_CONV3S2 = 3 };
+enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2, MODE_CONV3S2 = 3, MODE_CONV3X = 4 };
+constexpr int kTileWX = 14;             // output columns per tile in MODE_CONV3X (16 partial-sum columns, 1 halo each side)
 enum { OUT_NHWC_BF16 = 0, OUT_NCHW_F32 = 1 };
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
 
@@ -181,7 +182,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int ksteps = (chunks0 + chunks1) * dx_count;
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
     const uint32_t stage_tx = (uint32_t)(p.a_bytes + (p.b_resident ? 0 : taps_per_stage * p.umma_n * p.swz));
-    const int taps_total = p.mode == MODE_CONV3 ? 9 : (p.mode == MODE_CONV3S2 ? 9 : 1);
+    const int taps_total = p.mode == MODE_CONV3 ? 9 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV3X ? 3 : 1));
 
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.head_out)
@@ -212,6 +213,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         // ============================== TMA producer ==============================
         uint32_t stage = 0, phase = 0;
         const int halo = p.mode == MODE_CONV3 ? 1 : 0;
+        const int yhalo = (p.mode == MODE_CONV3 || p.mode == MODE_CONV3X) ? 1 : 0;
         if (p.b_resident && elect_one()) {
             // weights for every (K chunk, tap) once per CTA: layout [chunk][tap][umma_n rows x swz bytes]
             const uint32_t bb = smem_u32(bres_bar);
@@ -227,7 +229,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const int tx = r % p.tiles_x; r /= p.tiles_x;
             const int ty = r % p.tiles_y; r /= p.tiles_y;
             const int img = r;
-            const int x0 = tx * kTileW, y0 = ty * kTileH;
+            const int x0 = p.mode == MODE_CONV3X ? tx * kTileWX - 1 : tx * kTileW, y0 = ty * kTileH;
             const int n_off = n_tile * p.umma_n;
             int chunk = 0, dx = 0;
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -243,10 +245,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     if (p.mode == MODE_CONV3S2)      // stride 2: one box per tap, TMA element stride 2 in x and y
                         tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx % 3) - 1, 2 * y0 + (dx / 3) - 1, img);
                     else
-                        tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - halo, img);
+                        tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - yhalo, img);
                     for (int dy = 0; dy < (p.b_resident ? 0 : taps_per_stage); ++dy) {
                         const int tap = p.mode == MODE_CONV3 ? dy * 3 + dx
-                                      : (p.mode == MODE_CONV3S2 ? dx : 0);
+                                      : (p.mode == MODE_CONV3S2 ? dx : (p.mode == MODE_CONV3X ? dy : 0));
                         tma_load_3d(sb + dy * p.b_tap_stride, &tmB, fb, cin_off, n_off, tap);
                     }
                 }
@@ -280,7 +282,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     ? smem_u32(smem_bres) + (uint32_t)((chunk * taps_total + dx) * p.b_tap_stride)
                     : sa + p.a_bytes;
                 const uint64_t bdesc0 = dhi | (uint64_t)((sb >> 4) & 0x3FFFu);
-                const uint32_t b_stride_eff = (p.b_resident && p.mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;
+                const uint32_t b_stride_eff = (p.b_resident && p.mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;   // CONV3X: dy taps are consecutive
                 if (++dx == dxc) { dx = 0; ++chunk; }
                 if (elect_one()) {
                     issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
@@ -304,15 +306,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int ty_in = m / kTileW, tx_in = m % kTileW;
         const uint32_t acc = (uint32_t)group;
         uint32_t acc_phase = 0;
-        const int chunks16 = p.umma_n / 16;
+        const int chunks16 = (p.mode == MODE_CONV3X ? p.cout : p.umma_n) / 16;
         for (int t = blockIdx.x + group * gridDim.x; t < total_tiles; t += 2 * gridDim.x) {
             int r = t;
             const int n_tile = r % p.n_tiles; r /= p.n_tiles;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
             const int ty = r % p.tiles_y; r /= p.tiles_y;
             const int img = r;
-            const int x = tx * kTileW + tx_in, y = ty * kTileH + ty_in;
-            const bool valid = x < p.W && y < p.H;
+            const bool xmode = p.mode == MODE_CONV3X;
+            const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTileW + tx_in, y = ty * kTileH + ty_in;
+            const bool valid = x < p.W && y < p.H && (!xmode || (tx_in >= 1 && tx_in <= kTileWX));
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * (uint32_t)p.umma_n + ((uint32_t)(quad * 32) << 16);
@@ -322,7 +325,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             for (int j = 0; j < chunks16; ++j) {
                 uint32_t v[16];
                 tc_ld16(taddr + j * 16, v);
-                tc_ld_wait();
+                if (xmode) {
+                    // columns are (dx, co): out(j) = P[j-1, dx=0] + P[j, dx=1] + P[j+1, dx=2] along the 16-lane tile row
+                    uint32_t v0[16], v2[16];
+                    tc_ld16(taddr + p.cout + j * 16, v0);          // dx = 1 block (own column)
+                    tc_ld16(taddr + 2 * p.cout + j * 16, v2);      // dx = 2 block
+                    tc_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[i]), 1, 16);
+                        const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 1, 16);
+                        v[i] = __float_as_uint(left + __uint_as_float(v0[i]) + right);
+                    }
+                } else {
+                    tc_ld_wait();
+                }
                 int c0 = col_tile0 + j * 16;              // output channel of v[0]
                 size_t opix = pix_in;
                 if (p.mode == MODE_CONVT) {               // GEMM column = (a*2+b)*cout + co  ->  pixel (2y+a, 2x+b)
@@ -362,14 +379,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
-                            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+                            uint32_t o1 = xmode ? __shfl_down_sync(0xffffffffu, pk[i], 1) : __shfl_xor_sync(0xffffffffu, pk[i], 1);
                             a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o1));
                             uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
                             uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, 16);
                             a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
                             pk[i] = *reinterpret_cast<uint32_t*>(&a);
                         }
-                        if (valid && !(lane & 1) && !(lane & 16)) {
+                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16)) {
                             const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
                             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pp * p.cout_stride + c0);
                             op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -534,6 +551,11 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         if ((4 * cout) % umma_n) return fail("convT: 4*cout must be <= 256 or a multiple of 256");
         n_tiles = 4 * cout / umma_n;
     }
+    else if (mode == MODE_CONV3X) {
+        // x-shift folded into N: columns (dx, co), N = 3*cout
+        if (cout % 16 || 3 * cout > 256) return fail("conv3x: cout must be a multiple of 16 and <= 80");
+        umma_n = 3 * cout; n_tiles = 1;
+    }
     else {
         const int cpad = (cout + 15) / 16 * 16;
         umma_n = std::min(cpad, 256);
@@ -547,12 +569,13 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         return fail("conv: fused 1x1 head needs a single N tile, cout <= 64 and 1..4 head channels");
     if (out_mode == OUT_NHWC_BF16 && (cout % 16)) return fail("conv: NHWC output needs cout % 16 == 0");
     if (mode == MODE_CONVT ? (w_rows != cout) : (w_rows < n_tiles * umma_n)) return fail("conv: weight tensor has the wrong number of rows");
-    const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : (mode == MODE_CONVT ? 4 : 1);
+    if (mode == MODE_CONV3X && d.resid) return fail("conv3x: residual add is not supported in this mode");
+    const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : (mode == MODE_CONVT ? 4 : (mode == MODE_CONV3X ? 3 : 1));
     if (mode == MODE_CONV3S2 && (nsrc > 1 || (h & 1) || (w & 1))) return fail("stride-2 conv: single source, even h and w");
     const int in_h = h, in_w = w;
     if (mode == MODE_CONV3S2) { h /= 2; w /= 2; }        // tile over the OUTPUT grid
-    const int tps = mode == MODE_CONV3 ? 3 : 1;
-    const int box_h = mode == MODE_CONV3 ? kTileH + 2 : kTileH;
+    const int tps = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? 3 : 1;
+    const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? kTileH + 2 : kTileH;
     // shrink the K chunk until at least 3 pipeline stages fit
     int swz, a_bytes, b_tap_stride, stage_bytes, stages, b_resident = 0, b_res_bytes = 0;
     const int smem_budget = 227 * 1024 - 4096 - cout * 20;
@@ -577,7 +600,8 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (stages < 2) return fail("conv: tile does not fit in shared memory");
     ConvParams p{};
     p.mode = mode; p.n_img = n; p.H = h; p.W = w;
-    p.tiles_x = (w + kTileW - 1) / kTileW; p.tiles_y = (h + kTileH - 1) / kTileH; p.n_tiles = n_tiles;
+    p.tiles_x = mode == MODE_CONV3X ? (w + kTileWX - 1) / kTileWX : (w + kTileW - 1) / kTileW;
+    p.tiles_y = (h + kTileH - 1) / kTileH; p.n_tiles = n_tiles;
     p.umma_n = umma_n; p.nsrc = nsrc; p.cin0 = cin0; p.cin1 = nsrc > 1 ? cin1 : 0; p.kc = kc; p.swz = swz;
     p.cout = cout; p.cout_stride = cout_stride; p.act = act; p.out_mode = out_mode;
     p.stages = stages; p.stage_bytes = stage_bytes; p.a_bytes = a_bytes; p.b_tap_stride = b_tap_stride;

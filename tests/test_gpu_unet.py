@@ -238,3 +238,29 @@ def test_fused_pool_and_head_epilogues():
     act = F.leaky_relu(F.conv2d(_bf(x), _bf(wt), b, padding=1), 0.2)
     ref = F.conv2d(act, hw.view(4, 32, 1, 1), hb) + res
     assert (hout - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n,two", [(16, 32, 16, 32, 1, False), (32, 32, 24, 44, 2, False), (64, 64, 40, 72, 1, False),
+                                               (32, 32, 16, 30, 1, True), (64, 64, 24, 28, 1, True), (32, 64, 8, 16, 1, False)])
+def test_conv3x3_x_shift_in_n_mode(cin, cout, h, w, n, two):
+    """MODE_CONV3X == F.conv2d, including tiles_x = ceil(W/14) edges, two-source concat and the fused pool."""
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout + w)
+    x = torch.randn((n, cin, h, w), device="cuda", generator=g)
+    x2 = torch.randn((n, cin, h, w), device="cuda", generator=g) if two else None
+    ct = cin * (2 if two else 1)
+    wt = torch.randn((cout, ct, 3, 3), device="cuda", generator=g) / (3 * ct ** 0.5)
+    b = torch.randn((cout,), device="cuda", generator=g) * 0.1
+
+    class M:
+        pass
+    m = M()
+    m.weight, m.bias = wt, None
+    wp = archs._PackedLayer(m, "conv3x").get(wt.device)[0]
+    out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device="cuda")
+    pooled = torch.empty((n, h // 2, w // 2, cout), dtype=torch.bfloat16, device="cuda")
+    archs._conv(_lib.CONV3X, _nhwc(x), wp, b, out, cout, _lib.ACT_LEAKY, x1=None if x2 is None else _nhwc(x2), pool_out=pooled)
+    _no_pipeline_error()
+    xin = _bf(x) if x2 is None else torch.cat([_bf(x), _bf(x2)], 1)
+    ref = F.leaky_relu(F.conv2d(xin, _bf(wt), b, padding=1), 0.2)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(out), 2))

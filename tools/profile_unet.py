@@ -21,9 +21,9 @@ def conv_label(a, k):
     mode, x0, wt = a[0], a[1], a[2]
     n, h, w, c0 = x0.shape
     c1 = 0 if k.get("x1") is None else k["x1"].shape[3]
-    cout = a[5]; taps = {0: 9, 1: 1, 2: 4}[mode]
+    cout = a[5]; taps = {0: 9, 1: 1, 2: 4, 3: 9, 4: 9}[mode]
     flops = 2.0 * n * h * w * (c0 + c1) * cout * taps
-    return ("conv" if mode == 0 else "1x1" if mode == 1 else "convT", f"{c0+c1}->{cout} @{h}x{w}", flops)
+    return ({0: "conv", 1: "1x1", 2: "convT", 3: "convS2", 4: "convX"}[mode], f"{c0+c1}->{cout} @{h}x{w}", flops)
 with torch.no_grad():
     for _ in range(3): net(x)
     torch.cuda.synchronize()
@@ -42,4 +42,4 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     px = shape[0] * shape[1] * shape[2] * shape[3]
-    print(f"sum of layers {tot:.3f} ms; whole forward {ms:.3f} ms; {px/1e6/ms*1e3:.0f} MP/s; {92288*px/4/ms/1e9:.1f} TFLOP/s effective")
+    print(f"sum of layers {tot:.3f} ms; whole forward {ms:.3f} ms; {px/1e6/ms*1e3:.0f} MP/s; {92288*px/ms/1e9:.1f} TFLOP/s effective")
