@@ -140,7 +140,10 @@ class _TCNet(nn.Module):
     def _conv3(self, name, x0, out, cout, act, **kw):
         """3x3 stride-1 conv layer `name`: the x-shift-in-N kernel mode for narrow layers (Cout <= 64, where a
         128 x Cout MMA cannot amortise its A-operand read), the per-tap mode otherwise."""
-        if cout <= 64 and cout % 16 == 0 and kw.get("resid") is None and _X_MODE:
+        # measured on B200 (profiles/): x-mode wins when 3*Cout <= 128 (four TMEM accumulators / epilogue groups
+        # stay available) or when K is long (two-source decoder convs); otherwise the per-tap mode does.
+        narrow = cout <= 32 or (cout <= 64 and kw.get("x1") is not None)
+        if narrow and cout % 16 == 0 and kw.get("resid") is None and _X_MODE:
             w, b = self._packed(name, "conv3x")
             return _conv(_lib.CONV3X, x0, w, b, out, cout, act, **kw)
         w, b = self._packed(name)

@@ -32,7 +32,8 @@
 namespace pnnp {
 
 constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
-constexpr int kConvThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1
+constexpr int kMaxGroups = 4;            // epilogue groups == TMEM accumulator buffers (2 when N > 128, else 4)
+constexpr int kConvThreadsMax = 64 + 128 * kMaxGroups;   // warp 0 TMA, warp 1 MMA, then 4 epilogue warps per group
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSpinLimit = 1u << 27;      // ~ seconds; a broken pipeline terminates instead of hanging the GPU
 
@@ -54,6 +55,7 @@ struct ConvParams {
     int b_resident;                 // all taps x K chunks of the weights stay in smem for the whole kernel
     int b_res_bytes;
     int tmem_cols;
+    int groups;                     // epilogue groups / accumulator buffers in flight
     const float* bias;              // [cout] or null
     void* out;
     const __nv_bfloat16* resid;     // NHWC bf16 residual with the output's geometry, or null
@@ -63,6 +65,7 @@ struct ConvParams {
     const float* head_b;            // [head_cout]
     float* head_out;                // NCHW fp32, head_cout <= 4 planes
     int head_cout;
+    int dbg;                        // timing experiments only: 1 skip stores, 2 skip MMAs, 4 skip A loads, 8 skip epilogue math
     int* err;
 };
 
@@ -158,7 +161,7 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
 
 // ------------------------------------------------------------------------------------------ kernel
 template <int TPS, int K16S>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreadsMax, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -168,10 +171,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bres + p.b_res_bytes);
     uint64_t* full_bar = bars;                       // [stages]
     uint64_t* empty_bar = bars + kMaxStages;         // [stages]
-    uint64_t* tfull_bar = bars + 2 * kMaxStages;     // [2]
-    uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;  // [2]
-    uint64_t* bres_bar = bars + 2 * kMaxStages + 4;    // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;                    // [kMaxGroups]
+    uint64_t* tempty_bar = bars + 2 * kMaxStages + kMaxGroups;      // [kMaxGroups]
+    uint64_t* bres_bar = bars + 2 * kMaxStages + 2 * kMaxGroups;    // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxGroups + 2);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_head_w = s_bias + p.cout;            // [cout][4]
 
@@ -193,7 +196,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+        for (int a = 0; a < p.groups; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
         mbar_init(smem_u32(bres_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -240,7 +243,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 const uint32_t fb = smem_u32(&full_bar[stage]);
                 const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
                 const uint32_t sb = sa + p.a_bytes;
-                if (elect_one()) {
+                if ((p.dbg & 4) && (t != (int)blockIdx.x)) { if (elect_one()) mbar_arrive(fb); }
+                else if (elect_one()) {
                     mbar_expect_tx(fb, stage_tx);
                     if (p.mode == MODE_CONV3S2)      // stride 2: one box per tap, TMA element stride 2 in x and y
                         tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx % 3) - 1, 2 * y0 + (dx / 3) - 1, img);
@@ -285,7 +289,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 const uint32_t b_stride_eff = (p.b_resident && p.mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;   // CONV3X: dy taps are consecutive
                 if (++dx == dxc) { dx = 0; ++chunk; }
                 if (elect_one()) {
-                    issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
+                    if (!(p.dbg & 2)) issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
                     tc_commit(smem_u32(&empty_bar[stage]));              // frees the smem slot when these MMAs retire
                 }
                 __syncwarp();
@@ -293,13 +297,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             }
             if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete -> epilogue
             __syncwarp();
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == (uint32_t)p.groups) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ============================== epilogue (warps 2..5) ==============================
-        // Two epilogue groups of four warps: group g drains accumulator buffer g, i.e. every other tile of
-        // this CTA, so two tiles' epilogues overlap each other and the next tile's MMAs.
+        // Epilogue groups of four warps: group g drains accumulator buffer g, i.e. every groups-th tile of this
+        // CTA, so several tiles' epilogues (latency-bound: TMEM load -> math -> shuffle -> store chains) overlap
+        // each other and the following tiles' MMAs.
         const int group = (warp - 2) >> 2;
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
         const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
@@ -307,7 +311,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const uint32_t acc = (uint32_t)group;
         uint32_t acc_phase = 0;
         const int chunks16 = (p.mode == MODE_CONV3X ? p.cout : p.umma_n) / 16;
-        for (int t = blockIdx.x + group * gridDim.x; t < total_tiles; t += 2 * gridDim.x) {
+        for (int t = blockIdx.x + group * gridDim.x; t < total_tiles; t += p.groups * gridDim.x) {
             int r = t;
             const int n_tile = r % p.n_tiles; r /= p.n_tiles;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
@@ -319,6 +323,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * (uint32_t)p.umma_n + ((uint32_t)(quad * 32) << 16);
+            if (p.dbg & 8) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc])); acc_phase ^= 1; continue; }
             const int col_tile0 = n_tile * p.umma_n;     // first GEMM column of this tile
             const size_t pix_in = ((size_t)img * p.H + y) * (size_t)p.W + x;
             float head[4] = {0.f, 0.f, 0.f, 0.f};
@@ -368,7 +373,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                         pk[i] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    if (p.out && valid) {
+                    if (p.out && valid && !(p.dbg & 1)) {
                         uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0);
                         op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -386,7 +391,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
                             pk[i] = *reinterpret_cast<uint32_t*>(&a);
                         }
-                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16)) {
+                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16) && !(p.dbg & 1)) {
                             const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
                             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pp * p.cout_stride + c0);
                             op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -405,17 +410,23 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 } else if (valid) {
                     float* o = reinterpret_cast<float*>(p.out);
                     const size_t plane = (size_t)p.H * p.W;
-                    for (int i = 0; i < 16 && c0 + i < p.cout; ++i) {
-                        const size_t oi = ((size_t)img * p.cout + (c0 + i)) * plane + (size_t)y * p.W + x;
-                        o[oi] = f[i] + (p.resid_nchw ? p.resid_nchw[oi] : 0.f);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {           // static indices keep f[] in registers
+                        if (c0 + i < p.cout) {
+                            const size_t oi = ((size_t)img * p.cout + (c0 + i)) * plane + (size_t)y * p.W + x;
+                            o[oi] = f[i] + (p.resid_nchw ? p.resid_nchw[oi] : 0.f);
+                        }
                     }
                 }
             }
             if (p.head_out && valid) {
                 const size_t plane = (size_t)p.H * p.W;
-                for (int o = 0; o < p.head_cout; ++o) {
-                    const size_t oi = ((size_t)img * p.head_cout + o) * plane + (size_t)y * p.W + x;
-                    p.head_out[oi] = head[o] + p.head_b[o] + (p.resid_nchw ? p.resid_nchw[oi] : 0.f);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    if (o < p.head_cout) {
+                        const size_t oi = ((size_t)img * p.head_cout + o) * plane + (size_t)y * p.W + x;
+                        p.head_out[oi] = head[o] + p.head_b[o] + (p.resid_nchw ? p.resid_nchw[oi] : 0.f);
+                    }
                 }
             }
             tc_fence_before();
@@ -606,11 +617,13 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     p.cout = cout; p.cout_stride = cout_stride; p.act = act; p.out_mode = out_mode;
     p.stages = stages; p.stage_bytes = stage_bytes; p.a_bytes = a_bytes; p.b_tap_stride = b_tap_stride;
     p.b_resident = b_resident; p.b_res_bytes = b_res_bytes;
-    int tc = 32; while (tc < 2 * umma_n) tc <<= 1;
-    p.tmem_cols = tc;
+    const int groups = (umma_n <= 128 && !getenv("PNNP_CONV_2GROUPS")) ? 4 : 2;
+    int tc = 32; while (tc < groups * umma_n) tc <<= 1;
+    p.tmem_cols = tc; p.groups = groups;
     p.bias = bias; p.out = out; p.resid = static_cast<const __nv_bfloat16*>(resid); p.resid_nchw = resid_nchw;
     p.pool_out = static_cast<__nv_bfloat16*>(d.pool_out);
     p.head_w = d.head_w; p.head_b = d.head_b; p.head_out = d.head_out; p.head_cout = d.head_out ? d.head_cout : 0;
+    { const char* e = getenv("PNNP_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
     if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
     p.err = g_err_dev;
     CUtensorMap tmA0, tmA1, tmB;
@@ -624,7 +637,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int total_tiles = n * p.tiles_y * p.tiles_x * n_tiles;
     const int grid = std::min(total_tiles, sms);
-    const size_t smem = (size_t)stages * stage_bytes + b_res_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 16 + (size_t)cout * 4 * 5 + 64;
+    const size_t smem = (size_t)stages * stage_bytes + b_res_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 2 * kMaxGroups + 2) * 8 + 16 + (size_t)cout * 4 * 5 + 64;
     if (smem > 227 * 1024) return fail("conv: shared memory budget exceeded");
     static bool attr_done = false;
 #define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1) X(3, 2) X(3, 4) X(1, 1) X(1, 2) X(1, 4)
@@ -636,7 +649,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     }
     const int k16s = kc / 16;
     bool launched = false;
-#define X(T, K) if (!launched && tps == T && k16s == K) { conv_gemm_tc_kernel<T, K><<<grid, kConvThreads, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
+#define X(T, K) if (!launched && tps == T && k16s == K) { conv_gemm_tc_kernel<T, K><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
     PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
     if (!launched) return fail("conv: no kernel variant for this (taps per stage, K chunk)");
