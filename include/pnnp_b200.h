@@ -167,6 +167,13 @@ int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, 
 /* nn.MaxPool2d(2) on NHWC bf16 (Unet.py:57) */
 int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int w, int c, void* stream);
 
+/* D2 — SynBase_Dataset.random_crop + data_aug (data_process/syn_datasets.py:100-107,162-173) for up to 64
+ * crops of one packed frame (c x h x w fp32 -> n x c x patch x patch fp32): crop k is
+ * frame[:, hs:hs+patch, ws:ws+patch] rotated by numpy.rot90(k = mode % 4) on (H, W) and W-flipped if mode >= 4.
+ * The crop points / modes are host arrays (they come from the host RNG, init_random_crop_point :69-98). */
+int pnnp_crop_aug(const float* frame, float* out, int c, int h, int w, int patch, int n,
+                  const int* h_start_host, const int* w_start_host, const int* mode_host, void* stream);
+
 /* E1 / E2 — eval boundary on the device (trainer_SID.py:231-248; IlluminanceCorrect,
  * data_process/__init__.py:162-175; tensor2im + quality_assess, utils/visualization.py:9-31).
  * dn, hr: n x c x h x w fp32 (network output, clean target).  dn is scaled by `scale` (the ratio when

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pnnp_conv_pipeline_error": (_i, []),
     "pnnp_nchw_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "pnnp_maxpool2x2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "pnnp_crop_aug": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]),
     "pnnp_eval_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
 }
 

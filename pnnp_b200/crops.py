@@ -1,0 +1,57 @@
+"""Crop + augmentation of SynBase_Dataset (data_process/syn_datasets.py:69-107,162-173) on the device.
+
+`init_random_crop_point` reproduces the reference's draw order on NumPy's global RandomState
+(aug modes first, then per crop h_start, w_start), so the same seed gives the same crops;
+`random_crop` runs the gather kernel (csrc/crop_aug.cu)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def init_random_crop_point(h, w, patch_size, crop_per_image, mode='random_crop'):
+    """syn_datasets.py:69-98 -> (h_start, w_start, aug) lists."""
+    aug = np.random.randint(8, size=crop_per_image)
+    hs, ws = [], []
+    if mode == 'non-overlapped':
+        nh, nw = h // patch_size, w // patch_size
+        h0 = np.random.randint(0, h - nh * patch_size + 1)
+        w0 = np.random.randint(0, w - nw * patch_size + 1)
+        for i in range(nh):
+            for j in range(nw):
+                hs.append(h0 + i * patch_size)
+                ws.append(w0 + j * patch_size)
+    else:
+        for _ in range(crop_per_image):
+            hs.append(np.random.randint(0, h - patch_size + 1))
+            ws.append(np.random.randint(0, w - patch_size + 1))
+    return hs, ws, aug
+
+
+def data_aug(data, mode=0):
+    """syn_datasets.py:100-107 on a CUDA tensor (c,h,w) — via the same kernel with a full-frame crop."""
+    c, h, w = data.shape
+    if h != w:
+        raise RuntimeError("data_aug: square crops only (rot90 of a non-square crop changes its shape)")
+    return random_crop(data, [0], [0], [mode], h)[0]
+
+
+def random_crop(img, h_start, w_start, aug, patch_size):
+    """syn_datasets.py:162-173: img CUDA fp32 (c,h,w) -> crops (n,c,patch,patch)."""
+    _lib.require_cuda(img, "img")
+    img = img.float().contiguous()
+    c, h, w = img.shape
+    n = len(h_start)
+    k = min(n, len(aug))                  # the reference indexes aug[i] for i < crop_per_image
+    out = torch.empty((n, c, patch_size, patch_size), dtype=torch.float32, device=img.device)
+    L = _lib.lib()
+    with torch.cuda.device(img.device):
+        for s in range(0, n, 64):
+            m = min(64, n - s)
+            arr = lambda v: (C.c_int * m)(*[int(x) for x in v[s:s + m]])
+            modes = [int(aug[i]) if i < k else 0 for i in range(s, s + m)]
+            _lib.check(L.pnnp_crop_aug(img.data_ptr(), out[s:].data_ptr(), c, h, w, patch_size, m, arr(h_start), arr(w_start),
+                                       (C.c_int * m)(*modes), _lib.stream_ptr(img.device)), "crop_aug")
+    return out

@@ -72,3 +72,52 @@ class Synthetic_IMX686_Dataset(_SyntheticEvalBase):
     """LRID-shaped sweep: 9 scenes (phone_datasets.py:245), 4x1736x2312 frames."""
     default_frames, default_iso = 9, 6400
     legal_iso = (100, 6400)
+
+
+class Raw_Dataset(torch.utils.data.Dataset):
+    """Raw_Dataset.__getitem__ (data_process/syn_datasets.py:285-347) with the whole item built on the
+    device: synthetic uint16 RAW frame -> raw2bayer(norm, clip) -> random_crop + 8-mode aug ->
+    per-crop sample_params -> ONE fused synthesis launch -> lr.clip(lb, 1), hr.clip(0, 1).
+    Returns CUDA tensors (lr, hr: crop_per_image x 4 x patch x patch; ratio: crop_per_image).
+    The clean long-exposure RAW files of the reference are replaced by seeded synthetic frames."""
+
+    def __init__(self, args=None):
+        self.args = dict(args)
+        self.H, self.W = self.args['H'], self.args['W']
+        self.h, self.w, self.c = self.H // 2, self.W // 2, 4
+        self.length = int(self.args.get('synthetic_frames', 16))
+        self.args.setdefault('params', None)
+        self.args.setdefault('mode', 'train')
+
+    def __len__(self):
+        return self.length
+
+    def synthetic_raw(self, idx, device):
+        g = torch.Generator(device=device).manual_seed(4242 + idx)
+        wp, bl = self.args['wp'], self.args['bl']
+        u = torch.rand((self.H, self.W), device=device, generator=g)
+        return (bl + (u * u) * (wp - bl)).to(torch.int16)          # bit pattern of the uint16 sensor codes (< 2^15)
+
+    def __getitem__(self, idx):
+        from . import crops
+        from .isp_ops import raw2bayer
+        from .noise import synthesize_batch
+        from .noise_params import HALF_CLIP, sample_params
+        device = torch.device("cuda", torch.cuda.current_device())
+        a = self.args
+        hr_imgs = raw2bayer(self.synthetic_raw(idx, device), wp=a['wp'], bl=a['bl'], norm=True, clip=True)
+        if a['mode'] == 'train':
+            hs, ws, aug = crops.init_random_crop_point(self.h, self.w, a['patch_size'], a['crop_per_image'], a['croptype'])
+            hr_crops = crops.random_crop(hr_imgs, hs, ws, aug, a['patch_size'])
+        else:
+            hr_crops = hr_imgs[None]
+        n = hr_crops.shape[0]
+        params = [sample_params(camera_type=a['camera_type']) if a['params'] is None else a['params'] for _ in range(n)]
+        post = None
+        if a['clip']:
+            post = (-float("inf") if a['clip'] == HALF_CLIP else 0.0, 1.0)
+            hr_crops = hr_crops.clamp_(0, 1)
+        lr_crops = synthesize_batch(hr_crops, params, a['noise_code'], ori=a['ori'], post_clip=post)
+        ratio = torch.tensor([float(p['ratio']) for p in params], dtype=torch.float32, device=device)
+        return {"lr": lr_crops, "hr": hr_crops, "ratio": ratio, "wb": np.ones(4, np.float32),
+                "ccm": np.eye(3, dtype=np.float32), "name": f"syn_{idx:04d}"}
