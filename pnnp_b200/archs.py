@@ -211,10 +211,12 @@ class UNetSeeInDark(_TCNet):
             out = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=dev)
             if co <= 64 and self.out_nc <= 4:
                 # conv9_2 + LeakyReLU + conv10_1 (+ x) in one kernel: conv9 never goes to HBM (Unet.py:90-98)
-                m10 = self.conv10_1
-                hw = m10.weight.detach().reshape(self.out_nc, co).float().contiguous()
-                self._conv3("conv9_2", t, None, co, L, head=(hw, m10.bias.detach().float().contiguous(), out),
-                            resid_nchw=x if self.res else None)
+                m10 = self.conv10_1                      # 1x1 head kept in fp32 (it reads the fp32 accumulators)
+                hw = m10.weight.detach().reshape(self.out_nc, co)
+                hb = m10.bias.detach()
+                if hw.dtype != torch.float32 or not hw.is_contiguous():
+                    hw, hb = hw.float().contiguous(), hb.float().contiguous()
+                self._conv3("conv9_2", t, None, co, L, head=(hw, hb, out), resid_nchw=x if self.res else None)
             else:
                 w10, b10 = self._packed("conv10_1")
                 _conv(_lib.CONV1, cur, w10, b10, out, self.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,
