@@ -131,8 +131,11 @@ class SID_Trainer(Base_Trainer):
         ratios = data['ratio'].float().view(-1).tolist()
         if preprocess:
             params = data['param_list']
+            # Philox (seed, offset) = (fixed seed, sweep number) and crop id = dataset index: every rank count gives
+            # bit-identical noisy frames, so sharded and single-GPU sweeps report the same metrics
             lr = synthesize_batch(hr.contiguous(), params, self.dst['noise_code'], _lib.CHAIN_NUMPY, ori=self.dst['ori'],
-                                  clip=False, crop_id0=int(data['index'][0]))
+                                  clip=False, crop_id0=int(data['index'][0]),
+                                  seed_offset=(getattr(self, 'noise_seed', 1997), getattr(self, 'sweep_id', 0)))
         else:
             lr = tensor_dim5to4(data['lr']).float().to(self.device, non_blocking=True)
         ratio = torch.tensor(ratios, device=self.device).view(-1, 1, 1, 1)
@@ -153,6 +156,7 @@ class SID_Trainer(Base_Trainer):
     def eval(self, epoch=-1):
         self.net.eval()
         self.metrics_reset()
+        self.sweep_id = getattr(self, 'sweep_id', 0) + 1
         metrics, metrics_path = {}, f'./metrics/{self.model_name}_metrics.pkl'
         if self.rank == 0 and os.path.exists(metrics_path):
             with open(metrics_path, 'rb') as f:
@@ -248,7 +252,14 @@ def main_sid(argv=None):
             results[f'test_x{dgain}'] = trainer.eval(-1)
     if trainer.rank == 0:
         log(f'Metrics have been saved in ./metrics/{trainer.model_name}_metrics.pkl')
+    _shutdown(trainer)
     return results
+
+
+def _shutdown(trainer):
+    if trainer.world_size > 1 and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def main_lrid(argv=None):
@@ -268,4 +279,5 @@ def main_lrid(argv=None):
                 results[f'{mode}_x{dgain}'] = trainer.eval(-1)
     if trainer.rank == 0:
         log(f'Metrics have been saved in ./metrics/{trainer.model_name}_metrics.pkl')
+    _shutdown(trainer)
     return results
