@@ -10,6 +10,8 @@ Workloads (BASELINE.json configs; raw MP = Bayer samples = packed elements / 1e6
                synthetic 4x1424x2128 frame per GPU per step. Tensor-core roofline.
   imx686_eval  configs[3]: UNetSeeInDark eval on synthetic 4x1736x2312 frames, reflect-pad 4 -> net ->
                crop (trainer_LRID.py:224-229), one frame per GPU per step.
+  sony_evaltest configs[4]: per frame pack + noise synthesis (ratio x100/x200/x300) + ResUnet forward +
+               IlluminanceCorrect + PSNR/SSIM partial sums; e2e = pinned uint16 RAW frame in, metrics out.
 Every rank processes its own crops / frames (weak scaling, no data-path collective); crop ids — and so
 the Philox streams — are global.  One JSON line on stdout (rank 0).
 """
@@ -41,7 +43,12 @@ WORKLOADS = {
     "imx686_eval": dict(metric="raw megapixels/sec (UNetSeeInDark eval, 4x1736x2312 frame per GPU, reflect-pad path)", n=1,
                         c=4, h=1736, w=2312, bound="tensor", dtype="bf16",
                         desc="imx686_eval (BASELINE configs[3]): reflect-pad 4 -> UNetSeeInDark -> crop on 4x1736x2312 frames"),
+    "sony_evaltest": dict(metric="raw megapixels/sec (evaltest frame: noise synthesis + ResUnet forward + PSNR/SSIM, 4x1424x2128 per GPU)",
+                          n=1, c=4, h=1424, w=2128, bound="tensor", dtype="bf16",
+                          desc="sony_evaltest (BASELINE configs[4]): per frame pack + 'pgrq' synthesis at ratio 100/200/300 + ResUnet "
+                               "forward + clamp/IlluminanceCorrect + PSNR/SSIM partial sums"),
 }
+RESUNET_FLOP_PER_PIXEL = 119424.0
 
 
 # ----------------------------------------------------------------------------------------------
@@ -129,7 +136,7 @@ def _cpu_synth_one_crop(seed):
     return time.perf_counter() - t0
 
 
-def _cpu_unet_frames(wl, frames, threads):
+def _cpu_unet_frames(wl, frames, threads, resunet=False):
     """reference init + torch CPU fp32 forward (oracle restatement of archs/Unet.py), `threads` threads."""
     import torch
     import torch.nn.functional as F
@@ -137,14 +144,20 @@ def _cpu_unet_frames(wl, frames, threads):
     import pnnp_b200 as P
     torch.set_num_threads(threads)
     torch.manual_seed(1997)
-    net = P.UNetSeeInDark(ARCH)
+    net = (P.ResUnet if resunet else P.UNetSeeInDark)(ARCH)
     P.initialize_weights(net)
     sd = net.state_dict()
     x = torch.rand((1, 4, wl["h"], wl["w"]))
     t0 = time.perf_counter()
     with torch.no_grad():
         for _ in range(frames):
-            if wl["w"] % 16:
+            if resunet:
+                import numpy as np
+                np.random.seed(1)
+                prm = O.sample_params_max("SonyA7S2", ratio=100, iso=1600)
+                lr = torch.from_numpy(O.generate_noisy_obs(x[0].numpy(), param=prm, noise_code=NOISE_CODE))[None]
+                y = O.resunet_forward(lr, sd)
+            elif wl["w"] % 16:
                 y = O.unet_forward(F.pad(x, (4, 4, 4, 4), mode="reflect"), sd)[..., 4:-4, 4:-4]
             else:
                 y = O.unet_forward(x, sd)
@@ -161,9 +174,10 @@ def cpu_baseline(name, wl):
         return {"value": n * 4 * 512 * 512 / 1e6 / busy, "unit": UNIT, "cores": 1, "kind": "port",
                 "sample": f"{n} of 64 crops (4x512x512, '{NOISE_CODE}'), sequential, oracle_np.generate_noisy_obs "
                           "(NumPy/SciPy are single-threaded)"}
-    dt = _cpu_unet_frames(wl, 1, cores)
+    dt = _cpu_unet_frames(wl, 1, cores, resunet=(name == "sony_evaltest"))
+    what = "generate_noisy_obs + resunet_forward (metrics excluded)" if name == "sony_evaltest" else "unet_forward"
     return {"value": wl["c"] * wl["h"] * wl["w"] / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 frame 4x{wl['h']}x{wl['w']}, torch CPU fp32, {cores} threads, oracle_np.unet_forward"}
+            "sample": f"1 frame 4x{wl['h']}x{wl['w']}, torch CPU fp32, {cores} threads, oracle_np.{what}"}
 
 
 def run_reference_arm(args, name, wl):
@@ -187,8 +201,9 @@ def run_reference_arm(args, name, wl):
         used = workers
     else:
         steps = min(args.steps, 3)                             # ~5 s per frame on 8 cores
-        _cpu_unet_frames(wl, min(args.warmup, 1), cores)
-        dt = _cpu_unet_frames(wl, steps, cores) * args.steps / steps
+        rn = name == "sony_evaltest"
+        _cpu_unet_frames(wl, min(args.warmup, 1), cores, resunet=rn)
+        dt = _cpu_unet_frames(wl, steps, cores, resunet=rn) * args.steps / steps
         mp_step = wl["c"] * wl["h"] * wl["w"] / 1e6
         sample = f"1 frame per step ({steps} timed, scaled to {args.steps}), torch CPU fp32 on {cores} threads"
         used = cores
@@ -253,6 +268,27 @@ def run_gpu_arm(args, name, wl):
         algo = elems * 8.0                                                     # 4 B read + 4 B write per element
         l2_note = "no flush: 268 MB in + 268 MB out per step exceed the 126 MB L2"
         kernel = "noise_synth_kernel"
+    elif name == "sony_evaltest":
+        from pnnp_b200.pipeline import EvalPipeline
+        from pnnp_b200.metrics import eval_partial_sums
+        torch.manual_seed(1997)
+        net = P.ResUnet(dict(ARCH, name="ResUnet")).to(device).eval()
+        P.initialize_weights(net)
+        raw = (512 + (torch.rand((2 * h, 2 * w), device=device, generator=g) ** 2) * (16383 - 512)).to(torch.int16)
+        np.random.seed(1997 + rank)
+        sweep = [P.sample_params_max("SonyA7S2", ratio=r, iso=1600) for r in (100, 200, 300)]
+        state = {"i": 0}
+
+        def step():
+            with torch.no_grad():
+                prm = sweep[state["i"] % 3]
+                state["i"] += 1
+                hr = P.raw2bayer(raw, wp=16383, bl=512, norm=True, clip=True)[None]
+                lr = P.synthesize_batch(hr, [prm], NOISE_CODE, crop_id0=rank, seed_offset=(1997, state["i"]))
+                eval_partial_sums(net(lr), hr, 1.0, True)
+        algo = RESUNET_FLOP_PER_PIXEL * n * c * h * w
+        l2_note = "no flush: level-1/2 activations (194 MB per tensor) exceed the 126 MB L2"
+        kernel = "conv_gemm_tc_kernel (ResUnet convs) + noise_synth_kernel + ssim_mse_kernel"
     else:
         torch.manual_seed(1997)
         net = P.UNetSeeInDark(ARCH).to(device).eval()
@@ -302,6 +338,17 @@ def run_gpu_arm(args, name, wl):
             pipe.run(host_in, host_out, params, NOISE_CODE, generator=gen, crop_id0=crop0, post_clip=(-float("inf"), 1.0))
         h2d, d2h = elems * 4 + n * 128, elems * 4
         api = "pnnp_b200.pipeline.HostSynthPipeline.run (pinned host crops in, pinned host noisy crops out)"
+    elif name == "sony_evaltest":
+        pipe = EvalPipeline(net, 2 * h, 2 * w, 16383, 512, NOISE_CODE, brightness_correct=True, device=device)
+        host_raw = [raw.cpu().pin_memory(), raw.cpu().pin_memory()]
+        st2 = {"i": 0}
+
+        def e2e_step():
+            i = st2["i"]
+            st2["i"] += 1
+            pipe.submit(host_raw[i % 2], sweep[i % 3], crop_id=rank, seed_offset=(1997, i))
+        h2d, d2h = 2 * h * 2 * w * 2 + 128, 7 * 8
+        api = "pnnp_b200.pipeline.EvalPipeline.submit: pinned uint16 RAW frame in, PSNR/SSIM partial sums out"
     else:
         host_in = torch.empty((n, c, h, w), dtype=torch.float32).pin_memory()
         host_in.copy_(frame.cpu())

@@ -47,3 +47,49 @@ class HostSynthPipeline:
         for st in self.streams:
             cur.wait_stream(st)
         return host_out
+
+
+class EvalPipeline:
+    """Host-buffer entry of the eval path (trainer_SID.py:181-248 per frame): pinned uint16 RAW frame in ->
+    P1 pack/normalise -> S3+N1-N3 noise synthesis at the frame's ratio -> [reflect-pad 4] -> network forward ->
+    crop -> clamp / IlluminanceCorrect / PSNR + SSIM partial sums -> (3 + c) doubles back to pinned host memory.
+    The H2D copy of frame i+1 runs on a copy stream while frame i computes."""
+
+    def __init__(self, net, H, W, wp, bl, noise_code, ori=False, brightness_correct=False, device=None, depth=2):
+        import torch.nn.functional as F  # noqa: F401
+        self.net, self.H, self.W, self.wp, self.bl = net, H, W, wp, bl
+        self.noise_code, self.ori, self.correct = noise_code, ori, brightness_correct
+        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.d_raw = [torch.empty((H, W), dtype=torch.int16, device=self.device) for _ in range(depth)]
+        self.h_sums = [torch.empty((1, 7), dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [torch.cuda.Event() for _ in range(depth)]
+        self.slot = 0
+
+    def submit(self, raw_host_i16, param, crop_id=0, seed_offset=(1997, 0)):
+        """raw_host_i16: pinned CPU int16 tensor holding the uint16 sensor codes (H x W).  Returns the pinned
+        (1, 3+c) float64 tensor that will hold the partial sums once the current stream has been synchronised."""
+        import torch.nn.functional as F
+        from .isp_ops import raw2bayer
+        from .metrics import eval_partial_sums
+        k = self.slot
+        self.slot = (self.slot + 1) % len(self.d_raw)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[k])          # the previous user of this slot is done
+            self.d_raw[k].copy_(raw_host_i16, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        cur.wait_event(self.ready[k])
+        with torch.no_grad():
+            hr = raw2bayer(self.d_raw[k], wp=self.wp, bl=self.bl, norm=True, clip=True)[None]
+            self.consumed[k].record(cur)
+            lr = synthesize_batch(hr, [param], self.noise_code, ori=self.ori, crop_id0=crop_id, seed_offset=seed_offset)
+            if lr.shape[-1] % 16 or lr.shape[-2] % 16:
+                dn = self.net(F.pad(lr, (4, 4, 4, 4), mode="reflect"))[..., 4:-4, 4:-4].contiguous()
+            else:
+                dn = self.net(lr)
+            scale = float(param["ratio"]) if self.ori else 1.0
+            sums = eval_partial_sums(dn, hr, scale, self.correct)
+            self.h_sums[k].copy_(sums, non_blocking=True)
+        return self.h_sums[k]
