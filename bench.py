@@ -236,6 +236,12 @@ def run_gpu_arm(args, name, wl):
         raise RuntimeError("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    try:        # keep this rank (and the pinned buffers it first-touches) on the CPU cores / NUMA node next to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
