@@ -12,6 +12,8 @@ Workloads (BASELINE.json configs; raw MP = Bayer samples = packed elements / 1e6
                crop (trainer_LRID.py:224-229), one frame per GPU per step.
   sony_evaltest configs[4]: per frame pack + noise synthesis (ratio x100/x200/x300) + ResUnet forward +
                IlluminanceCorrect + PSNR/SSIM partial sums; e2e = pinned uint16 RAW frame in, metrics out.
+  train_step   configs[2]: synthetic-pair training step, 8 crops of 4x512x512 per GPU (64 global on 8 GPUs): fused noise
+               synthesis -> UNetSeeInDark forward -> L1 -> backward -> gradient all-reduce -> Adam; bf16 tensor cores.
 Every rank processes its own crops / frames (weak scaling, no data-path collective); crop ids — and so
 the Philox streams — are global.  One JSON line on stdout (rank 0).
 """
@@ -47,8 +49,14 @@ WORKLOADS = {
                           n=1, c=4, h=1424, w=2128, bound="tensor", dtype="bf16",
                           desc="sony_evaltest (BASELINE configs[4]): per frame pack + 'pgrq' synthesis at ratio 100/200/300 + ResUnet "
                                "forward + clamp/IlluminanceCorrect + PSNR/SSIM partial sums"),
+    "train_step": dict(metric="raw megapixels/sec (synthetic-pair training step: noise synthesis + UNetSeeInDark fwd/bwd + Adam, "
+                              "8 crops of 4x512x512 per GPU)", n=8, c=4, h=512, w=512, bound="tensor", dtype="bf16",
+                       desc="train_step (BASELINE configs[2]): per GPU 8 crops 4x512x512 -> 'pgrq' synthesis -> UNetSeeInDark "
+                            "forward + L1 + backward (bf16 tcgen05, fp32 accumulate) -> gradient all-reduce (DDP) -> Adam"),
 }
 RESUNET_FLOP_PER_PIXEL = 119424.0
+# forward + data gradients + weight gradients; conv1_1 needs no data gradient
+UNET_TRAIN_FLOP_PER_PIXEL = 3 * UNET_FLOP_PER_PIXEL - 2 * 9 * 4 * 32
 
 
 # ----------------------------------------------------------------------------------------------
@@ -164,6 +172,33 @@ def _cpu_unet_frames(wl, frames, threads, resunet=False):
     return time.perf_counter() - t0
 
 
+def _cpu_train_steps(steps, threads, crops=2):
+    """trainer_SID.py:93-101 on the CPU: per-crop generate_noisy_obs, fp32 autograd through the oracle UNet, Adam."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    O = _oracle()
+    import pnnp_b200 as P
+    torch.set_num_threads(threads)
+    torch.manual_seed(1997)
+    net = P.UNetSeeInDark(ARCH)
+    P.initialize_weights(net)
+    params = {k: v.clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    rs = np.random.RandomState(7)
+    hr = rs.rand(crops, 4, 512, 512).astype(np.float32) ** 2
+    t0 = time.perf_counter()
+    for s in range(steps):
+        np.random.seed(s)
+        lr = np.stack([np.clip(O.generate_noisy_obs(hr[i], param=O.sample_params("SonyA7S2"), noise_code=NOISE_CODE), None, 1.0)
+                       for i in range(crops)])
+        opt.zero_grad()
+        loss = F.l1_loss(O.unet_forward(torch.from_numpy(lr), params).clamp(0, 1), torch.from_numpy(hr))
+        loss.backward()
+        opt.step()
+    return time.perf_counter() - t0, crops
+
+
 def cpu_baseline(name, wl):
     cores = os.cpu_count() or 1
     if name == "synth64":
@@ -174,6 +209,11 @@ def cpu_baseline(name, wl):
         return {"value": n * 4 * 512 * 512 / 1e6 / busy, "unit": UNIT, "cores": 1, "kind": "port",
                 "sample": f"{n} of 64 crops (4x512x512, '{NOISE_CODE}'), sequential, oracle_np.generate_noisy_obs "
                           "(NumPy/SciPy are single-threaded)"}
+    if name == "train_step":
+        dt, k = _cpu_train_steps(1, cores)
+        return {"value": k * 4 * 512 * 512 / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"1 step on {k} of 8 crops (4x512x512): oracle generate_noisy_obs + torch CPU fp32 autograd of "
+                          f"oracle_np.unet_forward + Adam, {cores} threads"}
     dt = _cpu_unet_frames(wl, 1, cores, resunet=(name == "sony_evaltest"))
     what = "generate_noisy_obs + resunet_forward (metrics excluded)" if name == "sony_evaltest" else "unet_forward"
     return {"value": wl["c"] * wl["h"] * wl["w"] / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -199,6 +239,13 @@ def run_reference_arm(args, name, wl):
         mp_step = per_step * 4 * 512 * 512 / 1e6
         sample = f"{per_step} crops per step on {workers} worker processes (oracle port of generate_noisy_obs)"
         used = workers
+    elif name == "train_step":
+        steps = min(args.steps, 2)
+        dt, k = _cpu_train_steps(steps, cores)
+        dt = dt * args.steps / steps
+        mp_step = k * 4 * 512 * 512 / 1e6
+        sample = f"{k} of 8 crops per step ({steps} steps timed, scaled to {args.steps}), torch CPU fp32 autograd on {cores} threads"
+        used = cores
     else:
         steps = min(args.steps, 3)                             # ~5 s per frame on 8 cores
         rn = name == "sony_evaltest"
@@ -274,6 +321,27 @@ def run_gpu_arm(args, name, wl):
         algo = elems * 8.0                                                     # 4 B read + 4 B write per element
         l2_note = "no flush: 268 MB in + 268 MB out per step exceed the 126 MB L2"
         kernel = "noise_synth_kernel"
+    elif name == "train_step":
+        from pnnp_b200.train import UNetTrainStep
+        torch.manual_seed(1997)
+        net = P.UNetSeeInDark(ARCH).to(device)
+        P.initialize_weights(net)
+        trainer = UNetTrainStep(net, lr=1e-4)
+        clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2
+        np.random.seed(1997 + rank)
+        params = [P.sample_params("SonyA7S2") for _ in range(n)]
+        table = P.ParamTable(params, device)
+        noisy = torch.empty_like(clean)
+        crop0 = rank * n
+        losses = []
+
+        def step():
+            P.synthesize_batch(clean, None, NOISE_CODE, _lib.CHAIN_NUMPY, post_clip=(-float("inf"), 1.0),
+                               generator=gen, crop_id0=crop0, out=noisy, table=table)
+            losses.append(trainer.step(noisy, clean))
+        algo = UNET_TRAIN_FLOP_PER_PIXEL * elems
+        l2_note = "no flush: saved activations of a step (2.7 GB) exceed the 126 MB L2"
+        kernel = "conv_gemm_tc_kernel (fwd + dgrad) + wgrad_tc_kernel"
     elif name == "sony_evaltest":
         from pnnp_b200.pipeline import EvalPipeline
         from pnnp_b200.metrics import eval_partial_sums
@@ -344,6 +412,24 @@ def run_gpu_arm(args, name, wl):
             pipe.run(host_in, host_out, params, NOISE_CODE, generator=gen, crop_id0=crop0, post_clip=(-float("inf"), 1.0))
         h2d, d2h = elems * 4 + n * 128, elems * 4
         api = "pnnp_b200.pipeline.HostSynthPipeline.run (pinned host crops in, pinned host noisy crops out)"
+    elif name == "train_step":
+        # the loop body of trainer_SID.py:93-101 with host-resident clean crops (what the DataLoader hands over):
+        # H2D of the clean crops, synthesis + step on the device, the loss back on the host every step
+        host_clean = [clean.cpu().pin_memory(), clean.cpu().pin_memory()]
+        dev_clean = torch.empty_like(clean)
+        host_loss = torch.zeros(1).pin_memory()
+        st3 = {"i": 0}
+
+        def e2e_step():
+            i = st3["i"]
+            st3["i"] += 1
+            dev_clean.copy_(host_clean[i % 2], non_blocking=True)
+            P.synthesize_batch(dev_clean, None, NOISE_CODE, _lib.CHAIN_NUMPY, post_clip=(-float("inf"), 1.0),
+                               generator=gen, crop_id0=crop0, out=noisy, table=table)
+            host_loss.copy_(trainer.step(noisy, dev_clean).reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the reference logs loss.item() every step
+        h2d, d2h = elems * 4, 4
+        api = "pnnp_b200.train.UNetTrainStep.step on pinned host clean crops: H2D + synthesis + fwd/bwd/Adam + loss D2H"
     elif name == "sony_evaltest":
         pipe = EvalPipeline(net, 2 * h, 2 * w, 16383, 512, NOISE_CODE, brightness_correct=True, device=device)
         host_raw = [raw.cpu().pin_memory(), raw.cpu().pin_memory()]
@@ -395,6 +481,9 @@ def run_gpu_arm(args, name, wl):
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if name == "train_step":
+            line["config"]["global_batch"] = world * n
+            line["loss_first_last"] = [float(losses[0]), float(losses[-1])]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(name, wl)
         print(json.dumps(line), flush=True)

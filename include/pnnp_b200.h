@@ -17,6 +17,7 @@
 #ifndef PNNP_B200_H
 #define PNNP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -124,6 +125,7 @@ int pnnp_noise_synth_replay(const float* clean, float* noisy, const pnnp_noise_p
 /* 3x3 s1 p1 with the x-shift folded into N: weights [ky][kx*cout + co][cin], MMA N = 3*cout, the three
  * kx partial sums are combined across neighbouring pixels in the epilogue (cout <= 80) */
 #define PNNP_CONV3X 4
+#define PNNP_CONV2S2 5 /* nn.Conv2d(k=2, s=2, p=0): the data gradient of ConvTranspose2d(2, stride 2); weights [a*2+b][cout][cin] */
 #define PNNP_ACT_NONE 0
 #define PNNP_ACT_LEAKY02 1 /* nn.LeakyReLU(0.2)  Unet.py:52    */
 #define PNNP_ACT_RELU 2    /* nn.ReLU            ResUnet.py:44 */
@@ -183,6 +185,38 @@ int pnnp_crop_aug(const float* frame, float* out, int c, int h, int w, int patch
  * (h-6)(w-6) valid centres].  PSNR = 10 log10(255^2 c h w / sse); SSIM = mean_c(sum_c / ((h-6)(w-6))). */
 int pnnp_eval_epilogue(const float* dn, const float* hr, int n, int c, int h, int w, float scale,
                        int brightness_correct, double* sums, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * T1 — synthetic-pair training step (trainer_SID.py:93-101): L1 loss on pred.clamp(0,1)
+ * (losses/base_loss.py:92-103), backward through the UNet, Adam (trainer_SID.py:44).
+ * dgrad of a 3x3 conv = pnnp_conv2d_tc with transposed + flipped weights; the rest:
+ * ------------------------------------------------------------------------------------------ */
+/* loss_sum (device double) = sum |clamp(pred,0,1) - hr|;  gpred = d(mean L1)/d pred (NCHW fp32) */
+int pnnp_l1_loss(const float* pred, const float* hr, float* gpred, size_t total, double* loss_sum, void* stream);
+/* backward of the 1x1 head (conv10_1): gact = NHWC bf16 gradient w.r.t. the pre-activation of the layer feeding
+ * it (act' applied), dW[co][cin] / db[co] / dbias_prev[cin] accumulated in fp32 */
+int pnnp_head_bwd(const float* gpred, const void* act, const float* W, void* gact, float* dW, float* db,
+                  float* dbias_prev, int n, int h, int w, int cin, int co, int act_kind, void* stream);
+/* in place: g (NHWC bf16, w.r.t. activated output) *= act'(out); dbias[c] += sum over pixels (may be NULL) */
+int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t pixels, int c, int act_kind, void* stream);
+/* MaxPool2d(2) backward; gskip (optional) is added: gc = gskip + scatter(gp) (the U-Net skip connection) */
+int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c,
+                     void* stream);
+/* NHWC bf16 channels [c_off, c_off+c) -> channel-major [copies][c][out_row_elems] over a zero-ringed geometry of
+ * (h/stride + 2) rows x wp columns per image (wp >= w/stride + 2, a multiple of 8).  copies = 3 writes the three x-shifted
+ * versions out[s][ch][q] = base[ch][q + s - 1] the 3x3 weight-gradient GEMM reads for dx = 0,1,2 (a TMA box cannot start at
+ * an innermost coordinate that is not 16-byte aligned).  stride 2 + phase (pa, pb) sub-samples (ConvTranspose wgrad). */
+int pnnp_transpose_pad(const void* in, void* out, int n, int h, int w, int c_stride, int c_off, int c, int stride,
+                       int pa, int pb, size_t out_row_elems, int wp, int copies, void* stream);
+/* dW[tap][co][ci_off + ci] += sum_q gT[co][q] * xT[tap_plane[tap]][ci][q + tap_off[tap]]  (tcgen05 split-K GEMM, fp32
+ * atomics).  xT: [planes][ci][row_elems]; tap_off must be multiples of 8; tap_plane_host may be NULL (all taps plane 0). */
+int pnnp_wgrad_tc(const void* gT, const void* xT, size_t row_elems, size_t valid_elems, int co, int ci, int taps_total,
+                  const int* tap_off_host, const int* tap_plane_host, int planes, float* dw, int ci_off, int ci_total,
+                  void* stream);
+int pnnp_wgrad_pipeline_error(void);
+/* torch.optim.Adam step (no weight decay) over flat fp32 buffers; g is multiplied by gscale first */
+int pnnp_adam_step(float* p, const float* g, float* m, float* v, size_t total, float lr, float b1, float b2, float eps,
+                   int step, float gscale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,11 +58,19 @@ SIGNATURES = {
     "pnnp_conv_pipeline_error": (_i, []),
     "pnnp_nchw_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "pnnp_maxpool2x2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "pnnp_l1_loss": (_i, [_vp, _vp, _vp, C.c_size_t, _vp, _vp]),
+    "pnnp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pnnp_act_bwd_bias": (_i, [_vp, _vp, _vp, C.c_size_t, _i, _i, _vp]),
+    "pnnp_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pnnp_transpose_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.c_size_t, _i, _i, _vp]),
+    "pnnp_wgrad_tc": (_i, [_vp, _vp, C.c_size_t, C.c_size_t, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _vp, _i, _i, _vp]),
+    "pnnp_wgrad_pipeline_error": (_i, []),
+    "pnnp_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, _i, _f, _vp]),
     "pnnp_crop_aug": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]),
     "pnnp_eval_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
 }
 
-CONV3, CONV1, CONVT, CONV3S2, CONV3X = 0, 1, 2, 3, 4
+CONV3, CONV1, CONVT, CONV3S2, CONV3X, CONV2S2 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 OUT_NHWC_BF16, OUT_NCHW_F32 = 0, 1
 

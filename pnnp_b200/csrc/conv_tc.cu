@@ -27,6 +27,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "abi_common.h"
+#include "tc_common.cuh"
 #include "../../include/pnnp_b200.h"
 
 namespace pnnp {
@@ -35,9 +36,8 @@ constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
 constexpr int kMaxGroups = 4;            // epilogue groups == TMEM accumulator buffers (2 when N > 128, else 4)
 constexpr int kConvThreadsMax = 64 + 128 * kMaxGroups;   // warp 0 TMA, warp 1 MMA, then 4 epilogue warps per group
 constexpr int kMaxStages = 8;
-constexpr uint32_t kSpinLimit = 1u << 27;      // ~ seconds; a broken pipeline terminates instead of hanging the GPU
 
-enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2, MODE_CONV3S2 = 3, MODE_CONV3X = 4 };
+enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2, MODE_CONV3S2 = 3, MODE_CONV3X = 4, MODE_CONV2S2 = 5 };
 constexpr int kTileWX = 14;             // output columns per tile in MODE_CONV3X (16 partial-sum columns, 1 halo each side)
 enum { OUT_NHWC_BF16 = 0, OUT_NCHW_F32 = 1 };
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
@@ -68,74 +68,6 @@ struct ConvParams {
     int dbg;                        // timing experiments only: 1 skip stores, 2 skip MMAs, 4 skip A loads, 8 skip epilogue math
     int* err;
 };
-
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Spin on an mbarrier phase.  Returns nothing on purpose: loop control of the callers must not depend
-// on inline-asm outputs, otherwise nvcc treats the whole role loop as divergent and wraps every
-// tcgen05.mma in an ELECT/R2UR waterfall.  A wait that exceeds kSpinLimit polls raises the global error
-// word; once it is set every later wait returns after a single poll, so a broken pipeline terminates
-// in bounded time instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-    uint32_t ok = 0, it = 0;
-#pragma unroll 1
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-        if ((++it & 0x3FFu) == 0) {
-            if (*reinterpret_cast<volatile int*>(err) != 0) return;
-            if (it >= kSpinLimit) { atomicExch(err, code); return; }
-        }
-    }
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
-__device__ __forceinline__ uint64_t umma_desc_hi(int swz) {
-    const uint64_t layout = swz == 128 ? 2ull : (swz == 64 ? 4ull : 6ull);
-    const uint64_t sbo = (uint64_t)((8 * swz) >> 4);
-    return (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-__device__ __forceinline__ uint64_t umma_desc(uint64_t hi, uint32_t saddr) { return hi | (uint64_t)((saddr >> 4) & 0x3FFFu); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
@@ -180,12 +112,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int taps_per_stage = TPS;
-    const int dx_count = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : 1);   // pipeline stages per K chunk
+    const int dx_count = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV2S2 ? 4 : 1));   // pipeline stages per K chunk
     const int chunks0 = p.cin0 / p.kc, chunks1 = p.nsrc > 1 ? p.cin1 / p.kc : 0;
     const int ksteps = (chunks0 + chunks1) * dx_count;
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
     const uint32_t stage_tx = (uint32_t)(p.a_bytes + (p.b_resident ? 0 : taps_per_stage * p.umma_n * p.swz));
-    const int taps_total = p.mode == MODE_CONV3 ? 9 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV3X ? 3 : 1));
+    const int taps_total = p.mode == MODE_CONV3 ? 9 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV3X ? 3 : (p.mode == MODE_CONV2S2 ? 4 : 1)));
 
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.head_out)
@@ -246,13 +178,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 if ((p.dbg & 4) && (t != (int)blockIdx.x)) { if (elect_one()) mbar_arrive(fb); }
                 else if (elect_one()) {
                     mbar_expect_tx(fb, stage_tx);
-                    if (p.mode == MODE_CONV3S2)      // stride 2: one box per tap, TMA element stride 2 in x and y
+                    if (p.mode == MODE_CONV2S2)      // 2x2 stride 2, no padding (ConvTranspose2d dgrad): tap = a*2+b
+                        tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx & 1), 2 * y0 + (dx >> 1), img);
+                    else if (p.mode == MODE_CONV3S2) // stride 2: one box per tap, TMA element stride 2 in x and y
                         tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx % 3) - 1, 2 * y0 + (dx / 3) - 1, img);
                     else
                         tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - yhalo, img);
                     for (int dy = 0; dy < (p.b_resident ? 0 : taps_per_stage); ++dy) {
                         const int tap = p.mode == MODE_CONV3 ? dy * 3 + dx
-                                      : (p.mode == MODE_CONV3S2 ? dx : (p.mode == MODE_CONV3X ? dy : 0));
+                                      : ((p.mode == MODE_CONV3S2 || p.mode == MODE_CONV2S2) ? dx : (p.mode == MODE_CONV3X ? dy : 0));
                         tma_load_3d(sb + dy * p.b_tap_stride, &tmB, fb, cin_off, n_off, tap);
                     }
                 }
@@ -270,7 +204,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const uint32_t b_tap_stride = (uint32_t)p.b_tap_stride >> 4;
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0, p.err, 105);
-        const int dxc = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : 1);
+        const int dxc = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV2S2 ? 4 : 1));
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 102);
             int chunk = 0, dx = 0;
@@ -581,10 +515,11 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (out_mode == OUT_NHWC_BF16 && (cout % 16)) return fail("conv: NHWC output needs cout % 16 == 0");
     if (mode == MODE_CONVT ? (w_rows != cout) : (w_rows < n_tiles * umma_n)) return fail("conv: weight tensor has the wrong number of rows");
     if (mode == MODE_CONV3X && d.resid) return fail("conv3x: residual add is not supported in this mode");
-    const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : (mode == MODE_CONVT ? 4 : (mode == MODE_CONV3X ? 3 : 1));
-    if (mode == MODE_CONV3S2 && (nsrc > 1 || (h & 1) || (w & 1))) return fail("stride-2 conv: single source, even h and w");
+    const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : ((mode == MODE_CONVT || mode == MODE_CONV2S2) ? 4 : (mode == MODE_CONV3X ? 3 : 1));
+    const bool s2 = mode == MODE_CONV3S2 || mode == MODE_CONV2S2;
+    if (s2 && (nsrc > 1 || (h & 1) || (w & 1))) return fail("stride-2 conv: single source, even h and w");
     const int in_h = h, in_w = w;
-    if (mode == MODE_CONV3S2) { h /= 2; w /= 2; }        // tile over the OUTPUT grid
+    if (s2) { h /= 2; w /= 2; }        // tile over the OUTPUT grid
     const int tps = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? 3 : 1;
     const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? kTileH + 2 : kTileH;
     // shrink the K chunk until at least 3 pipeline stages fit
@@ -627,7 +562,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
     p.err = g_err_dev;
     CUtensorMap tmA0, tmA1, tmB;
-    if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, mode == MODE_CONV3S2 ? 2 : 1)) return e;
+    if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, s2 ? 2 : 1)) return e;
     if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz)) return e; }
     else tmA1 = tmA0;
     if (mode == MODE_CONVT) { if (int e = make_w_map(&tmB, weight, 1, 4 * cout, cin0, kc, umma_n, swz)) return e; }

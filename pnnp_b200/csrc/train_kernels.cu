@@ -1,0 +1,296 @@
+// Backward-pass helper kernels of the synthetic-pair training step (T1: trainer_SID.py:93-101,
+// losses/base_loss.py:92-103 — L1 loss on pred.clamp(0,1), Adam lr 1e-4).  The GEMM-shaped parts of
+// the backward (dgrad, wgrad) run on the tcgen05 kernels (conv_tc.cu, wgrad_tc.cu); everything here
+// is element-wise / small-reduction work on CUDA cores:
+//   l1_loss_kernel        loss = mean |clamp(pred,0,1) - hr| and d loss / d pred            (NCHW fp32)
+//   head_bwd_kernel       backward of the 1x1 head conv10_1 (4 <- 32): data, weight and bias gradients
+//   act_bwd_bias_kernel   g *= act'(out) in place (LeakyReLU 0.2 / ReLU / none) + per-channel bias gradient
+//   maxpool_bwd_kernel    routes the pooled gradient to the arg-max of each 2x2 window (+ skip gradient)
+//   transpose_pad_kernel  NHWC bf16 -> [C][n (h+2)(w+2)] bf16 with a zero ring (K-major operands of wgrad)
+//   adam_kernel           fused Adam over a flat fp32 parameter buffer
+#include <cuda_bf16.h>
+#include "abi_common.h"
+#include "../../include/pnnp_b200.h"
+
+namespace pnnp {
+
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- L1 loss (F.l1_loss(pred.clamp(0,1), hr), mean reduction)
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ pred, const float* __restrict__ hr,
+                                                      float* __restrict__ gpred, size_t total, float inv_total, double* loss_sum) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float p = pred[i], t = hr[i];
+        const float pc = fminf(fmaxf(p, 0.f), 1.f);
+        const float d = pc - t;
+        acc += (double)fabsf(d);
+        // d|x|/dx = sign(x) (0 at 0, as torch); clamp passes the gradient only for 0 <= p <= 1 (torch.clamp semantics)
+        const float s = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        gpred[i] = (p >= 0.f && p <= 1.f) ? s * inv_total : 0.f;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum, acc);
+}
+
+// ---------------------------------------------------------------- 1x1 head backward (out_nc <= 4, cin <= 64)
+// gpred: NCHW fp32 [n][co][h][w]; act: NHWC bf16 [n,h,w,cin] = LeakyReLU output feeding the head;
+// gact (out): NHWC bf16 gradient w.r.t. the PRE-activation of that layer (already multiplied by act');
+// dW[co][cin], db[co]: fp32, accumulated with atomics.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gpred, const __nv_bfloat16* __restrict__ act,
+                                                       const float* __restrict__ W, __nv_bfloat16* __restrict__ gact,
+                                                       float* dW, float* db, float* dbias_prev, int n, int h, int w, int cin,
+                                                       int co, int act_kind) {
+    extern __shared__ float s_acc[];                 // [co*cin] dW + [co] db + [cin] bias gradient of the previous conv
+    float* s_dw = s_acc; float* s_db = s_acc + co * cin; float* s_dbp = s_db + co;
+    for (int i = threadIdx.x; i < co * cin + co + cin; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    // work item = (pixel, channel pair); 256 * gridDim is a multiple of cin/2, so a thread keeps its channel pair and
+    // accumulates its slice of dW / db / dbias in registers over all of its pixels
+    const int cp_count = cin / 2;
+    const size_t plane = (size_t)h * w, total = (size_t)n * plane * cp_count;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(tid % cp_count) * 2;
+    float w0[4], w1[4], adw0[4] = {0, 0, 0, 0}, adw1[4] = {0, 0, 0, 0}, adb[4] = {0, 0, 0, 0}, abp0 = 0.f, abp1 = 0.f;
+    for (int o = 0; o < 4; ++o) { w0[o] = o < co ? W[o * cin + c] : 0.f; w1[o] = o < co ? W[o * cin + c + 1] : 0.f; }
+    for (size_t i = tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / cp_count;
+        const size_t img = pix / plane, off = pix - img * plane;
+        float gp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) if (o < co) gp[o] = gpred[(img * co + o) * plane + off];
+        const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(act + pix * cin + c);
+        const float a0 = __low2float(a2), a1 = __high2float(a2);
+        float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            g0 = fmaf(gp[o], w0[o], g0); g1 = fmaf(gp[o], w1[o], g1);
+            adw0[o] = fmaf(gp[o], a0, adw0[o]); adw1[o] = fmaf(gp[o], a1, adw1[o]);
+            if (c == 0) adb[o] += gp[o];
+        }
+        if (act_kind == 1) { g0 *= a0 > 0.f ? 1.f : 0.2f; g1 *= a1 > 0.f ? 1.f : 0.2f; }
+        else if (act_kind == 2) { g0 = a0 > 0.f ? g0 : 0.f; g1 = a1 > 0.f ? g1 : 0.f; }
+        abp0 += g0; abp1 += g1;       // pre-activation gradient: what the previous conv's bias gradient sums
+        *reinterpret_cast<__nv_bfloat162*>(gact + pix * cin + c) = __floats2bfloat162_rn(g0, g1);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) if (o < co) {
+        atomicAdd(&s_dw[o * cin + c], adw0[o]); atomicAdd(&s_dw[o * cin + c + 1], adw1[o]);
+        if (c == 0) atomicAdd(&s_db[o], adb[o]);
+    }
+    atomicAdd(&s_dbp[c], abp0); atomicAdd(&s_dbp[c + 1], abp1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < co * cin; i += blockDim.x) atomicAdd(&dW[i], s_dw[i]);
+    for (int i = threadIdx.x; i < co; i += blockDim.x) atomicAdd(&db[i], s_db[i]);
+    if (dbias_prev) for (int i = threadIdx.x; i < cin; i += blockDim.x) atomicAdd(&dbias_prev[i], s_dbp[i]);
+}
+
+// ---------------------------------------------------------------- activation backward + bias gradient
+// g (in/out): NHWC bf16 gradient w.r.t. the activated output -> w.r.t. the pre-activation; out: the activated
+// forward output (may be null for act == none); dbias[c] += sum over pixels of the pre-activation gradient.
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(__nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out,
+                                                           float* dbias, size_t pixels, int c, int act_kind) {
+    extern __shared__ float s_b[];                   // [c]
+    for (int i = threadIdx.x; i < c; i += blockDim.x) s_b[i] = 0.f;
+    __syncthreads();
+    const int c8 = c / 8;                            // 16-byte groups per pixel
+    const size_t total = pixels * c8;
+    // a thread keeps the same channel group while striding over pixels when blockDim*gridDim % c8 == 0
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int my_cg = -1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % c8);
+        if (cg != my_cg) {
+            if (my_cg >= 0) for (int k = 0; k < 8; ++k) { atomicAdd(&s_b[my_cg * 8 + k], acc[k]); acc[k] = 0.f; }
+            my_cg = cg;
+        }
+        uint4 gv = *reinterpret_cast<const uint4*>(g + i * 8);
+        __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&gv);
+        if (act_kind != 0) {
+            const uint4 ov = *reinterpret_cast<const uint4*>(out + i * 8);
+            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a = __low2float(g2[k]), b = __high2float(g2[k]);
+                const float oa = __low2float(o2[k]), ob = __high2float(o2[k]);
+                if (act_kind == 1) { a *= oa > 0.f ? 1.f : 0.2f; b *= ob > 0.f ? 1.f : 0.2f; }
+                else { a = oa > 0.f ? a : 0.f; b = ob > 0.f ? b : 0.f; }
+                g2[k] = __floats2bfloat162_rn(a, b);
+            }
+            *reinterpret_cast<uint4*>(g + i * 8) = gv;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[2 * k] += __low2float(g2[k]); acc[2 * k + 1] += __high2float(g2[k]); }
+    }
+    if (my_cg >= 0) for (int k = 0; k < 8; ++k) atomicAdd(&s_b[my_cg * 8 + k], acc[k]);
+    __syncthreads();
+    if (dbias) for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&dbias[i], s_b[i]);
+}
+
+// ---------------------------------------------------------------- 2x2 max-pool backward (+ skip-connection gradient)
+// gc[n,h,w,c] = (gskip ? gskip : 0) + gp[n,h/2,w/2,c] at the first arg-max of each window (row-major scan order, as torch)
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ gp, const __nv_bfloat16* __restrict__ cfull,
+                                                          const __nv_bfloat16* __restrict__ gskip, __nv_bfloat16* __restrict__ gc,
+                                                          int n, int h, int w, int c) {
+    const int ho = h / 2, wo = w / 2, c2 = c / 2;
+    const size_t total = (size_t)n * ho * wo * c2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c2);
+        size_t r = i / c2;
+        const int xo = (int)(r % wo); r /= wo;
+        const int yo = (int)(r % ho);
+        const int img = (int)(r / ho);
+        const size_t base = (((size_t)img * h + 2 * yo) * w + 2 * xo) * c + cc * 2;
+        const size_t idx[4] = {base, base + c, base + (size_t)w * c, base + (size_t)w * c + c};
+        float v0[4], v1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(cfull + idx[k]);
+            v0[k] = __low2float(t); v1[k] = __high2float(t);
+        }
+        int a0 = 0, a1 = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) { if (v0[k] > v0[a0]) a0 = k; if (v1[k] > v1[a1]) a1 = k; }
+        const __nv_bfloat162 gpv = *reinterpret_cast<const __nv_bfloat162*>(gp + (((size_t)img * ho + yo) * wo + xo) * c + cc * 2);
+        const float g0 = __low2float(gpv), g1 = __high2float(gpv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float s0 = 0.f, s1 = 0.f;
+            if (gskip) { const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(gskip + idx[k]); s0 = __low2float(t); s1 = __high2float(t); }
+            *reinterpret_cast<__nv_bfloat162*>(gc + idx[k]) = __floats2bfloat162_rn(s0 + (k == a0 ? g0 : 0.f), s1 + (k == a1 ? g1 : 0.f));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- NHWC -> channel-major with a zero ring
+// in: [n, h, w, c_stride] bf16 (channels [c_off, c_off + c) are taken);  out: [copies][c][out_row_elems] bf16.
+// Padded geometry per image: hp = ho + 2 rows of wp columns (wp >= wo + 2, a multiple of 8 so that a filter row shift is a
+// 16-byte aligned TMA coordinate);  base[ch][(img*hp + y+1)*wp + x+1] = in[img][y][x][ch], everything else 0.
+// copies == 1: out = base.  copies == 3: out[s][ch][q] = base[ch][q + s - 1] — the three x-shifted copies the wgrad GEMM reads
+// for the taps dx = 0, 1, 2 (TMA cannot start a box at an innermost coordinate that is not 16-byte aligned).
+// With stride 2 and phase (a,b): ho = h/2, wo = w/2 and the sample is in[img][2y+a][2x+b] (ConvTranspose wgrad operands).
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                            int n, int h, int w, int c_stride, int c_off, int c, int stride,
+                                                            int pa, int pb, size_t out_row_elems, int wp, int copies) {
+    __shared__ __nv_bfloat16 tile[34][33];
+    const int ho = h / stride, wo = w / stride, hp = ho + 2;
+    const size_t ppad = (size_t)n * hp * wp;
+    // grid: x = padded-pixel tiles of 32, y = channel tiles of 32; the tile holds pixels q0-1 .. q0+32
+    const size_t q0 = (size_t)blockIdx.x * 32;
+    const int ch0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 34; r += blockDim.y) {            // r: pixel within tile (+1), threadIdx.x: channel
+        const long long q = (long long)q0 + r - 1;
+        __nv_bfloat16 v = __float2bfloat16(0.f);
+        if (q >= 0 && (size_t)q < ppad && ch0 + (int)threadIdx.x < c) {
+            const int xp = (int)(q % wp);
+            const size_t t = q / wp;
+            const int yp = (int)(t % hp);
+            const int img = (int)(t / hp);
+            if (xp >= 1 && xp <= wo && yp >= 1 && yp <= ho)
+                v = in[(((size_t)img * h + (size_t)(yp - 1) * stride + pa) * w + (size_t)(xp - 1) * stride + pb) * c_stride + c_off + ch0 + threadIdx.x];
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    const size_t q = q0 + threadIdx.x;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {            // r: channel within tile, threadIdx.x: pixel
+        if (ch0 + r < c && q < out_row_elems) {
+            if (copies == 1) out[(size_t)(ch0 + r) * out_row_elems + q] = tile[threadIdx.x + 1][r];
+            else
+                for (int s = 0; s < 3; ++s) out[((size_t)s * c + ch0 + r) * out_row_elems + q] = tile[threadIdx.x + s][r];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- Adam (torch.optim.Adam defaults: betas .9/.999, eps 1e-8, no decay)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, size_t total, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2, float gscale) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / sqrtf(bc2) + eps;          // torch: (sqrt(v) / sqrt(bias_correction2)) + eps
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
+static int blocks_for(size_t items) { return (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, 148 * 8)); }
+
+}  // namespace pnnp
+
+using namespace pnnp;
+
+extern "C" int pnnp_l1_loss(const float* pred, const float* hr, float* gpred, size_t total, double* loss_sum, void* stream) {
+    if (!pred || !hr || !gpred || !loss_sum || !total) return fail("l1_loss: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PNNP_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
+    l1_loss_kernel<<<blocks_for(total), 256, 0, st>>>(pred, hr, gpred, total, 1.0f / (float)total, loss_sum);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_head_bwd(const float* gpred, const void* act, const float* W, void* gact, float* dW, float* db,
+                             float* dbias_prev, int n, int h, int w, int cin, int co, int act_kind, void* stream) {
+    if (!gpred || !act || !W || !gact || !dW || !db || co < 1 || co > 4 || cin > 64 || (cin & 1)) return fail("head_bwd: bad arguments");
+    const size_t smem = sizeof(float) * (size_t)(co * cin + co + cin);
+    head_bwd_kernel<<<blocks_for((size_t)n * h * w * (cin / 2)), 256, smem, (cudaStream_t)stream>>>(
+        gpred, static_cast<const __nv_bfloat16*>(act), W, static_cast<__nv_bfloat16*>(gact), dW, db, dbias_prev, n, h, w, cin, co, act_kind);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t pixels, int c, int act_kind, void* stream) {
+    if (!g || (act_kind && !out) || (c % 8) || c > 1024) return fail("act_bwd_bias: bad arguments");
+    // grid * 256 is a multiple of c/8 (c/8 is a power of two <= 128 for this network family): a thread keeps its channel group
+    act_bwd_bias_kernel<<<blocks_for(pixels * (c / 8)), 256, sizeof(float) * c, (cudaStream_t)stream>>>(
+        static_cast<__nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(out), dbias, pixels, c, act_kind);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c, void* stream) {
+    if (!gp || !cfull || !gc || (h & 1) || (w & 1) || (c & 1)) return fail("maxpool_bwd: bad arguments");
+    maxpool_bwd_kernel<<<blocks_for((size_t)n * (h / 2) * (w / 2) * (c / 2)), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(gp), static_cast<const __nv_bfloat16*>(cfull), static_cast<const __nv_bfloat16*>(gskip),
+        static_cast<__nv_bfloat16*>(gc), n, h, w, c);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_transpose_pad(const void* in, void* out, int n, int h, int w, int c_stride, int c_off, int c, int stride,
+                                  int pa, int pb, size_t out_row_elems, int wp, int copies, void* stream) {
+    if (!in || !out || stride < 1 || stride > 2 || (h % stride) || (w % stride) || (copies != 1 && copies != 3))
+        return fail("transpose_pad: bad arguments");
+    if (wp < w / stride + 2) return fail("transpose_pad: padded row pitch wp must be >= w/stride + 2");
+    const size_t ppad = (size_t)n * (h / stride + 2) * wp;
+    if (out_row_elems < ppad) return fail("transpose_pad: output rows too short");
+    dim3 grid((unsigned)((out_row_elems + 31) / 32), (unsigned)((c + 31) / 32)), block(32, 8);
+    transpose_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out),
+                                                                   n, h, w, c_stride, c_off, c, stride, pa, pb, out_row_elems, wp, copies);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_adam_step(float* p, const float* g, float* m, float* v, size_t total, float lr, float b1, float b2, float eps,
+                              int step, float gscale, void* stream) {
+    if (!p || !g || !m || !v || step < 1) return fail("adam_step: bad arguments");
+    const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+    adam_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, total, lr, b1, b2, eps, bc1, bc2, gscale);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}

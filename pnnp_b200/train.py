@@ -1,0 +1,254 @@
+"""Synthetic-pair training step (T1) for UNetSeeInDark on the B200 kernels.
+
+Reference loop body (trainer_SID.py:93-101):  pred = net(lr); loss = F.l1_loss(pred.clamp(0,1), hr)
+(losses/base_loss.py:92-103); loss.backward(); Adam(lr=1e-4).step()  (trainer_SID.py:44).
+
+Here the backward pass is explicit (no autograd graph, no eager fallback):
+  * data gradients of the 3x3 convs  = the SAME tcgen05 conv kernel with transposed + flipped weights;
+    ConvTranspose2d data gradient    = its 2x2 stride-2 mode;
+  * weight gradients                 = the tcgen05 split-K GEMM of csrc/wgrad_tc.cu over channel-major,
+    zero-ringed copies of the gradient and the layer input (a filter tap is a pixel offset);
+  * LeakyReLU', bias gradients, max-pool routing (+ skip-connection add), the 1x1 head, the L1 loss and Adam
+    are the CUDA-core kernels of csrc/train_kernels.cu.
+Parameters, gradients and Adam moments live in flat fp32 buffers (one all-reduce per step under DDP);
+activations and activation gradients are NHWC bf16.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .archs import UNetSeeInDark, _conv, _pad16, _to_nhwc16
+
+L = _lib
+
+
+def _pack_conv_weight(w4):
+    """[rows, cin, k, k] fp32 -> kernel layout [k*k][rows_pad16][cin_pad16] bf16."""
+    rows, cin, k = w4.shape[0], w4.shape[1], w4.shape[2]
+    buf = torch.zeros((k * k, _pad16(rows), _pad16(cin)), dtype=torch.bfloat16, device=w4.device)
+    buf[:, :rows, :cin] = w4.permute(2, 3, 0, 1).reshape(k * k, rows, cin).to(torch.bfloat16)
+    return buf
+
+
+def padded_pitch(w):
+    """Row pitch (pixels) of the zero-ringed channel-major wgrad operands: >= w + 2 and a multiple of 8 (TMA alignment)."""
+    return (w + 2 + 7) // 8 * 8
+
+
+def conv3_taps(w):
+    """(pixel offsets, x-shift planes) of the nine taps (dy, dx) of a 3x3 pad-1 conv over rows of padded_pitch(w) pixels."""
+    wp = padded_pitch(w)
+    return [(dy - 1) * wp for dy in range(3) for dx in range(3)], [dx for dy in range(3) for dx in range(3)]
+
+
+class _Scratch:
+    """Named device buffers reused across steps."""
+
+    def __init__(self, device):
+        self.device, self.bufs = device, {}
+
+    def get(self, name, shape, dtype=torch.bfloat16):
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t
+
+
+class UNetTrainStep:
+    """forward + L1 loss + backward + Adam for a UNetSeeInDark on one GPU (one rank of a DDP job)."""
+
+    def __init__(self, net: UNetSeeInDark, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.net = net
+        self.device = next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("pnnp_b200: the training step needs a CUDA device (no CPU fallback)")
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        # flat fp32 parameter / gradient / moment buffers; the module's parameters become views of the flat buffer
+        params = list(net.named_parameters())
+        total = sum(p.numel() for _, p in params)
+        self.flat_p = torch.empty(total, dtype=torch.float32, device=self.device)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.m, self.v = torch.zeros_like(self.flat_p), torch.zeros_like(self.flat_p)
+        self.slices, off = {}, 0
+        for name, p in params:
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + n].view_as(p)
+            self.slices[name] = (off, n, tuple(p.shape))
+            off += n
+        self.scr = _Scratch(self.device)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+
+    # ---------------------------------------------------------------- small wrappers over the C ABI
+    def _grad_view(self, name):
+        off, n, shape = self.slices[name]
+        return self.flat_g[off:off + n].view(shape)
+
+    def _stream(self):
+        return _lib.stream_ptr(self.device)
+
+    def _act_bwd(self, g, out, dbias, act):
+        pixels = g.numel() // g.shape[-1]
+        L.check(L.lib().pnnp_act_bwd_bias(g.data_ptr(), _lib.ptr(out), _lib.ptr(dbias), pixels, g.shape[-1], act, self._stream()),
+                "act_bwd_bias")
+
+    def _transpose(self, name, x, c_off, c, stride=1, pa=0, pb=0, copies=1):
+        """NHWC bf16 -> channel-major [copies][c][row] over the zero-ringed (h/stride+2) x wp geometry (wp % 8 == 0)."""
+        n, h, w, cs = x.shape
+        wp = padded_pitch(w // stride)
+        ppad = n * (h // stride + 2) * wp
+        row = (ppad + 63) // 64 * 64
+        out = self.scr.get(name, (copies, c, row))
+        L.check(L.lib().pnnp_transpose_pad(x.data_ptr(), out.data_ptr(), n, h, w, cs, c_off, c, stride, pa, pb, row, wp, copies,
+                                           self._stream()), "transpose_pad")
+        return out, row, ppad
+
+    def _wgrad(self, gT, xT, row, valid, co, ci, offs, planes, dw, ci_off, ci_total, dw_elem_off=0):
+        arr, pl = (C.c_int * len(offs))(*offs), (C.c_int * len(offs))(*planes)
+        L.check(L.lib().pnnp_wgrad_tc(gT.data_ptr(), xT.data_ptr(), row, valid, co, ci, len(offs), arr, pl, xT.shape[0],
+                                      dw.data_ptr() + 4 * dw_elem_off, ci_off, ci_total, self._stream()), "wgrad_tc")
+
+    # ---------------------------------------------------------------- layer backward passes
+    def _conv3_bwd(self, name, g, out_act, srcs, need_dx, act=_lib.ACT_LEAKY):
+        """g: NHWC bf16 gradient w.r.t. the activated output of conv `name` (modified in place to the pre-activation
+        gradient).  srcs: list of NHWC bf16 inputs (1, or 2 for torch.cat([up, skip], 1)).  Returns input gradients."""
+        m = self.net.get_submodule(name)
+        co = m.weight.shape[0]
+        n, h, w, _ = g.shape
+        self._act_bwd(g, out_act, self._grad_view(name + ".bias"), act)
+        gT, row, valid = self._transpose("gT", g, 0, co)
+        offs, planes = conv3_taps(w)
+        ci_total = sum(s.shape[-1] for s in srcs)
+        dw = self.scr.get("dw_" + name, (9, co, ci_total), torch.float32)
+        dw.zero_()
+        c_off = 0
+        for k, s in enumerate(srcs):
+            xT, _, _ = self._transpose(f"xT{k}", s, 0, s.shape[-1], copies=3)
+            self._wgrad(gT, xT, row, valid, co, s.shape[-1], offs, planes, dw, c_off, ci_total)
+            c_off += s.shape[-1]
+        cin_real = m.weight.shape[1]
+        self._grad_view(name + ".weight").copy_(dw[:, :, :cin_real].permute(1, 2, 0).reshape(co, cin_real, 3, 3))
+        gxs = []
+        if need_dx:
+            W = m.weight.detach()
+            c_off = 0
+            for k, s in enumerate(srcs):
+                ck = s.shape[-1]
+                wd = _pack_conv_weight(W[:, c_off:c_off + ck].transpose(0, 1).flip(2, 3))     # [ci][co][2-ky][2-kx]
+                gx = self.scr.get(f"gx_{name}_{k}", (n, h, w, ck))
+                _conv(_lib.CONV3, g, wd, None, gx, ck, _lib.ACT_NONE)
+                gxs.append(gx)
+                c_off += ck
+        return gxs
+
+    def _convT_bwd(self, name, g_up, x_in):
+        """ConvTranspose2d(2, stride 2) backward: g_up NHWC bf16 [n,2h,2w,co] -> g_in [n,h,w,ci]; dW [ci][co][2][2]; db."""
+        m = self.net.get_submodule(name)
+        ci, co = m.weight.shape[0], m.weight.shape[1]
+        n, h, w, _ = x_in.shape
+        self._act_bwd(g_up, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)
+        xT, row, valid = self._transpose("xT_up", x_in, 0, ci)
+        dw = self.scr.get("dw_" + name, (4, co, ci), torch.float32)
+        dw.zero_()
+        for a in range(2):
+            for b in range(2):
+                gT, _, _ = self._transpose("gT", g_up, 0, co, stride=2, pa=a, pb=b)
+                self._wgrad(gT, xT, row, valid, co, ci, [0], [0], dw, 0, ci, dw_elem_off=(a * 2 + b) * co * ci)
+        self._grad_view(name + ".weight").copy_(dw.permute(2, 1, 0).reshape(ci, co, 2, 2))
+        wd = _pack_conv_weight(m.weight.detach())            # [rows=ci][cin=co][a][b] -> [a*2+b][ci][co]
+        gx = self.scr.get("gx_" + name, (n, h, w, ci))
+        _conv(_lib.CONV2S2, g_up, wd, None, gx, ci, _lib.ACT_NONE)
+        return gx
+
+    # ---------------------------------------------------------------- the step
+    def forward(self, x):
+        """Training forward: like UNetSeeInDark.forward but every intermediate is kept (no fused head)."""
+        net, nf = self.net, self.net.nf
+        x = x.float().contiguous()
+        n, c, h, w = x.shape
+        if h % 16 or w % 16:
+            raise RuntimeError("pnnp_b200: h and w must be multiples of 16")
+        s = {}
+        buf = lambda name, hh, ww, cc: self.scr.get("a_" + name, (n, hh, ww, cc))
+        LK = _lib.ACT_LEAKY
+        cur = _to_nhwc16(x, buf("x16", h, w, 16))
+        s["x16"] = cur
+        hh, ww = h, w
+        for i in range(1, 6):
+            co = nf * 2 ** (i - 1)
+            s[f"in{i}_1"] = cur
+            s[f"c{i}a"] = net._conv3(f"conv{i}_1", cur, buf(f"c{i}a", hh, ww, co), co, LK)
+            if i < 5:
+                s[f"p{i}"] = buf(f"p{i}", hh // 2, ww // 2, co)
+                s[f"c{i}"] = net._conv3(f"conv{i}_2", s[f"c{i}a"], buf(f"c{i}", hh, ww, co), co, LK, pool_out=s[f"p{i}"])
+                cur, hh, ww = s[f"p{i}"], hh // 2, ww // 2
+            else:
+                s[f"c{i}"] = cur = net._conv3(f"conv{i}_2", s[f"c{i}a"], buf(f"c{i}", hh, ww, co), co, LK)
+        for i in range(6, 10):
+            co = nf * 2 ** (9 - i)
+            wu, bu = net._packed(f"upv{i}", "convT")
+            s[f"u{i}"] = _conv(_lib.CONVT, cur, wu, bu, buf(f"u{i}", hh * 2, ww * 2, co), co, _lib.ACT_NONE)
+            hh, ww = hh * 2, ww * 2
+            s[f"c{i}a"] = net._conv3(f"conv{i}_1", s[f"u{i}"], buf(f"c{i}a", hh, ww, co), co, LK, x1=s[f"c{10 - i}"])
+            s[f"c{i}"] = cur = net._conv3(f"conv{i}_2", s[f"c{i}a"], buf(f"c{i}", hh, ww, co), co, LK)
+        w10, b10 = net._packed("conv10_1")
+        pred = self.scr.get("pred", (n, net.out_nc, h, w), torch.float32)
+        _conv(_lib.CONV1, cur, w10, b10, pred, net.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,
+              resid_nchw=x if net.res else None)
+        s["pred"] = pred
+        return pred, s
+
+    def backward(self, gpred, s):
+        net, nf = self.net, self.net.nf
+        n, _, h, w = gpred.shape
+        LK = _lib.ACT_LEAKY
+        self.flat_g.zero_()
+        # 1x1 head: gradient w.r.t. conv9_2's pre-activation, dW10, db10 and conv9_2's bias gradient in one kernel
+        g = self.scr.get("g_c9", (n, h, w, nf))
+        m10 = net.conv10_1
+        L.check(L.lib().pnnp_head_bwd(gpred.data_ptr(), s["c9"].data_ptr(), m10.weight.detach().reshape(net.out_nc, nf).data_ptr(),
+                                      g.data_ptr(), self._grad_view("conv10_1.weight").data_ptr(),
+                                      self._grad_view("conv10_1.bias").data_ptr(), None, n, h, w, nf, net.out_nc, LK,
+                                      self._stream()), "head_bwd")
+        # decoder
+        g_skip = {}
+        for i in range(9, 5, -1):
+            act = _lib.ACT_NONE if i == 9 else LK            # conv9_2's act' is already applied by the head kernel
+            (g,) = self._conv3_bwd(f"conv{i}_2", g, s[f"c{i}"], [s[f"c{i}a"]], True, act=act)
+            g_up, g_skip[10 - i] = self._conv3_bwd(f"conv{i}_1", g, s[f"c{i}a"], [s[f"u{i}"], s[f"c{10 - i}"]], True)
+            src = s["c5"] if i == 6 else s[f"c{i - 1}"]
+            g = self._convT_bwd(f"upv{i}", g_up, src)
+        # encoder
+        for i in range(5, 0, -1):
+            if i < 5:
+                ci_ = s[f"c{i}"]
+                gc = self.scr.get(f"g_c{i}", tuple(ci_.shape))
+                L.check(L.lib().pnnp_maxpool_bwd(g.data_ptr(), ci_.data_ptr(), g_skip[i].data_ptr(), gc.data_ptr(),
+                                                 ci_.shape[0], ci_.shape[1], ci_.shape[2], ci_.shape[3], self._stream()), "maxpool_bwd")
+                g = gc
+            (g,) = self._conv3_bwd(f"conv{i}_2", g, s[f"c{i}"], [s[f"c{i}a"]], True)
+            res = self._conv3_bwd(f"conv{i}_1", g, s[f"c{i}a"], [s[f"in{i}_1"]], i > 1)
+            if i > 1:
+                g = res[0]
+
+    def step(self, lr_crops, hr_crops, grad_allreduce=True):
+        """One optimisation step on (noisy, clean) crops (CUDA fp32 NCHW).  Returns the loss as a 0-d CUDA tensor."""
+        pred, saved = self.forward(lr_crops)
+        hr = hr_crops.float().contiguous()
+        gpred = self.scr.get("gpred", tuple(pred.shape), torch.float32)
+        L.check(L.lib().pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gpred.data_ptr(), pred.numel(), self.loss_sum.data_ptr(),
+                                     self._stream()), "l1_loss")
+        self.backward(gpred, saved)
+        gscale = 1.0
+        if grad_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)          # DDP: average of the per-rank mean losses
+            gscale = 1.0 / dist.get_world_size()
+        self.t += 1
+        L.check(L.lib().pnnp_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                       self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale,
+                                       self._stream()), "adam_step")
+        self.net.__dict__.get("_pack_cache", {}).clear()                # weights changed in place: repack on next use
+        return (self.loss_sum / pred.numel()).float()[0]

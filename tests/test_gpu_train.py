@@ -1,0 +1,315 @@
+"""T1 — synthetic-pair training step (trainer_SID.py:93-101, losses/base_loss.py:92-103) through the C ABI.
+
+Every backward kernel is checked against torch autograd in fp32 on the same (bf16-rounded) operands, then the
+whole step (forward + L1 + backward + Adam) against an fp32 torch restatement of the reference loop body.
+Tolerances: activations and activation gradients are bf16 (2^-8 relative per rounding), accumulation fp32; weight
+gradients are compared by relative L2 error per parameter tensor (stated at each assert)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle_np as O
+import pnnp_b200 as P
+from pnnp_b200 import _lib, archs, train
+
+pytestmark = pytest.mark.gpu
+L = _lib
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _sp():
+    return L.stream_ptr(torch.device("cuda"))
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _ok():
+    torch.cuda.synchronize()
+    assert L.lib().pnnp_conv_pipeline_error() == 0 and L.lib().pnnp_wgrad_pipeline_error() == 0
+
+
+def test_l1_loss_and_gradient_match_torch():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pred = (torch.rand((2, 4, 32, 48), device="cuda", generator=g) * 1.4 - 0.2).requires_grad_(True)
+    hr = torch.rand((2, 4, 32, 48), device="cuda", generator=g)
+    loss = F.l1_loss(pred.clamp(0, 1), hr)
+    loss.backward()
+    gp = torch.empty_like(hr)
+    s = torch.zeros(1, dtype=torch.float64, device="cuda")
+    L.check(L.lib().pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gp.data_ptr(), pred.numel(), s.data_ptr(), _sp()), "l1")
+    assert abs(s.item() / pred.numel() - loss.item()) < 1e-6
+    assert torch.equal(gp, pred.grad)                      # +-1/N or 0: exact
+    assert abs(O.l1_loss(pred.detach().cpu().numpy(), hr.cpu().numpy()) - s.item() / pred.numel()) < 1e-6
+
+
+def test_adam_matches_torch_optim():
+    g = torch.Generator(device="cuda").manual_seed(1)
+    p0 = torch.randn(10007, device="cuda", generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-4)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for t in range(1, 4):
+        gr = torch.randn(10007, device="cuda", generator=g)
+        ref.grad = gr.clone()
+        opt.step()
+        L.check(L.lib().pnnp_adam_step(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-4, 0.9, 0.999,
+                                       1e-8, t, 1.0, _sp()), "adam")
+        assert (p - ref.detach()).abs().max().item() < 2e-7      # same formula, fp32; ulp-level differences only
+
+
+@pytest.mark.parametrize("act", [L.ACT_LEAKY, L.ACT_RELU, L.ACT_NONE])
+def test_act_backward_and_bias_gradient(act):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n, h, w, c = 2, 24, 40, 64
+    out = _bf(torch.randn((n, h, w, c), device="cuda", generator=g))
+    go = _bf(torch.randn((n, h, w, c), device="cuda", generator=g))
+    gk = go.to(torch.bfloat16).clone()
+    db = torch.zeros(c, device="cuda")
+    ob = out.to(torch.bfloat16)
+    L.check(L.lib().pnnp_act_bwd_bias(gk.data_ptr(), ob.data_ptr() if act else None, db.data_ptr(),
+                                      n * h * w, c, act, _sp()), "act_bwd")
+    slope = {L.ACT_LEAKY: torch.where(out > 0, 1.0, 0.2), L.ACT_RELU: (out > 0).float(), L.ACT_NONE: torch.ones_like(out)}[act]
+    want = _bf(go * slope)
+    assert torch.equal(gk.float(), want)
+    assert (db - want.sum((0, 1, 2))).abs().max().item() < 1e-2
+
+
+def test_maxpool_backward_with_skip():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, h, w, c = 2, 16, 32, 32
+    x = _bf(torch.randn((n, c, h, w), device="cuda", generator=g)).requires_grad_(True)
+    gp = _bf(torch.randn((n, c, h // 2, w // 2), device="cuda", generator=g))
+    gs = _bf(torch.randn((n, c, h, w), device="cuda", generator=g))
+    F.max_pool2d(x, 2).backward(gp)
+    gc = torch.empty((n, h, w, c), dtype=torch.bfloat16, device="cuda")
+    gpn, xn, gsn = _nhwc(gp), _nhwc(x.detach()), _nhwc(gs)
+    L.check(L.lib().pnnp_maxpool_bwd(gpn.data_ptr(), xn.data_ptr(), gsn.data_ptr(), gc.data_ptr(),
+                                     n, h, w, c, _sp()), "pool_bwd")
+    assert torch.equal(_nchw(gc), _bf(x.grad + gs))
+
+
+@pytest.mark.parametrize("stride,pa,pb,copies", [(1, 0, 0, 1), (1, 0, 0, 3), (2, 0, 1, 1), (2, 1, 0, 1)])
+def test_transpose_pad(stride, pa, pb, copies):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, h, w, c = 2, 12, 20, 48
+    x = torch.randn((n, h, w, c), device="cuda", generator=g).to(torch.bfloat16)
+    ho, wo = h // stride, w // stride
+    wp = train.padded_pitch(wo)
+    assert wp % 8 == 0 and wp >= wo + 2
+    ppad = n * (ho + 2) * wp
+    row = (ppad + 63) // 64 * 64
+    out = torch.full((copies, c, row), 7.0, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().pnnp_transpose_pad(x.data_ptr(), out.data_ptr(), n, h, w, c, 0, c, stride, pa, pb, row, wp, copies, _sp()), "tp")
+    base = torch.zeros((c, n, ho + 2, wp), dtype=torch.bfloat16, device="cuda")
+    base[:, :, 1:ho + 1, 1:wo + 1] = x[:, pa::stride, pb::stride, :].permute(3, 0, 1, 2)
+    flat = torch.zeros((c, row + 2), dtype=torch.bfloat16, device="cuda")       # flat[q + 1] = base[q], zero outside
+    flat[:, 1:ppad + 1] = base.reshape(c, -1)
+    for s in range(copies):
+        shift = s - 1 if copies == 3 else 0
+        assert torch.equal(out[s], flat[:, 1 + shift:1 + shift + row]), (s,)
+
+
+@pytest.mark.parametrize("ci,co,h,w,n", [(16, 32, 16, 32, 1), (32, 32, 24, 40, 2), (64, 128, 16, 16, 2), (128, 64, 16, 32, 1),
+                                         (256, 256, 8, 16, 1), (512, 256, 8, 8, 1), (256, 512, 8, 8, 2)])
+def test_wgrad_3x3_matches_autograd(ci, co, h, w, n):
+    g = torch.Generator(device="cuda").manual_seed(ci + co)
+    x = _bf(torch.randn((n, ci, h, w), device="cuda", generator=g))
+    go = _bf(torch.randn((n, co, h, w), device="cuda", generator=g))
+    wt = torch.zeros((co, ci, 3, 3), device="cuda", requires_grad=True)
+    F.conv2d(x, wt, padding=1).backward(go)
+    wp = train.padded_pitch(w)
+    ppad = n * (h + 2) * wp
+    row = (ppad + 63) // 64 * 64
+    gT = torch.empty((co, row), dtype=torch.bfloat16, device="cuda")
+    xT = torch.empty((3, ci, row), dtype=torch.bfloat16, device="cuda")
+    gon, xn = _nhwc(go), _nhwc(x)
+    L.check(L.lib().pnnp_transpose_pad(gon.data_ptr(), gT.data_ptr(), n, h, w, co, 0, co, 1, 0, 0, row, wp, 1, _sp()), "tp")
+    L.check(L.lib().pnnp_transpose_pad(xn.data_ptr(), xT.data_ptr(), n, h, w, ci, 0, ci, 1, 0, 0, row, wp, 3, _sp()), "tp")
+    offs, planes = train.conv3_taps(w)
+    dw = torch.zeros((9, co, ci), device="cuda")
+    L.check(L.lib().pnnp_wgrad_tc(gT.data_ptr(), xT.data_ptr(), row, ppad, co, ci, 9, (C.c_int * 9)(*offs), (C.c_int * 9)(*planes), 3,
+                                  dw.data_ptr(), 0, ci, _sp()), "wgrad")
+    _ok()
+    got = dw.permute(1, 2, 0).reshape(co, ci, 3, 3)
+    assert _rel(got, wt.grad) < 1e-4, _rel(got, wt.grad)          # bf16 operands are exact in both; fp32 summation order only
+
+
+@pytest.mark.parametrize("ci,co,h,w", [(64, 32, 16, 32), (512, 256, 8, 8)])
+def test_conv_transpose_backward_pieces(ci, co, h, w):
+    """ConvTranspose2d(2, s2): dgrad = the 2x2 stride-2 conv mode; wgrad = four phase-sampled GEMMs."""
+    g = torch.Generator(device="cuda").manual_seed(ci)
+    n = 2
+    x = _bf(torch.randn((n, ci, h, w), device="cuda", generator=g)).requires_grad_(True)
+    wt = _bf(torch.randn((ci, co, 2, 2), device="cuda", generator=g) / ci ** 0.5).requires_grad_(True)
+    go = _bf(torch.randn((n, co, 2 * h, 2 * w), device="cuda", generator=g))
+    F.conv_transpose2d(x, wt, stride=2).backward(go)
+    gx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device="cuda")
+    archs._conv(L.CONV2S2, _nhwc(go), train._pack_conv_weight(wt.detach()), None, gx, ci, L.ACT_NONE)
+    _ok()
+    assert _rel(_nchw(gx), x.grad) < 6e-3                          # bf16 output rounding
+    wp = train.padded_pitch(w)
+    ppad = n * (h + 2) * wp
+    row = (ppad + 63) // 64 * 64
+    xT = torch.empty((ci, row), dtype=torch.bfloat16, device="cuda")
+    xn = _nhwc(x.detach())
+    L.check(L.lib().pnnp_transpose_pad(xn.data_ptr(), xT.data_ptr(), n, h, w, ci, 0, ci, 1, 0, 0, row, wp, 1, _sp()), "tp")
+    dw = torch.zeros((4, co, ci), device="cuda")
+    gT = torch.empty((co, row), dtype=torch.bfloat16, device="cuda")
+    gon = _nhwc(go)
+    for a in range(2):
+        for b in range(2):
+            L.check(L.lib().pnnp_transpose_pad(gon.data_ptr(), gT.data_ptr(), n, 2 * h, 2 * w, co, 0, co, 2, a, b, row, wp, 1, _sp()), "tp")
+            L.check(L.lib().pnnp_wgrad_tc(gT.data_ptr(), xT.data_ptr(), row, ppad, co, ci, 1, (C.c_int * 1)(0), None, 1,
+                                          dw.data_ptr() + 4 * (a * 2 + b) * co * ci, 0, ci, _sp()), "wgrad")
+    _ok()
+    got = dw.permute(2, 1, 0).reshape(ci, co, 2, 2)
+    assert _rel(got, wt.grad) < 1e-4
+
+
+def test_head_backward():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, h, w, cin, co = 2, 16, 32, 32, 4
+    pre = _bf(torch.randn((n, cin, h, w), device="cuda", generator=g))
+    act = _bf(F.leaky_relu(pre, 0.2)).requires_grad_(True)
+    wt = (torch.randn((co, cin, 1, 1), device="cuda", generator=g) * 0.1).requires_grad_(True)
+    b = torch.zeros(co, device="cuda", requires_grad=True)
+    gp = torch.randn((n, co, h, w), device="cuda", generator=g)
+    F.conv2d(act, wt, b).backward(gp)
+    gact = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device="cuda")
+    dW, db, dbp = torch.zeros((co, cin), device="cuda"), torch.zeros(co, device="cuda"), torch.zeros(cin, device="cuda")
+    an, w2 = _nhwc(act.detach()), wt.detach().reshape(co, cin).contiguous()
+    L.check(L.lib().pnnp_head_bwd(gp.data_ptr(), an.data_ptr(), w2.data_ptr(),
+                                  gact.data_ptr(), dW.data_ptr(), db.data_ptr(), dbp.data_ptr(), n, h, w, cin, co, L.ACT_LEAKY, _sp()),
+            "head")
+    torch.cuda.synchronize()
+    want = act.grad * torch.where(act.detach() > 0, 1.0, 0.2)
+    assert _rel(_nchw(gact), want) < 6e-3
+    assert _rel(dW, wt.grad.reshape(co, cin)) < 1e-4 and _rel(db, b.grad) < 1e-4
+    assert _rel(dbp, want.sum((0, 2, 3))) < 1e-2
+
+
+def _reference_step(sd, lr_in, hr, steps=1):
+    """fp32 torch restatement of trainer_SID.py:93-101 on the oracle's functional UNet."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    losses, grads = [], None
+    for _ in range(steps):
+        opt.zero_grad()
+        pred = O.unet_forward(lr_in, params)
+        loss = F.l1_loss(pred.clamp(0, 1), hr)
+        loss.backward()
+        if grads is None:
+            grads = {k: v.grad.clone() for k, v in params.items()}
+        opt.step()
+        losses.append(loss.item())
+    return losses, grads, {k: v.detach() for k, v in params.items()}
+
+
+def _make(n=2, h=64, w=96, seed=11, std=None):
+    torch.manual_seed(seed)
+    net = P.UNetSeeInDark({"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}).cuda()
+    archs.initialize_weights(net)
+    if std is not None:            # He-like scaling so every layer carries signal and gradient of O(1)
+        for m in net.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                fan = m.weight.shape[1] * m.weight.shape[2] * m.weight.shape[3]
+                m.weight.data.normal_(0, std / fan ** 0.5)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    hr = torch.rand((n, 4, h, w), device="cuda", generator=g) ** 2
+    lr_in = (hr + 0.05 * torch.randn((n, 4, h, w), device="cuda", generator=g))
+    return net, lr_in, hr
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()          # F.cosine_similarity clamps norms at 1e-8: useless for tiny gradients
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
+
+
+def _ste(t):
+    """bf16 rounding with a straight-through gradient."""
+    return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
+def _unet_forward_bf16_storage(x, sd):
+    """archs/Unet.py:54-99 in fp32 arithmetic with every stored activation and every weight rounded to bf16 — the function
+    the tcgen05 path computes (bf16 operands, fp32 accumulation), so max-pool routing and LeakyReLU masks are decided
+    on the same values; autograd through it is the reference for the hand-written backward."""
+    act = lambda t: _ste(F.leaky_relu(t, 0.2))
+    cv = lambda t, n: F.conv2d(t, _ste(sd[n + ".weight"]), sd[n + ".bias"], padding=sd[n + ".weight"].shape[-1] // 2)
+    up = lambda t, n: _ste(F.conv_transpose2d(t, _ste(sd[n + ".weight"]), sd[n + ".bias"], stride=2))
+    c, cur = {}, _ste(x)
+    for i in range(1, 6):
+        c[i] = act(cv(act(cv(cur, f"conv{i}_1")), f"conv{i}_2"))
+        cur = F.max_pool2d(c[i], 2) if i < 5 else c[i]
+    for i in range(6, 10):
+        cur = act(cv(act(cv(torch.cat([up(cur, f"upv{i}"), c[10 - i]], 1), f"conv{i}_1")), f"conv{i}_2"))
+    return cv(cur, "conv10_1")
+
+
+@pytest.mark.parametrize("std", [None, 1.4])
+def test_training_step_gradients_match_fp32_autograd(std):
+    """Backward pass in isolation: both references are driven by the SAME d loss / d pred (the L1 gradient is a sign
+    function, so feeding each side its own would compare sign flips of a bf16-rounded prediction, not the backward)."""
+    net, lr_in, hr = _make(std=std)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    ts = train.UNetTrainStep(net)
+    pred, saved = ts.forward(lr_in)
+    gp = torch.empty_like(pred)
+    L.check(L.lib().pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gp.data_ptr(), pred.numel(), ts.loss_sum.data_ptr(), _sp()), "l1")
+    ts.backward(gp, saved)
+    _ok()
+    # (1) plain fp32 network (the reference's arithmetic)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    pred_ref = O.unet_forward(lr_in, params)
+    ref_loss = F.l1_loss(pred_ref.clamp(0, 1), hr).item()
+    pred_ref.backward(gp)
+    assert abs(ts.loss_sum.item() / pred.numel() - ref_loss) < 2e-3 * max(1.0, ref_loss)
+    assert (pred - pred_ref).abs().max().item() < 2e-2 * max(1.0, pred_ref.abs().max().item())
+    st32 = {name: (_rel(ts._grad_view(name), params[name].grad), _cos(ts._grad_view(name), params[name].grad)) for name in sd}
+    # (2) fp32 autograd through the bf16-storage network (same routing decisions as the kernels)
+    p16 = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    _unet_forward_bf16_storage(lr_in, p16).backward(gp)
+    st16 = {name: (_rel(ts._grad_view(name), p16[name].grad), _cos(ts._grad_view(name), p16[name].grad)) for name in sd}
+    for tag, st in (("fp32", st32), ("bf16-storage", st16)):
+        print(tag, "worst rel", max(st.items(), key=lambda kv: kv[1][0]), "worst cos", min(st.items(), key=lambda kv: kv[1][1]))
+    # vs plain fp32: max-pool ties / activation signs decided on bf16-rounded values re-route a few percent of the deep
+    # gradients (measured 2.7 % with the reference init, 9.8 % with O(1) activations): relative L2 < 15 %, cosine > 0.99
+    bad = {k: v for k, v in st32.items() if not (v[1] > 0.99 and v[0] < 0.15)}
+    assert not bad, bad
+    # vs the bf16-storage network: only bf16 rounding of the activation gradients remains: relative L2 < 5 %, cosine > 0.998
+    bad = {k: v for k, v in st16.items() if not (v[1] > 0.998 and v[0] < 0.05)}
+    assert not bad, bad
+
+
+def test_training_reduces_loss_like_the_reference_loop():
+    net, lr_in, hr = _make(n=2, h=64, w=64, seed=5)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    ref_losses, _, ref_params = _reference_step(sd, lr_in, hr, steps=8)
+    ts = train.UNetTrainStep(net)
+    losses = [ts.step(lr_in, hr).item() for _ in range(8)]
+    _ok()
+    assert losses[-1] < losses[0]
+    assert np.allclose(losses, ref_losses, rtol=2e-2, atol=2e-3), (losses, ref_losses)
+    # Adam's first steps move every weight by ~lr regardless of gradient scale: parameters must track the fp32 loop
+    for k, v in net.state_dict().items():
+        assert (v - ref_params[k]).abs().max().item() < 8 * 1e-4 + 1e-6, k
+    # the inference forward sees the updated weights (pack cache invalidated)
+    with torch.no_grad():
+        out = net.eval()(lr_in)
+    assert (out - O.unet_forward(lr_in, {k: v for k, v in net.state_dict().items()})).abs().max().item() < 1e-2
