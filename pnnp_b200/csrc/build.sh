@@ -11,10 +11,12 @@ pids=()
 for f in "$HERE"/*.cu; do
   o="$HERE/_obj/$(basename "${f%.cu}").o"
   if [[ ! -f "$o" || "$f" -nt "$o" || -n "$(find "$HERE" "$HERE/../../include" -name '*.h' -newer "$o" -o -name '*.cuh' -newer "$o")" ]]; then
-    ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
+    ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; rm -f "$o"; exit 1; } ) &
     pids+=($!)
   fi
 done
-for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+rc=0
+for p in "${pids[@]:-}"; do if [[ -n "$p" ]]; then wait "$p" || rc=1; fi; done
+if [[ $rc -ne 0 ]]; then echo "build.sh: compilation FAILED" >&2; rm -f "$OUT"; exit 1; fi
 "$NVCC" -shared -cudart shared -o "$OUT" "$HERE"/_obj/*.o
 echo "built $OUT"

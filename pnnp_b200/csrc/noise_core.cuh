@@ -25,24 +25,36 @@ constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
 constexpr uint32_t kStreamElem = 0u, kStreamRow = 1u;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+// Round keys k + r*W for r = 0..9, precomputed on the host and passed in the kernel-parameter block: with the round loop fully
+// unrolled every key is a constant-bank operand of the XOR, so a round is 2 IMAD.WIDE.U32 + 2 LOP3 and nothing else.
+struct PhiloxKeys { uint32_t k[20]; };
+inline PhiloxKeys philox_round_keys(uint64_t seed) {
+    PhiloxKeys r;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) { r.k[2 * i] = k0; r.k[2 * i + 1] = k1; k0 += kPhiloxW0; k1 += kPhiloxW1; }
+    return r;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& rk) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += kPhiloxW0;
-        k.y += kPhiloxW1;
+        c = make_uint4(hi1 ^ c.y ^ rk.k[2 * r], lo1, hi0 ^ c.w ^ rk.k[2 * r + 1], lo0);
     }
     return c;
 }
 
+// single-instruction special-function wrappers (the CUDA math-library forms add denormal-range fix-up code)
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 struct RngCtx {
-    uint2 key;
+    const PhiloxKeys& rk;               // lives in the kernel-parameter (constant) bank
     uint32_t off_lo, off_hi;
     __device__ __forceinline__ uint4 block(uint64_t index, uint32_t stream, uint32_t sub) const {
         const uint32_t c1 = (uint32_t)((index >> 32) & 0xFFFFu) | (sub << 16) | (stream << 24);
-        return philox4x32_10(make_uint4((uint32_t)index, c1, off_lo, off_hi), key);
+        return philox4x32_10(make_uint4((uint32_t)index, c1, off_lo, off_hi), rk);
     }
 };
 
@@ -52,6 +64,32 @@ __device__ __forceinline__ float u01_24(uint32_t w) { return ((float)(w >> 8) + 
 __device__ __forceinline__ float u01_24_closed0(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-8f; }
 // (0,1] ∩ float32 from all 32 bits: relative precision kept near 0 (tails)
 __device__ __forceinline__ float u01_32(uint32_t w) { return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// ------------------------------------------------------------------------------------------
+// Draw layout (all kernels).  Elements are grouped in fours by GLOBAL element index g; group G = g >> 2 owns the
+// Philox blocks (G, stream ELEM, sub):
+//   sub 0: word e            -> the shot-noise draw of element e = g & 3 (all 32 bits)
+//   sub 1: word e = "mix"    -> read-noise cell k = mix >> 12 (20 bits) | quantisation draw = mix & 0xFFF (12 bits)
+//   sub 2: word e            -> refinement of the read-noise draw, generated ONLY when k lies in the outer 256 cells of either
+//                               tail (probability 2^-11): the low 12 bits of the read word come from it instead of the cell centre
+// i.e. the read-noise sampler inverts the 32-bit word  w_read = k << 12 | (tail ? refine >> 20 : 0x800): 2^-20 resolution in
+// the body (quantile step < 4e-4 sigma there), full 2^-32 resolution where the quantile function is steep.  The quantisation
+// draw (U(-0.5, 0.5) DN, added to continuous read noise) has a 2^-12 DN lattice.  Two Philox blocks per four elements
+// instead of three.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kReadTailCells = 256u;
+__device__ __forceinline__ bool read_cell_is_tail(uint32_t k) { return (k - kReadTailCells) >= ((1u << 20) - 2u * kReadTailCells); }
+__device__ __forceinline__ uint32_t read_word(uint32_t mix, uint32_t refine) {
+    const uint32_t k = mix >> 12;
+    return (mix & 0xFFFFF000u) | (read_cell_is_tail(k) ? (refine >> 20) : 0x800u);
+}
+// numpy chain: U(-0.5, 0.5) on the 12-bit lattice, exact in float64: (qbits + 0.5) / 4096 - 0.5 (built from the bit pattern of
+// 1 + (qbits + 0.5) / 4096, no int->double conversion)
+__device__ __forceinline__ double quant_draw_f64(uint32_t mix) {
+    return __dadd_rn(__hiloint2double((int)(0x3FF00000u | ((mix & 0xFFFu) << 8) | 0x80u), 0), -1.5);
+}
+// torch chain: U[0, 1) on the 12-bit lattice
+__device__ __forceinline__ float quant_draw_f32(uint32_t mix) { return (float)(mix & 0xFFFu) * 2.44140625e-4f; }
 
 // ------------------------------------------------------------------------------------------
 // Standard normal by inversion of ONE 32-bit word: z = Phi^-1((w + 0.5) / 2^32).
@@ -66,7 +104,7 @@ __device__ __forceinline__ float normal_icdf(uint32_t w) {
     const bool lower = w < 0x80000000u;
     const uint32_t m = lower ? w : ~w;
     const float p = fmaf((float)m, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float t = -__log2f(4.0f * p * (1.0f - p));
+    const float t = -lg2_approx(4.0f * p * (1.0f - p));
     float e;
     if (t < 8.25f) {
         float q = 2.674857846e-08f;
@@ -97,15 +135,25 @@ __device__ __forceinline__ float normal_icdf(uint32_t w) {
 // Tukey-lambda quantile  Q(u) = (u^lam - (1-u)^lam) / lam   (lam -> 0: logit)
 // u and 1-u are formed separately from the word so both tails keep relative precision.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tukey_lambda_from_uv(float a, float b, float lam, float inv_lam);
+// body cell (k + 0.5) / 2^20 and its complement, both exact in float32, without int->float conversions:
+// 1 + (8k + 4) / 2^23 has the bit pattern 0x3F800000 | k << 3 | 4
+__device__ __forceinline__ float tukey_lambda_ppf_body(uint32_t mix, float lam, float inv_lam) {
+    const float a = __uint_as_float(0x3F800000u | ((mix >> 12) << 3) | 4u) - 1.0f;
+    return tukey_lambda_from_uv(a, 1.0f - a, lam, inv_lam);
+}
 __device__ __forceinline__ float tukey_lambda_ppf(uint32_t w, float lam, float inv_lam) {
-    const float a = u01_32(w), b = u01_32(~w);
-    const float la = __log2f(a), lb = __log2f(b);
+    if (!read_cell_is_tail(w >> 12)) return tukey_lambda_ppf_body(w, lam, inv_lam);
+    return tukey_lambda_from_uv(u01_32(w), u01_32(~w), lam, inv_lam);
+}
+__device__ __forceinline__ float tukey_lambda_from_uv(float a, float b, float lam, float inv_lam) {
+    const float la = lg2_approx(a), lb = lg2_approx(b);
     if (fabsf(lam) < 1e-3f) {
         const float xa = la * 0.6931471805599453f, xb = lb * 0.6931471805599453f;
         const float d1 = xa - xb, d2 = xa * xa - xb * xb, d3 = xa * xa * xa - xb * xb * xb;
         return d1 + lam * (0.5f * d2 + lam * 0.16666667f * d3);
     }
-    return (exp2f(lam * la) - exp2f(lam * lb)) * inv_lam;
+    return (ex2_approx(lam * la) - ex2_approx(lam * lb)) * inv_lam;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -134,7 +182,7 @@ constexpr float kPoissonSwitch = 10.0f;
 
 __device__ __forceinline__ float poisson_large(float lam, uint32_t w) {
     const float z = normal_icdf(w);
-    const float rs = rsqrtf(lam), s = lam * rs, z2 = z * z;
+    const float rs = rsqrt_approx(lam), s = lam * rs, z2 = z * z;
     float x = fmaf(s, z, lam);
     x += fmaf(z2, 0.16666667f, 0.33333334f);
     x = fmaf(-z * fmaf(z2, 0.013888889f, 0.027777778f), rs, x);
@@ -144,7 +192,7 @@ __device__ __forceinline__ float poisson_large(float lam, uint32_t w) {
 
 __device__ __forceinline__ float poisson_small(float lam, uint32_t w) {
     const float u = fminf(u01_32(w), 0.99999994f);
-    float p = __expf(-lam), F = p;
+    float p = ex2_approx(-1.4426950408889634f * lam), F = p;
     int k = 0;
 #pragma unroll 1
     while (u > F && k < kInvTab - 2) {          // two CDF terms per trip
@@ -160,9 +208,49 @@ __device__ __forceinline__ float poisson_small(float lam, uint32_t w) {
     return (float)k;
 }
 
-__device__ __forceinline__ float poisson_sample(float lam, uint32_t w) {
+// ------------------------------------------------------------------------------------------
+// lam < 10, table form of the same exact inversion (what the kernels use; poisson_small above stays as the fallback for
+// counts beyond the table and as the specification).  The sequential search costs every lane of a warp the trip count of
+// its slowest lane; this form has a fixed, short instruction sequence instead:
+//   * T[i][k] = P(Poisson(i/16) <= k), i = 0..160, k = 0..31: float32 rounded from a float64 evaluation on the host, copied
+//     to shared memory by every CTA (22.5 KB; five leading zeros per row stand for k < 0).
+//   * For lam = i/16 + delta (0 <= delta < 1/16), Poisson(lam) = Poisson(i/16) + Poisson(delta) gives the CDF at lam
+//     EXACTLY as a short convolution of row i:  F(k; lam) = e^-delta * sum_j delta^j/j! * T[i][k-j];  terms j <= 4 are kept
+//     (truncation <= delta^5/120 = 8e-9, below the float32 resolution of the table).
+//   * T[i][k] >= F(k; lam), so a 5-probe binary search of row i for the first entry >= u gives a lower bound k0 of the
+//     answer; the convolved CDF is then checked at k0, k0+1, ... (the first check succeeds with probability ~1 - delta/2).
+// ------------------------------------------------------------------------------------------
+constexpr int kPoisRows = 161, kPoisCols = 32, kPoisPad = 5, kPoisStride = kPoisCols + kPoisPad;   // 37 floats per row
+constexpr int kPoisTableFloats = kPoisRows * kPoisStride;
+
+__device__ __forceinline__ float poisson_small_table(float lam, uint32_t w, const float* __restrict__ T) {
+    lam = fmaxf(lam, 0.f);
+    const float u = fminf(u01_32(w), 0.99999994f);
+    const int i = (int)(lam * 16.0f);
+    const float delta = fmaf(-0.0625f, (float)i, lam);                        // exact
+    const float* row = T + i * kPoisStride + kPoisPad;
+    int k = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) k += (row[k + s - 1] < u) ? s : 0;     // entries 0..30 that are < u
+    const float c2 = 0.5f * delta * delta, c3 = c2 * delta * 0.33333334f, c4 = c3 * delta * 0.25f;
+    // u * e^delta (delta < 1/16: degree-5 Taylor, relative error 1e-10)
+    const float ed = fmaf(delta, fmaf(delta, fmaf(delta, fmaf(delta, fmaf(delta, 8.3333333e-3f, 4.1666667e-2f), 0.16666667f), 0.5f), 1.0f), 1.0f);
+    const float ue = u * ed;
+    float t1 = row[k - 1], t2 = row[k - 2], t3 = row[k - 3], t4 = row[k - 4];
+#pragma unroll 1
+    while (true) {
+        if (k >= kPoisCols) return poisson_small(lam, w);                      // probability < 1e-8: sequential search
+        const float t0 = row[k];
+        if (fmaf(c4, t4, fmaf(c3, t3, fmaf(c2, t2, fmaf(delta, t1, t0)))) >= ue) break;
+        t4 = t3; t3 = t2; t2 = t1; t1 = t0; ++k;
+    }
+    return (float)k;
+}
+
+// T: the shared-memory copy of the table above
+__device__ __forceinline__ float poisson_sample(float lam, uint32_t w, const float* __restrict__ T) {
     if (!(lam > 0.f)) return 0.f;
-    return lam < kPoissonSwitch ? poisson_small(lam, w) : poisson_large(lam, w);
+    return lam < kPoissonSwitch ? poisson_small_table(lam, w, T) : poisson_large(lam, w);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -192,6 +280,13 @@ __device__ __forceinline__ float poisson_rate_numpy(const ScaleIn& s, const RowP
     // 1.0*y/K in K's precision (float64 if either side is float64); our sampler consumes float32
     if (p.flags & (PNNP_F_K64 | PNNP_F_RATIO64)) return (float)(s.ysc64 / p.K);
     return __fdiv_rn(s.ysc32, (float)p.K);
+}
+
+// np.clip(z, lo, hi) on float64 as two compare+select pairs (fmin/fmax carry NaN-quieting logic that costs ~10 instructions
+// each in SASS; np.clip propagates NaN, which a plain select does too)
+__device__ __forceinline__ double clip_f64(double z, double lo, double hi) {
+    z = z < lo ? lo : z;
+    return z > hi ? hi : z;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -242,7 +337,7 @@ __device__ __forceinline__ float tail_numpy(float y, const RowP& p, uint32_t cod
     }
     if (a64) {
         double z = __ddiv_rn(A, p.span);
-        z = clip01 ? fmin(fmax(z, 0.0), 1.0) : fmin(fmax(z, p.lo), 1.0);
+        z = clip01 ? clip_f64(z, 0.0, 1.0) : clip_f64(z, p.lo, 1.0);
         if (!ori) z = __dmul_rn(z, p.ratio);
         return (float)z;
     }

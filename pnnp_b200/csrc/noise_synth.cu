@@ -9,8 +9,10 @@
 // up to four float4 groups (128-bit coalesced loads/stores, lane-interleaved).  The row-noise
 // draw is keyed on the (crop, channel, row) index, so every lane of every warp that touches the
 // row computes the same value — a broadcast by construction, no shuffle needed.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include "abi_common.h"
 #include "noise_core.cuh"
 
@@ -25,39 +27,83 @@ struct SynthArgs {
     int ori, clip;
     float post_lo, post_hi;
     uint64_t seed, offset, crop_id0;
+    PhiloxKeys rk;                   // round keys of `seed` (filled by launch_synth)
     // debug outputs / replay inputs (NULL when unused)
     float* d_shot; float* d_read; float* d_rowz; double* d_q;
 };
 
+// Poisson CDF table (noise_core.cuh: poisson_small_table), filled once per process by the host
+__device__ float g_pois_table[kPoisTableFloats];
+static int ensure_poisson_table() {
+    static bool done[64] = {};
+    int dev = 0;
+    PNNP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail("noise_synth: device index out of range");
+    if (done[dev]) return 0;
+    static float host[kPoisTableFloats];
+    for (int r = 0; r < kPoisRows; ++r) {
+        const double lam = r / 16.0;
+        double p = std::exp(-lam), F = p;
+        float* row = host + r * kPoisStride;
+        for (int z = 0; z < kPoisPad; ++z) row[z] = 0.f;
+        for (int k = 0; k < kPoisCols; ++k) {
+            if (k) { p *= lam / k; F += p; }
+            row[kPoisPad + k] = (float)std::min(F, 1.0);
+        }
+    }
+    PNNP_CUDA(cudaMemcpyToSymbol(g_pois_table, host, sizeof(host)));
+    done[dev] = true;
+    return 0;
+}
+__device__ __forceinline__ void load_poisson_table(float* s_table) {
+    for (int i = threadIdx.x; i < kPoisTableFloats; i += blockDim.x) s_table[i] = g_pois_table[i];
+    __syncthreads();
+}
+
 constexpr int kSeg = 512;          // elements per warp work unit
 constexpr int kThreads = 256;
 
-// Draw layout.  Elements are grouped in fours by GLOBAL element index g (crop_id0 * c*h*w + local index);
-// group G = g >> 2 owns three Philox blocks (sub = 0,1,2) = 12 words, and element e = g & 3 uses words
-// 3e, 3e+1, 3e+2 as (shot, read, quantisation).  Every draw is an inversion of exactly one word, so no
-// mode needs more than three words per element and nothing depends on thread/grid shape or on W % 4.
-struct GroupWords { uint32_t w[12]; };
-__device__ __forceinline__ GroupWords group_words(const RngCtx& rng, uint64_t group) {
-    GroupWords g;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-        const uint4 b = rng.block(group, kStreamElem, (uint32_t)s);
-        g.w[4 * s] = b.x; g.w[4 * s + 1] = b.y; g.w[4 * s + 2] = b.z; g.w[4 * s + 3] = b.w;
-    }
+// Draws of one group of four elements (layout: noise_core.cuh).  shot[e] / mix[e] are words e of blocks sub 0 / 1; read[e] is
+// the 32-bit word the read-noise sampler inverts (cell from mix, low bits from the refinement block only in the tails).
+struct GroupDraws { uint32_t shot[4], mix[4], read[4]; };
+__device__ __forceinline__ GroupDraws group_draws(const RngCtx& rng, uint64_t group) {
+    GroupDraws g;
+    const uint4 b0 = rng.block(group, kStreamElem, 0u), b1 = rng.block(group, kStreamElem, 1u);
+    g.shot[0] = b0.x; g.shot[1] = b0.y; g.shot[2] = b0.z; g.shot[3] = b0.w;
+    g.mix[0] = b1.x; g.mix[1] = b1.y; g.mix[2] = b1.z; g.mix[3] = b1.w;
+    uint4 b2 = make_uint4(0u, 0u, 0u, 0u);
+    if (read_cell_is_tail(b1.x >> 12) | read_cell_is_tail(b1.y >> 12) | read_cell_is_tail(b1.z >> 12) | read_cell_is_tail(b1.w >> 12))
+        b2 = rng.block(group, kStreamElem, 2u);
+    g.read[0] = read_word(b1.x, b2.x); g.read[1] = read_word(b1.y, b2.y);
+    g.read[2] = read_word(b1.z, b2.z); g.read[3] = read_word(b1.w, b2.w);
     return g;
 }
 
-// One element given its three words.  Returns the noisy value; optionally records the draws.
+// Read-noise / quantisation draws only (the specialised kernel generates the shot words in an earlier phase).
+__device__ __forceinline__ GroupDraws group_draws_read(const RngCtx& rng, uint64_t group) {
+    GroupDraws g;
+    const uint4 b1 = rng.block(group, kStreamElem, 1u);
+    g.mix[0] = b1.x; g.mix[1] = b1.y; g.mix[2] = b1.z; g.mix[3] = b1.w;
+    uint4 b2 = make_uint4(0u, 0u, 0u, 0u);
+    if (read_cell_is_tail(b1.x >> 12) | read_cell_is_tail(b1.y >> 12) | read_cell_is_tail(b1.z >> 12) | read_cell_is_tail(b1.w >> 12))
+        b2 = rng.block(group, kStreamElem, 2u);
+    g.read[0] = read_word(b1.x, b2.x); g.read[1] = read_word(b1.y, b2.y);
+    g.read[2] = read_word(b1.z, b2.z); g.read[3] = read_word(b1.w, b2.w);
+    return g;
+}
+
+// One element given its draws (shot word, read word, mix word carrying the quantisation bits).  Returns the noisy value;
+// optionally records the draws.
 template <int CHAIN, bool DEBUG>
 __device__ __forceinline__ float synth_one(float y, uint32_t w_shot, uint32_t w_read, uint32_t w_q, size_t lidx, int crop,
                                            int ch, const RowP& p, const SynthArgs& a, float rowz, float lam_tl,
-                                           float inv_lam_tl) {
+                                           float inv_lam_tl, const float* pois_table) {
     const uint32_t code = a.code;
     float lam, d_shot;
     ScaleIn s;
     if (CHAIN == PNNP_CHAIN_NUMPY) { s = scale_in_numpy(y, p); lam = poisson_rate_numpy(s, p); }
     else { s.ysc32 = scale_in_torch(y, p); s.ysc64 = 0.0; lam = __fdiv_rn(s.ysc32, (float)p.K); }
-    if (code & PNNP_CODE_P) d_shot = poisson_sample(lam, w_shot);
+    if (code & PNNP_CODE_P) d_shot = poisson_sample(lam, w_shot, pois_table);
     else d_shot = normal_icdf(w_shot);
 
     float d_read = 0.f;
@@ -70,12 +116,12 @@ __device__ __forceinline__ float synth_one(float y, uint32_t w_shot, uint32_t w_
     float out;
     double dq = 0.0;
     if (CHAIN == PNNP_CHAIN_NUMPY) {
-        // numpy: uniform(-0.5, 0.5) is float64; (w + 0.5) * 2^-32 - 0.5 is exact in float64
-        if (code & PNNP_CODE_Q) dq = fma((double)w_q, 2.3283064365386963e-10, 1.1641532182693481e-10) - 0.5;
+        // numpy: uniform(-0.5, 0.5) is float64; the 12-bit lattice value is exact in float64
+        if (code & PNNP_CODE_Q) dq = quant_draw_f64(w_q);
         const double bias_c = (code & PNNP_CODE_D) ? a.table[crop].bias[ch & 3] : 0.0;
         out = tail_numpy(y, p, code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, dq, bias_c);
     } else {
-        const float qu = u01_24_closed0(w_q);
+        const float qu = quant_draw_f32(w_q);
         dq = (double)qu;
         out = tail_torch(p, code, a.ori != 0, a.clip != 0, d_shot, d_read, rowz, qu);
     }
@@ -88,36 +134,17 @@ __device__ __forceinline__ float synth_one(float y, uint32_t w_shot, uint32_t w_
     return out;
 }
 
-// Specialised element: NumPy chain, code = p|g|r|q, float64 K/sigR, weak ratio, ori = clip = False.
-template <bool DEBUG>
-__device__ __forceinline__ float synth_one_fast(float y, uint32_t w_shot, uint32_t w_read, uint32_t w_q, size_t lidx,
-                                                const FastP& f, const SynthArgs& a) {
-    const float ysc = div_rn_by_const(__fmul_rn(y, f.span32), f.ratio32, f.rratio32);
-    const float cnt = poisson_sample(ysc * f.invK32, w_shot);
-    const float d_read = tukey_lambda_ppf(w_read, f.lam_tl, f.inv_lam_tl) * f.sigTL32;
-    const double dq = fma((double)w_q, 2.3283064365386963e-10, 1.1641532182693481e-10) - 0.5;
-    float out = tail_numpy_fast(f, cnt, d_read, dq);
-    out = fminf(fmaxf(out, a.post_lo), a.post_hi);
-    if (DEBUG) {
-        if (a.d_shot) a.d_shot[lidx] = cnt;
-        if (a.d_read) a.d_read[lidx] = d_read;
-        if (a.d_q) a.d_q[lidx] = dq;
-    }
-    return out;
-}
-
-template <int CHAIN, bool DEBUG, int VEC, bool FAST>
+template <int CHAIN, bool DEBUG, int VEC>
 __global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArgs a) {
+    __shared__ float s_pois[kPoisTableFloats];
+    load_poisson_table(s_pois);
     const int lane = threadIdx.x & 31;
     const long long warps_total = (long long)gridDim.x * (kThreads / 32);
     const long long warp_id = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const int nseg = (a.w + kSeg - 1) / kSeg;
     const long long rows = (long long)a.n * a.c * a.h;
     const long long units = rows * nseg;
-    RngCtx rng;
-    rng.key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-    rng.off_lo = (uint32_t)a.offset;
-    rng.off_hi = (uint32_t)(a.offset >> 32);
+    const RngCtx rng{a.rk, (uint32_t)a.offset, (uint32_t)(a.offset >> 32)};
     const size_t crop_elems = (size_t)a.c * a.h * a.w;
 
     for (long long u = warp_id; u < units; u += warps_total) {
@@ -144,25 +171,12 @@ __global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArg
                 const int x = x0 + (j * 32 + lane) * 4;
                 if (x >= a.w) break;
                 const float4 y = __ldcs(reinterpret_cast<const float4*>(a.clean + row_base + x));
-                const GroupWords g = group_words(rng, (g_base + x) >> 2);       // (g_base + x) % 4 == 0 on this path
+                const GroupDraws g = group_draws(rng, (g_base + x) >> 2);       // (g_base + x) % 4 == 0 on this path
                 float4 o;
-                if (FAST) {
-                    FastP f;
-                    f.span32 = (float)p.span; f.ratio32 = (float)p.ratio; f.rratio32 = __frcp_rn(f.ratio32);
-                    f.invK32 = (float)(1.0 / p.K); f.sigTL32 = (float)p.sigTL; f.lam_tl = lam_tl; f.inv_lam_tl = inv_lam_tl;
-                    f.K = p.K; f.span = p.span; f.rspan = __drcp_rn(p.span); f.lo = p.lo; f.ratio = p.ratio;
-                    f.row64 = __dmul_rn((double)rowz, p.sigR);
-                    o.x = synth_one_fast<DEBUG>(y.x, g.w[0], g.w[1], g.w[2], row_base + x + 0, f, a);
-                    o.y = synth_one_fast<DEBUG>(y.y, g.w[3], g.w[4], g.w[5], row_base + x + 1, f, a);
-                    o.z = synth_one_fast<DEBUG>(y.z, g.w[6], g.w[7], g.w[8], row_base + x + 2, f, a);
-                    o.w = synth_one_fast<DEBUG>(y.w, g.w[9], g.w[10], g.w[11], row_base + x + 3, f, a);
-                    __stcs(reinterpret_cast<float4*>(a.noisy + row_base + x), o);
-                    continue;
-                }
-                o.x = synth_one<CHAIN, DEBUG>(y.x, g.w[0], g.w[1], g.w[2], row_base + x + 0, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
-                o.y = synth_one<CHAIN, DEBUG>(y.y, g.w[3], g.w[4], g.w[5], row_base + x + 1, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
-                o.z = synth_one<CHAIN, DEBUG>(y.z, g.w[6], g.w[7], g.w[8], row_base + x + 2, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
-                o.w = synth_one<CHAIN, DEBUG>(y.w, g.w[9], g.w[10], g.w[11], row_base + x + 3, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
+                o.x = synth_one<CHAIN, DEBUG>(y.x, g.shot[0], g.read[0], g.mix[0], row_base + x + 0, crop, ch, p, a, rowz, lam_tl, inv_lam_tl, s_pois);
+                o.y = synth_one<CHAIN, DEBUG>(y.y, g.shot[1], g.read[1], g.mix[1], row_base + x + 1, crop, ch, p, a, rowz, lam_tl, inv_lam_tl, s_pois);
+                o.z = synth_one<CHAIN, DEBUG>(y.z, g.shot[2], g.read[2], g.mix[2], row_base + x + 2, crop, ch, p, a, rowz, lam_tl, inv_lam_tl, s_pois);
+                o.w = synth_one<CHAIN, DEBUG>(y.w, g.shot[3], g.read[3], g.mix[3], row_base + x + 3, crop, ch, p, a, rowz, lam_tl, inv_lam_tl, s_pois);
                 __stcs(reinterpret_cast<float4*>(a.noisy + row_base + x), o);
             }
         } else {
@@ -170,15 +184,177 @@ __global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArg
             for (int x = x0 + lane; x < min(a.w, x0 + kSeg); x += 32) {
                 const float y = a.clean[row_base + x];
                 const uint64_t gi = g_base + x;
-                const GroupWords g = group_words(rng, gi >> 2);
+                const GroupDraws g = group_draws(rng, gi >> 2);
                 const int e = (int)(gi & 3);
-                uint32_t w0 = g.w[0], w1 = g.w[1], w2 = g.w[2];
-                if (e == 1) { w0 = g.w[3]; w1 = g.w[4]; w2 = g.w[5]; }
-                else if (e == 2) { w0 = g.w[6]; w1 = g.w[7]; w2 = g.w[8]; }
-                else if (e == 3) { w0 = g.w[9]; w1 = g.w[10]; w2 = g.w[11]; }
-                a.noisy[row_base + x] = synth_one<CHAIN, DEBUG>(y, w0, w1, w2, row_base + x, crop, ch, p, a, rowz, lam_tl, inv_lam_tl);
+                uint32_t w0 = g.shot[0], w1 = g.read[0], w2 = g.mix[0];
+                if (e == 1) { w0 = g.shot[1]; w1 = g.read[1]; w2 = g.mix[1]; }
+                else if (e == 2) { w0 = g.shot[2]; w1 = g.read[2]; w2 = g.mix[2]; }
+                else if (e == 3) { w0 = g.shot[3]; w1 = g.read[3]; w2 = g.mix[3]; }
+                a.noisy[row_base + x] = synth_one<CHAIN, DEBUG>(y, w0, w1, w2, row_base + x, crop, ch, p, a, rowz, lam_tl, inv_lam_tl, s_pois);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Specialised kernel: NumPy chain, code = p|g|r|q, float64 K / sigR and python-float ratio (what sample_params returns),
+// ori = clip = False, w % 4 == 0 — BASELINE configs[1].  Bit-identical to the generic kernel (same draws, same tail;
+// test_specialised_kernel_is_bit_identical_to_replay_at_scale), organised around what the generic kernel wastes:
+//
+//  * The two Poisson samplers (exact CDF search below rate 10, Cornish-Fisher inversion above) are data-dependent branches
+//    that a warp pays for one after the other whenever its 32 lanes disagree — and with per-pixel rates they always do;
+//    inside the search every lane also waits for the slowest one.  Here a warp owns 512 consecutive elements of a row and
+//    first *sorts them by sampler* through a 4 KB shared-memory queue (ballot + popc compaction: low-rate entries fill the
+//    queue from the bottom, high-rate entries from the top), then runs each sampler over its part of the queue 32 entries at
+//    a time with every lane active, and writes the count back in place.  Each lane keeps the queue positions of its 16
+//    elements in registers and collects the counts afterwards.
+//  * Per-crop constants (reciprocals for the Markstein divisions, float32 copies) are rebuilt only when the warp moves to
+//    another crop; the row-noise draws of a warp's next 32 rows are generated in one go, one row per lane, and handed out
+//    by shuffle (row noise is keyed on the global row index, so the value does not depend on who computes it).
+//  * Phase 3 (read noise, quantisation, float64 tail, 128-bit streaming stores) needs only the counts, not the clean pixels.
+// ------------------------------------------------------------------------------------------
+constexpr int kFastUnit = 512;              // elements per warp work unit (16 per lane, four float4 groups)
+constexpr int kFastThreads = 256;
+
+constexpr int kFastQueueBytes = (kFastThreads / 32) * kFastUnit * 8, kFastPosBytes = (kFastThreads / 32) * kFastUnit * 2;
+constexpr int kFastSmemBytes = kFastQueueBytes + kFastPosBytes + kPoisTableFloats * 4;
+
+struct FastC {                              // per-crop constants
+    float span32, ratio32, rratio32, invK32, sigTL32, lam_tl, inv_lam_tl;
+    double K, span, rspan, lo, ratio, sigR;
+};
+
+template <bool DEBUG, int MINB>
+__global__ void __launch_bounds__(kFastThreads, MINB) noise_synth_fast_kernel(const SynthArgs a) {
+    // dynamic shared memory (kFastSmemBytes > 48 KB): [warps][512] uint2 queue | [warps][512] uint16 positions | Poisson table
+    extern __shared__ __align__(16) uint8_t s_fast[];
+    float* s_pois = reinterpret_cast<float*>(s_fast + kFastQueueBytes + kFastPosBytes);
+    load_poisson_table(s_pois);
+    const int lane = threadIdx.x & 31;
+    uint2* q = reinterpret_cast<uint2*>(s_fast) + (threadIdx.x >> 5) * kFastUnit;
+    uint16_t* qpos = reinterpret_cast<uint16_t*>(s_fast + kFastQueueBytes) + (threadIdx.x >> 5) * kFastUnit;   // queue position of every element
+    const unsigned lt = (1u << lane) - 1u;
+    const long long warps_total = (long long)gridDim.x * (kFastThreads / 32);
+    const long long warp_id = (long long)blockIdx.x * (kFastThreads / 32) + (threadIdx.x >> 5);
+    const int nseg = (a.w + kFastUnit - 1) / kFastUnit;
+    const long long rows_per_crop = (long long)a.c * a.h;
+    const long long units = (long long)a.n * rows_per_crop * nseg;
+    const RngCtx rng{a.rk, (uint32_t)a.offset, (uint32_t)(a.offset >> 32)};
+    const size_t crop_elems = (size_t)a.c * a.h * a.w;
+
+    FastC f = {};
+    int cur_crop = -1;
+    float rowz_batch = 0.f;
+    int it = 0;
+    for (long long u = warp_id; u < units; u += warps_total, ++it) {
+        if ((it & 31) == 0) {
+            // row draws of this warp's next 32 units, one per lane
+            const long long uu = u + (long long)lane * warps_total;
+            if (uu < units) rowz_batch = normal_icdf(rng.block(a.crop_id0 * (uint64_t)rows_per_crop + (uint64_t)(uu / nseg), kStreamRow, 0u).x);
+        }
+        const float rowz = __shfl_sync(0xffffffffu, rowz_batch, it & 31);
+        const long long row = u / nseg;
+        const int seg = (int)(u - row * nseg);
+        const int crop = (int)(row / rows_per_crop);
+        if (crop != cur_crop) {
+            const pnnp_noise_params* t = a.table + crop;
+            f.K = t->K; f.span = t->span; f.lo = t->clip_lo; f.ratio = t->ratio; f.sigR = t->sigR;
+            f.rspan = __drcp_rn(f.span);
+            f.span32 = (float)f.span; f.ratio32 = (float)f.ratio; f.rratio32 = __frcp_rn(f.ratio32);
+            f.invK32 = (float)(1.0 / f.K); f.sigTL32 = (float)t->sigTL; f.lam_tl = (float)t->lam;
+            f.inv_lam_tl = f.lam_tl != 0.f ? 1.0f / f.lam_tl : 0.f;
+            cur_crop = crop;
+        }
+        if (DEBUG && a.d_rowz && seg == 0 && lane == 0) a.d_rowz[row] = rowz;
+        const double row64 = __dmul_rn((double)rowz, f.sigR);
+        const size_t row_base = (size_t)row * a.w;
+        const uint64_t g_base = a.crop_id0 * (uint64_t)crop_elems + (uint64_t)row_base;
+        const int x0 = seg * kFastUnit;
+
+        // ---- phase 1: rates + shot words -> queue, sorted by sampler.  The j loops are deliberately NOT unrolled: the
+        // kernel is latency-bound, not issue-bound, and a 4x unrolled body (4 Philox blocks per phase) overflows the
+        // instruction cache once the warps of an SM spread over the three phases.
+        int n_small = 0, n_large = 0;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + (j * 32 + lane) * 4;
+            const bool valid = x < a.w;
+            const unsigned m_valid = __ballot_sync(0xffffffffu, valid);
+            const float4 yv = valid ? __ldcs(reinterpret_cast<const float4*>(a.clean + row_base + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint4 b0 = rng.block((g_base + x) >> 2, kStreamElem, 0u);      // (g_base + x) % 4 == 0 on this path
+            const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+            const uint32_t ws[4] = {b0.x, b0.y, b0.z, b0.w};
+            uint32_t pq[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float ysc = div_rn_by_const(__fmul_rn(ys[e], f.span32), f.ratio32, f.rratio32);
+                const float lam = ysc * f.invK32;
+                const bool small = lam < kPoissonSwitch;
+                const unsigned m_small = __ballot_sync(0xffffffffu, small && valid);
+                const unsigned m_large = m_valid & ~m_small;
+                const int p_small = n_small + __popc(m_small & lt);
+                const int p_large = kFastUnit - 1 - (n_large + __popc(m_large & lt));
+                pq[e] = (uint32_t)(small ? p_small : p_large);
+                if (valid) q[pq[e]] = make_uint2(__float_as_uint(lam), ws[e]);
+                n_small += __popc(m_small);
+                n_large += __popc(m_large);
+            }
+            *reinterpret_cast<uint2*>(qpos + (j * 32 + lane) * 4) = make_uint2(pq[0] | (pq[1] << 16), pq[2] | (pq[3] << 16));
+        }
+        __syncwarp();
+        // ---- phase 2: each sampler over its part of the queue, all lanes busy; the count replaces the rate in place
+        for (int i = lane; i < n_small; i += 32) {
+            const uint2 en = q[i];
+            q[i].x = __float_as_uint(poisson_small_table(__uint_as_float(en.x), en.y, s_pois));
+        }
+        for (int i = lane; i < n_large; i += 32) {
+            const uint2 en = q[kFastUnit - 1 - i];
+            q[kFastUnit - 1 - i].x = __float_as_uint(poisson_large(__uint_as_float(en.x), en.y));
+        }
+        __syncwarp();
+        // ---- phase 3: read noise + quantisation + tail (needs the counts, not the clean pixels)
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + (j * 32 + lane) * 4;
+            if (x < a.w) {
+                const uint64_t grp = (g_base + x) >> 2;
+                const uint4 b1 = rng.block(grp, kStreamElem, 1u);
+                const uint32_t mix[4] = {b1.x, b1.y, b1.z, b1.w};
+                const uint2 pp = *reinterpret_cast<const uint2*>(qpos + (j * 32 + lane) * 4);
+                const uint32_t pq[4] = {pp.x & 0xFFFFu, pp.x >> 16, pp.y & 0xFFFFu, pp.y >> 16};
+                float d_read[4];
+                if (read_cell_is_tail(b1.x >> 12) | read_cell_is_tail(b1.y >> 12) | read_cell_is_tail(b1.z >> 12) | read_cell_is_tail(b1.w >> 12)) {
+                    // rare (2^-9 per group): some draw lies in the outer cells -> refinement block, general sampler
+                    const uint4 b2 = rng.block(grp, kStreamElem, 2u);
+                    const uint32_t rf[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d_read[e] = tukey_lambda_ppf(read_word(mix[e], rf[e]), f.lam_tl, f.inv_lam_tl) * f.sigTL32;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d_read[e] = tukey_lambda_ppf_body(mix[e], f.lam_tl, f.inv_lam_tl) * f.sigTL32;
+                }
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float cnt = __uint_as_float(q[pq[e]].x);
+                    const double dq = quant_draw_f64(mix[e]);
+                    double A = __dmul_rn((double)cnt, f.K);
+                    A = __dadd_rn(A, (double)d_read[e]);
+                    A = __dadd_rn(A, row64);
+                    A = __dadd_rn(A, dq);
+                    const double z = clip_f64(div_rn_by_const(A, f.span, f.rspan), f.lo, 1.0);
+                    o[e] = fminf(fmaxf((float)__dmul_rn(z, f.ratio), a.post_lo), a.post_hi);
+                    if (DEBUG) {
+                        const size_t lidx = row_base + x + e;
+                        if (a.d_shot) a.d_shot[lidx] = cnt;
+                        if (a.d_read) a.d_read[lidx] = d_read[e];
+                        if (a.d_q) a.d_q[lidx] = dq;
+                    }
+                }
+                __stcs(reinterpret_cast<float4*>(a.noisy + row_base + x), make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+        __syncwarp();                       // the queue is reused by the next unit
     }
 }
 
@@ -225,6 +401,7 @@ static int check_common(const SynthArgs& a, int chain, bool replay) {
 template <bool DEBUG>
 static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
     if (int e = check_common(a, chain, false)) return e;
+    if (int e = ensure_poisson_table()) return e;
     int dev = 0, sms = 0;
     PNNP_CUDA(cudaGetDevice(&dev));
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -241,10 +418,23 @@ static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
                       ((a.code & 0x3Fu) == (PNNP_CODE_P | PNNP_CODE_G | PNNP_CODE_R | PNNP_CODE_Q)) && !a.ori && !a.clip;
     SynthArgs b = a;
     b.code = a.code & 0x3Fu;
-#define PNNP_LAUNCH(CH, V, F) noise_synth_kernel<CH, DEBUG, V, F><<<blocks, kThreads, 0, st>>>(b)
-    if (fast) PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 4, true);
-    else if (chain == PNNP_CHAIN_NUMPY) { if (vec) PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 4, false); else PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 1, false); }
-    else                                { if (vec) PNNP_LAUNCH(PNNP_CHAIN_TORCH, 4, false); else PNNP_LAUNCH(PNNP_CHAIN_TORCH, 1, false); }
+    b.rk = philox_round_keys(a.seed);
+#define PNNP_LAUNCH(CH, V) noise_synth_kernel<CH, DEBUG, V><<<blocks, kThreads, 0, st>>>(b)
+    if (fast) {
+        const long long funits = (long long)a.n * a.c * a.h * ((a.w + kFastUnit - 1) / kFastUnit);
+        const long long fwant = (funits + (kFastThreads / 32) - 1) / (kFastThreads / 32);
+        static const int minb = [] { const char* e = getenv("PNNP_NOISE_MINB"); return e ? atoi(e) : 3; }();   // tuning knob
+        static bool attr_done = false;
+        if (!attr_done) {
+            PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<DEBUG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
+            PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<DEBUG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
+            attr_done = true;
+        }
+        if (minb == 4) noise_synth_fast_kernel<DEBUG, 4><<<(int)std::min<long long>(fwant, (long long)sms * 4), kFastThreads, kFastSmemBytes, st>>>(b);
+        else           noise_synth_fast_kernel<DEBUG, 3><<<(int)std::min<long long>(fwant, (long long)sms * 3), kFastThreads, kFastSmemBytes, st>>>(b);
+    }
+    else if (chain == PNNP_CHAIN_NUMPY) { if (vec) PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 4); else PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 1); }
+    else                                { if (vec) PNNP_LAUNCH(PNNP_CHAIN_TORCH, 4); else PNNP_LAUNCH(PNNP_CHAIN_TORCH, 1); }
 #undef PNNP_LAUNCH
     count_launch();
     PNNP_CUDA(cudaGetLastError());
@@ -258,7 +448,7 @@ using namespace pnnp;
 extern "C" int pnnp_noise_synth(const float* clean, float* noisy, const pnnp_noise_params* table, int n, int c,
                                 int h, int w, uint32_t code_bits, int chain, int ori, int clip, float post_lo,
                                 float post_hi, uint64_t seed, uint64_t offset, uint64_t crop_id0, void* stream) {
-    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, seed, offset, crop_id0,
+    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, seed, offset, crop_id0, PhiloxKeys{},
                 nullptr, nullptr, nullptr, nullptr};
     return launch_synth<false>(a, chain, (cudaStream_t)stream);
 }
@@ -268,7 +458,7 @@ extern "C" int pnnp_noise_synth_debug(const float* clean, float* noisy, const pn
                                       float post_lo, float post_hi, uint64_t seed, uint64_t offset,
                                       uint64_t crop_id0, float* d_shot, float* d_read, float* d_rowz,
                                       double* d_q, void* stream) {
-    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, seed, offset, crop_id0,
+    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, seed, offset, crop_id0, PhiloxKeys{},
                 d_shot, d_read, d_rowz, d_q};
     return launch_synth<true>(a, chain, (cudaStream_t)stream);
 }
@@ -277,7 +467,7 @@ extern "C" int pnnp_noise_synth_replay(const float* clean, float* noisy, const p
                                        int c, int h, int w, uint32_t code_bits, int chain, int ori, int clip,
                                        float post_lo, float post_hi, const float* d_shot, const float* d_read,
                                        const float* d_rowz, const double* d_q, void* stream) {
-    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, 0, 0, 0,
+    SynthArgs a{clean, noisy, table, n, c, h, w, code_bits, ori, clip, post_lo, post_hi, 0, 0, 0, PhiloxKeys{},
                 const_cast<float*>(d_shot), const_cast<float*>(d_read), const_cast<float*>(d_rowz),
                 const_cast<double*>(d_q)};
     if (int e = check_common(a, chain, true)) return e;

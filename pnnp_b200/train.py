@@ -209,7 +209,8 @@ class UNetTrainStep:
         # 1x1 head: gradient w.r.t. conv9_2's pre-activation, dW10, db10 and conv9_2's bias gradient in one kernel
         g = self.scr.get("g_c9", (n, h, w, nf))
         m10 = net.conv10_1
-        L.check(L.lib().pnnp_head_bwd(gpred.data_ptr(), s["c9"].data_ptr(), m10.weight.detach().reshape(net.out_nc, nf).data_ptr(),
+        w10 = m10.weight.detach().reshape(net.out_nc, nf).to(torch.bfloat16).float()      # the forward multiplied by bf16 weights
+        L.check(L.lib().pnnp_head_bwd(gpred.data_ptr(), s["c9"].data_ptr(), w10.data_ptr(),
                                       g.data_ptr(), self._grad_view("conv10_1.weight").data_ptr(),
                                       self._grad_view("conv10_1.bias").data_ptr(), None, n, h, w, nf, net.out_nc, LK,
                                       self._stream()), "head_bwd")

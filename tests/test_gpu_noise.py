@@ -132,8 +132,9 @@ def test_specialised_kernel_is_bit_identical_to_replay_at_scale():
 
 
 def test_device_philox_words_match_cpu_philox():
-    """Element g uses words 3e..3e+2 (e = g & 3) of the three Philox blocks of group g >> 2; the
-    quantisation draw exposes word 3e+2 exactly: q = (w + 0.5) * 2^-32 - 0.5."""
+    """Draw layout (csrc/noise_core.cuh): group G = g >> 2 owns Philox blocks sub 0 (shot words) and sub 1 ("mix" words:
+    read-noise cell = mix >> 12, quantisation draw = mix & 0xFFF).  The quantisation draw exposes the low 12 bits of word
+    e = g & 3 of block sub 1 exactly: q = (bits + 0.5) / 4096 - 0.5."""
     n, c, h, w = 2, 4, 8, 64
     y = _cuda(_mk(n, h, w, 5))
     np.random.seed(1)
@@ -143,15 +144,36 @@ def test_device_philox_words_match_cpu_philox():
     gen.offset = 7
     _, d = P.synthesize_batch(y, params, "pgrq", generator=gen, crop_id0=crop0, debug=True)
     q = d["q"].cpu().numpy().reshape(-1)
-    words = np.round((q + 0.5) * 2.0 ** 32 - 0.5).astype(np.uint64)
+    bits = (q + 0.5) * 4096.0 - 0.5
+    assert np.array_equal(bits, np.round(bits)) and bits.min() >= 0 and bits.max() <= 4095
     g = np.arange(n * c * h * w, dtype=np.uint64) + np.uint64(crop0 * c * h * w)
     grp, e = g >> np.uint64(2), (g & np.uint64(3)).astype(np.int64)
-    slot = 3 * e + 2
-    sub, word = (slot // 4).astype(np.uint64), slot % 4
+    sub = np.ones_like(grp)
     ctr = np.stack([grp & np.uint64(0xFFFFFFFF), ((grp >> np.uint64(32)) & np.uint64(0xFFFF)) | (sub << np.uint64(16)),
                     np.full_like(grp, 7), np.zeros_like(grp)], -1).astype(np.uint32)
     ref = O.philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32))
-    assert np.array_equal(words, ref[np.arange(g.size), word].astype(np.uint64))
+    mix = ref[np.arange(g.size), e].astype(np.uint64)
+    assert np.array_equal(bits.astype(np.uint64), mix & np.uint64(0xFFF))
+    # the generic kernel (hint withheld) uses the same draws as the specialised one
+    tab = P.ParamTable(params, y.device)
+    tab.uniform_f64 = False
+    gen2 = P.PhiloxGenerator(seed)
+    gen2.offset = 7
+    out_f = P.synthesize_batch(y, params, "pgrq", generator=P.PhiloxGenerator(seed), crop_id0=crop0)
+    out_g = P.synthesize_batch(y, None, "pgrq", generator=P.PhiloxGenerator(seed), crop_id0=crop0, table=tab)
+    assert torch.equal(out_f, out_g)
+
+
+def test_read_noise_tail_refinement_keeps_full_resolution():
+    """The outer 256 cells of each tail of the 20-bit read-noise draw are refined with 12 more random bits: extreme
+    quantiles are not confined to the cell-centre lattice (2 x 2^21 draws -> ~2000 tail draws, almost all distinct)."""
+    y = torch.zeros((1, 4, 1024, 1024), device="cuda")
+    _, d = P.synthesize_batch(y, [_flat_param(1.0, sigTL=1.0, lam=-0.026)], "pg", generator=P.PhiloxGenerator(77), debug=True)
+    r = d["read"].flatten()
+    q_lo = float(O.tukeylambda_ppf(np.float64(256.0 / 2 ** 20), -0.026))
+    tail = r[r < q_lo]
+    assert 600 < tail.numel() < 1500                               # expected 4 Mi * 2^-12 = 1024
+    assert torch.unique(tail).numel() > 0.95 * tail.numel()        # cell centres alone would give <= 256 distinct values
 
 
 def test_shard_independence():

@@ -292,9 +292,74 @@ def test_training_step_gradients_match_fp32_autograd(std):
     # gradients (measured 2.7 % with the reference init, 9.8 % with O(1) activations): relative L2 < 15 %, cosine > 0.99
     bad = {k: v for k, v in st32.items() if not (v[1] > 0.99 and v[0] < 0.15)}
     assert not bad, bad
-    # vs the bf16-storage network: only bf16 rounding of the activation gradients remains: relative L2 < 5 %, cosine > 0.998
-    bad = {k: v for k, v in st16.items() if not (v[1] > 0.998 and v[0] < 0.05)}
+    # vs the bf16-storage network: the two bf16 forwards still drift apart (different fp32 summation orders -> different
+    # bf16 roundings, amplified layer by layer when activations are O(1)), which flips ~0.3 % of the LeakyReLU masks:
+    # measured 1.7 % (reference init) / 7.6 % (O(1) activations).  The exact statement is the layer-local test below.
+    bad = {k: v for k, v in st16.items() if not (v[1] > 0.995 and v[0] < 0.10)}
     assert not bad, bad
+
+
+def test_backward_is_exact_layer_by_layer_on_a_real_step():
+    """Chain rule, link by link: every layer's weight / bias / input gradients of a real training step are compared with
+    torch autograd of THAT layer evaluated on the step's own saved activations and incoming gradient, so routing decisions
+    (LeakyReLU masks, max-pool arg-max) are shared and only rounding remains: weight and bias gradients to 2e-3 relative
+    (fp32 accumulation of exact bf16 products), activation gradients to 6e-3 relative after bf16 rounding."""
+    net, lr_in, hr = _make(std=1.4)
+    ts = train.UNetTrainStep(net)
+    pred, s = ts.forward(lr_in)
+    gp = torch.empty_like(pred)
+    L.check(L.lib().pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gp.data_ptr(), pred.numel(), ts.loss_sum.data_ptr(), _sp()), "l1")
+    ts.backward(gp, s)
+    _ok()
+    B = ts.scr.bufs
+    W = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    slope = lambda a: torch.where(_nchw(a) > 0, 1.0, 0.2)               # LeakyReLU'(.) from the stored activated output
+    worst = {"w": 0.0, "b": 0.0, "x": 0.0}
+
+    def layer(name, xs, gz, conv):
+        """xs: NHWC bf16 inputs; gz: NHWC bf16 gradient w.r.t. the layer's pre-activation.  Returns input gradients (NCHW fp32)."""
+        xin = [_nchw(x).requires_grad_(True) for x in xs]
+        w = _bf(W[name + ".weight"]).requires_grad_(True)
+        b = W[name + ".bias"].clone().requires_grad_(True)
+        cin_real = w.shape[1] if conv else w.shape[0]
+        xcat = torch.cat(xin, 1)[:, :cin_real]                          # conv1_1: 16 stored channels, 4 real
+        out = F.conv2d(xcat, w, b, padding=w.shape[-1] // 2) if conv else F.conv_transpose2d(xcat, w, b, stride=2)
+        out.backward(_nchw(gz))
+        rw, rb = _rel(ts._grad_view(name + ".weight"), w.grad), _rel(ts._grad_view(name + ".bias"), b.grad)
+        worst["w"], worst["b"] = max(worst["w"], rw), max(worst["b"], rb)
+        assert rw < 2e-3 and rb < 2e-3, (name, rw, rb)
+        return [x.grad for x in xin]
+
+    def check_x(tag, ours, want):
+        r = _rel(_nchw(ours), _bf(want))
+        worst["x"] = max(worst["x"], r)
+        assert r < 6e-3, (tag, r)
+
+    # 1x1 head (its kernel also applies conv9_2's LeakyReLU')
+    (dx,) = layer("conv10_1", [s["c9"]], _nhwc(gp), True)
+    check_x("head", B["g_c9"], dx * slope(s["c9"]))
+    gz = B["g_c9"]
+    for i in range(9, 5, -1):                                               # decoder
+        (dx,) = layer(f"conv{i}_2", [s[f"c{i}a"]], gz, True)
+        check_x(f"conv{i}_2.dx", B[f"gx_conv{i}_2_0"], dx * slope(s[f"c{i}a"]))
+        dup, dskip = layer(f"conv{i}_1", [s[f"u{i}"], s[f"c{10 - i}"]], B[f"gx_conv{i}_2_0"], True)
+        check_x(f"conv{i}_1.dx_up", B[f"gx_conv{i}_1_0"], dup)
+        check_x(f"conv{i}_1.dx_skip", B[f"gx_conv{i}_1_1"], dskip)
+        src = s["c5"] if i == 6 else s[f"c{i - 1}"]
+        (dx,) = layer(f"upv{i}", [src], B[f"gx_conv{i}_1_0"], False)
+        check_x(f"upv{i}.dx", B[f"gx_upv{i}"], dx * slope(src))
+        gz = B[f"gx_upv{i}"]
+    for i in range(5, 0, -1):                                               # encoder
+        (dx,) = layer(f"conv{i}_2", [s[f"c{i}a"]], gz, True)
+        check_x(f"conv{i}_2.dx", B[f"gx_conv{i}_2_0"], dx * slope(s[f"c{i}a"]))
+        (dx,) = layer(f"conv{i}_1", [s[f"in{i}_1"]], B[f"gx_conv{i}_2_0"], True)
+        if i > 1:
+            check_x(f"conv{i}_1.dx", B[f"gx_conv{i}_1_0"], dx)
+            c = _nchw(s[f"c{i - 1}"]).requires_grad_(True)                  # max-pool routing + skip add + LeakyReLU'
+            F.max_pool2d(c, 2).backward(_nchw(B[f"gx_conv{i}_1_0"]))
+            check_x(f"pool{i - 1}", B[f"g_c{i - 1}"], _bf(c.grad + _nchw(B[f"gx_conv{11 - i}_1_1"])) * slope(s[f"c{i - 1}"]))
+            gz = B[f"g_c{i - 1}"]
+    print("worst relative errors:", worst)
 
 
 def test_training_reduces_loss_like_the_reference_loop():

@@ -67,3 +67,73 @@ def test_poisson_inversion_cdf_error_bounds():
     assert worst[10.0][0] < 5e-5 and worst[10.0][1] < 5e-4        # KS distance, total-variation bound at the switch point
     assert worst[32.0][0] < 5e-6 and worst[64.0][0] < 1e-6 and worst[835.0][0] < 1e-8
     assert all(worst[a][0] >= worst[b][0] for a, b in zip(sorted(worst)[:-1], sorted(worst)[1:]))   # monotone in lam
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# lam < 10: the table form of the exact inversion (csrc/noise_core.cuh: poisson_small_table), modelled in float32
+# ---------------------------------------------------------------------------------------------------------------
+ROWS, COLS, PAD = 161, 32, 5
+
+
+def _table():
+    from scipy import stats
+    t = np.zeros((ROWS, PAD + COLS), dtype=np.float32)
+    for r in range(ROWS):
+        t[r, PAD:] = np.minimum(stats.poisson.cdf(np.arange(COLS), r / 16.0), 1.0).astype(np.float32)
+    return t
+
+
+def _table_sampler(lam, words, t):
+    f32 = np.float32
+    lam = lam.astype(f32)
+    u = np.minimum((words.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(f32), f32(0.99999994))   # fmaf, one rounding
+    i = (lam * f32(16)).astype(np.int64)
+    delta = (lam.astype(np.float64) - 0.0625 * i).astype(f32)                                          # exact
+    k = np.zeros(lam.shape, dtype=np.int64)
+    rows = t[i]
+    for s in (16, 8, 4, 2, 1):
+        k += np.where(rows[np.arange(len(k)), PAD + k + s - 1] < u, s, 0)
+    c2 = f32(0.5) * delta * delta
+    c3 = c2 * delta * f32(0.33333334)
+    c4 = c3 * delta * f32(0.25)
+    ed = np.exp(delta.astype(np.float64)).astype(f32)
+    ue = u * ed
+    done = np.zeros(lam.shape, dtype=bool)
+    for _ in range(COLS):
+        kk = np.minimum(k, COLS - 1)
+        g = lambda j: rows[np.arange(len(k)), PAD + kk - j].astype(np.float64)
+        s_ = (g(0) + delta * g(1) + c2 * g(2) + c3 * g(3) + c4 * g(4)).astype(f32)
+        ok = (s_ >= ue) | (k >= COLS)
+        done |= ok
+        k = np.where(done, k, k + 1)
+        if done.all():
+            break
+    return k
+
+
+def test_kernel_source_uses_the_modelled_table_geometry():
+    src = open(os.path.join(ROOT, "pnnp_b200", "csrc", "noise_core.cuh")).read()
+    assert "kPoisRows = 161, kPoisCols = 32, kPoisPad = 5" in src and "lam * 16.0f" in src
+
+
+def test_small_rate_table_inversion_is_the_exact_inverse_cdf():
+    """k(u, lam) from the table algorithm == scipy's exact Poisson quantile, except within float32 rounding of a CDF
+    step (|F(k) - u| < 4e-7), for rates across [0, 10) including grid points and the ends of the grid cells."""
+    from scipy import stats
+    t = _table()
+    rs = np.random.RandomState(3)
+    n = 400_000
+    lam = np.concatenate([rs.uniform(0, 10, n), rs.randint(0, 160, 20_000) / 16.0, rs.randint(1, 160, 20_000) / 16.0 - 1e-6,
+                          rs.uniform(0, 0.05, 20_000)]).astype(np.float32)
+    lam = np.clip(lam, 0, np.float32(9.999999))
+    words = rs.randint(0, 2 ** 32, size=lam.size, dtype=np.uint64)
+    k = _table_sampler(lam, words, t)
+    u = np.minimum(words.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33, 0.99999994)
+    ref = stats.poisson.ppf(u, lam.astype(np.float64)).astype(np.int64)
+    bad = np.nonzero(k != ref)[0]
+    assert bad.size < 2e-5 * lam.size, bad.size                                  # a handful of boundary cases
+    if bad.size:
+        lo, hi = np.minimum(k[bad], ref[bad]), np.maximum(k[bad], ref[bad])
+        assert (hi - lo == 1).all()
+        assert np.abs(stats.poisson.cdf(lo, lam[bad].astype(np.float64)) - u[bad]).max() < 4e-7
+    assert k.max() < COLS                                                        # the sequential fallback was not needed here
