@@ -214,6 +214,14 @@ int pnnp_wgrad_tc(const void* gT, const void* xT, size_t row_elems, size_t valid
                   const int* tap_off_host, const int* tap_plane_host, int planes, float* dw, int ci_off, int ci_total,
                   void* stream);
 int pnnp_wgrad_pipeline_error(void);
+/* Weight gradients straight from the NHWC bf16 activations (tcgen05, MN-major operands via TMA; no transposed copies):
+ *   mode 0 (3x3 s1 p1 conv):      dw[ky*3+kx][ci_off + ci][co] += sum_p x[p + (ky-1, kx-1)][ci] * g[p][co]
+ *   mode 1 (ConvTranspose2d 2x2): dw[a*2+b][ci_off + ci][co]   += sum_p x[p][ci] * g[2p + (a, b)][co]
+ * g: [n][h|2h][w|2w][co_stride], x: [n][h][w][ci_stride]; dw: fp32 [taps][ci_total][co_pad] (zeroed by the caller).
+ * co, ci: 16, 32, 64 or a multiple of 128. */
+int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, const void* x, int ci, int ci_stride, int n, int h, int w,
+                    float* dw, int ci_off, int ci_total, int co_pad, void* stream);
+int pnnp_wgrad_nhwc_pipeline_error(void);
 /* torch.optim.Adam step (no weight decay) over flat fp32 buffers; g is multiplied by gscale first */
 int pnnp_adam_step(float* p, const float* g, float* m, float* v, size_t total, float lr, float b1, float b2, float eps,
                    int step, float gscale, void* stream);

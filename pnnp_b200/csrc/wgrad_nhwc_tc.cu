@@ -1,0 +1,329 @@
+// Weight gradients of the training step (T1) as an implicit GEMM straight from the NHWC bf16 activations — no
+// transposed copies, no padding pass:
+//
+//   3x3 conv      dW[ky*3+kx][ci][co] = sum over pixels p of  x[p + (ky-1, kx-1)][ci] * g[p][co]        (zero outside the image)
+//   convT 2x2 s2  dW[a*2+b][ci][co]   = sum over input pixels p of  x[p][ci] * g[2p + (a, b)][co]
+//
+// GEMM view: K = pixels, M = output channels of the layer (rows of g), N = (filter tap, input channel) (rows of x).  A TMA box
+// of an NHWC tensor — `cw` channels x 16 x 8 pixels (10 rows for the 3x3 halo) — lands in shared memory as [pixel][cw channels],
+// i.e. K rows of MN-contiguous elements: the canonical **MN-major** operand layout of tcgen05.mma (instruction-descriptor bits
+// 15/16 set, 32/64/128-byte swizzle = the row pitch, SBO = 8 rows, LBO = distance between channel blocks).  The conv's zero
+// padding is the TMA unit's out-of-bounds fill; a shift by one filter row is a 16-row offset of the operand start inside the
+// haloed box; a shift by one filter column is a separate box; the stride-2 gather of the transposed conv is the tensor map's
+// element stride.  One MMA covers 128 output channels x up to 192 (tap, channel) columns x 16 pixels; accumulators stay in
+// TMEM (<= 512 columns) over the CTA's whole pixel range (split-K across CTAs) and are added to the fp32 gradient with
+// coalesced red.global.add (the scratch layout is [tap][ci][co], output channel = TMEM lane = fastest index).
+//
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (once, after the K loop).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include "abi_common.h"
+#include "tc_common.cuh"
+#include "../../include/pnnp_b200.h"
+
+namespace pnnp {
+
+constexpr int kWnTileW = 16, kWnTileH = 8, kWnPix = 128;      // pixels per K stage
+constexpr int kWnMaxBoxes = 6, kWnMaxMmas = 3, kWnMaxAtoms = 9, kWnStagesMax = 4;
+
+struct WnBox { int is_x; int c0; int mul; int dx, dy; int smem_off; int bytes; };   // coords (c0, X0*mul+dx, Y0*mul+dy, img)
+struct WnMma { int a_off, b_off; int n; int lbo_b; int tmem_col; };                  // one MMA per 16-pixel K step
+struct WnAtom { int col, width, tap, ci0; };                                        // accumulator columns -> (tap, input channels)
+
+struct WnParams {
+    int n_boxes, n_mmas, n_atoms;
+    WnBox box[kWnMaxBoxes];
+    WnMma mma[kWnMaxMmas];
+    WnAtom atom[kWnMaxAtoms];
+    int pitch_a, pitch_b, lbo_a;       // bytes per pixel row of the g / x tiles (= swizzle span); distance between g channel blocks
+    int swz_a, swz_b;
+    int stage_bytes, stage_tx, stages;
+    int tiles_x, tiles_y, tiles_total; // pixel tiles of the K range (per image tiles_x * tiles_y)
+    int splits;
+    int m0, co;                        // first output channel of this launch's M tile; valid rows = co - m0
+    int ci_total, co_pad;              // dw scratch geometry [tap][ci_total][co_pad]
+    float* dw;
+    int tmem_cols;
+    int dbg;
+    int* err;
+};
+
+// MN-major shared-memory matrix descriptor: [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle
+__device__ __forceinline__ uint64_t umma_desc_mn_hi(int swz, int lbo_bytes) {
+    const uint64_t layout = swz == 128 ? 2ull : (swz == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (uint64_t)((8 * swz) >> 4);                 // 8 pixel rows of `swz` bytes
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWnStagesMax;
+    uint64_t* done_bar = bars + 2 * kWnStagesMax;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWnStagesMax + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int per = (p.tiles_total + p.splits - 1) / p.splits;
+    const int t_begin = split * per, t_end = min(p.tiles_total, t_begin + per);
+    const int nk = max(0, t_end - t_begin);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(done_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        uint32_t stage = 0, phase = 0;
+        const int tiles_img = p.tiles_x * p.tiles_y;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int img = t / tiles_img, r = t - img * tiles_img;
+            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const int X0 = tx * kWnTileW, Y0 = ty * kWnTileH;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 301);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            if (p.dbg & 1) { if (elect_one()) mbar_arrive(fb); }
+            else if (elect_one()) {
+                mbar_expect_tx(fb, (uint32_t)p.stage_tx);
+                for (int b = 0; b < p.n_boxes; ++b) {
+                    const WnBox& bx = p.box[b];
+                    tma_load_4d(sa + bx.smem_off, bx.is_x ? &tmX : &tmG, fb, bx.c0, X0 * bx.mul + bx.dx, Y0 * bx.mul + bx.dy, img);
+                }
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        const uint64_t ahi = umma_desc_mn_hi(p.swz_a, p.lbo_a);
+        // instruction descriptor: D fp32, A/B bf16, both operands MN-major (bits 15, 16), M = 128
+        const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t kstep_a = (uint32_t)(16 * p.pitch_a) >> 4, kstep_b = (uint32_t)(16 * p.pitch_b) >> 4;
+        uint32_t stage = 0, phase = 0;
+        for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 303);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            if (elect_one()) {
+                for (int m = 0; m < p.n_mmas; ++m) {
+                    const WnMma& mm = p.mma[m];
+                    const uint32_t idesc = idesc_base | ((uint32_t)(mm.n >> 3) << 17);
+                    const uint64_t adesc0 = ahi | (uint64_t)(((sa + (uint32_t)mm.a_off) >> 4) & 0x3FFFu);
+                    const uint64_t bdesc0 = umma_desc_mn_hi(p.swz_b, mm.lbo_b) | (uint64_t)(((sa + (uint32_t)mm.b_off) >> 4) & 0x3FFFu);
+#pragma unroll
+                    for (int k = 0; k < kWnPix / 16; ++k)
+                        if (!(p.dbg & 2))
+                            tc_mma_bf16(tmem_base + (uint32_t)mm.tmem_col, adesc0 + (uint64_t)(k * kstep_a), bdesc0 + (uint64_t)(k * kstep_b),
+                                        idesc, (ks | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(smem_u32(&empty_bar[stage]));
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) tc_commit(smem_u32(done_bar));
+        __syncwarp();
+    } else if (nk > 0) {
+        // ============================== epilogue ==============================
+        // thread = accumulator row = output channel; add the partial tile to dw[tap][ci][co] (co fastest: coalesced reds)
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const bool row_ok = p.m0 + row < p.co;
+        mbar_wait(smem_u32(done_bar), 0, p.err, 304);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int t = 0; t < p.n_atoms; ++t) {
+            const WnAtom& at = p.atom[t];
+            float* dst = p.dw + ((size_t)at.tap * p.ci_total + at.ci0) * p.co_pad + p.m0 + row;
+            for (int j = 0; j < at.width; j += 16) {
+                uint32_t v[16];
+                if (p.dbg & 4) continue;
+                tc_ld16(taddr + (uint32_t)(at.col + j), v);
+                tc_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(j + i) * p.co_pad, __uint_as_float(v[i]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn3 get_encode3() {
+    static EncodeTiledFn3 fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn3>(q);
+    }
+    return fn;
+}
+// NHWC bf16 [n][h][w][c_stride] viewed as (C, W, H, N); box (cw channels, 16, box_h, 1) pixels, traversal stride `stride` in x and y
+static int make_nhwc_map(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c_stride, int cw, int box_h, int stride) {
+    EncodeTiledFn3 enc = get_encode3();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)c_stride, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c_stride * 2, (cuuint64_t)w * c_stride * 2, (cuuint64_t)h * w * c_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)(kWnTileW * stride), (cuuint32_t)(box_h * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    const int swz = cw * 2;
+    const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(wgrad NHWC operand) failed: %d", (int)r); return fail(b); }
+    return 0;
+}
+
+static int* g_wn_err = nullptr;
+
+}  // namespace pnnp
+
+using namespace pnnp;
+
+// mode 0: 3x3 stride-1 pad-1 conv  — g: NHWC [n][h][w][co_stride], x: NHWC [n][h][w][ci_stride]; dw: [9][ci_total][co_pad]
+// mode 1: ConvTranspose2d(2, s2)   — g: NHWC [n][2h][2w][co_stride], x: NHWC [n][h][w][ci_stride]; dw: [4][ci_total][co_pad]
+// Accumulates (+=) rows [ci_off, ci_off + ci) x columns [0, co) of every tap; co, ci multiples of 16 (ci a power-of-two multiple
+// of 16 up to 64, or a multiple of 128 above... see the checks).
+extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, const void* x, int ci, int ci_stride, int n, int h, int w,
+                               float* dw, int ci_off, int ci_total, int co_pad, void* stream) {
+    if (!g || !x || !dw) return fail("wgrad_nhwc: null pointer");
+    if (mode != 0 && mode != 1) return fail("wgrad_nhwc: mode must be 0 (conv3x3) or 1 (convT2x2)");
+    if (co < 16 || (co % 16) || ci < 16 || (ci % 16) || co_pad < co || ci_off + ci > ci_total) return fail("wgrad_nhwc: bad channel geometry");
+    if (!((ci == 16 || ci == 32 || ci == 64) || (ci % 128 == 0))) return fail("wgrad_nhwc: ci must be 16, 32, 64 or a multiple of 128");
+    if (!((co == 16 || co == 32 || co == 64) || (co % 128 == 0))) return fail("wgrad_nhwc: co must be 16, 32, 64 or a multiple of 128");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    PNNP_CUDA(cudaGetDevice(&dev));
+    PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!g_wn_err) { PNNP_CUDA(cudaMalloc(&g_wn_err, sizeof(int))); PNNP_CUDA(cudaMemset(g_wn_err, 0, sizeof(int))); }
+    static bool attr_done = false;
+    if (!attr_done) { PNNP_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+
+    const int cw_g = std::min(co, 64), cw_x = std::min(ci, 64);          // channels per TMA box = swizzle span / 2
+    const int pitch_a = cw_g * 2, pitch_b = cw_x * 2;
+    const int box_h_x = mode == 0 ? kWnTileH + 2 : kWnTileH;
+    const int a_box_bytes = kWnPix * pitch_a;                              // one g block: 128 pixels
+    const int b_box_bytes = kWnTileW * box_h_x * pitch_b;                  // one x block: 160 (haloed) or 128 pixels
+    const int a_region = 128 / cw_g * a_box_bytes;                         // M = 128 rows always addressable (rows >= co are never stored)
+    CUtensorMap tmG, tmX;
+    if (int e = make_nhwc_map(&tmG, g, n, mode == 0 ? h : 2 * h, mode == 0 ? w : 2 * w, co_stride, cw_g, kWnTileH, mode == 0 ? 1 : 2)) return e;
+    if (int e = make_nhwc_map(&tmX, x, n, h, w, ci_stride, cw_x, box_h_x, 1)) return e;
+
+    const int tiles_x = (w + kWnTileW - 1) / kWnTileW, tiles_y = (h + kWnTileH - 1) / kWnTileH;
+    const int ci_tile = ci <= 64 ? ci : 128;
+    const int n_tiles = ci / ci_tile, m_tiles = (co + 127) / 128;
+    // tap sets: 3x3 with ci <= 32 keeps all nine taps (three dx boxes) in one CTA; otherwise one filter column per CTA;
+    // the transposed conv takes one of its four taps per CTA
+    const int tapsets = mode == 1 ? 4 : (ci <= 32 ? 1 : 3);
+    const int combos = m_tiles * n_tiles * tapsets;
+    const int tiles_total = n * tiles_x * tiles_y;
+    const int splits = std::max(1, std::min(tiles_total, (2 * sms + combos - 1) / combos));
+    const char* e = getenv("PNNP_WG_DBG");
+    const int dbg = e ? atoi(e) : 0;
+
+    for (int mt = 0; mt < m_tiles; ++mt)
+        for (int nt = 0; nt < n_tiles; ++nt)
+            for (int ts = 0; ts < tapsets; ++ts) {
+                WnParams p{};
+                p.pitch_a = pitch_a; p.pitch_b = pitch_b; p.swz_a = pitch_a; p.swz_b = pitch_b; p.lbo_a = a_box_bytes;
+                p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_total = tiles_total; p.splits = splits;
+                p.m0 = mt * 128; p.co = co; p.ci_total = ci_total; p.co_pad = co_pad; p.dw = dw; p.dbg = dbg; p.err = g_wn_err;
+                int off = 0, nb = 0;
+                // g blocks of this M tile
+                const int g_blocks = std::min(128, co - p.m0) / cw_g;
+                for (int b = 0; b < g_blocks; ++b) {
+                    WnBox& bx = p.box[nb++];
+                    bx.is_x = 0; bx.c0 = p.m0 + b * cw_g; bx.smem_off = b * a_box_bytes; bx.bytes = a_box_bytes;
+                    if (mode == 0) { bx.mul = 1; bx.dx = 0; bx.dy = 0; }
+                    else { bx.mul = 2; bx.dx = ts & 1; bx.dy = ts >> 1; }            // tap (a, b) = (ts >> 1, ts & 1): rows 2y + a, cols 2x + b
+                }
+                off = a_region;
+                int col = 0;
+                if (mode == 0 && ci <= 32) {
+                    for (int dx = 0; dx < 3; ++dx) {
+                        WnBox& bx = p.box[nb++];
+                        bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = dx - 1; bx.dy = -1; bx.smem_off = off; bx.bytes = b_box_bytes;
+                        WnMma& mm = p.mma[p.n_mmas++];
+                        mm.a_off = 0; mm.b_off = off; mm.n = 3 * ci; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = col;   // N blocks = the three dy taps
+                        for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{col + dy * ci, ci, dy * 3 + dx, ci_off};
+                        col += 3 * ci; off += b_box_bytes;
+                    }
+                } else if (mode == 0 && ci == 64) {
+                    WnBox& bx = p.box[nb++];
+                    bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = ts - 1; bx.dy = -1; bx.smem_off = off; bx.bytes = b_box_bytes;
+                    WnMma& mm = p.mma[p.n_mmas++];
+                    mm.a_off = 0; mm.b_off = off; mm.n = 192; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = 0;
+                    for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{dy * 64, 64, dy * 3 + ts, ci_off};
+                    col = 192; off += b_box_bytes;
+                } else if (mode == 0) {
+                    for (int c = 0; c < 2; ++c) {
+                        WnBox& bx = p.box[nb++];
+                        bx.is_x = 1; bx.c0 = nt * 128 + c * 64; bx.mul = 1; bx.dx = ts - 1; bx.dy = -1; bx.smem_off = off + c * b_box_bytes; bx.bytes = b_box_bytes;
+                    }
+                    for (int dy = 0; dy < 3; ++dy) {
+                        WnMma& mm = p.mma[p.n_mmas++];
+                        mm.a_off = 0; mm.b_off = off + dy * kWnTileW * pitch_b; mm.n = 128; mm.lbo_b = b_box_bytes; mm.tmem_col = dy * 128;
+                        for (int c = 0; c < 2; ++c) p.atom[p.n_atoms++] = WnAtom{dy * 128 + c * 64, 64, dy * 3 + ts, ci_off + nt * 128 + c * 64};
+                    }
+                    col = 384; off += 2 * b_box_bytes;
+                } else {
+                    const int blocks = ci_tile / cw_x;
+                    for (int c = 0; c < blocks; ++c) {
+                        WnBox& bx = p.box[nb++];
+                        bx.is_x = 1; bx.c0 = nt * ci_tile + c * cw_x; bx.mul = 1; bx.dx = 0; bx.dy = 0; bx.smem_off = off + c * b_box_bytes; bx.bytes = b_box_bytes;
+                        p.atom[p.n_atoms++] = WnAtom{c * cw_x, cw_x, ts, ci_off + nt * ci_tile + c * cw_x};
+                    }
+                    WnMma& mm = p.mma[p.n_mmas++];
+                    mm.a_off = 0; mm.b_off = off; mm.n = ci_tile; mm.lbo_b = b_box_bytes; mm.tmem_col = 0;
+                    col = ci_tile; off += blocks * b_box_bytes;
+                }
+                p.n_boxes = nb;
+                p.stage_tx = 0;
+                for (int b = 0; b < nb; ++b) p.stage_tx += p.box[b].bytes;
+                p.stage_bytes = (off + 1023) / 1024 * 1024;
+                p.stages = std::max(2, std::min(kWnStagesMax, (227 * 1024 - 2048) / p.stage_bytes));
+                int tc = 32; while (tc < col) tc <<= 1;
+                p.tmem_cols = tc;
+                const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * kWnStagesMax + 1) * 8 + 64;
+                if (smem > 227 * 1024 || tc > 512) return fail("wgrad_nhwc: shared memory / TMEM budget exceeded");
+                wgrad_nhwc_kernel<<<splits, 192, smem, st>>>(tmG, tmX, p);
+                count_launch();
+                PNNP_CUDA(cudaGetLastError());
+            }
+    return 0;
+}
+
+extern "C" int pnnp_wgrad_nhwc_pipeline_error(void) {
+    int v = 0;
+    if (g_wn_err) { cudaMemcpy(&v, g_wn_err, sizeof(int), cudaMemcpyDeviceToHost); if (v) cudaMemset(g_wn_err, 0, sizeof(int)); }
+    return v;
+}

@@ -106,6 +106,13 @@ class UNetTrainStep:
                                            self._stream()), "transpose_pad")
         return out, row, ppad
 
+    def _wgrad_nhwc(self, mode, g, co, x, dw, ci_off, ci_total):
+        """dw[tap][ci_off + ci][co] += the weight gradient of a 3x3 conv (mode 0) / 2x2 stride-2 transposed conv (mode 1)
+        with pre-activation output gradient g and input x (both NHWC bf16), by the tcgen05 kernel of csrc/wgrad_nhwc_tc.cu."""
+        n, h, w, ci = x.shape
+        L.check(L.lib().pnnp_wgrad_nhwc(mode, g.data_ptr(), co, g.shape[-1], x.data_ptr(), ci, ci, n, h, w, dw.data_ptr(), ci_off,
+                                        ci_total, dw.shape[-1], self._stream()), "wgrad_nhwc")
+
     def _wgrad(self, gT, xT, row, valid, co, ci, offs, planes, dw, ci_off, ci_total, dw_elem_off=0):
         arr, pl = (C.c_int * len(offs))(*offs), (C.c_int * len(offs))(*planes)
         L.check(L.lib().pnnp_wgrad_tc(gT.data_ptr(), xT.data_ptr(), row, valid, co, ci, len(offs), arr, pl, xT.shape[0],
@@ -119,18 +126,15 @@ class UNetTrainStep:
         co = m.weight.shape[0]
         n, h, w, _ = g.shape
         self._act_bwd(g, out_act, self._grad_view(name + ".bias"), act)
-        gT, row, valid = self._transpose("gT", g, 0, co)
-        offs, planes = conv3_taps(w)
         ci_total = sum(s.shape[-1] for s in srcs)
-        dw = self.scr.get("dw_" + name, (9, co, ci_total), torch.float32)
+        dw = self.scr.get("dw_" + name, (9, ci_total, co), torch.float32)
         dw.zero_()
         c_off = 0
-        for k, s in enumerate(srcs):
-            xT, _, _ = self._transpose(f"xT{k}", s, 0, s.shape[-1], copies=3)
-            self._wgrad(gT, xT, row, valid, co, s.shape[-1], offs, planes, dw, c_off, ci_total)
+        for s in srcs:
+            self._wgrad_nhwc(0, g, co, s, dw, c_off, ci_total)
             c_off += s.shape[-1]
         cin_real = m.weight.shape[1]
-        self._grad_view(name + ".weight").copy_(dw[:, :, :cin_real].permute(1, 2, 0).reshape(co, cin_real, 3, 3))
+        self._grad_view(name + ".weight").copy_(dw[:, :cin_real, :].permute(2, 1, 0).reshape(co, cin_real, 3, 3))
         gxs = []
         if need_dx:
             W = m.weight.detach()
@@ -150,14 +154,10 @@ class UNetTrainStep:
         ci, co = m.weight.shape[0], m.weight.shape[1]
         n, h, w, _ = x_in.shape
         self._act_bwd(g_up, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)
-        xT, row, valid = self._transpose("xT_up", x_in, 0, ci)
-        dw = self.scr.get("dw_" + name, (4, co, ci), torch.float32)
+        dw = self.scr.get("dw_" + name, (4, ci, co), torch.float32)
         dw.zero_()
-        for a in range(2):
-            for b in range(2):
-                gT, _, _ = self._transpose("gT", g_up, 0, co, stride=2, pa=a, pb=b)
-                self._wgrad(gT, xT, row, valid, co, ci, [0], [0], dw, 0, ci, dw_elem_off=(a * 2 + b) * co * ci)
-        self._grad_view(name + ".weight").copy_(dw.permute(2, 1, 0).reshape(ci, co, 2, 2))
+        self._wgrad_nhwc(1, g_up, co, x_in, dw, 0, ci)
+        self._grad_view(name + ".weight").copy_(dw.permute(1, 2, 0).reshape(ci, co, 2, 2))
         wd = _pack_conv_weight(m.weight.detach())            # [rows=ci][cin=co][a][b] -> [a*2+b][ci][co]
         gx = self.scr.get("gx_" + name, (n, h, w, ci))
         _conv(_lib.CONV2S2, g_up, wd, None, gx, ci, _lib.ACT_NONE)
