@@ -37,7 +37,7 @@ WORKLOADS = {
     "synth64": dict(metric="raw megapixels/sec (noise synthesis, 64x4x512x512 crops per GPU)", n=64, c=4, h=512, w=512,
                     bound="hbm", dtype="f64",
                     desc="synth64 (BASELINE configs[1]): SonyA7S2 'pgrq' noise synthesis, 64 crops of 4x512x512 per GPU, "
-                         "numpy (float64) chain, Philox4x32-10"),
+                         "numpy (float64) chain, Philox4x32-10, 2 blocks per 4 elements"),
     "unet_sony": dict(metric="raw megapixels/sec (UNetSeeInDark eval forward, 4x1424x2128 frame per GPU)", n=1, c=4, h=1424,
                       w=2128, bound="tensor", dtype="bf16",
                       desc="unet_sony (BASELINE configs[0] on GPU): UNetSeeInDark nf=32 forward, one 4x1424x2128 frame, "
@@ -320,7 +320,7 @@ def run_gpu_arm(args, name, wl):
                                generator=gen, crop_id0=crop0, out=out, table=table)
         algo = elems * 8.0                                                     # 4 B read + 4 B write per element
         l2_note = "no flush: 268 MB in + 268 MB out per step exceed the 126 MB L2"
-        kernel = "noise_synth_kernel"
+        kernel = "noise_synth_fast_kernel"
     elif name == "train_step":
         from pnnp_b200.train import UNetTrainStep
         torch.manual_seed(1997)

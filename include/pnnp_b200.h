@@ -189,7 +189,7 @@ int pnnp_eval_epilogue(const float* dn, const float* hr, int n, int c, int h, in
 /* ------------------------------------------------------------------------------------------
  * T1 — synthetic-pair training step (trainer_SID.py:93-101): L1 loss on pred.clamp(0,1)
  * (losses/base_loss.py:92-103), backward through the UNet, Adam (trainer_SID.py:44).
- * dgrad of a 3x3 conv = pnnp_conv2d_tc with transposed + flipped weights; the rest:
+ * dgrad of a 3x3 conv = pnnp_conv2d_tc with transposed + flipped weights; wgrad = pnnp_wgrad_nhwc; the rest:
  * ------------------------------------------------------------------------------------------ */
 /* loss_sum (device double) = sum |clamp(pred,0,1) - hr|;  gpred = d(mean L1)/d pred (NCHW fp32) */
 int pnnp_l1_loss(const float* pred, const float* hr, float* gpred, size_t total, double* loss_sum, void* stream);
@@ -202,18 +202,6 @@ int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t pixels, int
 /* MaxPool2d(2) backward; gskip (optional) is added: gc = gskip + scatter(gp) (the U-Net skip connection) */
 int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c,
                      void* stream);
-/* NHWC bf16 channels [c_off, c_off+c) -> channel-major [copies][c][out_row_elems] over a zero-ringed geometry of
- * (h/stride + 2) rows x wp columns per image (wp >= w/stride + 2, a multiple of 8).  copies = 3 writes the three x-shifted
- * versions out[s][ch][q] = base[ch][q + s - 1] the 3x3 weight-gradient GEMM reads for dx = 0,1,2 (a TMA box cannot start at
- * an innermost coordinate that is not 16-byte aligned).  stride 2 + phase (pa, pb) sub-samples (ConvTranspose wgrad). */
-int pnnp_transpose_pad(const void* in, void* out, int n, int h, int w, int c_stride, int c_off, int c, int stride,
-                       int pa, int pb, size_t out_row_elems, int wp, int copies, void* stream);
-/* dW[tap][co][ci_off + ci] += sum_q gT[co][q] * xT[tap_plane[tap]][ci][q + tap_off[tap]]  (tcgen05 split-K GEMM, fp32
- * atomics).  xT: [planes][ci][row_elems]; tap_off must be multiples of 8; tap_plane_host may be NULL (all taps plane 0). */
-int pnnp_wgrad_tc(const void* gT, const void* xT, size_t row_elems, size_t valid_elems, int co, int ci, int taps_total,
-                  const int* tap_off_host, const int* tap_plane_host, int planes, float* dw, int ci_off, int ci_total,
-                  void* stream);
-int pnnp_wgrad_pipeline_error(void);
 /* Weight gradients straight from the NHWC bf16 activations (tcgen05, MN-major operands via TMA; no transposed copies):
  *   mode 0 (3x3 s1 p1 conv):      dw[ky*3+kx][ci_off + ci][co] += sum_p x[p + (ky-1, kx-1)][ci] * g[p][co]
  *   mode 1 (ConvTranspose2d 2x2): dw[a*2+b][ci_off + ci][co]   += sum_p x[p][ci] * g[2p + (a, b)][co]

@@ -62,9 +62,6 @@ SIGNATURES = {
     "pnnp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pnnp_act_bwd_bias": (_i, [_vp, _vp, _vp, C.c_size_t, _i, _i, _vp]),
     "pnnp_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "pnnp_transpose_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.c_size_t, _i, _i, _vp]),
-    "pnnp_wgrad_tc": (_i, [_vp, _vp, C.c_size_t, C.c_size_t, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _vp, _i, _i, _vp]),
-    "pnnp_wgrad_pipeline_error": (_i, []),
     "pnnp_wgrad_nhwc": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "pnnp_wgrad_nhwc_pipeline_error": (_i, []),
     "pnnp_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, _i, _f, _vp]),

@@ -1,12 +1,11 @@
 // Backward-pass helper kernels of the synthetic-pair training step (T1: trainer_SID.py:93-101,
 // losses/base_loss.py:92-103 — L1 loss on pred.clamp(0,1), Adam lr 1e-4).  The GEMM-shaped parts of
-// the backward (dgrad, wgrad) run on the tcgen05 kernels (conv_tc.cu, wgrad_tc.cu); everything here
+// the backward (dgrad, wgrad) run on the tcgen05 kernels (conv_tc.cu, wgrad_nhwc_tc.cu); everything here
 // is element-wise / small-reduction work on CUDA cores:
 //   l1_loss_kernel        loss = mean |clamp(pred,0,1) - hr| and d loss / d pred            (NCHW fp32)
 //   head_bwd_kernel       backward of the 1x1 head conv10_1 (4 <- 32): data, weight and bias gradients
 //   act_bwd_bias_kernel   g *= act'(out) in place (LeakyReLU 0.2 / ReLU / none) + per-channel bias gradient
 //   maxpool_bwd_kernel    routes the pooled gradient to the arg-max of each 2x2 window (+ skip gradient)
-//   transpose_pad_kernel  NHWC bf16 -> [C][n (h+2)(w+2)] bf16 with a zero ring (K-major operands of wgrad)
 //   adam_kernel           fused Adam over a flat fp32 parameter buffer
 #include <cuda_bf16.h>
 #include "abi_common.h"
@@ -169,46 +168,6 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
     }
 }
 
-// ---------------------------------------------------------------- NHWC -> channel-major with a zero ring
-// in: [n, h, w, c_stride] bf16 (channels [c_off, c_off + c) are taken);  out: [copies][c][out_row_elems] bf16.
-// Padded geometry per image: hp = ho + 2 rows of wp columns (wp >= wo + 2, a multiple of 8 so that a filter row shift is a
-// 16-byte aligned TMA coordinate);  base[ch][(img*hp + y+1)*wp + x+1] = in[img][y][x][ch], everything else 0.
-// copies == 1: out = base.  copies == 3: out[s][ch][q] = base[ch][q + s - 1] — the three x-shifted copies the wgrad GEMM reads
-// for the taps dx = 0, 1, 2 (TMA cannot start a box at an innermost coordinate that is not 16-byte aligned).
-// With stride 2 and phase (a,b): ho = h/2, wo = w/2 and the sample is in[img][2y+a][2x+b] (ConvTranspose wgrad operands).
-__global__ void __launch_bounds__(256) transpose_pad_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                            int n, int h, int w, int c_stride, int c_off, int c, int stride,
-                                                            int pa, int pb, size_t out_row_elems, int wp, int copies) {
-    __shared__ __nv_bfloat16 tile[34][33];
-    const int ho = h / stride, wo = w / stride, hp = ho + 2;
-    const size_t ppad = (size_t)n * hp * wp;
-    // grid: x = padded-pixel tiles of 32, y = channel tiles of 32; the tile holds pixels q0-1 .. q0+32
-    const size_t q0 = (size_t)blockIdx.x * 32;
-    const int ch0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 34; r += blockDim.y) {            // r: pixel within tile (+1), threadIdx.x: channel
-        const long long q = (long long)q0 + r - 1;
-        __nv_bfloat16 v = __float2bfloat16(0.f);
-        if (q >= 0 && (size_t)q < ppad && ch0 + (int)threadIdx.x < c) {
-            const int xp = (int)(q % wp);
-            const size_t t = q / wp;
-            const int yp = (int)(t % hp);
-            const int img = (int)(t / hp);
-            if (xp >= 1 && xp <= wo && yp >= 1 && yp <= ho)
-                v = in[(((size_t)img * h + (size_t)(yp - 1) * stride + pa) * w + (size_t)(xp - 1) * stride + pb) * c_stride + c_off + ch0 + threadIdx.x];
-        }
-        tile[r][threadIdx.x] = v;
-    }
-    __syncthreads();
-    const size_t q = q0 + threadIdx.x;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {            // r: channel within tile, threadIdx.x: pixel
-        if (ch0 + r < c && q < out_row_elems) {
-            if (copies == 1) out[(size_t)(ch0 + r) * out_row_elems + q] = tile[threadIdx.x + 1][r];
-            else
-                for (int s = 0; s < 3; ++s) out[((size_t)s * c + ch0 + r) * out_row_elems + q] = tile[threadIdx.x + s][r];
-        }
-    }
-}
-
 // ---------------------------------------------------------------- Adam (torch.optim.Adam defaults: betas .9/.999, eps 1e-8, no decay)
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, size_t total, float lr, float b1, float b2, float eps,
@@ -265,21 +224,6 @@ extern "C" int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* g
     maxpool_bwd_kernel<<<blocks_for((size_t)n * (h / 2) * (w / 2) * (c / 2)), 256, 0, (cudaStream_t)stream>>>(
         static_cast<const __nv_bfloat16*>(gp), static_cast<const __nv_bfloat16*>(cfull), static_cast<const __nv_bfloat16*>(gskip),
         static_cast<__nv_bfloat16*>(gc), n, h, w, c);
-    count_launch();
-    PNNP_CUDA(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int pnnp_transpose_pad(const void* in, void* out, int n, int h, int w, int c_stride, int c_off, int c, int stride,
-                                  int pa, int pb, size_t out_row_elems, int wp, int copies, void* stream) {
-    if (!in || !out || stride < 1 || stride > 2 || (h % stride) || (w % stride) || (copies != 1 && copies != 3))
-        return fail("transpose_pad: bad arguments");
-    if (wp < w / stride + 2) return fail("transpose_pad: padded row pitch wp must be >= w/stride + 2");
-    const size_t ppad = (size_t)n * (h / stride + 2) * wp;
-    if (out_row_elems < ppad) return fail("transpose_pad: output rows too short");
-    dim3 grid((unsigned)((out_row_elems + 31) / 32), (unsigned)((c + 31) / 32)), block(32, 8);
-    transpose_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out),
-                                                                   n, h, w, c_stride, c_off, c, stride, pa, pb, out_row_elems, wp, copies);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

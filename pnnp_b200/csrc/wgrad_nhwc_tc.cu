@@ -29,9 +29,11 @@ namespace pnnp {
 constexpr int kWnTileW = 16, kWnTileH = 8, kWnPix = 128;      // pixels per K stage
 constexpr int kWnMaxBoxes = 6, kWnMaxMmas = 3, kWnMaxAtoms = 9, kWnStagesMax = 4;
 
-struct WnBox { int is_x; int c0; int mul; int dx, dy; int smem_off; int bytes; };   // coords (c0, X0*mul+dx, Y0*mul+dy, img)
+// coords (c0, X0*mul+dx, Y0*mul+dy, img); by_ts: 1 = filter column from the CTA's tap set (dx = ts - 1), 2 = transposed-conv tap
+// (dx, dy) = (ts & 1, ts >> 1); c0 advances with the CTA's M tile (g boxes, 128 channels) or N tile (x boxes, ci_tile channels)
+struct WnBox { int is_x; int c0; int mul; int dx, dy; int by_ts; int smem_off; int bytes; };
 struct WnMma { int a_off, b_off; int n; int lbo_b; int tmem_col; };                  // one MMA per 16-pixel K step
-struct WnAtom { int col, width, tap, ci0; };                                        // accumulator columns -> (tap, input channels)
+struct WnAtom { int col, width, tap, ci0; };                                        // accumulator columns -> (tap [+ ts], input channels [+ N tile])
 
 struct WnParams {
     int n_boxes, n_mmas, n_atoms;
@@ -42,8 +44,8 @@ struct WnParams {
     int swz_a, swz_b;
     int stage_bytes, stage_tx, stages;
     int tiles_x, tiles_y, tiles_total; // pixel tiles of the K range (per image tiles_x * tiles_y)
-    int splits;
-    int m0, co;                        // first output channel of this launch's M tile; valid rows = co - m0
+    int splits, tapsets, n_tiles, ci_tile, tap_by_ts;   // grid = m_tiles * n_tiles * tapsets * splits
+    int co;                            // valid accumulator rows of M tile mt: co - 128 * mt
     int ci_total, co_pad;              // dw scratch geometry [tap][ci_total][co_pad]
     float* dw;
     int tmem_cols;
@@ -69,7 +71,11 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWnStagesMax + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x;
+    int bid = blockIdx.x;
+    const int split = bid % p.splits; bid /= p.splits;
+    const int ts = bid % p.tapsets; bid /= p.tapsets;
+    const int nt = bid % p.n_tiles;
+    const int mt = bid / p.n_tiles;
     const int per = (p.tiles_total + p.splits - 1) / p.splits;
     const int t_begin = split * per, t_end = min(p.tiles_total, t_begin + per);
     const int nk = max(0, t_end - t_begin);
@@ -106,7 +112,10 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 mbar_expect_tx(fb, (uint32_t)p.stage_tx);
                 for (int b = 0; b < p.n_boxes; ++b) {
                     const WnBox& bx = p.box[b];
-                    tma_load_4d(sa + bx.smem_off, bx.is_x ? &tmX : &tmG, fb, bx.c0, X0 * bx.mul + bx.dx, Y0 * bx.mul + bx.dy, img);
+                    const int c0 = bx.c0 + (bx.is_x ? nt * p.ci_tile : mt * 128);
+                    const int dx = bx.by_ts == 1 ? ts - 1 : (bx.by_ts == 2 ? (ts & 1) : bx.dx);
+                    const int dy = bx.by_ts == 2 ? (ts >> 1) : bx.dy;
+                    tma_load_4d(sa + bx.smem_off, bx.is_x ? &tmX : &tmG, fb, c0, X0 * bx.mul + dx, Y0 * bx.mul + dy, img);
                 }
             }
             __syncwarp();
@@ -147,13 +156,14 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         // thread = accumulator row = output channel; add the partial tile to dw[tap][ci][co] (co fastest: coalesced reds)
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const bool row_ok = p.m0 + row < p.co;
+        const int m0 = mt * 128;
+        const bool row_ok = m0 + row < p.co;
         mbar_wait(smem_u32(done_bar), 0, p.err, 304);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         for (int t = 0; t < p.n_atoms; ++t) {
             const WnAtom& at = p.atom[t];
-            float* dst = p.dw + ((size_t)at.tap * p.ci_total + at.ci0) * p.co_pad + p.m0 + row;
+            float* dst = p.dw + ((size_t)(at.tap + (p.tap_by_ts ? ts : 0)) * p.ci_total + at.ci0 + nt * p.ci_tile) * p.co_pad + m0 + row;
             for (int j = 0; j < at.width; j += 16) {
                 uint32_t v[16];
                 if (p.dbg & 4) continue;
@@ -250,75 +260,69 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
     const char* e = getenv("PNNP_WG_DBG");
     const int dbg = e ? atoi(e) : 0;
 
-    for (int mt = 0; mt < m_tiles; ++mt)
-        for (int nt = 0; nt < n_tiles; ++nt)
-            for (int ts = 0; ts < tapsets; ++ts) {
-                WnParams p{};
-                p.pitch_a = pitch_a; p.pitch_b = pitch_b; p.swz_a = pitch_a; p.swz_b = pitch_b; p.lbo_a = a_box_bytes;
-                p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_total = tiles_total; p.splits = splits;
-                p.m0 = mt * 128; p.co = co; p.ci_total = ci_total; p.co_pad = co_pad; p.dw = dw; p.dbg = dbg; p.err = g_wn_err;
-                int off = 0, nb = 0;
-                // g blocks of this M tile
-                const int g_blocks = std::min(128, co - p.m0) / cw_g;
-                for (int b = 0; b < g_blocks; ++b) {
-                    WnBox& bx = p.box[nb++];
-                    bx.is_x = 0; bx.c0 = p.m0 + b * cw_g; bx.smem_off = b * a_box_bytes; bx.bytes = a_box_bytes;
-                    if (mode == 0) { bx.mul = 1; bx.dx = 0; bx.dy = 0; }
-                    else { bx.mul = 2; bx.dx = ts & 1; bx.dy = ts >> 1; }            // tap (a, b) = (ts >> 1, ts & 1): rows 2y + a, cols 2x + b
-                }
-                off = a_region;
-                int col = 0;
-                if (mode == 0 && ci <= 32) {
-                    for (int dx = 0; dx < 3; ++dx) {
-                        WnBox& bx = p.box[nb++];
-                        bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = dx - 1; bx.dy = -1; bx.smem_off = off; bx.bytes = b_box_bytes;
-                        WnMma& mm = p.mma[p.n_mmas++];
-                        mm.a_off = 0; mm.b_off = off; mm.n = 3 * ci; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = col;   // N blocks = the three dy taps
-                        for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{col + dy * ci, ci, dy * 3 + dx, ci_off};
-                        col += 3 * ci; off += b_box_bytes;
-                    }
-                } else if (mode == 0 && ci == 64) {
-                    WnBox& bx = p.box[nb++];
-                    bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = ts - 1; bx.dy = -1; bx.smem_off = off; bx.bytes = b_box_bytes;
-                    WnMma& mm = p.mma[p.n_mmas++];
-                    mm.a_off = 0; mm.b_off = off; mm.n = 192; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = 0;
-                    for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{dy * 64, 64, dy * 3 + ts, ci_off};
-                    col = 192; off += b_box_bytes;
-                } else if (mode == 0) {
-                    for (int c = 0; c < 2; ++c) {
-                        WnBox& bx = p.box[nb++];
-                        bx.is_x = 1; bx.c0 = nt * 128 + c * 64; bx.mul = 1; bx.dx = ts - 1; bx.dy = -1; bx.smem_off = off + c * b_box_bytes; bx.bytes = b_box_bytes;
-                    }
-                    for (int dy = 0; dy < 3; ++dy) {
-                        WnMma& mm = p.mma[p.n_mmas++];
-                        mm.a_off = 0; mm.b_off = off + dy * kWnTileW * pitch_b; mm.n = 128; mm.lbo_b = b_box_bytes; mm.tmem_col = dy * 128;
-                        for (int c = 0; c < 2; ++c) p.atom[p.n_atoms++] = WnAtom{dy * 128 + c * 64, 64, dy * 3 + ts, ci_off + nt * 128 + c * 64};
-                    }
-                    col = 384; off += 2 * b_box_bytes;
-                } else {
-                    const int blocks = ci_tile / cw_x;
-                    for (int c = 0; c < blocks; ++c) {
-                        WnBox& bx = p.box[nb++];
-                        bx.is_x = 1; bx.c0 = nt * ci_tile + c * cw_x; bx.mul = 1; bx.dx = 0; bx.dy = 0; bx.smem_off = off + c * b_box_bytes; bx.bytes = b_box_bytes;
-                        p.atom[p.n_atoms++] = WnAtom{c * cw_x, cw_x, ts, ci_off + nt * ci_tile + c * cw_x};
-                    }
-                    WnMma& mm = p.mma[p.n_mmas++];
-                    mm.a_off = 0; mm.b_off = off; mm.n = ci_tile; mm.lbo_b = b_box_bytes; mm.tmem_col = 0;
-                    col = ci_tile; off += blocks * b_box_bytes;
-                }
-                p.n_boxes = nb;
-                p.stage_tx = 0;
-                for (int b = 0; b < nb; ++b) p.stage_tx += p.box[b].bytes;
-                p.stage_bytes = (off + 1023) / 1024 * 1024;
-                p.stages = std::max(2, std::min(kWnStagesMax, (227 * 1024 - 2048) / p.stage_bytes));
-                int tc = 32; while (tc < col) tc <<= 1;
-                p.tmem_cols = tc;
-                const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * kWnStagesMax + 1) * 8 + 64;
-                if (smem > 227 * 1024 || tc > 512) return fail("wgrad_nhwc: shared memory / TMEM budget exceeded");
-                wgrad_nhwc_kernel<<<splits, 192, smem, st>>>(tmG, tmX, p);
-                count_launch();
-                PNNP_CUDA(cudaGetLastError());
-            }
+    WnParams p{};
+    p.pitch_a = pitch_a; p.pitch_b = pitch_b; p.swz_a = pitch_a; p.swz_b = pitch_b; p.lbo_a = a_box_bytes;
+    p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_total = tiles_total; p.splits = splits; p.tapsets = tapsets;
+    p.n_tiles = n_tiles; p.ci_tile = ci_tile; p.tap_by_ts = tapsets > 1 ? 1 : 0;
+    p.co = co; p.ci_total = ci_total; p.co_pad = co_pad; p.dw = dw; p.dbg = dbg; p.err = g_wn_err;
+    int off = 0, nb = 0, col = 0;
+    // g blocks of an M tile (first channel advances by 128 per M tile in the kernel)
+    const int g_blocks = std::min(128, co) / cw_g;
+    for (int b = 0; b < g_blocks; ++b) {
+        WnBox& bx = p.box[nb++];
+        bx.is_x = 0; bx.c0 = b * cw_g; bx.smem_off = b * a_box_bytes; bx.bytes = a_box_bytes;
+        bx.mul = mode == 0 ? 1 : 2; bx.dx = 0; bx.dy = 0; bx.by_ts = mode == 0 ? 0 : 2;      // transposed conv: rows 2y + a, cols 2x + b
+    }
+    off = a_region;
+    if (mode == 0 && ci <= 32) {                                       // all nine taps: three filter-column boxes, dy folded into N
+        for (int dx = 0; dx < 3; ++dx) {
+            WnBox& bx = p.box[nb++];
+            bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = dx - 1; bx.dy = -1; bx.by_ts = 0; bx.smem_off = off; bx.bytes = b_box_bytes;
+            WnMma& mm = p.mma[p.n_mmas++];
+            mm.a_off = 0; mm.b_off = off; mm.n = 3 * ci; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = col;
+            for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{col + dy * ci, ci, dy * 3 + dx, ci_off};
+            col += 3 * ci; off += b_box_bytes;
+        }
+    } else if (mode == 0 && ci == 64) {                                // one filter column (ts) per CTA, dy folded into N = 192
+        WnBox& bx = p.box[nb++];
+        bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = 0; bx.dy = -1; bx.by_ts = 1; bx.smem_off = off; bx.bytes = b_box_bytes;
+        WnMma& mm = p.mma[p.n_mmas++];
+        mm.a_off = 0; mm.b_off = off; mm.n = 192; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = 0;
+        for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{dy * 64, 64, dy * 3, ci_off};
+        col = 192; off += b_box_bytes;
+    } else if (mode == 0) {                                            // one filter column per CTA, 128 input channels, one MMA per dy
+        for (int c = 0; c < 2; ++c) {
+            WnBox& bx = p.box[nb++];
+            bx.is_x = 1; bx.c0 = c * 64; bx.mul = 1; bx.dx = 0; bx.dy = -1; bx.by_ts = 1; bx.smem_off = off + c * b_box_bytes; bx.bytes = b_box_bytes;
+        }
+        for (int dy = 0; dy < 3; ++dy) {
+            WnMma& mm = p.mma[p.n_mmas++];
+            mm.a_off = 0; mm.b_off = off + dy * kWnTileW * pitch_b; mm.n = 128; mm.lbo_b = b_box_bytes; mm.tmem_col = dy * 128;
+            for (int c = 0; c < 2; ++c) p.atom[p.n_atoms++] = WnAtom{dy * 128 + c * 64, 64, dy * 3, ci_off + c * 64};
+        }
+        col = 384; off += 2 * b_box_bytes;
+    } else {                                                           // transposed conv: one tap (ts) per CTA
+        const int blocks = ci_tile / cw_x;
+        for (int c = 0; c < blocks; ++c) {
+            WnBox& bx = p.box[nb++];
+            bx.is_x = 1; bx.c0 = c * cw_x; bx.mul = 1; bx.dx = 0; bx.dy = 0; bx.by_ts = 0; bx.smem_off = off + c * b_box_bytes; bx.bytes = b_box_bytes;
+            p.atom[p.n_atoms++] = WnAtom{c * cw_x, cw_x, 0, ci_off + c * cw_x};
+        }
+        WnMma& mm = p.mma[p.n_mmas++];
+        mm.a_off = 0; mm.b_off = off; mm.n = ci_tile; mm.lbo_b = b_box_bytes; mm.tmem_col = 0;
+        col = ci_tile; off += blocks * b_box_bytes;
+    }
+    p.n_boxes = nb;
+    for (int b = 0; b < nb; ++b) p.stage_tx += p.box[b].bytes;
+    p.stage_bytes = (off + 1023) / 1024 * 1024;
+    p.stages = std::max(2, std::min(kWnStagesMax, (227 * 1024 - 2048) / p.stage_bytes));
+    int tc = 32; while (tc < col) tc <<= 1;
+    p.tmem_cols = tc;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * kWnStagesMax + 1) * 8 + 64;
+    if (smem > 227 * 1024 || tc > 512) return fail("wgrad_nhwc: shared memory / TMEM budget exceeded");
+    wgrad_nhwc_kernel<<<combos * splits, 192, smem, st>>>(tmG, tmX, p);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -44,3 +44,12 @@ def reduce_metric_sums(psnr_sum, ssim_sum, count, device=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     p, s, n = t.tolist()
     return (p / n if n else 0.0), (s / n if n else 0.0), int(n)
+
+
+def allreduce_mean_(flat, world_size=None):
+    """DDP gradient reduction on one flat buffer (SURVEY §8e Train): in-place all-reduce(SUM), returns the factor
+    1 / world_size the caller folds into its optimiser step (mean of the per-rank mean losses, as DistributedDataParallel)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0

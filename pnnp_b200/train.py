@@ -6,19 +6,15 @@ Reference loop body (trainer_SID.py:93-101):  pred = net(lr); loss = F.l1_loss(p
 Here the backward pass is explicit (no autograd graph, no eager fallback):
   * data gradients of the 3x3 convs  = the SAME tcgen05 conv kernel with transposed + flipped weights;
     ConvTranspose2d data gradient    = its 2x2 stride-2 mode;
-  * weight gradients                 = the tcgen05 split-K GEMM of csrc/wgrad_tc.cu over channel-major,
-    zero-ringed copies of the gradient and the layer input (a filter tap is a pixel offset);
+  * weight gradients                 = the tcgen05 split-K GEMM of csrc/wgrad_nhwc_tc.cu straight from the NHWC tensors
+    (MN-major operands via TMA: K = pixels, zero padding = out-of-bounds fill, no transposed copies);
   * LeakyReLU', bias gradients, max-pool routing (+ skip-connection add), the 1x1 head, the L1 loss and Adam
     are the CUDA-core kernels of csrc/train_kernels.cu.
 Parameters, gradients and Adam moments live in flat fp32 buffers (one all-reduce per step under DDP);
 activations and activation gradients are NHWC bf16.
 """
-import ctypes as C
-
 import torch
-import torch.distributed as dist
-
-from . import _lib
+from . import _lib, distributed as D
 from .archs import UNetSeeInDark, _conv, _pad16, _to_nhwc16
 
 L = _lib
@@ -30,17 +26,6 @@ def _pack_conv_weight(w4):
     buf = torch.zeros((k * k, _pad16(rows), _pad16(cin)), dtype=torch.bfloat16, device=w4.device)
     buf[:, :rows, :cin] = w4.permute(2, 3, 0, 1).reshape(k * k, rows, cin).to(torch.bfloat16)
     return buf
-
-
-def padded_pitch(w):
-    """Row pitch (pixels) of the zero-ringed channel-major wgrad operands: >= w + 2 and a multiple of 8 (TMA alignment)."""
-    return (w + 2 + 7) // 8 * 8
-
-
-def conv3_taps(w):
-    """(pixel offsets, x-shift planes) of the nine taps (dy, dx) of a 3x3 pad-1 conv over rows of padded_pitch(w) pixels."""
-    wp = padded_pitch(w)
-    return [(dy - 1) * wp for dy in range(3) for dx in range(3)], [dx for dy in range(3) for dx in range(3)]
 
 
 class _Scratch:
@@ -81,11 +66,28 @@ class UNetTrainStep:
             off += n
         self.scr = _Scratch(self.device)
         self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # weight-gradient scratch of every layer ([taps][ci_pad16][co] fp32, the layout the wgrad kernel adds into with
+        # coalesced reds) carved out of ONE buffer: a single memset per step
+        self.dw, total_dw = {}, 0
+        for name, m in net.named_modules():
+            if isinstance(m, torch.nn.ConvTranspose2d):
+                shape = (4, m.weight.shape[0], m.weight.shape[1])
+            elif isinstance(m, torch.nn.Conv2d) and m.kernel_size == (3, 3):
+                shape = (9, _pad16(m.weight.shape[1]), m.weight.shape[0])
+            else:
+                continue
+            self.dw[name] = (total_dw, shape)
+            total_dw += shape[0] * shape[1] * shape[2]
+        self.dw_flat = torch.zeros(total_dw, dtype=torch.float32, device=self.device)
 
     # ---------------------------------------------------------------- small wrappers over the C ABI
     def _grad_view(self, name):
         off, n, shape = self.slices[name]
         return self.flat_g[off:off + n].view(shape)
+
+    def _dw_view(self, name):
+        off, shape = self.dw[name]
+        return self.dw_flat[off:off + shape[0] * shape[1] * shape[2]].view(shape)
 
     def _stream(self):
         return _lib.stream_ptr(self.device)
@@ -95,28 +97,12 @@ class UNetTrainStep:
         L.check(L.lib().pnnp_act_bwd_bias(g.data_ptr(), _lib.ptr(out), _lib.ptr(dbias), pixels, g.shape[-1], act, self._stream()),
                 "act_bwd_bias")
 
-    def _transpose(self, name, x, c_off, c, stride=1, pa=0, pb=0, copies=1):
-        """NHWC bf16 -> channel-major [copies][c][row] over the zero-ringed (h/stride+2) x wp geometry (wp % 8 == 0)."""
-        n, h, w, cs = x.shape
-        wp = padded_pitch(w // stride)
-        ppad = n * (h // stride + 2) * wp
-        row = (ppad + 63) // 64 * 64
-        out = self.scr.get(name, (copies, c, row))
-        L.check(L.lib().pnnp_transpose_pad(x.data_ptr(), out.data_ptr(), n, h, w, cs, c_off, c, stride, pa, pb, row, wp, copies,
-                                           self._stream()), "transpose_pad")
-        return out, row, ppad
-
     def _wgrad_nhwc(self, mode, g, co, x, dw, ci_off, ci_total):
         """dw[tap][ci_off + ci][co] += the weight gradient of a 3x3 conv (mode 0) / 2x2 stride-2 transposed conv (mode 1)
         with pre-activation output gradient g and input x (both NHWC bf16), by the tcgen05 kernel of csrc/wgrad_nhwc_tc.cu."""
         n, h, w, ci = x.shape
         L.check(L.lib().pnnp_wgrad_nhwc(mode, g.data_ptr(), co, g.shape[-1], x.data_ptr(), ci, ci, n, h, w, dw.data_ptr(), ci_off,
                                         ci_total, dw.shape[-1], self._stream()), "wgrad_nhwc")
-
-    def _wgrad(self, gT, xT, row, valid, co, ci, offs, planes, dw, ci_off, ci_total, dw_elem_off=0):
-        arr, pl = (C.c_int * len(offs))(*offs), (C.c_int * len(offs))(*planes)
-        L.check(L.lib().pnnp_wgrad_tc(gT.data_ptr(), xT.data_ptr(), row, valid, co, ci, len(offs), arr, pl, xT.shape[0],
-                                      dw.data_ptr() + 4 * dw_elem_off, ci_off, ci_total, self._stream()), "wgrad_tc")
 
     # ---------------------------------------------------------------- layer backward passes
     def _conv3_bwd(self, name, g, out_act, srcs, need_dx, act=_lib.ACT_LEAKY):
@@ -127,8 +113,7 @@ class UNetTrainStep:
         n, h, w, _ = g.shape
         self._act_bwd(g, out_act, self._grad_view(name + ".bias"), act)
         ci_total = sum(s.shape[-1] for s in srcs)
-        dw = self.scr.get("dw_" + name, (9, ci_total, co), torch.float32)
-        dw.zero_()
+        dw = self._dw_view(name)
         c_off = 0
         for s in srcs:
             self._wgrad_nhwc(0, g, co, s, dw, c_off, ci_total)
@@ -154,8 +139,7 @@ class UNetTrainStep:
         ci, co = m.weight.shape[0], m.weight.shape[1]
         n, h, w, _ = x_in.shape
         self._act_bwd(g_up, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)
-        dw = self.scr.get("dw_" + name, (4, ci, co), torch.float32)
-        dw.zero_()
+        dw = self._dw_view(name)
         self._wgrad_nhwc(1, g_up, co, x_in, dw, 0, ci)
         self._grad_view(name + ".weight").copy_(dw.permute(1, 2, 0).reshape(ci, co, 2, 2))
         wd = _pack_conv_weight(m.weight.detach())            # [rows=ci][cin=co][a][b] -> [a*2+b][ci][co]
@@ -206,6 +190,7 @@ class UNetTrainStep:
         n, _, h, w = gpred.shape
         LK = _lib.ACT_LEAKY
         self.flat_g.zero_()
+        self.dw_flat.zero_()
         # 1x1 head: gradient w.r.t. conv9_2's pre-activation, dW10, db10 and conv9_2's bias gradient in one kernel
         g = self.scr.get("g_c9", (n, h, w, nf))
         m10 = net.conv10_1
@@ -243,10 +228,7 @@ class UNetTrainStep:
         L.check(L.lib().pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gpred.data_ptr(), pred.numel(), self.loss_sum.data_ptr(),
                                      self._stream()), "l1_loss")
         self.backward(gpred, saved)
-        gscale = 1.0
-        if grad_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)          # DDP: average of the per-rank mean losses
-            gscale = 1.0 / dist.get_world_size()
+        gscale = D.allreduce_mean_(self.flat_g) if grad_allreduce else 1.0   # DDP: average of the per-rank mean losses
         self.t += 1
         L.check(L.lib().pnnp_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                        self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale,

@@ -10,7 +10,8 @@ Per frame: synthetic clean frame -> fused noise synthesis at the dataset's ratio
 [reflect-pad 4 if W % 16] -> UNet / ResUnet forward (tcgen05) -> crop -> x ratio if `ori` -> clamp ->
 IlluminanceCorrect (Sony, final eval) -> PSNR / SSIM partial sums (device) -> AverageMeter.
 Across ranks: one all-reduce of [sum PSNR, sum SSIM, count] per sweep.
-Out of scope: plotting, ProcessPool rendering, real-dataset loaders, train().
+`--mode train` runs the synthetic-pair training loop (trainer_SID.py:74-180) on the explicit training step of train.py.
+Out of scope: plotting, ProcessPool rendering, real-dataset loaders.
 """
 import argparse
 import os
@@ -24,7 +25,7 @@ import yaml
 
 from . import _lib, distributed as D
 from .archs import ResUnet, UNetSeeInDark, initialize_weights  # noqa: F401  (resolved by name from YAML)
-from .datasets import Synthetic_ELD_Dataset, Synthetic_IMX686_Dataset, Synthetic_SID_Dataset  # noqa: F401
+from .datasets import Raw_Dataset, Synthetic_ELD_Dataset, Synthetic_IMX686_Dataset, Synthetic_SID_Dataset  # noqa: F401
 from .metrics import eval_partial_sums, finish_metrics
 from .noise import synthesize_batch
 from .noise_params import HALF_CLIP
@@ -197,8 +198,88 @@ class SID_Trainer(Base_Trainer):
                     pkl.dump(metrics, f)
         return {"PSNR": self.eval_psnr.avg, "SSIM": self.eval_ssim.avg, "frames": total}
 
+    # -- T1: the synthetic-pair training loop of trainer_SID.py:74-180 on the explicit B200 training step
+    def get_lr_lambda_func(self):
+        """base_trainer.py:33-43,141-162."""
+        import math
+        num_of_epochs = self.hyper['stop_epoch'] - self.hyper['last_epoch']
+        step_size, T, base = self.hyper['step_size'], self.hyper.get('T', 1), self.hyper['learning_rate']
+        period = max(1, num_of_epochs // T)
+
+        def cos_lr(step, peak=step_size, ratio=0.2):
+            t, decay, step = step // period, 2 ** (step // period), step % period
+            if step <= peak and t > 0:
+                mul = step / peak
+            else:
+                mul = (1 - ratio) * (math.cos((step - peak) / max(1, period - peak) * math.pi) * 0.5 + 0.5) + ratio
+            return base * mul / decay
+
+        def multistep_lr(step, milestone=(step_size, step_size * 9 // 5), gamma=(0.5, 0.1)):
+            step, mul = step % period, 1
+            for i in range(len(milestone), 0, -1):
+                if step > milestone[i - 1]:
+                    mul = gamma[i - 1]
+                    break
+            return base * mul
+
+        return cos_lr if 'cos' in self.hyper['lr_scheduler'].lower() else multistep_lr
+
     def train(self):
-        raise NotImplementedError("pnnp_b200: the training step (T1) is not built in this round; eval entry points only")
+        """trainer_SID.py:74-180.  Per step: `batch_size` dataset items (each `crop_per_image` noisy/clean crop pairs built on
+        the device by Raw_Dataset: P1 -> D2 -> S2 -> fused N1-N3) -> UNetTrainStep (forward, L1 on pred.clamp(0,1), explicit
+        backward, DDP gradient all-reduce, Adam).  Ranks take disjoint items of every epoch (same permutation on every rank)."""
+        from .train import UNetTrainStep
+        if not isinstance(self.net, UNetSeeInDark):
+            raise RuntimeError("pnnp_b200: the explicit training step is built for UNetSeeInDark (runfiles/*/PNNP.yml)")
+        dst_args = dict(self.args['dst_train'])
+        if dst_args.get('ori'):
+            raise RuntimeError("pnnp_b200: training with ori=True (pred * ratio inside the loss) is not built")
+        self.dst_train = globals()[dst_args['dataset']](dst_args)       # trainer_SID.py:48
+        self.change_eval_dst('eval')
+        lr_lambda = self.get_lr_lambda_func()
+        step = UNetTrainStep(self.net, lr=lr_lambda(1))
+        self.train_psnr = AverageMeter('PSNR', ':2f')
+        bs = int(self.hyper['batch_size'])
+        for epoch in range(self.hyper['last_epoch'] + 1, self.hyper['stop_epoch'] + 1):
+            self.net.train()
+            self.train_psnr.reset()
+            step.lr = lr_lambda(epoch)                                  # scheduler.step() precedes each epoch (trainer_SID.py:75,139)
+            order = np.random.RandomState(1997 + epoch).permutation(len(self.dst_train))   # DataLoader(shuffle=True)
+            batches = [order[i:i + bs] for i in range(0, len(order), bs)]
+            losses = []
+            per_rank = -(-len(batches) // self.world_size)             # every rank takes the same number of steps (the
+            for j in range(per_rank):                                   # gradient all-reduce is collective); wrap around
+                k = (self.rank * per_rank + j) % len(batches)
+                items = [self.dst_train[int(i)] for i in batches[k]]
+                imgs_lr = torch.cat([it['lr'] for it in items]).contiguous()
+                imgs_hr = torch.cat([it['hr'] for it in items]).contiguous()
+                losses.append(step.step(imgs_lr, imgs_hr))
+            if losses:
+                with torch.no_grad():                                   # PSNR of the last batch, as the progress bar shows
+                    mse = (step.scr.bufs['pred'].clamp(0, 1) - imgs_hr.clamp(0, 1)).pow(2).mean()
+                    self.train_psnr.update(float(-10.0 * torch.log10(mse)))
+            if self.rank == 0:
+                mean_loss = float(torch.stack(losses).mean()) if losses else float('nan')
+                log(f"Epoch {epoch}: lr={step.lr:.2e}, L1={mean_loss:.5f}, PSNR={self.train_psnr.avg:.2f}", log=self.logfile)
+            if epoch % self.hyper['save_freq'] == 0 and self.rank == 0:
+                epoch_id = epoch // self.hyper['plot_freq'] * self.hyper['plot_freq']
+                torch.save(_detached_state(self.net), os.path.join(self.model_dir, '%s_e%04d.pth' % (self.model_name, epoch_id)))
+            if epoch % self.hyper['plot_freq'] == 0:                    # fast eval + last-model checkpoint
+                if self.rank == 0:
+                    log(f"learning_rate: {step.lr:.3e}", log=self.logfile)
+                self.eval(epoch=epoch)
+                if self.rank == 0:
+                    torch.save(_detached_state(self.net), f'{self.fast_ckpt}/{self.model_name}_last_model.pth')
+        if self.rank == 0:
+            torch.save(_detached_state(self.net), f'{self.fast_ckpt}/{self.model_name}_last_model.pth')
+        if self.world_size > 1:
+            torch.distributed.barrier()
+        return step
+
+
+def _detached_state(net):
+    """state_dict with private storage per tensor (the training step keeps all parameters as views of one flat buffer)."""
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
 
 
 class IMX686_Trainer(SID_Trainer):

@@ -54,3 +54,42 @@ def test_metric_allreduce_gloo_world2():
 def test_single_process_is_identity():
     assert D.reduce_metric_sums(6.0, 3.0, 3) == (2.0, 1.0, 3)
     assert D.world() == (0, 1)
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # flat gradient of this rank's half of a global batch: the mean of the two equals the full-batch gradient
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    scale = D.allreduce_mean_(g)
+    out.put((rank, (g * scale).tolist()))
+    dist.destroy_process_group()
+
+
+def test_ddp_gradient_allreduce_gloo_world2():
+    """T1 under DDP (SURVEY §8e Train): one all-reduce(SUM) of the flat gradient + a 1/world factor folded into Adam."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (torch.arange(10, dtype=torch.float32) * 1.5).tolist()
+    assert all(g == want for _, g in res)
+    assert D.allreduce_mean_(torch.ones(3)) == 1.0                 # single process: untouched
+
+
+def test_training_epoch_gives_every_rank_the_same_number_of_steps():
+    """trainer.train(): ranks wrap around the epoch's batches so the collective gradient all-reduce never deadlocks."""
+    for n_batches in (1, 3, 8, 17):
+        for world in (1, 2, 4, 8):
+            per_rank = -(-n_batches // world)
+            taken = [[(r * per_rank + j) % n_batches for j in range(per_rank)] for r in range(world)]
+            assert len({len(t) for t in taken}) == 1
+            assert set(i for t in taken for i in t) == set(range(n_batches))

@@ -50,3 +50,28 @@ def test_lrid_eval_entry_point_takes_reflect_pad_branch(tmp_path, monkeypatch):
     res = T.main_lrid(["-f", runfile, "--mode", "eval"])
     assert set(res) == {f"eval_x{r}" for r in (1, 2, 4, 8, 16)}
     assert all(v["frames"] == 2 and v["PSNR"] > 0 for v in res.values())
+
+
+def test_sid_train_mode_runs_the_reference_loop_and_learns(tmp_path, monkeypatch):
+    """`--mode train` (trainer_SID.py:74-180): Raw_Dataset items built on the device -> explicit training step; the L1 loss
+    falls over a few epochs, a checkpoint with the reference's state_dict keys is written, then the eval sweeps run."""
+    from pnnp_b200 import trainer as T
+    monkeypatch.chdir(tmp_path)
+    runfile, cfg = _small_runfile(tmp_path, "runfiles/SonyA7S2/PNNP.yml", 256, 384, 1)
+    cfg["dst_train"].update(H=256, W=384, patch_size=64, crop_per_image=4, synthetic_frames=4)
+    cfg["hyper"].update(stop_epoch=6, save_freq=3, plot_freq=6, batch_size=2, learning_rate=1e-3, lr_scheduler="MultiStep",
+                        step_size=100)
+    open(runfile, "w").write(yaml.dump(cfg))
+    import numpy as np
+    import torch
+    np.random.seed(5)                  # crop positions / noise parameters come from NumPy's global state, as in the reference
+    torch.manual_seed(5)
+    tr = T.SID_Trainer(["-f", runfile, "--mode", "train"])
+    step = tr.train()
+    text = open(tmp_path / "logs" / f"log_{cfg['model_name']}.log").read()
+    l1 = [float(x) for x in re.findall(r"L1=(\d+\.\d+)", text)]
+    assert len(l1) == 6 and min(l1[3:]) < 0.9 * l1[0], l1
+    assert step.t == 6 * 2                                            # 4 items / batch 2 = 2 steps per epoch
+    assert "Epoch 6: PSNR=" in text                                   # the fast eval at plot_freq
+    sd = torch.load(os.path.join(cfg["fast_ckpt"], f"{cfg['model_name']}_last_model.pth"))
+    assert "conv1_1.weight" in sd and "upv6.weight" in sd and len(sd) == 46
