@@ -76,6 +76,12 @@ int pnnp_pack_norm_u16(const uint16_t* raw, float* out, int n, int H, int W, dou
                        const double* black4_host, int norm, int clip, void* stream);
 int pnnp_pack_norm_f32(const float* raw, float* out, int n, int H, int W, double wp,
                        const double* black4_host, int norm, int clip, void* stream);
+/* Dark-shading correction fused into P1 (data_process/real_datasets.py:360-372 -> raw2bayer): per sample
+ * v = raw - dark[y][x] [+ add_mean] [+ add_bias] in the dark map's precision (H x W float32, or float64 when
+ * dark_is_f64 — NumPy's promotion of `uint16 array - map`), cast to float32, then the normalisation above. */
+int pnnp_pack_norm_dark_u16(const uint16_t* raw, const void* dark, int dark_is_f64, float* out, int n, int H, int W, double wp,
+                            const double* black4_host, int norm, int clip, double add_mean, int use_mean,
+                            double add_bias, int use_bias, void* stream);
 
 /* P2 — bayer2raw(packed, wp, bl)                                utils/isp_ops.py:98-112
  * packed: n x 4 x h x w float32 → raw: n x 2h x 2w uint16 (truncating cast). */
@@ -175,6 +181,20 @@ int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int w, int c, 
  * The crop points / modes are host arrays (they come from the host RNG, init_random_crop_point :69-98). */
 int pnnp_crop_aug(const float* frame, float* out, int c, int h, int w, int patch, int n,
                   const int* h_start_host, const int* w_start_host, const int* mode_host, void* stream);
+
+/* HighBitRecovery.map (data_process/process.py:726-751): samples whose rounded DN value x is in [low, high) are re-drawn as
+ * dist.ppf(cdf[x - low] + U * range[x - low]) (float64, rounded to float32), the sub-DN remainder is added back, then /span
+ * (norm) or +bl.  dist = Tukey-lambda(lam) * scale + loc, or N(loc, scale).  rand: caller-supplied U (replay) or NULL for
+ * Philox4x32-10 draws keyed on (seed, offset, index0 + element); rand_out (optional) receives the U used. */
+int pnnp_hbr_map(const float* in, float* out, size_t total, const double* cdf, const double* range, int low, int high,
+                 int scale_in, int norm, float span, float bl, int dist_tukey, double lam, double loc, double scale,
+                 const double* rand, uint64_t seed, uint64_t offset, uint64_t index0, double* rand_out, void* stream);
+
+/* Overlapped tiling for tile-wise inference and its inverse — SynBase_Dataset.eval_crop / eval_merge
+ * (data_process/syn_datasets.py:109-159): frame c x h x w fp32 <-> (h/l + 1)(w/l + 1) tiles of c x patch x patch,
+ * l = patch - base, reflect padding base/2; the merge keeps each tile's interior l x l (later tiles win on overlaps). */
+int pnnp_eval_crop(const float* frame, float* tiles, int c, int h, int w, int patch, int base, void* stream);
+int pnnp_eval_merge(const float* tiles, float* frame, int c, int h, int w, int patch, int base, void* stream);
 
 /* E1 / E2 — eval boundary on the device (trainer_SID.py:231-248; IlluminanceCorrect,
  * data_process/__init__.py:162-175; tensor2im + quality_assess, utils/visualization.py:9-31).

@@ -409,6 +409,70 @@ def random_crop(img, h_start, w_start, patch, aug):
     return crops
 
 
+def eval_crop(data, patch, base=64):
+    """syn_datasets.py:109-133 — (1,c,h,w) -> (nh*nw, c, patch, patch): reflect-pad by base/2, tiles every l = patch - base,
+    the last row / column of tiles flush with the padded frame's far edge."""
+    _, c, h, w = data.shape
+    d, l = base // 2, patch - base
+    nh, nw = h // l + 1, w // l + 1
+    pad = np.pad(data, ((0, 0), (0, 0), (d, d), (d, d)), mode="reflect")
+    out = np.empty((nh, nw, c, patch, patch), dtype=data.dtype)
+    for i in range(nh - 1):
+        for j in range(nw - 1):
+            out[i, j] = pad[0, :, i * l:i * l + patch, j * l:j * l + patch]
+    for i in range(nh - 1):
+        out[i, nw - 1] = pad[0, :, i * l:i * l + patch, -patch:]
+    for j in range(nw - 1):
+        out[nh - 1, j] = pad[0, :, -patch:, j * l:j * l + patch]
+    out[nh - 1, nw - 1] = pad[0, :, -patch:, -patch:]
+    return out.reshape(-1, c, patch, patch)
+
+
+def eval_merge(tiles, h, w, base=64):
+    """syn_datasets.py:135-159 — the inverse: interior l x l of every tile, written in the reference's order."""
+    n, c, patch, _ = tiles.shape
+    d, l = base // 2, patch - base
+    nh, nw = h // l + 1, w // l + 1
+    t = tiles.reshape(nh, nw, c, patch, patch)
+    out = np.empty((1, c, h, w), dtype=tiles.dtype)
+    for i in range(nh - 1):
+        for j in range(nw - 1):
+            out[..., i * l:i * l + l, j * l:j * l + l] = t[i, j, :, d:-d, d:-d]
+    for i in range(nh - 1):
+        out[..., i * l:i * l + l, -l:] = t[i, nw - 1, :, d:-d, d:-d]
+    for j in range(nw - 1):
+        out[..., -l:, j * l:j * l + l] = t[nh - 1, j, :, d:-d, d:-d]
+    out[..., -l:, -l:] = t[nh - 1, nw - 1, :, d:-d, d:-d]
+    return out
+
+
+def darkshading_raw2bayer(lr_raw, darkshading, wp=16383, bl=512, add_mean=False, bias_draw=None, clip=False):
+    """data_process/real_datasets.py:360-372 -> raw2bayer(norm=True, clip=False): NumPy's own promotion decides the
+    precision (uint16 - float32 map -> float32; - float64 map -> float64; in-place += keeps the array dtype)."""
+    lr = lr_raw - darkshading
+    if add_mean:
+        lr = lr + darkshading.mean()
+    if bias_draw is not None:
+        lr += bias_draw
+    return raw2bayer(lr, wp=wp, bl=bl, norm=True, clip=clip)
+
+
+def hbr_map(data, lut, rand, norm=True):
+    """HighBitRecovery.map (data_process/process.py:726-751) with the uniforms passed in; `lut` is the dict HB2LB_LUT
+    returns (keys param, dist, low, high, and per integer level cdf / range)."""
+    p = lut['param']
+    if np.max(data) <= 1:
+        data = data * (p['wp'] - p['bl'])
+    data_float = data.copy()
+    data = np.round(data_float)
+    delta = data_float - data
+    for x in range(lut['low'], lut['high']):
+        keys = (data == x)
+        data[keys] = lut['dist'].ppf(lut[x]['cdf'] + rand[keys] * lut[x]['range'])
+    data = data + delta
+    return data / (p['wp'] - p['bl']) if norm else data + p['bl']
+
+
 def post_synth_clip(lr, hr, clip):
     """syn_datasets.py:339-342 / trainer_SID.py:481-485.  clip==2 (HALF_CLIP) → lower bound -inf."""
     if clip:

@@ -47,6 +47,7 @@ SIGNATURES = {
     "pnnp_launch_count": (_u64, []),
     "pnnp_pack_norm_u16": (_i, [_vp, _vp, _i, _i, _i, _d, C.POINTER(C.c_double), _i, _i, _vp]),
     "pnnp_pack_norm_f32": (_i, [_vp, _vp, _i, _i, _i, _d, C.POINTER(C.c_double), _i, _i, _vp]),
+    "pnnp_pack_norm_dark_u16": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, C.c_double, C.POINTER(C.c_double), _i, _i, C.c_double, _i, C.c_double, _i, _vp]),
     "pnnp_unpack_quant": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "pnnp_noise_synth": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _f, _u64, _u64, _u64, _vp]),
     "pnnp_noise_synth_debug": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _i, _i, _i, _f, _f, _u64, _u64, _u64,
@@ -66,6 +67,9 @@ SIGNATURES = {
     "pnnp_wgrad_nhwc_pipeline_error": (_i, []),
     "pnnp_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, _i, _f, _vp]),
     "pnnp_crop_aug": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]),
+    "pnnp_hbr_map": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _d, _d, _d, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "pnnp_eval_crop": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pnnp_eval_merge": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pnnp_eval_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
 }
 

@@ -2,7 +2,8 @@
 
 `init_random_crop_point` reproduces the reference's draw order on NumPy's global RandomState
 (aug modes first, then per crop h_start, w_start), so the same seed gives the same crops;
-`random_crop` runs the gather kernel (csrc/crop_aug.cu)."""
+`random_crop` runs the gather kernel (csrc/crop_aug.cu).  `eval_crop` / `eval_merge` are the overlapped tiling of a full frame
+for tile-wise inference and its inverse (syn_datasets.py:109-159)."""
 import ctypes as C
 
 import numpy as np
@@ -54,4 +55,42 @@ def random_crop(img, h_start, w_start, aug, patch_size):
             modes = [int(aug[i]) if i < k else 0 for i in range(s, s + m)]
             _lib.check(L.pnnp_crop_aug(img.data_ptr(), out[s:].data_ptr(), c, h, w, patch_size, m, arr(h_start), arr(w_start),
                                        (C.c_int * m)(*modes), _lib.stream_ptr(img.device)), "crop_aug")
+    return out
+
+
+def tile_grid(h, w, patch_size, base=64):
+    """(nh, nw) of SynBase_Dataset.eval_crop (syn_datasets.py:112-115)."""
+    l = patch_size - base
+    return h // l + 1, w // l + 1
+
+
+def eval_crop(data, patch_size, base=64):
+    """syn_datasets.py:109-133: data CUDA fp32 (1,c,h,w) or (c,h,w) -> (nh*nw, c, patch, patch) overlapped tiles of the
+    reflect-padded frame."""
+    _lib.require_cuda(data, "data")
+    x = data.float().contiguous()
+    if x.dim() == 4:
+        if x.shape[0] != 1:
+            raise RuntimeError("eval_crop: one frame at a time (the reference's data has batch 1)")
+        x = x[0]
+    c, h, w = x.shape
+    nh, nw = tile_grid(h, w, patch_size, base)
+    out = torch.empty((nh * nw, c, patch_size, patch_size), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pnnp_eval_crop(x.data_ptr(), out.data_ptr(), c, h, w, patch_size, base, _lib.stream_ptr(x.device)),
+                   "eval_crop")
+    return out
+
+
+def eval_merge(croped_data, h, w, base=64):
+    """syn_datasets.py:135-159: (nh*nw, c, patch, patch) tiles -> (1, c, h, w): the interior of every tile, later tiles winning."""
+    _lib.require_cuda(croped_data, "croped_data")
+    t = croped_data.float().contiguous()
+    n, c, p, _ = t.shape
+    nh, nw = tile_grid(h, w, p, base)
+    if n != nh * nw:
+        raise RuntimeError(f"eval_merge: {n} tiles for a {nh} x {nw} grid")
+    out = torch.empty((1, c, h, w), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().pnnp_eval_merge(t.data_ptr(), out.data_ptr(), c, h, w, p, base, _lib.stream_ptr(t.device)), "eval_merge")
     return out

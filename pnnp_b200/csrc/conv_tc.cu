@@ -92,7 +92,11 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int TPS, int K16S>
+// EPI: compile-time specialisation of the epilogue.  -1 = generic (every feature decided at run time).  >= 0 = the hot NHWC-output
+// 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
+// the narrow full-resolution layers are bound by the epilogue's instruction count, and most of it was run-time feature tests.
+constexpr int EPI_GENERIC = -1, EPI_X = 1, EPI_POOL = 2, EPI_HEAD = 4;
+template <int TPS, int K16S, int EPI>
 __global__ void __launch_bounds__(kConvThreadsMax, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
@@ -244,14 +248,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int ty_in = m / kTileW, tx_in = m % kTileW;
         const uint32_t acc = (uint32_t)group;
         uint32_t acc_phase = 0;
-        const int chunks16 = (p.mode == MODE_CONV3X ? p.cout : p.umma_n) / 16;
+        constexpr bool kSpec = EPI >= 0;
+        const bool xmode = kSpec ? (EPI & EPI_X) != 0 : p.mode == MODE_CONV3X;
+        const bool is_convt = kSpec ? false : p.mode == MODE_CONVT;
+        const bool out_nhwc = kSpec ? true : p.out_mode == OUT_NHWC_BF16;
+        const bool has_resid = kSpec ? false : p.resid != nullptr;
+        const bool has_pool = kSpec ? (EPI & EPI_POOL) != 0 : p.pool_out != nullptr;
+        const bool has_head = kSpec ? (EPI & EPI_HEAD) != 0 : p.head_out != nullptr;
+        // activation as max(v, v * slope + 0): LeakyReLU 0.2 / ReLU (slope 0; the +0 turns -0 into +0) / identity (slope 1)
+        const float slope = p.act == ACT_LEAKY ? 0.2f : (p.act == ACT_RELU ? 0.f : 1.f);
+        const int chunks16 = (xmode ? p.cout : p.umma_n) / 16;
         for (int t = blockIdx.x + group * gridDim.x; t < total_tiles; t += p.groups * gridDim.x) {
             int r = t;
             const int n_tile = r % p.n_tiles; r /= p.n_tiles;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
             const int ty = r % p.tiles_y; r /= p.tiles_y;
             const int img = r;
-            const bool xmode = p.mode == MODE_CONV3X;
             const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTileW + tx_in, y = ty * kTileH + ty_in;
             const bool valid = x < p.W && y < p.H && (!xmode || (tx_in >= 1 && tx_in <= kTileWX));
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
@@ -281,17 +293,33 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
                 int c0 = col_tile0 + j * 16;              // output channel of v[0]
                 size_t opix = pix_in;
-                if (p.mode == MODE_CONVT) {               // GEMM column = (a*2+b)*cout + co  ->  pixel (2y+a, 2x+b)
+                if (is_convt) {                           // GEMM column = (a*2+b)*cout + co  ->  pixel (2y+a, 2x+b)
                     const int tap = c0 / p.cout;
                     c0 -= tap * p.cout;
                     opix = ((size_t)img * (2 * p.H) + (2 * y + (tap >> 1))) * (size_t)(2 * p.W) + (2 * x + (tap & 1));
                 }
                 if (c0 >= p.cout) continue;               // zero-padded weight rows (warp-uniform)
                 float f[16];
+                if (out_nhwc) {                           // cout % 16 == 0: the chunk's 16 biases are four aligned float4
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = apply_act(__uint_as_float(v[i]) + s_bias[min(c0 + i, p.cout - 1)], p.act);
-                if (p.out_mode == OUT_NHWC_BF16) {
-                    if (p.resid && valid) {
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i4);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float a = __uint_as_float(v[4 * i4 + i]) + bb[i];
+                            f[4 * i4 + i] = fmaxf(a, fmaf(a, slope, 0.0f));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float a = __uint_as_float(v[i]) + s_bias[min(c0 + i, p.cout - 1)];
+                        f[i] = fmaxf(a, fmaf(a, slope, 0.0f));
+                    }
+                }
+                if (out_nhwc) {
+                    if (has_resid && valid) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.resid + opix * p.cout_stride + c0);
                         const uint4 r0 = rp[0], r1 = rp[1];
                         const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -312,7 +340,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
-                    if (p.pool_out) {
+                    if (has_pool) {
                         // fused nn.MaxPool2d(2): lanes l^1 hold the x-neighbour, l^16 the y-neighbour of the same tile
                         // (a warp owns two 16-pixel tile rows); max of bf16-rounded values == rounding of the max
 #pragma unroll
@@ -332,7 +360,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
                     }
-                    if (p.head_out) {
+                    if (has_head) {
                         // fused 1x1 head (conv10_1, Unet.py:93): 4 dot products over this pixel's channels, fp32
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -353,7 +381,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     }
                 }
             }
-            if (p.head_out && valid) {
+            if (has_head && valid) {
                 const size_t plane = (size_t)p.H * p.W;
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
@@ -575,16 +603,24 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     const size_t smem = (size_t)stages * stage_bytes + b_res_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 2 * kMaxGroups + 2) * 8 + 16 + (size_t)cout * 4 * 5 + 64;
     if (smem > 227 * 1024) return fail("conv: shared memory budget exceeded");
     static bool attr_done = false;
-#define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1) X(3, 2) X(3, 4) X(1, 1) X(1, 2) X(1, 4)
+    // (taps per stage, K16 slices, epilogue specialisation); specialised epilogues exist for the 3-taps-per-stage shapes
+#define PNNP_SPEC_EPI(X, T, K) X(T, K, 0) X(T, K, 1) X(T, K, 2) X(T, K, 3) X(T, K, 4) X(T, K, 5)
+#define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1, -1) X(3, 2, -1) X(3, 4, -1) X(1, 1, -1) X(1, 2, -1) X(1, 4, -1) \
+    PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4)
     if (!attr_done) {
-#define X(T, K) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
         attr_done = true;
     }
     const int k16s = kc / 16;
+    int epi = EPI_GENERIC;
+    static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
+    if (!no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && tps == 3 && !p.dbg &&
+        !(d.pool_out && d.head_out))
+        epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0);
     bool launched = false;
-#define X(T, K) if (!launched && tps == T && k16s == K) { conv_gemm_tc_kernel<T, K><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
+#define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { conv_gemm_tc_kernel<T, K, E><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
     PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
     if (!launched) return fail("conv: no kernel variant for this (taps per stage, K chunk)");

@@ -2,6 +2,7 @@
 // (data_process/syn_datasets.py:69-107,162-173): crop = img[:, hs:hs+p, ws:ws+p];
 // rot90 by (mode % 4) on the (H, W) axes (numpy.rot90, counter-clockwise), then a W-flip if mode // 4.
 // A pure gather: one float4 of output per thread, source index computed per element.
+#include <algorithm>
 #include "abi_common.h"
 #include "../../include/pnnp_b200.h"
 
@@ -44,9 +45,85 @@ __global__ void __launch_bounds__(256) crop_aug_kernel(const CropArgs a) {
         *reinterpret_cast<float4*>(a.out + (((size_t)k * a.c + ch) * p + i) * p + 4 * j4) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Overlapped tiling of a frame for tile-wise inference and its inverse
+// (SynBase_Dataset.eval_crop / eval_merge, data_process/syn_datasets.py:109-159; caller trainer_SID.py:345-360).
+// d = base/2, l = patch - base, nh = h/l + 1, nw = w/l + 1.  The frame is reflect-padded by d; tile (i, j) starts at
+// (i*l, j*l) of the padded frame, the last row / column of tiles at (H_pad - patch) / (W_pad - patch).  The merge keeps the
+// interior l x l of every tile; where regions overlap the reference's later writes win (right column, bottom row, corner).
+// ------------------------------------------------------------------------------------------
+struct TileGeom { int c, h, w, patch, d, l, nh, nw; };
+__device__ __forceinline__ int reflect_idx(int t, int n) { t = t < 0 ? -t : t; return t >= n ? 2 * (n - 1) - t : t; }
+
+__global__ void __launch_bounds__(256) eval_crop_kernel(const float* __restrict__ frame, float* __restrict__ tiles, const TileGeom g) {
+    const int p = g.patch, p4 = p / 4;
+    const size_t total = (size_t)g.nh * g.nw * g.c * p * p4;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int x4 = (int)(t % p4);
+        size_t r = t / p4;
+        const int y = (int)(r % p); r /= p;
+        const int ch = (int)(r % g.c); r /= g.c;
+        const int j = (int)(r % g.nw), i = (int)(r / g.nw);
+        const int oy = i < g.nh - 1 ? i * g.l : g.h + 2 * g.d - p;       // tile origin in the padded frame
+        const int ox = j < g.nw - 1 ? j * g.l : g.w + 2 * g.d - p;
+        const float* row = frame + ((size_t)ch * g.h + reflect_idx(oy + y - g.d, g.h)) * g.w;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = __ldg(row + reflect_idx(ox + 4 * x4 + e - g.d, g.w));
+        *reinterpret_cast<float4*>(tiles + ((((size_t)i * g.nw + j) * g.c + ch) * p + y) * p + 4 * x4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) eval_merge_kernel(const float* __restrict__ tiles, float* __restrict__ frame, const TileGeom g) {
+    const int p = g.patch;
+    const size_t total = (size_t)g.c * g.h * g.w;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % g.w);
+        size_t r = t / g.w;
+        const int y = (int)(r % g.h);
+        const int ch = (int)(r / g.h);
+        int i, ty, j, tx;
+        if (y >= g.h - g.l) { i = g.nh - 1; ty = y - (g.h - g.l) + g.d; } else { i = y / g.l; ty = y - i * g.l + g.d; }
+        if (x >= g.w - g.l) { j = g.nw - 1; tx = x - (g.w - g.l) + g.d; } else { j = x / g.l; tx = x - j * g.l + g.d; }
+        frame[t] = __ldg(tiles + ((((size_t)i * g.nw + j) * g.c + ch) * p + ty) * p + tx);
+    }
+}
+
+static int tile_geom(TileGeom& g, int c, int h, int w, int patch, int base) {
+    if (c < 1 || base < 0 || (base & 1) || patch <= base || (patch & 3)) return fail("eval tiling: patch must be a multiple of 4 and > base (even)");
+    g.c = c; g.h = h; g.w = w; g.patch = patch; g.d = base / 2; g.l = patch - base;
+    g.nh = h / g.l + 1; g.nw = w / g.l + 1;
+    if (h + base < patch || w + base < patch) return fail("eval tiling: the padded frame is smaller than one tile");
+    if (g.d >= h || g.d >= w) return fail("eval tiling: reflect padding needs base/2 < h, w");
+    return 0;
+}
 }  // namespace pnnp
 
 using namespace pnnp;
+
+extern "C" int pnnp_eval_crop(const float* frame, float* tiles, int c, int h, int w, int patch, int base, void* stream) {
+    if (!frame || !tiles) return fail("eval_crop: null pointer");
+    TileGeom g;
+    if (int e = tile_geom(g, c, h, w, patch, base)) return e;
+    const size_t total = (size_t)g.nh * g.nw * c * patch * (patch / 4);
+    eval_crop_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(frame, tiles, g);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_eval_merge(const float* tiles, float* frame, int c, int h, int w, int patch, int base, void* stream) {
+    if (!frame || !tiles) return fail("eval_merge: null pointer");
+    TileGeom g;
+    if (int e = tile_geom(g, c, h, w, patch, base)) return e;
+    if (h < g.l || w < g.l) return fail("eval_merge: frame smaller than one tile interior");
+    const size_t total = (size_t)c * h * w;
+    eval_merge_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(tiles, frame, g);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int pnnp_crop_aug(const float* frame, float* out, int c, int h, int w, int patch, int n,
                              const int* h_start_host, const int* w_start_host, const int* mode_host, void* stream) {

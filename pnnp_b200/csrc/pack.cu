@@ -150,6 +150,45 @@ static int grid_for(size_t work_items) {
     return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)sms * 8));
 }
 
+// ------------------------------------------------------------------------------------------
+// Dark-shading correction fused into the pack (the real-data side of the same boundary:
+// data_process/real_datasets.py:360-372 feeding raw2bayer): per sensor sample
+//     v = raw - darkshading[y][x]  [+ mean(darkshading) if 'd' in noise_code]  [+ randn * biassig ('darkshading2', train)]
+// in the dark map's precision — float32 arithmetic for a float32 map, float64 for a float64 map (what NumPy's
+// promotion makes of `uint16 array - map`; `ds_k * iso + ds_b + BLE` is float64 when BLE is an np.float64) — then the
+// cast to float32 and the normalisation of raw2bayer.  One element per thread of the packed output.
+// ------------------------------------------------------------------------------------------
+template <typename D>
+__global__ void __launch_bounds__(256) pack_norm_dark_kernel(const uint16_t* __restrict__ raw, const D* __restrict__ dark, float* __restrict__ out,
+                                                             int n, int H, int W, double wp, double b0, double b1, double b2, double b3,
+                                                             int norm, int clip, D add_mean, int use_mean, D add_bias, int use_bias) {
+    const int h = H / 2, w = W / 2;
+    const size_t plane = (size_t)h * w, total = (size_t)n * 4 * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w);
+        size_t t = i / w;
+        const int y = (int)(t % h); t /= h;
+        const int c = (int)(t % 4);
+        const int f = (int)(t / 4);
+        const int dy = (c >= 2), dx = (c == 1 || c == 2);
+        const size_t pix = (size_t)(2 * y + dy) * W + 2 * x + dx;
+        float v32;
+        if (sizeof(D) == 8) {
+            double v = __dsub_rn((double)raw[(size_t)f * H * W + pix], (double)dark[pix]);
+            if (use_mean) v = __dadd_rn(v, (double)add_mean);
+            if (use_bias) v = __dadd_rn(v, (double)add_bias);
+            v32 = (float)v;
+        } else {
+            float v = __fsub_rn((float)raw[(size_t)f * H * W + pix], (float)dark[pix]);
+            if (use_mean) v = __fadd_rn(v, (float)add_mean);
+            if (use_bias) v = __fadd_rn(v, (float)add_bias);
+            v32 = v;
+        }
+        const double black = c == 0 ? b0 : (c == 1 ? b1 : (c == 2 ? b2 : b3));
+        out[i] = norm_one(v32, black, wp, norm, clip);
+    }
+}
+
 template <typename T>
 static int pack_impl(const T* raw, float* out, int n, int H, int W, double wp, const double* black4, int norm,
                      int clip, void* stream) {
@@ -178,6 +217,24 @@ extern "C" int pnnp_pack_norm_u16(const uint16_t* raw, float* out, int n, int H,
 extern "C" int pnnp_pack_norm_f32(const float* raw, float* out, int n, int H, int W, double wp,
                                   const double* black4_host, int norm, int clip, void* stream) {
     return pack_impl<float>(raw, out, n, H, W, wp, black4_host, norm, clip, stream);
+}
+extern "C" int pnnp_pack_norm_dark_u16(const uint16_t* raw, const void* dark, int dark_is_f64, float* out, int n, int H, int W, double wp,
+                                       const double* black4_host, int norm, int clip, double add_mean, int use_mean,
+                                       double add_bias, int use_bias, void* stream) {
+    if (!raw || !dark || !out || !black4_host) return fail("pack_norm_dark: null pointer");
+    if (n <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return fail("pack_norm_dark: H and W must be positive and even");
+    const int blocks = grid_for((size_t)n * H * W);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* b = black4_host;
+    if (dark_is_f64)
+        pack_norm_dark_kernel<double><<<blocks, 256, 0, st>>>(raw, static_cast<const double*>(dark), out, n, H, W, wp, b[0], b[1], b[2], b[3],
+                                                              norm, clip, add_mean, use_mean, add_bias, use_bias);
+    else
+        pack_norm_dark_kernel<float><<<blocks, 256, 0, st>>>(raw, static_cast<const float*>(dark), out, n, H, W, wp, b[0], b[1], b[2], b[3],
+                                                             norm, clip, (float)add_mean, use_mean, (float)add_bias, use_bias);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
 }
 extern "C" int pnnp_unpack_quant(const float* packed, uint16_t* raw, int n, int h, int w, float wp, float bl,
                                  void* stream) {

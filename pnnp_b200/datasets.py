@@ -36,6 +36,16 @@ class _SyntheticEvalBase(torch.utils.data.Dataset):
     def __len__(self):
         return self.length
 
+    def eval_crop(self, data, base=64):
+        """SynBase_Dataset.eval_crop (syn_datasets.py:109-133): overlapped `patch_size` tiles of a (1,c,h,w) CUDA frame."""
+        from . import crops
+        return crops.eval_crop(data, self.args["patch_size"], base)
+
+    def eval_merge(self, croped_data, base=64):
+        """SynBase_Dataset.eval_merge (syn_datasets.py:135-159)."""
+        from . import crops
+        return crops.eval_merge(croped_data, self.h, self.w, base)
+
     def clean_frame(self, scene):
         g = torch.Generator().manual_seed(1997 + scene)
         return torch.rand((self.c, self.h, self.w), generator=g) ** 2

@@ -198,6 +198,23 @@ class SID_Trainer(Base_Trainer):
                     pkl.dump(metrics, f)
         return {"PSNR": self.eval_psnr.avg, "SSIM": self.eval_ssim.avg, "frames": total}
 
+    def predict(self, raw, name='ds', tile_batch=8):
+        """trainer_SID.py:345-360: tile-wise inference of a full RAW frame — raw2bayer(raw + bl) (the reference passes no
+        wp / bl here, i.e. raw2bayer's defaults) -> eval_crop (overlapped tiles) -> network per tile -> eval_merge ->
+        `<name>.npy`.  Returns the merged (c, h, w) array."""
+        from .isp_ops import raw2bayer
+        self.net.eval()
+        if not hasattr(self, 'dst_eval'):
+            self.change_eval_dst('eval')
+        raw = torch.as_tensor(np.asarray(raw)).to(self.device)
+        img_lr = raw2bayer((raw.float() + self.dst["bl"]).contiguous())[None]
+        with torch.no_grad():
+            tiles = self.dst_eval.eval_crop(img_lr)
+            outs = [self.net(tiles[s:s + tile_batch].contiguous()) for s in range(0, tiles.shape[0], tile_batch)]
+            img_dn = self.dst_eval.eval_merge(torch.cat(outs))[0].cpu().numpy()
+        np.save(f'{name}.npy', img_dn)
+        return img_dn
+
     # -- T1: the synthetic-pair training loop of trainer_SID.py:74-180 on the explicit B200 training step
     def get_lr_lambda_func(self):
         """base_trainer.py:33-43,141-162."""

@@ -61,3 +61,29 @@ def test_raw_dataset_item_on_device():
     np.random.seed(11)
     hs, ws, aug = crops.init_random_crop_point(256, 384, 128, 8, cfg["croptype"])
     assert item["hr"].cpu().numpy().tobytes() == O.random_crop(packed, hs, ws, 128, aug).tobytes()
+
+
+def test_eval_crop_and_merge_match_reference_goldens(golden):
+    """Overlapped tiling for tile-wise inference (syn_datasets.py:109-159): bit-exact vs the reference's own output."""
+    g = golden("tiling")
+    k = 0
+    while f"case{k}_geom" in g:
+        c, h, w, patch, base = (int(v) for v in g[f"case{k}_geom"])
+        x = torch.from_numpy(g[f"case{k}_x"]).cuda()
+        tiles = crops.eval_crop(x, patch, base)
+        assert tiles.cpu().numpy().tobytes() == g[f"case{k}_tiles"].tobytes()
+        marked = tiles + torch.arange(tiles.shape[0], dtype=torch.float32, device="cuda").view(-1, 1, 1, 1)
+        assert crops.eval_merge(marked, h, w, base).cpu().numpy().tobytes() == g[f"case{k}_merged"].tobytes()
+        k += 1
+    assert k == 5
+
+
+def test_eval_tiling_round_trip_at_frame_size():
+    """4x1424x2128 Sony frame, 512 tiles with 64 overlap: crop -> merge is the identity; the tile grid is the reference's."""
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand((1, 4, 1424, 2128), device="cuda", generator=gen)
+    tiles = crops.eval_crop(x, 512, 64)
+    assert tiles.shape == (4 * 5, 4, 512, 512) and crops.tile_grid(1424, 2128, 512, 64) == (4, 5)
+    assert torch.equal(crops.eval_merge(tiles, 1424, 2128, 64), x)
+    assert torch.equal(tiles[0, :, 32:, 32:], x[0, :, :480, :480])            # first tile = reflect-padded top-left corner
+    assert torch.equal(tiles[0, :, 0, 32:], x[0, :, 32, :480])                # reflect (no edge repeat): padded row -32 = row 32

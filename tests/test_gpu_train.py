@@ -188,10 +188,10 @@ def test_head_backward():
     assert _rel(dbp, want.sum((0, 2, 3))) < 1e-2
 
 
-def _reference_step(sd, lr_in, hr, steps=1):
+def _reference_step(sd, lr_in, hr, steps=1, lr=1e-4):
     """fp32 torch restatement of trainer_SID.py:93-101 on the oracle's functional UNet."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    opt = torch.optim.Adam(list(params.values()), lr=lr)
     losses, grads = [], None
     for _ in range(steps):
         opt.zero_grad()
@@ -347,17 +347,22 @@ def test_backward_is_exact_layer_by_layer_on_a_real_step():
 
 
 def test_training_reduces_loss_like_the_reference_loop():
+    """Ten Adam steps (lr 1e-3) on fixed crops: the loss curve follows the fp32 reference loop and the parameters move with it."""
     net, lr_in, hr = _make(n=2, h=64, w=64, seed=5)
+    net.conv10_1.bias.data.fill_(0.05)       # all four outputs start inside the clamp (a negative bias means zero gradient)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    ref_losses, _, ref_params = _reference_step(sd, lr_in, hr, steps=8)
-    ts = train.UNetTrainStep(net)
-    losses = [ts.step(lr_in, hr).item() for _ in range(8)]
+    ref_losses, _, ref_params = _reference_step(sd, lr_in, hr, steps=10, lr=1e-3)
+    ts = train.UNetTrainStep(net, lr=1e-3)
+    losses = [ts.step(lr_in, hr).item() for _ in range(10)]
     _ok()
-    assert losses[-1] < losses[0]
-    assert np.allclose(losses, ref_losses, rtol=2e-2, atol=2e-3), (losses, ref_losses)
-    # Adam's first steps move every weight by ~lr regardless of gradient scale: parameters must track the fp32 loop
-    for k, v in net.state_dict().items():
-        assert (v - ref_params[k]).abs().max().item() < 8 * 1e-4 + 1e-6, k
+    assert losses[-1] < 0.97 * losses[0] and ref_losses[-1] < 0.97 * ref_losses[0], (losses, ref_losses)
+    assert np.allclose(losses, ref_losses, rtol=3e-2, atol=2e-3), (losses, ref_losses)
+    moved = max((v - sd[k]).abs().max().item() for k, v in net.state_dict().items())
+    assert 5e-3 < moved < 1.5e-2                                   # ~ steps * lr, as Adam's first steps do
+    # sign-like early Adam steps: weights whose tiny gradient flips sign between bf16 and fp32 drift apart by 2 lr per step, so
+    # the bound is on the bulk: 99 % of all parameters within 20 % of the distance travelled
+    diff = torch.cat([(v - ref_params[k]).abs().flatten() for k, v in net.state_dict().items()])
+    assert torch.quantile(diff[::7].float(), 0.99).item() < 0.2 * moved, torch.quantile(diff[::7].float(), 0.99).item()
     # the inference forward sees the updated weights (pack cache invalidated)
     with torch.no_grad():
         out = net.eval()(lr_in)

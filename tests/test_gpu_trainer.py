@@ -67,6 +67,9 @@ def test_sid_train_mode_runs_the_reference_loop_and_learns(tmp_path, monkeypatch
     np.random.seed(5)                  # crop positions / noise parameters come from NumPy's global state, as in the reference
     torch.manual_seed(5)
     tr = T.SID_Trainer(["-f", runfile, "--mode", "train"])
+    # The reference's loss clamps BEFORE the L1 (losses/base_loss.py:92-103): an output channel whose N(0, 0.02) bias starts
+    # negative predicts < 0 everywhere and gets zero gradient.  Start all four channels alive so the loss can move.
+    tr.net.conv10_1.bias.data.fill_(0.05)
     step = tr.train()
     text = open(tmp_path / "logs" / f"log_{cfg['model_name']}.log").read()
     l1 = [float(x) for x in re.findall(r"L1=(\d+\.\d+)", text)]
@@ -75,3 +78,30 @@ def test_sid_train_mode_runs_the_reference_loop_and_learns(tmp_path, monkeypatch
     assert "Epoch 6: PSNR=" in text                                   # the fast eval at plot_freq
     sd = torch.load(os.path.join(cfg["fast_ckpt"], f"{cfg['model_name']}_last_model.pth"))
     assert "conv1_1.weight" in sd and "upv6.weight" in sd and len(sd) == 46
+
+
+def test_predict_tiles_a_full_frame_like_the_reference(tmp_path, monkeypatch):
+    """trainer_SID.py:345-360: raw2bayer(raw + bl) -> eval_crop -> net per tile -> eval_merge -> <name>.npy."""
+    import numpy as np
+    import torch
+    import pnnp_b200 as P
+    from pnnp_b200 import trainer as T
+    monkeypatch.chdir(tmp_path)
+    runfile, cfg = _small_runfile(tmp_path, "runfiles/SonyA7S2/PNNP.yml", 256, 384, 1)
+    for k in ("dst", "dst_train", "dst_eval", "dst_test"):
+        cfg[k]["patch_size"] = 96                      # l = 96 - 64 = 32: a 5 x 7 grid of overlapped tiles on the 128 x 192 frame
+    open(runfile, "w").write(yaml.dump(cfg))
+    tr = T.SID_Trainer(["-f", runfile, "--mode", "evaltest"])
+    raw = np.random.RandomState(0).randint(0, 900, size=(256, 384)).astype(np.float32)
+    want_in = P.raw2bayer(torch.from_numpy(raw + cfg["dst_eval"]["bl"]).cuda())            # reference defaults wp=1023, bl=64
+    net = tr.net
+    tr.net = type("Identity", (), {"eval": lambda self: self, "__call__": lambda self, x: x})()
+    out = tr.predict(raw, name=str(tmp_path / "ident"))
+    assert out.shape == (4, 128, 192) and np.array_equal(out, want_in.reshape(4, 128, 192).cpu().numpy())   # crop -> merge = identity
+    assert np.array_equal(np.load(tmp_path / "ident.npy"), out)
+    tr.net = net
+    dn = tr.predict(raw, name=str(tmp_path / "dn"))
+    tiles = tr.dst_eval.eval_crop(want_in.reshape(1, 4, 128, 192))
+    with torch.no_grad():
+        ref = tr.dst_eval.eval_merge(net.eval()(tiles))[0].cpu().numpy()
+    assert np.array_equal(dn, ref) and np.isfinite(dn).all()

@@ -141,3 +141,18 @@ def test_psnr_ssim_sanity():
     assert O.ssim(a, a) == pytest.approx(1.0, abs=1e-12)
     b = a + 1.0
     assert O.psnr(a, b) == pytest.approx(10 * np.log10(255 ** 2 / 1.0), abs=1e-4)   # float32 inputs: a+1 is inexact
+
+
+def test_eval_tiling_oracle_matches_reference_goldens(golden):
+    """SynBase_Dataset.eval_crop / eval_merge (syn_datasets.py:109-159) — bit-exact data movement."""
+    g = golden("tiling")
+    k = 0
+    while f"case{k}_geom" in g:
+        c, h, w, patch, base = (int(v) for v in g[f"case{k}_geom"])
+        x, tiles = g[f"case{k}_x"], g[f"case{k}_tiles"]
+        assert np.array_equal(O.eval_crop(x, patch, base), tiles)
+        marked = tiles + np.arange(tiles.shape[0], dtype=np.float32).reshape(-1, 1, 1, 1)
+        assert np.array_equal(O.eval_merge(marked, h, w, base), g[f"case{k}_merged"])
+        assert np.array_equal(O.eval_merge(tiles, h, w, base), x)            # round trip = identity
+        k += 1
+    assert k == 5
