@@ -230,6 +230,15 @@ int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void*
 int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, const void* x, int ci, int ci_stride, int n, int h, int w,
                     float* dw, int ci_off, int ci_total, int co_pad, void* stream);
 int pnnp_wgrad_nhwc_pipeline_error(void);
+/* Batched strided copy / cast: desc i copies dim[0] x dim[1] x dim[2] x dim[3] fp32 elements src[sum idx*sstride] ->
+ * dst[sum idx*dstride] (fp32, or bf16 when dst_bf16).  Strides in elements, may be negative (src / dst point at index 0).
+ * One launch for all descriptors (device array): weight packing for the tensor-core layouts and gradient re-layout. */
+typedef struct pnnp_copy_desc {
+    const void* src; void* dst;
+    int dst_bf16; int dim[4];
+    long long sstride[4]; long long dstride[4];
+} pnnp_copy_desc;
+int pnnp_strided_copy_batch(const pnnp_copy_desc* descs_dev, int n_desc, int blocks_per_desc, void* stream);
 /* torch.optim.Adam step (no weight decay) over flat fp32 buffers; g is multiplied by gscale first */
 int pnnp_adam_step(float* p, const float* g, float* m, float* v, size_t total, float lr, float b1, float b2, float eps,
                    int step, float gscale, void* stream);

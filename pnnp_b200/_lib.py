@@ -65,6 +65,7 @@ SIGNATURES = {
     "pnnp_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "pnnp_wgrad_nhwc": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "pnnp_wgrad_nhwc_pipeline_error": (_i, []),
+    "pnnp_strided_copy_batch": (_i, [_vp, _i, _i, _vp]),
     "pnnp_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, _i, _f, _vp]),
     "pnnp_crop_aug": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]),
     "pnnp_hbr_map": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _d, _d, _d, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp]),
@@ -72,6 +73,12 @@ SIGNATURES = {
     "pnnp_eval_merge": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pnnp_eval_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
 }
+
+class CopyDesc(C.Structure):
+    """pnnp_copy_desc (include/pnnp_b200.h)."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_bf16", C.c_int), ("dim", C.c_int * 4),
+                ("sstride", C.c_longlong * 4), ("dstride", C.c_longlong * 4)]
+
 
 CONV3, CONV1, CONVT, CONV3S2, CONV3X, CONV2S2 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2

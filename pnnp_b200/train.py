@@ -28,6 +28,32 @@ def _pack_conv_weight(w4):
     return buf
 
 
+class _StaticPacked:
+    """Entry of the network's pack cache whose bf16 buffer is refreshed by the step's batched pack launch instead of being
+    rebuilt with framework ops; a framework-side in-place change of the weight (load_state_dict) triggers a refresh."""
+
+    def __init__(self, owner, module, weight_buf):
+        self.owner, self.module, self.weight = owner, module, weight_buf
+        self.version = module.weight._version
+
+    def get(self, device):
+        if self.module.weight._version != self.version:
+            self.owner.refresh_packed()
+        b = self.module.bias
+        return self.weight, (None if b is None else b.detach())
+
+
+def _desc(src_ptr, dst_ptr, dst_bf16, dims, sstrides, dstrides):
+    d = _lib.CopyDesc()
+    d.src, d.dst, d.dst_bf16 = src_ptr, dst_ptr, int(dst_bf16)
+    dims, sstrides, dstrides = list(dims), list(sstrides), list(dstrides)
+    while len(dims) < 4:                               # leading unit dimensions
+        dims.insert(0, 1); sstrides.insert(0, 0); dstrides.insert(0, 0)
+    for i in range(4):
+        d.dim[i], d.sstride[i], d.dstride[i] = int(dims[i]), int(sstrides[i]), int(dstrides[i])
+    return d
+
+
 class _Scratch:
     """Named device buffers reused across steps."""
 
@@ -79,6 +105,73 @@ class UNetTrainStep:
             self.dw[name] = (total_dw, shape)
             total_dw += shape[0] * shape[1] * shape[2]
         self.dw_flat = torch.zeros(total_dw, dtype=torch.float32, device=self.device)
+        self._build_copy_tables()
+
+    # ---------------------------------------------------------------- batched weight packing / gradient layout
+    def _build_copy_tables(self):
+        """Descriptor tables of the two batched strided-copy launches of a step (csrc/train_kernels.cu):
+        `pack`   fp32 master weights -> every bf16 tensor-core layout the step reads (forward layers as the network's pack
+                 cache holds them, transposed + flipped data-gradient forms), run after each Adam update;
+        `unpack` wgrad scratch [tap][ci][co] -> the parameters' own gradient layout in the flat gradient buffer."""
+        net = self.net
+        with torch.no_grad():                              # dry run: lets the network decide each layer's kernel mode / layout
+            self.forward(torch.zeros((1, net.conv1_1.weight.shape[1], 32, 32), device=self.device))
+        self.scr.bufs.clear()
+        fp = lambda name: self.flat_p.data_ptr() + 4 * self.slices[name + ".weight"][0]
+        gp = lambda name: self.flat_g.data_ptr() + 4 * self.slices[name + ".weight"][0]
+        pack, unpack, self.wd = [], [], {}
+        cache = net.__dict__["_pack_cache"]
+        for (name, kind), entry in list(cache.items()):
+            m, buf = net.get_submodule(name), entry.weight
+            rows_p, cin_p = buf.shape[1], buf.shape[2]
+            if kind == "convT":                            # W[ci][co][a][b] -> [a*2+b][co][ci]
+                ci, co = m.weight.shape[0], m.weight.shape[1]
+                pack.append(_desc(fp(name), buf.data_ptr(), 1, (4, co, ci), (1, 4, co * 4), (rows_p * cin_p, cin_p, 1)))
+            elif kind == "conv3x":                         # W[co][ci][ky][kx] -> [ky][kx*co + co'][ci]
+                co, ci = m.weight.shape[0], m.weight.shape[1]
+                pack.append(_desc(fp(name), buf.data_ptr(), 1, (3, 3, co, ci), (3, 1, ci * 9, 9), (rows_p * cin_p, co * cin_p, cin_p, 1)))
+            else:                                          # W[co][ci][ky][kx] -> [tap][co][ci]
+                co, ci, kk = m.weight.shape[0], m.weight.shape[1], m.weight.shape[2] * m.weight.shape[3]
+                pack.append(_desc(fp(name), buf.data_ptr(), 1, (kk, co, ci), (1, ci * kk, kk), (rows_p * cin_p, cin_p, 1)))
+            cache[(name, kind)] = _StaticPacked(self, m, buf)
+        for name, m in net.named_modules():
+            if isinstance(m, torch.nn.ConvTranspose2d):    # dgrad: [a*2+b][ci][co] = W[ci][co][a][b];  grad[ci][co][tap] = dw[tap][ci][co]
+                ci, co = m.weight.shape[0], m.weight.shape[1]
+                buf = torch.zeros((4, _pad16(ci), _pad16(co)), dtype=torch.bfloat16, device=self.device)
+                self.wd[name] = buf
+                pack.append(_desc(fp(name), buf.data_ptr(), 1, (4, ci, co), (1, co * 4, 4), (buf.shape[1] * buf.shape[2], buf.shape[2], 1)))
+                unpack.append(_desc(self._dw_view(name).data_ptr(), gp(name), 0, (ci, co, 4), (co, 1, ci * co), (co * 4, 4, 1)))
+            elif isinstance(m, torch.nn.Conv2d) and m.kernel_size == (3, 3):
+                co, cin = m.weight.shape[0], m.weight.shape[1]
+                ci_total = self.dw[name][1][1]
+                unpack.append(_desc(self._dw_view(name).data_ptr(), gp(name), 0, (co, cin, 9), (1, co, ci_total * co), (cin * 9, 9, 1)))
+                if name == "conv1_1":
+                    continue                               # the network input needs no gradient
+                halves = (cin // 2, cin // 2) if (name.endswith("_1") and int(name[4]) >= 6) else (cin,)   # cat([up, skip], 1)
+                c_off = 0
+                for k, ck in enumerate(halves):            # dgrad: [8 - tap][ci][co] <- W[co][c_off + ci][tap]  (180-degree flip)
+                    buf = torch.zeros((9, _pad16(ck), _pad16(co)), dtype=torch.bfloat16, device=self.device)
+                    self.wd[(name, k)] = buf
+                    pack.append(_desc(fp(name) + 4 * (c_off * 9 + 8), buf.data_ptr(), 1, (9, ck, co), (-1, 9, cin * 9),
+                                      (buf.shape[1] * buf.shape[2], buf.shape[2], 1)))
+                    c_off += ck
+        def table(descs):
+            arr = (_lib.CopyDesc * len(descs))(*descs)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            return host.to(self.device), len(descs)
+        self._pack_tab, self._unpack_tab = table(pack), table(unpack)
+        self.refresh_packed()
+
+    def refresh_packed(self):
+        """Re-pack every bf16 weight layout from the fp32 master weights (one launch)."""
+        tab, n = self._pack_tab
+        L.check(L.lib().pnnp_strided_copy_batch(tab.data_ptr(), n, 48, self._stream()), "pack weights")
+        cache = self.net.__dict__["_pack_cache"]
+        for key in list(cache):
+            if isinstance(cache[key], _StaticPacked):
+                cache[key].version = cache[key].module.weight._version
+            else:
+                del cache[key]                             # framework-packed entries cannot see this step's in-place update
 
     # ---------------------------------------------------------------- small wrappers over the C ABI
     def _grad_view(self, name):
@@ -118,19 +211,13 @@ class UNetTrainStep:
         for s in srcs:
             self._wgrad_nhwc(0, g, co, s, dw, c_off, ci_total)
             c_off += s.shape[-1]
-        cin_real = m.weight.shape[1]
-        self._grad_view(name + ".weight").copy_(dw[:, :cin_real, :].permute(2, 1, 0).reshape(co, cin_real, 3, 3))
         gxs = []
         if need_dx:
-            W = m.weight.detach()
-            c_off = 0
-            for k, s in enumerate(srcs):
+            for k, s in enumerate(srcs):                  # data gradient: the forward kernel on the transposed + flipped weights
                 ck = s.shape[-1]
-                wd = _pack_conv_weight(W[:, c_off:c_off + ck].transpose(0, 1).flip(2, 3))     # [ci][co][2-ky][2-kx]
                 gx = self.scr.get(f"gx_{name}_{k}", (n, h, w, ck))
-                _conv(_lib.CONV3, g, wd, None, gx, ck, _lib.ACT_NONE)
+                _conv(_lib.CONV3, g, self.wd[(name, k)], None, gx, ck, _lib.ACT_NONE)
                 gxs.append(gx)
-                c_off += ck
         return gxs
 
     def _convT_bwd(self, name, g_up, x_in):
@@ -141,10 +228,8 @@ class UNetTrainStep:
         self._act_bwd(g_up, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)
         dw = self._dw_view(name)
         self._wgrad_nhwc(1, g_up, co, x_in, dw, 0, ci)
-        self._grad_view(name + ".weight").copy_(dw.permute(1, 2, 0).reshape(ci, co, 2, 2))
-        wd = _pack_conv_weight(m.weight.detach())            # [rows=ci][cin=co][a][b] -> [a*2+b][ci][co]
         gx = self.scr.get("gx_" + name, (n, h, w, ci))
-        _conv(_lib.CONV2S2, g_up, wd, None, gx, ci, _lib.ACT_NONE)
+        _conv(_lib.CONV2S2, g_up, self.wd[name], None, gx, ci, _lib.ACT_NONE)      # [a*2+b][ci][co] = W[ci][co][a][b]
         return gx
 
     # ---------------------------------------------------------------- the step
@@ -219,6 +304,8 @@ class UNetTrainStep:
             res = self._conv3_bwd(f"conv{i}_1", g, s[f"c{i}a"], [s[f"in{i}_1"]], i > 1)
             if i > 1:
                 g = res[0]
+        tab, nd = self._unpack_tab                           # wgrad scratch -> the parameters' gradient layout (one launch)
+        L.check(L.lib().pnnp_strided_copy_batch(tab.data_ptr(), nd, 48, self._stream()), "unpack gradients")
 
     def step(self, lr_crops, hr_crops, grad_allreduce=True):
         """One optimisation step on (noisy, clean) crops (CUDA fp32 NCHW).  Returns the loss as a 0-d CUDA tensor."""
@@ -233,5 +320,5 @@ class UNetTrainStep:
         L.check(L.lib().pnnp_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                        self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale,
                                        self._stream()), "adam_step")
-        self.net.__dict__.get("_pack_cache", {}).clear()                # weights changed in place: repack on next use
+        self.refresh_packed()                                           # weights changed in place: re-pack for the next forward
         return (self.loss_sum / pred.numel()).float()[0]
