@@ -224,8 +224,11 @@ struct FastC {                              // per-crop constants
     double K, span, rspan, lo, ratio, sigR;
 };
 
-template <bool DEBUG, int MINB>
-__global__ void __launch_bounds__(kFastThreads, MINB) noise_synth_fast_kernel(const SynthArgs a) {
+// Three CTAs (24 warps) per SM at 79 registers without spills.  Measured alternatives (r01): four CTAs at 64 registers spill and
+// run 15 % slower; reading the Poisson table through L1 instead of a per-CTA shared-memory copy (41 KB instead of 65 KB of
+// shared memory) is 12 % slower at equal occupancy.
+template <bool DEBUG>
+__global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const SynthArgs a) {
     // dynamic shared memory (kFastSmemBytes > 48 KB): [warps][512] uint2 queue | [warps][512] uint16 positions | Poisson table
     extern __shared__ __align__(16) uint8_t s_fast[];
     float* s_pois = reinterpret_cast<float*>(s_fast + kFastQueueBytes + kFastPosBytes);
@@ -234,28 +237,28 @@ __global__ void __launch_bounds__(kFastThreads, MINB) noise_synth_fast_kernel(co
     uint2* q = reinterpret_cast<uint2*>(s_fast) + (threadIdx.x >> 5) * kFastUnit;
     uint16_t* qpos = reinterpret_cast<uint16_t*>(s_fast + kFastQueueBytes) + (threadIdx.x >> 5) * kFastUnit;   // queue position of every element
     const unsigned lt = (1u << lane) - 1u;
-    const long long warps_total = (long long)gridDim.x * (kFastThreads / 32);
-    const long long warp_id = (long long)blockIdx.x * (kFastThreads / 32) + (threadIdx.x >> 5);
+    // 32-bit index arithmetic (the launcher takes this kernel only below 2^31 elements): registers are what limits occupancy
+    const int warps_total = (int)gridDim.x * (kFastThreads / 32);
+    const int warp_id = (int)blockIdx.x * (kFastThreads / 32) + (int)(threadIdx.x >> 5);
     const int nseg = (a.w + kFastUnit - 1) / kFastUnit;
-    const long long rows_per_crop = (long long)a.c * a.h;
-    const long long units = (long long)a.n * rows_per_crop * nseg;
+    const int rows_per_crop = a.c * a.h;
+    const int units = a.n * rows_per_crop * nseg;
     const RngCtx rng{a.rk, (uint32_t)a.offset, (uint32_t)(a.offset >> 32)};
-    const size_t crop_elems = (size_t)a.c * a.h * a.w;
 
     FastC f = {};
     int cur_crop = -1;
     float rowz_batch = 0.f;
     int it = 0;
-    for (long long u = warp_id; u < units; u += warps_total, ++it) {
+    for (int u = warp_id; u < units; u += warps_total, ++it) {
         if ((it & 31) == 0) {
             // row draws of this warp's next 32 units, one per lane
-            const long long uu = u + (long long)lane * warps_total;
+            const long long uu = (long long)u + (long long)lane * warps_total;
             if (uu < units) rowz_batch = normal_icdf(rng.block(a.crop_id0 * (uint64_t)rows_per_crop + (uint64_t)(uu / nseg), kStreamRow, 0u).x);
         }
         const float rowz = __shfl_sync(0xffffffffu, rowz_batch, it & 31);
-        const long long row = u / nseg;
-        const int seg = (int)(u - row * nseg);
-        const int crop = (int)(row / rows_per_crop);
+        const int row = u / nseg;
+        const int seg = u - row * nseg;
+        const int crop = row / rows_per_crop;
         if (crop != cur_crop) {
             const pnnp_noise_params* t = a.table + crop;
             f.K = t->K; f.span = t->span; f.lo = t->clip_lo; f.ratio = t->ratio; f.sigR = t->sigR;
@@ -267,8 +270,8 @@ __global__ void __launch_bounds__(kFastThreads, MINB) noise_synth_fast_kernel(co
         }
         if (DEBUG && a.d_rowz && seg == 0 && lane == 0) a.d_rowz[row] = rowz;
         const double row64 = __dmul_rn((double)rowz, f.sigR);
-        const size_t row_base = (size_t)row * a.w;
-        const uint64_t g_base = a.crop_id0 * (uint64_t)crop_elems + (uint64_t)row_base;
+        const uint32_t row_base = (uint32_t)row * (uint32_t)a.w;
+        const uint64_t g_base = a.crop_id0 * (uint64_t)rows_per_crop * (uint64_t)a.w + (uint64_t)row_base;
         const int x0 = seg * kFastUnit;
 
         // ---- phase 1: rates + shot words -> queue, sorted by sampler.  The j loops are deliberately NOT unrolled: the
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) noise_synth_fast_kernel(co
                     const double z = clip_f64(div_rn_by_const(A, f.span, f.rspan), f.lo, 1.0);
                     o[e] = fminf(fmaxf((float)__dmul_rn(z, f.ratio), a.post_lo), a.post_hi);
                     if (DEBUG) {
-                        const size_t lidx = row_base + x + e;
+                        const size_t lidx = (size_t)row_base + x + e;
                         if (a.d_shot) a.d_shot[lidx] = cnt;
                         if (a.d_read) a.d_read[lidx] = d_read[e];
                         if (a.d_q) a.d_q[lidx] = dq;
@@ -414,7 +417,7 @@ static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
     // Specialised path: the caller asserts (PNNP_CODE_UNIFORM_F64) that every table row has flags == K64|SIG64
     // (sample_params output); together with code == p|g|r|q, ori = clip = 0 and the vector layout this selects
     // the branch-free instantiation.  Anything else runs the generic kernel.
-    const bool fast = vec && chain == PNNP_CHAIN_NUMPY && (a.code & PNNP_CODE_UNIFORM_F64) &&
+    const bool fast = vec && chain == PNNP_CHAIN_NUMPY && (a.code & PNNP_CODE_UNIFORM_F64) && (long long)a.n * a.c * a.h * a.w < (1ll << 31) &&
                       ((a.code & 0x3Fu) == (PNNP_CODE_P | PNNP_CODE_G | PNNP_CODE_R | PNNP_CODE_Q)) && !a.ori && !a.clip;
     SynthArgs b = a;
     b.code = a.code & 0x3Fu;
@@ -423,15 +426,12 @@ static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
     if (fast) {
         const long long funits = (long long)a.n * a.c * a.h * ((a.w + kFastUnit - 1) / kFastUnit);
         const long long fwant = (funits + (kFastThreads / 32) - 1) / (kFastThreads / 32);
-        static const int minb = [] { const char* e = getenv("PNNP_NOISE_MINB"); return e ? atoi(e) : 3; }();   // tuning knob
         static bool attr_done = false;
         if (!attr_done) {
-            PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<DEBUG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
-            PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<DEBUG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
+            PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
             attr_done = true;
         }
-        if (minb == 4) noise_synth_fast_kernel<DEBUG, 4><<<(int)std::min<long long>(fwant, (long long)sms * 4), kFastThreads, kFastSmemBytes, st>>>(b);
-        else           noise_synth_fast_kernel<DEBUG, 3><<<(int)std::min<long long>(fwant, (long long)sms * 3), kFastThreads, kFastSmemBytes, st>>>(b);
+        noise_synth_fast_kernel<DEBUG><<<(int)std::min<long long>(fwant, (long long)sms * 3), kFastThreads, kFastSmemBytes, st>>>(b);
     }
     else if (chain == PNNP_CHAIN_NUMPY) { if (vec) PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 4); else PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 1); }
     else                                { if (vec) PNNP_LAUNCH(PNNP_CHAIN_TORCH, 4); else PNNP_LAUNCH(PNNP_CHAIN_TORCH, 1); }
