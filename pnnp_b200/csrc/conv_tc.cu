@@ -75,6 +75,29 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// Tile walk.  A CTA owns a CONTIGUOUS range of tiles (order: n_tile fastest, then x, y, image), so neighbouring tiles' halos
+// meet in L2 while they are hot and the (n_tile, x, y, image) coordinates advance by increment-and-carry: the per-tile index
+// arithmetic (three run-time divisions per tile in each of the three warp roles) was, for the small-K full-resolution
+// layers, most of a single warp's serial instruction stream per tile — ~800 cycles per tile with loads, MMAs and epilogue all
+// switched off (r01 experiment PNNP_CONV_DBG=14).
+struct TileIter {
+    int t, t_end, n_tile, tx, ty, img;
+    __device__ __forceinline__ void init(int total_tiles, int n_tiles, int tiles_x, int tiles_y) {
+        const int per = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+        t = min(total_tiles, (int)blockIdx.x * per);
+        t_end = min(total_tiles, t + per);
+        int r = t;
+        n_tile = r % n_tiles; r /= n_tiles;
+        tx = r % tiles_x; r /= tiles_x;
+        ty = r % tiles_y; img = r / tiles_y;
+    }
+    __device__ __forceinline__ bool valid() const { return t < t_end; }
+    __device__ __forceinline__ void next(int n_tiles, int tiles_x, int tiles_y) {
+        ++t;
+        if (++n_tile == n_tiles) { n_tile = 0; if (++tx == tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } } }
+    }
+};
+
 // All MMAs of one pipeline stage: TPS taps x K16S K-slices, fully unrolled; descriptors advance by adding
 // to the 14-bit start-address field (no carry out of the field: shared memory is < 256 KB).
 template <int TPS, int K16S>
@@ -150,92 +173,113 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // commit instructions themselves are predicated on one elected lane.
     if (warp == 0) {
         // ============================== TMA producer ==============================
-        uint32_t stage = 0, phase = 0;
-        const int halo = p.mode == MODE_CONV3 ? 1 : 0;
-        const int yhalo = (p.mode == MODE_CONV3 || p.mode == MODE_CONV3X) ? 1 : 0;
-        if (p.b_resident && elect_one()) {
+        // Everything the loops need is copied into registers first: the asm statements carry "memory" clobbers, so every p.field
+        // used inside a loop would otherwise be re-read from the parameter bank per tile, and for the small-K full-resolution
+        // layers (one pipeline stage per tile) this single warp's serial instruction stream IS the tile rate.
+        const int mode = p.mode, n_tiles = p.n_tiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, umma_n = p.umma_n, kc = p.kc;
+        const int cin0 = p.cin0, stages = p.stages, stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, b_tap_bytes = p.b_tap_stride;
+        const int dbg = p.dbg;
+        const bool b_res = p.b_resident != 0;
+        int* const err = p.err;
+        const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        const int halo = mode == MODE_CONV3 ? 1 : 0;
+        const int yhalo = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? 1 : 0;
+        const int tile_w = mode == MODE_CONV3X ? kTileWX : kTileW, x_first = mode == MODE_CONV3X ? -1 : 0;
+        const bool plain = mode != MODE_CONV2S2 && mode != MODE_CONV3S2;
+        if (b_res && elect_one()) {
             // weights for every (K chunk, tap) once per CTA: layout [chunk][tap][umma_n rows x swz bytes]
             const uint32_t bb = smem_u32(bres_bar);
-            mbar_expect_tx(bb, (uint32_t)((chunks0 + chunks1) * taps_total * p.umma_n * p.swz));
+            mbar_expect_tx(bb, (uint32_t)((chunks0 + chunks1) * taps_total * umma_n * p.swz));
             for (int ch = 0; ch < chunks0 + chunks1; ++ch)
                 for (int tap = 0; tap < taps_total; ++tap)
-                    tma_load_3d(smem_u32(smem_bres) + (ch * taps_total + tap) * p.b_tap_stride, &tmB, bb, ch * p.kc, 0, tap);
+                    tma_load_3d(smem_u32(smem_bres) + (ch * taps_total + tap) * b_tap_bytes, &tmB, bb, ch * kc, 0, tap);
         }
         __syncwarp();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            int r = t;
-            const int n_tile = r % p.n_tiles; r /= p.n_tiles;
-            const int tx = r % p.tiles_x; r /= p.tiles_x;
-            const int ty = r % p.tiles_y; r /= p.tiles_y;
-            const int img = r;
-            const int x0 = p.mode == MODE_CONV3X ? tx * kTileWX - 1 : tx * kTileW, y0 = ty * kTileH;
-            const int n_off = n_tile * p.umma_n;
+        TileIter ti;
+        ti.init(total_tiles, n_tiles, tiles_x, tiles_y);
+        const int first_tile = ti.t;
+        uint32_t stage = 0, phase = 0, sa = smem0, fb = full0, eb = empty0;
+        for (; ti.valid(); ti.next(n_tiles, tiles_x, tiles_y)) {
+            const int img = ti.img;
+            const int x0 = ti.tx * tile_w + x_first, y0 = ti.ty * kTileH;
+            const int n_off = ti.n_tile * umma_n;
+            const bool skip_loads = (dbg & 4) && ti.t != first_tile;
             int chunk = 0, dx = 0;
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int src = chunk >= chunks0 ? 1 : 0;
                 const int cc = src ? chunk - chunks0 : chunk;
-                const int cin_off = (src ? p.cin0 : 0) + cc * p.kc;
-                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 101);
-                const uint32_t fb = smem_u32(&full_bar[stage]);
-                const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                const uint32_t sb = sa + p.a_bytes;
-                if ((p.dbg & 4) && (t != (int)blockIdx.x)) { if (elect_one()) mbar_arrive(fb); }
+                mbar_wait(eb, phase ^ 1, err, 101);
+                if (skip_loads) { if (elect_one()) mbar_arrive(fb); }
                 else if (elect_one()) {
                     mbar_expect_tx(fb, stage_tx);
-                    if (p.mode == MODE_CONV2S2)      // 2x2 stride 2, no padding (ConvTranspose2d dgrad): tap = a*2+b
-                        tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx & 1), 2 * y0 + (dx >> 1), img);
-                    else if (p.mode == MODE_CONV3S2) // stride 2: one box per tap, TMA element stride 2 in x and y
-                        tma_load_4d(sa, &tmA0, fb, cc * p.kc, 2 * x0 + (dx % 3) - 1, 2 * y0 + (dx / 3) - 1, img);
-                    else
-                        tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * p.kc, x0 + dx - halo, y0 - yhalo, img);
-                    for (int dy = 0; dy < (p.b_resident ? 0 : taps_per_stage); ++dy) {
-                        const int tap = p.mode == MODE_CONV3 ? dy * 3 + dx
-                                      : ((p.mode == MODE_CONV3S2 || p.mode == MODE_CONV2S2) ? dx : (p.mode == MODE_CONV3X ? dy : 0));
-                        tma_load_3d(sb + dy * p.b_tap_stride, &tmB, fb, cin_off, n_off, tap);
+                    if (plain)
+                        tma_load_4d(sa, src ? &tmA1 : &tmA0, fb, cc * kc, x0 + dx - halo, y0 - yhalo, img);
+                    else if (mode == MODE_CONV2S2)   // 2x2 stride 2, no padding (ConvTranspose2d dgrad): tap = a*2+b
+                        tma_load_4d(sa, &tmA0, fb, cc * kc, 2 * x0 + (dx & 1), 2 * y0 + (dx >> 1), img);
+                    else                             // stride 2: one box per tap, TMA element stride 2 in x and y
+                        tma_load_4d(sa, &tmA0, fb, cc * kc, 2 * x0 + (dx % 3) - 1, 2 * y0 + (dx / 3) - 1, img);
+                    if (!b_res) {
+                        const int cin_off = (src ? cin0 : 0) + cc * kc;
+                        for (int dy = 0; dy < taps_per_stage; ++dy) {
+                            const int tap = mode == MODE_CONV3 ? dy * 3 + dx
+                                          : ((mode == MODE_CONV3S2 || mode == MODE_CONV2S2) ? dx : (mode == MODE_CONV3X ? dy : 0));
+                            tma_load_3d(sa + a_bytes + dy * b_tap_bytes, &tmB, fb, cin_off, n_off, tap);
+                        }
                     }
                 }
                 __syncwarp();
                 if (++dx == dx_count) { dx = 0; ++chunk; }
-                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                sa += stage_bytes; fb += 8; eb += 8;
+                if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; sa = smem0; fb = full0; eb = empty0; }
             }
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
         // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        const int mode = p.mode, umma_n = p.umma_n, stages = p.stages, stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, dbg = p.dbg;
+        const int groups = p.groups;
+        const bool b_res = p.b_resident != 0;
+        int* const err = p.err;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
         const uint64_t dhi = umma_desc_hi(p.swz);
         const uint32_t a_tap_stride = (uint32_t)(kTileW * p.swz) >> 4;      // descriptor units (16 B)
         const uint32_t b_tap_stride = (uint32_t)p.b_tap_stride >> 4;
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        if (p.b_resident) mbar_wait(smem_u32(bres_bar), 0, p.err, 105);
-        const int dxc = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV2S2 ? 4 : 1));
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 102);
-            int chunk = 0, dx = 0;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.umma_n;
+        const uint32_t b_tap_bytes = (uint32_t)p.b_tap_stride;
+        const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar), bres0 = smem_u32(smem_bres);
+        // resident layout [chunk][tap]: CONV3 stage dx uses taps dy*3+dx (stride 3 taps); CONV3X: dy taps are consecutive
+        const uint32_t b_stride_eff = (b_res && mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;
+        if (b_res) mbar_wait(smem_u32(bres_bar), 0, err, 105);
+        const int dxc = mode == MODE_CONV3 ? 3 : (mode == MODE_CONV3S2 ? 9 : (mode == MODE_CONV2S2 ? 4 : 1));
+        const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int t_begin = min(total_tiles, (int)blockIdx.x * per_cta), t_stop = min(total_tiles, t_begin + per_cta);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, sa = smem0, fb = full0, eb = empty0;
+        for (int t = t_begin; t < t_stop; ++t) {
+            if (!(dbg & 32)) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, err, 102);
+            if (!(dbg & 64)) tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)umma_n;
+            uint32_t sb_res = bres0;                                       // resident weights of (chunk, dx): advances by one tap
+            int dx = 0;
             for (int ks = 0; ks < ksteps; ++ks) {
-                mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 103);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                mbar_wait(fb, phase, err, 103);
+                if (!(dbg & 64)) tc_fence_after();
                 const uint64_t adesc0 = dhi | (uint64_t)((sa >> 4) & 0x3FFFu);
-                // resident layout [chunk][tap]: CONV3 stage dx uses taps dy*3+dx (stride 3 taps); S2 stage uses tap dx
-                const uint32_t sb = p.b_resident
-                    ? smem_u32(smem_bres) + (uint32_t)((chunk * taps_total + dx) * p.b_tap_stride)
-                    : sa + p.a_bytes;
+                const uint32_t sb = b_res ? sb_res : sa + (uint32_t)a_bytes;
                 const uint64_t bdesc0 = dhi | (uint64_t)((sb >> 4) & 0x3FFFu);
-                const uint32_t b_stride_eff = (p.b_resident && p.mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;   // CONV3X: dy taps are consecutive
-                if (++dx == dxc) { dx = 0; ++chunk; }
+                // (chunk * taps_total + dx) * tap bytes: +1 tap per stage, +taps_total per chunk
+                if (++dx == dxc) { dx = 0; sb_res += (uint32_t)(taps_total - dxc + 1) * b_tap_bytes; } else sb_res += b_tap_bytes;
                 if (elect_one()) {
-                    if (!(p.dbg & 2)) issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
-                    tc_commit(smem_u32(&empty_bar[stage]));              // frees the smem slot when these MMAs retire
+                    if (!(dbg & 2)) issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
+                    if (dbg & 16) mbar_arrive(eb);
+                    else tc_commit(eb);                                    // frees the smem slot when these MMAs retire
                 }
                 __syncwarp();
-                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                sa += (uint32_t)stage_bytes; fb += 8; eb += 8;
+                if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; sa = smem0; fb = full0; eb = empty0; }
             }
-            if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete -> epilogue
+            if (elect_one() && !(dbg & 32)) { if (dbg & 16) mbar_arrive(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc); }   // accumulator complete -> epilogue
             __syncwarp();
-            if (++acc == (uint32_t)p.groups) { acc = 0; acc_phase ^= 1; }
+            if (++acc == (uint32_t)groups) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ============================== epilogue (warps 2..5) ==============================
@@ -258,12 +302,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         // activation as max(v, v * slope + 0): LeakyReLU 0.2 / ReLU (slope 0; the +0 turns -0 into +0) / identity (slope 1)
         const float slope = p.act == ACT_LEAKY ? 0.2f : (p.act == ACT_RELU ? 0.f : 1.f);
         const int chunks16 = (xmode ? p.cout : p.umma_n) / 16;
-        for (int t = blockIdx.x + group * gridDim.x; t < total_tiles; t += p.groups * gridDim.x) {
-            int r = t;
-            const int n_tile = r % p.n_tiles; r /= p.n_tiles;
-            const int tx = r % p.tiles_x; r /= p.tiles_x;
-            const int ty = r % p.tiles_y; r /= p.tiles_y;
-            const int img = r;
+        TileIter ti;
+        ti.init(total_tiles, p.n_tiles, p.tiles_x, p.tiles_y);
+        if (p.dbg & 32) ti.t = ti.t_end;
+        for (int g = 0; g < group && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);   // group g: every groups-th tile
+        for (; ti.valid(); ) {
+            const int n_tile = ti.n_tile, tx = ti.tx, ty = ti.ty, img = ti.img;
+            for (int g = 0; g < p.groups && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);
             const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTileW + tx_in, y = ty * kTileH + ty_in;
             const bool valid = x < p.W && y < p.H && (!xmode || (tx_in >= 1 && tx_in <= kTileWX));
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
@@ -580,7 +625,18 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     p.cout = cout; p.cout_stride = cout_stride; p.act = act; p.out_mode = out_mode;
     p.stages = stages; p.stage_bytes = stage_bytes; p.a_bytes = a_bytes; p.b_tap_stride = b_tap_stride;
     p.b_resident = b_resident; p.b_res_bytes = b_res_bytes;
-    const int groups = (umma_n <= 128 && !getenv("PNNP_CONV_2GROUPS")) ? 4 : 2;
+    // Small-K layers with resident weights (one or two pipeline stages per tile) are bound by the per-tile hand-shake latency of
+    // the single producer / MMA warp pair (~650 cycles per tile with every unit of work switched off, r01 experiments): run TWO
+    // CTAs per SM for them — half the shared memory, two accumulator buffers (<= 256 TMEM columns) and 320 threads each.
+    const int ksteps_tile = (cin_total / kc) * (mode == MODE_CONV3 ? 3 : (mode == MODE_CONV3S2 ? 9 : (mode == MODE_CONV2S2 ? 4 : 1)));
+    const bool two_ctas = b_resident && umma_n <= 128 && ksteps_tile <= 2 && !getenv("PNNP_CONV_1CTA");
+    if (two_ctas) {
+        const int half_budget = 110 * 1024 - 2048 - cout * 20;
+        stages = std::min(stages, (half_budget - b_res_bytes) / stage_bytes);
+        if (stages < 3) return fail("conv: two-CTA configuration does not fit (internal)");
+    }
+    const int groups = two_ctas ? 2 : ((umma_n <= 128 && !getenv("PNNP_CONV_2GROUPS")) ? 4 : 2);
+    p.stages = stages;
     int tc = 32; while (tc < groups * umma_n) tc <<= 1;
     p.tmem_cols = tc; p.groups = groups;
     p.bias = bias; p.out = out; p.resid = static_cast<const __nv_bfloat16*>(resid); p.resid_nchw = resid_nchw;
@@ -599,7 +655,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     PNNP_CUDA(cudaGetDevice(&dev));
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int total_tiles = n * p.tiles_y * p.tiles_x * n_tiles;
-    const int grid = std::min(total_tiles, sms);
+    const int grid = std::min(total_tiles, two_ctas ? 2 * sms : sms);
     const size_t smem = (size_t)stages * stage_bytes + b_res_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 2 * kMaxGroups + 2) * 8 + 16 + (size_t)cout * 4 * 5 + 64;
     if (smem > 227 * 1024) return fail("conv: shared memory budget exceeded");
     static bool attr_done = false;

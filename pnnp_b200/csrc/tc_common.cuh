@@ -28,8 +28,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     uint32_t ok = 0, it = 0;
 #pragma unroll 1
     while (true) {
+#ifdef PNNP_MBAR_TEST_WAIT
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
         if (ok) return;
         if ((++it & 0x3FFu) == 0) {
             if (*reinterpret_cast<volatile int*>(err) != 0) return;
