@@ -403,7 +403,8 @@ def run_gpu_arm(args, name, wl):
     # ---- end-to-end through the public host-buffer API (pinned host in, host result out)
     e2e_steps = max(3, min(args.steps, 20))
     if name == "synth64":
-        pipe = HostSynthPipeline(n, c, h, w, device)
+        pipe = HostSynthPipeline(n, c, h, w, device, chunk=int(os.environ.get("PNNP_E2E_CHUNK", "8")),
+                                 n_streams=int(os.environ.get("PNNP_E2E_STREAMS", "3")))
         host_in = torch.empty((n, c, h, w), dtype=torch.float32).pin_memory()
         host_in.copy_(clean.cpu())
         host_out = torch.empty_like(host_in).pin_memory()

@@ -164,6 +164,8 @@ typedef struct pnnp_conv_desc {
     const float* resid_nchw;
     void* pool_out;
     const float* head_w; const float* head_b; float* head_out; int head_cout;
+    const void* mask; float mask_slope;   /* NHWC bf16 activation shaped like the output: out *= (mask > 0 ? 1 : mask_slope) — the
+                                           * activation derivative fused into a data-gradient conv (training); NULL = off */
 } pnnp_conv_desc;
 int pnnp_conv2d_tc_ex(const pnnp_conv_desc* desc, void* stream);
 /* Non-zero if a tcgen05/TMA pipeline wait timed out since the last call (the kernels terminate
@@ -219,9 +221,10 @@ int pnnp_head_bwd(const float* gpred, const void* act, const float* W, void* gac
                   float* dbias_prev, int n, int h, int w, int cin, int co, int act_kind, void* stream);
 /* in place: g (NHWC bf16, w.r.t. activated output) *= act'(out); dbias[c] += sum over pixels (may be NULL) */
 int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t pixels, int c, int act_kind, void* stream);
-/* MaxPool2d(2) backward; gskip (optional) is added: gc = gskip + scatter(gp) (the U-Net skip connection) */
+/* MaxPool2d(2) backward; gskip (optional) is added: gc = gskip + scatter(gp) (the U-Net skip connection); with act_kind != 0
+ * the result is also multiplied by act'(cfull) (cfull is the activated output whose pooling this undoes) */
 int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c,
-                     void* stream);
+                     int act_kind, void* stream);
 /* Weight gradients straight from the NHWC bf16 activations (tcgen05, MN-major operands via TMA; no transposed copies):
  *   mode 0 (3x3 s1 p1 conv):      dw[ky*3+kx][ci_off + ci][co] += sum_p x[p + (ky-1, kx-1)][ci] * g[p][co]
  *   mode 1 (ConvTranspose2d 2x2): dw[a*2+b][ci_off + ci][co]   += sum_p x[p][ci] * g[2p + (a, b)][co]

@@ -84,7 +84,7 @@ class _Workspace:
 
 
 def _conv(mode, x0, w, b, out, cout, act, x1=None, resid=None, out_mode=_lib.OUT_NHWC_BF16, resid_nchw=None,
-          pool_out=None, head=None):
+          pool_out=None, head=None, mask=None, mask_slope=0.2):
     """x0/x1: NHWC bf16 (n,h,w,c).  out: NHWC bf16 tensor, NCHW fp32 tensor, or None with `head`.
     pool_out: NHWC bf16 (n,h/2,w/2,cout) receiving the fused 2x2 max-pool.
     head = (w fp32 [co2, cout], b fp32 [co2], out fp32 NCHW): fused 1x1 conv on the activated output."""
@@ -97,6 +97,8 @@ def _conv(mode, x0, w, b, out, cout, act, x1=None, resid=None, out_mode=_lib.OUT
     d.out, d.cout = _lib.ptr(out), cout
     d.cout_stride = cout if (out is None or out_mode != _lib.OUT_NHWC_BF16) else out.shape[3]
     d.resid, d.resid_nchw, d.pool_out = _lib.ptr(resid), _lib.ptr(resid_nchw), _lib.ptr(pool_out)
+    if mask is not None:          # training dgrad: out *= act'(mask), mask = the activated output of the layer being differentiated
+        d.mask, d.mask_slope = mask.data_ptr(), float(mask_slope)
     if head is not None:
         hw, hb, hout = head
         d.head_w, d.head_b, d.head_out, d.head_cout = hw.data_ptr(), hb.data_ptr(), hout.data_ptr(), hw.shape[0]

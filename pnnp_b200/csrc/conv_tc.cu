@@ -60,6 +60,8 @@ struct ConvParams {
     void* out;
     const __nv_bfloat16* resid;     // NHWC bf16 residual with the output's geometry, or null
     const float* resid_nchw;        // NCHW fp32 residual for OUT_NCHW_F32 / the fused head, or null
+    const __nv_bfloat16* mask;      // NHWC bf16 activation with the output's geometry: out *= (mask > 0 ? 1 : mask_slope), or null
+    float mask_slope;               //   (LeakyReLU' / ReLU' of the layer whose data gradient this conv computes)
     __nv_bfloat16* pool_out;        // optional fused 2x2 max-pool output (NHWC bf16, H/2 x W/2)
     const float* head_w;            // optional fused 1x1 head: [head_cout][cout] fp32 weights
     const float* head_b;            // [head_cout]
@@ -118,7 +120,7 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
 // EPI: compile-time specialisation of the epilogue.  -1 = generic (every feature decided at run time).  >= 0 = the hot NHWC-output
 // 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
 // the narrow full-resolution layers are bound by the epilogue's instruction count, and most of it was run-time feature tests.
-constexpr int EPI_GENERIC = -1, EPI_X = 1, EPI_POOL = 2, EPI_HEAD = 4;
+constexpr int EPI_GENERIC = -1, EPI_X = 1, EPI_POOL = 2, EPI_HEAD = 4, EPI_MASK = 8;   // bit 3: activation-derivative mask (training dgrad)
 template <int TPS, int K16S, int EPI>
 __global__ void __launch_bounds__(kConvThreadsMax, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -297,6 +299,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const bool is_convt = kSpec ? false : p.mode == MODE_CONVT;
         const bool out_nhwc = kSpec ? true : p.out_mode == OUT_NHWC_BF16;
         const bool has_resid = kSpec ? false : p.resid != nullptr;
+        const bool has_mask = kSpec ? (EPI & EPI_MASK) != 0 : p.mask != nullptr;
         const bool has_pool = kSpec ? (EPI & EPI_POOL) != 0 : p.pool_out != nullptr;
         const bool has_head = kSpec ? (EPI & EPI_HEAD) != 0 : p.head_out != nullptr;
         // activation as max(v, v * slope + 0): LeakyReLU 0.2 / ReLU (slope 0; the +0 turns -0 into +0) / identity (slope 1)
@@ -372,6 +375,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         for (int i = 0; i < 8; ++i) {
                             f[2 * i] += __uint_as_float(rw[i] << 16);
                             f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+                        }
+                    }
+                    if (has_mask && valid) {
+                        // backward of the producing layer's activation, fused: g_pre = g * act'(out), out > 0 ? 1 : slope
+                        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + opix * p.cout_stride + c0);
+                        const uint4 m0 = mp[0], m1 = mp[1];
+                        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            f[2 * i] *= __uint_as_float(mw[i] << 16) > 0.f ? 1.f : p.mask_slope;
+                            f[2 * i + 1] *= __uint_as_float(mw[i] & 0xFFFF0000u) > 0.f ? 1.f : p.mask_slope;
                         }
                     }
                     uint32_t pk[8];
@@ -640,6 +654,8 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     int tc = 32; while (tc < groups * umma_n) tc <<= 1;
     p.tmem_cols = tc; p.groups = groups;
     p.bias = bias; p.out = out; p.resid = static_cast<const __nv_bfloat16*>(resid); p.resid_nchw = resid_nchw;
+    p.mask = static_cast<const __nv_bfloat16*>(d.mask); p.mask_slope = d.mask_slope;
+    if (d.mask && out_mode != OUT_NHWC_BF16) return fail("conv: the activation mask needs NHWC bf16 output");
     p.pool_out = static_cast<__nv_bfloat16*>(d.pool_out);
     p.head_w = d.head_w; p.head_b = d.head_b; p.head_out = d.head_out; p.head_cout = d.head_out ? d.head_cout : 0;
     { const char* e = getenv("PNNP_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -662,7 +678,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // (taps per stage, K16 slices, epilogue specialisation); specialised epilogues exist for the 3-taps-per-stage shapes
 #define PNNP_SPEC_EPI(X, T, K) X(T, K, 0) X(T, K, 1) X(T, K, 2) X(T, K, 3) X(T, K, 4) X(T, K, 5)
 #define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1, -1) X(3, 2, -1) X(3, 4, -1) X(1, 1, -1) X(1, 2, -1) X(1, 4, -1) \
-    PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4)
+    PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8)
     if (!attr_done) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_CONV_VARIANT(X)
@@ -673,8 +689,8 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     int epi = EPI_GENERIC;
     static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
     if (!no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && tps == 3 && !p.dbg &&
-        !(d.pool_out && d.head_out))
-        epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0);
+        !(d.pool_out && d.head_out) && !(d.mask && (mode == MODE_CONV3X || d.pool_out || d.head_out)))
+        epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
     bool launched = false;
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { conv_gemm_tc_kernel<T, K, E><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
     PNNP_FOR_EACH_CONV_VARIANT(X)

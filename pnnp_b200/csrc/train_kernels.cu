@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(__nv_bfloat16* __rest
 // gc[n,h,w,c] = (gskip ? gskip : 0) + gp[n,h/2,w/2,c] at the first arg-max of each window (row-major scan order, as torch)
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ gp, const __nv_bfloat16* __restrict__ cfull,
                                                           const __nv_bfloat16* __restrict__ gskip, __nv_bfloat16* __restrict__ gc,
-                                                          int n, int h, int w, int c) {
+                                                          int n, int h, int w, int c, int act_kind) {
     const int ho = h / 2, wo = w / 2, c2 = c / 2;
     const size_t total = (size_t)n * ho * wo * c2;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -163,7 +163,12 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
         for (int k = 0; k < 4; ++k) {
             float s0 = 0.f, s1 = 0.f;
             if (gskip) { const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(gskip + idx[k]); s0 = __low2float(t); s1 = __high2float(t); }
-            *reinterpret_cast<__nv_bfloat162*>(gc + idx[k]) = __floats2bfloat162_rn(s0 + (k == a0 ? g0 : 0.f), s1 + (k == a1 ? g1 : 0.f));
+            __nv_bfloat162 o = __floats2bfloat162_rn(s0 + (k == a0 ? g0 : 0.f), s1 + (k == a1 ? g1 : 0.f));
+            if (act_kind) {         // fused act'(cfull): the sum is rounded to bf16 first, as when the two steps were separate kernels
+                const float sl = act_kind == 1 ? 0.2f : 0.f;
+                o = __floats2bfloat162_rn(__low2float(o) * (v0[k] > 0.f ? 1.f : sl), __high2float(o) * (v1[k] > 0.f ? 1.f : sl));
+            }
+            *reinterpret_cast<__nv_bfloat162*>(gc + idx[k]) = o;
         }
     }
 }
@@ -211,19 +216,25 @@ extern "C" int pnnp_head_bwd(const float* gpred, const void* act, const float* W
 
 extern "C" int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t pixels, int c, int act_kind, void* stream) {
     if (!g || (act_kind && !out) || (c % 8) || c > 1024) return fail("act_bwd_bias: bad arguments");
-    // grid * 256 is a multiple of c/8 (c/8 is a power of two <= 128 for this network family): a thread keeps its channel group
-    act_bwd_bias_kernel<<<blocks_for(pixels * (c / 8)), 256, sizeof(float) * c, (cudaStream_t)stream>>>(
+    // grid * 256 is a multiple of c/8 (c/8 is a power of two <= 128 for this network family): a thread keeps its channel group.
+    // Every block ends with c global atomics, so small tensors get few blocks (>= 8 items per thread) instead of 1184 x c atomics.
+    const size_t items = pixels * (size_t)(c / 8);
+    int blocks = (int)std::max<size_t>(1, std::min<size_t>(items / (256 * 8), 148 * 8));
+    const int quantum = std::max(1, (c / 8) / 256);                  // keep grid * 256 a multiple of c / 8
+    blocks = std::max(quantum, blocks / quantum * quantum);
+    act_bwd_bias_kernel<<<blocks, 256, sizeof(float) * c, (cudaStream_t)stream>>>(
         static_cast<__nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(out), dbias, pixels, c, act_kind);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;
 }
 
-extern "C" int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c, void* stream) {
+extern "C" int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c, int act_kind,
+                                void* stream) {
     if (!gp || !cfull || !gc || (h & 1) || (w & 1) || (c & 1)) return fail("maxpool_bwd: bad arguments");
     maxpool_bwd_kernel<<<blocks_for((size_t)n * (h / 2) * (w / 2) * (c / 2)), 256, 0, (cudaStream_t)stream>>>(
         static_cast<const __nv_bfloat16*>(gp), static_cast<const __nv_bfloat16*>(cfull), static_cast<const __nv_bfloat16*>(gskip),
-        static_cast<__nv_bfloat16*>(gc), n, h, w, c);
+        static_cast<__nv_bfloat16*>(gc), n, h, w, c, act_kind);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

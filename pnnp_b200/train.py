@@ -43,6 +43,11 @@ class _StaticPacked:
         return self.weight, (None if b is None else b.detach())
 
 
+def archs_x_mode():
+    from . import archs
+    return archs._X_MODE
+
+
 def _desc(src_ptr, dst_ptr, dst_bf16, dims, sstrides, dstrides):
     d = _lib.CopyDesc()
     d.src, d.dst, d.dst_bf16 = src_ptr, dst_ptr, int(dst_bf16)
@@ -150,10 +155,15 @@ class UNetTrainStep:
                 halves = (cin // 2, cin // 2) if (name.endswith("_1") and int(name[4]) >= 6) else (cin,)   # cat([up, skip], 1)
                 c_off = 0
                 for k, ck in enumerate(halves):            # dgrad: [8 - tap][ci][co] <- W[co][c_off + ci][tap]  (180-degree flip)
-                    buf = torch.zeros((9, _pad16(ck), _pad16(co)), dtype=torch.bfloat16, device=self.device)
+                    if ck <= 32 and archs_x_mode():        # narrow output: the x-shift-in-N layout [ky][kx*ck + ci][co], as in the forward
+                        buf = torch.zeros((3, _pad16(3 * ck), _pad16(co)), dtype=torch.bfloat16, device=self.device)
+                        pack.append(_desc(fp(name) + 4 * (c_off * 9 + 8), buf.data_ptr(), 1, (3, 3, ck, co), (-3, -1, 9, cin * 9),
+                                          (buf.shape[1] * buf.shape[2], ck * buf.shape[2], buf.shape[2], 1)))
+                    else:
+                        buf = torch.zeros((9, _pad16(ck), _pad16(co)), dtype=torch.bfloat16, device=self.device)
+                        pack.append(_desc(fp(name) + 4 * (c_off * 9 + 8), buf.data_ptr(), 1, (9, ck, co), (-1, 9, cin * 9),
+                                          (buf.shape[1] * buf.shape[2], buf.shape[2], 1)))
                     self.wd[(name, k)] = buf
-                    pack.append(_desc(fp(name) + 4 * (c_off * 9 + 8), buf.data_ptr(), 1, (9, ck, co), (-1, 9, cin * 9),
-                                      (buf.shape[1] * buf.shape[2], buf.shape[2], 1)))
                     c_off += ck
         def table(descs):
             arr = (_lib.CopyDesc * len(descs))(*descs)
@@ -198,13 +208,15 @@ class UNetTrainStep:
                                         ci_total, dw.shape[-1], self._stream()), "wgrad_nhwc")
 
     # ---------------------------------------------------------------- layer backward passes
-    def _conv3_bwd(self, name, g, out_act, srcs, need_dx, act=_lib.ACT_LEAKY):
-        """g: NHWC bf16 gradient w.r.t. the activated output of conv `name` (modified in place to the pre-activation
-        gradient).  srcs: list of NHWC bf16 inputs (1, or 2 for torch.cat([up, skip], 1)).  Returns input gradients."""
+    def _conv3_bwd(self, name, g, srcs, need_dx, dx_masks=None):
+        """g: NHWC bf16 gradient w.r.t. the PRE-activation output of conv `name` (the producer of g fused this layer's
+        LeakyReLU').  srcs: list of NHWC bf16 inputs (1, or 2 for torch.cat([up, skip], 1)).  dx_masks[k]: activated tensor
+        whose LeakyReLU' is fused into the k-th input gradient (None: the input is not an activation output).
+        Returns the input gradients."""
         m = self.net.get_submodule(name)
         co = m.weight.shape[0]
         n, h, w, _ = g.shape
-        self._act_bwd(g, out_act, self._grad_view(name + ".bias"), act)
+        self._act_bwd(g, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)        # bias gradient = sum over pixels
         ci_total = sum(s.shape[-1] for s in srcs)
         dw = self._dw_view(name)
         c_off = 0
@@ -216,12 +228,15 @@ class UNetTrainStep:
             for k, s in enumerate(srcs):                  # data gradient: the forward kernel on the transposed + flipped weights
                 ck = s.shape[-1]
                 gx = self.scr.get(f"gx_{name}_{k}", (n, h, w, ck))
-                _conv(_lib.CONV3, g, self.wd[(name, k)], None, gx, ck, _lib.ACT_NONE)
+                wd = self.wd[(name, k)]
+                _conv(_lib.CONV3X if wd.shape[0] == 3 else _lib.CONV3, g, wd, None, gx, ck, _lib.ACT_NONE,
+                      mask=None if dx_masks is None else dx_masks[k])
                 gxs.append(gx)
         return gxs
 
     def _convT_bwd(self, name, g_up, x_in):
-        """ConvTranspose2d(2, stride 2) backward: g_up NHWC bf16 [n,2h,2w,co] -> g_in [n,h,w,ci]; dW [ci][co][2][2]; db."""
+        """ConvTranspose2d(2, stride 2) backward: g_up NHWC bf16 [n,2h,2w,co] -> g_in [n,h,w,ci] (times LeakyReLU'(x_in): x_in is an
+        activation output); dW [ci][co][2][2]; db."""
         m = self.net.get_submodule(name)
         ci, co = m.weight.shape[0], m.weight.shape[1]
         n, h, w, _ = x_in.shape
@@ -229,7 +244,7 @@ class UNetTrainStep:
         dw = self._dw_view(name)
         self._wgrad_nhwc(1, g_up, co, x_in, dw, 0, ci)
         gx = self.scr.get("gx_" + name, (n, h, w, ci))
-        _conv(_lib.CONV2S2, g_up, self.wd[name], None, gx, ci, _lib.ACT_NONE)      # [a*2+b][ci][co] = W[ci][co][a][b]
+        _conv(_lib.CONV2S2, g_up, self.wd[name], None, gx, ci, _lib.ACT_NONE, mask=x_in)      # [a*2+b][ci][co] = W[ci][co][a][b]
         return gx
 
     # ---------------------------------------------------------------- the step
@@ -284,12 +299,11 @@ class UNetTrainStep:
                                       g.data_ptr(), self._grad_view("conv10_1.weight").data_ptr(),
                                       self._grad_view("conv10_1.bias").data_ptr(), None, n, h, w, nf, net.out_nc, LK,
                                       self._stream()), "head_bwd")
-        # decoder
+        # decoder (every data gradient that lands on an activation output carries that activation's derivative: `mask`)
         g_skip = {}
         for i in range(9, 5, -1):
-            act = _lib.ACT_NONE if i == 9 else LK            # conv9_2's act' is already applied by the head kernel
-            (g,) = self._conv3_bwd(f"conv{i}_2", g, s[f"c{i}"], [s[f"c{i}a"]], True, act=act)
-            g_up, g_skip[10 - i] = self._conv3_bwd(f"conv{i}_1", g, s[f"c{i}a"], [s[f"u{i}"], s[f"c{10 - i}"]], True)
+            (g,) = self._conv3_bwd(f"conv{i}_2", g, [s[f"c{i}a"]], True, dx_masks=[s[f"c{i}a"]])
+            g_up, g_skip[10 - i] = self._conv3_bwd(f"conv{i}_1", g, [s[f"u{i}"], s[f"c{10 - i}"]], True)
             src = s["c5"] if i == 6 else s[f"c{i - 1}"]
             g = self._convT_bwd(f"upv{i}", g_up, src)
         # encoder
@@ -298,10 +312,10 @@ class UNetTrainStep:
                 ci_ = s[f"c{i}"]
                 gc = self.scr.get(f"g_c{i}", tuple(ci_.shape))
                 L.check(L.lib().pnnp_maxpool_bwd(g.data_ptr(), ci_.data_ptr(), g_skip[i].data_ptr(), gc.data_ptr(),
-                                                 ci_.shape[0], ci_.shape[1], ci_.shape[2], ci_.shape[3], self._stream()), "maxpool_bwd")
+                                                 ci_.shape[0], ci_.shape[1], ci_.shape[2], ci_.shape[3], LK, self._stream()), "maxpool_bwd")
                 g = gc
-            (g,) = self._conv3_bwd(f"conv{i}_2", g, s[f"c{i}"], [s[f"c{i}a"]], True)
-            res = self._conv3_bwd(f"conv{i}_1", g, s[f"c{i}a"], [s[f"in{i}_1"]], i > 1)
+            (g,) = self._conv3_bwd(f"conv{i}_2", g, [s[f"c{i}a"]], True, dx_masks=[s[f"c{i}a"]])
+            res = self._conv3_bwd(f"conv{i}_1", g, [s[f"in{i}_1"]], i > 1)
             if i > 1:
                 g = res[0]
         tab, nd = self._unpack_tab                           # wgrad scratch -> the parameters' gradient layout (one launch)

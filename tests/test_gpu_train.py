@@ -98,8 +98,12 @@ def test_maxpool_backward_with_skip():
     gc = torch.empty((n, h, w, c), dtype=torch.bfloat16, device="cuda")
     gpn, xn, gsn = _nhwc(gp), _nhwc(x.detach()), _nhwc(gs)
     L.check(L.lib().pnnp_maxpool_bwd(gpn.data_ptr(), xn.data_ptr(), gsn.data_ptr(), gc.data_ptr(),
-                                     n, h, w, c, _sp()), "pool_bwd")
+                                     n, h, w, c, L.ACT_NONE, _sp()), "pool_bwd")
     assert torch.equal(_nchw(gc), _bf(x.grad + gs))
+    # fused LeakyReLU'(x): x is the activated output whose pooling is undone
+    L.check(L.lib().pnnp_maxpool_bwd(gpn.data_ptr(), xn.data_ptr(), gsn.data_ptr(), gc.data_ptr(),
+                                     n, h, w, c, L.ACT_LEAKY, _sp()), "pool_bwd")
+    assert torch.equal(_nchw(gc), _bf(_bf(x.grad + gs) * torch.where(x.detach() > 0, 1.0, 0.2)))
 
 
 @pytest.mark.parametrize("ci,co,h,w,n", [(16, 32, 16, 32, 1), (32, 32, 24, 40, 2), (32, 64, 20, 36, 1), (64, 64, 16, 48, 2),
