@@ -278,12 +278,28 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
         // kernel is latency-bound, not issue-bound, and a 4x unrolled body (4 Philox blocks per phase) overflows the
         // instruction cache once the warps of an SM spread over the three phases.
         int n_small = 0, n_large = 0;
+        // all four 128-bit loads of the unit are issued before the first use (one exposed memory latency per unit instead of
+        // four: the first multiply of a freshly loaded pixel was 13 % of all stall samples), and the next unit's lines are
+        // requested into L2 while this unit computes
+        float4 ybuf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + (j * 32 + lane) * 4;
+            ybuf[j] = x < a.w ? __ldcs(reinterpret_cast<const float4*>(a.clean + row_base + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (u + warps_total < units) {
+            const int un = u + warps_total, rown = un / nseg, xn0 = (un - rown * nseg) * kFastUnit;
+            const float* nb = a.clean + (size_t)rown * a.w + xn0 + lane * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (xn0 + (j * 32 + lane) * 4 < a.w) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + j * 128));
+        }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             const int x = x0 + (j * 32 + lane) * 4;
             const bool valid = x < a.w;
             const unsigned m_valid = __ballot_sync(0xffffffffu, valid);
-            const float4 yv = valid ? __ldcs(reinterpret_cast<const float4*>(a.clean + row_base + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 yv = j == 0 ? ybuf[0] : (j == 1 ? ybuf[1] : (j == 2 ? ybuf[2] : ybuf[3]));
             const uint4 b0 = rng.block((g_base + x) >> 2, kStreamElem, 0u);      // (g_base + x) % 4 == 0 on this path
             const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
             const uint32_t ws[4] = {b0.x, b0.y, b0.z, b0.w};
