@@ -33,7 +33,7 @@ constexpr int kWnMaxBoxes = 6, kWnMaxMmas = 3, kWnMaxAtoms = 9, kWnStagesMax = 4
 // (dx, dy) = (ts & 1, ts >> 1); c0 advances with the CTA's M tile (g boxes, 128 channels) or N tile (x boxes, ci_tile channels)
 struct WnBox { int is_x; int c0; int mul; int dx, dy; int by_ts; int smem_off; int bytes; };
 struct WnMma { int a_off, b_off; int n; int lbo_b; int tmem_col; };                  // one MMA per 16-pixel K step
-struct WnAtom { int col, width, tap, ci0; };                                        // accumulator columns -> (tap [+ ts], input channels [+ N tile])
+struct WnAtom { int col, width, tap, ci0, ky_base; };   // rows-by-filter-row mode: row block rb holds ky = ky_base - rb (valid 0..2), tap = kx                                        // accumulator columns -> (tap [+ ts], input channels [+ N tile])
 
 struct WnParams {
     int n_boxes, n_mmas, n_atoms;
@@ -46,6 +46,8 @@ struct WnParams {
     int tiles_x, tiles_y, tiles_total; // pixel tiles of the K range (per image tiles_x * tiles_y)
     int splits, tapsets, n_tiles, ci_tile, tap_by_ts;   // grid = m_tiles * n_tiles * tapsets * splits
     int co;                            // valid accumulator rows of M tile mt: co - 128 * mt
+    int row_block;                     // != 0: accumulator rows are (filter row, co) in blocks of row_block rows, see WnAtom::ky_base
+                                       // (3x3 layers with 32 / 64 output channels)
     int ci_total, co_pad;              // dw scratch geometry [tap][ci_total][co_pad]
     float* dw;
     int tmem_cols;
@@ -157,19 +159,28 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int m0 = mt * 128;
-        const bool row_ok = m0 + row < p.co;
+        int out_row = m0 + row, rb = 0;
+        bool row_ok = out_row < p.co;
+        if (p.row_block) {                                   // rows = (ky, co); row_block is 32 or 64, so rb is warp-uniform
+            rb = row / p.row_block;
+            out_row = row - rb * p.row_block;
+            row_ok = out_row < p.co;
+        }
         mbar_wait(smem_u32(done_bar), 0, p.err, 304);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         for (int t = 0; t < p.n_atoms; ++t) {
             const WnAtom& at = p.atom[t];
-            float* dst = p.dw + ((size_t)(at.tap + (p.tap_by_ts ? ts : 0)) * p.ci_total + at.ci0 + nt * p.ci_tile) * p.co_pad + m0 + row;
+            const int ky = at.ky_base - rb;
+            const bool ok = row_ok && (!p.row_block || (ky >= 0 && ky <= 2));
+            const int tap = p.row_block ? ky * 3 + at.tap : at.tap + (p.tap_by_ts ? ts : 0);
+            float* dst = p.dw + ((size_t)(ok ? tap : 0) * p.ci_total + at.ci0 + nt * p.ci_tile) * p.co_pad + out_row;
             for (int j = 0; j < at.width; j += 16) {
                 uint32_t v[16];
                 if (p.dbg & 4) continue;
                 tc_ld16(taddr + (uint32_t)(at.col + j), v);
                 tc_ld_wait();
-                if (row_ok) {
+                if (ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(j + i) * p.co_pad, __uint_as_float(v[i]));
                 }
@@ -240,12 +251,17 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
 
     const int cw_g = std::min(co, 64), cw_x = std::min(ci, 64);          // channels per TMA box = swizzle span / 2
     const int pitch_a = cw_g * 2, pitch_b = cw_x * 2;
-    const int box_h_x = mode == 0 ? kWnTileH + 2 : kWnTileH;
+    // 3x3 layers with 32 output channels (the full-resolution layers): M = 128 would be 3/4 padding.  There the filter ROW shift
+    // goes to the g side instead — one haloed g box, M blocks = (ky, co) through LBO = 16 pixel rows — and the filter COLUMN
+    // shift to the x side (three boxes, N = (kx, ci)): all nine taps in ONE MMA per 16 pixels, a third of the tensor work.
+    const bool rows_ky = mode == 0 && (co == 32 || co == 64) && ci <= 64 && !getenv("PNNP_WG_NO_ROWS_KY");
+    const int box_h_x = (mode == 0 && !rows_ky) ? kWnTileH + 2 : kWnTileH;
     const int a_box_bytes = kWnPix * pitch_a;                              // one g block: 128 pixels
     const int b_box_bytes = kWnTileW * box_h_x * pitch_b;                  // one x block: 160 (haloed) or 128 pixels
     const int a_region = 128 / cw_g * a_box_bytes;                         // M = 128 rows always addressable (rows >= co are never stored)
     CUtensorMap tmG, tmX;
-    if (int e = make_nhwc_map(&tmG, g, n, mode == 0 ? h : 2 * h, mode == 0 ? w : 2 * w, co_stride, cw_g, kWnTileH, mode == 0 ? 1 : 2)) return e;
+    if (int e = make_nhwc_map(&tmG, g, n, mode == 0 ? h : 2 * h, mode == 0 ? w : 2 * w, co_stride, cw_g, rows_ky ? kWnTileH + 2 : kWnTileH,
+                              mode == 0 ? 1 : 2)) return e;
     if (int e = make_nhwc_map(&tmX, x, n, h, w, ci_stride, cw_x, box_h_x, 1)) return e;
 
     const int tiles_x = (w + kWnTileW - 1) / kWnTileW, tiles_y = (h + kWnTileH - 1) / kWnTileH;
@@ -253,7 +269,7 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
     const int n_tiles = ci / ci_tile, m_tiles = (co + 127) / 128;
     // tap sets: 3x3 with ci <= 32 keeps all nine taps (three dx boxes) in one CTA; otherwise one filter column per CTA;
     // the transposed conv takes one of its four taps per CTA
-    const int tapsets = mode == 1 ? 4 : (ci <= 32 ? 1 : 3);
+    const int tapsets = mode == 1 ? 4 : ((ci <= 32 || rows_ky) ? 1 : 3);
     const int combos = m_tiles * n_tiles * tapsets;
     const int tiles_total = n * tiles_x * tiles_y;
     const int splits = std::max(1, std::min(tiles_total, (2 * sms + combos - 1) / combos));
@@ -266,21 +282,46 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
     p.n_tiles = n_tiles; p.ci_tile = ci_tile; p.tap_by_ts = tapsets > 1 ? 1 : 0;
     p.co = co; p.ci_total = ci_total; p.co_pad = co_pad; p.dw = dw; p.dbg = dbg; p.err = g_wn_err;
     int off = 0, nb = 0, col = 0;
+    if (rows_ky) {
+        WnBox& gb = p.box[nb++];
+        gb.is_x = 0; gb.c0 = 0; gb.mul = 1; gb.dx = 0; gb.dy = -1; gb.by_ts = 0; gb.smem_off = 0;
+        gb.bytes = kWnTileW * (kWnTileH + 2) * pitch_a;                 // haloed in y: tile rows -1 .. 8
+        p.lbo_a = kWnTileW * pitch_a;                                   // M blocks = filter rows: 16 pixel rows apart
+        p.row_block = co;                                               // 32: blocks ky = 2,1,0,(unused); 64: two MMAs (2,1) and (0,unused)
+        const int n_mma = co == 32 ? 1 : 2, blocks_per_mma = 128 / co;
+        // M = 128 rows from the last MMA's first block stay inside the stage
+        off = (((n_mma - 1) * blocks_per_mma * kWnTileW + (blocks_per_mma - 1) * kWnTileW + kWnPix) * pitch_a + 1023) / 1024 * 1024;
+        const int xb = kWnPix * pitch_b;
+        for (int dx = 0; dx < 3; ++dx) {
+            WnBox& bx = p.box[nb++];
+            bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = dx - 1; bx.dy = 0; bx.by_ts = 0; bx.smem_off = off + dx * xb; bx.bytes = xb;
+        }
+        for (int m = 0; m < n_mma; ++m) {
+            WnMma& mm = p.mma[p.n_mmas++];
+            mm.a_off = m * blocks_per_mma * kWnTileW * pitch_a;           // first block of MMA m starts at box row m * blocks_per_mma
+            mm.b_off = off; mm.n = 3 * ci; mm.lbo_b = xb; mm.tmem_col = m * 3 * ci;
+            for (int dx = 0; dx < 3; ++dx)                               // box row r of the haloed g tile <-> ky = 2 - r; tap field = kx
+                p.atom[p.n_atoms++] = WnAtom{m * 3 * ci + dx * ci, ci, dx, ci_off, 2 - m * blocks_per_mma};
+        }
+        col = n_mma * 3 * ci; off += 3 * xb;
+    }
     // g blocks of an M tile (first channel advances by 128 per M tile in the kernel)
-    const int g_blocks = std::min(128, co) / cw_g;
+    const int g_blocks = rows_ky ? 0 : std::min(128, co) / cw_g;
     for (int b = 0; b < g_blocks; ++b) {
         WnBox& bx = p.box[nb++];
         bx.is_x = 0; bx.c0 = b * cw_g; bx.smem_off = b * a_box_bytes; bx.bytes = a_box_bytes;
         bx.mul = mode == 0 ? 1 : 2; bx.dx = 0; bx.dy = 0; bx.by_ts = mode == 0 ? 0 : 2;      // transposed conv: rows 2y + a, cols 2x + b
     }
-    off = a_region;
-    if (mode == 0 && ci <= 32) {                                       // all nine taps: three filter-column boxes, dy folded into N
+    if (!rows_ky) off = a_region;
+    if (rows_ky) {
+        // planned above
+    } else if (mode == 0 && ci <= 32) {                                // all nine taps: three filter-column boxes, dy folded into N
         for (int dx = 0; dx < 3; ++dx) {
             WnBox& bx = p.box[nb++];
             bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = dx - 1; bx.dy = -1; bx.by_ts = 0; bx.smem_off = off; bx.bytes = b_box_bytes;
             WnMma& mm = p.mma[p.n_mmas++];
             mm.a_off = 0; mm.b_off = off; mm.n = 3 * ci; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = col;
-            for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{col + dy * ci, ci, dy * 3 + dx, ci_off};
+            for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{col + dy * ci, ci, dy * 3 + dx, ci_off, 0};
             col += 3 * ci; off += b_box_bytes;
         }
     } else if (mode == 0 && ci == 64) {                                // one filter column (ts) per CTA, dy folded into N = 192
@@ -288,7 +329,7 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
         bx.is_x = 1; bx.c0 = 0; bx.mul = 1; bx.dx = 0; bx.dy = -1; bx.by_ts = 1; bx.smem_off = off; bx.bytes = b_box_bytes;
         WnMma& mm = p.mma[p.n_mmas++];
         mm.a_off = 0; mm.b_off = off; mm.n = 192; mm.lbo_b = kWnTileW * pitch_b; mm.tmem_col = 0;
-        for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{dy * 64, 64, dy * 3, ci_off};
+        for (int dy = 0; dy < 3; ++dy) p.atom[p.n_atoms++] = WnAtom{dy * 64, 64, dy * 3, ci_off, 0};
         col = 192; off += b_box_bytes;
     } else if (mode == 0) {                                            // one filter column per CTA, 128 input channels, one MMA per dy
         for (int c = 0; c < 2; ++c) {
@@ -298,7 +339,7 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
         for (int dy = 0; dy < 3; ++dy) {
             WnMma& mm = p.mma[p.n_mmas++];
             mm.a_off = 0; mm.b_off = off + dy * kWnTileW * pitch_b; mm.n = 128; mm.lbo_b = b_box_bytes; mm.tmem_col = dy * 128;
-            for (int c = 0; c < 2; ++c) p.atom[p.n_atoms++] = WnAtom{dy * 128 + c * 64, 64, dy * 3, ci_off + c * 64};
+            for (int c = 0; c < 2; ++c) p.atom[p.n_atoms++] = WnAtom{dy * 128 + c * 64, 64, dy * 3, ci_off + c * 64, 0};
         }
         col = 384; off += 2 * b_box_bytes;
     } else {                                                           // transposed conv: one tap (ts) per CTA
@@ -306,7 +347,7 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
         for (int c = 0; c < blocks; ++c) {
             WnBox& bx = p.box[nb++];
             bx.is_x = 1; bx.c0 = c * cw_x; bx.mul = 1; bx.dx = 0; bx.dy = 0; bx.by_ts = 0; bx.smem_off = off + c * b_box_bytes; bx.bytes = b_box_bytes;
-            p.atom[p.n_atoms++] = WnAtom{c * cw_x, cw_x, 0, ci_off + c * cw_x};
+            p.atom[p.n_atoms++] = WnAtom{c * cw_x, cw_x, 0, ci_off + c * cw_x, 0};
         }
         WnMma& mm = p.mma[p.n_mmas++];
         mm.a_off = 0; mm.b_off = off; mm.n = ci_tile; mm.lbo_b = b_box_bytes; mm.tmem_col = 0;
