@@ -42,7 +42,10 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 // ---------------------------------------------------------------- 1x1 head backward (out_nc <= 4, cin <= 64)
 // gpred: NCHW fp32 [n][co][h][w]; act: NHWC bf16 [n,h,w,cin] = LeakyReLU output feeding the head;
 // gact (out): NHWC bf16 gradient w.r.t. the PRE-activation of that layer (already multiplied by act');
-// dW[co][cin], db[co]: fp32, accumulated with atomics.
+// dW[co][cin], db[co], dbias_prev[cin] (bias gradient of the layer feeding the head): fp32, accumulated with atomics.
+// Work item = (pixel, group of 8 channels): one 16-byte load of the activation, one 16-byte store of the gradient; a thread
+// keeps its channel group over all its pixels (grid * 256 is a multiple of cin / 8) and accumulates its 4 x 8 slice of dW, its 8
+// bias sums (and db in group 0) in registers; lanes with the same group are combined by shuffles before the shared / global atomics.
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gpred, const __nv_bfloat16* __restrict__ act,
                                                        const float* __restrict__ W, __nv_bfloat16* __restrict__ gact,
                                                        float* dW, float* db, float* dbias_prev, int n, int h, int w, int cin,
@@ -51,40 +54,68 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     float* s_dw = s_acc; float* s_db = s_acc + co * cin; float* s_dbp = s_db + co;
     for (int i = threadIdx.x; i < co * cin + co + cin; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
-    // work item = (pixel, channel pair); 256 * gridDim is a multiple of cin/2, so a thread keeps its channel pair and
-    // accumulates its slice of dW / db / dbias in registers over all of its pixels
-    const int cp_count = cin / 2;
-    const size_t plane = (size_t)h * w, total = (size_t)n * plane * cp_count;
+    const int groups = cin / 8;                      // 1, 2, 4 or 8: divides 32, so a warp holds whole pixels
+    const size_t plane = (size_t)h * w, total = (size_t)n * plane * groups;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = (int)(tid % cp_count) * 2;
-    float w0[4], w1[4], adw0[4] = {0, 0, 0, 0}, adw1[4] = {0, 0, 0, 0}, adb[4] = {0, 0, 0, 0}, abp0 = 0.f, abp1 = 0.f;
-    for (int o = 0; o < 4; ++o) { w0[o] = o < co ? W[o * cin + c] : 0.f; w1[o] = o < co ? W[o * cin + c + 1] : 0.f; }
+    const int grp = (int)(tid % groups), c = grp * 8;
+    float wv[4][8], adw[4][8], adb[4] = {0.f, 0.f, 0.f, 0.f}, abp[8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wv[o][k] = o < co ? W[o * cin + c + k] : 0.f; adw[o][k] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) abp[k] = 0.f;
+    const float slope = act_kind == 1 ? 0.2f : (act_kind == 2 ? 0.f : 1.f);
     for (size_t i = tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t pix = i / cp_count;
+        const size_t pix = i / groups;
         const size_t img = pix / plane, off = pix - img * plane;
         float gp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int o = 0; o < 4; ++o) if (o < co) gp[o] = gpred[(img * co + o) * plane + off];
-        const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(act + pix * cin + c);
-        const float a0 = __low2float(a2), a1 = __high2float(a2);
-        float g0 = 0.f, g1 = 0.f;
+        const uint4 av = *reinterpret_cast<const uint4*>(act + pix * cin + c);
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+        uint32_t gw[4];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            g0 = fmaf(gp[o], w0[o], g0); g1 = fmaf(gp[o], w1[o], g1);
-            adw0[o] = fmaf(gp[o], a0, adw0[o]); adw1[o] = fmaf(gp[o], a1, adw1[o]);
-            if (c == 0) adb[o] += gp[o];
+        for (int k2 = 0; k2 < 4; ++k2) {
+            const float a0 = __uint_as_float(aw[k2] << 16), a1 = __uint_as_float(aw[k2] & 0xFFFF0000u);
+            float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                g0 = fmaf(gp[o], wv[o][2 * k2], g0); g1 = fmaf(gp[o], wv[o][2 * k2 + 1], g1);
+                adw[o][2 * k2] = fmaf(gp[o], a0, adw[o][2 * k2]); adw[o][2 * k2 + 1] = fmaf(gp[o], a1, adw[o][2 * k2 + 1]);
+            }
+            g0 *= a0 > 0.f ? 1.f : slope; g1 *= a1 > 0.f ? 1.f : slope;
+            abp[2 * k2] += g0; abp[2 * k2 + 1] += g1;      // pre-activation gradient: what the previous conv's bias gradient sums
+            const __nv_bfloat162 hb = __floats2bfloat162_rn(g0, g1);
+            gw[k2] = *reinterpret_cast<const uint32_t*>(&hb);
         }
-        if (act_kind == 1) { g0 *= a0 > 0.f ? 1.f : 0.2f; g1 *= a1 > 0.f ? 1.f : 0.2f; }
-        else if (act_kind == 2) { g0 = a0 > 0.f ? g0 : 0.f; g1 = a1 > 0.f ? g1 : 0.f; }
-        abp0 += g0; abp1 += g1;       // pre-activation gradient: what the previous conv's bias gradient sums
-        *reinterpret_cast<__nv_bfloat162*>(gact + pix * cin + c) = __floats2bfloat162_rn(g0, g1);
-    }
+        if (grp == 0) {
 #pragma unroll
-    for (int o = 0; o < 4; ++o) if (o < co) {
-        atomicAdd(&s_dw[o * cin + c], adw0[o]); atomicAdd(&s_dw[o * cin + c + 1], adw1[o]);
-        if (c == 0) atomicAdd(&s_db[o], adb[o]);
+            for (int o = 0; o < 4; ++o) adb[o] += gp[o];
+        }
+        *reinterpret_cast<uint4*>(gact + pix * cin + c) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
     }
-    atomicAdd(&s_dbp[c], abp0); atomicAdd(&s_dbp[c + 1], abp1);
+    // lanes l, l + groups, l + 2 groups, ... hold the same channel group: combine them
+    for (int o = groups; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) adw[q][k] += __shfl_xor_sync(0xffffffffu, adw[q][k], o);
+            adb[q] += __shfl_xor_sync(0xffffffffu, adb[q], o);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) abp[k] += __shfl_xor_sync(0xffffffffu, abp[k], o);
+    }
+    if ((int)(threadIdx.x & 31) < groups) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) if (o < co) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&s_dw[o * cin + c + k], adw[o][k]);
+            if (grp == 0) atomicAdd(&s_db[o], adb[o]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&s_dbp[c + k], abp[k]);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < co * cin; i += blockDim.x) atomicAdd(&dW[i], s_dw[i]);
     for (int i = threadIdx.x; i < co; i += blockDim.x) atomicAdd(&db[i], s_db[i]);
@@ -134,42 +165,55 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(__nv_bfloat16* __rest
 }
 
 // ---------------------------------------------------------------- 2x2 max-pool backward (+ skip-connection gradient)
-// gc[n,h,w,c] = (gskip ? gskip : 0) + gp[n,h/2,w/2,c] at the first arg-max of each window (row-major scan order, as torch)
+// gc[n,h,w,c] = (gskip ? gskip : 0) + gp[n,h/2,w/2,c] at the first arg-max of each window (row-major scan order, as torch),
+// optionally times act'(cfull).  Work item = (pooled pixel, 8 channels): 16-byte loads / stores throughout.
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ gp, const __nv_bfloat16* __restrict__ cfull,
                                                           const __nv_bfloat16* __restrict__ gskip, __nv_bfloat16* __restrict__ gc,
                                                           int n, int h, int w, int c, int act_kind) {
-    const int ho = h / 2, wo = w / 2, c2 = c / 2;
-    const size_t total = (size_t)n * ho * wo * c2;
+    const int ho = h / 2, wo = w / 2, c8 = c / 8;
+    const size_t total = (size_t)n * ho * wo * c8;
+    const float sl = act_kind == 1 ? 0.2f : 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int cc = (int)(i % c2);
-        size_t r = i / c2;
+        const int cc = (int)(i % c8);
+        size_t r = i / c8;
         const int xo = (int)(r % wo); r /= wo;
         const int yo = (int)(r % ho);
         const int img = (int)(r / ho);
-        const size_t base = (((size_t)img * h + 2 * yo) * w + 2 * xo) * c + cc * 2;
+        const size_t base = (((size_t)img * h + 2 * yo) * w + 2 * xo) * c + cc * 8;
         const size_t idx[4] = {base, base + c, base + (size_t)w * c, base + (size_t)w * c + c};
-        float v0[4], v1[4];
+        uint4 cv[4], sv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(cfull + idx[k]);
-            v0[k] = __low2float(t); v1[k] = __high2float(t);
+            cv[k] = *reinterpret_cast<const uint4*>(cfull + idx[k]);
+            sv[k] = gskip ? *reinterpret_cast<const uint4*>(gskip + idx[k]) : make_uint4(0u, 0u, 0u, 0u);
         }
-        int a0 = 0, a1 = 0;
+        const uint4 gv = *reinterpret_cast<const uint4*>(gp + (((size_t)img * ho + yo) * wo + xo) * c + cc * 8);
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        uint32_t ow[4][4];
 #pragma unroll
-        for (int k = 1; k < 4; ++k) { if (v0[k] > v0[a0]) a0 = k; if (v1[k] > v1[a1]) a1 = k; }
-        const __nv_bfloat162 gpv = *reinterpret_cast<const __nv_bfloat162*>(gp + (((size_t)img * ho + yo) * wo + xo) * c + cc * 2);
-        const float g0 = __low2float(gpv), g1 = __high2float(gpv);
+        for (int q = 0; q < 4; ++q) {                         // channel pair q of the group
+            float v0[4], v1[4], s0[4], s1[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float s0 = 0.f, s1 = 0.f;
-            if (gskip) { const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(gskip + idx[k]); s0 = __low2float(t); s1 = __high2float(t); }
-            __nv_bfloat162 o = __floats2bfloat162_rn(s0 + (k == a0 ? g0 : 0.f), s1 + (k == a1 ? g1 : 0.f));
-            if (act_kind) {         // fused act'(cfull): the sum is rounded to bf16 first, as when the two steps were separate kernels
-                const float sl = act_kind == 1 ? 0.2f : 0.f;
-                o = __floats2bfloat162_rn(__low2float(o) * (v0[k] > 0.f ? 1.f : sl), __high2float(o) * (v1[k] > 0.f ? 1.f : sl));
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t cw = q == 0 ? cv[k].x : (q == 1 ? cv[k].y : (q == 2 ? cv[k].z : cv[k].w));
+                const uint32_t sw = q == 0 ? sv[k].x : (q == 1 ? sv[k].y : (q == 2 ? sv[k].z : sv[k].w));
+                v0[k] = __uint_as_float(cw << 16); v1[k] = __uint_as_float(cw & 0xFFFF0000u);
+                s0[k] = __uint_as_float(sw << 16); s1[k] = __uint_as_float(sw & 0xFFFF0000u);
             }
-            *reinterpret_cast<__nv_bfloat162*>(gc + idx[k]) = o;
+            int a0 = 0, a1 = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) { if (v0[k] > v0[a0]) a0 = k; if (v1[k] > v1[a1]) a1 = k; }
+            const float g0 = __uint_as_float(gw[q] << 16), g1 = __uint_as_float(gw[q] & 0xFFFF0000u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 o = __floats2bfloat162_rn(s0[k] + (k == a0 ? g0 : 0.f), s1[k] + (k == a1 ? g1 : 0.f));
+                if (act_kind)           // fused act'(cfull): the sum is rounded to bf16 first, as when the two steps were separate kernels
+                    o = __floats2bfloat162_rn(__low2float(o) * (v0[k] > 0.f ? 1.f : sl), __high2float(o) * (v1[k] > 0.f ? 1.f : sl));
+                ow[k][q] = *reinterpret_cast<const uint32_t*>(&o);
+            }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(gc + idx[k]) = make_uint4(ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
     }
 }
 
@@ -205,9 +249,10 @@ extern "C" int pnnp_l1_loss(const float* pred, const float* hr, float* gpred, si
 
 extern "C" int pnnp_head_bwd(const float* gpred, const void* act, const float* W, void* gact, float* dW, float* db,
                              float* dbias_prev, int n, int h, int w, int cin, int co, int act_kind, void* stream) {
-    if (!gpred || !act || !W || !gact || !dW || !db || co < 1 || co > 4 || cin > 64 || (cin & 1)) return fail("head_bwd: bad arguments");
+    if (!gpred || !act || !W || !gact || !dW || !db || co < 1 || co > 4 || (cin != 8 && cin != 16 && cin != 32 && cin != 64))
+        return fail("head_bwd: bad arguments (1..4 outputs, 8/16/32/64 input channels)");
     const size_t smem = sizeof(float) * (size_t)(co * cin + co + cin);
-    head_bwd_kernel<<<blocks_for((size_t)n * h * w * (cin / 2)), 256, smem, (cudaStream_t)stream>>>(
+    head_bwd_kernel<<<blocks_for((size_t)n * h * w * (cin / 8)), 256, smem, (cudaStream_t)stream>>>(
         gpred, static_cast<const __nv_bfloat16*>(act), W, static_cast<__nv_bfloat16*>(gact), dW, db, dbias_prev, n, h, w, cin, co, act_kind);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
@@ -231,8 +276,8 @@ extern "C" int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t 
 
 extern "C" int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c, int act_kind,
                                 void* stream) {
-    if (!gp || !cfull || !gc || (h & 1) || (w & 1) || (c & 1)) return fail("maxpool_bwd: bad arguments");
-    maxpool_bwd_kernel<<<blocks_for((size_t)n * (h / 2) * (w / 2) * (c / 2)), 256, 0, (cudaStream_t)stream>>>(
+    if (!gp || !cfull || !gc || (h & 1) || (w & 1) || (c & 7)) return fail("maxpool_bwd: bad arguments (even h, w; c % 8 == 0)");
+    maxpool_bwd_kernel<<<blocks_for((size_t)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
         static_cast<const __nv_bfloat16*>(gp), static_cast<const __nv_bfloat16*>(cfull), static_cast<const __nv_bfloat16*>(gskip),
         static_cast<__nv_bfloat16*>(gc), n, h, w, c, act_kind);
     count_launch();

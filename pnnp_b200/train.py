@@ -208,7 +208,7 @@ class UNetTrainStep:
                                         ci_total, dw.shape[-1], self._stream()), "wgrad_nhwc")
 
     # ---------------------------------------------------------------- layer backward passes
-    def _conv3_bwd(self, name, g, srcs, need_dx, dx_masks=None):
+    def _conv3_bwd(self, name, g, srcs, need_dx, dx_masks=None, bias_done=False):
         """g: NHWC bf16 gradient w.r.t. the PRE-activation output of conv `name` (the producer of g fused this layer's
         LeakyReLU').  srcs: list of NHWC bf16 inputs (1, or 2 for torch.cat([up, skip], 1)).  dx_masks[k]: activated tensor
         whose LeakyReLU' is fused into the k-th input gradient (None: the input is not an activation output).
@@ -216,7 +216,8 @@ class UNetTrainStep:
         m = self.net.get_submodule(name)
         co = m.weight.shape[0]
         n, h, w, _ = g.shape
-        self._act_bwd(g, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)        # bias gradient = sum over pixels
+        if not bias_done:
+            self._act_bwd(g, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)    # bias gradient = sum over pixels
         ci_total = sum(s.shape[-1] for s in srcs)
         dw = self._dw_view(name)
         c_off = 0
@@ -297,12 +298,13 @@ class UNetTrainStep:
         w10 = m10.weight.detach().reshape(net.out_nc, nf).to(torch.bfloat16).float()      # the forward multiplied by bf16 weights
         L.check(L.lib().pnnp_head_bwd(gpred.data_ptr(), s["c9"].data_ptr(), w10.data_ptr(),
                                       g.data_ptr(), self._grad_view("conv10_1.weight").data_ptr(),
-                                      self._grad_view("conv10_1.bias").data_ptr(), None, n, h, w, nf, net.out_nc, LK,
+                                      self._grad_view("conv10_1.bias").data_ptr(), self._grad_view("conv9_2.bias").data_ptr(),
+                                      n, h, w, nf, net.out_nc, LK,
                                       self._stream()), "head_bwd")
         # decoder (every data gradient that lands on an activation output carries that activation's derivative: `mask`)
         g_skip = {}
         for i in range(9, 5, -1):
-            (g,) = self._conv3_bwd(f"conv{i}_2", g, [s[f"c{i}a"]], True, dx_masks=[s[f"c{i}a"]])
+            (g,) = self._conv3_bwd(f"conv{i}_2", g, [s[f"c{i}a"]], True, dx_masks=[s[f"c{i}a"]], bias_done=(i == 9))   # head kernel summed it
             g_up, g_skip[10 - i] = self._conv3_bwd(f"conv{i}_1", g, [s[f"u{i}"], s[f"c{10 - i}"]], True)
             src = s["c5"] if i == 6 else s[f"c{i - 1}"]
             g = self._convT_bwd(f"upv{i}", g_up, src)
