@@ -290,6 +290,7 @@ def run_gpu_arm(args, name, wl):
     except Exception:
         pass
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's own log lines (version banner) must not land on stdout
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():

@@ -67,6 +67,8 @@ const char* pnnp_last_error(void);
 int pnnp_abi_version(void);
 /* number of kernels this library has launched in the calling process (for gpu_launches) */
 uint64_t pnnp_launch_count(void);
+/* adds n to that counter: the caller replayed a CUDA graph holding n of this library's kernels */
+void pnnp_count_graph_launches(uint64_t n);
 
 /* P1 — raw2bayer(raw, wp, bl, norm, clip, bias)                 utils/isp_ops.py:84-96
  * raw: n frames of H x W (uint16 or float32), out: n x 4 x H/2 x W/2 float32, plane order
@@ -233,6 +235,10 @@ int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void*
 int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, const void* x, int ci, int ci_stride, int n, int h, int w,
                     float* dw, int ci_off, int ci_total, int co_pad, void* stream);
 int pnnp_wgrad_nhwc_pipeline_error(void);
+/* Same update with the learning rate and the step count in device memory (state_dev[0] = lr, state_dev[1] = steps taken, as
+ * floats; the call increments the step first), so a captured CUDA graph of the training step stays valid across steps. */
+int pnnp_adam_step_dev(float* p, const float* g, float* m, float* v, size_t total, float* state_dev, float b1, float b2,
+                       float eps, float gscale, void* stream);
 /* Batched strided copy / cast: desc i copies dim[0] x dim[1] x dim[2] x dim[3] fp32 elements src[sum idx*sstride] ->
  * dst[sum idx*dstride] (fp32, or bf16 when dst_bf16).  Strides in elements, may be negative (src / dst point at index 0).
  * One launch for all descriptors (device array): weight packing for the tensor-core layouts and gradient re-layout. */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "pnnp_last_error": (C.c_char_p, []),
     "pnnp_abi_version": (_i, []),
     "pnnp_launch_count": (_u64, []),
+    "pnnp_count_graph_launches": (None, [_u64]),
     "pnnp_pack_norm_u16": (_i, [_vp, _vp, _i, _i, _i, _d, C.POINTER(C.c_double), _i, _i, _vp]),
     "pnnp_pack_norm_f32": (_i, [_vp, _vp, _i, _i, _i, _d, C.POINTER(C.c_double), _i, _i, _vp]),
     "pnnp_pack_norm_dark_u16": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, C.c_double, C.POINTER(C.c_double), _i, _i, C.c_double, _i, C.c_double, _i, _vp]),
@@ -66,6 +67,7 @@ SIGNATURES = {
     "pnnp_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pnnp_wgrad_nhwc": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "pnnp_wgrad_nhwc_pipeline_error": (_i, []),
+    "pnnp_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _f, _f, _f, _f, _vp]),
     "pnnp_strided_copy_batch": (_i, [_vp, _i, _i, _vp]),
     "pnnp_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, _i, _f, _vp]),
     "pnnp_crop_aug": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]),

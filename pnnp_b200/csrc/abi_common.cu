@@ -21,3 +21,5 @@ void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxe
 extern "C" const char* pnnp_last_error(void) { return pnnp::g_err; }
 extern "C" int pnnp_abi_version(void) { return PNNP_ABI_VERSION; }
 extern "C" uint64_t pnnp_launch_count(void) { return pnnp::g_launches.load(); }
+// kernels launched through a replayed CUDA graph (captured launches are counted once, at capture time)
+extern "C" void pnnp_count_graph_launches(uint64_t n) { pnnp::count_launch(n); }

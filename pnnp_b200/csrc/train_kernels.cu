@@ -231,6 +231,24 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// Graph-friendly Adam: the step count and the learning rate live in device memory (state[0] = lr, state[1] = step as float), so a
+// captured CUDA graph of the whole training step can be replayed while both change.  A one-thread kernel advances the step.
+__global__ void adam_tick_kernel(float* state) { state[1] += 1.0f; }
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, size_t total, const float* __restrict__ state, float b1,
+                                                       float b2, float eps, float gscale) {
+    const float lr = state[0], t = state[1];
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
 static int blocks_for(size_t items) { return (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, 148 * 8)); }
 
 }  // namespace pnnp
@@ -318,6 +336,16 @@ __global__ void __launch_bounds__(256) strided_copy_batch_kernel(const pnnp_copy
     }
 }
 }  // namespace pnnp
+
+extern "C" int pnnp_adam_step_dev(float* p, const float* g, float* m, float* v, size_t total, float* state_dev, float b1, float b2,
+                                  float eps, float gscale, void* stream) {
+    if (!p || !g || !m || !v || !state_dev) return pnnp::fail("adam_step_dev: bad arguments");
+    pnnp::adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state_dev);
+    pnnp::adam_dev_kernel<<<pnnp::blocks_for(total), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, total, state_dev, b1, b2, eps, gscale);
+    pnnp::count_launch(2);
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int pnnp_strided_copy_batch(const pnnp_copy_desc* descs_dev, int n_desc, int blocks_per_desc, void* stream) {
     if (!descs_dev || n_desc < 1 || blocks_per_desc < 1) return pnnp::fail("strided_copy_batch: bad arguments");

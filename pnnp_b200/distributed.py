@@ -21,6 +21,7 @@ def init_from_env(device_index=None):
     if torch.cuda.is_available():
         idx = int(os.environ.get("LOCAL_RANK", "0")) if device_index is None else device_index
         torch.cuda.set_device(idx)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner off stdout (bench lines are parsed from it)
         dist.init_process_group("nccl", device_id=torch.device("cuda", idx))
     else:
         dist.init_process_group("gloo")

@@ -13,7 +13,10 @@ Here the backward pass is explicit (no autograd graph, no eager fallback):
 Parameters, gradients and Adam moments live in flat fp32 buffers (one all-reduce per step under DDP);
 activations and activation gradients are NHWC bf16.
 """
+import os
+
 import torch
+
 from . import _lib, distributed as D
 from .archs import UNetSeeInDark, _conv, _pad16, _to_nhwc16
 
@@ -81,7 +84,12 @@ class UNetTrainStep:
         self.device = next(net.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("pnnp_b200: the training step needs a CUDA device (no CPU fallback)")
-        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.betas, self.eps, self.t = betas, eps, 0
+        # learning rate and step count in device memory: the whole step is replayed as one CUDA graph (see step())
+        self.adam_state = torch.tensor([float(lr), 0.0], dtype=torch.float32, device=self.device)
+        self._lr = float(lr)
+        self.use_graph = os.environ.get("PNNP_TRAIN_GRAPH", "1") != "0"
+        self._graphs = {}
         # flat fp32 parameter / gradient / moment buffers; the module's parameters become views of the flat buffer
         params = list(net.named_parameters())
         total = sum(p.numel() for _, p in params)
@@ -323,18 +331,57 @@ class UNetTrainStep:
         tab, nd = self._unpack_tab                           # wgrad scratch -> the parameters' gradient layout (one launch)
         L.check(L.lib().pnnp_strided_copy_batch(tab.data_ptr(), nd, 48, self._stream()), "unpack gradients")
 
-    def step(self, lr_crops, hr_crops, grad_allreduce=True):
-        """One optimisation step on (noisy, clean) crops (CUDA fp32 NCHW).  Returns the loss as a 0-d CUDA tensor."""
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        if float(value) != self._lr:
+            self._lr = float(value)
+            self.adam_state[0:1].fill_(self._lr)
+
+    def _step_body(self, lr_crops, hr, grad_allreduce):
         pred, saved = self.forward(lr_crops)
-        hr = hr_crops.float().contiguous()
         gpred = self.scr.get("gpred", tuple(pred.shape), torch.float32)
         L.check(L.lib().pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gpred.data_ptr(), pred.numel(), self.loss_sum.data_ptr(),
                                      self._stream()), "l1_loss")
         self.backward(gpred, saved)
         gscale = D.allreduce_mean_(self.flat_g) if grad_allreduce else 1.0   # DDP: average of the per-rank mean losses
-        self.t += 1
-        L.check(L.lib().pnnp_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                       self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.t, gscale,
-                                       self._stream()), "adam_step")
+        L.check(L.lib().pnnp_adam_step_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                           self.flat_p.numel(), self.adam_state.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                                           gscale, self._stream()), "adam_step")
         self.refresh_packed()                                           # weights changed in place: re-pack for the next forward
-        return (self.loss_sum / pred.numel()).float()[0]
+        return pred
+
+    def step(self, lr_crops, hr_crops, grad_allreduce=True):
+        """One optimisation step on (noisy, clean) crops (CUDA fp32 NCHW).  Returns the loss as a 0-d CUDA tensor.
+
+        The step is a fixed sequence of ~110 kernels on fixed buffers, so after one eager step per input shape (allocations,
+        tensor maps) it is captured into a CUDA graph and replayed: the inputs are copied into static buffers first, the
+        learning rate and Adam's step count are read from device memory, the gradient all-reduce is part of the graph.  With
+        eight ranks sharing a host the eager step is bound by launch overhead (6.4 ms against 5.1 ms of kernels)."""
+        key = (tuple(lr_crops.shape), bool(grad_allreduce))
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = {"lr": torch.empty_like(lr_crops, dtype=torch.float32).contiguous(),
+                                      "hr": torch.empty_like(hr_crops, dtype=torch.float32).contiguous(), "graph": None, "calls": 0}
+        st["lr"].copy_(lr_crops)
+        st["hr"].copy_(hr_crops)
+        self.t += 1
+        if st["graph"] is not None:
+            st["graph"].replay()
+            L.lib().pnnp_count_graph_launches(st["launches"])
+        elif self.use_graph and st["calls"] >= 1:                        # second call with this shape: capture (capturing only
+            torch.cuda.synchronize(self.device)                         # records the work, so the graph is replayed right after)
+            l0 = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body(st["lr"], st["hr"], grad_allreduce)
+            st["launches"] = _lib.launch_count() - l0
+            st["graph"] = g
+            g.replay()
+        else:
+            self._step_body(st["lr"], st["hr"], grad_allreduce)
+        st["calls"] += 1
+        return (self.loss_sum / st["lr"].numel()).float()[0]

@@ -371,3 +371,26 @@ def test_training_reduces_loss_like_the_reference_loop():
     with torch.no_grad():
         out = net.eval()(lr_in)
     assert (out - O.unet_forward(lr_in, {k: v for k, v in net.state_dict().items()})).abs().max().item() < 1e-2
+
+
+def test_graph_replay_takes_the_same_steps_as_eager_launches():
+    """The captured CUDA graph of a step (device-side learning rate / step count) == the same kernels launched one by one; the
+    learning rate can change between replays."""
+    outs = {}
+    for use_graph in (False, True):
+        net, lr_in, hr = _make(n=2, h=64, w=64, seed=5)
+        net.conv10_1.bias.data.fill_(0.05)
+        ts = train.UNetTrainStep(net, lr=1e-3)
+        ts.use_graph = use_graph
+        losses = []
+        for i in range(6):
+            if i == 3:
+                ts.lr = 5e-4
+            losses.append(ts.step(lr_in, hr).item())
+        _ok()
+        assert (ts._graphs[((2, 4, 64, 64), True)]["graph"] is not None) == use_graph
+        assert abs(ts.adam_state[1].item() - 6.0) < 1e-6 and abs(ts.adam_state[0].item() - 5e-4) < 1e-9
+        outs[use_graph] = (losses, ts.flat_p.clone())
+    assert np.allclose(outs[False][0], outs[True][0], rtol=1e-4, atol=1e-6), outs
+    # split-K / bias sums use fp32 atomics, so the two runs agree to summation order, not bit for bit
+    assert (outs[False][1] - outs[True][1]).abs().max().item() < 2e-4
