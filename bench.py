@@ -290,8 +290,19 @@ def run_gpu_arm(args, name, wl):
     except Exception:
         pass
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's own log lines (version banner) must not land on stdout
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout carries the one JSON line,
+        # so file descriptor 1 points at stderr while the process group and its first collective are set up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:
@@ -328,7 +339,8 @@ def run_gpu_arm(args, name, wl):
         net = P.UNetSeeInDark(ARCH).to(device)
         P.initialize_weights(net)
         trainer = UNetTrainStep(net, lr=1e-4)
-        clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2
+        trainer.use_graph = os.environ.get("PNNP_TRAIN_GRAPH", "1") != "0"     # CUDA-graph replay of the step at every N (8 ranks
+        clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2     # launching eagerly from one host: 6.4 ms; replayed: 5.2)
         np.random.seed(1997 + rank)
         params = [P.sample_params("SonyA7S2") for _ in range(n)]
         table = P.ParamTable(params, device)
@@ -490,6 +502,17 @@ def run_gpu_arm(args, name, wl):
             line["cpu_baseline"] = cpu_baseline(name, wl)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if name == "train_step":
+            # A process group whose all-reduce was captured into live CUDA graphs did not shut down cleanly in the r01 8-GPU run
+            # (destroy_process_group never returned after the JSON line was out): drop the graphs, meet at a barrier, and leave
+            # without the NCCL teardown.
+            trainer._graphs.clear()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -88,7 +88,11 @@ class UNetTrainStep:
         # learning rate and step count in device memory: the whole step is replayed as one CUDA graph (see step())
         self.adam_state = torch.tensor([float(lr), 0.0], dtype=torch.float32, device=self.device)
         self._lr = float(lr)
-        self.use_graph = os.environ.get("PNNP_TRAIN_GRAPH", "1") != "0"
+        # CUDA-graph replay of the step: on by default for a single process; under torch.distributed the captured all-reduce works
+        # (r01, 8 GPUs: 5.2 ms against 6.4 ms eager) but the process group then has to be left without destroy_process_group
+        # (bench.py does), so multi-rank callers opt in with PNNP_TRAIN_GRAPH=1 or `step.use_graph = True`
+        env = os.environ.get("PNNP_TRAIN_GRAPH")
+        self.use_graph = (env != "0") if env is not None else (D.world()[1] == 1)
         self._graphs = {}
         # flat fp32 parameter / gradient / moment buffers; the module's parameters become views of the flat buffer
         params = list(net.named_parameters())
