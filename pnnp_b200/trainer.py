@@ -29,7 +29,7 @@ from .datasets import Raw_Dataset, Synthetic_ELD_Dataset, Synthetic_IMX686_Datas
 from .metrics import eval_partial_sums, finish_metrics
 from .noise import synthesize_batch
 from .noise_params import HALF_CLIP
-from .utils import AverageMeter, load_weights, log, tensor_dim5to4
+from .utils import AverageMeter, load_weights, log, lr_lambda_from_hyper, tensor_dim5to4
 
 
 class BaseParser():
@@ -217,29 +217,9 @@ class SID_Trainer(Base_Trainer):
 
     # -- T1: the synthetic-pair training loop of trainer_SID.py:74-180 on the explicit B200 training step
     def get_lr_lambda_func(self):
-        """base_trainer.py:33-43,141-162."""
-        import math
-        num_of_epochs = self.hyper['stop_epoch'] - self.hyper['last_epoch']
-        step_size, T, base = self.hyper['step_size'], self.hyper.get('T', 1), self.hyper['learning_rate']
-        period = max(1, num_of_epochs // T)
-
-        def cos_lr(step, peak=step_size, ratio=0.2):
-            t, decay, step = step // period, 2 ** (step // period), step % period
-            if step <= peak and t > 0:
-                mul = step / peak
-            else:
-                mul = (1 - ratio) * (math.cos((step - peak) / max(1, period - peak) * math.pi) * 0.5 + 0.5) + ratio
-            return base * mul / decay
-
-        def multistep_lr(step, milestone=(step_size, step_size * 9 // 5), gamma=(0.5, 0.1)):
-            step, mul = step % period, 1
-            for i in range(len(milestone), 0, -1):
-                if step > milestone[i - 1]:
-                    mul = gamma[i - 1]
-                    break
-            return base * mul
-
-        return cos_lr if 'cos' in self.hyper['lr_scheduler'].lower() else multistep_lr
+        """base_trainer.py:33-43."""
+        self.lr_lambda = lr_lambda_from_hyper(self.hyper)
+        return self.lr_lambda
 
     def train(self):
         """trainer_SID.py:74-180.  Per step: `batch_size` dataset items (each `crop_per_image` noisy/clean crop pairs built on

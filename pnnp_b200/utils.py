@@ -64,3 +64,42 @@ def tensor_dim5to4(tensor):
     """utils/utils.py:194-197 — DataLoader adds a batch dim in front of the crop dim."""
     b, crops, c, h, w = tensor.shape
     return tensor.reshape(b * crops, c, h, w)
+
+
+def get_cos_lr(step, period=1000, peak=20, lr=1e-4, ratio=0.2):
+    """base_trainer.py:141-149 — WarmUpCosine (SGDR): the rate halves every period; linear warm-up over `peak` steps from the
+    second period on; cosine from lr down to ratio * lr inside a period."""
+    import math
+    T = step // period
+    decay = 2 ** T
+    step = step % period
+    if step <= peak and T > 0:
+        mul = step / peak
+    else:
+        mul = (1 - ratio) * (math.cos((step - peak) / (period - peak) * math.pi) * 0.5 + 0.5) + ratio
+    return lr * mul / decay
+
+
+def get_multistep_lr(step, period=1000, lr=1e-4, milestone=[500, 900], gamma=[0.5, 0.1], decay_base=1):
+    """base_trainer.py:151-160."""
+    decay = decay_base ** (step // period)
+    step = step % period
+    mul = 1
+    for i in range(len(milestone), 0, -1):
+        if step > milestone[i - 1]:
+            mul = gamma[i - 1]
+            break
+    return lr * mul / decay
+
+
+def lr_lambda_from_hyper(hyper):
+    """base_trainer.py:33-43 (get_lr_lambda_func): the schedule the YAML `hyper` block selects, as a function of the epoch."""
+    num_of_epochs = hyper['stop_epoch'] - hyper['last_epoch']
+    step_size = hyper['step_size']
+    T = hyper['T'] if 'T' in hyper else 1
+    if 'cos' in hyper['lr_scheduler'].lower():
+        return lambda x: get_cos_lr(x, period=num_of_epochs // T, lr=hyper['learning_rate'], peak=step_size)
+    if 'multi' in hyper['lr_scheduler'].lower():
+        return lambda x: get_multistep_lr(x, period=num_of_epochs // T, decay_base=1, milestone=[step_size, step_size * 9 // 5],
+                                          gamma=[0.5, 0.1], lr=hyper['learning_rate'])
+    raise KeyError(f"lr_scheduler {hyper['lr_scheduler']!r}: the reference knows 'cos' and 'multi' schedules")

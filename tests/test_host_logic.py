@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -101,3 +102,27 @@ def test_product_never_imports_oracle():
                 assert not pat_py.search(open(src_path).read()), fn
             elif fn.endswith((".cu", ".cuh", ".h", ".sh")):
                 assert not pat_c.search(open(src_path).read()), fn
+
+
+def test_lr_schedules_match_the_reference_functions():
+    """base_trainer.py:33-43,141-160: WarmupCosine / MultiStep as the YAML `hyper` block selects them."""
+    import math
+    from pnnp_b200.utils import get_cos_lr, get_multistep_lr, lr_lambda_from_hyper
+    hyper = {"lr_scheduler": "WarmupCosine", "learning_rate": 1e-4, "last_epoch": 0, "stop_epoch": 1600, "step_size": 10, "T": 2}
+    f = lr_lambda_from_hyper(hyper)                                      # period 800, peak 10
+    assert f(10) == pytest.approx(1e-4) and f(800 - 1e-9) == pytest.approx(0.2e-4, rel=1e-3)
+    assert f(800) == 0.0 and f(805) == pytest.approx(0.5 * 1e-4 * 0.5) and f(810) == pytest.approx(0.5e-4)   # warm-up of period 2
+    assert f(1) == pytest.approx(1e-4 * (0.8 * (math.cos((1 - 10) / 790 * math.pi) * 0.5 + 0.5) + 0.2))
+    g = lr_lambda_from_hyper(dict(hyper, lr_scheduler="MultiStep", step_size=100))
+    assert [g(e) for e in (1, 100, 101, 180, 181, 799, 900, 901)] == pytest.approx([1e-4, 1e-4, 5e-5, 5e-5, 1e-5, 1e-5, 1e-4, 5e-5])
+    with pytest.raises(KeyError):
+        lr_lambda_from_hyper(dict(hyper, lr_scheduler="linear"))
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):                                          # live check against the unmodified reference
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_harness as rh
+        rh.load()
+        B = sys.modules.get("base_trainer") or __import__("base_trainer")
+        for step in (0, 1, 9, 10, 11, 400, 799, 800, 801, 805, 1599):
+            assert get_cos_lr(step, period=800, peak=10, lr=1e-4) == B.get_cos_lr(step, period=800, peak=10, lr=1e-4)
+            assert get_multistep_lr(step, period=800, lr=1e-4, milestone=[10, 18]) == B.get_multistep_lr(step, period=800, lr=1e-4, milestone=[10, 18])
