@@ -156,3 +156,45 @@ def test_eval_tiling_oracle_matches_reference_goldens(golden):
         assert np.array_equal(O.eval_merge(tiles, h, w, base), x)            # round trip = identity
         k += 1
     assert k == 5
+
+
+def test_training_loop_restatement_matches_reference_goldens():
+    """T1 oracle: trainer_SID.py:93-101 restated with the oracle's functional UNet (oracle_np.unet_forward), torch autograd and
+    Adam reproduces the reference's own nn.Module / Unet_Loss / Adam loop (tests/golden/train_step.json, written by
+    oracle/make_golden_train.py from the unmodified reference): same seeded init through this package's module classes
+    (identical parameter creation order and state_dict keys), same losses, gradients and parameters after three steps."""
+    import json
+    import os
+    import torch.nn.functional as F
+    from conftest import GOLDEN
+    import pnnp_b200 as P
+    with open(os.path.join(GOLDEN, "train_step.json")) as fh:
+        g = json.load(fh)
+    torch.set_num_threads(4)
+    torch.manual_seed(1997)
+    net = P.UNetSeeInDark(dict(name="UNetSeeInDark", in_nc=4, out_nc=4, nf=32, nframes=1, use_dpsv=False, res=False, cascade=False,
+                               add=False, lock_wb=False))
+    P.initialize_weights(net)
+    net.conv10_1.bias.data.fill_(0.05)
+    assert list(dict(net.named_parameters())) == list(g["grad_abs_sum_step0"])
+    gen = torch.Generator().manual_seed(7)
+    hr = torch.rand((2, 4, 32, 48), generator=gen) ** 2
+    lr = hr + 0.05 * torch.randn((2, 4, 32, 48), generator=gen)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    losses = []
+    for step in range(3):
+        opt.zero_grad()
+        pred = O.unet_forward(lr, params)
+        loss = F.l1_loss(pred.clamp(0, 1), hr)
+        loss.backward()
+        if step == 0:
+            assert float(pred.detach().abs().sum()) == pytest.approx(g["pred0_abs_sum"], rel=1e-5)
+            assert O.l1_loss(pred.detach().numpy(), hr.numpy()) == pytest.approx(g["losses"][0], rel=1e-6)
+            for k, v in params.items():
+                assert float(v.grad.abs().sum()) == pytest.approx(g["grad_abs_sum_step0"][k], rel=2e-4, abs=1e-12), k
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses == pytest.approx(g["losses"], rel=1e-5)
+    for k, v in params.items():
+        assert float(v.detach().double().abs().sum()) == pytest.approx(g["param_abs_sum_after"][k], rel=1e-5), k
