@@ -121,7 +121,11 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
 // 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
 // the narrow full-resolution layers are bound by the epilogue's instruction count, and most of it was run-time feature tests.
 constexpr int EPI_GENERIC = -1, EPI_X = 1, EPI_POOL = 2, EPI_HEAD = 4, EPI_MASK = 8;   // bit 3: activation-derivative mask (training dgrad)
-template <int TPS, int K16S, int EPI>
+// SUP: super-tile.  One pipeline stage carries a 16-row box (8 + 8 + 2 halo rows, ONE TMA load) and feeds TWO M = 128 tiles —
+// rows 0-7 into accumulator buffer a, rows 8-15 (A descriptor start + 128 pixel rows) into buffer a + 1 — so the producer <-> MMA
+// hand-shake, which bounds the small-K full-resolution layers, is paid once per 256 pixels, and a tile's halo
+// rows are 2 in 18 instead of 2 in 10.  Epilogue group g drains buffer g = half (g & 1) of every (groups / 2)-th super-tile.
+template <int TPS, int K16S, int EPI, int SUP = 0>
 __global__ void __launch_bounds__(kConvThreadsMax, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
@@ -203,7 +207,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint32_t stage = 0, phase = 0, sa = smem0, fb = full0, eb = empty0;
         for (; ti.valid(); ti.next(n_tiles, tiles_x, tiles_y)) {
             const int img = ti.img;
-            const int x0 = ti.tx * tile_w + x_first, y0 = ti.ty * kTileH;
+            const int x0 = ti.tx * tile_w + x_first, y0 = ti.ty * (SUP ? 2 * kTileH : kTileH);
             const int n_off = ti.n_tile * umma_n;
             const bool skip_loads = (dbg & 4) && ti.t != first_tile;
             int chunk = 0, dx = 0;
@@ -251,6 +255,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar), bres0 = smem_u32(smem_bres);
         // resident layout [chunk][tap]: CONV3 stage dx uses taps dy*3+dx (stride 3 taps); CONV3X: dy taps are consecutive
         const uint32_t b_stride_eff = (b_res && mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;
+        const uint32_t a_half = (uint32_t)(kTileH * kTileW * p.swz) >> 4;   // SUP: second tile's A rows start 8 x 16 pixel rows further
         if (b_res) mbar_wait(smem_u32(bres_bar), 0, err, 105);
         const int dxc = mode == MODE_CONV3 ? 3 : (mode == MODE_CONV3S2 ? 9 : (mode == MODE_CONV2S2 ? 4 : 1));
         const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -258,6 +263,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, sa = smem0, fb = full0, eb = empty0;
         for (int t = t_begin; t < t_stop; ++t) {
             if (!(dbg & 32)) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, err, 102);
+            if (SUP && !(dbg & 32)) mbar_wait(tempty0 + 8 * (acc + 1), acc_phase ^ 1, err, 106);
             if (!(dbg & 64)) tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)umma_n;
             uint32_t sb_res = bres0;                                       // resident weights of (chunk, dx): advances by one tap
@@ -272,6 +278,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 if (++dx == dxc) { dx = 0; sb_res += (uint32_t)(taps_total - dxc + 1) * b_tap_bytes; } else sb_res += b_tap_bytes;
                 if (elect_one()) {
                     if (!(dbg & 2)) issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
+                    if (SUP && !(dbg & 2))
+                        issue_stage_mmas<TPS, K16S>(d_tmem + (uint32_t)umma_n, adesc0 + a_half, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
                     if (dbg & 16) mbar_arrive(eb);
                     else tc_commit(eb);                                    // frees the smem slot when these MMAs retire
                 }
@@ -279,9 +287,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 sa += (uint32_t)stage_bytes; fb += 8; eb += 8;
                 if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; sa = smem0; fb = full0; eb = empty0; }
             }
-            if (elect_one() && !(dbg & 32)) { if (dbg & 16) mbar_arrive(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc); }   // accumulator complete -> epilogue
+            if (elect_one() && !(dbg & 32)) {                              // accumulator(s) complete -> epilogue
+                if (dbg & 16) mbar_arrive(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc);
+                if (SUP) { if (dbg & 16) mbar_arrive(tfull0 + 8 * (acc + 1)); else tc_commit(tfull0 + 8 * (acc + 1)); }
+            }
             __syncwarp();
-            if (++acc == (uint32_t)groups) { acc = 0; acc_phase ^= 1; }
+            acc += SUP ? 2 : 1;
+            if (acc == (uint32_t)groups) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ============================== epilogue (warps 2..5) ==============================
@@ -308,11 +320,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         TileIter ti;
         ti.init(total_tiles, p.n_tiles, p.tiles_x, p.tiles_y);
         if (p.dbg & 32) ti.t = ti.t_end;
-        for (int g = 0; g < group && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);   // group g: every groups-th tile
+        const int slot = SUP ? group >> 1 : group, n_slots = SUP ? p.groups >> 1 : p.groups;     // SUP: two groups share a super-tile
+        const int y_in = SUP ? (group & 1) * kTileH + ty_in : ty_in, tile_rows = SUP ? 2 * kTileH : kTileH;
+        for (int g = 0; g < slot && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);   // slot s: every n_slots-th tile
         for (; ti.valid(); ) {
             const int n_tile = ti.n_tile, tx = ti.tx, ty = ti.ty, img = ti.img;
-            for (int g = 0; g < p.groups && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);
-            const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTileW + tx_in, y = ty * kTileH + ty_in;
+            for (int g = 0; g < n_slots && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);
+            const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTileW + tx_in, y = ty * tile_rows + y_in;
             const bool valid = x < p.W && y < p.H && (!xmode || (tx_in >= 1 && tx_in <= kTileWX));
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
             tc_fence_after();
@@ -608,7 +622,20 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     const int in_h = h, in_w = w;
     if (s2) { h /= 2; w /= 2; }        // tile over the OUTPUT grid
     const int tps = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? 3 : 1;
-    const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? kTileH + 2 : kTileH;
+    // Super-tile variant (two M = 128 tiles per pipeline stage, see the kernel's SUP parameter).  OPT-IN until it has been measured
+    // on a B200: PNNP_CONV_SUPER=1 -> one CTA per SM, four accumulators (two super-tiles in flight); =2 -> keeps two CTAs per SM
+    // for the small-K resident-weight layers (one super-tile in flight per CTA).  Only the compile-time specialised NHWC 3x3
+    // layers with N <= 128 take it (decided below, once the epilogue specialisation is known).
+    const int super_env = getenv("PNNP_CONV_SUPER") ? atoi(getenv("PNNP_CONV_SUPER")) : 0;      // read per launch: tests flip it
+    static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
+    const int dbg_env = getenv("PNNP_CONV_DBG") ? atoi(getenv("PNNP_CONV_DBG")) : 0;
+    int epi = EPI_GENERIC;
+    if (!no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && !dbg_env &&
+        !(d.pool_out && d.head_out) && !(d.mask && (mode == MODE_CONV3X || d.pool_out || d.head_out)))
+        epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
+    const bool sup = super_env > 0 && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
+    const int tile_rows = sup ? 2 * kTileH : kTileH;
+    const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? tile_rows + 2 : kTileH;
     // shrink the K chunk until at least 3 pipeline stages fit
     int swz, a_bytes, b_tap_stride, stage_bytes, stages, b_resident = 0, b_res_bytes = 0;
     const int smem_budget = 227 * 1024 - 4096 - cout * 20;
@@ -634,7 +661,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     ConvParams p{};
     p.mode = mode; p.n_img = n; p.H = h; p.W = w;
     p.tiles_x = mode == MODE_CONV3X ? (w + kTileWX - 1) / kTileWX : (w + kTileW - 1) / kTileW;
-    p.tiles_y = (h + kTileH - 1) / kTileH; p.n_tiles = n_tiles;
+    p.tiles_y = (h + tile_rows - 1) / tile_rows; p.n_tiles = n_tiles;
     p.umma_n = umma_n; p.nsrc = nsrc; p.cin0 = cin0; p.cin1 = nsrc > 1 ? cin1 : 0; p.kc = kc; p.swz = swz;
     p.cout = cout; p.cout_stride = cout_stride; p.act = act; p.out_mode = out_mode;
     p.stages = stages; p.stage_bytes = stage_bytes; p.a_bytes = a_bytes; p.b_tap_stride = b_tap_stride;
@@ -643,11 +670,13 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // the single producer / MMA warp pair (~650 cycles per tile with every unit of work switched off, r01 experiments): run TWO
     // CTAs per SM for them — half the shared memory, two accumulator buffers (<= 256 TMEM columns) and 320 threads each.
     const int ksteps_tile = (cin_total / kc) * (mode == MODE_CONV3 ? 3 : (mode == MODE_CONV3S2 ? 9 : (mode == MODE_CONV2S2 ? 4 : 1)));
-    const bool two_ctas = b_resident && umma_n <= 128 && ksteps_tile <= 2 && !getenv("PNNP_CONV_1CTA");
+    bool two_ctas = b_resident && umma_n <= 128 && ksteps_tile <= 2 && !getenv("PNNP_CONV_1CTA") && !(sup && super_env == 1);
     if (two_ctas) {
         const int half_budget = 110 * 1024 - 2048 - cout * 20;
-        stages = std::min(stages, (half_budget - b_res_bytes) / stage_bytes);
-        if (stages < 3) return fail("conv: two-CTA configuration does not fit (internal)");
+        const int st2 = std::min(stages, (half_budget - b_res_bytes) / stage_bytes);
+        if (st2 >= 3) stages = st2;
+        else if (sup) two_ctas = false;                      // the 18-row stages of a super-tile may not fit twice: one CTA per SM then
+        else return fail("conv: two-CTA configuration does not fit (internal)");
     }
     const int groups = two_ctas ? 2 : ((umma_n <= 128 && !getenv("PNNP_CONV_2GROUPS")) ? 4 : 2);
     p.stages = stages;
@@ -658,7 +687,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (d.mask && out_mode != OUT_NHWC_BF16) return fail("conv: the activation mask needs NHWC bf16 output");
     p.pool_out = static_cast<__nv_bfloat16*>(d.pool_out);
     p.head_w = d.head_w; p.head_b = d.head_b; p.head_out = d.head_out; p.head_cout = d.head_out ? d.head_cout : 0;
-    { const char* e = getenv("PNNP_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg_env;
     if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
     p.err = g_err_dev;
     CUtensorMap tmA0, tmA1, tmB;
@@ -679,19 +708,25 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 #define PNNP_SPEC_EPI(X, T, K) X(T, K, 0) X(T, K, 1) X(T, K, 2) X(T, K, 3) X(T, K, 4) X(T, K, 5)
 #define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1, -1) X(3, 2, -1) X(3, 4, -1) X(1, 1, -1) X(1, 2, -1) X(1, 4, -1) \
     PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8)
+#define PNNP_FOR_EACH_SUPER_VARIANT(X) PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8)
     if (!attr_done) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
+#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PNNP_FOR_EACH_SUPER_VARIANT(X)
+#undef X
         attr_done = true;
     }
     const int k16s = kc / 16;
-    int epi = EPI_GENERIC;
-    static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
-    if (!no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && tps == 3 && !p.dbg &&
-        !(d.pool_out && d.head_out) && !(d.mask && (mode == MODE_CONV3X || d.pool_out || d.head_out)))
-        epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
     bool launched = false;
+    if (sup) {
+        if (groups & 1) return fail("conv: the super-tile variant needs an even number of accumulator buffers (internal)");
+#define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { conv_gemm_tc_kernel<T, K, E, 1><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
+        PNNP_FOR_EACH_SUPER_VARIANT(X)
+#undef X
+        if (!launched) return fail("conv: no super-tile kernel variant for this (K chunk, epilogue)");
+    }
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { conv_gemm_tc_kernel<T, K, E><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
     PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
