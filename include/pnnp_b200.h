@@ -186,6 +186,13 @@ int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int w, int c, 
 int pnnp_crop_aug(const float* frame, float* out, int c, int h, int w, int patch, int n,
                   const int* h_start_host, const int* w_start_host, const int* mode_host, void* stream);
 
+/* White-balance jitter of Raw_Dataset.__getitem__ (data_process/syn_datasets.py:313-319; gains from random_gains,
+ * data_process/unprocess.py:60-77), in place on n x c x h x w fp32 crops: every plane times rgb_gain (float32), then plane ch
+ * times gain[ch] where kind[ch] = 1 (float32 product) or 2 (float64 product rounded to float32 once: what NumPy does when the
+ * frame's white balance is np.float64); kind[ch] = 0 leaves the plane at the common gain.  kind / gain: host arrays, c entries. */
+int pnnp_wb_gains(float* data, int n, int c, int h, int w, float rgb_gain, const int* kind_host, const double* gain_host,
+                  void* stream);
+
 /* HighBitRecovery.map (data_process/process.py:726-751): samples whose rounded DN value x is in [low, high) are re-drawn as
  * dist.ppf(cdf[x - low] + U * range[x - low]) (float64, rounded to float32), the sub-DN remainder is added back, then /span
  * (norm) or +bl.  dist = Tukey-lambda(lam) * scale + loc, or N(loc, scale).  rand: caller-supplied U (replay) or NULL for

@@ -473,6 +473,41 @@ def hbr_map(data, lut, rand, norm=True):
     return data / (p['wp'] - p['bl']) if norm else data + p['bl']
 
 
+def random_gains(camera_type="SonyA7S2"):
+    """data_process/unprocess.py:60-77: (rgb_gain, red_gain, blue_gain) as float32 arrays of shape (1,).
+    Draw order: one torch.distributions.Normal(0.8, 0.1) sample (torch's global CPU generator), then one
+    np.random.uniform for the red gain; the blue gain is a quadratic fit of the red gain (float64, rounded to float32 once)."""
+    import torch
+    import torch.distributions as tdist
+    n = tdist.Normal(loc=torch.tensor([0.8]), scale=torch.tensor([0.1]))
+    rgb_gain = 1.0 / n.sample()
+    if camera_type == "SonyA7S2":
+        red_gain = np.random.uniform(1.75, 2.65)
+        fit = [14.65, -9.63942308, 1.80288462]
+    elif camera_type == "IMX686":
+        red_gain = np.random.uniform(1.4, 2.3)
+        fit = [6.14381188, -3.65620261, 0.70205967]
+    else:
+        raise NotImplementedError
+    blue_gain = fit[0] + fit[1] * red_gain + fit[2] * red_gain ** 2
+    return rgb_gain.numpy(), np.array([red_gain]).astype(F32), np.array([blue_gain]).astype(F32)
+
+
+def wb_jitter(hr_crops, wb, gains):
+    """syn_datasets.py:313-319 given the gains of random_gains(): every plane times rgb_gain (float32, in place), then plane 0
+    times wb[0] / red_gain and plane 2 times wb[2] / blue_gain.  The type of `wb` decides the arithmetic of the second product
+    (NEP 50): a float32 / python-float white balance keeps it float32; an np.float64 white balance makes `wb / gain` a float64
+    array, the product float64, and the assignment rounds it to float32 once."""
+    rgb_gain, red_gain, blue_gain = gains
+    hr_crops = hr_crops.copy()
+    red = wb[0] / red_gain
+    blue = wb[2] / blue_gain
+    hr_crops *= rgb_gain
+    hr_crops[:, 0] = hr_crops[:, 0] * red
+    hr_crops[:, 2] = hr_crops[:, 2] * blue
+    return hr_crops
+
+
 def post_synth_clip(lr, hr, clip):
     """syn_datasets.py:339-342 / trainer_SID.py:481-485.  clip==2 (HALF_CLIP) → lower bound -inf."""
     if clip:

@@ -71,6 +71,7 @@ SIGNATURES = {
     "pnnp_strided_copy_batch": (_i, [_vp, _i, _i, _vp]),
     "pnnp_adam_step": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _f, _f, _f, _f, _i, _f, _vp]),
     "pnnp_crop_aug": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]),
+    "pnnp_wb_gains": (_i, [_vp, _i, _i, _i, _i, _f, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp]),
     "pnnp_hbr_map": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _d, _d, _d, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "pnnp_eval_crop": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pnnp_eval_merge": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -58,6 +58,29 @@ def random_crop(img, h_start, w_start, aug, patch_size):
     return out
 
 
+def wb_jitter(hr_crops, wb, gains):
+    """syn_datasets.py:314-319 on CUDA crops (n,c,h,w), IN PLACE: `hr_crops *= rgb_gain`, then planes 0 and 2 times
+    `wb[0] / red_gain` and `wb[2] / blue_gain`.  `gains` = random_gains().  The effective gains are formed on the host with the
+    reference's own NumPy expression, so their dtype — float32 for a float32 / python-float white balance, float64 for an
+    np.float64 one (NEP 50) — selects the float32 or the float64 product on the device exactly as NumPy would."""
+    _lib.require_cuda(hr_crops, "hr_crops")
+    if hr_crops.dtype != torch.float32:
+        raise RuntimeError("wb_jitter: float32 crops")
+    n, c, h, w = hr_crops.shape
+    rgb_gain, red_gain, blue_gain = (g.numpy() if isinstance(g, torch.Tensor) else np.asarray(g) for g in gains)
+    eff = {0: wb[0] / red_gain, 2: wb[2] / blue_gain}
+    kind, gain = [0] * c, [1.0] * c
+    for ch, g in eff.items():
+        g = np.asarray(g)
+        kind[ch] = 2 if g.dtype == np.float64 else 1
+        gain[ch] = float(g.reshape(-1)[0])                     # float32 -> python float is exact
+    with torch.cuda.device(hr_crops.device):
+        _lib.check(_lib.lib().pnnp_wb_gains(hr_crops.data_ptr(), n, c, h, w, float(np.float32(rgb_gain.reshape(-1)[0])),
+                                            (C.c_int * c)(*kind), (C.c_double * c)(*gain), _lib.stream_ptr(hr_crops.device)),
+                   "wb_gains")
+    return hr_crops
+
+
 def tile_grid(h, w, patch_size, base=64):
     """(nh, nw) of SynBase_Dataset.eval_crop (syn_datasets.py:112-115)."""
     l = patch_size - base

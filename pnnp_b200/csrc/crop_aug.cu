@@ -98,9 +98,54 @@ static int tile_geom(TileGeom& g, int c, int h, int w, int patch, int base) {
     if (g.d >= h || g.d >= w) return fail("eval tiling: reflect padding needs base/2 < h, w");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// White-balance jitter of Raw_Dataset.__getitem__ (data_process/syn_datasets.py:313-319), in place on n x c x h x w crops:
+//   hr_crops *= rgb_gain                  float32, every plane
+//   hr_crops[:, ch] = hr_crops[:, ch] * g  for ch = 0 (red) and 2 (blue), g = wb[ch] / gain:
+//     kind 1: g is float32 -> float32 product;  kind 2: g is float64 (np.float64 white balance, NEP 50) -> the product is
+//     formed in float64 and rounded to float32 once on assignment.
+// Explicit _rn intrinsics: no FMA contraction, two separately rounded float32 products like NumPy's.
+struct GainArgs { float common; int kind[8]; float g32[8]; double g64[8]; };
+
+__global__ void __launch_bounds__(256) wb_gains_kernel(float* __restrict__ data, size_t plane4, int c, size_t total4, const GainArgs a) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)((t / plane4) % (size_t)c);
+        float4 v = reinterpret_cast<float4*>(data)[t];
+        float* f = reinterpret_cast<float*>(&v);
+        const int kind = a.kind[ch];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x = __fmul_rn(f[e], a.common);
+            if (kind == 1) x = __fmul_rn(x, a.g32[ch]);
+            else if (kind == 2) x = __double2float_rn(__dmul_rn((double)x, a.g64[ch]));
+            f[e] = x;
+        }
+        reinterpret_cast<float4*>(data)[t] = v;
+    }
+}
 }  // namespace pnnp
 
 using namespace pnnp;
+
+extern "C" int pnnp_wb_gains(float* data, int n, int c, int h, int w, float rgb_gain, const int* kind_host,
+                             const double* gain_host, void* stream) {
+    if (!data || !kind_host || !gain_host) return fail("wb_gains: null pointer");
+    if (n < 1 || c < 1 || c > 8 || h < 1 || w < 1) return fail("wb_gains: 1..8 planes per crop");
+    const size_t plane = (size_t)h * w;
+    if (plane & 3) return fail("wb_gains: h * w must be a multiple of 4");
+    GainArgs a{};
+    a.common = rgb_gain;
+    for (int ch = 0; ch < c; ++ch) {
+        if (kind_host[ch] < 0 || kind_host[ch] > 2) return fail("wb_gains: kind must be 0 (none), 1 (float32) or 2 (float64)");
+        a.kind[ch] = kind_host[ch]; a.g64[ch] = gain_host[ch]; a.g32[ch] = (float)gain_host[ch];
+    }
+    const size_t total4 = (size_t)n * c * plane / 4;
+    wb_gains_kernel<<<(int)std::min<size_t>((total4 + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(data, plane / 4, c, total4, a);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int pnnp_eval_crop(const float* frame, float* tiles, int c, int h, int w, int patch, int base, void* stream) {
     if (!frame || !tiles) return fail("eval_crop: null pointer");

@@ -122,12 +122,18 @@ class Raw_Dataset(torch.utils.data.Dataset):
         else:
             hr_crops = hr_imgs[None]
         n = hr_crops.shape[0]
+        wb = np.ones(4, np.float32)
+        if a["lock_wb"] is False and np.random.randint(2):          # syn_datasets.py:313-319: white-balance jitter, one item in two
+            from .unprocess import random_gains
+            crops.wb_jitter(hr_crops, wb, random_gains())
         params = [sample_params(camera_type=a['camera_type']) if a['params'] is None else a['params'] for _ in range(n)]
         post = None
         if a['clip']:
             post = (-float("inf") if a['clip'] == HALF_CLIP else 0.0, 1.0)
-            hr_crops = hr_crops.clamp_(0, 1)
+        # the noise is synthesised from the crops as they are (a jittered crop may exceed 1); hr is clipped afterwards (:339-342)
         lr_crops = synthesize_batch(hr_crops, params, a['noise_code'], ori=a['ori'], post_clip=post)
+        if a['clip']:
+            hr_crops = hr_crops.clamp_(0, 1)
         ratio = torch.tensor([float(p['ratio']) for p in params], dtype=torch.float32, device=device)
-        return {"lr": lr_crops, "hr": hr_crops, "ratio": ratio, "wb": np.ones(4, np.float32),
+        return {"lr": lr_crops, "hr": hr_crops, "ratio": ratio, "wb": wb,
                 "ccm": np.eye(3, dtype=np.float32), "name": f"syn_{idx:04d}"}

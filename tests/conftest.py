@@ -24,7 +24,7 @@ def pytest_collection_modifyitems(config, items):
     # first, the tolerance-based training tests (fp32 atomics: results vary with summation order from run to run) go last, so a
     # marginal training tolerance cannot hide the parity results of everything else.  Stable sort: order inside a group is kept.
     def late(it):
-        return int("test_gpu_train.py" in it.nodeid or "train_mode" in it.nodeid)
+        return int("test_gpu_train.py" in it.nodeid or "train_mode" in it.nodeid or "test_gpu_wb_jitter.py" in it.nodeid)
     items.sort(key=late)
     if torch.cuda.is_available():
         return

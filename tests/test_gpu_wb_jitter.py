@@ -1,0 +1,59 @@
+"""White-balance jitter of Raw_Dataset.__getitem__ (syn_datasets.py:313-319) on the device: bit-exact against the golden
+outputs of the unmodified reference and against the oracle, for the three white-balance types NumPy treats differently."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_np as O
+from pnnp_b200 import crops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["wb32", "wb64", "wbpy"])
+def test_wb_gains_kernel_is_bit_exact_vs_reference_golden(golden, tag):
+    g = golden("wb_jitter")
+    wb = [float(v) for v in g[f"{tag}_wb"]] if tag == "wbpy" else g[f"{tag}_wb"]
+    gains = (g[f"{tag}_rgb"], g[f"{tag}_red"], g[f"{tag}_blue"])
+    x = torch.from_numpy(g["base"]).cuda()
+    out = crops.wb_jitter(x, wb, gains)
+    assert out.data_ptr() == x.data_ptr()                                         # in place, like `hr_crops *= ...`
+    assert out.cpu().numpy().tobytes() == g[f"{tag}_out"].tobytes()
+
+
+def test_wb_gains_kernel_vs_oracle_on_crops():
+    rs = np.random.RandomState(4)
+    base = (rs.rand(8, 4, 128, 128).astype(np.float32)) ** 2
+    for wb in (np.array([2.2, 1, 1.7, 1], np.float32), np.array([2.013, 1, 1.555, 1], np.float64)):
+        gains = (np.array([1.31], np.float32), np.array([2.05], np.float32), np.array([1.62], np.float32))
+        got = crops.wb_jitter(torch.from_numpy(base).cuda(), wb, gains).cpu().numpy()
+        assert got.tobytes() == O.wb_jitter(base, wb, gains).tobytes()
+
+
+def test_raw_dataset_item_with_wb_jitter_follows_the_reference_order():
+    """lock_wb False: coin -> random_gains -> products -> per-crop sample_params -> synthesis from the UNCLIPPED jittered crops
+    -> hr.clip(0, 1) (syn_datasets.py:313-342)."""
+    import os
+    import yaml
+    from conftest import ROOT
+    from pnnp_b200.datasets import Raw_Dataset
+    cfg = yaml.load(open(os.path.join(ROOT, "runfiles/SonyA7S2/PNNP.yml")), Loader=yaml.FullLoader)["dst_train"]
+    cfg.update(H=256, W=384, patch_size=64, crop_per_image=4, lock_wb=False)
+    ds = Raw_Dataset(cfg)
+    seen = set()
+    for seed in range(6):
+        np.random.seed(seed); torch.manual_seed(seed)
+        item = ds[0]
+        raw = ds.synthetic_raw(0, item["lr"].device).cpu().numpy().view(np.uint16)
+        packed = O.raw2bayer(raw, cfg["wp"], cfg["bl"], True, True)
+        np.random.seed(seed); torch.manual_seed(seed)
+        hs, ws, aug = crops.init_random_crop_point(128, 192, 64, 4, cfg["croptype"])
+        hr = O.random_crop(packed, hs, ws, 64, aug)
+        coin = np.random.randint(2)
+        seen.add(int(coin))
+        if coin:
+            hr = O.wb_jitter(hr, np.ones(4, np.float32), O.random_gains())
+        params = [O.sample_params("SonyA7S2") for _ in range(4)]
+        assert item["hr"].cpu().numpy().tobytes() == hr.clip(0, 1).tobytes()
+        assert np.array_equal(item["ratio"].cpu().numpy(), np.array([p["ratio"] for p in params], np.float32))
+    assert seen == {0, 1}

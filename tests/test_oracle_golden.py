@@ -198,3 +198,33 @@ def test_training_loop_restatement_matches_reference_goldens():
     assert losses == pytest.approx(g["losses"], rel=1e-5)
     for k, v in params.items():
         assert float(v.detach().double().abs().sum()) == pytest.approx(g["param_abs_sum_after"][k], rel=1e-5), k
+
+
+def _wb_of(g, tag):
+    wb = g[f"{tag}_wb"]
+    return [float(v) for v in wb] if tag == "wbpy" else wb          # the python-list case was stored as a float64 array
+
+
+@pytest.mark.parametrize("k,tag", [(0, "wb32"), (1, "wb64"), (2, "wbpy")])
+def test_wb_jitter_matches_reference_golden(golden, k, tag):
+    """syn_datasets.py:313-319 + unprocess.py:60-77: same draws under the same seeds (NumPy + torch global generators), same
+    products — float32 for a float32 / python-float white balance, float64 for an np.float64 one."""
+    g = golden("wb_jitter")
+    from pnnp_b200.unprocess import random_gains
+    for fn in (O.random_gains, lambda: tuple(t.numpy() for t in random_gains())):
+        np.random.seed(40 + k)
+        torch.manual_seed(40 + k)
+        assert np.random.randint(2) == int(g[f"{tag}_coin"])
+        gains = fn()
+        for got, name in zip(gains, ("rgb", "red", "blue")):
+            assert got.dtype == np.float32 and got.shape == (1,) and got.tobytes() == g[f"{tag}_{name}"].tobytes()
+    wb = _wb_of(g, tag)
+    out = O.wb_jitter(g["base"], wb, gains)
+    assert out.dtype == np.float32 and out.tobytes() == g[f"{tag}_out"].tobytes()
+    assert str(np.asarray(wb[0] / gains[1]).dtype) == str(g[f"{tag}_red_eff_dtype"])
+    np.random.seed(77)
+    torch.manual_seed(77)
+    for got, name in zip(O.random_gains("IMX686"), ("rgb", "red", "blue")):
+        assert got.tobytes() == g[f"imx_{name}"].tobytes()
+    with pytest.raises(NotImplementedError):
+        random_gains("NikonD850")

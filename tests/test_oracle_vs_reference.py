@@ -57,3 +57,23 @@ def test_networks_live(R):
         net.eval()
         with torch.no_grad():
             assert torch.equal(net(x), fn(x, net.state_dict()))
+
+
+def test_wb_jitter_live(R):
+    """random_gains (unprocess.py:60-77) and the statements of syn_datasets.py:314-319 against the oracle, fresh seeds."""
+    rs = np.random.RandomState(9)
+    base = rs.rand(2, 4, 8, 12).astype(np.float32)
+    for s, wb in ((1, np.array([2.0, 1, 1.5, 1], np.float32)), (2, np.array([1.87, 1, 1.61, 1], np.float64)), (3, [2.3, 1.0, 1.4, 1.0])):
+        for cam in ("SonyA7S2", "IMX686"):
+            np.random.seed(s); torch.manual_seed(s)
+            rgb_gain, red_gain, blue_gain = R.syn_datasets.random_gains(cam)
+            np.random.seed(s); torch.manual_seed(s)
+            gains = O.random_gains(cam)
+            assert all(a.numpy().tobytes() == b.tobytes() for a, b in zip((rgb_gain, red_gain, blue_gain), gains))
+            hr_crops = base.copy()
+            red = wb[0] / red_gain.numpy()
+            blue = wb[2] / blue_gain.numpy()
+            hr_crops *= rgb_gain.numpy()
+            hr_crops[:, 0] = hr_crops[:, 0] * red
+            hr_crops[:, 2] = hr_crops[:, 2] * blue
+            assert O.wb_jitter(base, wb, gains).tobytes() == hr_crops.tobytes()
