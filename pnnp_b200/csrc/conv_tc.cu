@@ -121,6 +121,7 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
 // 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
 // the narrow full-resolution layers are bound by the epilogue's instruction count, and most of it was run-time feature tests.
 constexpr int EPI_GENERIC = -1, EPI_X = 1, EPI_POOL = 2, EPI_HEAD = 4, EPI_MASK = 8;   // bit 3: activation-derivative mask (training dgrad)
+constexpr int EPI_CONVT = 16;           // bit 4: ConvTranspose2d pixel-shuffle store (bf16 NHWC, bias only) — opt-in, see conv_layer_launch
 // SUP: super-tile.  One pipeline stage carries a 16-row box (8 + 8 + 2 halo rows, ONE TMA load) and feeds TWO M = 128 tiles —
 // rows 0-7 into accumulator buffer a, rows 8-15 (A descriptor start + 128 pixel rows) into buffer a + 1 — so the producer <-> MMA
 // hand-shake, which bounds the small-K full-resolution layers, is paid once per 256 pixels, and a tile's halo
@@ -308,7 +309,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint32_t acc_phase = 0;
         constexpr bool kSpec = EPI >= 0;
         const bool xmode = kSpec ? (EPI & EPI_X) != 0 : p.mode == MODE_CONV3X;
-        const bool is_convt = kSpec ? false : p.mode == MODE_CONVT;
+        const bool is_convt = kSpec ? (EPI & EPI_CONVT) != 0 : p.mode == MODE_CONVT;
         const bool out_nhwc = kSpec ? true : p.out_mode == OUT_NHWC_BF16;
         const bool has_resid = kSpec ? false : p.resid != nullptr;
         const bool has_mask = kSpec ? (EPI & EPI_MASK) != 0 : p.mask != nullptr;
@@ -499,6 +500,35 @@ __global__ void nchw_f32_to_nhwc16_bf16_kernel(const float* __restrict__ in, __n
     }
 }
 
+// Same conversion, four pixels per thread (h * w % 4 == 0): one 128-bit load per plane (all issued before the first use) and a
+// contiguous 128-byte store per thread.  OPT-IN (PNNP_IN_V2=1) until measured: the one-pixel kernel above takes 53 us for a Sony
+// frame (146 MB of traffic: 2.7 TB/s).
+__global__ void __launch_bounds__(256) nchw_f32_to_nhwc16_bf16_x4_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                                         int n, int c, int h, int w, float scale) {
+    const size_t plane4 = ((size_t)h * w) >> 2, total4 = (size_t)n * plane4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t img = i / plane4, q = i - img * plane4;
+        float4 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            v[k] = k < c ? __ldcs(reinterpret_cast<const float4*>(in + (img * c + k) * (plane4 << 2)) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4* o = reinterpret_cast<uint4*>(out + (i << 2) * 16);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float a = reinterpret_cast<const float*>(&v[2 * k])[px] * scale;
+                const float b = reinterpret_cast<const float*>(&v[2 * k + 1])[px] * scale;
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+                pk[k] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            o[2 * px] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[2 * px + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+    }
+}
+
 // 2x2 max pooling, NHWC bf16, 8 channels (16 bytes) per thread
 __global__ void maxpool2x2_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int h,
                                             int w, int c) {
@@ -626,6 +656,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // on a B200: PNNP_CONV_SUPER=1 -> one CTA per SM, four accumulators (two super-tiles in flight); =2 -> keeps two CTAs per SM
     // for the small-K resident-weight layers (one super-tile in flight per CTA).  Only the compile-time specialised NHWC 3x3
     // layers with N <= 128 take it (decided below, once the epilogue specialisation is known).
+    const bool convt_fast = getenv("PNNP_CONVT_FAST") && atoi(getenv("PNNP_CONVT_FAST")) > 0;
     const int super_env = getenv("PNNP_CONV_SUPER") ? atoi(getenv("PNNP_CONV_SUPER")) : 0;      // read per launch: tests flip it
     static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
     const int dbg_env = getenv("PNNP_CONV_DBG") ? atoi(getenv("PNNP_CONV_DBG")) : 0;
@@ -633,7 +664,10 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (!no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && !dbg_env &&
         !(d.pool_out && d.head_out) && !(d.mask && (mode == MODE_CONV3X || d.pool_out || d.head_out)))
         epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
-    const bool sup = super_env > 0 && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
+    if (convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
+        !no_spec && !dbg_env)
+        epi = EPI_CONVT;
+    const bool sup = super_env > 0 && mode != MODE_CONVT && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
     const int tile_rows = sup ? 2 * kTileH : kTileH;
     const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? tile_rows + 2 : kTileH;
     // shrink the K chunk until at least 3 pipeline stages fit
@@ -643,9 +677,11 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     {
         // weights resident in smem when all taps x chunks fit beside >= 3 A-only stages (single N tile, not convT)
         const int swz_r = kc * 2, bts = (umma_n * swz_r + 1023) / 1024 * 1024;
-        const int res_bytes = (cin_total / kc) * taps * bts;
+        const int res_bytes = (cin_total / kc) * (mode == MODE_CONVT ? 1 : taps) * bts;   // convT: the four taps are N columns of one block
         const int a_only = (box_h * kTileW * swz_r + 1023) / 1024 * 1024;
-        if (mode != MODE_CONVT && n_tiles == 1 && res_bytes + 3 * a_only <= smem_budget && !getenv("PNNP_NO_RESIDENT_W")) {
+        // ConvTranspose2d layers with a single N tile (4 * cout <= 256) can keep their weights resident too: opt-in
+        // (PNNP_CONVT_FAST=1) until measured — it also lets the K = 64 layer run two CTAs per SM
+        if ((mode != MODE_CONVT || convt_fast) && n_tiles == 1 && res_bytes + 3 * a_only <= smem_budget && !getenv("PNNP_NO_RESIDENT_W")) {
             b_resident = 1; b_res_bytes = res_bytes;
         }
     }
@@ -707,7 +743,8 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // (taps per stage, K16 slices, epilogue specialisation); specialised epilogues exist for the 3-taps-per-stage shapes
 #define PNNP_SPEC_EPI(X, T, K) X(T, K, 0) X(T, K, 1) X(T, K, 2) X(T, K, 3) X(T, K, 4) X(T, K, 5)
 #define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1, -1) X(3, 2, -1) X(3, 4, -1) X(1, 1, -1) X(1, 2, -1) X(1, 4, -1) \
-    PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8)
+    PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8) \
+    X(1, 1, 16) X(1, 2, 16) X(1, 4, 16)
 #define PNNP_FOR_EACH_SUPER_VARIANT(X) PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8)
     if (!attr_done) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -764,6 +801,13 @@ extern "C" int pnnp_conv_pipeline_error(void) {
 extern "C" int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, float scale, void* stream) {
     if (!in || !out || c > 16) return fail("nchw_to_nhwc16: bad arguments");
     const size_t total = (size_t)n * h * w;
+    if (getenv("PNNP_IN_V2") && atoi(getenv("PNNP_IN_V2")) > 0 && (((size_t)h * w) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        const int blocks4 = (int)std::min<size_t>((total / 4 + 255) / 256, 148 * 8);
+        nchw_f32_to_nhwc16_bf16_x4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(in, static_cast<__nv_bfloat16*>(out), n, c, h, w, scale);
+        count_launch();
+        PNNP_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     nchw_f32_to_nhwc16_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, static_cast<__nv_bfloat16*>(out), n, c, h, w, scale);
     count_launch();

@@ -1,10 +1,13 @@
-"""Super-tile variant of the conv kernel (conv_tc.cu, template parameter SUP; PNNP_CONV_SUPER=1|2): two M = 128 tiles per pipeline
-stage.  Every output pixel sees the same MMAs in the same order as in the default kernel, so the two must agree BIT FOR BIT —
-outputs, fused max-pool, fused 1x1 head and the masked data-gradient epilogue alike.
+"""Opt-in kernel variants written after round 1's GPU budget was spent (none has run on a B200 yet).  Each is selected by an
+environment variable that is off by default, and these tests are opt-in too (PNNP_TEST_EXPERIMENTAL=1), so the default
+`pytest -m gpu` run exercises only measured code.  `tools/r02_sweep.sh` runs them and times every variant.
 
-The variant was written after the round's GPU budget was spent and has not run on a B200 yet: it is opt-in in the product
-(environment variable, default off) and these tests are opt-in too (PNNP_TEST_EXPERIMENTAL=1), so the default `pytest -m gpu`
-run exercises only measured code."""
+* PNNP_CONV_SUPER=1|2 — super-tile conv kernel (conv_tc.cu, template parameter SUP): two M = 128 tiles per pipeline stage.  Every
+  output pixel sees the same MMAs in the same order as in the default kernel, so the two must agree BIT FOR BIT — outputs,
+  fused max-pool, fused 1x1 head and the masked data-gradient epilogue alike.
+* PNNP_CONVT_FAST=1 — ConvTranspose2d layers: compile-time specialised pixel-shuffle epilogue, weights resident in shared memory
+  when 4 * cout <= 256, two CTAs per SM for the K = 64 layer.  Bit-identical to the default.
+* PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default."""
 import os
 
 import pytest
@@ -100,4 +103,65 @@ def test_super_tile_whole_unet_forward_is_unchanged(monkeypatch, sup):
             return net(x).clone()
     want = _run(monkeypatch, 0, call)
     got = _run(monkeypatch, sup, call)
+    assert torch.equal(got, want)
+
+
+def _run_env(monkeypatch, name, value, fn):
+    if value:
+        monkeypatch.setenv(name, str(value))
+    else:
+        monkeypatch.delenv(name, raising=False)
+    out = fn()
+    torch.cuda.synchronize()
+    assert _lib.lib().pnnp_conv_pipeline_error() == 0, "tcgen05/TMA pipeline wait timed out"
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n", [(64, 32, 16, 32, 1), (64, 32, 356, 532, 1), (128, 64, 24, 40, 2), (256, 128, 8, 24, 1),
+                                            (512, 256, 8, 8, 1)])
+def test_conv_transpose_fast_path_equals_default(monkeypatch, cin, cout, h, w, n):
+    g = torch.Generator(device="cuda").manual_seed(cin + h)
+    x = _nhwc(torch.randn((n, cin, h, w), device="cuda", generator=g))
+    wt = torch.randn((cin, cout, 2, 2), device="cuda", generator=g) / cin ** 0.5
+    b = torch.randn((cout,), device="cuda", generator=g) * 0.1
+
+    class M:
+        pass
+    m = M()
+    m.weight, m.bias = wt, None
+    wp = archs._PackedLayer(m, "convT").get(wt.device)[0]
+
+    def call():
+        out = torch.zeros((n, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device="cuda")
+        archs._conv(_lib.CONVT, x, wp, b, out, cout, _lib.ACT_NONE)
+        return out
+    want = _run_env(monkeypatch, "PNNP_CONVT_FAST", 0, call)
+    got = _run_env(monkeypatch, "PNNP_CONVT_FAST", 1, call)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 64, 96), (2, 4, 30, 34), (1, 4, 1424, 2128), (1, 12, 32, 48)])
+def test_input_layout_v2_equals_default(monkeypatch, shape):
+    x = torch.rand(shape, device="cuda") - 0.3
+
+    def call():
+        out = torch.zeros((shape[0], shape[2], shape[3], 16), dtype=torch.bfloat16, device="cuda")
+        return archs._to_nhwc16(x, out, 0.75)
+    want = _run_env(monkeypatch, "PNNP_IN_V2", 0, call)
+    got = _run_env(monkeypatch, "PNNP_IN_V2", 1, call)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
+def test_all_variants_together_leave_the_unet_forward_unchanged(monkeypatch):
+    torch.manual_seed(4)
+    net = P.UNetSeeInDark({"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}).cuda().eval()
+    P.initialize_weights(net)
+    x = torch.rand((1, 4, 304, 400), device="cuda")
+    with torch.no_grad():
+        want = net(x).clone()
+        for k, v in (("PNNP_CONV_SUPER", "1"), ("PNNP_CONVT_FAST", "1"), ("PNNP_IN_V2", "1")):
+            monkeypatch.setenv(k, v)
+        got = net(x).clone()
+    torch.cuda.synchronize()
+    assert _lib.lib().pnnp_conv_pipeline_error() == 0
     assert torch.equal(got, want)

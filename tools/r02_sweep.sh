@@ -1,0 +1,29 @@
+#!/bin/bash
+# Round-2 first GPU call: correctness of the opt-in kernel variants written without a GPU at the end of round 1, then their timing.
+#   gpurun --timeout 900 -- 'bash tools/r02_sweep.sh'
+# Everything lands in gpurun_out/r02_sweep/.  Order: cheap correctness first, so a hang / failure is seen before time is spent.
+set -u
+OUT=gpurun_out/r02_sweep
+mkdir -p "$OUT"
+export PNNP_TEST_EXPERIMENTAL=1
+timeout 300 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_wb_jitter.py -q -x > "$OUT/pytest_experimental.log" 2>&1
+echo "experimental tests rc=$?" | tee -a "$OUT/summary.txt"
+unset PNNP_TEST_EXPERIMENTAL
+run() {  # label, env assignments...
+  local label=$1; shift
+  ( export "$@"; timeout 200 python tools/profile_unet.py > "$OUT/layers_$label.txt" 2>&1
+    timeout 200 python bench.py --workload unet_sony --steps 50 --warmup 5 --no-cpu-baseline > "$OUT/bench_unet_$label.json" 2> "$OUT/bench_unet_$label.err" )
+  echo "$label: $(tail -1 "$OUT/layers_$label.txt")" | tee -a "$OUT/summary.txt"
+}
+run default PNNP_NOOP=1
+run super1 PNNP_CONV_SUPER=1
+run super2 PNNP_CONV_SUPER=2
+run convt PNNP_CONVT_FAST=1
+run inv2 PNNP_IN_V2=1
+run all1 PNNP_CONV_SUPER=1 PNNP_CONVT_FAST=1 PNNP_IN_V2=1
+run all2 PNNP_CONV_SUPER=2 PNNP_CONVT_FAST=1 PNNP_IN_V2=1
+for v in 0 1 2; do
+  ( export PNNP_CONV_SUPER=$v PNNP_CONVT_FAST=$((v>0)); timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
+      > "$OUT/bench_train_super$v.json" 2> "$OUT/bench_train_super$v.err" )
+done
+cat "$OUT/summary.txt"
