@@ -26,4 +26,11 @@ for v in 0 1 2; do
   ( export PNNP_CONV_SUPER=$v PNNP_CONVT_FAST=$((v>0)); timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
       > "$OUT/bench_train_super$v.json" 2> "$OUT/bench_train_super$v.err" )
 done
+# end-to-end synthesis (pinned host in / out): chunk size x stream count of HostSynthPipeline (defaults 8 x 3)
+for cfg in "8 3" "4 3" "2 3" "2 4" "4 4" "16 3"; do
+  set -- $cfg
+  ( export PNNP_E2E_CHUNK=$1 PNNP_E2E_STREAMS=$2; timeout 120 python bench.py --steps 30 --warmup 5 --no-cpu-baseline \
+      > "$OUT/bench_synth_chunk$1_streams$2.json" 2> /dev/null )
+  echo "synth64 e2e chunk=$1 streams=$2: $(python -c "import json,sys; print(json.load(open('$OUT/bench_synth_chunk$1_streams$2.json'))['e2e']['value'])" 2>/dev/null)" | tee -a "$OUT/summary.txt"
+done
 cat "$OUT/summary.txt"
