@@ -126,10 +126,15 @@ constexpr int EPI_CONVT = 16;           // bit 4: ConvTranspose2d pixel-shuffle 
 // rows 0-7 into accumulator buffer a, rows 8-15 (A descriptor start + 128 pixel rows) into buffer a + 1 — so the producer <-> MMA
 // hand-shake, which bounds the small-K full-resolution layers, is paid once per 256 pixels, and a tile's halo
 // rows are 2 in 18 instead of 2 in 10.  Epilogue group g drains buffer g = half (g & 1) of every (groups / 2)-th super-tile.
-template <int TPS, int K16S, int EPI, int SUP = 0>
+// VAR bit 0 = SUP (above); bit 1 = PDL: the kernel is launched with programmatic stream serialization and waits for the previous
+// grid of the stream before its first global-memory access (see the top of the body).  Both are compile-time so that the
+// default instantiations (VAR = 0) keep exactly the machine code that was measured in round 1.
+template <int TPS, int K16S, int EPI, int VAR = 0>
 __global__ void __launch_bounds__(kConvThreadsMax, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    constexpr int SUP = VAR & 1;
+    constexpr bool kPdl = (VAR & 2) != 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x stage_bytes] [barriers] [tmem slot] [bias]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -153,6 +158,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t stage_tx = (uint32_t)(p.a_bytes + (p.b_resident ? 0 : taps_per_stage * p.umma_n * p.swz));
     const int taps_total = p.mode == MODE_CONV3 ? 9 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV3X ? 3 : (p.mode == MODE_CONV2S2 ? 4 : 1)));
 
+    if constexpr (kPdl) {
+        // Programmatic dependent launch (opt-in, PNNP_CONV_PDL=1): this grid may have been scheduled while the previous kernel of
+        // the stream was still draining.  Nothing above touches global memory; every thread waits here for the previous grid to
+        // complete and flush, then lets the next conv layer's CTAs be scheduled as ours retire.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.head_out)
         for (int i = threadIdx.x; i < 4 * p.cout; i += blockDim.x)      // [channel][4 outputs], zero beyond head_cout
@@ -750,21 +762,39 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
-#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                   PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_SUPER_VARIANT(X)
+#undef X
+#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
         attr_done = true;
     }
     const int k16s = kc / 16;
+    // Programmatic dependent launch (opt-in until measured): the kernel waits (griddepcontrol.wait) before its first global access
+    const bool pdl = getenv("PNNP_CONV_PDL") && atoi(getenv("PNNP_CONV_PDL")) > 0;
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t pdl_cfg = {};
+    pdl_cfg.gridDim = dim3((unsigned)grid); pdl_cfg.blockDim = dim3((unsigned)(64 + 128 * groups)); pdl_cfg.dynamicSmemBytes = smem;
+    pdl_cfg.stream = st; pdl_cfg.attrs = pdl_attr; pdl_cfg.numAttrs = 1;
     bool launched = false;
     if (sup) {
         if (groups & 1) return fail("conv: the super-tile variant needs an even number of accumulator buffers (internal)");
-#define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { conv_gemm_tc_kernel<T, K, E, 1><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
+#define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
+        if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 3>, tmA0, tmA1, tmB, p)); \
+        else conv_gemm_tc_kernel<T, K, E, 1><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \
+        launched = true; }
         PNNP_FOR_EACH_SUPER_VARIANT(X)
 #undef X
         if (!launched) return fail("conv: no super-tile kernel variant for this (K chunk, epilogue)");
     }
-#define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { conv_gemm_tc_kernel<T, K, E><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); launched = true; }
+#define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
+        if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 2>, tmA0, tmA1, tmB, p)); \
+        else conv_gemm_tc_kernel<T, K, E><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \
+        launched = true; }
     PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
     if (!launched) return fail("conv: no kernel variant for this (taps per stage, K chunk)");

@@ -7,7 +7,9 @@ environment variable that is off by default, and these tests are opt-in too (PNN
   fused max-pool, fused 1x1 head and the masked data-gradient epilogue alike.
 * PNNP_CONVT_FAST=1 — ConvTranspose2d layers: compile-time specialised pixel-shuffle epilogue, weights resident in shared memory
   when 4 * cout <= 256, two CTAs per SM for the K = 64 layer.  Bit-identical to the default.
-* PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default."""
+* PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default.
+* PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
+  layer's tail; `griddepcontrol.wait` before the first global access).  Bit-identical to the default."""
 import os
 
 import pytest
@@ -159,9 +161,32 @@ def test_all_variants_together_leave_the_unet_forward_unchanged(monkeypatch):
     x = torch.rand((1, 4, 304, 400), device="cuda")
     with torch.no_grad():
         want = net(x).clone()
-        for k, v in (("PNNP_CONV_SUPER", "1"), ("PNNP_CONVT_FAST", "1"), ("PNNP_IN_V2", "1")):
+        for k, v in (("PNNP_CONV_SUPER", "1"), ("PNNP_CONVT_FAST", "1"), ("PNNP_IN_V2", "1"), ("PNNP_CONV_PDL", "1")):
             monkeypatch.setenv(k, v)
         got = net(x).clone()
     torch.cuda.synchronize()
     assert _lib.lib().pnnp_conv_pipeline_error() == 0
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("sup", [0, 1, 2])
+def test_programmatic_dependent_launch_leaves_both_networks_unchanged(monkeypatch, sup):
+    """Back-to-back conv layers under PDL: every layer must still see its predecessor's complete output (UNet and ResUnet,
+    repeated forwards so that a layer of forward k + 1 follows the last layer of forward k)."""
+    torch.manual_seed(6)
+    arch = {"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}
+    for cls in (P.UNetSeeInDark, P.ResUnet):
+        net = cls(arch).cuda().eval()
+        P.initialize_weights(net)
+        xs = [torch.rand((1, 4, 176, 240), device="cuda") for _ in range(4)]
+        with torch.no_grad():
+            want = [net(x).clone() for x in xs]
+            monkeypatch.setenv("PNNP_CONV_PDL", "1")
+            if sup:
+                monkeypatch.setenv("PNNP_CONV_SUPER", str(sup))
+            got = [net(x).clone() for x in xs]
+            monkeypatch.delenv("PNNP_CONV_PDL")
+            monkeypatch.delenv("PNNP_CONV_SUPER", raising=False)
+        torch.cuda.synchronize()
+        assert _lib.lib().pnnp_conv_pipeline_error() == 0
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
