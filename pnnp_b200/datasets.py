@@ -126,14 +126,20 @@ class Raw_Dataset(torch.utils.data.Dataset):
         if a["lock_wb"] is False and np.random.randint(2):          # syn_datasets.py:313-319: white-balance jitter, one item in two
             from .unprocess import random_gains
             crops.wb_jitter(hr_crops, wb, random_gains())
-        params = [sample_params(camera_type=a['camera_type']) if a['params'] is None else a['params'] for _ in range(n)]
         post = None
         if a['clip']:
             post = (-float("inf") if a['clip'] == HALF_CLIP else 0.0, 1.0)
-        # the noise is synthesised from the crops as they are (a jittered crop may exceed 1); hr is clipped afterwards (:339-342)
-        lr_crops = synthesize_batch(hr_crops, params, a['noise_code'], ori=a['ori'], post_clip=post)
+        if a['gpu_preprocess'] is False:                            # syn_datasets.py:325-337: the noise is added by the dataset
+            params = [sample_params(camera_type=a['camera_type']) if a['params'] is None else a['params'] for _ in range(n)]
+            # synthesised from the crops as they are (a jittered crop may exceed 1); hr is clipped afterwards (:339-342)
+            lr_crops = synthesize_batch(hr_crops, params, a['noise_code'], ori=a['ori'], post_clip=post)
+            ratio = torch.tensor([float(p['ratio']) for p in params], dtype=torch.float32, device=device)
+        else:                                                       # noise left to the trainer's preprocess (trainer_SID.py:449-462)
+            lr_crops = hr_crops.clone()
+            if post is not None:
+                lr_crops.clamp_(post[0], post[1])
+            ratio = torch.ones(n, dtype=torch.float32, device=device)
         if a['clip']:
             hr_crops = hr_crops.clamp_(0, 1)
-        ratio = torch.tensor([float(p['ratio']) for p in params], dtype=torch.float32, device=device)
         return {"lr": lr_crops, "hr": hr_crops, "ratio": ratio, "wb": wb,
                 "ccm": np.eye(3, dtype=np.float32), "name": f"syn_{idx:04d}"}

@@ -28,7 +28,7 @@ from .archs import ResUnet, UNetSeeInDark, initialize_weights  # noqa: F401  (re
 from .datasets import Raw_Dataset, Synthetic_ELD_Dataset, Synthetic_IMX686_Dataset, Synthetic_SID_Dataset  # noqa: F401
 from .metrics import eval_partial_sums, finish_metrics
 from .noise import synthesize_batch
-from .noise_params import HALF_CLIP
+from .noise_params import HALF_CLIP, sample_params_max
 from .utils import AverageMeter, load_weights, log, lr_lambda_from_hyper, tensor_dim5to4
 
 
@@ -221,6 +221,21 @@ class SID_Trainer(Base_Trainer):
         self.lr_lambda = lr_lambda_from_hyper(self.hyper)
         return self.lr_lambda
 
+    def preprocess_train(self, imgs_lr, imgs_hr, dst_args):
+        """The `gpu_preprocess: True` route of trainer_SID.py:449-462 + :481-485 for Raw_Dataset batches: the dataset hands over
+        clean crops, every crop gets `sample_params_max(camera_type, ratio=None)` and the float32 (torch) noise chain —
+        generate_noisy_torch's arithmetic, one fused launch for the batch — then lr.clamp(lb, 1), hr.clamp(0, 1).  As in the
+        reference only the codes 'p', 'pr', 'prq' exist on this route ('g' / 'd' raise)."""
+        n = imgs_lr.shape[0]
+        params = [sample_params_max(camera_type=dst_args['camera_type'], ratio=None) if dst_args.get('params') is None
+                  else dst_args['params'] for _ in range(n)]
+        imgs_lr = synthesize_batch(imgs_lr, params, dst_args['noise_code'], _lib.CHAIN_TORCH, ori=dst_args['ori'],
+                                   clip=bool(dst_args['clip']))
+        if dst_args['clip']:
+            lb = -np.inf if dst_args['clip'] == HALF_CLIP else 0
+            imgs_lr, imgs_hr = imgs_lr.clamp(lb, 1), imgs_hr.clamp(0, 1)
+        return imgs_lr, imgs_hr
+
     def train(self):
         """trainer_SID.py:74-180.  Per step: `batch_size` dataset items (each `crop_per_image` noisy/clean crop pairs built on
         the device by Raw_Dataset: P1 -> D2 -> S2 -> fused N1-N3) -> UNetTrainStep (forward, L1 on pred.clamp(0,1), explicit
@@ -250,6 +265,8 @@ class SID_Trainer(Base_Trainer):
                 items = [self.dst_train[int(i)] for i in batches[k]]
                 imgs_lr = torch.cat([it['lr'] for it in items]).contiguous()
                 imgs_hr = torch.cat([it['hr'] for it in items]).contiguous()
+                if dst_args['gpu_preprocess'] is not False:
+                    imgs_lr, imgs_hr = self.preprocess_train(imgs_lr, imgs_hr, dst_args)
                 losses.append(step.step(imgs_lr, imgs_hr))
             if losses:
                 with torch.no_grad():                                   # PSNR of the last batch, as the progress bar shows

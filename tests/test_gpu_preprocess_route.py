@@ -1,0 +1,88 @@
+"""The `gpu_preprocess: True` route of the reference's training loop (trainer_SID.py:449-462, :481-485): Raw_Dataset hands over
+clean crops (syn_datasets.py:325 skips the noise), the trainer draws sample_params_max per crop and applies the float32 noise
+chain of generate_noisy_torch, then clamps.  runfiles/IMX686/PNNP.yml trains through it (sample_params has no IMX686 branch)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+import oracle_np as O
+from conftest import ROOT
+from pnnp_b200 import _lib, crops
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(runfile, **kw):
+    cfg = yaml.load(open(os.path.join(ROOT, runfile)), Loader=yaml.FullLoader)["dst_train"]
+    cfg.update(kw)
+    return cfg
+
+
+def test_raw_dataset_leaves_the_noise_to_the_trainer():
+    from pnnp_b200.datasets import Raw_Dataset
+    cfg = _cfg("runfiles/SonyA7S2/PNNP.yml", H=256, W=384, patch_size=64, crop_per_image=4, gpu_preprocess=True)
+    np.random.seed(3)
+    item = Raw_Dataset(cfg)[1]
+    after_item = np.random.get_state()[1].copy()
+    assert torch.equal(item["lr"], item["hr"]) and torch.equal(item["ratio"].cpu(), torch.ones(4))
+    assert float(item["hr"].min()) >= 0 and float(item["hr"].max()) <= 1
+    np.random.seed(3)
+    crops.init_random_crop_point(128, 192, 64, 4, cfg["croptype"])
+    assert np.array_equal(after_item, np.random.get_state()[1])      # the crop points are the item's only draws: no parameters
+
+
+def test_preprocess_train_is_the_reference_loop_in_one_launch():
+    from pnnp_b200 import trainer as T
+    cfg = _cfg("runfiles/IMX686/PNNP.yml", H=256, W=384, patch_size=64, crop_per_image=6)
+    assert cfg["gpu_preprocess"] is True and cfg["noise_code"] == "prq"
+    tr = T.SID_Trainer.__new__(T.SID_Trainer)                       # preprocess_train uses no trainer state
+    g = torch.Generator(device="cuda").manual_seed(2)
+    hr = torch.rand((6, 4, 64, 64), device="cuda", generator=g) * 0.8 + 0.1
+    np.random.seed(12)
+    l0 = _lib.launch_count()
+    lr, hr2 = tr.preprocess_train(hr.clone(), hr.clone(), cfg)
+    assert _lib.launch_count() - l0 == 1                            # six crops, one fused launch
+    np.random.seed(12)
+    params = [O.sample_params_max("IMX686", ratio=None) for _ in range(6)]
+    after = np.random.get_state()[1].copy()
+    np.random.seed(12)
+    tr.preprocess_train(hr.clone(), hr.clone(), cfg)
+    assert np.array_equal(after, np.random.get_state()[1])          # same draws, same order as the reference's per-crop loop
+    assert torch.equal(hr2, hr)                                      # clip False: hr untouched
+    res = (lr - hr).cpu().numpy()
+    assert np.isfinite(res).all()
+    for i, p in enumerate(params):                                   # unbiased, and the shot-noise variance of the model: K * y * ratio / span
+        span, ratio, K = p["wp"] - p["bl"], float(p["ratio"]), float(p["K"])
+        want_var = (K * hr[i].cpu().numpy().mean() * ratio / span) + (float(p["sigR"]) ** 2 + 1 / 12 * (float(p["q"]) * span) ** 2) * (ratio / span) ** 2
+        assert abs(res[i].mean()) < 6 * np.sqrt(want_var / 256) + 1e-4                  # 256 independent row draws bound the mean's variance
+        assert 0.8 < res[i].var() / want_var < 1.25, (i, res[i].var(), want_var)
+    cfg_g = dict(cfg, noise_code="pgrq")
+    with pytest.raises(RuntimeError):                                # as in the reference: 'g' does not exist on this route
+        tr.preprocess_train(hr.clone(), hr.clone(), cfg_g)
+
+
+def test_lrid_train_mode_runs_through_the_gpu_route(tmp_path, monkeypatch):
+    from pnnp_b200 import trainer as T
+    monkeypatch.chdir(tmp_path)
+    cfg = yaml.load(open(os.path.join(ROOT, "runfiles/IMX686/PNNP.yml")), Loader=yaml.FullLoader)
+    for k in ("dst", "dst_train", "dst_eval", "dst_test"):
+        cfg[k]["H"], cfg[k]["W"], cfg[k]["synthetic_frames"] = 128, 192, 1
+        if "ratio_list" in cfg[k]:
+            cfg[k]["ratio_list"] = cfg[k]["ratio_list"][:1]
+    cfg["dst_train"].update(patch_size=32, crop_per_image=4, synthetic_frames=4)
+    cfg["hyper"].update(stop_epoch=2, save_freq=2, plot_freq=2, batch_size=2, learning_rate=1e-3, lr_scheduler="MultiStep", step_size=100)
+    cfg["fast_ckpt"], cfg["checkpoint"] = str(tmp_path / "ckpt"), str(tmp_path / "saved")
+    p = tmp_path / "run.yml"
+    p.write_text(yaml.dump(cfg))
+    np.random.seed(8)
+    torch.manual_seed(8)
+    tr = T.IMX686_Trainer(["-f", str(p), "--mode", "train"])
+    step = tr.train()
+    text = open(tmp_path / "logs" / f"log_{cfg['model_name']}.log").read()
+    l1 = [float(x) for x in re.findall(r"L1=(\d+\.\d+)", text)]
+    assert len(l1) == 2 and all(np.isfinite(l1)) and step.t == 4
+    assert os.path.exists(os.path.join(cfg["fast_ckpt"], f"{cfg['model_name']}_last_model.pth"))
