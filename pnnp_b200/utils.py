@@ -19,26 +19,25 @@ def log(string, log=None, str=False, end='\n', notime=False):
 
 
 class AverageMeter(object):
-    """utils/utils.py:88-139 without the matplotlib history plot: avg = sum / count."""
+    """utils/utils.py:88-139 without the matplotlib history plot: running sum / count; `reset` files a positive average into
+    `history` first; printing follows the reference's '{name}:{val}({avg})' format."""
 
     def __init__(self, name, fmt=':f', log=True, last_epoch=0):
-        self.name, self.fmt, self.log, self.history, self.last_epoch = name, fmt, log, [], last_epoch
-        self.reset()
+        self.name, self.fmt, self.log, self.last_epoch = name, fmt, log, last_epoch
+        self.history = []
+        self.val = self.avg = self.sum = self.count = 0
 
     def reset(self):
-        if self.log and getattr(self, "avg", 0) > 0:
+        if self.log and self.avg > 0:
             self.history.append(self.avg)
         self.val = self.avg = self.sum = self.count = 0
 
     def update(self, val, n=1):
-        self.val = val
-        self.sum += val * n
-        self.count += n
+        self.val, self.sum, self.count = val, self.sum + val * n, self.count + n
         self.avg = self.sum / self.count
 
     def __str__(self):
-        fmtstr = '{name}:{val' + self.fmt + '}({avg' + self.fmt + '})'
-        return fmtstr.format(**self.__dict__)
+        return ('{name}:{val' + self.fmt + '}({avg' + self.fmt + '})').format(name=self.name, val=self.val, avg=self.avg)
 
 
 def load_weights(model, pretrained_dict, multi_gpu=False, by_name=False):
@@ -67,29 +66,25 @@ def tensor_dim5to4(tensor):
 
 
 def get_cos_lr(step, period=1000, peak=20, lr=1e-4, ratio=0.2):
-    """base_trainer.py:141-149 — WarmUpCosine (SGDR): the rate halves every period; linear warm-up over `peak` steps from the
-    second period on; cosine from lr down to ratio * lr inside a period."""
+    """base_trainer.py:141-149 — WarmUpCosine (SGDR): cycle k of `period` steps runs at lr / 2^k; from the second cycle on the
+    first `peak` steps ramp up linearly; otherwise a half cosine from lr down to ratio * lr (same operation order as the
+    reference, so the values are equal to the last bit)."""
     import math
-    T = step // period
-    decay = 2 ** T
-    step = step % period
-    if step <= peak and T > 0:
-        mul = step / peak
+    cycle, pos = divmod(step, period)
+    if cycle > 0 and pos <= peak:
+        shape = pos / peak
     else:
-        mul = (1 - ratio) * (math.cos((step - peak) / (period - peak) * math.pi) * 0.5 + 0.5) + ratio
-    return lr * mul / decay
+        half_cos = math.cos((pos - peak) / (period - peak) * math.pi) * 0.5 + 0.5
+        shape = (1 - ratio) * half_cos + ratio
+    return lr * shape / 2 ** cycle
 
 
 def get_multistep_lr(step, period=1000, lr=1e-4, milestone=[500, 900], gamma=[0.5, 0.1], decay_base=1):
-    """base_trainer.py:151-160."""
-    decay = decay_base ** (step // period)
-    step = step % period
-    mul = 1
-    for i in range(len(milestone), 0, -1):
-        if step > milestone[i - 1]:
-            mul = gamma[i - 1]
-            break
-    return lr * mul / decay
+    """base_trainer.py:151-160: inside a cycle the factor of the LAST milestone already passed (strictly), 1 before the first;
+    cycle k divides by decay_base^k."""
+    cycle, pos = divmod(step, period)
+    passed = [g for m, g in zip(milestone, gamma) if pos > m]
+    return lr * (passed[-1] if passed else 1) / decay_base ** cycle
 
 
 def lr_lambda_from_hyper(hyper):
