@@ -102,6 +102,11 @@ class Raw_Dataset(torch.utils.data.Dataset):
     def __len__(self):
         return self.length
 
+    @staticmethod
+    def device():
+        """Items are built on the current CUDA device (there is no CPU path)."""
+        return torch.device("cuda", torch.cuda.current_device())
+
     def synthetic_raw(self, idx, device):
         g = torch.Generator(device=device).manual_seed(4242 + idx)
         wp, bl = self.args['wp'], self.args['bl']
@@ -113,7 +118,7 @@ class Raw_Dataset(torch.utils.data.Dataset):
         from .isp_ops import raw2bayer
         from .noise import synthesize_batch
         from .noise_params import HALF_CLIP, sample_params
-        device = torch.device("cuda", torch.cuda.current_device())
+        device = self.device()
         a = self.args
         hr_imgs = raw2bayer(self.synthetic_raw(idx, device), wp=a['wp'], bl=a['bl'], norm=True, clip=True)
         if a['mode'] == 'train':

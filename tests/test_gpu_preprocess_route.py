@@ -13,7 +13,10 @@ import oracle_np as O
 from conftest import ROOT
 from pnnp_b200 import _lib, crops
 
-pytestmark = pytest.mark.gpu
+# Written after round 1's GPU budget was spent: these have not run on a B200 yet, so they are opt-in (PNNP_TEST_EXPERIMENTAL=1,
+# tools/r02_sweep.sh) and the default `pytest -m gpu` run holds exactly the tests that were green on the device.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PNNP_TEST_EXPERIMENTAL") != "1", reason="not yet run on a B200: opt-in")]
 
 
 def _cfg(runfile, **kw):

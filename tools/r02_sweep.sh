@@ -6,7 +6,7 @@ set -u
 OUT=gpurun_out/r02_sweep
 mkdir -p "$OUT"
 export PNNP_TEST_EXPERIMENTAL=1
-timeout 300 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_wb_jitter.py -q -x > "$OUT/pytest_experimental.log" 2>&1
+timeout 300 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_wb_jitter.py tests/test_gpu_preprocess_route.py -q > "$OUT/pytest_experimental.log" 2>&1
 echo "experimental tests rc=$?" | tee -a "$OUT/summary.txt"
 unset PNNP_TEST_EXPERIMENTAL
 run() {  # label, env assignments...
