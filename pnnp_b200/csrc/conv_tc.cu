@@ -762,6 +762,13 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
+        attr_done = true;
+    }
+    // the opt-in instantiations are touched only once one of their switches is on: a default run loads and configures exactly
+    // the kernels it did when it was measured
+    const bool pdl = getenv("PNNP_CONV_PDL") && atoi(getenv("PNNP_CONV_PDL")) > 0;
+    static bool attr_optin_done = false;
+    if ((sup || pdl) && !attr_optin_done) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
                    PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_SUPER_VARIANT(X)
@@ -769,11 +776,10 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
-        attr_done = true;
+        attr_optin_done = true;
     }
     const int k16s = kc / 16;
     // Programmatic dependent launch (opt-in until measured): the kernel waits (griddepcontrol.wait) before its first global access
-    const bool pdl = getenv("PNNP_CONV_PDL") && atoi(getenv("PNNP_CONV_PDL")) > 0;
     cudaLaunchAttribute pdl_attr[1];
     pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
