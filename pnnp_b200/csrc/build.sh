@@ -20,3 +20,9 @@ for p in "${pids[@]:-}"; do if [[ -n "$p" ]]; then wait "$p" || rc=1; fi; done
 if [[ $rc -ne 0 ]]; then echo "build.sh: compilation FAILED" >&2; rm -f "$OUT"; exit 1; fi
 "$NVCC" -shared -cudart shared -o "$OUT" "$HERE"/_obj/*.o
 echo "built $OUT"
+# developer tools (micro-benchmarks run under gpurun; not part of the library): built when stale, never fatal
+TOOLS="$HERE/../../tools"
+if [[ -f "$TOOLS/ubench_pipeline.cu" && ( ! -x "$TOOLS/_bin/ubench_pipeline" || "$TOOLS/ubench_pipeline.cu" -nt "$TOOLS/_bin/ubench_pipeline" ) ]]; then
+  mkdir -p "$TOOLS/_bin"
+  "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o "$TOOLS/_bin/ubench_pipeline" "$TOOLS/ubench_pipeline.cu" > /dev/null 2>&1 || echo "build.sh: tools/ubench_pipeline not built (ignored)"
+fi

@@ -5,6 +5,8 @@
 set -u
 OUT=gpurun_out/r02_sweep
 mkdir -p "$OUT"
+# hand-shake micro-benchmarks (seconds): what one trip through the producer/consumer mbarrier ring costs, per signalling scheme
+if [[ -x tools/_bin/ubench_pipeline ]]; then timeout 120 tools/_bin/ubench_pipeline > "$OUT/ubench_pipeline.txt" 2>&1; echo "ubench rc=$?" | tee -a "$OUT/summary.txt"; fi
 export PNNP_TEST_EXPERIMENTAL=1
 timeout 300 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_wb_jitter.py tests/test_gpu_preprocess_route.py -q > "$OUT/pytest_experimental.log" 2>&1
 echo "experimental tests rc=$?" | tee -a "$OUT/summary.txt"
