@@ -11,6 +11,11 @@ pinned against *outputs of the live reference run in the build container*
 re-checks live whenever /root/reference is present).  Versions the goldens were made with
 are stored inside each fixture (numpy 2.3.5 / scipy 1.18.1 / torch 2.11.0).
 
+PARITY UNPINNED for one row: ``psnr`` / ``ssim`` (E2) restate scikit-image's documented defaults, but scikit-image is
+not installed in the build container, so no output of the reference's own metric calls exists to pin them against
+(DESIGN.md §2).  The third-party samplers the reference calls (NumPy ``RandomState.poisson``, SciPy ``tukeylambda.rvs``)
+are called here as well, not restated.
+
 Every function cites the reference lines it restates (paths relative to /root/reference).
 """
 from __future__ import annotations
