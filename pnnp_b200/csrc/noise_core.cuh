@@ -9,7 +9,9 @@
 // a mul+add into an FMA: the reference rounds after every NumPy / torch op.
 #pragma once
 #include <cstdint>
+#ifndef PNNP_HOST_EMUL            // tests/emul/: the CPU suite compiles this file with g++ through a shim (test infrastructure only)
 #include <cuda_runtime.h>
+#endif
 #include "../../include/pnnp_b200.h"
 
 namespace pnnp {
@@ -45,9 +47,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& rk) {
 }
 
 // single-instruction special-function wrappers (the CUDA math-library forms add denormal-range fix-up code)
+#ifndef PNNP_HOST_EMUL
 __device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+inline float lg2_approx(float x) { return log2f(x); }
+inline float ex2_approx(float x) { return exp2f(x); }
+inline float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
+#endif
 
 struct RngCtx {
     const PhiloxKeys& rk;               // lives in the kernel-parameter (constant) bank

@@ -1,0 +1,47 @@
+// Host shim for compiling pnnp_b200/csrc/noise_core.cuh with g++ (TEST INFRASTRUCTURE, tests/test_device_core_on_cpu.py).
+// It lets the CPU suite run the DEVICE source of the samplers and of the deterministic tails against the oracle and the
+// reference goldens.  Never part of the product: the library has no CPU path.
+//
+// Every CUDA intrinsic the core uses is an IEEE-754 round-to-nearest operation; with -ffp-contract=off the plain C++ operator
+// is the same operation (x86-64 SSE2 arithmetic: no excess precision).  fmaf / fma are correctly rounded in glibc.  The three
+// MUFU approximations (lg2 / ex2 / rsqrt) are replaced by libm: they only appear in the samplers, whose parity criterion is
+// statistical.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __constant__ static const
+#define __restrict__
+
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+struct float4 { float x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dsqrt_rn(double a) { return sqrt(a); }
+static inline double __drcp_rn(double a) { return 1.0 / a; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline float __double2float_rn(double a) { return (float)a; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline double __hiloint2double(int hi, int lo) {
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double d; memcpy(&d, &b, 8); return d;
+}
