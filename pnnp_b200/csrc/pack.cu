@@ -10,6 +10,7 @@
 // reads 8 samples of an even raw row and 8 of the odd row below (2 x 128-bit loads for uint16,
 // 4 for float32) and writes one float4 into each of the four planes.
 #include "abi_common.h"
+#include "pack_core.cuh"
 #include "../../include/pnnp_b200.h"
 
 namespace pnnp {
@@ -18,14 +19,6 @@ struct PackArgs {
     const void* raw; float* out; int n, H, W; double wp; double black[4]; int norm, clip;
 };
 
-__device__ __forceinline__ float norm_one(float v, double black, double wp, int norm, int clip) {
-    if (norm) {
-        const double d = __ddiv_rn(__dsub_rn((double)v, black), __dsub_rn(wp, black));
-        v = (float)d;                       // clip in float64 then round == round then clip (0 and 1 are exact)
-    }
-    if (clip) v = fminf(fmaxf(v, 0.f), 1.f);
-    return v;
-}
 
 template <typename T> struct Load8;
 template <> struct Load8<uint16_t> {
@@ -91,11 +84,6 @@ __global__ void __launch_bounds__(256) pack_norm_kernel(const PackArgs a) {
     }
 }
 
-__device__ __forceinline__ uint32_t quant_one(float v, float span, float bl) {
-    v = fminf(fmaxf(v, 0.f), 1.f);
-    v = __fadd_rn(__fmul_rn(v, span), bl);
-    return (uint32_t)__float2uint_rz(v) & 0xFFFFu;       // numpy float32 -> uint16 cast truncates
-}
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) unpack_quant_kernel(const float* packed, uint16_t* raw, int n, int h, int w,

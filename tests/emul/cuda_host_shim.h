@@ -34,6 +34,8 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline uint32_t __float2uint_rz(float a) { return a <= 0.f ? 0u : (a >= 4294967296.f ? 0xFFFFFFFFu : (uint32_t)a); }   // saturating, truncating
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
 static inline double __drcp_rn(double a) { return 1.0 / a; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }

@@ -3,6 +3,7 @@
 #define PNNP_HOST_EMUL 1
 #include "cuda_host_shim.h"
 #include "../../pnnp_b200/csrc/noise_core.cuh"
+#include "../../pnnp_b200/csrc/pack_core.cuh"
 
 using namespace pnnp;
 
@@ -82,6 +83,14 @@ void emul_div_by_const_f32(const float* a, const float* b, int n, float* out) {
 }
 void emul_div_by_const_f64(const double* a, const double* b, int n, double* out) {
     for (int i = 0; i < n; ++i) out[i] = div_rn_by_const(a[i], b[i], __drcp_rn(b[i]));
+}
+
+// pack.cu's per-sample arithmetic over arrays (one black level per call: the kernels pick black[c] by plane)
+void emul_norm_one(const float* v, int n, double black, double wp, int norm, int clip, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = norm_one(v[i], black, wp, norm, clip);
+}
+void emul_quant_one(const float* v, int n, float span, float bl, uint16_t* out) {
+    for (int i = 0; i < n; ++i) out[i] = (uint16_t)quant_one(v[i], span, bl);
 }
 
 }  // extern "C"

@@ -34,7 +34,8 @@ def core():
         pytest.skip("g++ not available")
     out = os.path.join(EMUL, "_build", "libnoise_core_host.so")
     srcs = [os.path.join(EMUL, "noise_core_host.cpp"), os.path.join(EMUL, "cuda_host_shim.h"),
-            os.path.join(ROOT, "pnnp_b200", "csrc", "noise_core.cuh"), os.path.join(ROOT, "include", "pnnp_b200.h")]
+            os.path.join(ROOT, "pnnp_b200", "csrc", "noise_core.cuh"), os.path.join(ROOT, "pnnp_b200", "csrc", "pack_core.cuh"),
+            os.path.join(ROOT, "include", "pnnp_b200.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, srcs[0]], check=True)
@@ -189,3 +190,44 @@ def test_sampler_sources_follow_their_distributions(core):
     q64, q32 = np.empty(n), np.empty(n, np.float32)
     core.emul_quant_draws(_p(w, _u32p), n, _p(q64, _f64p), _p(q32, _f32p))
     assert np.array_equal(q64, ((w & 0xFFF).astype(np.float64) + 0.5) / 4096 - 0.5) and np.array_equal(q32, (w & 0xFFF).astype(np.float32) / 4096)
+
+
+def test_pack_and_unpack_sources_are_bit_exact_vs_reference_goldens(core, golden, meta):
+    """pack.cu's per-sample arithmetic (csrc/pack_core.cuh) over EVERY sensor code: equals the tables the unmodified reference
+    produced, with per-plane bias, without normalisation, and bayer2raw(raw2bayer(x)) == clip(x, bl, wp)."""
+    import hashlib
+    g = golden("pack")
+    _u16p = C.POINTER(C.c_uint16)
+
+    def norm(v, black, wp, do_norm, clip):
+        v = np.ascontiguousarray(v, np.float32)
+        out = np.empty_like(v)
+        core.emul_norm_one(_p(v, _f32p), v.size, C.c_double(black), C.c_double(wp), int(do_norm), int(clip), _p(out, _f32p))
+        return out
+
+    def quant(v, wp, bl):
+        v = np.ascontiguousarray(v, np.float32)
+        out = np.empty(v.shape, np.uint16)
+        core.emul_quant_one(_p(v, _f32p), v.size, C.c_float(wp - bl), C.c_float(bl), out.ctypes.data_as(_u16p))
+        return out
+
+    for cam, wp, bl, n in (("sony", 16383, 512, 16384), ("imx686", 1023, 64, 1024)):
+        codes = np.arange(n, dtype=np.float32)
+        for clip in (0, 1):
+            t = norm(codes, bl, wp, True, clip)
+            assert np.array_equal(t, g[f"{cam}_clip{clip}"])
+            assert hashlib.sha1(t.tobytes()).hexdigest()[:16] == meta[f"pack_sha1_{cam}_clip{clip}"]
+        rt = quant(norm(codes, bl, wp, True, True), wp, bl)
+        assert np.array_equal(rt, np.clip(np.arange(n), bl, wp).astype(np.uint16))
+    raw = g["rand_raw"]
+    planes = lambda a: np.stack([a[0::2, 0::2], a[0::2, 1::2], a[1::2, 1::2], a[1::2, 0::2]])     # R G1 B G2 (isp_ops.py:87-90)
+    got = np.stack([norm(planes(raw)[c], 512 + b, 16383, True, True) for c, b in enumerate((1, -2, 3, 0))])
+    assert got.tobytes() == g["rand_packed_bias"].tobytes()
+    got = np.stack([norm(planes(raw)[c], 512, 16383, False, False) for c in range(4)])
+    assert got.tobytes() == g["rand_packed_nonorm"].tobytes()
+    u = g["unpack_in"].reshape(4, -1) if g["unpack_in"].ndim == 3 else g["unpack_in"].reshape(-1, 4, *g["unpack_in"].shape[-2:])[0].reshape(4, -1)
+    h, w = g["unpack_in"].shape[-2:]
+    q = quant(u, 16383, 512).reshape(4, h, w)
+    mosaic = np.empty((2 * h, 2 * w), np.uint16)
+    mosaic[0::2, 0::2], mosaic[0::2, 1::2], mosaic[1::2, 1::2], mosaic[1::2, 0::2] = q
+    assert np.array_equal(mosaic, g["unpack_out"].reshape(2 * h, 2 * w))
