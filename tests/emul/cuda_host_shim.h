@@ -47,3 +47,19 @@ static inline double __hiloint2double(int hi, int lo) {
     const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
     double d; memcpy(&d, &b, 8); return d;
 }
+
+// ---- whole kernels on the host: a grid-stride kernel without shared memory / warp collectives runs exactly when its threads
+// execute one after the other.  The driver (EMUL_LAUNCH) sets these and calls the kernel once per (block, thread).
+#define __global__
+#define __launch_bounds__(...)
+struct EmulDim3 { unsigned x, y, z; };
+static thread_local EmulDim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+#define EMUL_LAUNCH(grid, block, call)                                               \
+    do {                                                                             \
+        gridDim.x = (grid); blockDim.x = (block);                                    \
+        for (unsigned b_ = 0; b_ < (unsigned)(grid); ++b_)                           \
+            for (unsigned t_ = 0; t_ < (unsigned)(block); ++t_) { blockIdx.x = b_; threadIdx.x = t_; call; } \
+    } while (0)
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcs(const T* p) { return *p; }
+template <typename T> static inline void __stcs(T* p, const T& v) { *p = v; }

@@ -1,0 +1,83 @@
+// The grid-stride kernels of pack.cu and crop_aug.cu compiled for the HOST and run thread by thread — TEST INFRASTRUCTURE ONLY
+// (tests/test_device_kernels_on_cpu.py).  Same kernel source as the GPU build (csrc/pack_kernels.cuh, csrc/crop_kernels.cuh);
+// the entry points mirror the C ABI's argument checks only as far as the tests need.
+#define PNNP_HOST_EMUL 1
+#include "cuda_host_shim.h"
+#include "../../pnnp_b200/csrc/pack_kernels.cuh"
+#include "../../pnnp_b200/csrc/crop_kernels.cuh"
+
+using namespace pnnp;
+
+extern "C" {
+
+// grid x block are free parameters: results must not depend on them
+int emul_pack_norm_u16(const uint16_t* raw, float* out, int n, int H, int W, double wp, const double* black4, int norm, int clip,
+                       int vec, int grid, int block) {
+    PackArgs a{raw, out, n, H, W, wp, {black4[0], black4[1], black4[2], black4[3]}, norm, clip};
+    if (vec) { if ((W / 2) % 4) return 1; EMUL_LAUNCH(grid, block, (pack_norm_kernel<uint16_t, true>(a))); }
+    else EMUL_LAUNCH(grid, block, (pack_norm_kernel<uint16_t, false>(a)));
+    return 0;
+}
+int emul_pack_norm_f32(const float* raw, float* out, int n, int H, int W, double wp, const double* black4, int norm, int clip,
+                       int vec, int grid, int block) {
+    PackArgs a{raw, out, n, H, W, wp, {black4[0], black4[1], black4[2], black4[3]}, norm, clip};
+    if (vec) { if ((W / 2) % 4) return 1; EMUL_LAUNCH(grid, block, (pack_norm_kernel<float, true>(a))); }
+    else EMUL_LAUNCH(grid, block, (pack_norm_kernel<float, false>(a)));
+    return 0;
+}
+int emul_unpack_quant(const float* packed, uint16_t* raw, int n, int h, int w, float wp, float bl, int vec, int grid, int block) {
+    const float span = wp - bl;
+    if (vec) { if (w % 4) return 1; EMUL_LAUNCH(grid, block, (unpack_quant_kernel<true>(packed, raw, n, h, w, span, bl))); }
+    else EMUL_LAUNCH(grid, block, (unpack_quant_kernel<false>(packed, raw, n, h, w, span, bl)));
+    return 0;
+}
+int emul_pack_norm_dark_u16(const uint16_t* raw, const void* dark, int dark_is_f64, float* out, int n, int H, int W, double wp,
+                            const double* b, int norm, int clip, double add_mean, int use_mean, double add_bias, int use_bias,
+                            int grid, int block) {
+    if (dark_is_f64)
+        EMUL_LAUNCH(grid, block, (pack_norm_dark_kernel<double>(raw, static_cast<const double*>(dark), out, n, H, W, wp, b[0], b[1], b[2],
+                                                                b[3], norm, clip, add_mean, use_mean, add_bias, use_bias)));
+    else
+        EMUL_LAUNCH(grid, block, (pack_norm_dark_kernel<float>(raw, static_cast<const float*>(dark), out, n, H, W, wp, b[0], b[1], b[2],
+                                                               b[3], norm, clip, (float)add_mean, use_mean, (float)add_bias, use_bias)));
+    return 0;
+}
+
+int emul_crop_aug(const float* frame, float* out, int c, int h, int w, int patch, int n, const int* hs, const int* ws, const int* mode,
+                  int grid, int block) {
+    if (n < 1 || n > kMaxCrops || (patch & 3)) return 1;
+    CropArgs a{};
+    a.frame = frame; a.out = out; a.c = c; a.h = h; a.w = w; a.patch = patch; a.n = n;
+    for (int k = 0; k < n; ++k) { a.hs[k] = hs[k]; a.ws[k] = ws[k]; a.mode[k] = mode[k]; }
+    EMUL_LAUNCH(grid, block, (crop_aug_kernel(a)));
+    return 0;
+}
+static int geom(TileGeom& g, int c, int h, int w, int patch, int base) {       // crop_aug.cu: tile_geom
+    if (c < 1 || base < 0 || (base & 1) || patch <= base || (patch & 3)) return 1;
+    g.c = c; g.h = h; g.w = w; g.patch = patch; g.d = base / 2; g.l = patch - base;
+    g.nh = h / g.l + 1; g.nw = w / g.l + 1;
+    return (h + base < patch || w + base < patch || g.d >= h || g.d >= w) ? 1 : 0;
+}
+int emul_eval_crop(const float* frame, float* tiles, int c, int h, int w, int patch, int base, int grid, int block) {
+    TileGeom g;
+    if (geom(g, c, h, w, patch, base)) return 1;
+    EMUL_LAUNCH(grid, block, (eval_crop_kernel(frame, tiles, g)));
+    return 0;
+}
+int emul_eval_merge(const float* tiles, float* frame, int c, int h, int w, int patch, int base, int grid, int block) {
+    TileGeom g;
+    if (geom(g, c, h, w, patch, base)) return 1;
+    EMUL_LAUNCH(grid, block, (eval_merge_kernel(tiles, frame, g)));
+    return 0;
+}
+int emul_wb_gains(float* data, int n, int c, int h, int w, float rgb_gain, const int* kind, const double* gain, int grid, int block) {
+    const size_t plane = (size_t)h * w;
+    if (c > 8 || (plane & 3)) return 1;
+    GainArgs a{};
+    a.common = rgb_gain;
+    for (int ch = 0; ch < c; ++ch) { a.kind[ch] = kind[ch]; a.g64[ch] = gain[ch]; a.g32[ch] = (float)gain[ch]; }
+    EMUL_LAUNCH(grid, block, (wb_gains_kernel(data, plane / 4, c, (size_t)n * c * plane / 4, a)));
+    return 0;
+}
+
+}  // extern "C"
