@@ -63,3 +63,17 @@ static thread_local EmulDim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockD
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
 template <typename T> static inline void __stcs(T* p, const T& v) { *p = v; }
+
+// ---- bf16 (cuda_bf16.h): storage type + the three operations the layout kernels use
+struct __nv_bfloat16 { uint16_t x; };
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline __nv_bfloat16 emul_f2bf(float f) {                 // round to nearest even, NaN kept quiet
+    uint32_t u = __float_as_uint(f);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return __nv_bfloat16{(uint16_t)0x7FFF};
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return __nv_bfloat16{(uint16_t)(u >> 16)};
+}
+static inline float emul_bf2f(__nv_bfloat16 h) { return __uint_as_float((uint32_t)h.x << 16); }
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{emul_f2bf(a), emul_f2bf(b)}; }
+static inline __nv_bfloat16 emul_bfmax(__nv_bfloat16 a, __nv_bfloat16 b) { return emul_bf2f(a) >= emul_bf2f(b) ? a : b; }
+static inline __nv_bfloat162 __hmax2(__nv_bfloat162 a, __nv_bfloat162 b) { return __nv_bfloat162{emul_bfmax(a.x, b.x), emul_bfmax(a.y, b.y)}; }

@@ -5,6 +5,7 @@
 #include "cuda_host_shim.h"
 #include "../../pnnp_b200/csrc/pack_kernels.cuh"
 #include "../../pnnp_b200/csrc/crop_kernels.cuh"
+#include "../../pnnp_b200/csrc/layout_kernels.cuh"
 
 using namespace pnnp;
 
@@ -77,6 +78,18 @@ int emul_wb_gains(float* data, int n, int c, int h, int w, float rgb_gain, const
     a.common = rgb_gain;
     for (int ch = 0; ch < c; ++ch) { a.kind[ch] = kind[ch]; a.g64[ch] = gain[ch]; a.g32[ch] = (float)gain[ch]; }
     EMUL_LAUNCH(grid, block, (wb_gains_kernel(data, plane / 4, c, (size_t)n * c * plane / 4, a)));
+    return 0;
+}
+
+int emul_nchw_to_nhwc16(const float* in, uint16_t* out, int n, int c, int h, int w, float scale, int v2, int grid, int block) {
+    if (c > 16) return 1;
+    if (v2) { if (((size_t)h * w) & 3) return 1; EMUL_LAUNCH(grid, block, (nchw_f32_to_nhwc16_bf16_x4_kernel(in, reinterpret_cast<__nv_bfloat16*>(out), n, c, h, w, scale))); }
+    else EMUL_LAUNCH(grid, block, (nchw_f32_to_nhwc16_bf16_kernel(in, reinterpret_cast<__nv_bfloat16*>(out), n, c, h, w, scale)));
+    return 0;
+}
+int emul_maxpool2x2_nhwc(const uint16_t* in, uint16_t* out, int n, int h, int w, int c, int grid, int block) {
+    if ((c % 8) || (h & 1) || (w & 1)) return 1;
+    EMUL_LAUNCH(grid, block, (maxpool2x2_nhwc_bf16_kernel(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c)));
     return 0;
 }
 

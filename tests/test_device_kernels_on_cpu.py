@@ -28,7 +28,7 @@ def K():
         pytest.skip("g++ not available")
     out = os.path.join(EMUL, "_build", "libkernels_host.so")
     srcs = [os.path.join(EMUL, "kernels_host.cpp"), os.path.join(EMUL, "cuda_host_shim.h")] + \
-           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh")]
+           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh", "layout_kernels.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-shared", "-fPIC", "-o", out, srcs[0]],
@@ -164,3 +164,33 @@ def test_wb_gains_kernel_vs_reference_goldens(K, golden, tag):
         assert K.emul_wb_gains(_p(x, _f32p), n, c, h, w, C.c_float(float(g[f"{tag}_rgb"][0])), (C.c_int * 4)(*kind),
                                (C.c_double * 4)(*gain), *shape) == 0
         assert x.tobytes() == g[f"{tag}_out"].tobytes()
+
+
+def test_input_layout_and_pool_kernels(K):
+    """Network-input conversion NCHW fp32 -> NHWC16 bf16 (default kernel == torch's bf16 rounding; the opt-in four-pixel kernel ==
+    the default one bit for bit) and the 2x2 max-pool on NHWC bf16 == F.max_pool2d."""
+    import torch
+    import torch.nn.functional as F
+    rs = np.random.RandomState(5)
+    for (n, c, h, w), scale in (((2, 4, 6, 10), 1.0), ((1, 4, 16, 24), 0.37), ((1, 12, 8, 8), 1.0), ((3, 1, 2, 2), 2.5)):
+        x = (rs.standard_normal((n, c, h, w)) * 3).astype(np.float32)
+        xin = _aligned(x.shape, np.float32)
+        xin[...] = x
+        want = torch.zeros((n, h, w, 16), dtype=torch.bfloat16)
+        want[..., :c] = (torch.from_numpy(x) * scale).permute(0, 2, 3, 1).to(torch.bfloat16)
+        want_bits = want.view(torch.int16).numpy().view(np.uint16)
+        outs = {}
+        for v2 in (0, 1):
+            for shape in SHAPES:
+                out = _aligned((n, h, w, 16), np.uint16)
+                out[...] = 0xFFFF
+                assert K.emul_nchw_to_nhwc16(_p(xin, _f32p), _p(out, _u16p), n, c, h, w, C.c_float(scale), v2, *shape) == 0
+                assert np.array_equal(out, want_bits), (v2, shape)
+    x = torch.from_numpy(rs.standard_normal((2, 16, 12, 20)).astype(np.float32)).to(torch.bfloat16)      # NCHW
+    nhwc = _aligned((2, 12, 20, 16), np.uint16)
+    nhwc[...] = x.permute(0, 2, 3, 1).contiguous().view(torch.int16).numpy().view(np.uint16)
+    want = F.max_pool2d(x.float(), 2).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().view(torch.int16).numpy().view(np.uint16)
+    for shape in SHAPES:
+        out = _aligned((2, 6, 10, 16), np.uint16)
+        assert K.emul_maxpool2x2_nhwc(_p(nhwc, _u16p), _p(out, _u16p), 2, 12, 20, 16, *shape) == 0
+        assert np.array_equal(out, want)
