@@ -116,6 +116,12 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
     }
 }
 
+// Packed fp32 pairs (sm_100: FADD2 / FFMA2 — two IEEE operations per instruction, results identical to the scalar forms)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // ------------------------------------------------------------------------------------------ kernel
 // EPI: compile-time specialisation of the epilogue.  -1 = generic (every feature decided at run time).  >= 0 = the hot NHWC-output
 // 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
@@ -129,12 +135,15 @@ constexpr int EPI_CONVT = 16;           // bit 4: ConvTranspose2d pixel-shuffle 
 // VAR bit 0 = SUP (above); bit 1 = PDL: the kernel is launched with programmatic stream serialization and waits for the previous
 // grid of the stream before its first global-memory access (see the top of the body).  Both are compile-time so that the
 // default instantiations (VAR = 0) keep exactly the machine code that was measured in round 1.
+// VAR bit 2 = X2: the epilogue's fp32 arithmetic (x-mode partial-sum combine, bias + activation, fused 1x1 head) in packed pairs —
+// the same IEEE additions / FMAs, half the instructions (opt-in, PNNP_CONV_F32X2=1).
 template <int TPS, int K16S, int EPI, int VAR = 0>
 __global__ void __launch_bounds__(kConvThreadsMax, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     constexpr int SUP = VAR & 1;
     constexpr bool kPdl = (VAR & 2) != 0;
+    constexpr bool kX2 = (VAR & 4) != 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x stage_bytes] [barriers] [tmem slot] [bias]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -357,11 +366,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     tc_ld16(taddr + p.cout + j * 16, v0);          // dx = 1 block (own column)
                     tc_ld16(taddr + 2 * p.cout + j * 16, v2);      // dx = 2 block
                     tc_ld_wait();
+                    if constexpr (kX2) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            const float l0 = __shfl_up_sync(0xffffffffu, __uint_as_float(v[i]), 1, 16);
+                            const float l1 = __shfl_up_sync(0xffffffffu, __uint_as_float(v[i + 1]), 1, 16);
+                            const float r0 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 1, 16);
+                            const float r1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i + 1]), 1, 16);
+                            float s0, s1;          // (left + own) + right, as in the scalar form
+                            f2_unpack(f2_add(f2_add(f2_pack(l0, l1), f2_pack(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1]))), f2_pack(r0, r1)), s0, s1);
+                            v[i] = __float_as_uint(s0); v[i + 1] = __float_as_uint(s1);
+                        }
+                    } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[i]), 1, 16);
                         const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 1, 16);
                         v[i] = __float_as_uint(left + __uint_as_float(v0[i]) + right);
+                    }
                     }
                 } else {
                     tc_ld_wait();
@@ -375,7 +397,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
                 if (c0 >= p.cout) continue;               // zero-padded weight rows (warp-uniform)
                 float f[16];
-                if (out_nhwc) {                           // cout % 16 == 0: the chunk's 16 biases are four aligned float4
+                if (kX2 && out_nhwc) {
+                    const uint64_t slope2 = f2_pack(slope, slope), zero2 = f2_pack(0.0f, 0.0f);
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i4);
+                        const uint64_t a01 = f2_add(f2_pack(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1])), f2_pack(b4.x, b4.y));
+                        const uint64_t a23 = f2_add(f2_pack(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3])), f2_pack(b4.z, b4.w));
+                        float a0, a1, a2, a3, m0, m1, m2, m3;
+                        f2_unpack(a01, a0, a1); f2_unpack(a23, a2, a3);
+                        f2_unpack(f2_fma(a01, slope2, zero2), m0, m1); f2_unpack(f2_fma(a23, slope2, zero2), m2, m3);
+                        f[4 * i4] = fmaxf(a0, m0); f[4 * i4 + 1] = fmaxf(a1, m1); f[4 * i4 + 2] = fmaxf(a2, m2); f[4 * i4 + 3] = fmaxf(a3, m3);
+                    }
+                } else if (out_nhwc) {                    // cout % 16 == 0: the chunk's 16 biases are four aligned float4
 #pragma unroll
                     for (int i4 = 0; i4 < 4; ++i4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i4);
@@ -448,11 +482,23 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     }
                     if (has_head) {
                         // fused 1x1 head (conv10_1, Unet.py:93): 4 dot products over this pixel's channels, fp32
+                        if constexpr (kX2) {
+                            uint64_t h01 = f2_pack(head[0], head[1]), h23 = f2_pack(head[2], head[3]);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float4 w4 = *reinterpret_cast<const float4*>(&s_head_w[(c0 + i) * 4]);
+                                const uint64_t ff = f2_pack(f[i], f[i]);
+                                h01 = f2_fma(ff, f2_pack(w4.x, w4.y), h01);
+                                h23 = f2_fma(ff, f2_pack(w4.z, w4.w), h23);
+                            }
+                            f2_unpack(h01, head[0], head[1]); f2_unpack(h23, head[2], head[3]);
+                        } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float4 w4 = *reinterpret_cast<const float4*>(&s_head_w[(c0 + i) * 4]);
                             head[0] = fmaf(f[i], w4.x, head[0]); head[1] = fmaf(f[i], w4.y, head[1]);
                             head[2] = fmaf(f[i], w4.z, head[2]); head[3] = fmaf(f[i], w4.w, head[3]);
+                        }
                         }
                     }
                 } else if (valid) {
@@ -693,10 +739,17 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // the opt-in instantiations are touched only once one of their switches is on: a default run loads and configures exactly
     // the kernels it did when it was measured
     const bool pdl = getenv("PNNP_CONV_PDL") && atoi(getenv("PNNP_CONV_PDL")) > 0;
+    // packed-pair epilogue arithmetic: built for the specialised 3x3 epilogues, alone (VAR 4) or with both other switches (VAR 7)
+    const bool x2 = getenv("PNNP_CONV_F32X2") && atoi(getenv("PNNP_CONV_F32X2")) > 0 && epi != EPI_GENERIC && epi != EPI_CONVT &&
+                    (mode == MODE_CONV3 || mode == MODE_CONV3X) && sup == pdl;
     static bool attr_optin_done = false;
-    if ((sup || pdl) && !attr_optin_done) {
+    if ((sup || pdl || x2) && !attr_optin_done) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
                    PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PNNP_FOR_EACH_SUPER_VARIANT(X)
+#undef X
+#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                   PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_SUPER_VARIANT(X)
 #undef X
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -713,8 +766,16 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     pdl_cfg.gridDim = dim3((unsigned)grid); pdl_cfg.blockDim = dim3((unsigned)(64 + 128 * groups)); pdl_cfg.dynamicSmemBytes = smem;
     pdl_cfg.stream = st; pdl_cfg.attrs = pdl_attr; pdl_cfg.numAttrs = 1;
     bool launched = false;
-    if (sup) {
-        if (groups & 1) return fail("conv: the super-tile variant needs an even number of accumulator buffers (internal)");
+    if (sup && (groups & 1)) return fail("conv: the super-tile variant needs an even number of accumulator buffers (internal)");
+    if (x2) {
+#define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
+        if (sup) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 7>, tmA0, tmA1, tmB, p)); \
+        else conv_gemm_tc_kernel<T, K, E, 4><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \
+        launched = true; }
+        PNNP_FOR_EACH_SUPER_VARIANT(X)
+#undef X
+    }
+    if (sup && !launched) {
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
         if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 3>, tmA0, tmA1, tmB, p)); \
         else conv_gemm_tc_kernel<T, K, E, 1><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \
@@ -723,6 +784,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 #undef X
         if (!launched) return fail("conv: no super-tile kernel variant for this (K chunk, epilogue)");
     }
+
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
         if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 2>, tmA0, tmA1, tmB, p)); \
         else conv_gemm_tc_kernel<T, K, E><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \

@@ -8,6 +8,8 @@ environment variable that is off by default, and these tests are opt-in too (PNN
 * PNNP_CONVT_FAST=1 — ConvTranspose2d layers: compile-time specialised pixel-shuffle epilogue, weights resident in shared memory
   when 4 * cout <= 256, two CTAs per SM for the K = 64 layer.  Bit-identical to the default.
 * PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default.
+* PNNP_CONV_F32X2=1 — the specialised 3x3 epilogues' fp32 arithmetic in packed pairs (FADD2 / FFMA2: the same IEEE operations, 16-20 %
+  fewer epilogue instructions by SASS count).  Bit-identical to the default.  Built alone and together with SUPER + PDL.
 * PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
   layer's tail; `griddepcontrol.wait` before the first global access).  Bit-identical to the default."""
 import os
@@ -190,3 +192,44 @@ def test_programmatic_dependent_launch_leaves_both_networks_unchanged(monkeypatc
         torch.cuda.synchronize()
         assert _lib.lib().pnnp_conv_pipeline_error() == 0
         assert all(torch.equal(a, b) for a, b in zip(got, want))
+
+
+@pytest.mark.parametrize("combo", [{"PNNP_CONV_F32X2": "1"},
+                                   {"PNNP_CONV_F32X2": "1", "PNNP_CONV_SUPER": "1", "PNNP_CONV_PDL": "1"},
+                                   {"PNNP_CONV_F32X2": "1", "PNNP_CONV_SUPER": "2", "PNNP_CONV_PDL": "1"}])
+def test_packed_pair_epilogue_is_bit_identical(monkeypatch, combo):
+    """x-mode combine, bias + LeakyReLU, fused pool and fused head through FADD2 / FFMA2, per layer and for both networks."""
+    wp, b, g = _layer("conv3x", 32, 32, False)
+    x = _nhwc(torch.randn((2, 32, 40, 44), device="cuda", generator=g))
+    hw = torch.randn((4, 32), device="cuda", generator=g) / 6
+    hb = torch.randn((4,), device="cuda", generator=g) * 0.1
+    wp2, b2, _ = _layer("conv", 64, 64, False)
+    x2 = _nhwc(torch.randn((1, 64, 24, 48), device="cuda", generator=g))
+    torch.manual_seed(11)
+    nets = []
+    for cls in (P.UNetSeeInDark, P.ResUnet):
+        net = cls({"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}).cuda().eval()
+        P.initialize_weights(net)
+        nets.append(net)
+    frame = torch.rand((1, 4, 144, 208), device="cuda")
+
+    def call():
+        out = torch.zeros((2, 40, 44, 32), dtype=torch.bfloat16, device="cuda")
+        pooled = torch.zeros((2, 20, 22, 32), dtype=torch.bfloat16, device="cuda")
+        archs._conv(_lib.CONV3X, x, wp, b, out, 32, _lib.ACT_LEAKY, pool_out=pooled)
+        hout = torch.zeros((2, 4, 40, 44), dtype=torch.float32, device="cuda")
+        archs._conv(_lib.CONV3X, x, wp, b, None, 32, _lib.ACT_LEAKY, head=(hw, hb, hout))
+        out2 = torch.zeros((1, 24, 48, 64), dtype=torch.bfloat16, device="cuda")
+        archs._conv(_lib.CONV3, x2, wp2, b2, out2, 64, _lib.ACT_RELU)
+        with torch.no_grad():
+            full = [net(frame).clone() for net in nets]
+        return [out.view(torch.int16), pooled.view(torch.int16), hout, out2.view(torch.int16)] + full
+    for k in ("PNNP_CONV_F32X2", "PNNP_CONV_SUPER", "PNNP_CONV_PDL"):
+        monkeypatch.delenv(k, raising=False)
+    want = call()
+    for k, v in combo.items():
+        monkeypatch.setenv(k, v)
+    got = call()
+    torch.cuda.synchronize()
+    assert _lib.lib().pnnp_conv_pipeline_error() == 0
+    assert all(torch.equal(a, c) for a, c in zip(got, want))

@@ -23,8 +23,9 @@ run super2 PNNP_CONV_SUPER=2
 run convt PNNP_CONVT_FAST=1
 run inv2 PNNP_IN_V2=1
 run pdl PNNP_CONV_PDL=1
-run all1 PNNP_CONV_SUPER=1 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1
-run all2 PNNP_CONV_SUPER=2 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1
+run x2 PNNP_CONV_F32X2=1
+run all1 PNNP_CONV_SUPER=1 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1 PNNP_CONV_F32X2=1
+run all2 PNNP_CONV_SUPER=2 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1 PNNP_CONV_F32X2=1
 for v in 0 1 2; do
   ( export PNNP_CONV_SUPER=$v PNNP_CONVT_FAST=$((v>0)); timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
       > "$OUT/bench_train_super$v.json" 2> "$OUT/bench_train_super$v.err" )
