@@ -484,9 +484,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         // fused 1x1 head (conv10_1, Unet.py:93): 4 dot products over this pixel's channels, fp32
                         if constexpr (kX2) {
                             uint64_t h01 = f2_pack(head[0], head[1]), h23 = f2_pack(head[2], head[3]);
+                            // one base address for the chunk's 16 weight rows: indexing s_head_w[(c0 + i) * 4] per channel made the
+                            // scalar form spend five 64-bit address instructions on every load (80 of its 318 per chunk)
+                            const float4* hw4 = reinterpret_cast<const float4*>(s_head_w) + c0;
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float4 w4 = *reinterpret_cast<const float4*>(&s_head_w[(c0 + i) * 4]);
+                                const float4 w4 = hw4[i];
                                 const uint64_t ff = f2_pack(f[i], f[i]);
                                 h01 = f2_fma(ff, f2_pack(w4.x, w4.y), h01);
                                 h23 = f2_fma(ff, f2_pack(w4.z, w4.w), h23);
