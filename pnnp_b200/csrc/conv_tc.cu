@@ -144,6 +144,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     constexpr int SUP = VAR & 1;
     constexpr bool kPdl = (VAR & 2) != 0;
     constexpr bool kX2 = (VAR & 4) != 0;
+    // Super-tile variants exist only for the specialised 3x3 epilogues without debug switches, so their mode (per-tap or x-shift-in-N,
+    // bit 0 of EPI), the debug word and the swizzle span (32 bytes per K16 slice) are compile-time constants: the serial loops of the
+    // producer and MMA warps — whose instruction count IS the tile rate of the small-K layers — lose their run-time selects.
+    constexpr bool kCt = SUP != 0;
+    constexpr int kCtMode = (EPI >= 0 && (EPI & EPI_X)) ? MODE_CONV3X : MODE_CONV3;
+#define PNNP_MODE_K (kCt ? kCtMode : p.mode)        /* expressions, not locals: the default instantiations must compile exactly as before */
+#define PNNP_DBG_K (kCt ? 0 : p.dbg)
+#define PNNP_SWZ_K (kCt ? 32 * K16S : p.swz)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x stage_bytes] [barriers] [tmem slot] [bias]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -160,12 +168,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int taps_per_stage = TPS;
-    const int dx_count = p.mode == MODE_CONV3 ? 3 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV2S2 ? 4 : 1));   // pipeline stages per K chunk
+    const int dx_count = PNNP_MODE_K == MODE_CONV3 ? 3 : (PNNP_MODE_K == MODE_CONV3S2 ? 9 : (PNNP_MODE_K == MODE_CONV2S2 ? 4 : 1));   // pipeline stages per K chunk
     const int chunks0 = p.cin0 / p.kc, chunks1 = p.nsrc > 1 ? p.cin1 / p.kc : 0;
     const int ksteps = (chunks0 + chunks1) * dx_count;
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
-    const uint32_t stage_tx = (uint32_t)(p.a_bytes + (p.b_resident ? 0 : taps_per_stage * p.umma_n * p.swz));
-    const int taps_total = p.mode == MODE_CONV3 ? 9 : (p.mode == MODE_CONV3S2 ? 9 : (p.mode == MODE_CONV3X ? 3 : (p.mode == MODE_CONV2S2 ? 4 : 1)));
+    const uint32_t stage_tx = (uint32_t)(p.a_bytes + (p.b_resident ? 0 : taps_per_stage * p.umma_n * PNNP_SWZ_K));
+    const int taps_total = PNNP_MODE_K == MODE_CONV3 ? 9 : (PNNP_MODE_K == MODE_CONV3S2 ? 9 : (PNNP_MODE_K == MODE_CONV3X ? 3 : (PNNP_MODE_K == MODE_CONV2S2 ? 4 : 1)));
 
     if constexpr (kPdl) {
         // Programmatic dependent launch (opt-in, PNNP_CONV_PDL=1): this grid may have been scheduled while the previous kernel of
@@ -204,9 +212,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         // Everything the loops need is copied into registers first: the asm statements carry "memory" clobbers, so every p.field
         // used inside a loop would otherwise be re-read from the parameter bank per tile, and for the small-K full-resolution
         // layers (one pipeline stage per tile) this single warp's serial instruction stream IS the tile rate.
-        const int mode = p.mode, n_tiles = p.n_tiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, umma_n = p.umma_n, kc = p.kc;
+        const int mode = PNNP_MODE_K, n_tiles = p.n_tiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, umma_n = p.umma_n, kc = kCt ? 16 * K16S : p.kc;
         const int cin0 = p.cin0, stages = p.stages, stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, b_tap_bytes = p.b_tap_stride;
-        const int dbg = p.dbg;
+        const int dbg = PNNP_DBG_K;
         const bool b_res = p.b_resident != 0;
         int* const err = p.err;
         const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
@@ -217,7 +225,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         if (b_res && elect_one()) {
             // weights for every (K chunk, tap) once per CTA: layout [chunk][tap][umma_n rows x swz bytes]
             const uint32_t bb = smem_u32(bres_bar);
-            mbar_expect_tx(bb, (uint32_t)((chunks0 + chunks1) * taps_total * umma_n * p.swz));
+            mbar_expect_tx(bb, (uint32_t)((chunks0 + chunks1) * taps_total * umma_n * PNNP_SWZ_K));
             for (int ch = 0; ch < chunks0 + chunks1; ++ch)
                 for (int tap = 0; tap < taps_total; ++tap)
                     tma_load_3d(smem_u32(smem_bres) + (ch * taps_total + tap) * b_tap_bytes, &tmB, bb, ch * kc, 0, tap);
@@ -264,20 +272,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
         // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-        const int mode = p.mode, umma_n = p.umma_n, stages = p.stages, stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, dbg = p.dbg;
+        const int mode = PNNP_MODE_K, umma_n = p.umma_n, stages = p.stages, stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, dbg = PNNP_DBG_K;
         const int groups = p.groups;
         const bool b_res = p.b_resident != 0;
         int* const err = p.err;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-        const uint64_t dhi = umma_desc_hi(p.swz);
-        const uint32_t a_tap_stride = (uint32_t)(kTileW * p.swz) >> 4;      // descriptor units (16 B)
+        const uint64_t dhi = umma_desc_hi(PNNP_SWZ_K);
+        const uint32_t a_tap_stride = (uint32_t)(kTileW * PNNP_SWZ_K) >> 4;      // descriptor units (16 B)
         const uint32_t b_tap_stride = (uint32_t)p.b_tap_stride >> 4;
         const uint32_t b_tap_bytes = (uint32_t)p.b_tap_stride;
         const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
         const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar), bres0 = smem_u32(smem_bres);
         // resident layout [chunk][tap]: CONV3 stage dx uses taps dy*3+dx (stride 3 taps); CONV3X: dy taps are consecutive
         const uint32_t b_stride_eff = (b_res && mode == MODE_CONV3) ? 3 * b_tap_stride : b_tap_stride;
-        const uint32_t a_half = (uint32_t)(kTileH * kTileW * p.swz) >> 4;   // SUP: second tile's A rows start 8 x 16 pixel rows further
+        const uint32_t a_half = (uint32_t)(kTileH * kTileW * PNNP_SWZ_K) >> 4;   // SUP: second tile's A rows start 8 x 16 pixel rows further
         if (b_res) mbar_wait(smem_u32(bres_bar), 0, err, 105);
         const int dxc = mode == MODE_CONV3 ? 3 : (mode == MODE_CONV3S2 ? 9 : (mode == MODE_CONV2S2 ? 4 : 1));
         const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -341,7 +349,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int chunks16 = (xmode ? p.cout : p.umma_n) / 16;
         TileIter ti;
         ti.init(total_tiles, p.n_tiles, p.tiles_x, p.tiles_y);
-        if (p.dbg & 32) ti.t = ti.t_end;
+        if (PNNP_DBG_K & 32) ti.t = ti.t_end;
         const int slot = SUP ? group >> 1 : group, n_slots = SUP ? p.groups >> 1 : p.groups;     // SUP: two groups share a super-tile
         const int y_in = SUP ? (group & 1) * kTileH + ty_in : ty_in, tile_rows = SUP ? 2 * kTileH : kTileH;
         for (int g = 0; g < slot && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);   // slot s: every n_slots-th tile
@@ -353,7 +361,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * (uint32_t)p.umma_n + ((uint32_t)(quad * 32) << 16);
-            if (p.dbg & 8) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc])); acc_phase ^= 1; continue; }
+            if (PNNP_DBG_K & 8) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc])); acc_phase ^= 1; continue; }
             const int col_tile0 = n_tile * p.umma_n;     // first GEMM column of this tile
             const size_t pix_in = ((size_t)img * p.H + y) * (size_t)p.W + x;
             float head[4] = {0.f, 0.f, 0.f, 0.f};
@@ -455,7 +463,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                         pk[i] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    if (p.out && valid && !(p.dbg & 1)) {
+                    if (p.out && valid && !(PNNP_DBG_K & 1)) {
                         uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0);
                         op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -473,7 +481,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
                             pk[i] = *reinterpret_cast<uint32_t*>(&a);
                         }
-                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16) && !(p.dbg & 1)) {
+                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16) && !(PNNP_DBG_K & 1)) {
                             const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
                             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pp * p.cout_stride + c0);
                             op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -539,6 +547,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
     }
 }
+#undef PNNP_MODE_K
+#undef PNNP_DBG_K
+#undef PNNP_SWZ_K
 
 }  // namespace pnnp
 #include "layout_kernels.cuh"      // nchw_f32_to_nhwc16_bf16_kernel(s), maxpool2x2_nhwc_bf16_kernel
