@@ -365,6 +365,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const int col_tile0 = n_tile * p.umma_n;     // first GEMM column of this tile
             const size_t pix_in = ((size_t)img * p.H + y) * (size_t)p.W + x;
             float head[4] = {0.f, 0.f, 0.f, 0.f};
+            // specialised ConvTranspose2d epilogue: (tap, channel block) of chunk j kept as a running pair — one division per tile
+            constexpr bool kCtT = EPI >= 0 && (EPI & EPI_CONVT) != 0;
+            int t_cpt = 1, t_tap = 0, t_rem = 0;
+            if constexpr (kCtT) { t_cpt = p.cout >> 4; t_tap = (col_tile0 >> 4) / t_cpt; t_rem = (col_tile0 >> 4) - t_tap * t_cpt; }
             for (int j = 0; j < chunks16; ++j) {
                 uint32_t v[16];
                 tc_ld16(taddr + j * 16, v);
@@ -398,14 +402,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
                 int c0 = col_tile0 + j * 16;              // output channel of v[0]
                 size_t opix = pix_in;
-                if (is_convt) {                           // GEMM column = (a*2+b)*cout + co  ->  pixel (2y+a, 2x+b)
+                if constexpr (kCtT) {
+                    const int tap = t_tap;
+                    c0 = t_rem << 4;
+                    if (++t_rem == t_cpt) { t_rem = 0; ++t_tap; }
+                    opix = ((size_t)img * (2 * p.H) + (2 * y + (tap >> 1))) * (size_t)(2 * p.W) + (2 * x + (tap & 1));
+                } else if (is_convt) {                    // GEMM column = (a*2+b)*cout + co  ->  pixel (2y+a, 2x+b)
                     const int tap = c0 / p.cout;
                     c0 -= tap * p.cout;
                     opix = ((size_t)img * (2 * p.H) + (2 * y + (tap >> 1))) * (size_t)(2 * p.W) + (2 * x + (tap & 1));
                 }
                 if (c0 >= p.cout) continue;               // zero-padded weight rows (warp-uniform)
                 float f[16];
-                if (kX2 && out_nhwc) {
+                if constexpr (kCtT) {                     // bias only: the launcher takes this epilogue for act == NONE (identity) alone
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i4);
+                        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1])), f2_pack(b4.x, b4.y)), f[4 * i4], f[4 * i4 + 1]);
+                        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3])), f2_pack(b4.z, b4.w)), f[4 * i4 + 2], f[4 * i4 + 3]);
+                    }
+                } else if (kX2 && out_nhwc) {
                     const uint64_t slope2 = f2_pack(slope, slope), zero2 = f2_pack(0.0f, 0.0f);
 #pragma unroll
                     for (int i4 = 0; i4 < 4; ++i4) {
@@ -663,7 +679,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         !(d.pool_out && d.head_out) && !(d.mask && (mode == MODE_CONV3X || d.pool_out || d.head_out)))
         epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
     if (convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
-        !no_spec && !dbg_env)
+        act == ACT_NONE && !no_spec && !dbg_env)
         epi = EPI_CONVT;
     const bool sup = super_env > 0 && mode != MODE_CONVT && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
     const int tile_rows = sup ? 2 * kTileH : kTileH;
