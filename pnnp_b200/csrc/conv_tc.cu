@@ -144,11 +144,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     constexpr int SUP = VAR & 1;
     constexpr bool kPdl = (VAR & 2) != 0;
     constexpr bool kX2 = (VAR & 4) != 0;
-    // Super-tile variants exist only for the specialised 3x3 epilogues without debug switches, so their mode (per-tap or x-shift-in-N,
-    // bit 0 of EPI), the debug word and the swizzle span (32 bytes per K16 slice) are compile-time constants: the serial loops of the
+    // Opt-in variants (VAR != 0) with a specialised epilogue are never launched with debug switches, so their mode (bits 0 / 4 of
+    // EPI), the debug word and the swizzle span (32 bytes per K16 slice) are compile-time constants: the serial loops of the
     // producer and MMA warps — whose instruction count IS the tile rate of the small-K layers — lose their run-time selects.
-    constexpr bool kCt = SUP != 0;
-    constexpr int kCtMode = (EPI >= 0 && (EPI & EPI_X)) ? MODE_CONV3X : MODE_CONV3;
+    constexpr bool kCt = VAR != 0 && EPI >= 0;       // every opt-in instantiation with a specialised epilogue (the launcher never
+    constexpr int kCtMode = (EPI >= 0 && (EPI & EPI_CONVT)) ? MODE_CONVT : ((EPI >= 0 && (EPI & EPI_X)) ? MODE_CONV3X : MODE_CONV3);   // pairs those with debug switches)
 #define PNNP_MODE_K (kCt ? kCtMode : p.mode)        /* expressions, not locals: the default instantiations must compile exactly as before */
 #define PNNP_DBG_K (kCt ? 0 : p.dbg)
 #define PNNP_SWZ_K (kCt ? 32 * K16S : p.swz)
