@@ -12,7 +12,9 @@
 //
 // sums layout per frame (double): [0] num  [1] den  [2] sum sq err (x255 domain)
 //                                 [3 .. 3+c) per-channel sum of the SSIM map over valid centres
+#include <cstdlib>
 #include "abi_common.h"
+#include "ssim_core.cuh"
 #include "../../include/pnnp_b200.h"
 
 namespace pnnp {
@@ -108,6 +110,24 @@ __global__ void __launch_bounds__(256) ssim_mse_kernel(const float* __restrict__
     if (threadIdx.x == 0) { atomicAdd(&sums[frame * stride + 2], se); atomicAdd(&sums[frame * stride + 3 + ch], ssum); }
 }
 
+// pass 2, separable form (ssim_core.cuh): one block = one 32 x 16 tile of window centres of one (frame, channel) plane
+__global__ void __launch_bounds__(kS2Threads) ssim_mse_v2_kernel(Ssim2Args g, double* sums, int stride) {
+    extern __shared__ __align__(16) uint8_t s2_raw[];
+    Ssim2Tile& t = *reinterpret_cast<Ssim2Tile*>(s2_raw);
+    __shared__ double s_red[8];
+    const int plane_id = blockIdx.z, frame = plane_id / g.c, ch = plane_id - frame * g.c;
+    if (g.use_gain) g.gain = (float)sums[frame * stride + 0] / (float)sums[frame * stride + 1];   // num / den in float32 like torch
+    const int x0 = blockIdx.x * kS2TileX, y0 = blockIdx.y * kS2TileY;
+    double se = ssim2_load(threadIdx.x, g, plane_id, x0, y0, t);
+    __syncthreads();
+    ssim2_hsum(threadIdx.x, t);
+    __syncthreads();
+    double ssum = ssim2_vsum(threadIdx.x, g, x0, y0, t);
+    se = block_reduce_sum(se, s_red);
+    ssum = block_reduce_sum(ssum, s_red);
+    if (threadIdx.x == 0) { atomicAdd(&sums[frame * stride + 2], se); atomicAdd(&sums[frame * stride + 3 + ch], ssum); }
+}
+
 }  // namespace pnnp
 
 using namespace pnnp;
@@ -124,6 +144,19 @@ extern "C" int pnnp_eval_epilogue(const float* dn, const float* hr, int n, int c
         dim3 g((unsigned)std::min<size_t>((per_frame + 255) / 256, 592), (unsigned)n);
         illum_dots_kernel<<<g, 256, 0, st>>>(dn, hr, per_frame, scale, sums, stride);
         count_launch();
+    }
+    if (getenv("PNNP_SSIM_V2") && atoi(getenv("PNNP_SSIM_V2")) > 0) {          // opt-in separable form (ssim_core.cuh)
+        static bool attr_done = false;
+        if (!attr_done) {
+            PNNP_CUDA(cudaFuncSetAttribute(ssim_mse_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ssim2Tile)));
+            attr_done = true;
+        }
+        Ssim2Args a{dn, hr, c, h, w, scale, 1.0f, brightness_correct};
+        dim3 gv((w + kS2TileX - 1) / kS2TileX, (h + kS2TileY - 1) / kS2TileY, n * c);
+        ssim_mse_v2_kernel<<<gv, kS2Threads, sizeof(Ssim2Tile), st>>>(a, sums, stride);
+        count_launch();
+        PNNP_CUDA(cudaGetLastError());
+        return 0;
     }
     dim3 g2((w + kTileX - 1) / kTileX, (h + kTileY - 1) / kTileY, n * c);
     ssim_mse_kernel<<<g2, 256, 0, st>>>(dn, hr, c, h, w, scale, brightness_correct, sums, stride);

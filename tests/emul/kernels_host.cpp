@@ -6,6 +6,7 @@
 #include "../../pnnp_b200/csrc/pack_kernels.cuh"
 #include "../../pnnp_b200/csrc/crop_kernels.cuh"
 #include "../../pnnp_b200/csrc/layout_kernels.cuh"
+#include "../../pnnp_b200/csrc/ssim_core.cuh"
 
 using namespace pnnp;
 
@@ -90,6 +91,30 @@ int emul_nchw_to_nhwc16(const float* in, uint16_t* out, int n, int c, int h, int
 int emul_maxpool2x2_nhwc(const uint16_t* in, uint16_t* out, int n, int h, int w, int c, int grid, int block) {
     if ((c % 8) || (h & 1) || (w & 1)) return 1;
     EMUL_LAUNCH(grid, block, (maxpool2x2_nhwc_bf16_kernel(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c)));
+    return 0;
+}
+
+// ssim_mse_v2_kernel (eval_metrics.cu) phase by phase: every phase runs for all 256 threads of a block before the next one starts,
+// which is what the __syncthreads() between them guarantees on the device.  sums: n x (3 + c) doubles as pnnp_eval_epilogue
+// lays them out ([0], [1] = illuminance dots, supplied by the caller when use_gain).
+int emul_ssim_mse_v2(const float* dn, const float* hr, int n, int c, int h, int w, float scale, int use_gain, double* sums) {
+    static Ssim2Tile tile;
+    const int stride = 3 + c;
+    for (int plane = 0; plane < n * c; ++plane) {
+        const int frame = plane / c, ch = plane - frame * c;
+        Ssim2Args g{dn, hr, c, h, w, scale, 1.0f, use_gain};
+        if (use_gain) g.gain = (float)sums[frame * stride + 0] / (float)sums[frame * stride + 1];
+        for (int by = 0; by < (h + kS2TileY - 1) / kS2TileY; ++by)
+            for (int bx = 0; bx < (w + kS2TileX - 1) / kS2TileX; ++bx) {
+                const int x0 = bx * kS2TileX, y0 = by * kS2TileY;
+                double se = 0.0, ssum = 0.0;
+                for (int tid = 0; tid < kS2Threads; ++tid) se += ssim2_load(tid, g, plane, x0, y0, tile);
+                for (int tid = 0; tid < kS2Threads; ++tid) ssim2_hsum(tid, tile);
+                for (int tid = 0; tid < kS2Threads; ++tid) ssum += ssim2_vsum(tid, g, x0, y0, tile);
+                sums[frame * stride + 2] += se;
+                sums[frame * stride + 3 + ch] += ssum;
+            }
+    }
     return 0;
 }
 

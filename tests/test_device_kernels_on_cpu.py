@@ -28,7 +28,7 @@ def K():
         pytest.skip("g++ not available")
     out = os.path.join(EMUL, "_build", "libkernels_host.so")
     srcs = [os.path.join(EMUL, "kernels_host.cpp"), os.path.join(EMUL, "cuda_host_shim.h")] + \
-           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh", "layout_kernels.cuh")]
+           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh", "layout_kernels.cuh", "ssim_core.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-shared", "-fPIC", "-o", out, srcs[0]],
@@ -194,3 +194,32 @@ def test_input_layout_and_pool_kernels(K):
         out = _aligned((2, 6, 10, 16), np.uint16)
         assert K.emul_maxpool2x2_nhwc(_p(nhwc, _u16p), _p(out, _u16p), 2, 12, 20, 16, *shape) == 0
         assert np.array_equal(out, want)
+
+
+def test_separable_ssim_phases_vs_oracle(K):
+    """The opt-in separable SSIM / squared-error pass (csrc/ssim_core.cuh), phase by phase as the device runs it between its
+    __syncthreads(): PSNR / SSIM from its partial sums == the oracle's restatement of skimage's defaults, including frames that
+    are not multiples of the 32 x 16 tile, scaling + clamping of the estimate, and the IlluminanceCorrect gain."""
+    import math
+    rs = np.random.RandomState(7)
+    for (n, c, h, w), scale, use_gain in (((1, 4, 40, 56), 1.0, 0), ((2, 3, 23, 37), 1.7, 0), ((1, 4, 64, 96), 1.0, 1), ((1, 1, 7, 7), 1.0, 0)):
+        hr = rs.rand(n, c, h, w).astype(np.float32)
+        dn = np.clip(hr + rs.standard_normal((n, c, h, w)).astype(np.float32) * 0.08, -0.2, 1.3).astype(np.float32) / np.float32(scale)
+        sums = np.zeros((n, 3 + c), np.float64)
+        est = []
+        for f in range(n):
+            p = np.clip(dn[f] * np.float32(scale), 0, 1).astype(np.float32)
+            if use_gain:
+                m = hr[f] != 1.0
+                num, den = float((p[m].astype(np.float64) * hr[f][m]).sum()), float((p[m].astype(np.float64) ** 2).sum())
+                sums[f, 0], sums[f, 1] = num, den
+                p = (np.float32(num) / np.float32(den)) * p
+            est.append(p)
+        assert K.emul_ssim_mse_v2(_p(np.ascontiguousarray(dn), _f32p), _p(hr, _f32p), n, c, h, w, C.c_float(scale), use_gain,
+                                  _p(sums, _f64p)) == 0
+        for f in range(n):
+            X, Y = O.tensor2im(hr[f:f + 1]), O.tensor2im(est[f][None])                         # target, estimate as HWC x255
+            mse = sums[f, 2] / (c * h * w)
+            assert abs(10.0 * math.log10(255.0 ** 2 / mse) - O.psnr(X, Y)) < 1e-9
+            ssim = sums[f, 3:3 + c].sum() / (c * (h - 6) * (w - 6))
+            assert abs(ssim - O.ssim(X, Y)) < 1e-9, (ssim, O.ssim(X, Y))

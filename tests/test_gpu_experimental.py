@@ -10,6 +10,8 @@ environment variable that is off by default, and these tests are opt-in too (PNN
 * PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default.
 * PNNP_CONV_F32X2=1 — the specialised 3x3 epilogues' fp32 arithmetic in packed pairs (FADD2 / FFMA2: the same IEEE operations, 16-20 %
   fewer epilogue instructions by SASS count).  Bit-identical to the default.  Built alone and together with SUPER + PDL.
+* PNNP_SSIM_V2=1 — separable 7x7 window sums in the eval epilogue (csrc/ssim_core.cuh; the same source is run phase by phase on the
+  CPU against the oracle in tests/test_device_kernels_on_cpu.py).  Equal to the default kernel's sums to float64 summation order.
 * PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
   layer's tail; `griddepcontrol.wait` before the first global access).  Bit-identical to the default."""
 import os
@@ -233,3 +235,16 @@ def test_packed_pair_epilogue_is_bit_identical(monkeypatch, combo):
     torch.cuda.synchronize()
     assert _lib.lib().pnnp_conv_pipeline_error() == 0
     assert all(torch.equal(a, c) for a, c in zip(got, want))
+
+
+@pytest.mark.parametrize("shape,scale,correct", [((1, 4, 64, 96), 1.0, False), ((2, 3, 45, 70), 1.5, False), ((1, 4, 128, 192), 1.0, True)])
+def test_separable_ssim_equals_default_kernel(monkeypatch, shape, scale, correct):
+    from pnnp_b200.metrics import eval_partial_sums
+    g = torch.Generator(device="cuda").manual_seed(9)
+    hr = torch.rand(shape, device="cuda", generator=g)
+    dn = ((hr + 0.07 * torch.randn(shape, device="cuda", generator=g)) / scale).contiguous()
+    monkeypatch.delenv("PNNP_SSIM_V2", raising=False)
+    want = eval_partial_sums(dn, hr, scale, correct).clone()
+    monkeypatch.setenv("PNNP_SSIM_V2", "1")
+    got = eval_partial_sums(dn, hr, scale, correct)
+    assert torch.allclose(got, want, rtol=1e-11, atol=1e-9), (got, want)

@@ -30,6 +30,11 @@ for v in 0 1 2; do
   ( export PNNP_CONV_SUPER=$v PNNP_CONVT_FAST=$((v>0)); timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
       > "$OUT/bench_train_super$v.json" 2> "$OUT/bench_train_super$v.err" )
 done
+for v in 0 1; do
+  ( export PNNP_SSIM_V2=$v; timeout 200 python bench.py --workload sony_evaltest --steps 30 --warmup 5 --no-cpu-baseline \
+      > "$OUT/bench_evaltest_ssim$v.json" 2> /dev/null )
+  echo "sony_evaltest PNNP_SSIM_V2=$v: $(python -c "import json; d=json.load(open('$OUT/bench_evaltest_ssim$v.json')); print(d['ms_per_step'], 'ms/frame')" 2>/dev/null)" | tee -a "$OUT/summary.txt"
+done
 # end-to-end synthesis (pinned host in / out): chunk size x stream count of HostSynthPipeline (defaults 8 x 3)
 for cfg in "8 3" "4 3" "2 3" "2 4" "4 4" "16 3"; do
   set -- $cfg
