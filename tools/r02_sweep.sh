@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 first GPU call: correctness of the opt-in kernel variants written without a GPU at the end of round 1, then their timing.
-#   gpurun --timeout 900 -- 'bash tools/r02_sweep.sh'
+#   gpurun --timeout 1500 -- 'bash tools/r02_sweep.sh'      (about 13 minutes of box time)
 # Everything lands in gpurun_out/r02_sweep/.  Order: cheap correctness first, so a hang / failure is seen before time is spent.
 set -u
 OUT=gpurun_out/r02_sweep
