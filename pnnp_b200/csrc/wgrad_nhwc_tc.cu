@@ -62,6 +62,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_hi(int swz, int lbo_bytes) {
     return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
+// VAR 1 (OPT-IN, PNNP_WGRAD_V2=1, until measured): the producer and MMA warps — one warp each, so the instruction count of their
+// per-stage loops is the stage rate (352 and 139 SASS instructions in VAR 0: two integer divisions and a walk over the box / MMA
+// tables in the kernel-parameter bank per stage) — keep everything that does not change from stage to stage in registers: the
+// boxes' coordinates offsets, shared-memory offsets and tensor maps, the MMAs' descriptors, the (image, tile row, tile column) of the
+// stage advanced by increment-and-carry, the stage's barrier / buffer addresses advanced by a constant.  Same loads, same MMAs.
+template <int VAR>
 __global__ void __launch_bounds__(192, 1)
 wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -98,7 +104,81 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (VAR == 1 && warp == 0) {
+        // ============================== TMA producer, loop-invariant state in registers ==============================
+        int bc0[kWnMaxBoxes], bdx[kWnMaxBoxes], bdy[kWnMaxBoxes], bmul[kWnMaxBoxes], boff[kWnMaxBoxes];
+        bool bisx[kWnMaxBoxes];
+#pragma unroll
+        for (int b = 0; b < kWnMaxBoxes; ++b) {
+            const WnBox& bx = p.box[b < p.n_boxes ? b : 0];
+            bisx[b] = bx.is_x != 0;
+            bc0[b] = bx.c0 + (bx.is_x ? nt * p.ci_tile : mt * 128);
+            bdx[b] = bx.by_ts == 1 ? ts - 1 : (bx.by_ts == 2 ? (ts & 1) : bx.dx);
+            bdy[b] = bx.by_ts == 2 ? (ts >> 1) : bx.dy;
+            bmul[b] = bx.mul; boff[b] = bx.smem_off;
+        }
+        const int n_boxes = p.n_boxes, tiles_x = p.tiles_x, tiles_y = p.tiles_y, stages = p.stages, stage_bytes = p.stage_bytes;
+        const uint32_t stage_tx = (uint32_t)p.stage_tx, smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        int* const err = p.err;
+        const int tiles_img = tiles_x * tiles_y;
+        int img = t_begin / tiles_img, ty = (t_begin - img * tiles_img) / tiles_x, tx = t_begin - img * tiles_img - ty * tiles_x;
+        uint32_t stage = 0, phase = 0, sa = smem0, fb = full0, eb = empty0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int X0 = tx * kWnTileW, Y0 = ty * kWnTileH;
+            mbar_wait(eb, phase ^ 1, err, 301);
+            if (elect_one()) {
+                mbar_expect_tx(fb, stage_tx);
+#pragma unroll
+                for (int b = 0; b < kWnMaxBoxes; ++b)
+                    if (b < n_boxes)
+                        tma_load_4d(sa + (uint32_t)boff[b], bisx[b] ? &tmX : &tmG, fb, bc0[b], X0 * bmul[b] + bdx[b], Y0 * bmul[b] + bdy[b], img);
+            }
+            __syncwarp();
+            if (++tx == tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
+            sa += (uint32_t)stage_bytes; fb += 8; eb += 8;
+            if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; sa = smem0; fb = full0; eb = empty0; }
+        }
+    } else if (VAR == 1 && warp == 1) {
+        // ============================== MMA issuer, descriptors in registers ==============================
+        const uint64_t ahi = umma_desc_mn_hi(p.swz_a, p.lbo_a);
+        const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t kstep_a = (uint32_t)(16 * p.pitch_a) >> 4, kstep_b = (uint32_t)(16 * p.pitch_b) >> 4;
+        uint32_t m_idesc[kWnMaxMmas], m_aoff[kWnMaxMmas], m_boff[kWnMaxMmas], m_col[kWnMaxMmas];
+        uint64_t m_bhi[kWnMaxMmas];
+#pragma unroll
+        for (int m = 0; m < kWnMaxMmas; ++m) {
+            const WnMma& mm = p.mma[m < p.n_mmas ? m : 0];
+            m_idesc[m] = idesc_base | ((uint32_t)(mm.n >> 3) << 17);
+            m_aoff[m] = (uint32_t)mm.a_off; m_boff[m] = (uint32_t)mm.b_off; m_col[m] = tmem_base + (uint32_t)mm.tmem_col;
+            m_bhi[m] = umma_desc_mn_hi(p.swz_b, mm.lbo_b);
+        }
+        const int n_mmas = p.n_mmas, stages = p.stages, stage_bytes = p.stage_bytes;
+        const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        int* const err = p.err;
+        uint32_t stage = 0, phase = 0, sa = smem0, fb = full0, eb = empty0;
+        for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(fb, phase, err, 303);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int m = 0; m < kWnMaxMmas; ++m) {
+                    if (m < n_mmas) {
+                        const uint64_t adesc0 = ahi | (uint64_t)(((sa + m_aoff[m]) >> 4) & 0x3FFFu);
+                        const uint64_t bdesc0 = m_bhi[m] | (uint64_t)(((sa + m_boff[m]) >> 4) & 0x3FFFu);
+#pragma unroll
+                        for (int k = 0; k < kWnPix / 16; ++k)
+                            tc_mma_bf16(m_col[m], adesc0 + (uint64_t)(k * kstep_a), bdesc0 + (uint64_t)(k * kstep_b), m_idesc[m], (ks | k) != 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(eb);
+            }
+            __syncwarp();
+            sa += (uint32_t)stage_bytes; fb += 8; eb += 8;
+            if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; sa = smem0; fb = full0; eb = empty0; }
+        }
+        if (elect_one()) tc_commit(smem_u32(done_bar));
+        __syncwarp();
+    } else if (warp == 0) {
         // ============================== TMA producer ==============================
         uint32_t stage = 0, phase = 0;
         const int tiles_img = p.tiles_x * p.tiles_y;
@@ -247,7 +327,7 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (!g_wn_err) { PNNP_CUDA(cudaMalloc(&g_wn_err, sizeof(int))); PNNP_CUDA(cudaMemset(g_wn_err, 0, sizeof(int))); }
     static bool attr_done = false;
-    if (!attr_done) { PNNP_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+    if (!attr_done) { PNNP_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
 
     const int cw_g = std::min(co, 64), cw_x = std::min(ci, 64);          // channels per TMA box = swizzle span / 2
     const int pitch_a = cw_g * 2, pitch_b = cw_x * 2;
@@ -361,7 +441,12 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
     p.tmem_cols = tc;
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * kWnStagesMax + 1) * 8 + 64;
     if (smem > 227 * 1024 || tc > 512) return fail("wgrad_nhwc: shared memory / TMEM budget exceeded");
-    wgrad_nhwc_kernel<<<combos * splits, 192, smem, st>>>(tmG, tmX, p);
+    if (getenv("PNNP_WGRAD_V2") && atoi(getenv("PNNP_WGRAD_V2")) > 0 && !p.dbg) {
+        static bool attr2_done = false;
+        if (!attr2_done) { PNNP_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2_done = true; }
+        wgrad_nhwc_kernel<1><<<combos * splits, 192, smem, st>>>(tmG, tmX, p);
+    } else
+        wgrad_nhwc_kernel<0><<<combos * splits, 192, smem, st>>>(tmG, tmX, p);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

@@ -10,6 +10,8 @@ environment variable that is off by default, and these tests are opt-in too (PNN
 * PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default.
 * PNNP_CONV_F32X2=1 — the specialised 3x3 epilogues' fp32 arithmetic in packed pairs (FADD2 / FFMA2: the same IEEE operations, 16-20 %
   fewer epilogue instructions by SASS count).  Bit-identical to the default.  Built alone and together with SUPER + PDL.
+* PNNP_WGRAD_V2=1 — weight-gradient kernel with the producer / MMA warps' loop-invariant state in registers (per-stage loops 352 -> ~100
+  and 139 -> ~80 executed SASS instructions).  Same loads and MMAs: checked against autograd like the default kernel.
 * PNNP_SSIM_V2=1 — separable 7x7 window sums in the eval epilogue (csrc/ssim_core.cuh; the same source is run phase by phase on the
   CPU against the oracle in tests/test_device_kernels_on_cpu.py).  Equal to the default kernel's sums to float64 summation order.
 * PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
@@ -248,3 +250,19 @@ def test_separable_ssim_equals_default_kernel(monkeypatch, shape, scale, correct
     monkeypatch.setenv("PNNP_SSIM_V2", "1")
     got = eval_partial_sums(dn, hr, scale, correct)
     assert torch.allclose(got, want, rtol=1e-11, atol=1e-9), (got, want)
+
+
+def test_wgrad_v2_matches_autograd_like_the_default_kernel(monkeypatch):
+    """The register-resident producer / MMA loops of wgrad_nhwc_kernel<1> through the default kernel's own tests: every layer
+    shape (all operand modes: filter rows in M, tap-in-N, per-column CTAs, two sources, transposed conv) and a whole step."""
+    import test_gpu_train as T
+    monkeypatch.setenv("PNNP_WGRAD_V2", "1")
+    for args in [(16, 32, 16, 32, 1), (32, 32, 24, 40, 2), (32, 64, 20, 36, 1), (64, 64, 16, 48, 2), (64, 128, 16, 16, 2),
+                 (128, 64, 16, 32, 1), (128, 128, 24, 16, 1), (256, 256, 8, 16, 1), (512, 256, 8, 8, 1), (256, 512, 4, 6, 2)]:
+        T.test_wgrad_nhwc_3x3_matches_autograd(*args)
+    T.test_wgrad_nhwc_two_sources_accumulate_into_one_gradient()
+    for args in [(64, 32, 16, 32), (128, 64, 8, 24), (512, 256, 8, 8)]:
+        T.test_wgrad_nhwc_conv_transpose(*args)
+    T.test_training_step_gradients_match_fp32_autograd(None)
+    torch.cuda.synchronize()
+    assert _lib.lib().pnnp_wgrad_nhwc_pipeline_error() == 0

@@ -26,6 +26,8 @@ run pdl PNNP_CONV_PDL=1
 run x2 PNNP_CONV_F32X2=1
 run all1 PNNP_CONV_SUPER=1 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1 PNNP_CONV_F32X2=1
 run all2 PNNP_CONV_SUPER=2 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1 PNNP_CONV_F32X2=1
+( export PNNP_WGRAD_V2=1; timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
+    > "$OUT/bench_train_wgradv2.json" 2> "$OUT/bench_train_wgradv2.err" )
 for v in 0 1 2; do
   ( export PNNP_CONV_SUPER=$v PNNP_CONVT_FAST=$((v>0)); timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
       > "$OUT/bench_train_super$v.json" 2> "$OUT/bench_train_super$v.err" )
@@ -42,4 +44,5 @@ for cfg in "8 3" "4 3" "2 3" "2 4" "4 4" "16 3"; do
       > "$OUT/bench_synth_chunk$1_streams$2.json" 2> /dev/null )
   echo "synth64 e2e chunk=$1 streams=$2: $(python -c "import json,sys; print(json.load(open('$OUT/bench_synth_chunk$1_streams$2.json'))['e2e']['value'])" 2>/dev/null)" | tee -a "$OUT/summary.txt"
 done
+for f in "$OUT"/bench_train_*.json; do echo "$(basename "$f"): $(python -c "import json; print(json.load(open('$f'))['ms_per_step'], 'ms/step')" 2>/dev/null)" | tee -a "$OUT/summary.txt"; done
 cat "$OUT/summary.txt"
