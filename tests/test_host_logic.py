@@ -126,3 +126,34 @@ def test_lr_schedules_match_the_reference_functions():
         for step in (0, 1, 9, 10, 11, 400, 799, 800, 801, 805, 1599):
             assert get_cos_lr(step, period=800, peak=10, lr=1e-4) == B.get_cos_lr(step, period=800, peak=10, lr=1e-4)
             assert get_multistep_lr(step, period=800, lr=1e-4, milestone=[10, 18]) == B.get_multistep_lr(step, period=800, lr=1e-4, milestone=[10, 18])
+
+
+def test_built_library_uses_tcgen05_tma_and_packed_fp32():
+    """The machine code in pnnp_b200/libpnnp_b200.so (sm_100a): the conv / wgrad kernels issue tcgen05.mma (SASS UTCHMMA) with
+    operands staged by TMA (UTMALDG) and accumulators read back from TMEM (LDTM); no legacy mma.sync (HMMA) anywhere; the noise
+    kernel streams with 128-bit accesses; the opt-in epilogues use packed fp32 pairs (FADD2 / FFMA2)."""
+    import shutil
+    import subprocess
+    from pnnp_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "arch = sm_100a" in sass
+    per_fn, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            per_fn[cur] = []
+        elif cur is not None:
+            per_fn[cur].append(line)
+    conv = {k: "\n".join(v) for k, v in per_fn.items() if "conv_gemm_tc_kernel" in k}
+    wgrad = {k: "\n".join(v) for k, v in per_fn.items() if "wgrad_nhwc_kernel" in k}
+    assert len(conv) >= 27 and len(wgrad) >= 1
+    for body in list(conv.values()) + list(wgrad.values()):
+        assert "UTCHMMA" in body and "UTMALDG" in body and "LDTM" in body and "UTCBAR" in body
+    assert "HMMA." not in sass and "IMMA." not in sass
+    noise = "\n".join(per_fn[next(k for k in per_fn if "noise_synth_fast_kernelILb0" in k)])
+    import re
+    assert re.search(r"LDG\.E\S*\.128", noise) and re.search(r"STG\.E\S*\.128", noise)      # 128-bit coalesced HBM loads and stores
+    packed = [k for k in conv if k.endswith("ELi4EEEv14CUtensorMap_stS1_S1_NS_10ConvParamsE")]
+    assert packed and all("FADD2" in conv[k] and "FFMA2" in conv[k] for k in packed)
