@@ -13,7 +13,14 @@ from .rng import default_generator
 
 
 class HostSynthPipeline:
-    def __init__(self, n, c, h, w, device, chunk=8, n_streams=3):
+    """zero_copy (OPT-IN, PNNP_E2E_ZERO_COPY=1, until measured): ONE launch of the fused kernel that reads the pinned host crops and
+    writes the pinned host result directly over PCIe (pinned memory is device-addressable under unified virtual addressing).  The
+    same bytes cross the bus as in the chunked copy -> kernel -> copy pipeline, but both directions stream for the whole step with
+    no pipeline fill or drain, and no staging buffers in HBM."""
+
+    def __init__(self, n, c, h, w, device, chunk=8, n_streams=3, zero_copy=None):
+        import os
+        self.zero_copy = (os.environ.get("PNNP_E2E_ZERO_COPY", "0") == "1") if zero_copy is None else bool(zero_copy)
         self.shape = (n, c, h, w)
         self.chunk = min(chunk, n)
         self.device = torch.device(device)
@@ -31,6 +38,20 @@ class HostSynthPipeline:
         seed_offset = gen.next()
         cur = torch.cuda.current_stream(self.device)
         table = ParamTable(params, self.device, torch_chain=(chain == _lib.CHAIN_TORCH))
+        if self.zero_copy:
+            if not (host_in.is_pinned() and host_out.is_pinned() and host_in.is_contiguous() and host_out.is_contiguous()):
+                raise RuntimeError("pnnp_b200: zero-copy synthesis needs contiguous pinned host tensors")
+            from .noise import noise_code_bits
+            c, h, w = self.shape[1:]
+            bits = noise_code_bits(noise_code) if isinstance(noise_code, str) else int(noise_code)
+            if chain == _lib.CHAIN_NUMPY and getattr(table, "uniform_f64", False):
+                bits |= _lib.CODE_UNIFORM_F64
+            lo, hi = (-float("inf"), float("inf")) if post_clip is None else post_clip
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().pnnp_noise_synth(host_in.data_ptr(), host_out.data_ptr(), table.data_ptr(), n, c, h, w, bits, chain,
+                                                       int(bool(ori)), int(bool(clip)), lo, hi, seed_offset[0], seed_offset[1], crop_id0,
+                                                       _lib.stream_ptr(self.device)), "noise_synth (zero-copy)")
+            return host_out
         ready = torch.cuda.Event()
         ready.record(cur)
         for i, s0 in enumerate(range(0, n, self.chunk)):

@@ -12,6 +12,8 @@ environment variable that is off by default, and these tests are opt-in too (PNN
   fewer epilogue instructions by SASS count).  Bit-identical to the default.  Built alone and together with SUPER + PDL.
 * PNNP_WGRAD_V2=1 — weight-gradient kernel with the producer / MMA warps' loop-invariant state in registers (per-stage loops 352 -> ~100
   and 139 -> ~80 executed SASS instructions).  Same loads and MMAs: checked against autograd like the default kernel.
+* PNNP_E2E_ZERO_COPY=1 — HostSynthPipeline as ONE launch that reads / writes the pinned host buffers directly over PCIe.  Same result as
+  the chunked copy -> kernel -> copy pipeline, bit for bit (draws are keyed on global element indices).
 * PNNP_SSIM_V2=1 — separable 7x7 window sums in the eval epilogue (csrc/ssim_core.cuh; the same source is run phase by phase on the
   CPU against the oracle in tests/test_device_kernels_on_cpu.py).  Equal to the default kernel's sums to float64 summation order.
 * PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
@@ -266,3 +268,20 @@ def test_wgrad_v2_matches_autograd_like_the_default_kernel(monkeypatch):
     T.test_training_step_gradients_match_fp32_autograd(None)
     torch.cuda.synchronize()
     assert _lib.lib().pnnp_wgrad_nhwc_pipeline_error() == 0
+
+
+def test_zero_copy_host_pipeline_equals_the_chunked_pipeline():
+    import numpy as np
+    from pnnp_b200.pipeline import HostSynthPipeline
+    n, c, h, w = 12, 4, 64, 128
+    np.random.seed(3)
+    params = [P.sample_params("SonyA7S2") for _ in range(n)]
+    host_in = (torch.rand((n, c, h, w)) ** 2).pin_memory()
+    outs = []
+    for zc in (False, True):
+        pipe = HostSynthPipeline(n, c, h, w, torch.device("cuda", 0), chunk=5, n_streams=2, zero_copy=zc)
+        host_out = torch.empty_like(host_in).pin_memory()
+        pipe.run(host_in, host_out, params, "pgrq", generator=P.PhiloxGenerator(21), crop_id0=7, post_clip=(-float("inf"), 1.0))
+        torch.cuda.synchronize()
+        outs.append(host_out.clone())
+    assert torch.equal(outs[0], outs[1]) and float(outs[1].max()) <= 1.0 and not torch.equal(outs[1], host_in)

@@ -45,4 +45,6 @@ for cfg in "8 3" "4 3" "2 3" "2 4" "4 4" "16 3"; do
   echo "synth64 e2e chunk=$1 streams=$2: $(python -c "import json,sys; print(json.load(open('$OUT/bench_synth_chunk$1_streams$2.json'))['e2e']['value'])" 2>/dev/null)" | tee -a "$OUT/summary.txt"
 done
 for f in "$OUT"/bench_train_*.json; do echo "$(basename "$f"): $(python -c "import json; print(json.load(open('$f'))['ms_per_step'], 'ms/step')" 2>/dev/null)" | tee -a "$OUT/summary.txt"; done
+( export PNNP_E2E_ZERO_COPY=1; timeout 120 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$OUT/bench_synth_zero_copy.json" 2> /dev/null )
+echo "synth64 e2e zero-copy: $(python -c "import json; print(json.load(open('$OUT/bench_synth_zero_copy.json'))['e2e']['value'])" 2>/dev/null)" | tee -a "$OUT/summary.txt"
 cat "$OUT/summary.txt"
