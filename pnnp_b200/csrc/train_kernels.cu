@@ -8,6 +8,7 @@
 //   maxpool_bwd_kernel    routes the pooled gradient to the arg-max of each 2x2 window (+ skip gradient)
 //   adam_kernel           fused Adam over a flat fp32 parameter buffer
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "abi_common.h"
 #include "../../include/pnnp_b200.h"
 
@@ -318,24 +319,7 @@ extern "C" int pnnp_adam_step(float* p, const float* g, float* m, float* v, size
 // transposed + flipped data-gradient forms), and the weight gradients come out of the wgrad kernel as [tap][ci][co]: ~190 small
 // permute / cast / copy launches when done with framework ops.  Here each of them is one descriptor (4 logical dims, source and
 // destination strides in elements; a negative source stride expresses the 180-degree filter flip) and ONE launch walks them all.
-namespace pnnp {
-__global__ void __launch_bounds__(256) strided_copy_batch_kernel(const pnnp_copy_desc* __restrict__ descs) {
-    const pnnp_copy_desc d = descs[blockIdx.y];
-    const long long n = (long long)d.dim[0] * d.dim[1] * d.dim[2] * d.dim[3];
-    const float* src = static_cast<const float*>(d.src);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        long long r = i;
-        const int i3 = (int)(r % d.dim[3]); r /= d.dim[3];
-        const int i2 = (int)(r % d.dim[2]); r /= d.dim[2];
-        const int i1 = (int)(r % d.dim[1]);
-        const int i0 = (int)(r / d.dim[1]);
-        const float v = src[i0 * d.sstride[0] + i1 * d.sstride[1] + i2 * d.sstride[2] + i3 * d.sstride[3]];
-        const long long o = i0 * d.dstride[0] + i1 * d.dstride[1] + i2 * d.dstride[2] + i3 * d.dstride[3];
-        if (d.dst_bf16) static_cast<__nv_bfloat16*>(d.dst)[o] = __float2bfloat16_rn(v);
-        else static_cast<float*>(d.dst)[o] = v;
-    }
-}
-}  // namespace pnnp
+#include "copy_kernels.cuh"      // strided_copy_batch_kernel, strided_copy_batch_v2_kernel
 
 extern "C" int pnnp_adam_step_dev(float* p, const float* g, float* m, float* v, size_t total, float* state_dev, float b1, float b2,
                                   float eps, float gscale, void* stream) {
@@ -349,6 +333,9 @@ extern "C" int pnnp_adam_step_dev(float* p, const float* g, float* m, float* v, 
 
 extern "C" int pnnp_strided_copy_batch(const pnnp_copy_desc* descs_dev, int n_desc, int blocks_per_desc, void* stream) {
     if (!descs_dev || n_desc < 1 || blocks_per_desc < 1) return pnnp::fail("strided_copy_batch: bad arguments");
+    if (getenv("PNNP_COPY_V2") && atoi(getenv("PNNP_COPY_V2")) > 0)      // 32-bit index arithmetic; every descriptor the trainer builds is < 2^31 elements
+        pnnp::strided_copy_batch_v2_kernel<<<dim3((unsigned)blocks_per_desc, (unsigned)n_desc), 256, 0, (cudaStream_t)stream>>>(descs_dev);
+    else
     pnnp::strided_copy_batch_kernel<<<dim3((unsigned)blocks_per_desc, (unsigned)n_desc), 256, 0, (cudaStream_t)stream>>>(descs_dev);
     pnnp::count_launch();
     PNNP_CUDA(cudaGetLastError());

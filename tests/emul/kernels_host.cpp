@@ -7,6 +7,7 @@
 #include "../../pnnp_b200/csrc/crop_kernels.cuh"
 #include "../../pnnp_b200/csrc/layout_kernels.cuh"
 #include "../../pnnp_b200/csrc/ssim_core.cuh"
+#include "../../pnnp_b200/csrc/copy_kernels.cuh"
 
 using namespace pnnp;
 
@@ -115,6 +116,17 @@ int emul_ssim_mse_v2(const float* dn, const float* hr, int n, int c, int h, int 
                 sums[frame * stride + 3 + ch] += ssum;
             }
     }
+    return 0;
+}
+
+int emul_strided_copy_batch(const pnnp_copy_desc* descs, int n_desc, int v2, int grid, int block) {
+    gridDim.y = (unsigned)n_desc;
+    for (int y = 0; y < n_desc; ++y) {
+        blockIdx.y = (unsigned)y;
+        if (v2) EMUL_LAUNCH(grid, block, (strided_copy_batch_v2_kernel(descs)));
+        else EMUL_LAUNCH(grid, block, (strided_copy_batch_kernel(descs)));
+    }
+    blockIdx.y = 0; gridDim.y = 1;
     return 0;
 }
 

@@ -28,7 +28,7 @@ def K():
         pytest.skip("g++ not available")
     out = os.path.join(EMUL, "_build", "libkernels_host.so")
     srcs = [os.path.join(EMUL, "kernels_host.cpp"), os.path.join(EMUL, "cuda_host_shim.h")] + \
-           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh", "layout_kernels.cuh", "ssim_core.cuh")]
+           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh", "layout_kernels.cuh", "ssim_core.cuh", "copy_kernels.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-shared", "-fPIC", "-o", out, srcs[0]],
@@ -223,3 +223,36 @@ def test_separable_ssim_phases_vs_oracle(K):
             assert abs(10.0 * math.log10(255.0 ** 2 / mse) - O.psnr(X, Y)) < 1e-9
             ssim = sums[f, 3:3 + c].sum() / (c * (h - 6) * (w - 6))
             assert abs(ssim - O.ssim(X, Y)) < 1e-9, (ssim, O.ssim(X, Y))
+
+
+def test_strided_copy_kernels_pack_weights_like_numpy(K):
+    """The batched strided copy / cast of the training step (weight packing incl. the 180-degree filter flip through negative source
+    strides, bf16 casts) — default kernel and the opt-in 32-bit-index form — against NumPy's own strided views."""
+    import torch
+    from pnnp_b200 import _lib
+    rs = np.random.RandomState(11)
+    w = rs.standard_normal((24, 16, 3, 3)).astype(np.float32)              # [co][ci][ky][kx]
+    # forward layout [tap][co][ci] (bf16), flipped + transposed data-gradient layout [tap'][ci][co] (bf16), plain fp32 transpose
+    jobs = [((3, 3, 24, 16), w.transpose(2, 3, 0, 1), True), ((3, 3, 16, 24), w[:, :, ::-1, ::-1].transpose(2, 3, 1, 0), True),
+            ((16, 24, 3, 3), w.transpose(1, 0, 2, 3), False)]
+    for v2 in (0, 1):
+        descs = (_lib.CopyDesc * len(jobs))()
+        outs = []
+        for d, (dims, view, to_bf16) in zip(descs, jobs):
+            assert view.shape == dims
+            out = np.zeros(dims, np.uint16 if to_bf16 else np.float32)
+            outs.append(out)
+            first = view[0, 0, 0, 0:1]                                    # address of logical index 0 (negative strides start late in memory)
+            d.src, d.dst, d.dst_bf16 = first.ctypes.data, out.ctypes.data, int(to_bf16)
+            for k in range(4):
+                d.dim[k], d.sstride[k], d.dstride[k] = dims[k], view.strides[k] // 4, out.strides[k] // out.itemsize
+        for shape in SHAPES:
+            for o in outs:
+                o[...] = 0
+            assert K.emul_strided_copy_batch(descs, len(jobs), v2, *shape) == 0
+            for (dims, view, to_bf16), o in zip(jobs, outs):
+                if to_bf16:
+                    want = torch.from_numpy(np.ascontiguousarray(view)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+                else:
+                    want = np.ascontiguousarray(view)
+                assert np.array_equal(o, want), (v2, shape, dims)

@@ -14,6 +14,8 @@ environment variable that is off by default, and these tests are opt-in too (PNN
   and 139 -> ~80 executed SASS instructions).  Same loads and MMAs: checked against autograd like the default kernel.
 * PNNP_E2E_ZERO_COPY=1 — HostSynthPipeline as ONE launch that reads / writes the pinned host buffers directly over PCIe.  Same result as
   the chunked copy -> kernel -> copy pipeline, bit for bit (draws are keyed on global element indices).
+* PNNP_COPY_V2=1 — weight-packing / gradient re-layout copy with 32-bit index arithmetic (the kernel source is run on the CPU against NumPy
+  in tests/test_device_kernels_on_cpu.py); on the device: a training step gives the same loss and parameters.
 * PNNP_SSIM_V2=1 — separable 7x7 window sums in the eval epilogue (csrc/ssim_core.cuh; the same source is run phase by phase on the
   CPU against the oracle in tests/test_device_kernels_on_cpu.py).  Equal to the default kernel's sums to float64 summation order.
 * PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
@@ -285,3 +287,28 @@ def test_zero_copy_host_pipeline_equals_the_chunked_pipeline():
         torch.cuda.synchronize()
         outs.append(host_out.clone())
     assert torch.equal(outs[0], outs[1]) and float(outs[1].max()) <= 1.0 and not torch.equal(outs[1], host_in)
+
+
+def test_copy_v2_training_step_is_unchanged(monkeypatch):
+    """Weight packing and gradient re-layout through the 32-bit-index copy kernel: forward output bit-identical (same packed
+    weights), one training step equal to the default's up to the fp32 atomics of the weight-gradient kernel."""
+    from pnnp_b200.train import UNetTrainStep
+    res = {}
+    for v2 in (0, 1):
+        if v2:
+            monkeypatch.setenv("PNNP_COPY_V2", "1")
+        else:
+            monkeypatch.delenv("PNNP_COPY_V2", raising=False)
+        torch.manual_seed(13)
+        net = P.UNetSeeInDark({"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}).cuda()
+        P.initialize_weights(net)
+        g = torch.Generator(device="cuda").manual_seed(2)
+        hr = torch.rand((2, 4, 64, 64), device="cuda", generator=g)
+        lr = (hr + 0.05 * torch.randn((2, 4, 64, 64), device="cuda", generator=g)).contiguous()
+        ts = UNetTrainStep(net.train(), lr=1e-3)
+        ts.use_graph = False
+        loss = float(ts.step(lr, hr))
+        res[v2] = (loss, ts.scr.bufs["pred"].clone(), ts.flat_p.clone())
+    assert torch.equal(res[0][1], res[1][1])                               # prediction of the first step: packed weights are the same bits
+    assert abs(res[0][0] - res[1][0]) < 1e-7
+    assert (res[0][2] - res[1][2]).abs().max().item() < 2.5e-3            # Adam's first step is sign-like: |update| <= lr
