@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 #include <cstdlib>
 #include "abi_common.h"
+#include "actbwd_core.cuh"
 #include "../../include/pnnp_b200.h"
 
 namespace pnnp {
@@ -250,6 +251,17 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, co
     }
 }
 
+// act_bwd_bias, second form (actbwd_core.cuh): phases of one block, atomics on the shared / global accumulators
+struct Ab2Atomic { __device__ __forceinline__ void operator()(float* p, float v) const { atomicAdd(p, v); } };
+__global__ void __launch_bounds__(kAb2Threads) act_bwd_bias_v2_kernel(const ActBwd2Args a, float* dbias) {
+    extern __shared__ float s_b2[];
+    ab2_clear(threadIdx.x, a, s_b2);
+    __syncthreads();
+    ab2_main(threadIdx.x, blockIdx.x, gridDim.x, a, s_b2, Ab2Atomic());
+    __syncthreads();
+    ab2_flush(threadIdx.x, a, s_b2, dbias, Ab2Atomic());
+}
+
 static int blocks_for(size_t items) { return (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, 148 * 8)); }
 
 }  // namespace pnnp
@@ -286,6 +298,14 @@ extern "C" int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t 
     int blocks = (int)std::max<size_t>(1, std::min<size_t>(items / (256 * 8), 148 * 8));
     const int quantum = std::max(1, (c / 8) / 256);                  // keep grid * 256 a multiple of c / 8
     blocks = std::max(quantum, blocks / quantum * quantum);
+    const int c8 = c / 8;
+    if (getenv("PNNP_ACTBWD_V2") && atoi(getenv("PNNP_ACTBWD_V2")) > 0 && (c8 & (c8 - 1)) == 0 && c8 <= 256 && items < (1ull << 32) - (1ull << 24)) {
+        ActBwd2Args a{static_cast<uint16_t*>(g), static_cast<const uint16_t*>(out), (uint32_t)items, c, act_kind};
+        act_bwd_bias_v2_kernel<<<blocks, kAb2Threads, sizeof(float) * c, (cudaStream_t)stream>>>(a, dbias);
+        count_launch();
+        PNNP_CUDA(cudaGetLastError());
+        return 0;
+    }
     act_bwd_bias_kernel<<<blocks, 256, sizeof(float) * c, (cudaStream_t)stream>>>(
         static_cast<__nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(out), dbias, pixels, c, act_kind);
     count_launch();

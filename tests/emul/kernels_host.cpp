@@ -8,6 +8,7 @@
 #include "../../pnnp_b200/csrc/layout_kernels.cuh"
 #include "../../pnnp_b200/csrc/ssim_core.cuh"
 #include "../../pnnp_b200/csrc/copy_kernels.cuh"
+#include "../../pnnp_b200/csrc/actbwd_core.cuh"
 
 using namespace pnnp;
 
@@ -127,6 +128,21 @@ int emul_strided_copy_batch(const pnnp_copy_desc* descs, int n_desc, int v2, int
         else EMUL_LAUNCH(grid, block, (strided_copy_batch_kernel(descs)));
     }
     blockIdx.y = 0; gridDim.y = 1;
+    return 0;
+}
+
+// act_bwd_bias_v2_kernel (train_kernels.cu) phase by phase; the atomics of the device become plain additions (threads run one after
+// the other), so the bias sums agree with the device up to summation order and the in-place gradient update bit for bit
+struct HostAdd { void operator()(float* p, float v) const { *p += v; } };
+int emul_act_bwd_bias_v2(uint16_t* g, const uint16_t* out, float* dbias, uint32_t items, int c, int act_kind, int nblocks) {
+    static float s_b[2048];
+    if (c > 2048 || ((c / 8) & (c / 8 - 1))) return 1;
+    ActBwd2Args a{g, out, items, c, act_kind};
+    for (int b = 0; b < nblocks; ++b) {
+        for (int t = 0; t < kAb2Threads; ++t) ab2_clear(t, a, s_b);
+        for (int t = 0; t < kAb2Threads; ++t) ab2_main(t, (uint32_t)b, (uint32_t)nblocks, a, s_b, HostAdd());
+        for (int t = 0; t < kAb2Threads; ++t) ab2_flush(t, a, s_b, dbias, HostAdd());
+    }
     return 0;
 }
 

@@ -28,7 +28,7 @@ def K():
         pytest.skip("g++ not available")
     out = os.path.join(EMUL, "_build", "libkernels_host.so")
     srcs = [os.path.join(EMUL, "kernels_host.cpp"), os.path.join(EMUL, "cuda_host_shim.h")] + \
-           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh", "layout_kernels.cuh", "ssim_core.cuh", "copy_kernels.cuh")]
+           [os.path.join(ROOT, "pnnp_b200", "csrc", f) for f in ("pack_kernels.cuh", "pack_core.cuh", "crop_kernels.cuh", "layout_kernels.cuh", "ssim_core.cuh", "copy_kernels.cuh", "actbwd_core.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-shared", "-fPIC", "-o", out, srcs[0]],
@@ -256,3 +256,28 @@ def test_strided_copy_kernels_pack_weights_like_numpy(K):
                 else:
                     want = np.ascontiguousarray(view)
                 assert np.array_equal(o, want), (v2, shape, dims)
+
+
+@pytest.mark.parametrize("act_kind", [0, 1, 2])
+def test_act_backward_v2_phases_vs_torch(K, act_kind):
+    """The opt-in activation-backward + bias-gradient kernel (csrc/actbwd_core.cuh), phase by phase: the in-place gradient update is
+    bit-identical to torch's bf16 arithmetic (g * act'(out), rounded to bf16), the bias gradient is the per-channel sum."""
+    import torch
+    rs = np.random.RandomState(13 + act_kind)
+    for (pixels, c, nblocks) in ((300, 16, 1), (1000, 32, 3), (257, 64, 2), (64, 512, 5)):
+        g = torch.from_numpy(rs.standard_normal((pixels, c)).astype(np.float32)).to(torch.bfloat16)
+        out = torch.from_numpy(rs.standard_normal((pixels, c)).astype(np.float32)).to(torch.bfloat16)
+        if act_kind == 1:
+            want = (g.float() * torch.where(out.float() > 0, 1.0, 0.2)).to(torch.bfloat16)
+        elif act_kind == 2:
+            want = torch.where(out.float() > 0, g.float(), torch.zeros(())).to(torch.bfloat16)
+        else:
+            want = g.clone()
+        gb = _aligned((pixels, c), np.uint16)
+        gb[...] = g.view(torch.int16).numpy().view(np.uint16)
+        ob = _aligned((pixels, c), np.uint16)
+        ob[...] = out.view(torch.int16).numpy().view(np.uint16)
+        dbias = np.full(c, 0.5, np.float32)                                    # accumulates on top of what is there
+        assert K.emul_act_bwd_bias_v2(_p(gb, _u16p), _p(ob, _u16p), _p(dbias, _f32p), pixels * (c // 8), c, act_kind, nblocks) == 0
+        assert np.array_equal(gb, want.view(torch.int16).numpy().view(np.uint16))
+        assert np.allclose(dbias - 0.5, want.float().sum(0).numpy(), rtol=1e-4, atol=1e-3)
