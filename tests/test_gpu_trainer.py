@@ -54,12 +54,12 @@ def test_lrid_eval_entry_point_takes_reflect_pad_branch(tmp_path, monkeypatch):
 
 def test_sid_train_mode_runs_the_reference_loop_and_learns(tmp_path, monkeypatch):
     """`--mode train` (trainer_SID.py:74-180): Raw_Dataset items built on the device -> explicit training step; the L1 loss
-    falls over a few epochs, a checkpoint with the reference's state_dict keys is written, then the eval sweeps run."""
+    falls over ten epochs, a checkpoint with the reference's state_dict keys is written, then the eval sweeps run."""
     from pnnp_b200 import trainer as T
     monkeypatch.chdir(tmp_path)
     runfile, cfg = _small_runfile(tmp_path, "runfiles/SonyA7S2/PNNP.yml", 256, 384, 1)
     cfg["dst_train"].update(H=256, W=384, patch_size=64, crop_per_image=4, synthetic_frames=4)
-    cfg["hyper"].update(stop_epoch=6, save_freq=3, plot_freq=6, batch_size=2, learning_rate=1e-3, lr_scheduler="MultiStep",
+    cfg["hyper"].update(stop_epoch=10, save_freq=5, plot_freq=10, batch_size=2, learning_rate=1e-3, lr_scheduler="MultiStep",
                         step_size=100)
     open(runfile, "w").write(yaml.dump(cfg))
     import numpy as np
@@ -73,9 +73,12 @@ def test_sid_train_mode_runs_the_reference_loop_and_learns(tmp_path, monkeypatch
     step = tr.train()
     text = open(tmp_path / "logs" / f"log_{cfg['model_name']}.log").read()
     l1 = [float(x) for x in re.findall(r"L1=(\d+\.\d+)", text)]
-    assert len(l1) == 6 and min(l1[3:]) < 0.97 * l1[0], l1          # ~7 % after 12 Adam steps at lr 1e-3
-    assert step.t == 6 * 2                                            # 4 items / batch 2 = 2 steps per epoch
-    assert "Epoch 6: PSNR=" in text                                   # the fast eval at plot_freq
+    # 20 Adam steps at lr 1e-3.  The same loop in fp32 on the CPU (oracle UNet + autograd + Adam on statistically identical
+    # items) falls from 0.297 to the constant-predictor plateau ~0.25 (-15 %) by epoch 8 and is at -10 % after 6 epochs; the r01
+    # GPU run measured -7 % after 6.  Per-epoch means still scatter (two batches each), hence the minimum over the second half.
+    assert len(l1) == 10 and min(l1[5:]) < 0.97 * l1[0], l1
+    assert step.t == 10 * 2                                           # 4 items / batch 2 = 2 steps per epoch
+    assert "Epoch 10: PSNR=" in text                                  # the fast eval at plot_freq
     sd = torch.load(os.path.join(cfg["fast_ckpt"], f"{cfg['model_name']}_last_model.pth"))
     assert "conv1_1.weight" in sd and "upv6.weight" in sd and len(sd) == 46
 
