@@ -16,6 +16,9 @@ environment variable that is off by default, and these tests are opt-in too (PNN
   the chunked copy -> kernel -> copy pipeline, bit for bit (draws are keyed on global element indices).
 * PNNP_COPY_V2=1 — weight-packing / gradient re-layout copy with 32-bit index arithmetic (the kernel source is run on the CPU against NumPy
   in tests/test_device_kernels_on_cpu.py); on the device: a training step gives the same loss and parameters.
+* PNNP_ACTBWD_V2=1 — activation backward + bias gradient with 32-bit item indices and no per-item modulo (csrc/actbwd_core.cuh; its phases
+  are run on the CPU against torch's bf16 arithmetic).  In-place gradient bit-identical to the default kernel, bias sums equal to
+  fp32 summation order.
 * PNNP_SSIM_V2=1 — separable 7x7 window sums in the eval epilogue (csrc/ssim_core.cuh; the same source is run phase by phase on the
   CPU against the oracle in tests/test_device_kernels_on_cpu.py).  Equal to the default kernel's sums to float64 summation order.
 * PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
@@ -312,3 +315,27 @@ def test_copy_v2_training_step_is_unchanged(monkeypatch):
     assert torch.equal(res[0][1], res[1][1])                               # prediction of the first step: packed weights are the same bits
     assert abs(res[0][0] - res[1][0]) < 1e-7
     assert (res[0][2] - res[1][2]).abs().max().item() < 2.5e-3            # Adam's first step is sign-like: |update| <= lr
+
+
+@pytest.mark.parametrize("act_kind", [0, 1, 2])
+def test_act_backward_v2_equals_the_default_kernel(monkeypatch, act_kind):
+    """pnnp_act_bwd_bias through the second kernel form: the in-place gradient is the same bits, the bias gradient the same sums
+    (fp32 atomics: order differs), on the channel counts of the UNet (c / 8 a power of two) and a ragged pixel count."""
+    L = _lib.lib()
+    for pixels, c in ((4099, 16), (64 * 64 * 2, 32), (3001, 64), (1025, 256), (300, 512)):
+        g0 = torch.randn((pixels, c), device="cuda").to(torch.bfloat16)
+        out = torch.randn((pixels, c), device="cuda").to(torch.bfloat16)
+        res = {}
+        for v2 in (0, 1):
+            if v2:
+                monkeypatch.setenv("PNNP_ACTBWD_V2", "1")
+            else:
+                monkeypatch.delenv("PNNP_ACTBWD_V2", raising=False)
+            g = g0.clone()
+            db = torch.full((c,), 0.25, device="cuda")
+            _lib.check(L.pnnp_act_bwd_bias(g.data_ptr(), out.data_ptr(), db.data_ptr(), pixels, c, act_kind, _lib.stream_ptr(g.device)),
+                       "act_bwd_bias")
+            torch.cuda.synchronize()
+            res[v2] = (g, db)
+        assert torch.equal(res[0][0], res[1][0]), (pixels, c)
+        assert torch.allclose(res[0][1], res[1][1], rtol=1e-4, atol=1e-3), (pixels, c)

@@ -28,6 +28,8 @@ run all1 PNNP_CONV_SUPER=1 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1 PNNP_C
 run all2 PNNP_CONV_SUPER=2 PNNP_CONVT_FAST=1 PNNP_IN_V2=1 PNNP_CONV_PDL=1 PNNP_CONV_F32X2=1
 ( export PNNP_COPY_V2=1; timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
     > "$OUT/bench_train_copyv2.json" 2> "$OUT/bench_train_copyv2.err" )
+( export PNNP_ACTBWD_V2=1; timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
+    > "$OUT/bench_train_actbwdv2.json" 2> "$OUT/bench_train_actbwdv2.err" )
 ( export PNNP_WGRAD_V2=1; timeout 300 python bench.py --workload train_step --steps 30 --warmup 5 --no-cpu-baseline \
     > "$OUT/bench_train_wgradv2.json" 2> "$OUT/bench_train_wgradv2.err" )
 for v in 0 1 2; do
