@@ -78,3 +78,5 @@ static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __
 static inline __nv_bfloat16 emul_bfmax(__nv_bfloat16 a, __nv_bfloat16 b) { return emul_bf2f(a) >= emul_bf2f(b) ? a : b; }
 static inline __nv_bfloat162 __hmax2(__nv_bfloat162 a, __nv_bfloat162 b) { return __nv_bfloat162{emul_bfmax(a.x, b.x), emul_bfmax(a.y, b.y)}; }
 static inline __nv_bfloat16 __float2bfloat16_rn(float f) { return emul_f2bf(f); }
+static inline float __low2float(__nv_bfloat162 v) { return emul_bf2f(v.x); }
+static inline float __high2float(__nv_bfloat162 v) { return emul_bf2f(v.y); }

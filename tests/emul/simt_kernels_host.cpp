@@ -4,8 +4,12 @@
 #include "cuda_host_shim.h"
 #include "simt_host.h"
 #include "../../pnnp_b200/csrc/noise_kernels.cuh"
+#include "../../pnnp_b200/csrc/train_kernels.cuh"
 
-namespace pnnp { alignas(16) uint8_t s_fast[kFastSmemBytes]; }     // the fast kernel's dynamic shared memory
+namespace pnnp {                                     // the kernels' dynamic shared memory (`extern __shared__` arrays)
+alignas(16) uint8_t s_fast[kFastSmemBytes];
+float s_acc[4 * 64 + 4 + 64], s_b[1024], s_b2[2048];
+}
 
 using namespace pnnp;
 
@@ -36,6 +40,52 @@ int emul_noise_synth(const float* clean, float* noisy, const pnnp_noise_params* 
         else             { if (debug) EMUL_K(PNNP_CHAIN_TORCH, true, 1); else EMUL_K(PNNP_CHAIN_TORCH, false, 1); }
     }
 #undef EMUL_K
+    return 0;
+}
+
+// ---- training-step helpers (csrc/train_kernels.cuh); `blocks` is free wherever the launcher's choice is not part of the contract
+int emul_l1_loss(const float* pred, const float* hr, float* gpred, size_t total, double* loss_sum, int blocks) {
+    *loss_sum = 0.0;
+    SIMT_LAUNCH(blocks, 256, (l1_loss_kernel(pred, hr, gpred, total, 1.0f / (float)total, loss_sum)));
+    return 0;
+}
+int emul_head_bwd(const float* gpred, const uint16_t* act, const float* W, uint16_t* gact, float* dW, float* db, float* dbias_prev,
+                  int n, int h, int w, int cin, int co, int act_kind, int blocks) {
+    if (co < 1 || co > 4 || (cin != 8 && cin != 16 && cin != 32 && cin != 64)) return 1;
+    SIMT_LAUNCH(blocks, 256, (head_bwd_kernel(gpred, reinterpret_cast<const __nv_bfloat16*>(act), W, reinterpret_cast<__nv_bfloat16*>(gact),
+                                              dW, db, dbias_prev, n, h, w, cin, co, act_kind)));
+    return 0;
+}
+int emul_act_bwd_bias(uint16_t* g, const uint16_t* out, float* dbias, size_t pixels, int c, int act_kind, int blocks) {
+    if ((c % 8) || c > 1024 || ((size_t)blocks * 256) % (size_t)(c / 8)) return 1;       // the launcher keeps grid * 256 a multiple of c / 8
+    SIMT_LAUNCH(blocks, 256, (act_bwd_bias_kernel(reinterpret_cast<__nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(out), dbias,
+                                                  pixels, c, act_kind)));
+    return 0;
+}
+int emul_act_bwd_bias_v2_kernel(uint16_t* g, const uint16_t* out, float* dbias, uint32_t items, int c, int act_kind, int blocks) {
+    if (c > 2048 || ((c / 8) & (c / 8 - 1))) return 1;
+    const ActBwd2Args a{g, out, items, c, act_kind};
+    SIMT_LAUNCH(blocks, kAb2Threads, (act_bwd_bias_v2_kernel(a, dbias)));
+    return 0;
+}
+int emul_maxpool_bwd(const uint16_t* gp, const uint16_t* cfull, const uint16_t* gskip, uint16_t* gc, int n, int h, int w, int c,
+                     int act_kind, int blocks) {
+    if ((h & 1) || (w & 1) || (c & 7)) return 1;
+    SIMT_LAUNCH(blocks, 256, (maxpool_bwd_kernel(reinterpret_cast<const __nv_bfloat16*>(gp), reinterpret_cast<const __nv_bfloat16*>(cfull),
+                                                 reinterpret_cast<const __nv_bfloat16*>(gskip), reinterpret_cast<__nv_bfloat16*>(gc), n, h, w, c,
+                                                 act_kind)));
+    return 0;
+}
+int emul_adam(float* p, const float* g, float* m, float* v, size_t total, float lr, float b1, float b2, float eps, int step, float gscale,
+              int on_device_state, int blocks) {
+    if (on_device_state) {                       // pnnp_adam_step_dev: learning rate and step count read by the kernel
+        float state[2] = {lr, (float)(step - 1)};
+        adam_tick_kernel(state);
+        SIMT_LAUNCH(blocks, 256, (adam_dev_kernel(p, g, m, v, total, state, b1, b2, eps, gscale)));
+    } else {
+        const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+        SIMT_LAUNCH(blocks, 256, (adam_kernel(p, g, m, v, total, lr, b1, b2, eps, bc1, bc2, gscale)));
+    }
     return 0;
 }
 

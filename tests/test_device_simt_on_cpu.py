@@ -125,3 +125,150 @@ def test_generic_kernel_vector_and_scalar_paths_agree_and_follow_the_oracle_tail
         for i, p in enumerate(params):
             draws = {k: v[i] for k, v in da.items()}
             assert O.noisy_obs_tail_explicit(clean[i], p, code, draws).tobytes() == a[i].tobytes()
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# Training-step helper kernels (csrc/train_kernels.cuh) — warp-shuffle reductions, shared-memory accumulators, block barriers —
+# against torch's CPU autograd / optimiser.  bf16 tensors travel as uint16 bit patterns.
+# ----------------------------------------------------------------------------------------------------------------------------
+_u16p = C.POINTER(C.c_uint16)
+
+
+def _bf16_bits(t):
+    import torch
+    return t.to(torch.bfloat16).contiguous().view(torch.int16).numpy().view(np.uint16).copy()       # a private copy: kernels work in place
+
+
+def _from_bits(a):
+    import torch
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+
+
+@pytest.mark.parametrize("blocks", [1, 3])
+def test_l1_loss_kernel_vs_torch_autograd(S, blocks):
+    """losses/base_loss.py:92-103: F.l1_loss(pred.clamp(0, 1), hr), mean reduction, and its gradient (clamp passes 0 <= p <= 1,
+    sign(0) = 0)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    pred = (torch.rand((2, 4, 9, 23), generator=g) * 1.6 - 0.3)
+    hr = torch.rand((2, 4, 9, 23), generator=g)
+    pred.view(-1)[:6] = torch.tensor([0.0, 1.0, 0.5, -0.0, 1.0000001, 0.25])
+    hr.view(-1)[:6] = torch.tensor([0.3, 0.2, 0.5, 0.0, 0.4, 0.25])                  # exact ties: zero gradient
+    p = pred.clone().requires_grad_(True)
+    want = F.l1_loss(p.clamp(0, 1), hr)
+    want.backward()
+    pn, hn = pred.numpy().copy(), hr.numpy().copy()
+    gp, loss = np.full_like(pn, np.nan), C.c_double(-1.0)
+    assert S.emul_l1_loss(_p(pn, _f32p), _p(hn, _f32p), _p(gp, _f32p), C.c_size_t(pn.size), C.byref(loss), blocks) == 0
+    assert abs(loss.value / pn.size - want.item()) < 1e-7
+    assert np.array_equal(gp, p.grad.numpy())
+
+
+@pytest.mark.parametrize("cin,co,act_kind,blocks", [(32, 4, 1, 2), (16, 4, 1, 1), (64, 3, 2, 3), (8, 1, 0, 1)])
+def test_head_backward_kernel_vs_torch_autograd(S, cin, co, act_kind, blocks):
+    """1x1 head (conv10_1) backward fused with the feeding layer's activation derivative: data gradient (bf16, NHWC), weight and
+    bias gradients of the head, bias gradient of the feeding conv — lanes of a warp are combined by shuffles, then shared / global
+    accumulators."""
+    import torch
+    g = torch.Generator().manual_seed(cin + co)
+    n, h, w = 2, 5, 13                                                   # 130 pixels: ragged against every channel-group count
+    pre = torch.randn((n, h, w, cin), generator=g)
+    slope = {0: 1.0, 1: 0.2, 2: 0.0}[act_kind]
+    act = torch.where(pre > 0, pre, pre * slope).to(torch.bfloat16)     # the stored activation the kernel reads
+    W = torch.randn((co, cin), generator=g) * 0.3
+    gpred = torch.randn((n, co, h, w), generator=g)
+    a32 = act.float()
+    gp_pix = gpred.permute(0, 2, 3, 1)                                   # n h w co
+    g_act = gp_pix.double() @ W.double()                                 # d loss / d activation
+    deriv = torch.where(a32 > 0, torch.ones(()), torch.full((), slope)).double()
+    g_pre = g_act * deriv
+    want_dW = torch.einsum("nhwo,nhwc->oc", gp_pix.double(), a32.double())
+    want_db = gp_pix.double().sum((0, 1, 2))
+    want_dbp = g_pre.sum((0, 1, 2))
+    act_b = _bf16_bits(act)
+    gact = np.zeros_like(act_b)
+    dW, db, dbp = np.full((co, cin), 0.5, np.float32), np.full(co, 0.25, np.float32), np.full(cin, -1.0, np.float32)
+    Wn, gpn = W.numpy().copy(), gpred.numpy().copy()
+    assert S.emul_head_bwd(_p(gpn, _f32p), _p(act_b, _u16p), _p(Wn, _f32p), _p(gact, _u16p), _p(dW, _f32p), _p(db, _f32p), _p(dbp, _f32p),
+                           n, h, w, cin, co, act_kind, blocks) == 0
+    got = _from_bits(gact).float().reshape(n, h, w, cin).double()
+    # bf16 data gradient: within one rounding of the float64 value (fp32 FMA chain, then round to nearest even)
+    assert ((got - g_pre).abs() <= g_pre.abs() * 2.0 ** -8 + 1e-30).all()
+    assert (got == g_pre.float().to(torch.bfloat16).double()).float().mean() > 0.995
+    assert np.allclose(dW - 0.5, want_dW.numpy(), rtol=1e-4, atol=1e-4)          # accumulates on top of what is there
+    assert np.allclose(db - 0.25, want_db.numpy(), rtol=1e-4, atol=1e-4)
+    assert np.allclose(dbp + 1.0, want_dbp.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("act_kind", [0, 1, 2])
+def test_act_backward_kernels_whole_vs_torch(S, act_kind):
+    """The default activation-backward + bias-gradient kernel and the opt-in second form, as whole kernels: in-place gradient
+    bit-identical to torch's bf16 arithmetic and to each other, bias sums per channel."""
+    import torch
+    rs = np.random.RandomState(3 + act_kind)
+    for pixels, c, blocks in ((301, 16, 1), (999, 32, 2), (130, 64, 1), (77, 512, 3)):
+        g = torch.from_numpy(rs.standard_normal((pixels, c)).astype(np.float32)).to(torch.bfloat16)
+        out = torch.from_numpy(rs.standard_normal((pixels, c)).astype(np.float32)).to(torch.bfloat16)
+        if act_kind == 1:
+            want = (g.float() * torch.where(out.float() > 0, 1.0, 0.2)).to(torch.bfloat16)
+        elif act_kind == 2:
+            want = torch.where(out.float() > 0, g.float(), torch.zeros(())).to(torch.bfloat16)
+        else:
+            want = g.clone()
+        res = []
+        for fn, args in ((S.emul_act_bwd_bias, (C.c_size_t(pixels),)), (S.emul_act_bwd_bias_v2_kernel, (C.c_uint32(pixels * (c // 8)),))):
+            gb, ob, dbias = _bf16_bits(g), _bf16_bits(out), np.full(c, 0.5, np.float32)
+            assert fn(_p(gb, _u16p), _p(ob, _u16p), _p(dbias, _f32p), *args, c, act_kind, blocks) == 0
+            assert np.array_equal(gb, _bf16_bits(want))
+            assert np.allclose(dbias - 0.5, want.float().sum(0).numpy(), rtol=1e-4, atol=1e-3)
+            res.append(gb)
+        assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("act_kind,skip", [(0, False), (1, True), (2, True), (1, False)])
+def test_maxpool_backward_kernel_vs_torch_autograd(S, act_kind, skip):
+    """2x2 max-pool backward (+ skip-connection gradient, + act'(cfull)): the pooled gradient goes to the FIRST arg-max of each window
+    in scan order, as torch's CPU max_pool2d does (ties are common in bf16)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(17 + act_kind)
+    n, h, w, c = 2, 6, 10, 24
+    cfull = (torch.randint(-3, 4, (n, c, h, w), generator=g).float() * 0.25).to(torch.bfloat16)      # few distinct values: many ties
+    gp = torch.randn((n, c, h // 2, w // 2), generator=g).to(torch.bfloat16)
+    gskip = torch.randn((n, c, h, w), generator=g).to(torch.bfloat16) if skip else None
+    x = cfull.float().requires_grad_(True)
+    F.max_pool2d(x, 2).backward(gp.float())
+    tot = x.grad + (gskip.float() if skip else 0.0)
+    want = tot.to(torch.bfloat16)                                        # the sum is rounded to bf16 first ...
+    if act_kind:
+        sl = 0.2 if act_kind == 1 else 0.0
+        want = (want.float() * torch.where(cfull.float() > 0, 1.0, sl)).to(torch.bfloat16)      # ... then multiplied by act'
+    nhwc = lambda t: _bf16_bits(t.permute(0, 2, 3, 1))
+    gc = np.zeros((n, h, w, c), np.uint16)
+    for blocks in (1, 2):
+        gc[...] = 0
+        assert S.emul_maxpool_bwd(_p(nhwc(gp), _u16p), _p(nhwc(cfull), _u16p), _p(nhwc(gskip), _u16p) if skip else None, _p(gc, _u16p),
+                                  n, h, w, c, act_kind, blocks) == 0
+        got, ref = _from_bits(gc).float(), want.permute(0, 2, 3, 1).float()
+        assert torch.equal(got + 0.0, ref + 0.0)                         # +0.0: -0 and +0 compare equal either way; kept explicit
+
+
+@pytest.mark.parametrize("on_device_state", [0, 1])
+def test_adam_kernels_vs_torch_optim(S, on_device_state):
+    """torch.optim.Adam defaults (betas 0.9 / 0.999, eps 1e-8, no weight decay), three steps; `gscale` = the 1 / world factor of the
+    DDP gradient mean folded into the update."""
+    import torch
+    g = torch.Generator().manual_seed(1)
+    p0 = torch.randn(1000, generator=g)
+    grads = [torch.randn(1000, generator=g) * s for s in (1.0, 0.1, 3.0)]
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p, m, v = p0.numpy().copy(), np.zeros(1000, np.float32), np.zeros(1000, np.float32)
+    for step, gr in enumerate(grads, 1):
+        ref.grad = gr.clone() * 0.5
+        opt.step()
+        gn = gr.numpy().copy()
+        assert S.emul_adam(_p(p, _f32p), _p(gn, _f32p), _p(m, _f32p), _p(v, _f32p), C.c_size_t(1000), C.c_float(1e-3), C.c_float(0.9),
+                           C.c_float(0.999), C.c_float(1e-8), step, C.c_float(0.5), on_device_state, 2) == 0
+        assert np.allclose(p, ref.detach().numpy(), rtol=2e-6, atol=2e-7)
