@@ -143,6 +143,38 @@ def test_psnr_ssim_sanity():
     assert O.psnr(a, b) == pytest.approx(10 * np.log10(255 ** 2 / 1.0), abs=1e-4)   # float32 inputs: a+1 is inexact
 
 
+def test_psnr_ssim_against_independent_implementations():
+    """E2 stays "parity unpinned" (scikit-image is not in this image), but the restatement is not alone: PSNR against OpenCV's
+    cv2.PSNR, and SSIM against (a) the same statistics from OpenCV's box filter (another filter implementation; the cropped border
+    makes the border mode irrelevant) and (b) the definition itself — per 7x7 window the mean, the SAMPLE variance / covariance
+    (ddof = 1, skimage's default `use_sample_covariance=True`), the SSIM formula with K1 = 0.01, K2 = 0.03, averaged over the valid
+    windows and then over channels."""
+    cv2 = pytest.importorskip("cv2")
+    from numpy.lib.stride_tricks import sliding_window_view
+    rs = np.random.RandomState(5)
+    a = np.clip(rs.rand(40, 52, 4).astype(np.float32) ** 2 * 255, 0, 255)
+    b = np.clip(a + rs.randn(40, 52, 4).astype(np.float32) * 7, 0, 255)
+    assert O.psnr(a, b) == pytest.approx(cv2.PSNR(a.astype(np.float64), b.astype(np.float64), 255.0), abs=1e-10)
+    X, Y = a.astype(np.float64), b.astype(np.float64)
+    C1, C2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    box = lambda z: cv2.boxFilter(z, cv2.CV_64F, (7, 7), normalize=True, borderType=cv2.BORDER_REFLECT)
+    via_cv, by_definition = [], []
+    for ch in range(4):
+        x, y = X[..., ch], Y[..., ch]
+        ux, uy = box(x), box(y)
+        vx, vy, vxy = (49 / 48 * (box(p) - q) for p, q in ((x * x, ux * ux), (y * y, uy * uy), (x * y, ux * uy)))
+        S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+        via_cv.append(S[3:-3, 3:-3].mean())
+        wx, wy = (sliding_window_view(z, (7, 7)).reshape(z.shape[0] - 6, z.shape[1] - 6, 49) for z in (x, y))
+        mx, my = wx.mean(-1), wy.mean(-1)
+        sx, sy = wx.var(-1, ddof=1), wy.var(-1, ddof=1)
+        sxy = ((wx - mx[..., None]) * (wy - my[..., None])).sum(-1) / 48
+        by_definition.append((((2 * mx * my + C1) * (2 * sxy + C2)) / ((mx ** 2 + my ** 2 + C1) * (sx + sy + C2))).mean())
+    assert O.ssim(a, b) == pytest.approx(np.mean(via_cv), abs=1e-12)
+    assert O.ssim(a, b) == pytest.approx(np.mean(by_definition), abs=1e-10)
+    assert 0.5 < O.ssim(a, b) < 0.9999
+
+
 def test_eval_tiling_oracle_matches_reference_goldens(golden):
     """SynBase_Dataset.eval_crop / eval_merge (syn_datasets.py:109-159) — bit-exact data movement."""
     g = golden("tiling")
