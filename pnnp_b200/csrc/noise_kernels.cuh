@@ -6,10 +6,12 @@
 #include <cmath>
 #include "noise_core.cuh"
 
+#ifndef PNNP_SMEM
 #ifdef PNNP_HOST_EMUL
 #define PNNP_SMEM static                 // one CTA at a time on the host: a static array is the CTA's shared memory
 #else
 #define PNNP_SMEM __shared__
+#endif
 #endif
 
 namespace pnnp {

@@ -80,3 +80,24 @@ static inline __nv_bfloat162 __hmax2(__nv_bfloat162 a, __nv_bfloat162 b) { retur
 static inline __nv_bfloat16 __float2bfloat16_rn(float f) { return emul_f2bf(f); }
 static inline float __low2float(__nv_bfloat162 v) { return emul_bf2f(v.x); }
 static inline float __high2float(__nv_bfloat162 v) { return emul_bf2f(v.y); }
+
+// normcdfinv (CUDA math library, used by the HighBitRecovery map): Acklam's rational start, then two Halley steps on
+// Phi(x) - p with libm's erfc -> accurate to a few ulp of double
+static inline double normcdfinv(double p) {
+    if (!(p > 0.0)) return p == 0.0 ? -INFINITY : NAN;
+    if (!(p < 1.0)) return p == 1.0 ? INFINITY : NAN;
+    static const double a[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02, 1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[5] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02, 6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c[6] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00, -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+    static const double d[4] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+    double x;
+    if (p < 0.02425) { const double q = sqrt(-2 * log(p)); x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1); }
+    else if (p > 1 - 0.02425) { const double q = sqrt(-2 * log1p(-p)); x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1); }
+    else { const double q = p - 0.5, r = q * q; x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q / (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1); }
+    for (int it = 0; it < 2; ++it) {
+        const double e = 0.5 * erfc(-x * 0.70710678118654752440) - p;
+        const double u = e * 2.50662827463100050242 * exp(0.5 * x * x);
+        x -= u / (1 + 0.5 * x * u);
+    }
+    return x;
+}

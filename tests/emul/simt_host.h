@@ -27,7 +27,6 @@ struct WarpState {
 struct Cta {
     unsigned nthreads = 0, cur = 0;
     std::vector<ucontext_t> ctx;
-    std::vector<std::vector<char>> stacks;
     std::vector<char> done;
     std::vector<WarpState> warps;
     ucontext_t sched;
@@ -53,13 +52,16 @@ static inline void run_cta(unsigned nthreads, std::function<void()> body, size_t
     if (nthreads % 32) { std::fprintf(stderr, "simt: CTA size must be a multiple of 32\n"); std::abort(); }
     Cta c;
     c.nthreads = nthreads;
-    c.ctx.resize(nthreads); c.stacks.resize(nthreads); c.done.assign(nthreads, 0); c.warps.resize(nthreads / 32);
+    c.ctx.resize(nthreads); c.done.assign(nthreads, 0); c.warps.resize(nthreads / 32);
+    static std::vector<char*> pool;                      // fibre stacks, kept across CTAs (never zeroed, never freed)
+    static size_t pool_bytes = 0;
+    if (pool_bytes != stack_bytes) { for (char* q : pool) std::free(q); pool.clear(); pool_bytes = stack_bytes; }
+    while (pool.size() < nthreads) pool.push_back(static_cast<char*>(std::malloc(stack_bytes)));
     c.body = std::move(body);
     g_cta = &c;
     for (unsigned t = 0; t < nthreads; ++t) {
-        c.stacks[t].resize(stack_bytes);
         getcontext(&c.ctx[t]);
-        c.ctx[t].uc_stack.ss_sp = c.stacks[t].data();
+        c.ctx[t].uc_stack.ss_sp = pool[t];
         c.ctx[t].uc_stack.ss_size = stack_bytes;
         c.ctx[t].uc_link = &c.sched;
         makecontext(&c.ctx[t], trampoline, 0);
@@ -131,4 +133,15 @@ static inline int max(int a, int b) { return a > b ? a : b; }
     do {                                                                                      \
         gridDim.x = (grid); blockDim.x = (block);                                             \
         for (unsigned b_ = 0; b_ < (unsigned)(grid); ++b_) { blockIdx.x = b_; simt::run_cta((block), [&]() { call; }); } \
+    } while (0)
+#define SIMT_LAUNCH3(gx, gy, gz, block, call)                                                 \
+    do {                                                                                      \
+        gridDim.x = (gx); gridDim.y = (gy); gridDim.z = (gz); blockDim.x = (block);           \
+        for (unsigned z_ = 0; z_ < (unsigned)(gz); ++z_)                                      \
+            for (unsigned y_ = 0; y_ < (unsigned)(gy); ++y_)                                  \
+                for (unsigned x_ = 0; x_ < (unsigned)(gx); ++x_) {                            \
+                    blockIdx.x = x_; blockIdx.y = y_; blockIdx.z = z_;                        \
+                    simt::run_cta((block), [&]() { call; });                                  \
+                }                                                                             \
+        gridDim.y = gridDim.z = 1; blockIdx.y = blockIdx.z = 0;                               \
     } while (0)

@@ -5,10 +5,13 @@
 #include "simt_host.h"
 #include "../../pnnp_b200/csrc/noise_kernels.cuh"
 #include "../../pnnp_b200/csrc/train_kernels.cuh"
+#include "../../pnnp_b200/csrc/eval_kernels.cuh"
+#include "../../pnnp_b200/csrc/hbr_kernels.cuh"
 
 namespace pnnp {                                     // the kernels' dynamic shared memory (`extern __shared__` arrays)
 alignas(16) uint8_t s_fast[kFastSmemBytes];
 float s_acc[4 * 64 + 4 + 64], s_b[1024], s_b2[2048];
+alignas(16) uint8_t s2_raw[sizeof(Ssim2Tile)];
 }
 
 using namespace pnnp;
@@ -86,6 +89,35 @@ int emul_adam(float* p, const float* g, float* m, float* v, size_t total, float 
         const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
         SIMT_LAUNCH(blocks, 256, (adam_kernel(p, g, m, v, total, lr, b1, b2, eps, bc1, bc2, gscale)));
     }
+    return 0;
+}
+
+// ---- eval epilogue (csrc/eval_kernels.cuh), as pnnp_eval_epilogue launches it; dots_blocks is free
+int emul_eval_epilogue(const float* dn, const float* hr, int n, int c, int h, int w, float scale, int brightness_correct, double* sums,
+                       int v2, int dots_blocks) {
+    if (n <= 0 || c <= 0 || h < kSsimWin || w < kSsimWin) return 1;
+    const int stride = 3 + c;
+    for (int i = 0; i < n * stride; ++i) sums[i] = 0.0;
+    const size_t per_frame = (size_t)c * h * w;
+    if (brightness_correct) SIMT_LAUNCH3(dots_blocks, n, 1, 256, (illum_dots_kernel(dn, hr, per_frame, scale, sums, stride)));
+    if (v2) {
+        const Ssim2Args a{dn, hr, c, h, w, scale, 1.0f, brightness_correct};
+        SIMT_LAUNCH3((w + kS2TileX - 1) / kS2TileX, (h + kS2TileY - 1) / kS2TileY, n * c, kS2Threads, (ssim_mse_v2_kernel(a, sums, stride)));
+    } else {
+        SIMT_LAUNCH3((w + kTileX - 1) / kTileX, (h + kTileY - 1) / kTileY, n * c, 256,
+                     (ssim_mse_kernel(dn, hr, c, h, w, scale, brightness_correct, sums, stride)));
+    }
+    return 0;
+}
+
+// ---- HighBitRecovery map (csrc/hbr_kernels.cuh), arguments of pnnp_hbr_map
+int emul_hbr_map(const float* in, float* out, size_t total, const double* cdf, const double* range, int low, int high, int scale_in,
+                 int norm, float span, float bl, int dist_tukey, double lam, double loc, double scale, const double* rand, uint64_t seed,
+                 uint64_t offset, uint64_t index0, double* rand_out, int blocks) {
+    if (high < low) return 1;
+    const HbrArgs a{in, out, total, cdf, range, low, high, scale_in, norm, span, bl, dist_tukey, lam, loc, scale, rand,
+                    philox_round_keys(seed), (uint32_t)offset, (uint32_t)(offset >> 32), index0, rand_out};
+    SIMT_LAUNCH(blocks, 256, (hbr_map_kernel(a)));
     return 0;
 }
 

@@ -272,3 +272,88 @@ def test_adam_kernels_vs_torch_optim(S, on_device_state):
         assert S.emul_adam(_p(p, _f32p), _p(gn, _f32p), _p(m, _f32p), _p(v, _f32p), C.c_size_t(1000), C.c_float(1e-3), C.c_float(0.9),
                            C.c_float(0.999), C.c_float(1e-8), step, C.c_float(0.5), on_device_state, 2) == 0
         assert np.allclose(p, ref.detach().numpy(), rtol=2e-6, atol=2e-7)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# Eval epilogue (csrc/eval_kernels.cuh: IlluminanceCorrect dots, squared error, SSIM map sums; shuffle + shared-memory block
+# reductions, 3-D grid) and the HighBitRecovery map (csrc/hbr_kernels.cuh) — the same checks the `-m gpu` files make on a B200.
+# ----------------------------------------------------------------------------------------------------------------------------
+def _oracle_metrics(dn, hr, scale, correct):
+    import torch
+    d = torch.clamp(torch.from_numpy(dn) * scale, 0, 1)
+    t = torch.from_numpy(hr)
+    if correct:
+        d = O.illuminance_correct(d, t)
+    a, b = O.tensor2im(d.numpy()), O.tensor2im(hr)
+    return O.psnr(b, a), O.ssim(b, a)
+
+
+@pytest.mark.parametrize("v2", [0, 1])
+@pytest.mark.parametrize("shape,correct,scale", [((1, 4, 40, 72), False, 1.0), ((2, 3, 37, 67), True, 1.0), ((1, 4, 33, 34), True, 100.0)])
+def test_eval_epilogue_kernels_vs_oracle(S, golden, shape, correct, scale, v2):
+    from pnnp_b200.metrics import finish_metrics
+    import torch
+    n, c, h, w = shape
+    rs = np.random.RandomState(h)
+    hr = rs.rand(*shape).astype(np.float32)
+    hr[:, 0, :2, :7] = 1.0                                       # saturated pixels are excluded from the gain
+    dn = ((hr * 0.9 + 0.05 * rs.randn(*shape)) / scale).astype(np.float32)
+    sums = np.full((n, 3 + c), np.nan, np.float64)
+    assert S.emul_eval_epilogue(_p(dn, _f32p), _p(hr, _f32p), n, c, h, w, C.c_float(scale), int(correct), _p(sums, _f64p), v2, 3) == 0
+    res = finish_metrics(torch.from_numpy(sums), c, h, w)
+    for i in range(n):
+        p, s = _oracle_metrics(dn[i:i + 1], hr[i:i + 1], scale, correct)
+        assert res[i]["PSNR"] == pytest.approx(p, abs=2e-4) and res[i]["SSIM"] == pytest.approx(s, abs=1e-6), (res[i], p, s)
+    if correct and scale == 1.0:                                 # the gain itself: num / den of the reference's masked dot products
+        d = np.clip(dn[0], 0, 1)
+        m = hr[0] != 1
+        assert sums[0, 0] / sums[0, 1] == pytest.approx(float(np.dot(d[m].astype(np.float64), hr[0][m])) / float(np.dot(d[m].astype(np.float64), d[m])), rel=1e-12)
+
+
+def test_illuminance_correct_kernel_vs_reference_golden(S, golden):
+    """data_process/__init__.py:162-175 on the golden of the unmodified reference: gain = num / den in float32, times the clamped prediction."""
+    g = golden("eval")
+    pred, src = np.ascontiguousarray(np.clip(g["pred"], 0, 1), np.float32), np.ascontiguousarray(g["src"], np.float32)
+    n, c, h, w = pred.shape
+    sums = np.zeros((n, 3 + c), np.float64)
+    assert S.emul_eval_epilogue(_p(pred, _f32p), _p(src, _f32p), n, c, h, w, C.c_float(1.0), 1, _p(sums, _f64p), 0, 2) == 0
+    gain = np.float32(sums[0, 0]) / np.float32(sums[0, 1])
+    np.testing.assert_allclose(gain * pred, g["corrected"], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("k,cam,code,iso", ((0, "SonyA7S2", "pgrq", 3200), (1, "IMX686", "prq", 6400)))
+def test_hbr_map_kernel_vs_reference_goldens(S, golden, k, cam, code, iso):
+    """HighBitRecovery.map (process.py:726-751) fed the reference's own uniforms: float64 quantile (libm here, CUDA's math library on
+    the device, SciPy in the reference) rounded to float32 — equal to the reference except for isolated last-bit differences; and
+    the Philox path re-draws every sample inside its quantisation cell."""
+    from pnnp_b200.real_preproc import HighBitRecovery
+    g = golden("realdata")
+    np.random.seed(100 + k)
+    hb = HighBitRecovery(camera_type=cam, noise_code=code)
+    hb.get_lut([iso], blc_mean=None)
+    lut = hb.lut[iso]
+    p = lut["param"]
+    span = float(p["wp"] - p["bl"])
+    tukey = "g" in code
+    tab = np.ascontiguousarray(lut["_table"])
+
+    def run(data, norm, rand, seed=0, offset=0):
+        data = np.ascontiguousarray(data, np.float32)
+        out, r_out = np.full_like(data, np.nan), np.full(data.shape, np.nan, np.float64)
+        assert S.emul_hbr_map(_p(data, _f32p), _p(out, _f32p), C.c_size_t(data.size), _p(tab[0], _f64p), _p(tab[1], _f64p), int(lut["low"]),
+                              int(lut["high"]), int(data.max() <= 1), int(norm), C.c_float(span), C.c_float(p["bl"]), int(tukey),
+                              C.c_double(p["lam"]), C.c_double(lut["bias"]), C.c_double(p["sigTL"] if tukey else p["sigGs"]),
+                              _p(rand, _f64p), C.c_uint64(seed), C.c_uint64(offset), C.c_uint64(0), _p(r_out, _f64p), 3) == 0
+        return out, r_out
+
+    data, rand = g[f"hbr{k}_data"], np.ascontiguousarray(g[f"hbr{k}_rand"], np.float64)
+    for d_in, norm, want in ((data, True, g[f"hbr{k}_out"]), (data * np.float32(span), False, g[f"hbr{k}_out_dn"])):
+        got, _ = run(d_in, norm, rand)
+        assert (got == want).mean() > 0.995 and np.abs(got - want).max() <= 2 * np.spacing(np.abs(want).max())
+    from scipy import stats
+    cell = np.full((64, 64), 2.0 / span, np.float32)                     # every sample in the DN cell x = 2
+    out, u = run(cell, False, None, seed=11, offset=5)
+    assert stats.kstest(u.ravel(), "uniform").pvalue > 1e-3
+    x = out.ravel().astype(np.float64) - p["bl"]
+    assert x.min() >= 1.5 - 1e-3 and x.max() <= 2.5 + 1e-3
+    assert np.array_equal(run(cell, False, np.ascontiguousarray(u))[0], out)    # same arithmetic with the draws replayed
