@@ -116,12 +116,6 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
     }
 }
 
-// Packed fp32 pairs (sm_100: FADD2 / FFMA2 — two IEEE operations per instruction, results identical to the scalar forms)
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
 // ------------------------------------------------------------------------------------------ kernel
 // EPI: compile-time specialisation of the epilogue.  -1 = generic (every feature decided at run time).  >= 0 = the hot NHWC-output
 // 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
@@ -179,26 +173,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         // Programmatic dependent launch (opt-in, PNNP_CONV_PDL=1): this grid may have been scheduled while the previous kernel of
         // the stream was still draining.  Nothing above touches global memory; every thread waits here for the previous grid to
         // complete and flush, then lets the next conv layer's CTAs be scheduled as ours retire.
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        pdl_wait_then_release();
     }
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.head_out)
         for (int i = threadIdx.x; i < 4 * p.cout; i += blockDim.x)      // [channel][4 outputs], zero beyond head_cout
             s_head_w[i] = (i & 3) < p.head_cout ? p.head_w[(i & 3) * p.cout + (i >> 2)] : 0.f;
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        prefetch_tensormap(&tmA0);
+        prefetch_tensormap(&tmA1);
+        prefetch_tensormap(&tmB);
         for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         for (int a = 0; a < p.groups; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
         mbar_init(smem_u32(bres_bar), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbarrier_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -560,7 +550,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 #undef PNNP_MODE_K

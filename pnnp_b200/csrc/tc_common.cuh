@@ -1,5 +1,10 @@
 // Shared PTX wrappers for the tcgen05 / TMA / mbarrier kernels (conv_tc.cu, wgrad_tc.cu), sm_100a.
 #pragma once
+#ifdef PNNP_HOST_EMUL
+// tests/emul/: the CPU suite compiles the tensor-core kernels for the host against a FUNCTIONAL MODEL of these wrappers (mbarrier
+// phases, TMA tile copies with swizzle and zero fill, tcgen05.mma on K-major swizzled operands, TMEM) — test infrastructure only
+#include "tc_host_model.h"
+#else
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -71,6 +76,25 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {          // one warp; the base address lands in the smem slot
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols));
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+__device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// programmatic dependent launch: wait for the previous grid of the stream, then let the next one be scheduled
+__device__ __forceinline__ void pdl_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// Packed fp32 pairs (sm_100: FADD2 / FFMA2 — two IEEE operations per instruction, results identical to the scalar forms)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
@@ -83,3 +107,4 @@ __device__ __forceinline__ uint64_t umma_desc(uint64_t hi, uint32_t saddr) { ret
 
 
 }  // namespace pnnp
+#endif  // PNNP_HOST_EMUL
