@@ -2,7 +2,9 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#ifndef PNNP_HOST_EMUL
 #include <cuda_runtime.h>
+#endif
 
 namespace pnnp {
 int fail(const char* msg);                 // records msg, returns 1

@@ -20,8 +20,10 @@
 // elected lane), warps 2-5 = epilogue (TMEM -> registers -> bias/activation/residual -> global).
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), TMEM accumulator double buffer
 // full/empty mbarriers (MMA <-> epilogue).
+#ifndef PNNP_HOST_EMUL
 #include <cuda.h>
 #include <cuda_bf16.h>
+#endif
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -29,6 +31,14 @@
 #include "abi_common.h"
 #include "tc_common.cuh"
 #include "../../include/pnnp_b200.h"
+
+// kernel launch of the (taps per stage, K16 slices, epilogue, variant) instantiation; tests/emul/ compiles this file for the host and
+// runs the launch on its SIMT emulator + tensor-core model instead (test infrastructure only)
+#ifdef PNNP_HOST_EMUL
+#define PNNP_CONV_KLAUNCH(T, K, E, V) emul_launch_1d(grid, 64 + 128 * groups, [&]() { conv_gemm_tc_kernel<T, K, E, V>(tmA0, tmA1, tmB, p); })
+#else
+#define PNNP_CONV_KLAUNCH(T, K, E, V) conv_gemm_tc_kernel<T, K, E, V><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p)
+#endif
 
 namespace pnnp {
 
@@ -558,7 +568,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #undef PNNP_SWZ_K
 
 }  // namespace pnnp
+#ifndef PNNP_HOST_EMUL
 #include "layout_kernels.cuh"      // nchw_f32_to_nhwc16_bf16_kernel(s), maxpool2x2_nhwc_bf16_kernel
+#endif
 namespace pnnp {
 
 // ------------------------------------------------------------------------------------------ host side
@@ -671,7 +683,24 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
         act == ACT_NONE && !no_spec && !dbg_env)
         epi = EPI_CONVT;
-    const bool sup = super_env > 0 && mode != MODE_CONVT && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
+    // K chunk the shared-memory plan below ends up with for a given A-box height.  The super-tile variant is taken only where its
+    // 18-row boxes leave the plan's K chunk (hence the order in which a pixel's products are accumulated) as the default kernel
+    // has it: found on the CPU model (tests/test_device_tc_on_cpu.py) — for Cout = 128 the taller boxes evict the resident weights,
+    // the chunk drops from 64 to 32 channels and outputs differ from the default kernel's in the last bf16 bit.
+    auto plan_kc = [&](int box_rows) {
+        const int budget = 227 * 1024 - 4096 - cout * 20, cin_all = cin0 + (nsrc > 1 ? cin1 : 0);
+        int k = kc;
+        const int bts = (umma_n * k * 2 + 1023) / 1024 * 1024;
+        const int res_bytes = (cin_all / k) * (mode == MODE_CONVT ? 1 : taps) * bts, a_only = (box_rows * kTileW * k * 2 + 1023) / 1024 * 1024;
+        const bool res = (mode != MODE_CONVT || convt_fast) && n_tiles == 1 && res_bytes + 3 * a_only <= budget && !getenv("PNNP_NO_RESIDENT_W");
+        for (;; k >>= 1) {
+            const int a_b = box_rows * kTileW * k * 2, b_ts = (umma_n * k * 2 + 1023) / 1024 * 1024;
+            const int st_b = ((res ? a_b : a_b + tps * b_ts) + 1023) / 1024 * 1024;
+            if ((budget - (res ? res_bytes : 0)) / st_b >= 3 || k == 16 || res) return k;
+        }
+    };
+    const bool sup_wanted = super_env > 0 && mode != MODE_CONVT && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
+    const bool sup = sup_wanted && plan_kc(2 * kTileH + 2) == plan_kc(kTileH + 2);
     const int tile_rows = sup ? 2 * kTileH : kTileH;
     const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? tile_rows + 2 : kTileH;
     // shrink the K chunk until at least 3 pipeline stages fit
@@ -790,7 +819,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (x2) {
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
         if (sup) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 7>, tmA0, tmA1, tmB, p)); \
-        else conv_gemm_tc_kernel<T, K, E, 4><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \
+        else PNNP_CONV_KLAUNCH(T, K, E, 4); \
         launched = true; }
         PNNP_FOR_EACH_SUPER_VARIANT(X)
 #undef X
@@ -798,7 +827,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (sup && !launched) {
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
         if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 3>, tmA0, tmA1, tmB, p)); \
-        else conv_gemm_tc_kernel<T, K, E, 1><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \
+        else PNNP_CONV_KLAUNCH(T, K, E, 1); \
         launched = true; }
         PNNP_FOR_EACH_SUPER_VARIANT(X)
 #undef X
@@ -807,7 +836,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
         if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 2>, tmA0, tmA1, tmB, p)); \
-        else conv_gemm_tc_kernel<T, K, E><<<grid, 64 + 128 * groups, smem, st>>>(tmA0, tmA1, tmB, p); \
+        else PNNP_CONV_KLAUNCH(T, K, E, 0); \
         launched = true; }
     PNNP_FOR_EACH_CONV_VARIANT(X)
 #undef X
@@ -842,6 +871,7 @@ extern "C" int pnnp_conv_pipeline_error(void) {
     return v;
 }
 
+#ifndef PNNP_HOST_EMUL
 extern "C" int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, float scale, void* stream) {
     if (!in || !out || c > 16) return fail("nchw_to_nhwc16: bad arguments");
     const size_t total = (size_t)n * h * w;
@@ -869,3 +899,4 @@ extern "C" int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int
     PNNP_CUDA(cudaGetLastError());
     return 0;
 }
+#endif  // PNNP_HOST_EMUL

@@ -123,6 +123,19 @@ template <typename T> static inline T __shfl_xor_sync(unsigned mask, T val, int 
     const unsigned lane = simt::g_cta->cur & 31;
     return simt::from_bits<T>(simt::warp_exchange(simt::to_bits(val))[(lane ^ (unsigned)lane_mask) & 31]);
 }
+// width-limited forms: lanes are grouped in segments of `width`; a source outside the caller's segment returns the caller's own value
+template <typename T> static inline T __shfl_up_sync(unsigned mask, T val, unsigned delta, int width = 32) {
+    if (mask != 0xffffffffu) { std::fprintf(stderr, "simt: partial-mask shuffle\n"); std::abort(); }
+    const unsigned lane = simt::g_cta->cur & 31;
+    const uint64_t* v = simt::warp_exchange(simt::to_bits(val));
+    return (lane % (unsigned)width) >= delta ? simt::from_bits<T>(v[lane - delta]) : val;
+}
+template <typename T> static inline T __shfl_down_sync(unsigned mask, T val, unsigned delta, int width = 32) {
+    if (mask != 0xffffffffu) { std::fprintf(stderr, "simt: partial-mask shuffle\n"); std::abort(); }
+    const unsigned lane = simt::g_cta->cur & 31;
+    const uint64_t* v = simt::warp_exchange(simt::to_bits(val));
+    return (lane % (unsigned)width) + delta < (unsigned)width ? simt::from_bits<T>(v[lane + delta]) : val;
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> static inline T atomicAdd(T* p, T v) { const T old = *p; *p = old + v; return old; }
 static inline int min(int a, int b) { return a < b ? a : b; }

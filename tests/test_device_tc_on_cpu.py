@@ -1,0 +1,329 @@
+"""pnnp_b200/csrc/conv_tc.cu ITSELF — the tcgen05 / TMEM / TMA implicit-GEMM convolution kernel, its launcher (variant selection,
+shared-memory plan, tensor-map encoding) — compiled for the host and run without a GPU:
+
+  tests/emul/simt_host.h       every CUDA thread of a CTA is a fibre; ballots, shuffles, __syncthreads are real rendezvous;
+  tests/emul/tc_host_model.h   a FUNCTIONAL model of what the kernel asks of the hardware: mbarrier phases / arrivals / transaction
+                               bytes, TMA tiled loads (element strides, zero fill outside the tensor, 32/64/128-byte swizzle),
+                               tcgen05.mma on K-major swizzled shared-memory descriptors into TMEM (M = 128), tcgen05.ld by lane
+                               quadrant, tcgen05.commit, TMEM allocation.  Waits that can never complete are reported through the
+                               kernel's own pipeline-error word instead of hanging.
+
+The model is CALIBRATED by the instantiations that are parity-green on a B200 (round-1 `-m gpu` runs): under it they reproduce
+torch's convolutions here — every mode of the kernel, fused epilogues included, through the product's own host code
+(`archs._conv`, `_PackedLayer`, `UNetSeeInDark.forward`).  The same semantics then check the OPT-IN instantiations written after the
+round's GPU budget was spent (super-tile, ConvTranspose2d fast path, packed-pair epilogue, PDL build) for bit-equality with the
+default kernels before they are given GPU time.  Not modelled: timing, and hazards that only asynchronous execution exposes.
+Test infrastructure only: the product has no CPU path."""
+import contextlib
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle_np as O
+import pnnp_b200 as P
+from conftest import ROOT
+from pnnp_b200 import _lib, archs
+
+EMUL = os.path.join(ROOT, "tests", "emul")
+CSRC = os.path.join(ROOT, "pnnp_b200", "csrc")
+_VARIANT_ENV = ("PNNP_CONV_SUPER", "PNNP_CONVT_FAST", "PNNP_CONV_F32X2", "PNNP_CONV_PDL", "PNNP_IN_V2")
+
+
+def _build(name, src, deps):
+    out = os.path.join(EMUL, "_build", name)
+    srcs = [os.path.join(EMUL, src)] + deps
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-I", EMUL, "-shared", "-fPIC", "-o", out,
+                        srcs[0]], check=True)
+    return C.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def libs():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    shim = [os.path.join(EMUL, f) for f in ("cuda_host_shim.h", "simt_host.h", "tc_host_model.h")]
+    tc = _build("libtc_kernels_host.so", "tc_kernels_host.cpp",
+                shim + [os.path.join(CSRC, f) for f in ("conv_tc.cu", "tc_common.cuh", "abi_common.h")] + [os.path.join(ROOT, "include", "pnnp_b200.h")])
+    tc.emul_tc_last_error.restype = C.c_char_p
+    k = _build("libkernels_host.so", "kernels_host.cpp", shim[:1] + [os.path.join(CSRC, "layout_kernels.cuh")])
+    return tc, k
+
+
+class _EmulatedLibrary:
+    """Stands where ctypes' libpnnp_b200.so stands in the product's host code; every ABI entry the forward uses goes to the
+    host-compiled device source."""
+
+    def __init__(self, tc, k):
+        self.tc, self.k = tc, k
+
+    def pnnp_conv2d_tc_ex(self, desc, stream):
+        return self.tc.emul_conv2d_tc_ex(C.byref(desc))
+
+    def pnnp_nchw_to_nhwc16(self, src, dst, n, c, h, w, scale, stream):
+        v2 = int(os.environ.get("PNNP_IN_V2", "0") == "1" and (h * w) % 4 == 0)
+        return self.k.emul_nchw_to_nhwc16(C.c_void_p(src), C.c_void_p(dst), n, c, h, w, C.c_float(scale), v2, 3, 256)
+
+    def pnnp_maxpool2x2_nhwc(self, src, dst, n, h, w, c, stream):
+        return self.k.emul_maxpool2x2_nhwc(C.c_void_p(src), C.c_void_p(dst), n, h, w, c, 2, 256)
+
+    def pnnp_last_error(self):
+        return self.tc.emul_tc_last_error()
+
+    def pnnp_conv_pipeline_error(self):
+        return self.tc.emul_conv_pipeline_error()
+
+
+@pytest.fixture
+def emu(monkeypatch, libs):
+    lib = _EmulatedLibrary(*libs)
+    monkeypatch.setattr(_lib, "lib", lambda: lib)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda device=None: None)
+    monkeypatch.setattr(_lib, "require_cuda", lambda t, name="tensor": None)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    for k in _VARIANT_ENV:
+        monkeypatch.delenv(k, raising=False)
+    yield lib
+    assert lib.pnnp_conv_pipeline_error() == 0, "a pipeline wait of the emulated kernel could never complete"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _pack(w, kind="conv"):
+    m = type("M", (), {})()
+    m.weight, m.bias = w, None
+    return archs._PackedLayer(m, kind).get(w.device)[0]
+
+
+def _bits(t):
+    return t.view(torch.int16) if t.dtype == torch.bfloat16 else t
+
+
+def _with_env(monkeypatch, env, fn):
+    for k in _VARIANT_ENV:
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    try:
+        return fn()
+    finally:
+        for k in env:
+            monkeypatch.delenv(k, raising=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------- calibration
+@pytest.mark.parametrize("cin,cout,h,w,n,act", [(16, 32, 16, 32, 1, 1), (32, 32, 24, 40, 2, 0), (64, 64, 20, 36, 1, 1), (128, 256, 8, 16, 1, 1),
+                                                (256, 512, 8, 8, 1, 0), (64, 32, 12, 72, 1, 2)])
+def test_conv3x3_layer_vs_torch(emu, cin, cout, h, w, n, act):
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn((n, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, 3, 3), generator=g) / (3 * cin ** 0.5)
+    b = torch.randn((cout,), generator=g) * 0.1
+    out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16)
+    archs._conv(_lib.CONV3, _nhwc(x), _pack(wt), b, out, cout, act)
+    ref = F.conv2d(_bf(x), _bf(wt), b, padding=1)
+    ref = F.leaky_relu(ref, 0.2) if act == 1 else (F.relu(ref) if act == 2 else ref)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_two_sources_transposed_1x1_stride2_and_residual_modes_vs_torch(emu):
+    g = torch.Generator().manual_seed(5)
+    up, skip = torch.randn((1, 64, 24, 32), generator=g), torch.randn((1, 64, 24, 32), generator=g)
+    wt = torch.randn((64, 128, 3, 3), generator=g) / 30
+    b = torch.randn((64,), generator=g) * 0.1
+    out = torch.empty((1, 24, 32, 64), dtype=torch.bfloat16)
+    archs._conv(_lib.CONV3, _nhwc(up), _pack(wt), b, out, 64, _lib.ACT_LEAKY, x1=_nhwc(skip))           # torch.cat([up, skip], 1)
+    ref = F.leaky_relu(F.conv2d(torch.cat([_bf(up), _bf(skip)], 1), _bf(wt), b, padding=1), 0.2)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    for cin, cout in ((256, 128), (64, 32), (512, 256)):                                                    # ConvTranspose2d(2, stride 2)
+        x = torch.randn((1, cin, 8, 24), generator=g)
+        wt = torch.randn((cin, cout, 2, 2), generator=g) / cin ** 0.5
+        b = torch.randn((cout,), generator=g) * 0.1
+        out = torch.empty((1, 16, 48, cout), dtype=torch.bfloat16)
+        archs._conv(_lib.CONVT, _nhwc(x), _pack(wt, "convT"), b, out, cout, _lib.ACT_NONE)
+        ref = F.conv_transpose2d(_bf(x), _bf(wt), b, stride=2)
+        assert (_nchw(out) - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    x = torch.randn((2, 32, 24, 40), generator=g)                                                          # 1x1 -> NCHW fp32 + residual
+    wt = torch.randn((4, 32, 1, 1), generator=g) / 6
+    b = torch.randn((4,), generator=g) * 0.1
+    res = torch.randn((2, 4, 24, 40), generator=g)
+    out = torch.empty((2, 4, 24, 40), dtype=torch.float32)
+    archs._conv(_lib.CONV1, _nhwc(x), _pack(wt), b, out, 4, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32, resid_nchw=res)
+    ref = F.conv2d(_bf(x), _bf(wt), b) + res
+    assert (out - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    for cin, cout, h, w in ((32, 64, 32, 64), (64, 128, 16, 32), (32, 64, 24, 40)):                       # 3x3 stride 2 (ResUnet downsample)
+        x = torch.randn((2, cin, h, w), generator=g)
+        wt = torch.randn((cout, cin, 3, 3), generator=g) / (3 * cin ** 0.5)
+        b = torch.randn((cout,), generator=g) * 0.1
+        out = torch.empty((2, h // 2, w // 2, cout), dtype=torch.bfloat16)
+        archs._conv(_lib.CONV3S2, _nhwc(x), _pack(wt), b, out, cout, _lib.ACT_NONE)
+        ref = F.conv2d(_bf(x), _bf(wt), b, padding=1, stride=2)
+        assert (_nchw(out) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    x = torch.randn((1, 64, 16, 32), generator=g)                                                          # residual add in the epilogue
+    wt = torch.randn((64, 64, 3, 3), generator=g) / 24
+    out = torch.empty((1, 16, 32, 64), dtype=torch.bfloat16)
+    xb = _nhwc(x)
+    archs._conv(_lib.CONV3, xb, _pack(wt), None, out, 64, _lib.ACT_NONE, resid=xb)
+    ref = F.conv2d(_bf(x), _bf(wt), None, padding=1) + _bf(x)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+def test_fused_pool_head_and_mask_epilogues_vs_torch(emu):
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn((2, 32, 24, 48), generator=g)
+    wt = torch.randn((32, 32, 3, 3), generator=g) / 17
+    b = torch.randn((32,), generator=g) * 0.1
+    out = torch.empty((2, 24, 48, 32), dtype=torch.bfloat16)
+    pooled = torch.empty((2, 12, 24, 32), dtype=torch.bfloat16)
+    archs._conv(_lib.CONV3, _nhwc(x), _pack(wt), b, out, 32, _lib.ACT_LEAKY, pool_out=pooled)
+    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(out), 2))
+    hw = torch.randn((4, 32), generator=g) / 6
+    hb = torch.randn((4,), generator=g) * 0.1
+    res = torch.randn((2, 4, 24, 48), generator=g)
+    hout = torch.empty((2, 4, 24, 48), dtype=torch.float32)
+    archs._conv(_lib.CONV3, _nhwc(x), _pack(wt), b, None, 32, _lib.ACT_LEAKY, head=(hw, hb, hout), resid_nchw=res)
+    act = F.leaky_relu(F.conv2d(_bf(x), _bf(wt), b, padding=1), 0.2)
+    ref = F.conv2d(act, hw.view(4, 32, 1, 1), hb) + res
+    assert (hout - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    mask = _nhwc(torch.randn((2, 32, 24, 48), generator=g))                                                # training dgrad: g * act'(mask)
+    dx = torch.empty((2, 24, 48, 32), dtype=torch.bfloat16)
+    archs._conv(_lib.CONV3, _nhwc(x), _pack(wt), None, dx, 32, _lib.ACT_NONE, mask=mask, mask_slope=0.2)
+    ref = F.conv2d(_bf(x), _bf(wt), None, padding=1) * torch.where(_nchw(mask) > 0, 1.0, 0.2)
+    assert (_nchw(dx) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n,two", [(16, 32, 16, 32, 1, False), (32, 32, 24, 44, 2, False), (32, 32, 16, 30, 1, True), (64, 64, 24, 28, 1, True)])
+def test_x_shift_in_n_mode_vs_torch(emu, cin, cout, h, w, n, two):
+    g = torch.Generator().manual_seed(cin * 7 + cout + w)
+    x = torch.randn((n, cin, h, w), generator=g)
+    x2 = torch.randn((n, cin, h, w), generator=g) if two else None
+    ct = cin * (2 if two else 1)
+    wt = torch.randn((cout, ct, 3, 3), generator=g) / (3 * ct ** 0.5)
+    b = torch.randn((cout,), generator=g) * 0.1
+    out = torch.empty((n, h, w, cout), dtype=torch.bfloat16)
+    pooled = torch.empty((n, h // 2, w // 2, cout), dtype=torch.bfloat16)
+    archs._conv(_lib.CONV3X, _nhwc(x), _pack(wt, "conv3x"), b, out, cout, _lib.ACT_LEAKY, x1=None if x2 is None else _nhwc(x2), pool_out=pooled)
+    xin = _bf(x) if x2 is None else torch.cat([_bf(x), _bf(x2)], 1)
+    ref = F.leaky_relu(F.conv2d(xin, _bf(wt), b, padding=1), 0.2)
+    assert (_nchw(out) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(out), 2))
+
+
+def _unet(nf=16, seed=7):
+    torch.manual_seed(seed)
+    net = P.UNetSeeInDark({"in_nc": 4, "out_nc": 4, "nf": nf, "nframes": 1, "res": False}).eval()
+    P.initialize_weights(net)
+    return net
+
+
+def test_whole_unet_forward_vs_fp32_oracle(emu):
+    """UNetSeeInDark.forward — the product's own module code, 23 emulated tcgen05 launches — against the oracle's fp32 restatement
+    of archs/Unet.py:54-99 (reference init): the north-star bound of 1e-3 max-abs."""
+    net = _unet(nf=32)
+    x = torch.rand((1, 4, 32, 48), generator=torch.Generator().manual_seed(1997))
+    with torch.no_grad():
+        got = net(x)
+        want = O.unet_forward(x, net.state_dict())
+    assert (got - want).abs().max().item() <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------- opt-in variants == default kernels
+@pytest.mark.parametrize("sup", [1, 2])
+@pytest.mark.parametrize("xmode,cin,cout,h,w,n,two", [(True, 16, 32, 16, 32, 1, False), (True, 32, 32, 24, 44, 2, False), (True, 32, 32, 40, 30, 1, True),
+                                                      (False, 32, 64, 32, 48, 1, False), (False, 64, 128, 24, 32, 1, False), (False, 64, 64, 40, 36, 1, True)])
+def test_super_tile_equals_default_kernel_bit_for_bit(emu, monkeypatch, sup, xmode, cin, cout, h, w, n, two):
+    g = torch.Generator().manual_seed(cin * 31 + cout)
+    ct = cin * (2 if two else 1)
+    wp = _pack(torch.randn((cout, ct, 3, 3), generator=g) / (3 * ct ** 0.5), "conv3x" if xmode else "conv")
+    b = torch.randn((cout,), generator=g) * 0.1
+    x = _nhwc(torch.randn((n, cin, h, w), generator=g))
+    x2 = _nhwc(torch.randn((n, cin, h, w), generator=g)) if two else None
+
+    def call():
+        out = torch.zeros((n, h, w, cout), dtype=torch.bfloat16)
+        pooled = torch.zeros((n, h // 2, w // 2, cout), dtype=torch.bfloat16)
+        archs._conv(_lib.CONV3X if xmode else _lib.CONV3, x, wp, b, out, cout, _lib.ACT_LEAKY, x1=x2, pool_out=pooled)
+        return out, pooled
+    want = _with_env(monkeypatch, {}, call)
+    got = _with_env(monkeypatch, {"PNNP_CONV_SUPER": sup}, call)
+    assert torch.equal(_bits(got[0]), _bits(want[0])) and torch.equal(_bits(got[1]), _bits(want[1]))
+
+
+@pytest.mark.parametrize("env", [{"PNNP_CONV_SUPER": 1}, {"PNNP_CONV_SUPER": 2}, {"PNNP_CONV_F32X2": 1}, {"PNNP_CONV_PDL": 1},
+                                 {"PNNP_CONV_F32X2": 1, "PNNP_CONV_SUPER": 1, "PNNP_CONV_PDL": 1}, {"PNNP_CONV_F32X2": 1, "PNNP_CONV_SUPER": 2, "PNNP_CONV_PDL": 1}])
+def test_variants_fused_head_mask_and_packed_pairs_are_bit_identical(emu, monkeypatch, env):
+    g = torch.Generator().manual_seed(77)
+    wp = _pack(torch.randn((32, 32, 3, 3), generator=g) / 17)
+    wpx = _pack(torch.randn((32, 32, 3, 3), generator=g) / 17, "conv3x")
+    b = torch.randn((32,), generator=g) * 0.1
+    x = _nhwc(torch.randn((2, 32, 40, 44), generator=g))
+    hw = torch.randn((4, 32), generator=g) / 6
+    hb = torch.randn((4,), generator=g) * 0.1
+    res = torch.randn((2, 4, 40, 44), generator=g)
+    mask = _nhwc(torch.randn((2, 32, 40, 44), generator=g))
+    wp2 = _pack(torch.randn((64, 64, 3, 3), generator=g) / 24)
+    x2 = _nhwc(torch.randn((1, 64, 24, 48), generator=g))
+
+    def call():
+        hout = torch.zeros((2, 4, 40, 44), dtype=torch.float32)
+        archs._conv(_lib.CONV3, x, wp, b, None, 32, _lib.ACT_LEAKY, head=(hw, hb, hout), resid_nchw=res)
+        dx = torch.zeros((2, 40, 44, 32), dtype=torch.bfloat16)
+        archs._conv(_lib.CONV3, x, wp, None, dx, 32, _lib.ACT_NONE, mask=mask, mask_slope=0.2)
+        out = torch.zeros((2, 40, 44, 32), dtype=torch.bfloat16)
+        pooled = torch.zeros((2, 20, 22, 32), dtype=torch.bfloat16)
+        archs._conv(_lib.CONV3X, x, wpx, b, out, 32, _lib.ACT_LEAKY, pool_out=pooled)
+        houtx = torch.zeros((2, 4, 40, 44), dtype=torch.float32)
+        archs._conv(_lib.CONV3X, x, wpx, b, None, 32, _lib.ACT_LEAKY, head=(hw, hb, houtx))
+        out2 = torch.zeros((1, 24, 48, 64), dtype=torch.bfloat16)
+        archs._conv(_lib.CONV3, x2, wp2, b[:1].repeat(64), out2, 64, _lib.ACT_RELU)
+        return [hout, _bits(dx), _bits(out), _bits(pooled), houtx, _bits(out2)]
+    want = _with_env(monkeypatch, {}, call)
+    got = _with_env(monkeypatch, env, call)
+    assert all(torch.equal(a, c) for a, c in zip(got, want))
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n", [(64, 32, 16, 32, 1), (128, 64, 24, 40, 2), (256, 128, 8, 24, 1), (512, 256, 8, 8, 1)])
+def test_conv_transpose_fast_path_equals_default(emu, monkeypatch, cin, cout, h, w, n):
+    g = torch.Generator().manual_seed(cin + h)
+    x = _nhwc(torch.randn((n, cin, h, w), generator=g))
+    wp = _pack(torch.randn((cin, cout, 2, 2), generator=g) / cin ** 0.5, "convT")
+    b = torch.randn((cout,), generator=g) * 0.1
+
+    def call():
+        out = torch.zeros((n, 2 * h, 2 * w, cout), dtype=torch.bfloat16)
+        archs._conv(_lib.CONVT, x, wp, b, out, cout, _lib.ACT_NONE)
+        return out
+    want = _with_env(monkeypatch, {}, call)
+    got = _with_env(monkeypatch, {"PNNP_CONVT_FAST": 1}, call)
+    assert torch.equal(_bits(got), _bits(want))
+
+
+@pytest.mark.parametrize("env", [{"PNNP_CONV_SUPER": 1, "PNNP_CONVT_FAST": 1, "PNNP_IN_V2": 1, "PNNP_CONV_PDL": 1, "PNNP_CONV_F32X2": 1},
+                                 {"PNNP_CONV_SUPER": 2, "PNNP_CONVT_FAST": 1, "PNNP_IN_V2": 1, "PNNP_CONV_PDL": 1, "PNNP_CONV_F32X2": 1}])
+def test_all_variants_together_leave_the_unet_forward_unchanged(emu, monkeypatch, env):
+    net = _unet(nf=16, seed=4)
+    x = torch.rand((1, 4, 48, 64), generator=torch.Generator().manual_seed(2))
+
+    def call():
+        with torch.no_grad():
+            return net(x).clone()
+    want = _with_env(monkeypatch, {}, call)
+    got = _with_env(monkeypatch, env, call)
+    assert torch.isfinite(want).all() and torch.equal(got, want)
