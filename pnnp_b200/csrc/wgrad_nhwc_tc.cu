@@ -15,14 +15,23 @@
 // coalesced red.global.add (the scratch layout is [tap][ci][co], output channel = TMEM lane = fastest index).
 //
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (once, after the K loop).
+#ifndef PNNP_HOST_EMUL
 #include <cuda.h>
 #include <cuda_bf16.h>
+#endif
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include "abi_common.h"
 #include "tc_common.cuh"
 #include "../../include/pnnp_b200.h"
+
+// kernel launch; tests/emul/ compiles this file for the host and runs the launch on its SIMT emulator + tensor-core model instead
+#ifdef PNNP_HOST_EMUL
+#define PNNP_WGRAD_KLAUNCH(V) emul_launch_1d(combos * splits, 192, [&]() { wgrad_nhwc_kernel<V>(tmG, tmX, p); })
+#else
+#define PNNP_WGRAD_KLAUNCH(V) wgrad_nhwc_kernel<V><<<combos * splits, 192, smem, st>>>(tmG, tmX, p)
+#endif
 
 namespace pnnp {
 
@@ -89,16 +98,13 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int nk = max(0, t_end - t_begin);
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        prefetch_tensormap(&tmG);
+        prefetch_tensormap(&tmX);
         for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         mbar_init(smem_u32(done_bar), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbarrier_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -271,7 +277,7 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -444,9 +450,9 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
     if (getenv("PNNP_WGRAD_V2") && atoi(getenv("PNNP_WGRAD_V2")) > 0 && !p.dbg) {
         static bool attr2_done = false;
         if (!attr2_done) { PNNP_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2_done = true; }
-        wgrad_nhwc_kernel<1><<<combos * splits, 192, smem, st>>>(tmG, tmX, p);
+        PNNP_WGRAD_KLAUNCH(1);
     } else
-        wgrad_nhwc_kernel<0><<<combos * splits, 192, smem, st>>>(tmG, tmX, p);
+        PNNP_WGRAD_KLAUNCH(0);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

@@ -3,14 +3,14 @@
 // Include after cuda_host_shim.h and simt_host.h.  With it the CPU suite compiles conv_tc.cu ITSELF for the host — kernel, launcher,
 // tensor-map set-up — and runs it on the fibre SIMT emulator.
 //
-// What is modelled (cta_group::1, kind::f16, K-major operands — all the conv kernel uses):
+// What is modelled (cta_group::1, kind::f16 — all the conv and weight-gradient kernels use):
 //   * shared memory = pnnp::smem_raw (1024-aligned), shared "addresses" = offset + kSmemBase;
 //   * mbarrier: phase bit, pending arrivals, outstanding transaction bytes (init / arrive / arrive.expect_tx / complete_tx /
 //     try_wait.parity); a failed wait yields to the other fibres of the CTA;
 //   * TMA tiled loads (3-D / 4-D, element strides, zero fill outside the tensor, 32 / 64 / 128-byte swizzle = XOR of address bits
 //     [4,7) with bits [7,10) limited to the swizzle span) completing bytes on an mbarrier; executed at issue;
-//   * tcgen05.mma: D[M x N] (+)= A[M x 16] * B[N x 16]^T in fp32 from the two shared-memory descriptors (start, SBO, swizzle mode;
-//     8-row atoms of one swizzle span per row), M = 128 rows -> TMEM lanes; executed at issue, so tcgen05.commit is a plain arrive;
+//   * tcgen05.mma: D[M x N] (+)= A[M x 16] * B[N x 16]^T in fp32 from the two shared-memory descriptors (start, LBO, SBO, swizzle
+//     mode; K-major and MN-major canonical layouts), M = 128 rows -> TMEM lanes; executed at issue, so tcgen05.commit is a plain arrive;
 //   * TMEM = 128 lanes x 512 columns; tcgen05.ld 32x32b.x16 with the warp-quadrant lane restriction checked.
 // The model is calibrated by the kernels that are parity-green on a B200: under it the default instantiations reproduce torch's
 // convolutions; the same semantics then check the opt-in instantiations before they are given GPU time.  It does NOT model timing,
@@ -191,25 +191,36 @@ static inline void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, 
     if (M != 128) tc_model_fail("tcgen05.mma: only M = 128 (cta_group::1) is modelled");
     if (N < 16 || N > 256 || (N & 15)) tc_model_fail("tcgen05.mma: N must be a multiple of 16 in [16, 256] for M = 128");
     if ((idesc & ((1u << 4) | (1u << 7) | (1u << 10))) != ((1u << 4) | (1u << 7) | (1u << 10))) tc_model_fail("tcgen05.mma: expected f32 accumulate, bf16 A and B");
-    if (idesc & ((1u << 15) | (1u << 16))) tc_model_fail("tcgen05.mma: MN-major operands are not modelled");
-    auto decode = [](uint64_t desc, uint32_t& start, uint32_t& sbo, int& span) {
-        start = (uint32_t)(desc & 0x3FFFu) << 4; sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
+    const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;          // operand major-ness: 0 = K-major, 1 = MN-major
+    struct Op { uint32_t start, sbo, lbo; int span; bool mn; };
+    auto decode = [](uint64_t desc, bool mn) {
+        Op o;
+        o.start = (uint32_t)(desc & 0x3FFFu) << 4; o.lbo = (uint32_t)((desc >> 16) & 0x3FFFu) << 4; o.sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
+        o.mn = mn;
         const unsigned layout = (unsigned)(desc >> 61);
-        span = layout == 2 ? 128 : (layout == 4 ? 64 : (layout == 6 ? 32 : 0));
-        if (!span) tc_model_fail("shared-memory descriptor: only the 32 / 64 / 128-byte swizzled K-major layouts are modelled");
-        if (sbo != 8u * (uint32_t)span) tc_model_fail("shared-memory descriptor: SBO must be 8 rows of one swizzle span");
-        if ((start % (8u * (uint32_t)span)) + 32u > (uint32_t)span) tc_model_fail("shared-memory descriptor: start address leaves the first row of its swizzle atom (base offset not modelled)");
+        o.span = layout == 2 ? 128 : (layout == 4 ? 64 : (layout == 6 ? 32 : 0));
+        if (!o.span) tc_model_fail("shared-memory descriptor: only the 32 / 64 / 128-byte swizzled layouts are modelled");
+        if (o.sbo != 8u * (uint32_t)o.span) tc_model_fail("shared-memory descriptor: SBO must be 8 rows of one swizzle span");
+        if (mn ? (o.start % (8u * (uint32_t)o.span)) != 0 : (o.start % (8u * (uint32_t)o.span)) + 32u > (uint32_t)o.span)
+            tc_model_fail("shared-memory descriptor: start address not at the head of a swizzle atom (base offset not modelled)");
+        if (mn && (o.lbo % (8u * (uint32_t)o.span))) tc_model_fail("shared-memory descriptor: MN-major LBO must be a whole number of swizzle atoms");
+        return o;
     };
-    uint32_t sa, sbo_a, sb, sbo_b; int span_a, span_b;
-    decode(adesc, sa, sbo_a, span_a);
-    decode(bdesc, sb, sbo_b, span_b);
+    // element (i = M or N index, k = 0..15) of an operand.  K-major: 8-row atoms of one span per row, k contiguous.  MN-major (cute
+    // canonical ((T,span/16,m),(8,k)) : ((1,T,LBO),(span/2,SBO)) in elements): span/2 consecutive MN elements per K row, further MN
+    // blocks LBO bytes apart, 8 K rows per atom, atoms SBO bytes apart.
+    auto addr = [](const Op& o, int i, int k) {
+        const uint32_t e = (uint32_t)o.span / 2;
+        const uint32_t a = o.mn ? o.start + ((uint32_t)i % e) * 2 + ((uint32_t)i / e) * o.lbo + (uint32_t)(k & 7) * (uint32_t)o.span + (uint32_t)(k >> 3) * o.sbo
+                                : o.start + (uint32_t)(i >> 3) * o.sbo + (uint32_t)(i & 7) * (uint32_t)o.span + (uint32_t)k * 2;
+        return swizzle_addr(a, o.span);
+    };
+    const Op oa = decode(adesc, a_mn), ob = decode(bdesc, b_mn);
     const uint32_t col0 = d_tmem & 0xFFFFu;
     if ((d_tmem >> 16) != 0 || col0 + (uint32_t)N > 512) tc_model_fail("tcgen05.mma: accumulator outside TMEM");
     static float a[128][16], b[256][16];
-    for (int m = 0; m < M; ++m) for (int k = 0; k < 16; ++k)
-        a[m][k] = bf16_at(swizzle_addr(sa + (uint32_t)(m >> 3) * sbo_a + (uint32_t)(m & 7) * (uint32_t)span_a + (uint32_t)k * 2, span_a));
-    for (int n = 0; n < N; ++n) for (int k = 0; k < 16; ++k)
-        b[n][k] = bf16_at(swizzle_addr(sb + (uint32_t)(n >> 3) * sbo_b + (uint32_t)(n & 7) * (uint32_t)span_b + (uint32_t)k * 2, span_b));
+    for (int m = 0; m < M; ++m) for (int k = 0; k < 16; ++k) a[m][k] = bf16_at(addr(oa, m, k));
+    for (int n = 0; n < N; ++n) for (int k = 0; k < 16; ++k) b[n][k] = bf16_at(addr(ob, n, k));
     for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
         float s = 0.f;
         for (int k = 0; k < 16; ++k) s += a[m][k] * b[n][k];

@@ -19,11 +19,17 @@ void count_launch(uint64_t n) { g_launches += n; }
 }  // namespace pnnp
 
 #include "../../pnnp_b200/csrc/conv_tc.cu"
+#include "../../pnnp_b200/csrc/wgrad_nhwc_tc.cu"
 
 extern "C" {
 int emul_conv2d_tc_ex(const pnnp_conv_desc* d) { return pnnp::conv_layer_launch(*d, nullptr); }
 const char* emul_tc_last_error(void) { return pnnp::g_err_msg; }
 int emul_conv_pipeline_error(void) { return pnnp_conv_pipeline_error(); }
+int emul_wgrad_nhwc(int mode, const void* g, int co, int co_stride, const void* x, int ci, int ci_stride, int n, int h, int w, float* dw,
+                    int ci_off, int ci_total, int co_pad) {
+    return pnnp_wgrad_nhwc(mode, g, co, co_stride, x, ci, ci_stride, n, h, w, dw, ci_off, ci_total, co_pad, nullptr);
+}
+int emul_wgrad_pipeline_error(void) { return pnnp_wgrad_nhwc_pipeline_error(); }
 // counters of the model since the last call: [mma instructions, TMA loads, zero-filled elements, mbarrier waits]
 void emul_tc_stats(unsigned long* out4) {
     out4[0] = pnnp::g_tc_stats.mma; out4[1] = pnnp::g_tc_stats.tma; out4[2] = pnnp::g_tc_stats.tma_oob_elems; out4[3] = pnnp::g_tc_stats.waits;

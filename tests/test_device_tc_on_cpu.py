@@ -327,3 +327,72 @@ def test_all_variants_together_leave_the_unet_forward_unchanged(emu, monkeypatch
     want = _with_env(monkeypatch, {}, call)
     got = _with_env(monkeypatch, env, call)
     assert torch.isfinite(want).all() and torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------ weight gradients (wgrad_nhwc_tc.cu)
+# MN-major tcgen05 operands straight from NHWC boxes: the model's MN-major descriptor semantics (LBO = distance between channel
+# blocks — or, for the 32 / 64-output-channel layers, between filter rows) are calibrated by the default kernel (B200-green in round
+# 1) against torch's autograd; the opt-in register-resident producer / MMA loops (PNNP_WGRAD_V2=1) must then give the same sums.
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _wgrad(libs, mode, gon, co, xn, ci, n, h, w, dw, ci_off, ci_total):
+    tc = libs[0]
+    rc = tc.emul_wgrad_nhwc(mode, C.c_void_p(gon.data_ptr()), co, co, C.c_void_p(xn.data_ptr()), ci, ci, n, h, w, C.c_void_p(dw.data_ptr()),
+                            ci_off, ci_total, co)
+    assert rc == 0, tc.emul_tc_last_error()
+    assert tc.emul_wgrad_pipeline_error() == 0
+
+
+@pytest.mark.parametrize("v2", [0, 1])
+@pytest.mark.parametrize("ci,co,h,w,n", [(16, 32, 16, 32, 1), (32, 32, 24, 40, 2), (32, 64, 20, 36, 1), (64, 64, 16, 48, 2), (64, 128, 16, 16, 2),
+                                         (128, 64, 16, 32, 1), (128, 128, 24, 16, 1), (256, 256, 8, 16, 1), (256, 512, 4, 6, 2)])
+def test_wgrad_3x3_matches_autograd(libs, monkeypatch, v2, ci, co, h, w, n):
+    monkeypatch.setenv("PNNP_WGRAD_V2", str(v2))
+    g = torch.Generator().manual_seed(3 * ci + co)
+    x = _bf(torch.randn((n, ci, h, w), generator=g))
+    go = _bf(torch.randn((n, co, h, w), generator=g))
+    wt = torch.zeros((co, ci, 3, 3), requires_grad=True)
+    F.conv2d(x, wt, padding=1).backward(go)
+    dw = torch.zeros((9, ci, co))
+    _wgrad(libs, 0, _nhwc(go), co, _nhwc(x), ci, n, h, w, dw, 0, ci)
+    assert _rel(dw.permute(2, 1, 0).reshape(co, ci, 3, 3), wt.grad) < 1e-4      # bf16 operands are exact in both: fp32 summation order only
+
+
+@pytest.mark.parametrize("v2", [0, 1])
+def test_wgrad_two_sources_and_transposed_conv_match_autograd(libs, monkeypatch, v2):
+    monkeypatch.setenv("PNNP_WGRAD_V2", str(v2))
+    g = torch.Generator().manual_seed(9)
+    n, h, w, c0, c1, co = 2, 16, 32, 32, 32, 32
+    x0, x1 = (_bf(torch.randn((n, c, h, w), generator=g)) for c in (c0, c1))
+    go = _bf(torch.randn((n, co, h, w), generator=g))
+    wt = torch.zeros((co, c0 + c1, 3, 3), requires_grad=True)
+    F.conv2d(torch.cat([x0, x1], 1), wt, padding=1).backward(go)                  # torch.cat([up, skip], 1): each source adds its rows
+    dw = torch.zeros((9, c0 + c1, co))
+    _wgrad(libs, 0, _nhwc(go), co, _nhwc(x0), c0, n, h, w, dw, 0, c0 + c1)
+    _wgrad(libs, 0, _nhwc(go), co, _nhwc(x1), c1, n, h, w, dw, c0, c0 + c1)
+    assert _rel(dw.permute(2, 1, 0).reshape(co, c0 + c1, 3, 3), wt.grad) < 1e-4
+    for ci, co, h, w in ((64, 32, 16, 32), (128, 64, 8, 24), (512, 256, 8, 8)):   # ConvTranspose2d(2, stride 2)
+        x = _bf(torch.randn((2, ci, h, w), generator=g))
+        wt = torch.zeros((ci, co, 2, 2), requires_grad=True)
+        go = _bf(torch.randn((2, co, 2 * h, 2 * w), generator=g))
+        F.conv_transpose2d(x, wt, stride=2).backward(go)
+        dw = torch.zeros((4, ci, co))
+        _wgrad(libs, 1, _nhwc(go), co, _nhwc(x), ci, 2, h, w, dw, 0, ci)
+        assert _rel(dw.permute(1, 2, 0).reshape(ci, co, 2, 2), wt.grad) < 1e-4
+
+
+def test_data_gradient_modes_of_the_conv_kernel_match_autograd(emu):
+    """Backward data paths that run on conv_tc.cu: ConvTranspose2d dgrad = the 2x2 stride-2 mode; 3x3 dgrad = a 3x3 conv with the
+    flipped, transposed filter and the activation-derivative mask fused (checked above)."""
+    from pnnp_b200 import train
+    g = torch.Generator().manual_seed(64)
+    for ci, co, h, w in ((64, 32, 16, 32), (256, 128, 8, 8)):
+        x = _bf(torch.randn((2, ci, h, w), generator=g)).requires_grad_(True)
+        wt = _bf(torch.randn((ci, co, 2, 2), generator=g) / ci ** 0.5).requires_grad_(True)
+        go = _bf(torch.randn((2, co, 2 * h, 2 * w), generator=g))
+        F.conv_transpose2d(x, wt, stride=2).backward(go)
+        gx = torch.empty((2, h, w, ci), dtype=torch.bfloat16)
+        archs._conv(_lib.CONV2S2, _nhwc(go), train._pack_conv_weight(wt.detach()), None, gx, ci, _lib.ACT_NONE)
+        assert _rel(_nchw(gx), x.grad) < 6e-3                          # bf16 output rounding
