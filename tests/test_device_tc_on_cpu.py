@@ -244,6 +244,19 @@ def test_whole_unet_forward_vs_fp32_oracle(emu):
     assert (got - want).abs().max().item() <= 1e-3
 
 
+def test_whole_resunet_forward_vs_fp32_oracle(emu):
+    """ResUnet.forward (archs/ResUnet.py:46-88: bias-free residual blocks, 1x1 shortcuts over two sources, stride-2 3x3 downsampling,
+    residual add in the epilogue) against the oracle's fp32 restatement."""
+    torch.manual_seed(11)
+    net = P.ResUnet({"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}).eval()
+    P.initialize_weights(net)
+    x = torch.rand((1, 4, 32, 48), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        got = net(x)
+        want = O.resunet_forward(x, net.state_dict())
+    assert (got - want).abs().max().item() <= 1e-3
+
+
 # ------------------------------------------------------------------------------------------- opt-in variants == default kernels
 @pytest.mark.parametrize("sup", [1, 2])
 @pytest.mark.parametrize("xmode,cin,cout,h,w,n,two", [(True, 16, 32, 16, 32, 1, False), (True, 32, 32, 24, 44, 2, False), (True, 32, 32, 40, 30, 1, True),

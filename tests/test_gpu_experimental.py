@@ -4,7 +4,8 @@ environment variable that is off by default, and these tests are opt-in too (PNN
 
 * PNNP_CONV_SUPER=1|2 — super-tile conv kernel (conv_tc.cu, template parameter SUP): two M = 128 tiles per pipeline stage.  Every
   output pixel sees the same MMAs in the same order as in the default kernel, so the two must agree BIT FOR BIT — outputs,
-  fused max-pool, fused 1x1 head and the masked data-gradient epilogue alike.
+  fused max-pool, fused 1x1 head and the masked data-gradient epilogue alike.  (Checked on the CPU tensor-core model first,
+  tests/test_device_tc_on_cpu.py: the variant is only taken where its taller boxes keep the plan's K chunk.)
 * PNNP_CONVT_FAST=1 — ConvTranspose2d layers: compile-time specialised pixel-shuffle epilogue, weights resident in shared memory
   when 4 * cout <= 256, two CTAs per SM for the K = 64 layer.  Bit-identical to the default.
 * PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default.
