@@ -251,6 +251,8 @@ static inline uint64_t umma_desc(uint64_t hi, uint32_t saddr) { return hi | (uin
 
 // launch on the SIMT emulator: CTAs one after the other
 static inline void emul_launch_1d(int grid, int threads, const std::function<void()>& body) {
+    if (grid < 1 || threads < 32 || threads > 1024) tc_model_fail("kernel launch with an invalid grid / block size");
+    if (std::getenv("PNNP_EMUL_PLAN_ONLY")) return;          // launcher dry run: variant selection, smem / TMEM plan, tensor maps — no compute
     gridDim.x = (unsigned)grid; blockDim.x = (unsigned)threads;
     for (int b = 0; b < grid; ++b) { blockIdx.x = (unsigned)b; g_stalled_polls = 0; simt::run_cta((unsigned)threads, body); }
 }

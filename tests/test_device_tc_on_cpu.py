@@ -409,3 +409,28 @@ def test_data_gradient_modes_of_the_conv_kernel_match_autograd(emu):
         gx = torch.empty((2, h, w, ci), dtype=torch.bfloat16)
         archs._conv(_lib.CONV2S2, _nhwc(go), train._pack_conv_weight(wt.detach()), None, gx, ci, _lib.ACT_NONE)
         assert _rel(_nchw(gx), x.grad) < 6e-3                          # bf16 output rounding
+
+
+# ------------------------------------------------------------------------------------------ launcher dry run at the real frame sizes
+@pytest.mark.parametrize("env", [{}, {"PNNP_CONV_SUPER": 1}, {"PNNP_CONV_SUPER": 2, "PNNP_CONVT_FAST": 1},
+                                 {"PNNP_CONV_SUPER": 1, "PNNP_CONVT_FAST": 1, "PNNP_CONV_PDL": 1, "PNNP_CONV_F32X2": 1},
+                                 {"PNNP_CONV_SUPER": 2, "PNNP_CONVT_FAST": 1, "PNNP_CONV_PDL": 1, "PNNP_CONV_F32X2": 1}])
+def test_every_layer_of_both_networks_plans_at_the_benchmark_frame_sizes(emu, monkeypatch, env):
+    """The launcher of conv_tc.cu (kernel variant, K chunk, stages, resident weights, CTAs per SM, TMEM columns, tensor maps) for every
+    layer of UNetSeeInDark / ResUnet at the Sony frame (4 x 1424 x 2128), the padded IMX686 frame (4 x 1744 x 2320) and the training
+    crop batch (8 x 4 x 512 x 512), default and opt-in variants, on a 148-SM "device": PNNP_EMUL_PLAN_ONLY skips the kernels, so an
+    `internal` / budget failure of a configuration surfaces here instead of in a GPU call."""
+    monkeypatch.setenv("PNNP_EMUL_SMS", "148")
+    monkeypatch.setenv("PNNP_EMUL_PLAN_ONLY", "1")
+    monkeypatch.setattr(archs, "_to_nhwc16", lambda x, out, scale=1.0: out)          # layout kernel: nothing to plan
+    arch = {"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    for cls in (P.UNetSeeInDark, P.ResUnet):
+        net = cls(arch).eval()
+        for shape in ((1, 4, 1424, 2128), (1, 4, 1744, 2320), (8, 4, 512, 512)):
+            net.__dict__.pop("_workspace", None)                                      # release the previous geometry's activation buffers
+            with torch.no_grad():
+                out = net(torch.zeros(shape))
+            assert out.shape == shape
+        net.__dict__.pop("_workspace", None)
