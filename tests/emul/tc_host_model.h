@@ -8,18 +8,21 @@
 //   * mbarrier: phase bit, pending arrivals, outstanding transaction bytes (init / arrive / arrive.expect_tx / complete_tx /
 //     try_wait.parity); a failed wait yields to the other fibres of the CTA;
 //   * TMA tiled loads (3-D / 4-D, element strides, zero fill outside the tensor, 32 / 64 / 128-byte swizzle = XOR of address bits
-//     [4,7) with bits [7,10) limited to the swizzle span) completing bytes on an mbarrier; executed at issue;
+//     [4,7) with bits [7,10) limited to the swizzle span) completing bytes on an mbarrier;
 //   * tcgen05.mma: D[M x N] (+)= A[M x 16] * B[N x 16]^T in fp32 from the two shared-memory descriptors (start, LBO, SBO, swizzle
-//     mode; K-major and MN-major canonical layouts), M = 128 rows -> TMEM lanes; executed at issue, so tcgen05.commit is a plain arrive;
+//     mode; K-major and MN-major canonical layouts), M = 128 rows -> TMEM lanes; tcgen05.commit arrives after the MMAs queued before it;
 //   * TMEM = 128 lanes x 512 columns; tcgen05.ld 32x32b.x16 with the warp-quadrant lane restriction checked.
 // The model is calibrated by the kernels that are parity-green on a B200: under it the default instantiations reproduce torch's
-// convolutions; the same semantics then check the opt-in instantiations before they are given GPU time.  It does NOT model timing,
-// asynchrony hazards (a missing wait that happens to work in issue order) or alignment faults beyond the checks below.
+// convolutions; the same semantics then check the opt-in instantiations before they are given GPU time.  TMA loads, MMAs and
+// commits are asynchronous here too — queued at issue, executed as late as possible, TMA destinations poisoned meanwhile — so a
+// consumer that does not wait for the announcing barrier is caught.  Not modelled: timing, reordering between the two agents, and
+// alignment faults beyond the checks below.
 #pragma once
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 
 #define __grid_constant__
@@ -94,6 +97,19 @@ static uint32_t g_tmem[128][512];
 static unsigned long g_stalled_polls = 0;                    // consecutive failed mbarrier polls of the running CTA (deadlock detector)
 struct TcStats { unsigned long mma = 0, tma = 0, tma_oob_elems = 0, waits = 0; };
 static TcStats g_tc_stats;
+// Asynchronous agents (TMA unit, tensor pipe): an operation is queued at issue and EXECUTED AS LATE AS POSSIBLE — one queued operation
+// per failed mbarrier poll, in issue order — so device code that consumes a result without waiting for the barrier that announces it
+// (shared-memory stage, accumulator, reused slot) reads poison / stale data here instead of passing by luck of issue order.
+static std::deque<std::function<void()>> g_async;
+static unsigned long g_async_work = 0;                      // queued TMA loads / MMAs (commits are not counted)
+static unsigned long g_trailing_commits = 0;                // commits that were still queued when their CTA exited (no work before them)
+static inline bool async_run_one() {
+    if (g_async.empty()) return false;
+    std::function<void()> op = std::move(g_async.front());
+    g_async.pop_front();
+    op();
+    return true;
+}
 
 static inline void tc_model_fail(const char* what) { std::fprintf(stderr, "tc_host_model: %s\n", what); std::abort(); }
 static inline uint8_t* smem_ptr(uint32_t addr, size_t bytes) {
@@ -124,7 +140,8 @@ static inline void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) 
     while (true) {
         if ((mbar_at(bar)->phase & 1u) != (parity & 1u)) return;              // the phase with this parity has completed
         if (*err != 0) return;
-        if (++g_stalled_polls > 400000ul) { *err = code; return; }            // every fibre parked: the device would time out here
+        if (async_run_one()) { g_stalled_polls = 0; continue; }               // let the oldest queued TMA / MMA / commit happen, poll again
+        if (++g_stalled_polls > 400000ul) { *err = code; return; }            // every fibre parked, nothing in flight: the device would time out here
         const unsigned tid = simt::g_cta->cur;
         simt::yield();
         threadIdx.x = tid;
@@ -140,23 +157,31 @@ static inline void tma_load(uint32_t dst, const CUtensorMap* tm, uint32_t bar, c
     uint32_t cnt[5] = {1, 1, 1, 1, 1};
     size_t total = 1;
     for (int d = 0; d < tm->rank; ++d) { cnt[d] = (tm->box[d] + tm->estride[d] - 1) / tm->estride[d]; total *= cnt[d]; }
-    size_t lin = 0;
-    for (uint32_t i4 = 0; i4 < cnt[4]; ++i4) for (uint32_t i3 = 0; i3 < cnt[3]; ++i3) for (uint32_t i2 = 0; i2 < cnt[2]; ++i2)
-    for (uint32_t i1 = 0; i1 < cnt[1]; ++i1) for (uint32_t i0 = 0; i0 < cnt[0]; ++i0, ++lin) {
-        const uint32_t idx[5] = {i0, i1, i2, i3, i4};
-        bool inside = true;
-        size_t goff = 0;
-        for (int d = 0; d < tm->rank; ++d) {
-            const long long g = (long long)c[d] + (long long)idx[d] * tm->estride[d];
-            if (g < 0 || g >= (long long)tm->dims[d]) { inside = false; break; }
-            goff += (size_t)g * tm->strides[d];
+    const uint16_t poison = 0x7FC0;                                           // bf16 NaN: the unit may write the box any time from now on
+    for (size_t lin = 0; lin < total; ++lin) std::memcpy(smem_ptr(swizzle_addr(dst + (uint32_t)(lin * 2), tm->swizzle_bytes), 2), &poison, 2);
+    const CUtensorMap map = *tm;
+    int cc[5];
+    for (int d = 0; d < 5; ++d) cc[d] = c[d];
+    ++g_async_work;
+    g_async.push_back([=]() {
+        --g_async_work;
+        size_t lin = 0;
+        for (uint32_t i4 = 0; i4 < cnt[4]; ++i4) for (uint32_t i3 = 0; i3 < cnt[3]; ++i3) for (uint32_t i2 = 0; i2 < cnt[2]; ++i2)
+        for (uint32_t i1 = 0; i1 < cnt[1]; ++i1) for (uint32_t i0 = 0; i0 < cnt[0]; ++i0, ++lin) {
+            const uint32_t idx[5] = {i0, i1, i2, i3, i4};
+            bool inside = true;
+            size_t goff = 0;
+            for (int d = 0; d < map.rank; ++d) {
+                const long long g = (long long)cc[d] + (long long)idx[d] * map.estride[d];
+                if (g < 0 || g >= (long long)map.dims[d]) { inside = false; break; }
+                goff += (size_t)g * map.strides[d];
+            }
+            uint16_t v = 0;
+            if (inside) std::memcpy(&v, map.base + goff, 2); else ++g_tc_stats.tma_oob_elems;
+            std::memcpy(smem_ptr(swizzle_addr(dst + (uint32_t)(lin * 2), map.swizzle_bytes), 2), &v, 2);
         }
-        uint16_t v = 0;
-        if (inside) std::memcpy(&v, tm->base + goff, 2); else ++g_tc_stats.tma_oob_elems;
-        const uint32_t a = swizzle_addr(dst + (uint32_t)(lin * 2), tm->swizzle_bytes);
-        std::memcpy(smem_ptr(a, 2), &v, 2);
-    }
-    mbar_complete_tx(bar, (uint32_t)(total * 2));
+        mbar_complete_tx(bar, (uint32_t)(total * 2));
+    });
 }
 static inline void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
     if (tm->rank != 4) tc_model_fail("tma_load_4d on a tensor map of another rank");
@@ -183,7 +208,7 @@ static inline void tmem_alloc(uint32_t slot, uint32_t cols) {
     if ((simt::g_cta->cur & 31u) == 0) for (auto& lane : g_tmem) for (auto& w : lane) w = 0x7FC00000u;     // unwritten accumulators read as NaN
 }
 static inline void tmem_dealloc(uint32_t, uint32_t) {}
-static inline void tc_commit(uint32_t bar) { mbar_arrive(bar); }        // MMAs execute at issue in this model
+static inline void tc_commit(uint32_t bar) { g_async.push_back([=]() { mbar_arrive(bar); }); }     // arrives once every MMA queued before it has executed
 static inline float bf16_at(uint32_t addr) { uint16_t h; std::memcpy(&h, smem_ptr(addr, 2), 2); return __uint_as_float((uint32_t)h << 16); }
 static inline void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     ++g_tc_stats.mma;
@@ -218,15 +243,19 @@ static inline void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, 
     const Op oa = decode(adesc, a_mn), ob = decode(bdesc, b_mn);
     const uint32_t col0 = d_tmem & 0xFFFFu;
     if ((d_tmem >> 16) != 0 || col0 + (uint32_t)N > 512) tc_model_fail("tcgen05.mma: accumulator outside TMEM");
-    static float a[128][16], b[256][16];
-    for (int m = 0; m < M; ++m) for (int k = 0; k < 16; ++k) a[m][k] = bf16_at(addr(oa, m, k));
-    for (int n = 0; n < N; ++n) for (int k = 0; k < 16; ++k) b[n][k] = bf16_at(addr(ob, n, k));
-    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
-        float s = 0.f;
-        for (int k = 0; k < 16; ++k) s += a[m][k] * b[n][k];
-        uint32_t& d = g_tmem[m][col0 + n];
-        d = __float_as_uint(accumulate ? __uint_as_float(d) + s : s);
-    }
+    ++g_async_work;
+    g_async.push_back([=]() {
+        --g_async_work;
+        static float a[128][16], b[256][16];
+        for (int m = 0; m < M; ++m) for (int k = 0; k < 16; ++k) a[m][k] = bf16_at(addr(oa, m, k));
+        for (int n = 0; n < N; ++n) for (int k = 0; k < 16; ++k) b[n][k] = bf16_at(addr(ob, n, k));
+        for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+            float s = 0.f;
+            for (int k = 0; k < 16; ++k) s += a[m][k] * b[n][k];
+            uint32_t& d = g_tmem[m][col0 + n];
+            d = __float_as_uint(accumulate ? __uint_as_float(d) + s : s);
+        }
+    });
 }
 static inline void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     const unsigned tid = simt::g_cta->cur, lane = tid & 31u, warp = tid >> 5;
@@ -254,7 +283,12 @@ static inline void emul_launch_1d(int grid, int threads, const std::function<voi
     if (grid < 1 || threads < 32 || threads > 1024) tc_model_fail("kernel launch with an invalid grid / block size");
     if (std::getenv("PNNP_EMUL_PLAN_ONLY")) return;          // launcher dry run: variant selection, smem / TMEM plan, tensor maps — no compute
     gridDim.x = (unsigned)grid; blockDim.x = (unsigned)threads;
-    for (int b = 0; b < grid; ++b) { blockIdx.x = (unsigned)b; g_stalled_polls = 0; simt::run_cta((unsigned)threads, body); }
+    for (int b = 0; b < grid; ++b) {
+        blockIdx.x = (unsigned)b; g_stalled_polls = 0;
+        simt::run_cta((unsigned)threads, body);
+        if (g_async_work) tc_model_fail("CTA exited with TMA loads / MMAs still in flight (nobody waited for them)");
+        while (!g_async.empty()) { ++g_trailing_commits; async_run_one(); }    // a commit with nothing before it: completes at once on the device
+    }
 }
 
 }  // namespace pnnp

@@ -31,6 +31,7 @@ int emul_wgrad_nhwc(int mode, const void* g, int co, int co_stride, const void* 
 }
 int emul_wgrad_pipeline_error(void) { return pnnp_wgrad_nhwc_pipeline_error(); }
 // counters of the model since the last call: [mma instructions, TMA loads, zero-filled elements, mbarrier waits]
+unsigned long emul_tc_trailing_commits(void) { const unsigned long v = pnnp::g_trailing_commits; pnnp::g_trailing_commits = 0; return v; }
 void emul_tc_stats(unsigned long* out4) {
     out4[0] = pnnp::g_tc_stats.mma; out4[1] = pnnp::g_tc_stats.tma; out4[2] = pnnp::g_tc_stats.tma_oob_elems; out4[3] = pnnp::g_tc_stats.waits;
     pnnp::g_tc_stats = pnnp::TcStats();

@@ -434,3 +434,36 @@ def test_every_layer_of_both_networks_plans_at_the_benchmark_frame_sizes(emu, mo
                 out = net(torch.zeros(shape))
             assert out.shape == shape
         net.__dict__.pop("_workspace", None)
+
+
+# ------------------------------------------------------------------------------------------ the model has teeth
+_WAITS = {"mma_full": "                mbar_wait(fb, phase, err, 103);",                                   # MMA issuer: stage loaded?
+          "epilogue_tfull": "            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);",     # epilogue: accumulator complete?
+          "producer_empty": "                mbar_wait(eb, phase ^ 1, err, 101);"}                          # producer: stage free again?
+
+
+@pytest.mark.parametrize("which", sorted(_WAITS))
+def test_model_catches_a_removed_wait(libs, tmp_path, which):
+    """TMA loads, MMAs and commits are asynchronous in the model (queued at issue, executed as late as possible, TMA destinations
+    poisoned meanwhile): conv_tc.cu with one of its pipeline waits deleted must NOT pass — it aborts inside the model (work in
+    flight at CTA exit, a barrier arrived beyond its count) or computes garbage.  (The intact source passes the same layer in every test above.)"""
+    import subprocess
+    import sys
+    src = open(os.path.join(CSRC, "conv_tc.cu")).read()
+    assert src.count(_WAITS[which]) == 1
+    src = src.replace(_WAITS[which], "/* wait removed */")
+    for inc in ("abi_common.h", "tc_common.cuh", "layout_kernels.cuh"):
+        src = src.replace(f'#include "{inc}"', f'#include "{os.path.join(CSRC, inc)}"')
+    src = src.replace('#include "../../include/pnnp_b200.h"', f'#include "{os.path.join(ROOT, "include", "pnnp_b200.h")}"')
+    (tmp_path / "conv_tc_mut.cu").write_text(src)
+    tu = open(os.path.join(EMUL, "tc_kernels_host.cpp")).read()
+    tu = tu.replace('#include "../../pnnp_b200/csrc/conv_tc.cu"', f'#include "{tmp_path / "conv_tc_mut.cu"}"')
+    tu = tu.replace('#include "../../pnnp_b200/csrc/wgrad_nhwc_tc.cu"', f'#include "{os.path.join(CSRC, "wgrad_nhwc_tc.cu")}"')
+    (tmp_path / "tu.cpp").write_text(tu)
+    so = str(tmp_path / "libmut.so")
+    subprocess.run(["g++", "-O0", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-I", EMUL, "-shared", "-fPIC", "-o", so,
+                    str(tmp_path / "tu.cpp")], check=True)
+    r = subprocess.run([sys.executable, os.path.join(EMUL, "tc_mutation_probe.py"), so], capture_output=True, text=True, timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")]
+    caught = r.returncode != 0 or not line or not (float(line[0].split()[1]) < 0.05) or int(line[0].split()[2]) != 0
+    assert caught, f"{which}: the build without this wait passed: {line}"
