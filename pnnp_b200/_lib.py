@@ -125,6 +125,11 @@ def launch_count() -> int:
     return int(lib().pnnp_launch_count())
 
 
+def require_cuda_device(device, what="this operation"):
+    if torch.device(device).type != "cuda":
+        raise RuntimeError(f"pnnp_b200: {what} needs a CUDA device (no CPU fallback)")
+
+
 def require_cuda(t, name="tensor"):
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
         raise RuntimeError(f"pnnp_b200: {name} must be a CUDA tensor (no CPU fallback)")

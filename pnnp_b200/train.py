@@ -82,8 +82,7 @@ class UNetTrainStep:
     def __init__(self, net: UNetSeeInDark, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
         self.net = net
         self.device = next(net.parameters()).device
-        if self.device.type != "cuda":
-            raise RuntimeError("pnnp_b200: the training step needs a CUDA device (no CPU fallback)")
+        _lib.require_cuda_device(self.device, "the training step")
         self.betas, self.eps, self.t = betas, eps, 0
         # learning rate and step count in device memory: the whole step is replayed as one CUDA graph (see step())
         self.adam_state = torch.tensor([float(lr), 0.0], dtype=torch.float32, device=self.device)

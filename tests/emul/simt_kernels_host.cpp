@@ -92,6 +92,13 @@ int emul_adam(float* p, const float* g, float* m, float* v, size_t total, float 
     return 0;
 }
 
+// pnnp_adam_step_dev as the training step calls it: learning rate and step count live in `state` (advanced by the tick kernel)
+int emul_adam_dev(float* p, const float* g, float* m, float* v, size_t total, float* state, float b1, float b2, float eps, float gscale, int blocks) {
+    adam_tick_kernel(state);
+    SIMT_LAUNCH(blocks, 256, (adam_dev_kernel(p, g, m, v, total, state, b1, b2, eps, gscale)));
+    return 0;
+}
+
 // ---- eval epilogue (csrc/eval_kernels.cuh), as pnnp_eval_epilogue launches it; dots_blocks is free
 int emul_eval_epilogue(const float* dn, const float* hr, int n, int c, int h, int w, float scale, int brightness_correct, double* sums,
                        int v2, int dots_blocks) {

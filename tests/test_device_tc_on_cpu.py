@@ -53,16 +53,50 @@ def libs():
     tc = _build("libtc_kernels_host.so", "tc_kernels_host.cpp",
                 shim + [os.path.join(CSRC, f) for f in ("conv_tc.cu", "tc_common.cuh", "abi_common.h")] + [os.path.join(ROOT, "include", "pnnp_b200.h")])
     tc.emul_tc_last_error.restype = C.c_char_p
-    k = _build("libkernels_host.so", "kernels_host.cpp", shim[:1] + [os.path.join(CSRC, "layout_kernels.cuh")])
-    return tc, k
+    k = _build("libkernels_host.so", "kernels_host.cpp", shim[:1] + [os.path.join(CSRC, f) for f in ("layout_kernels.cuh", "copy_kernels.cuh")])
+    sk = _build("libsimt_kernels_host.so", "simt_kernels_host.cpp", shim[:2] + [os.path.join(CSRC, f) for f in ("train_kernels.cuh", "actbwd_core.cuh", "noise_kernels.cuh", "eval_kernels.cuh", "hbr_kernels.cuh")])
+    return tc, k, sk
 
 
 class _EmulatedLibrary:
     """Stands where ctypes' libpnnp_b200.so stands in the product's host code; every ABI entry the forward uses goes to the
     host-compiled device source."""
 
-    def __init__(self, tc, k):
-        self.tc, self.k = tc, k
+    def __init__(self, tc, k, sk=None):
+        self.tc, self.k, self.sk, self.launches = tc, k, sk, 0
+
+    # ---- training step (csrc/train_kernels.cuh, copy_kernels.cuh, wgrad_nhwc_tc.cu)
+    def pnnp_strided_copy_batch(self, tab, n, blocks, stream):
+        return self.k.emul_strided_copy_batch(C.c_void_p(tab), n, int(os.environ.get("PNNP_COPY_V2", "0") == "1"), 3, 256)
+
+    def pnnp_act_bwd_bias(self, g, out, dbias, pixels, c, act, stream):
+        return self.sk.emul_act_bwd_bias(C.c_void_p(g), C.c_void_p(out), C.c_void_p(dbias), C.c_size_t(pixels), c, act, 2)
+
+    def pnnp_wgrad_nhwc(self, mode, g, co, co_stride, x, ci, ci_stride, n, h, w, dw, ci_off, ci_total, co_pad, stream):
+        return self.tc.emul_wgrad_nhwc(mode, C.c_void_p(g), co, co_stride, C.c_void_p(x), ci, ci_stride, n, h, w, C.c_void_p(dw), ci_off, ci_total, co_pad)
+
+    def pnnp_head_bwd(self, gpred, act, w, gact, dw, db, dbp, n, h, wd, cin, co, act_kind, stream):
+        return self.sk.emul_head_bwd(C.c_void_p(gpred), C.c_void_p(act), C.c_void_p(w), C.c_void_p(gact), C.c_void_p(dw), C.c_void_p(db),
+                                     C.c_void_p(dbp), n, h, wd, cin, co, act_kind, 2)
+
+    def pnnp_maxpool_bwd(self, gp, cfull, gskip, gc, n, h, w, c, act, stream):
+        return self.sk.emul_maxpool_bwd(C.c_void_p(gp), C.c_void_p(cfull), C.c_void_p(gskip), C.c_void_p(gc), n, h, w, c, act, 2)
+
+    def pnnp_l1_loss(self, pred, hr, gpred, total, loss_sum, stream):
+        return self.sk.emul_l1_loss(C.c_void_p(pred), C.c_void_p(hr), C.c_void_p(gpred), C.c_size_t(total), C.c_void_p(loss_sum), 2)
+
+    def pnnp_adam_step_dev(self, p, g, m, v, total, state, b1, b2, eps, gscale, stream):
+        return self.sk.emul_adam_dev(C.c_void_p(p), C.c_void_p(g), C.c_void_p(m), C.c_void_p(v), C.c_size_t(total), C.c_void_p(state),
+                                     C.c_float(b1), C.c_float(b2), C.c_float(eps), C.c_float(gscale), 3)
+
+    def pnnp_wgrad_nhwc_pipeline_error(self):
+        return self.tc.emul_wgrad_pipeline_error()
+
+    def pnnp_launch_count(self):
+        return self.launches
+
+    def pnnp_count_graph_launches(self, n):
+        self.launches += n
 
     def pnnp_conv2d_tc_ex(self, desc, stream):
         return self.tc.emul_conv2d_tc_ex(C.byref(desc))
@@ -87,11 +121,12 @@ def emu(monkeypatch, libs):
     monkeypatch.setattr(_lib, "lib", lambda: lib)
     monkeypatch.setattr(_lib, "stream_ptr", lambda device=None: None)
     monkeypatch.setattr(_lib, "require_cuda", lambda t, name="tensor": None)
+    monkeypatch.setattr(_lib, "require_cuda_device", lambda device, what="": None)
     monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
     for k in _VARIANT_ENV:
         monkeypatch.delenv(k, raising=False)
     yield lib
-    assert lib.pnnp_conv_pipeline_error() == 0, "a pipeline wait of the emulated kernel could never complete"
+    assert lib.pnnp_conv_pipeline_error() == 0 and lib.pnnp_wgrad_nhwc_pipeline_error() == 0, "a pipeline wait of an emulated kernel could never complete"
 
 
 def _bf(t):
@@ -409,6 +444,50 @@ def test_data_gradient_modes_of_the_conv_kernel_match_autograd(emu):
         gx = torch.empty((2, h, w, ci), dtype=torch.bfloat16)
         archs._conv(_lib.CONV2S2, _nhwc(go), train._pack_conv_weight(wt.detach()), None, gx, ci, _lib.ACT_NONE)
         assert _rel(_nchw(gx), x.grad) < 6e-3                          # bf16 output rounding
+
+
+# ------------------------------------------------------------------------------------------ the whole training step
+def test_whole_training_step_vs_fp32_autograd_and_reference_loop(emu, monkeypatch):
+    """T1 end to end on the CPU models — pnnp_b200.train.UNetTrainStep's own host code (weight packing tables, forward, L1, explicit
+    backward through dgrad convs / wgrad / head / pool / activation kernels, gradient re-layout, Adam) with every launch emulated:
+    (1) the gradients of one step against fp32 autograd driven by the SAME d loss / d pred; (2) three Adam steps against the
+    reference loop (losses/base_loss.py:92-103 + torch.optim.Adam, fp32).  Bounds as in the `-m gpu` tests."""
+    import test_gpu_train as G
+    from pnnp_b200 import train
+    monkeypatch.setenv("PNNP_TRAIN_GRAPH", "0")
+    torch.manual_seed(11)
+    net = P.UNetSeeInDark({"in_nc": 4, "out_nc": 4, "nf": 16, "nframes": 1, "res": False})
+    P.initialize_weights(net)
+    net.conv10_1.bias.data.fill_(0.05)                                  # all four outputs start inside the clamp
+    g = torch.Generator().manual_seed(5)
+    hr = torch.rand((2, 4, 32, 32), generator=g) ** 2
+    lr_in = hr + 0.05 * torch.randn((2, 4, 32, 32), generator=g)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    ts = train.UNetTrainStep(net, lr=1e-3)
+    pred, saved = ts.forward(lr_in)
+    gp = torch.empty_like(pred)
+    assert emu.pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gp.data_ptr(), pred.numel(), ts.loss_sum.data_ptr(), None) == 0
+    ts.backward(gp, saved)
+    p16 = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    G._unet_forward_bf16_storage(lr_in, p16).backward(gp)               # fp32 autograd through the bf16-storage network
+    ref_loss = F.l1_loss(O.unet_forward(lr_in, sd).clamp(0, 1), hr).item()
+    assert abs(ts.loss_sum.item() / pred.numel() - ref_loss) < 2e-3 * max(1.0, ref_loss)
+    bad = {}
+    for name in sd:
+        got, want = ts._grad_view(name), p16[name].grad
+        rel, cos = G._rel(got, want), G._cos(got, want)
+        if not (cos > 0.995 and rel < 0.10):
+            bad[name] = (rel, cos)
+    assert not bad, bad
+    ref_losses, _, _ = G._reference_step(sd, lr_in, hr, steps=3, lr=1e-3)
+    net2 = P.UNetSeeInDark({"in_nc": 4, "out_nc": 4, "nf": 16, "nframes": 1, "res": False})
+    net2.load_state_dict(sd)
+    ts2 = train.UNetTrainStep(net2, lr=1e-3)
+    losses = [ts2.step(lr_in, hr, grad_allreduce=False).item() for _ in range(3)]
+    assert np.allclose(losses, ref_losses, rtol=3e-2, atol=2e-3), (losses, ref_losses)
+    moved = max((v - sd[k]).abs().max().item() for k, v in net2.state_dict().items())
+    assert 1.5e-3 < moved < 4.5e-3                                      # ~ steps * lr, as Adam's first steps do
+    assert ts2.t == 3 and abs(ts2.adam_state[1].item() - 3.0) < 1e-6
 
 
 # ------------------------------------------------------------------------------------------ launcher dry run at the real frame sizes
