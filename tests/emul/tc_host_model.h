@@ -15,8 +15,8 @@
 // The model is calibrated by the kernels that are parity-green on a B200: under it the default instantiations reproduce torch's
 // convolutions; the same semantics then check the opt-in instantiations before they are given GPU time.  TMA loads, MMAs and
 // commits are asynchronous here too — queued at issue, executed as late as possible, TMA destinations poisoned meanwhile — so a
-// consumer that does not wait for the announcing barrier is caught.  Not modelled: timing, reordering between the two agents, and
-// alignment faults beyond the checks below.
+// consumer that does not wait for the announcing barrier is caught; PNNP_EMUL_ASYNC picks which agent lags (fifo / tma_first /
+// tc_first).  Not modelled: timing, and alignment faults beyond the checks below.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -100,17 +100,30 @@ static TcStats g_tc_stats;
 // Asynchronous agents (TMA unit, tensor pipe): an operation is queued at issue and EXECUTED AS LATE AS POSSIBLE — one queued operation
 // per failed mbarrier poll, in issue order — so device code that consumes a result without waiting for the barrier that announces it
 // (shared-memory stage, accumulator, reused slot) reads poison / stale data here instead of passing by luck of issue order.
-static std::deque<std::function<void()>> g_async;
+static std::deque<std::function<void()>> g_async_tma, g_async_tc;     // per agent, each in issue order (commits ride the tensor-pipe queue)
+static std::deque<int> g_async_order;                                  // issue order across both agents: 0 = TMA, 1 = tensor pipe
 static unsigned long g_async_work = 0;                      // queued TMA loads / MMAs (commits are not counted)
 static unsigned long g_trailing_commits = 0;                // commits that were still queued when their CTA exited (no work before them)
+// Which queued operation happens next when a fibre's barrier poll fails — PNNP_EMUL_ASYNC = fifo (default: issue order across both
+// agents), tma_first (the TMA unit runs ahead, the tensor pipe lags as far as the barriers allow) or tc_first (the reverse).
+static inline int async_policy() {
+    const char* e = std::getenv("PNNP_EMUL_ASYNC");          // read per operation: a test switches it between launches
+    return !e ? 0 : (!std::strcmp(e, "tma_first") ? 1 : (!std::strcmp(e, "tc_first") ? 2 : 0));
+}
+static inline void async_push(int agent, std::function<void()> op) { (agent ? g_async_tc : g_async_tma).push_back(std::move(op)); g_async_order.push_back(agent); }
 static inline bool async_run_one() {
-    if (g_async.empty()) return false;
-    std::function<void()> op = std::move(g_async.front());
-    g_async.pop_front();
+    if (g_async_order.empty()) return false;
+    int agent = g_async_order.front();
+    const int pol = async_policy();
+    if (pol == 1 && !g_async_tma.empty()) agent = 0;
+    if (pol == 2 && !g_async_tc.empty()) agent = 1;
+    for (auto it = g_async_order.begin(); it != g_async_order.end(); ++it) if (*it == agent) { g_async_order.erase(it); break; }
+    auto& q = agent ? g_async_tc : g_async_tma;
+    std::function<void()> op = std::move(q.front());
+    q.pop_front();
     op();
     return true;
 }
-
 static inline void tc_model_fail(const char* what) { std::fprintf(stderr, "tc_host_model: %s\n", what); std::abort(); }
 static inline uint8_t* smem_ptr(uint32_t addr, size_t bytes) {
     if (addr < kSmemBase || (size_t)(addr - kSmemBase) + bytes > kSmemBytes) tc_model_fail("shared-memory address out of range");
@@ -163,7 +176,7 @@ static inline void tma_load(uint32_t dst, const CUtensorMap* tm, uint32_t bar, c
     int cc[5];
     for (int d = 0; d < 5; ++d) cc[d] = c[d];
     ++g_async_work;
-    g_async.push_back([=]() {
+    async_push(0, [=]() {
         --g_async_work;
         size_t lin = 0;
         for (uint32_t i4 = 0; i4 < cnt[4]; ++i4) for (uint32_t i3 = 0; i3 < cnt[3]; ++i3) for (uint32_t i2 = 0; i2 < cnt[2]; ++i2)
@@ -208,7 +221,7 @@ static inline void tmem_alloc(uint32_t slot, uint32_t cols) {
     if ((simt::g_cta->cur & 31u) == 0) for (auto& lane : g_tmem) for (auto& w : lane) w = 0x7FC00000u;     // unwritten accumulators read as NaN
 }
 static inline void tmem_dealloc(uint32_t, uint32_t) {}
-static inline void tc_commit(uint32_t bar) { g_async.push_back([=]() { mbar_arrive(bar); }); }     // arrives once every MMA queued before it has executed
+static inline void tc_commit(uint32_t bar) { async_push(1, [=]() { mbar_arrive(bar); }); }     // arrives once every MMA queued before it has executed
 static inline float bf16_at(uint32_t addr) { uint16_t h; std::memcpy(&h, smem_ptr(addr, 2), 2); return __uint_as_float((uint32_t)h << 16); }
 static inline void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     ++g_tc_stats.mma;
@@ -244,7 +257,7 @@ static inline void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, 
     const uint32_t col0 = d_tmem & 0xFFFFu;
     if ((d_tmem >> 16) != 0 || col0 + (uint32_t)N > 512) tc_model_fail("tcgen05.mma: accumulator outside TMEM");
     ++g_async_work;
-    g_async.push_back([=]() {
+    async_push(1, [=]() {
         --g_async_work;
         static float a[128][16], b[256][16];
         for (int m = 0; m < M; ++m) for (int k = 0; k < 16; ++k) a[m][k] = bf16_at(addr(oa, m, k));
@@ -287,7 +300,7 @@ static inline void emul_launch_1d(int grid, int threads, const std::function<voi
         blockIdx.x = (unsigned)b; g_stalled_polls = 0;
         simt::run_cta((unsigned)threads, body);
         if (g_async_work) tc_model_fail("CTA exited with TMA loads / MMAs still in flight (nobody waited for them)");
-        while (!g_async.empty()) { ++g_trailing_commits; async_run_one(); }    // a commit with nothing before it: completes at once on the device
+        while (!g_async_order.empty()) { ++g_trailing_commits; async_run_one(); }    // a commit with nothing before it: completes at once on the device
     }
 }
 

@@ -515,6 +515,43 @@ def test_every_layer_of_both_networks_plans_at_the_benchmark_frame_sizes(emu, mo
         net.__dict__.pop("_workspace", None)
 
 
+@pytest.mark.parametrize("policy", ["tma_first", "tc_first"])
+def test_results_do_not_depend_on_which_asynchronous_agent_lags(emu, libs, monkeypatch, policy):
+    """The model's TMA unit and tensor pipe each work through their own queue; by default the oldest operation of either happens
+    next.  Here one agent runs ahead and the other lags as far as the barriers allow: a correctly synchronised kernel gives the
+    same bits — a default 3x3 layer with a deep K loop, the super-tile + packed-pair variant, a transposed conv and a weight
+    gradient."""
+    g = torch.Generator().manual_seed(3)
+    x = _nhwc(torch.randn((2, 128, 24, 40), generator=g))
+    wp = _pack(torch.randn((64, 128, 3, 3), generator=g) / 34)
+    b = torch.randn((64,), generator=g) * 0.1
+    xs = _nhwc(torch.randn((1, 32, 40, 44), generator=g))
+    wpx = _pack(torch.randn((32, 32, 3, 3), generator=g) / 17, "conv3x")
+    xt = _nhwc(torch.randn((1, 64, 8, 24), generator=g))
+    wt = _pack(torch.randn((64, 32, 2, 2), generator=g) / 8, "convT")
+    go, xin = _nhwc(_bf(torch.randn((1, 64, 16, 48), generator=g))), _nhwc(_bf(torch.randn((1, 64, 16, 48), generator=g)))
+
+    def call():
+        out = torch.zeros((2, 24, 40, 64), dtype=torch.bfloat16)
+        archs._conv(_lib.CONV3, x, wp, b, out, 64, _lib.ACT_LEAKY)
+        outs = torch.zeros((1, 40, 44, 32), dtype=torch.bfloat16)
+        pooled = torch.zeros((1, 20, 22, 32), dtype=torch.bfloat16)
+        monkeypatch.setenv("PNNP_CONV_SUPER", "1"); monkeypatch.setenv("PNNP_CONV_F32X2", "1"); monkeypatch.setenv("PNNP_CONV_PDL", "1")
+        archs._conv(_lib.CONV3X, xs, wpx, b[:32].contiguous(), outs, 32, _lib.ACT_LEAKY, pool_out=pooled)
+        for k in ("PNNP_CONV_SUPER", "PNNP_CONV_F32X2", "PNNP_CONV_PDL"):
+            monkeypatch.delenv(k)
+        outt = torch.zeros((1, 16, 48, 32), dtype=torch.bfloat16)
+        archs._conv(_lib.CONVT, xt, wt, b[:32].contiguous(), outt, 32, _lib.ACT_NONE)
+        dw = torch.zeros((9, 64, 64))
+        _wgrad(libs, 0, go, 64, xin, 64, 1, 16, 48, dw, 0, 64)
+        return [_bits(out), _bits(outs), _bits(pooled), _bits(outt), dw]
+    monkeypatch.delenv("PNNP_EMUL_ASYNC", raising=False)
+    want = call()
+    monkeypatch.setenv("PNNP_EMUL_ASYNC", policy)
+    got = call()
+    assert all(torch.equal(a, c) for a, c in zip(got, want))
+
+
 # ------------------------------------------------------------------------------------------ the model has teeth
 _WAITS = {"mma_full": "                mbar_wait(fb, phase, err, 103);",                                   # MMA issuer: stage loaded?
           "epilogue_tfull": "            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);",     # epilogue: accumulator complete?
