@@ -365,8 +365,11 @@ def test_conv_transpose_fast_path_equals_default(emu, monkeypatch, cin, cout, h,
 
 @pytest.mark.parametrize("env", [{"PNNP_CONV_SUPER": 1, "PNNP_CONVT_FAST": 1, "PNNP_IN_V2": 1, "PNNP_CONV_PDL": 1, "PNNP_CONV_F32X2": 1},
                                  {"PNNP_CONV_SUPER": 2, "PNNP_CONVT_FAST": 1, "PNNP_IN_V2": 1, "PNNP_CONV_PDL": 1, "PNNP_CONV_F32X2": 1}])
-def test_all_variants_together_leave_the_unet_forward_unchanged(emu, monkeypatch, env):
-    net = _unet(nf=16, seed=4)
+@pytest.mark.parametrize("cls", ["UNetSeeInDark", "ResUnet"])
+def test_all_variants_together_leave_the_network_forward_unchanged(emu, monkeypatch, env, cls):
+    torch.manual_seed(4)
+    net = getattr(P, cls)({"in_nc": 4, "out_nc": 4, "nf": 16, "nframes": 1, "res": False}).eval()
+    P.initialize_weights(net)
     x = torch.rand((1, 4, 48, 64), generator=torch.Generator().manual_seed(2))
 
     def call():
