@@ -125,6 +125,17 @@ def launch_count() -> int:
     return int(lib().pnnp_launch_count())
 
 
+def cuda_device(index=None, set_current=False):
+    """The CUDA device the product works on: the current one, or `index` (made current when set_current).  No CPU fallback."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("pnnp_b200: no CUDA device (there is no CPU fallback)")
+    if index is None:
+        index = torch.cuda.current_device()
+    elif set_current:
+        torch.cuda.set_device(index)
+    return torch.device("cuda", index)
+
+
 def require_cuda_device(device, what="this operation"):
     if torch.device(device).type != "cuda":
         raise RuntimeError(f"pnnp_b200: {what} needs a CUDA device (no CPU fallback)")

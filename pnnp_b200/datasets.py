@@ -105,7 +105,8 @@ class Raw_Dataset(torch.utils.data.Dataset):
     @staticmethod
     def device():
         """Items are built on the current CUDA device (there is no CPU path)."""
-        return torch.device("cuda", torch.cuda.current_device())
+        from . import _lib
+        return _lib.cuda_device()
 
     def synthetic_raw(self, idx, device):
         g = torch.Generator(device=device).manual_seed(4242 + idx)

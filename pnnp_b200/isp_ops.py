@@ -12,9 +12,7 @@ from . import _lib
 
 
 def _device():
-    if not torch.cuda.is_available():
-        raise RuntimeError("pnnp_b200: no CUDA device (there is no CPU fallback)")
-    return torch.device("cuda", torch.cuda.current_device())
+    return _lib.cuda_device()
 
 
 def raw2bayer(raw, wp=1023, bl=64, norm=True, clip=False, bias=np.array([0, 0, 0, 0])):

@@ -62,11 +62,8 @@ class Base_Trainer():
         self.save_plot = False
         self.dst, self.hyper, self.arch = self.args['dst'], self.args['hyper'], self.args['arch']
         self.rank, self.world_size = D.init_from_env()
-        if not torch.cuda.is_available():
-            raise RuntimeError("pnnp_b200 trainer: no CUDA device (there is no CPU fallback)")
         index = int(os.environ.get("LOCAL_RANK", self.parser.gpu.split(",")[0] if self.world_size == 1 else 0))
-        torch.cuda.set_device(index)
-        self.device = torch.device("cuda", index)
+        self.device = _lib.cuda_device(index, set_current=True)         # raises without a CUDA device: there is no CPU fallback
         self.model_name, self.fast_ckpt = self.args['model_name'], self.args['fast_ckpt']
         self.model_dir = self.args['checkpoint']
         self.sample_dir = os.path.join(self.args['result_dir'], f"samples-{self.model_name}")

@@ -89,6 +89,27 @@ class _EmulatedLibrary:
         return self.sk.emul_adam_dev(C.c_void_p(p), C.c_void_p(g), C.c_void_p(m), C.c_void_p(v), C.c_size_t(total), C.c_void_p(state),
                                      C.c_float(b1), C.c_float(b2), C.c_float(eps), C.c_float(gscale), 3)
 
+    # ---- data path (csrc/pack_kernels.cuh, crop_kernels.cuh, noise_kernels.cuh, eval_kernels.cuh), launcher choices mirrored
+    def pnnp_pack_norm_u16(self, raw, out, n, H, W, wp, black4, norm, clip, stream):
+        return self.k.emul_pack_norm_u16(C.c_void_p(raw), C.c_void_p(out), n, H, W, C.c_double(wp), black4, norm, clip, int((W // 2) % 4 == 0), 3, 128)
+
+    def pnnp_pack_norm_f32(self, raw, out, n, H, W, wp, black4, norm, clip, stream):
+        return self.k.emul_pack_norm_f32(C.c_void_p(raw), C.c_void_p(out), n, H, W, C.c_double(wp), black4, norm, clip, int((W // 2) % 4 == 0), 3, 128)
+
+    def pnnp_crop_aug(self, frame, out, c, h, w, patch, n, hs, ws, mode, stream):
+        return self.k.emul_crop_aug(C.c_void_p(frame), C.c_void_p(out), c, h, w, patch, n, hs, ws, mode, 3, 128)
+
+    def pnnp_noise_synth(self, clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, seed, offset, crop_id0, stream):
+        vec = w % 4 == 0 and (crop_id0 * c * h * w) % 4 == 0
+        fast = vec and chain == _lib.CHAIN_NUMPY and (bits & _lib.CODE_UNIFORM_F64) and (bits & 0x3F) == 0x0F and not ori and not clip
+        return self.sk.emul_noise_synth(C.c_void_p(clean), C.c_void_p(noisy), C.c_void_p(table), n, c, h, w, C.c_uint32(bits), chain, ori, clip,
+                                        C.c_float(lo), C.c_float(hi), C.c_uint64(seed), C.c_uint64(offset), C.c_uint64(crop_id0),
+                                        2 if fast else (0 if vec else 1), 0, None, None, None, None, 2)
+
+    def pnnp_eval_epilogue(self, dn, hr, n, c, h, w, scale, correct, sums, stream):
+        return self.sk.emul_eval_epilogue(C.c_void_p(dn), C.c_void_p(hr), n, c, h, w, C.c_float(scale), correct, C.c_void_p(sums),
+                                          int(os.environ.get("PNNP_SSIM_V2", "0") == "1"), 2)
+
     def pnnp_wgrad_nhwc_pipeline_error(self):
         return self.tc.emul_wgrad_pipeline_error()
 
@@ -122,6 +143,7 @@ def emu(monkeypatch, libs):
     monkeypatch.setattr(_lib, "stream_ptr", lambda device=None: None)
     monkeypatch.setattr(_lib, "require_cuda", lambda t, name="tensor": None)
     monkeypatch.setattr(_lib, "require_cuda_device", lambda device, what="": None)
+    monkeypatch.setattr(_lib, "cuda_device", lambda index=None, set_current=False: torch.device("cpu"))
     monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
     for k in _VARIANT_ENV:
         monkeypatch.delenv(k, raising=False)
@@ -491,6 +513,41 @@ def test_whole_training_step_vs_fp32_autograd_and_reference_loop(emu, monkeypatc
     moved = max((v - sd[k]).abs().max().item() for k, v in net2.state_dict().items())
     assert 1.5e-3 < moved < 4.5e-3                                      # ~ steps * lr, as Adam's first steps do
     assert ts2.t == 3 and abs(ts2.adam_state[1].item() - 3.0) < 1e-6
+
+
+def test_trainer_entry_point_trains_and_evaluates_on_the_cpu_models(emu, monkeypatch, tmp_path):
+    """`trainer_SID.py --mode train` (trainer_SID.py:74-180) end to end with EVERY kernel emulated from its device source: Raw_Dataset
+    items (pack + normalise -> crop + augmentation -> per-crop sample_params -> fused noise synthesis), the explicit training step,
+    checkpoints with the reference's state_dict keys, then the ELD-shaped eval sweep (synthesis at the frame's ratio -> UNet forward
+    -> PSNR / SSIM partial sums) and the reference's log format.  Tiny shapes: this checks the plumbing, not the learning curve."""
+    import re
+    import yaml
+    from pnnp_b200 import trainer as T
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("PNNP_TRAIN_GRAPH", "0")
+    cfg = yaml.load(open(os.path.join(ROOT, "runfiles/SonyA7S2/PNNP.yml")), Loader=yaml.FullLoader)
+    for k in ("dst", "dst_train", "dst_eval", "dst_test"):
+        cfg[k].update(H=64, W=64, synthetic_frames=1, patch_size=32)
+        if "iso_list" in cfg[k]:
+            cfg[k]["iso_list"] = cfg[k]["iso_list"][:1]
+    cfg["dst_train"].update(crop_per_image=2, synthetic_frames=2)
+    cfg["arch"]["nf"] = 16
+    cfg["hyper"].update(stop_epoch=2, save_freq=1, plot_freq=2, batch_size=2, learning_rate=1e-3, lr_scheduler="MultiStep", step_size=100)
+    cfg["fast_ckpt"], cfg["checkpoint"] = str(tmp_path / "ckpt"), str(tmp_path / "saved")
+    (tmp_path / "run.yml").write_text(yaml.dump(cfg))
+    np.random.seed(5)
+    torch.manual_seed(5)
+    tr = T.SID_Trainer(["-f", str(tmp_path / "run.yml"), "--mode", "train"])
+    assert tr.device.type == "cpu"                                       # the emulated "device"
+    step = tr.train()
+    assert step.t == 2
+    text = open(tmp_path / "logs" / f"log_{cfg['model_name']}.log").read()
+    l1 = [float(x) for x in re.findall(r"L1=(\d+\.\d+)", text)]
+    assert len(l1) == 2 and all(0.0 < v < 1.0 for v in l1), text
+    assert re.search(r"Epoch 2: PSNR=\d+\.\d\d\npsnrs_lr=\d+\.\d\d, psnrs_dn=\d+\.\d\d\nssims_lr=-?\d\.\d{4}, ssims_dn=-?\d\.\d{4}", text), text
+    sd = torch.load(os.path.join(cfg["fast_ckpt"], f"{cfg['model_name']}_last_model.pth"))
+    assert "conv1_1.weight" in sd and "upv6.weight" in sd and len(sd) == 46
+    assert os.path.exists(os.path.join(cfg["checkpoint"], f"{cfg['model_name']}_e0000.pth"))
 
 
 # ------------------------------------------------------------------------------------------ launcher dry run at the real frame sizes
