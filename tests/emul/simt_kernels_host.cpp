@@ -46,6 +46,17 @@ int emul_noise_synth(const float* clean, float* noisy, const pnnp_noise_params* 
     return 0;
 }
 
+// replay kernel (pnnp_noise_synth_replay): the tails on caller-supplied draws
+int emul_noise_replay(const float* clean, float* noisy, const pnnp_noise_params* table, int n, int c, int h, int w, uint32_t code, int chain,
+                      int ori, int clip, float post_lo, float post_hi, const float* d_shot, const float* d_read, const float* d_rowz,
+                      const double* d_q, int blocks) {
+    SynthArgs a{clean, noisy, table, n, c, h, w, code, ori, clip, post_lo, post_hi, 0, 0, 0, PhiloxKeys{},
+                const_cast<float*>(d_shot), const_cast<float*>(d_read), const_cast<float*>(d_rowz), const_cast<double*>(d_q)};
+    if (chain == PNNP_CHAIN_NUMPY) SIMT_LAUNCH(blocks, 256, (noise_replay_kernel<PNNP_CHAIN_NUMPY>(a)));
+    else SIMT_LAUNCH(blocks, 256, (noise_replay_kernel<PNNP_CHAIN_TORCH>(a)));
+    return 0;
+}
+
 // ---- training-step helpers (csrc/train_kernels.cuh); `blocks` is free wherever the launcher's choice is not part of the contract
 int emul_l1_loss(const float* pred, const float* hr, float* gpred, size_t total, double* loss_sum, int blocks) {
     *loss_sum = 0.0;

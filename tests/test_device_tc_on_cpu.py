@@ -106,6 +106,10 @@ class _EmulatedLibrary:
                                         C.c_float(lo), C.c_float(hi), C.c_uint64(seed), C.c_uint64(offset), C.c_uint64(crop_id0),
                                         2 if fast else (0 if vec else 1), 0, None, None, None, None, 2)
 
+    def pnnp_noise_synth_replay(self, clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, shot, read, rowz, q, stream):
+        return self.sk.emul_noise_replay(C.c_void_p(clean), C.c_void_p(noisy), C.c_void_p(table), n, c, h, w, C.c_uint32(bits), chain, ori, clip,
+                                         C.c_float(lo), C.c_float(hi), C.c_void_p(shot), C.c_void_p(read), C.c_void_p(rowz), C.c_void_p(q), 3)
+
     def pnnp_eval_epilogue(self, dn, hr, n, c, h, w, scale, correct, sums, stream):
         return self.sk.emul_eval_epilogue(C.c_void_p(dn), C.c_void_p(hr), n, c, h, w, C.c_float(scale), correct, C.c_void_p(sums),
                                           int(os.environ.get("PNNP_SSIM_V2", "0") == "1"), 2)
@@ -548,6 +552,23 @@ def test_trainer_entry_point_trains_and_evaluates_on_the_cpu_models(emu, monkeyp
     sd = torch.load(os.path.join(cfg["fast_ckpt"], f"{cfg['model_name']}_last_model.pth"))
     assert "conv1_1.weight" in sd and "upv6.weight" in sd and len(sd) == 46
     assert os.path.exists(os.path.join(cfg["checkpoint"], f"{cfg['model_name']}_e0000.pth"))
+
+
+def test_smoke_entry_runs_on_the_cpu_models(emu, monkeypatch, capsys):
+    """__graft_entry__.smoke() — the function the driver runs on a B200 before the bench — line by line with every launch emulated:
+    pack bit-exact, replay bit-exact, Philox synthesis, UNet forward vs the fp32 oracle, one training step vs the oracle's L1."""
+    import sys
+    monkeypatch.setenv("PNNP_TRAIN_GRAPH", "0")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.syspath_prepend(ROOT)
+    import __graft_entry__ as G
+    G.smoke()
+    assert "smoke ok" in capsys.readouterr().out
 
 
 # ------------------------------------------------------------------------------------------ launcher dry run at the real frame sizes
