@@ -100,6 +100,9 @@ class _EmulatedLibrary:
         return self.k.emul_crop_aug(C.c_void_p(frame), C.c_void_p(out), c, h, w, patch, n, hs, ws, mode, 3, 128)
 
     def pnnp_noise_synth(self, clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, seed, offset, crop_id0, stream):
+        if chain == _lib.CHAIN_TORCH and (not bits & _lib.CODE_P or (bits & _lib.CODE_G and not bits & _lib.CODE_B) or bits & _lib.CODE_D):
+            return 1                                  # noise_synth.cu check_common: the reference's own failures on the float32 route
+        self.launches += 1
         vec = w % 4 == 0 and (crop_id0 * c * h * w) % 4 == 0
         fast = vec and chain == _lib.CHAIN_NUMPY and (bits & _lib.CODE_UNIFORM_F64) and (bits & 0x3F) == 0x0F and not ori and not clip
         return self.sk.emul_noise_synth(C.c_void_p(clean), C.c_void_p(noisy), C.c_void_p(table), n, c, h, w, C.c_uint32(bits), chain, ori, clip,
@@ -124,7 +127,12 @@ class _EmulatedLibrary:
         self.launches += n
 
     def pnnp_conv2d_tc_ex(self, desc, stream):
+        self.launches += 1
         return self.tc.emul_conv2d_tc_ex(C.byref(desc))
+
+    def pnnp_wb_gains(self, data, n, c, h, w, rgb_gain, kind, gain, stream):
+        self.launches += 1
+        return self.k.emul_wb_gains(C.c_void_p(data), n, c, h, w, C.c_float(rgb_gain), kind, gain, 3, 128)
 
     def pnnp_nchw_to_nhwc16(self, src, dst, n, c, h, w, scale, stream):
         v2 = int(os.environ.get("PNNP_IN_V2", "0") == "1" and (h * w) % 4 == 0)
