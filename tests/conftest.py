@@ -11,6 +11,23 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))   # tests are allowed to import
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# PNNP_GPU_TESTS_ON_CPU_MODELS=1: rehearse `-m gpu` test files without a GPU — every kernel launch goes to the host-compiled device
+# source on the CPU models of tests/emul/ (SIMT emulator + tensor-core model), "cuda" means the host (see
+# tests/test_gpu_tests_on_cpu_models.py).  Slow for the full-size cases; meant for picking files / -k expressions.
+ON_CPU_MODELS = os.environ.get("PNNP_GPU_TESTS_ON_CPU_MODELS") == "1"
+
+
+@pytest.fixture(autouse=True)
+def _gpu_tests_on_cpu_models(request):
+    if ON_CPU_MODELS and "gpu" in request.keywords:
+        request.getfixturevalue("cuda_is_the_host")
+    yield
+
+
+if ON_CPU_MODELS:
+    from test_gpu_tests_on_cpu_models import cuda_is_the_host, libs  # noqa: E402,F401
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
@@ -28,7 +45,7 @@ def pytest_collection_modifyitems(config, items):
             return 2                      # rows added after round 1's GPU budget was spent: not yet run on a B200
         return int("test_gpu_train.py" in it.nodeid or "train_mode" in it.nodeid)
     items.sort(key=late)
-    if torch.cuda.is_available():
+    if torch.cuda.is_available() or ON_CPU_MODELS:
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:

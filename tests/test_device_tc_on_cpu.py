@@ -100,14 +100,56 @@ class _EmulatedLibrary:
         return self.k.emul_crop_aug(C.c_void_p(frame), C.c_void_p(out), c, h, w, patch, n, hs, ws, mode, 3, 128)
 
     def pnnp_noise_synth(self, clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, seed, offset, crop_id0, stream):
+        return self._synth(clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, seed, offset, crop_id0, 0, None, None, None, None)
+
+    def _synth(self, clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, seed, offset, crop_id0, debug, shot, read, rowz, q):
+        if n <= 0 or c <= 0 or h <= 0 or w <= 0 or not clean or not noisy or not table:
+            return 1
         if chain == _lib.CHAIN_TORCH and (not bits & _lib.CODE_P or (bits & _lib.CODE_G and not bits & _lib.CODE_B) or bits & _lib.CODE_D):
             return 1                                  # noise_synth.cu check_common: the reference's own failures on the float32 route
+        if bits & _lib.CODE_D and c > 4:
+            return 1
         self.launches += 1
-        vec = w % 4 == 0 and (crop_id0 * c * h * w) % 4 == 0
+        vec = w % 4 == 0 and (crop_id0 * c * h * w) % 4 == 0 and clean % 16 == 0 and noisy % 16 == 0
         fast = vec and chain == _lib.CHAIN_NUMPY and (bits & _lib.CODE_UNIFORM_F64) and (bits & 0x3F) == 0x0F and not ori and not clip
         return self.sk.emul_noise_synth(C.c_void_p(clean), C.c_void_p(noisy), C.c_void_p(table), n, c, h, w, C.c_uint32(bits), chain, ori, clip,
                                         C.c_float(lo), C.c_float(hi), C.c_uint64(seed), C.c_uint64(offset), C.c_uint64(crop_id0),
-                                        2 if fast else (0 if vec else 1), 0, None, None, None, None, 2)
+                                        2 if fast else (0 if vec else 1), debug, C.c_void_p(shot), C.c_void_p(read), C.c_void_p(rowz), C.c_void_p(q), 2)
+
+    def pnnp_abi_version(self):
+        return 1
+
+    def pnnp_unpack_quant(self, packed, raw, n, h, w, wp, bl, stream):
+        return self.k.emul_unpack_quant(C.c_void_p(packed), C.c_void_p(raw), n, h, w, C.c_float(wp), C.c_float(bl), int(w % 4 == 0), 3, 128)
+
+    def pnnp_pack_norm_dark_u16(self, raw, dark, dark_f64, out, n, H, W, wp, black4, norm, clip, add_mean, use_mean, add_bias, use_bias, stream):
+        return self.k.emul_pack_norm_dark_u16(C.c_void_p(raw), C.c_void_p(dark), dark_f64, C.c_void_p(out), n, H, W, C.c_double(wp), black4, norm, clip,
+                                              C.c_double(add_mean), use_mean, C.c_double(add_bias), use_bias, 3, 128)
+
+    def pnnp_eval_crop(self, frame, tiles, c, h, w, patch, base, stream):
+        return self.k.emul_eval_crop(C.c_void_p(frame), C.c_void_p(tiles), c, h, w, patch, base, 3, 128)
+
+    def pnnp_eval_merge(self, tiles, frame, c, h, w, patch, base, stream):
+        return self.k.emul_eval_merge(C.c_void_p(tiles), C.c_void_p(frame), c, h, w, patch, base, 3, 128)
+
+    def pnnp_hbr_map(self, src, dst, total, cdf, rng_, low, high, scale_in, norm, span, bl, tukey, lam, loc, scale, rand, seed, offset, index0, rand_out, stream):
+        return self.sk.emul_hbr_map(C.c_void_p(src), C.c_void_p(dst), C.c_size_t(total), C.c_void_p(cdf), C.c_void_p(rng_), low, high, scale_in, norm,
+                                    C.c_float(span), C.c_float(bl), tukey, C.c_double(lam), C.c_double(loc), C.c_double(scale), C.c_void_p(rand),
+                                    C.c_uint64(seed), C.c_uint64(offset), C.c_uint64(index0), C.c_void_p(rand_out), 3)
+
+    def pnnp_adam_step(self, p, g, m, v, total, lr, b1, b2, eps, step, gscale, stream):
+        return self.sk.emul_adam(C.c_void_p(p), C.c_void_p(g), C.c_void_p(m), C.c_void_p(v), C.c_size_t(total), C.c_float(lr), C.c_float(b1),
+                                 C.c_float(b2), C.c_float(eps), step, C.c_float(gscale), 0, 3)
+
+    def pnnp_conv2d_tc(self, mode, in0, cin0, in1, cin1, weight, w_rows, bias, out, cout, cout_stride, n, h, w, act, out_mode, resid, resid_nchw, stream):
+        d = _lib.ConvDesc()
+        d.mode, d.act, d.out_mode, d.n, d.h, d.w = mode, act, out_mode, n, h, w
+        d.in0, d.cin0, d.in1, d.cin1, d.weight, d.w_rows, d.bias = in0, cin0, in1, cin1, weight, w_rows, bias
+        d.out, d.cout, d.cout_stride, d.resid, d.resid_nchw = out, cout, cout_stride, resid, resid_nchw
+        return self.pnnp_conv2d_tc_ex(d, stream)
+
+    def pnnp_noise_synth_debug(self, clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, seed, offset, crop_id0, shot, read, rowz, q, stream):
+        return self._synth(clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, seed, offset, crop_id0, 1, shot, read, rowz, q)
 
     def pnnp_noise_synth_replay(self, clean, noisy, table, n, c, h, w, bits, chain, ori, clip, lo, hi, shot, read, rowz, q, stream):
         return self.sk.emul_noise_replay(C.c_void_p(clean), C.c_void_p(noisy), C.c_void_p(table), n, c, h, w, C.c_uint32(bits), chain, ori, clip,

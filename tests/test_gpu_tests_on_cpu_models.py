@@ -36,6 +36,7 @@ def cuda_is_the_host(monkeypatch, libs):  # noqa: F811
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone())     # a copy, as a host-to-device transfer is
     monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     for name in ("rand", "randn", "zeros", "ones", "empty", "full", "arange", "tensor", "Generator"):
         monkeypatch.setattr(torch, name, _on_host(getattr(torch, name)))
