@@ -21,9 +21,7 @@ def darkshading_raw2bayer(lr_raw, darkshading, wp=16383, bl=512, add_mean=False,
     """lr_raw: H x W (or n x H x W) uint16 sensor frame (NumPy array or CUDA int16/uint16 tensor); darkshading: H x W float32 or
     float64 map (`ds_k * iso + ds_b + BLE`).  Returns the packed float32 CUDA tensor raw2bayer would give for
     `lr_raw - darkshading [+ darkshading.mean()] [+ bias_draw]`, evaluated in the map's precision as NumPy does."""
-    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
-    if dev is None:
-        raise RuntimeError("pnnp_b200: no CUDA device (there is no CPU fallback)")
+    dev = _lib.cuda_device()                                    # raises without a CUDA device: there is no CPU fallback
     if isinstance(lr_raw, torch.Tensor):
         t = lr_raw
         if t.dtype not in (torch.int16, torch.uint16):

@@ -22,6 +22,26 @@ def _on_host(fn):
     return wrapped
 
 
+_Generator = torch.Generator
+
+
+class _HostGenerator(_Generator):
+    """torch.Generator(device='cuda') -> a host generator (a subclass: annotations such as `torch.Generator | None` keep working)."""
+
+    def __new__(cls, device="cpu"):
+        return _Generator.__new__(cls, device="cpu" if str(device).startswith("cuda") else device)
+
+
+def _to_host(orig):
+    @functools.wraps(orig)
+    def to(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) or (isinstance(x, torch.device) and x.type == "cuda") else x for x in a)
+        if "device" in k and str(k["device"]).startswith("cuda"):
+            k["device"] = "cpu"
+        return orig(self, *a, **k)
+    return to
+
+
 @pytest.fixture
 def cuda_is_the_host(monkeypatch, libs):  # noqa: F811
     lib = _EmulatedLibrary(*libs)
@@ -34,12 +54,17 @@ def cuda_is_the_host(monkeypatch, libs):  # noqa: F811
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)        # torch.optim asks before every step
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone())     # a copy, as a host-to-device transfer is
     monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
-    for name in ("rand", "randn", "zeros", "ones", "empty", "full", "arange", "tensor", "Generator"):
+    for name in ("rand", "randn", "zeros", "ones", "empty", "full", "arange", "tensor", "as_tensor", "zeros_like", "empty_like", "randint"):
         monkeypatch.setattr(torch, name, _on_host(getattr(torch, name)))
+    monkeypatch.setattr(torch, "Generator", _HostGenerator)
+    monkeypatch.setattr(torch.Tensor, "to", _to_host(torch.Tensor.to))
+    monkeypatch.setattr(torch.nn.Module, "to", _to_host(torch.nn.Module.to))
     monkeypatch.setenv("PNNP_TRAIN_GRAPH", "0")
     for k in _VARIANT_ENV:
         monkeypatch.delenv(k, raising=False)
