@@ -90,6 +90,38 @@ def test_no_cpu_fallback():
         P.raw2bayer(np.zeros((4, 4), np.uint16))
 
 
+def test_host_emulation_is_unreachable_from_the_product(tmp_path, monkeypatch):
+    """The CPU models of tests/emul/ are test infrastructure: the product build never defines PNNP_HOST_EMUL (the only way the csrc
+    headers see tests/emul/), no Python module of the package refers to tests/ or to an emulated library, the built library exports
+    no emulation entry point, and without a CUDA device the trainer, the dataset and the training step raise."""
+    import subprocess
+    import torch
+    pkg = os.path.join(ROOT, "pnnp_b200")
+    assert "PNNP_HOST_EMUL" not in open(os.path.join(pkg, "csrc", "build.sh")).read()
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "emul" not in src.lower() and "tests/emul" not in src and "cuda_is_the_host" not in src, fn
+    so = os.path.join(pkg, "libpnnp_b200.so")
+    if os.path.exists(so):
+        syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+        assert "emul_" not in syms and "simt" not in syms
+    if torch.cuda.is_available():
+        return
+    import yaml
+    from pnnp_b200 import trainer as T
+    from pnnp_b200.datasets import Raw_Dataset
+    from pnnp_b200.train import UNetTrainStep
+    cfg = yaml.load(open(os.path.join(ROOT, "runfiles/SonyA7S2/PNNP.yml")), Loader=yaml.FullLoader)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        Raw_Dataset(dict(cfg["dst_train"], H=64, W=64, patch_size=32))[0]
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        UNetTrainStep(P.UNetSeeInDark(cfg["arch"]))
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        T.SID_Trainer(["-f", os.path.join(ROOT, "runfiles/SonyA7S2/PNNP.yml"), "--mode", "train"])
+
+
 def test_product_never_imports_oracle():
     """No import / include / dlopen of anything under oracle/ from the product package."""
     pkg = os.path.join(ROOT, "pnnp_b200")
