@@ -42,7 +42,7 @@ def pytest_collection_modifyitems(config, items):
     # marginal training tolerance cannot hide the parity results of everything else.  Stable sort: order inside a group is kept.
     def late(it):
         if "test_gpu_wb_jitter.py" in it.nodeid or "test_gpu_preprocess_route.py" in it.nodeid:
-            return 2                      # rows added after round 1's GPU budget was spent: not yet run on a B200
+            return 2                      # rows added after round 1's GPU budget was spent: rehearsed on the CPU models, first B200 run at round end
         return int("test_gpu_train.py" in it.nodeid or "train_mode" in it.nodeid)
     items.sort(key=late)
     if torch.cuda.is_available() or ON_CPU_MODELS:
