@@ -182,7 +182,7 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             sa += (uint32_t)stage_bytes; fb += 8; eb += 8;
             if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; sa = smem0; fb = full0; eb = empty0; }
         }
-        if (elect_one()) tc_commit(smem_u32(done_bar));
+        if (nk > 0 && elect_one()) tc_commit(smem_u32(done_bar));      // an empty K range has no epilogue: nobody would wait for this commit
         __syncwarp();
     } else if (warp == 0) {
         // ============================== TMA producer ==============================
