@@ -195,7 +195,8 @@ int pnnp_wb_gains(float* data, int n, int c, int h, int w, float rgb_gain, const
 
 /* HighBitRecovery.map (data_process/process.py:726-751): samples whose rounded DN value x is in [low, high) are re-drawn as
  * dist.ppf(cdf[x - low] + U * range[x - low]) (float64, rounded to float32), the sub-DN remainder is added back, then /span
- * (norm) or +bl.  dist = Tukey-lambda(lam) * scale + loc, or N(loc, scale).  rand: caller-supplied U (replay) or NULL for
+ * (norm bit 0) or +bl; norm bit 1 = HighBitRecovery(float=False): the remainder is dropped.  dist = Tukey-lambda(lam) * scale + loc
+ * (scipy's boxcox(u) - boxcox1p(-u), each term divided by lam), or N(loc, scale).  rand: caller-supplied U (replay) or NULL for
  * Philox4x32-10 draws keyed on (seed, offset, index0 + element); rand_out (optional) receives the U used. */
 int pnnp_hbr_map(const float* in, float* out, size_t total, const double* cdf, const double* range, int low, int high,
                  int scale_in, int norm, float span, float bl, int dist_tukey, double lam, double loc, double scale,

@@ -406,10 +406,12 @@ def data_aug(data, mode=0):
 
 
 def random_crop(img, h_start, w_start, patch, aug):
-    """syn_datasets.py:162-173 with the crop points passed in."""
+    """syn_datasets.py:162-173 with the crop points passed in: crop_per_image = len(aug) crops from the first crop points
+    (IndexError when there are fewer points, as the reference's h_start[i])."""
     c = img.shape[0]
-    crops = np.empty((len(h_start), c, patch, patch), dtype=F32)
-    for i, (hs, ws) in enumerate(zip(h_start, w_start)):
+    crops = np.empty((len(aug), c, patch, patch), dtype=F32)
+    for i in range(len(aug)):
+        hs, ws = h_start[i], w_start[i]
         crops[i] = data_aug(img[:, hs:hs + patch, ws:ws + patch], mode=aug[i])
     return crops
 
@@ -462,9 +464,9 @@ def darkshading_raw2bayer(lr_raw, darkshading, wp=16383, bl=512, add_mean=False,
     return raw2bayer(lr, wp=wp, bl=bl, norm=True, clip=clip)
 
 
-def hbr_map(data, lut, rand, norm=True):
+def hbr_map(data, lut, rand, norm=True, keep_remainder=True):
     """HighBitRecovery.map (data_process/process.py:726-751) with the uniforms passed in; `lut` is the dict HB2LB_LUT
-    returns (keys param, dist, low, high, and per integer level cdf / range)."""
+    returns (keys param, dist, low, high, and per integer level cdf / range).  keep_remainder = the object's `float` flag."""
     p = lut['param']
     if np.max(data) <= 1:
         data = data * (p['wp'] - p['bl'])
@@ -474,7 +476,8 @@ def hbr_map(data, lut, rand, norm=True):
     for x in range(lut['low'], lut['high']):
         keys = (data == x)
         data[keys] = lut['dist'].ppf(lut[x]['cdf'] + rand[keys] * lut[x]['range'])
-    data = data + delta
+    if keep_remainder:
+        data = data + delta
     return data / (p['wp'] - p['bl']) if norm else data + p['bl']
 
 
@@ -620,6 +623,31 @@ def ssim(target, estimate, data_range=255):
         uxx, uyy, uxy = uniform_filter(x * x, win), uniform_filter(y * y, win), uniform_filter(x * y, win)
         vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
         S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+        pad = (win - 1) // 2
+        vals.append(S[pad:-pad, pad:-pad].mean(dtype=F64))
+    return float(np.mean(vals))
+
+
+def ssim_float32_path(target, estimate, data_range=255):
+    """The same algorithm the way scikit-image >= 0.19 executes it for float32 images (`_supported_float_type` keeps float32: the
+    five uniform filters, their products and the S map are float32; only the final mean is float64).  scikit-image is not in this
+    image's wheelhouse, so neither restatement can be checked against the library itself (E2 stays "parity unpinned"); this one
+    bounds what the library's own float32 rounding could move: tests require |ssim - ssim_float32_path| < 5e-5."""
+    from scipy.ndimage import uniform_filter
+    X = np.asarray(target, F32)
+    Y = np.asarray(estimate, F32)
+    win, K1, K2 = 7, 0.01, 0.03
+    cov_norm = (win * win) / (win * win - 1)
+    C1, C2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+    vals = []
+    for ch in range(X.shape[-1]):
+        x, y = X[..., ch], Y[..., ch]
+        ux, uy = uniform_filter(x, size=win), uniform_filter(y, size=win)
+        uxx, uyy, uxy = uniform_filter(x * x, size=win), uniform_filter(y * y, size=win), uniform_filter(x * y, size=win)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        A1, A2, B1, B2 = 2 * ux * uy + C1, 2 * vxy + C2, ux ** 2 + uy ** 2 + C1, vx + vy + C2
+        S = (A1 * A2) / (B1 * B2)
+        assert S.dtype == F32
         pad = (win - 1) // 2
         vals.append(S[pad:-pad, pad:-pad].mean(dtype=F64))
     return float(np.mean(vals))

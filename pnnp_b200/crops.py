@@ -40,12 +40,15 @@ def data_aug(data, mode=0):
 
 
 def random_crop(img, h_start, w_start, aug, patch_size):
-    """syn_datasets.py:162-173: img CUDA fp32 (c,h,w) -> crops (n,c,patch,patch)."""
+    """syn_datasets.py:162-173: img CUDA fp32 (c,h,w) -> crops (crop_per_image,c,patch,patch), crop_per_image = len(aug)
+    (init_random_crop_point draws exactly that many aug modes).  As in the reference the first crop_per_image start points
+    are used — a 'non-overlapped' grid may hold more — and fewer start points than crops raise IndexError."""
     _lib.require_cuda(img, "img")
     img = img.float().contiguous()
     c, h, w = img.shape
-    n = len(h_start)
-    k = min(n, len(aug))                  # the reference indexes aug[i] for i < crop_per_image
+    n = k = len(aug)
+    if len(h_start) < n or len(w_start) < n:
+        raise IndexError(f"random_crop: {n} crops per image but only {min(len(h_start), len(w_start))} crop points")
     out = torch.empty((n, c, patch_size, patch_size), dtype=torch.float32, device=img.device)
     L = _lib.lib()
     with torch.cuda.device(img.device):

@@ -2,6 +2,7 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #ifndef PNNP_HOST_EMUL
 #include <cuda_runtime.h>
 #endif
@@ -10,6 +11,9 @@ namespace pnnp {
 int fail(const char* msg);                 // records msg, returns 1
 int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(uint64_t n = 1);
+// Kernel variants measured on a B200 in round 2 (tools/r02_sweep.sh, profiles/r02_sweep_summary.txt) and promoted to defaults;
+// NAME=0 in the environment switches one off again (A/B timing, bisecting).  Read per launch: tests flip them.
+inline bool variant_on(const char* name) { const char* e = getenv(name); return !e || atoi(e) > 0; }
 }  // namespace pnnp
 
 #define PNNP_CUDA(expr)                                                             \

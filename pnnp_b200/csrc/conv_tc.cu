@@ -672,8 +672,12 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // on a B200: PNNP_CONV_SUPER=1 -> one CTA per SM, four accumulators (two super-tiles in flight); =2 -> keeps two CTAs per SM
     // for the small-K resident-weight layers (one super-tile in flight per CTA).  Only the compile-time specialised NHWC 3x3
     // layers with N <= 128 take it (decided below, once the epilogue specialisation is known).
-    const bool convt_fast = getenv("PNNP_CONVT_FAST") && atoi(getenv("PNNP_CONVT_FAST")) > 0;
-    const int super_env = getenv("PNNP_CONV_SUPER") ? atoi(getenv("PNNP_CONV_SUPER")) : 0;      // read per launch: tests flip it
+    // ConvTranspose2d fast path (specialised pixel-shuffle epilogue, resident weights): 31 -> 25, 39 -> 35, 62 -> 50 us on the Sony
+    // frame's 512 / 256 / 128-channel layers, but 89 -> 95-99 us on the 64-channel full-resolution one, which keeps the generic path
+    const bool convt_fast = variant_on("PNNP_CONVT_FAST") && cin0 > 64;
+    // super-tile: measured faster on the MODE_CONV3 layers it applies to (64->64 @712x1064: 86 -> 70 us, 32->64: 64 -> 58) and
+    // slower on the x-shift-in-N layers (16->32: 99 -> 109, 64->32: 134 -> 146), which therefore stay on single tiles
+    const int super_env = getenv("PNNP_CONV_SUPER") ? atoi(getenv("PNNP_CONV_SUPER")) : (mode == MODE_CONV3 ? 1 : 0);
     static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
     const int dbg_env = getenv("PNNP_CONV_DBG") ? atoi(getenv("PNNP_CONV_DBG")) : 0;
     int epi = EPI_GENERIC;
@@ -787,10 +791,11 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     }
     // the opt-in instantiations are touched only once one of their switches is on: a default run loads and configures exactly
     // the kernels it did when it was measured
-    const bool pdl = getenv("PNNP_CONV_PDL") && atoi(getenv("PNNP_CONV_PDL")) > 0;
-    // packed-pair epilogue arithmetic: built for the specialised 3x3 epilogues, alone (VAR 4) or with both other switches (VAR 7)
-    const bool x2 = getenv("PNNP_CONV_F32X2") && atoi(getenv("PNNP_CONV_F32X2")) > 0 && epi != EPI_GENERIC && epi != EPI_CONVT &&
-                    (mode == MODE_CONV3 || mode == MODE_CONV3X) && sup == pdl;
+    const bool pdl = variant_on("PNNP_CONV_PDL");
+    // packed-pair epilogue arithmetic: built for the specialised 3x3 epilogues, alone (VAR 4), with PDL (VAR 6) or with both other
+    // switches (VAR 7)
+    const bool x2 = variant_on("PNNP_CONV_F32X2") && epi != EPI_GENERIC && epi != EPI_CONVT &&
+                    (mode == MODE_CONV3 || mode == MODE_CONV3X) && (pdl || !sup);
     static bool attr_optin_done = false;
     if ((sup || pdl || x2) && !attr_optin_done) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
@@ -798,6 +803,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         PNNP_FOR_EACH_SUPER_VARIANT(X)
 #undef X
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                   PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
                    PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_SUPER_VARIANT(X)
 #undef X
@@ -819,6 +825,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (x2) {
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
         if (sup) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 7>, tmA0, tmA1, tmB, p)); \
+        else if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 6>, tmA0, tmA1, tmB, p)); \
         else PNNP_CONV_KLAUNCH(T, K, E, 4); \
         launched = true; }
         PNNP_FOR_EACH_SUPER_VARIANT(X)
@@ -875,7 +882,7 @@ extern "C" int pnnp_conv_pipeline_error(void) {
 extern "C" int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, float scale, void* stream) {
     if (!in || !out || c > 16) return fail("nchw_to_nhwc16: bad arguments");
     const size_t total = (size_t)n * h * w;
-    if (getenv("PNNP_IN_V2") && atoi(getenv("PNNP_IN_V2")) > 0 && (((size_t)h * w) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    if (variant_on("PNNP_IN_V2") && (((size_t)h * w) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
         const int blocks4 = (int)std::min<size_t>((total / 4 + 255) / 256, 148 * 8);
         nchw_f32_to_nhwc16_bf16_x4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(in, static_cast<__nv_bfloat16*>(out), n, c, h, w, scale);
         count_launch();

@@ -18,13 +18,14 @@ struct HbrArgs {
 __device__ __forceinline__ double hbr_ppf(double u, const HbrArgs& a) {
     double q;
     if (a.dist_tukey) {
-        // scipy.stats.tukeylambda._ppf: boxcox(u, lam) - boxcox1p(-u, lam)
-        if (fabs(a.lam) < 1e-19) q = log(u) - log1p(-u);
-        else q = (expm1(a.lam * log(u)) - expm1(a.lam * log1p(-u))) / a.lam;
+        // scipy.stats.tukeylambda._ppf = boxcox(u, lam) - boxcox1p(-u, lam); scipy/special/_boxcox.pxd divides each term by lam
+        // before the subtraction: the same operations in the same order, none contracted
+        if (fabs(a.lam) < 1e-19) q = __dsub_rn(log(u), log1p(-u));
+        else q = __dsub_rn(__ddiv_rn(expm1(__dmul_rn(a.lam, log(u))), a.lam), __ddiv_rn(expm1(__dmul_rn(a.lam, log1p(-u))), a.lam));
     } else {
         q = normcdfinv(u);
     }
-    return q * a.scale + a.loc;
+    return __dadd_rn(__dmul_rn(q, a.scale), a.loc);             // rv_continuous.ppf: _ppf(q) * scale + loc, two NumPy operations
 }
 
 __global__ void __launch_bounds__(256) hbr_map_kernel(const HbrArgs a) {
@@ -45,10 +46,10 @@ __global__ void __launch_bounds__(256) hbr_map_kernel(const HbrArgs a) {
         if (a.rand_out) a.rand_out[i] = u;
         if (r >= (float)a.low && r < (float)a.high) {
             const int k = (int)r - a.low;
-            r = (float)hbr_ppf(a.cdf[k] + u * a.range[k], a);
+            r = (float)hbr_ppf(__dadd_rn(a.cdf[k], __dmul_rn(u, a.range[k])), a);
         }
-        float o = __fadd_rn(r, delta);
-        o = a.norm ? __fdiv_rn(o, a.span) : __fadd_rn(o, a.bl);
+        float o = (a.norm & 2) ? r : __fadd_rn(r, delta);       // HighBitRecovery(float=False) leaves the remainder out
+        o = (a.norm & 1) ? __fdiv_rn(o, a.span) : __fadd_rn(o, a.bl);
         a.out[i] = o;
     }
 }

@@ -52,7 +52,7 @@ extern "C" int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t 
     const int quantum = std::max(1, (c / 8) / 256);                  // keep grid * 256 a multiple of c / 8
     blocks = std::max(quantum, blocks / quantum * quantum);
     const int c8 = c / 8;
-    if (getenv("PNNP_ACTBWD_V2") && atoi(getenv("PNNP_ACTBWD_V2")) > 0 && (c8 & (c8 - 1)) == 0 && c8 <= 256 && items < (1ull << 32) - (1ull << 24)) {
+    if (variant_on("PNNP_ACTBWD_V2") && (c8 & (c8 - 1)) == 0 && c8 <= 256 && items < (1ull << 32) - (1ull << 24)) {
         ActBwd2Args a{static_cast<uint16_t*>(g), static_cast<const uint16_t*>(out), (uint32_t)items, c, act_kind};
         act_bwd_bias_v2_kernel<<<blocks, kAb2Threads, sizeof(float) * c, (cudaStream_t)stream>>>(a, dbias);
         count_launch();
@@ -106,7 +106,7 @@ extern "C" int pnnp_adam_step_dev(float* p, const float* g, float* m, float* v, 
 
 extern "C" int pnnp_strided_copy_batch(const pnnp_copy_desc* descs_dev, int n_desc, int blocks_per_desc, void* stream) {
     if (!descs_dev || n_desc < 1 || blocks_per_desc < 1) return pnnp::fail("strided_copy_batch: bad arguments");
-    if (getenv("PNNP_COPY_V2") && atoi(getenv("PNNP_COPY_V2")) > 0)      // 32-bit index arithmetic; every descriptor the trainer builds is < 2^31 elements
+    if (variant_on("PNNP_COPY_V2"))      // 32-bit index arithmetic; every descriptor the trainer builds is < 2^31 elements
         pnnp::strided_copy_batch_v2_kernel<<<dim3((unsigned)blocks_per_desc, (unsigned)n_desc), 256, 0, (cudaStream_t)stream>>>(descs_dev);
     else
     pnnp::strided_copy_batch_kernel<<<dim3((unsigned)blocks_per_desc, (unsigned)n_desc), 256, 0, (cudaStream_t)stream>>>(descs_dev);

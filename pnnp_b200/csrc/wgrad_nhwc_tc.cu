@@ -447,7 +447,7 @@ extern "C" int pnnp_wgrad_nhwc(int mode, const void* g, int co, int co_stride, c
     p.tmem_cols = tc;
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * kWnStagesMax + 1) * 8 + 64;
     if (smem > 227 * 1024 || tc > 512) return fail("wgrad_nhwc: shared memory / TMEM budget exceeded");
-    if (getenv("PNNP_WGRAD_V2") && atoi(getenv("PNNP_WGRAD_V2")) > 0 && !p.dbg) {
+    if (variant_on("PNNP_WGRAD_V2") && !p.dbg) {
         static bool attr2_done = false;
         if (!attr2_done) { PNNP_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2_done = true; }
         PNNP_WGRAD_KLAUNCH(1);

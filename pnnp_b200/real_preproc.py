@@ -111,8 +111,6 @@ class HighBitRecovery:
         x = data.float().contiguous()
         span = float(p['wp'] - p['bl'])
         scale_in = bool((x.max() <= 1).item())                       # `if np.max(data) <= 1`
-        if not self.float:
-            raise RuntimeError("HighBitRecovery(float=False) is not built (every reference call site uses float=True)")
         tab = torch.from_numpy(lut['_table']).to(x.device)
         out = torch.empty_like(x)
         tukey = 'g' in self.noise_code.lower()
@@ -127,7 +125,7 @@ class HighBitRecovery:
         r_out = torch.empty(x.shape, dtype=torch.float64, device=x.device) if return_rand else None
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().pnnp_hbr_map(x.data_ptr(), out.data_ptr(), x.numel(), tab[0].data_ptr(), tab[1].data_ptr(),
-                                               int(lut['low']), int(lut['high']), int(scale_in), int(bool(norm)), span, float(p['bl']),
+                                               int(lut['low']), int(lut['high']), int(scale_in), int(bool(norm)) | (0 if self.float else 2), span, float(p['bl']),
                                                int(tukey), float(p['lam']), float(lut['bias']), sc, _lib.ptr(rand), seed, offset,
                                                int(index0), _lib.ptr(r_out), _lib.stream_ptr(x.device)), "hbr_map")
         return (out, r_out) if return_rand else out

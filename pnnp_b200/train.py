@@ -106,6 +106,7 @@ class UNetTrainStep:
             p.data = self.flat_p[off:off + n].view_as(p)
             self.slices[name] = (off, n, tuple(p.shape))
             off += n
+        self.sync_parameters()
         self.scr = _Scratch(self.device)
         self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         # weight-gradient scratch of every layer ([taps][ci_pad16][co] fp32, the layout the wgrad kernel adds into with
@@ -122,6 +123,15 @@ class UNetTrainStep:
             total_dw += shape[0] * shape[1] * shape[2]
         self.dw_flat = torch.zeros(total_dw, dtype=torch.float32, device=self.device)
         self._build_copy_tables()
+
+    def sync_parameters(self, src=0):
+        """Every rank starts from (and, after a checkpoint reload, continues from) rank `src`'s parameters, as the
+        DistributedDataParallel constructor does: each process seeds its own CPU generator, so `initialize_weights` and the
+        default-initialised ConvTranspose2d biases differ between ranks until this broadcast.  No-op for a single process."""
+        if D.world()[1] > 1:
+            torch.distributed.broadcast(self.flat_p, src)
+            if hasattr(self, "_pack_tab"):
+                self.refresh_packed()
 
     # ---------------------------------------------------------------- batched weight packing / gradient layout
     def _build_copy_tables(self):

@@ -29,7 +29,7 @@ from .datasets import Raw_Dataset, Synthetic_ELD_Dataset, Synthetic_IMX686_Datas
 from .metrics import eval_partial_sums, finish_metrics
 from .noise import synthesize_batch
 from .noise_params import HALF_CLIP, sample_params_max
-from .utils import AverageMeter, load_weights, log, lr_lambda_from_hyper, tensor_dim5to4
+from .utils import AverageMeter, load_weights, log, lr_for_epoch, lr_lambda_from_hyper, tensor_dim5to4
 
 
 class BaseParser():
@@ -181,11 +181,23 @@ class SID_Trainer(Base_Trainer):
             psnr_sum += r_dn['PSNR']; ssim_sum += r_dn['SSIM']
             psnr_lr_sum += r_lr['PSNR']; ssim_lr_sum += r_lr['SSIM']
         cnt = len(pending)
+        if self.world_size > 1 and epoch < 0:                            # per-frame entries of every rank's shard -> rank 0's pickle
+            mine_named = {name: metrics[name] for name, *_ in pending}
+            gathered = [None] * self.world_size if self.rank == 0 else None
+            torch.distributed.gather_object(mine_named, gathered, dst=0)
+            if self.rank == 0:
+                for part in gathered:
+                    metrics.update(part)
         p_dn, s_dn, total = D.reduce_metric_sums(psnr_sum, ssim_sum, cnt, self.device)
         p_lr, s_lr, _ = D.reduce_metric_sums(psnr_lr_sum, ssim_lr_sum, cnt, self.device)
         self.eval_psnr.update(p_dn, total); self.eval_ssim.update(s_dn, total)
         self.eval_psnr_lr.update(p_lr, total); self.eval_ssim_lr.update(s_lr, total)
         self.eval_psnr_dn, self.eval_ssim_dn = self.eval_psnr, self.eval_ssim
+        if self.eval_psnr_dn.avg >= self.best_psnr and epoch > 0:        # trainer_SID.py:302-307 (the all-reduced average: every
+            self.best_psnr = self.eval_psnr_dn.avg                       # rank tracks the same record, rank 0 writes the file)
+            if self.rank == 0:
+                log(f"Best PSNR is {self.best_psnr} now!!")
+                torch.save(_detached_state(self.net), f'{self.fast_ckpt}/{self.model_name}_best_model.pth')
         if self.rank == 0:
             log(f"Epoch {epoch}: PSNR={self.eval_psnr.avg:.2f}\n"
                 + f"psnrs_lr={self.eval_psnr_lr.avg:.2f}, psnrs_dn={self.eval_psnr_dn.avg:.2f}"
@@ -252,7 +264,9 @@ class SID_Trainer(Base_Trainer):
         for epoch in range(self.hyper['last_epoch'] + 1, self.hyper['stop_epoch'] + 1):
             self.net.train()
             self.train_psnr.reset()
-            step.lr = lr_lambda(epoch)                                  # scheduler.step() precedes each epoch (trainer_SID.py:75,139)
+            # LambdaScheduler starts at last_epoch = -1 whatever hyper['last_epoch'] is, is stepped once by its constructor, once at
+            # the top of train() and once per trained epoch (trainer_SID.py:57,75,127): the k-th trained epoch runs at lr_lambda(k)
+            step.lr = lr_for_epoch(lr_lambda, epoch, self.hyper['last_epoch'])
             order = np.random.RandomState(1997 + epoch).permutation(len(self.dst_train))   # DataLoader(shuffle=True)
             batches = [order[i:i + bs] for i in range(0, len(order), bs)]
             losses = []
@@ -281,6 +295,18 @@ class SID_Trainer(Base_Trainer):
                 self.eval(epoch=epoch)
                 if self.rank == 0:
                     torch.save(_detached_state(self.net), f'{self.fast_ckpt}/{self.model_name}_last_model.pth')
+            # reload best model each period (trainer_SID.py:170-179); optimiser moments are kept, as there
+            period = (self.hyper['stop_epoch'] - self.hyper['last_epoch']) // (self.hyper['T'] if 'T' in self.hyper else 1)
+            if period > 0 and (self.hyper['last_epoch'] + epoch) % period == 0:
+                if self.world_size > 1:
+                    torch.distributed.barrier()                         # rank 0 may just have written the file
+                model_path = f'{self.fast_ckpt}/{self.model_name}_best_model.pth'
+                if os.path.exists(model_path):
+                    self.net = load_weights(self.net, torch.load(model_path, map_location=self.device), by_name=True)
+                    step.sync_parameters()                              # the parameters are views of the step's flat buffer
+                    step.refresh_packed()
+                    if self.rank == 0:
+                        log(f'Successfully reload best model (Eval PSNR:{self.best_psnr})', log=self.logfile)
         if self.rank == 0:
             torch.save(_detached_state(self.net), f'{self.fast_ckpt}/{self.model_name}_last_model.pth')
         if self.world_size > 1:
@@ -325,6 +351,7 @@ def main_sid(argv=None):
     trainer = SID_Trainer(argv)
     if trainer.mode == 'train':
         trainer.train()
+        trainer.mode = 'evaltest'                                       # trainer_SID.py:527: training ends with the full sweeps
     _load_best_or_make_checkpoint(trainer)
     results = {}
     if 'eval' in trainer.mode:
@@ -359,6 +386,7 @@ def main_lrid(argv=None):
     trainer = IMX686_Trainer(argv)
     if trainer.mode == 'train':
         trainer.train()
+        trainer.mode = 'evaltest'                                       # trainer_LRID.py:481
     _load_best_or_make_checkpoint(trainer)
     results = {}
     for mode in ('eval', 'test'):

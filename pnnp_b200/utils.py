@@ -98,3 +98,11 @@ def lr_lambda_from_hyper(hyper):
         return lambda x: get_multistep_lr(x, period=num_of_epochs // T, decay_base=1, milestone=[step_size, step_size * 9 // 5],
                                           gamma=[0.5, 0.1], lr=hyper['learning_rate'])
     raise KeyError(f"lr_scheduler {hyper['lr_scheduler']!r}: the reference knows 'cos' and 'multi' schedules")
+
+
+def lr_for_epoch(lr_lambda, epoch, last_epoch):
+    """Learning rate of training epoch `epoch` (the loop runs last_epoch+1 .. stop_epoch).  The reference's LambdaScheduler
+    (base_trainer.py:131-138) is built with torch's default last_epoch = -1 regardless of hyper['last_epoch'], stepped once by
+    its constructor, once at the top of train() (trainer_SID.py:75) and once after every trained epoch (:127), and returns
+    lmbda(last_epoch) itself: the k-th trained epoch runs at lr_lambda(k), k = epoch - hyper['last_epoch']."""
+    return lr_lambda(epoch - last_epoch)

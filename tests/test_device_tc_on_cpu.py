@@ -67,7 +67,7 @@ class _EmulatedLibrary:
 
     # ---- training step (csrc/train_kernels.cuh, copy_kernels.cuh, wgrad_nhwc_tc.cu)
     def pnnp_strided_copy_batch(self, tab, n, blocks, stream):
-        return self.k.emul_strided_copy_batch(C.c_void_p(tab), n, int(os.environ.get("PNNP_COPY_V2", "0") == "1"), 3, 256)
+        return self.k.emul_strided_copy_batch(C.c_void_p(tab), n, int(os.environ.get("PNNP_COPY_V2", "1") != "0"), 3, 256)
 
     def pnnp_act_bwd_bias(self, g, out, dbias, pixels, c, act, stream):
         return self.sk.emul_act_bwd_bias(C.c_void_p(g), C.c_void_p(out), C.c_void_p(dbias), C.c_size_t(pixels), c, act, 2)
@@ -157,7 +157,7 @@ class _EmulatedLibrary:
 
     def pnnp_eval_epilogue(self, dn, hr, n, c, h, w, scale, correct, sums, stream):
         return self.sk.emul_eval_epilogue(C.c_void_p(dn), C.c_void_p(hr), n, c, h, w, C.c_float(scale), correct, C.c_void_p(sums),
-                                          int(os.environ.get("PNNP_SSIM_V2", "0") == "1"), 2)
+                                          int(os.environ.get("PNNP_SSIM_V2", "1") != "0"), 2)
 
     def pnnp_wgrad_nhwc_pipeline_error(self):
         return self.tc.emul_wgrad_pipeline_error()
@@ -177,7 +177,7 @@ class _EmulatedLibrary:
         return self.k.emul_wb_gains(C.c_void_p(data), n, c, h, w, C.c_float(rgb_gain), kind, gain, 3, 128)
 
     def pnnp_nchw_to_nhwc16(self, src, dst, n, c, h, w, scale, stream):
-        v2 = int(os.environ.get("PNNP_IN_V2", "0") == "1" and (h * w) % 4 == 0)
+        v2 = int(os.environ.get("PNNP_IN_V2", "1") != "0" and (h * w) % 4 == 0)
         return self.k.emul_nchw_to_nhwc16(C.c_void_p(src), C.c_void_p(dst), n, c, h, w, C.c_float(scale), v2, 3, 256)
 
     def pnnp_maxpool2x2_nhwc(self, src, dst, n, h, w, c, stream):
@@ -228,14 +228,16 @@ def _bits(t):
 
 
 def _with_env(monkeypatch, env, fn):
+    """Run fn with every variant switch forced OFF (the round-1 kernels) except those in `env`; afterwards back to the product's
+    defaults (the variants promoted in round 2 are on when the variable is unset)."""
     for k in _VARIANT_ENV:
-        monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv(k, "0")
     for k, v in env.items():
         monkeypatch.setenv(k, str(v))
     try:
         return fn()
     finally:
-        for k in env:
+        for k in _VARIANT_ENV:
             monkeypatch.delenv(k, raising=False)
 
 

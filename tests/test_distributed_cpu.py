@@ -93,3 +93,44 @@ def test_training_epoch_gives_every_rank_the_same_number_of_steps():
             taken = [[(r * per_rank + j) % n_batches for j in range(per_rank)] for r in range(world)]
             assert len({len(t) for t in taken}) == 1
             assert set(i for t in taken for i in t) == set(range(n_batches))
+
+
+def _sync_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pnnp_b200.train import UNetTrainStep
+
+    class Step:                                            # the flat parameter buffer of a training step, without its CUDA parts
+        refreshed = 0
+
+        def refresh_packed(self):
+            self.refreshed += 1
+    st = Step()
+    torch.manual_seed(100 + rank)                          # every process initialises its own weights (initialize_weights on CPU)
+    st.flat_p = torch.randn(1000)
+    before = st.flat_p.clone()
+    UNetTrainStep.sync_parameters(st)                      # constructor path: no pack tables yet
+    st._pack_tab = object()
+    UNetTrainStep.sync_parameters(st)                      # checkpoint-reload path: re-packs the tensor-core weight layouts
+    out.put((rank, before.tolist(), st.flat_p.tolist(), st.refreshed))
+    dist.destroy_process_group()
+
+
+def test_initial_parameters_are_broadcast_from_rank0_gloo_world2():
+    """torchrun --mode train must start every replica from rank 0's weights, as DistributedDataParallel's
+    constructor does (the reference's single-process DataParallel has one copy, base_trainer.py:115-118)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, rest) for r, *rest in (q.get(timeout=120) for _ in procs))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][0] != res[1][0]                          # different initial weights per process ...
+    assert res[0][1] == res[1][1] == res[0][0]             # ... identical, rank 0's, after the broadcast
+    assert res[0][2] == res[1][2] == 1

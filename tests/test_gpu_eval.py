@@ -51,10 +51,15 @@ def test_illuminance_correct_vs_reference_golden(golden):
     np.testing.assert_allclose(out.cpu().numpy(), g["corrected"], rtol=2e-6, atol=1e-7)
 
 
-def test_full_frame_size():
+def test_full_frame_vs_oracle():
+    """E1 + E2 at the BASELINE frame shape (1 x 4 x 1424 x 2128, configs[0] / [4]) against the oracle — clamp, IlluminanceCorrect
+    gain, tensor2im, PSNR and SSIM (trainer_SID.py:231-244) — not just a plausible range."""
     g = torch.Generator(device="cuda").manual_seed(0)
     hr = torch.rand((1, 4, 1424, 2128), device="cuda", generator=g)
-    dn = (hr + 0.02 * torch.randn(hr.shape, device="cuda", generator=g)).contiguous()
-    r = metrics.eval_frame_metrics(dn, hr, 1.0, True)[0]
-    mse = ((dn.clamp(0, 1) * (r_gain := 1.0) - hr) ** 2).mean().item()
-    assert 30 < r["PSNR"] < 40 and 0.5 < r["SSIM"] < 1.0
+    hr[:, 1, :3, :11] = 1.0                                      # saturated samples: excluded from the gain's dot products
+    dn = (0.93 * hr + 0.02 * torch.randn(hr.shape, device="cuda", generator=g)).contiguous()
+    for correct in (True, False):
+        r = metrics.eval_frame_metrics(dn, hr, 1.0, correct)[0]
+        p, s = _oracle_metrics(dn.cpu().numpy(), hr.cpu().numpy(), 1.0, correct)
+        print(f"full frame correct={correct}: PSNR {r['PSNR']:.6f} (oracle {p:.6f}), SSIM {r['SSIM']:.8f} (oracle {s:.8f})")
+        assert r["PSNR"] == pytest.approx(p, abs=2e-4) and r["SSIM"] == pytest.approx(s, abs=1e-6)

@@ -97,16 +97,16 @@ def test_lrid_eval_entry_point_reflect_pad_branch(cuda_is_the_host, tmp_path, mo
 
 @pytest.mark.parametrize("shape,scale,correct", [((1, 4, 64, 96), 1.0, False), ((2, 3, 45, 70), 1.5, False), ((1, 4, 128, 192), 1.0, True)])
 def test_experimental_separable_ssim(cuda_is_the_host, monkeypatch, shape, scale, correct):
-    import test_gpu_experimental as E
+    import test_gpu_variants as E
     E.test_separable_ssim_equals_default_kernel(monkeypatch, shape, scale, correct)
 
 
 @pytest.mark.parametrize("act_kind", [0, 1, 2])
 def test_experimental_act_backward_v2(cuda_is_the_host, monkeypatch, act_kind):
-    import test_gpu_experimental as E
+    import test_gpu_variants as E
     E.test_act_backward_v2_equals_the_default_kernel(monkeypatch, act_kind)
 
 
 def test_experimental_wgrad_v2(cuda_is_the_host, monkeypatch):
-    import test_gpu_experimental as E
+    import test_gpu_variants as E
     E.test_wgrad_v2_matches_autograd_like_the_default_kernel(monkeypatch)

@@ -264,3 +264,42 @@ def test_conv3x3_x_shift_in_n_mode(cin, cout, h, w, n, two):
     ref = F.leaky_relu(F.conv2d(xin, _bf(wt), b, padding=1), 0.2)
     assert (_nchw(out) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
     assert torch.equal(_nchw(pooled), F.max_pool2d(_nchw(out), 2))
+
+
+def _cpu_state(net):
+    return {k: v.detach().cpu() for k, v in net.state_dict().items()}
+
+
+@pytest.mark.parametrize("arch_name", ["UNetSeeInDark", "ResUnet"])
+@pytest.mark.parametrize("shape,reflect", [((1, 4, 1424, 2128), False),        # BASELINE configs[0] / [4]: Sony frame, 89 x 133 bottleneck
+                                           ((1, 4, 1744, 2320), False),        # configs[3]: the padded IMX686 extent the network sees
+                                           ((1, 4, 1736, 2312), True)])        # configs[3] through the reflect-pad branch
+def test_full_frame_forward_vs_cpu_fp32_oracle(arch_name, shape, reflect):
+    """U1 / U2 at the BASELINE frame shapes against the oracle's fp32 forward run on the CPU (independent of cuDNN): max-abs
+    <= 1e-3 with the reference's initialiser (north_star), relative error printed.  `reflect`: the eval boundary of
+    trainer_LRID.py:224-229 / trainer_SID.py:221-226 — F.pad(reflect, 4) -> net -> crop 4 — as the product's trainer runs it
+    (2312 % 16 == 8); the oracle pads, runs and crops on the CPU."""
+    from pnnp_b200.trainer import SID_Trainer
+    torch.manual_seed(23)
+    net = getattr(P, arch_name)(_arch()).cuda()
+    P.initialize_weights(net)
+    net.eval()
+    x = torch.rand(shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1997))
+    oracle_fwd = O.unet_forward if arch_name == "UNetSeeInDark" else O.resunet_forward
+    with torch.no_grad():
+        if reflect:
+            holder = type("T", (), {"net": net})()
+            got = SID_Trainer.forward_frame(holder, x)
+            want = oracle_fwd(F.pad(x.cpu(), (4, 4, 4, 4), mode="reflect"), _cpu_state(net))[..., 4:-4, 4:-4]
+        else:
+            got = net(x)
+            want = oracle_fwd(x.cpu(), _cpu_state(net))
+    _no_pipeline_error()
+    assert got.shape == x.shape
+    err = (got.cpu() - want).abs().max().item()
+    rel = err / want.abs().max().item()
+    print(f"{arch_name} {shape} reflect={reflect}: max-abs {err:.3e}, rel {rel:.3e}, out absmax {want.abs().max().item():.3e}")
+    assert err <= 1e-3, err
+    target = torch.rand(want.shape, generator=torch.Generator().manual_seed(3))
+    psnr = lambda a: 10 * torch.log10(1.0 / ((a.clamp(0, 1) - target) ** 2).mean())
+    assert abs(psnr(got.cpu()).item() - psnr(want).item()) < 0.01           # PSNR +- 0.01 dB on the same inputs

@@ -1,29 +1,23 @@
-"""Opt-in kernel variants written after round 1's GPU budget was spent (none has run on a B200 yet).  Each is selected by an
-environment variable that is off by default, and these tests are opt-in too (PNNP_TEST_EXPERIMENTAL=1), so the default
-`pytest -m gpu` run exercises only measured code.  `tools/r02_sweep.sh` runs them and times every variant.
+"""Kernel variants written at the end of round 1 and measured on a B200 at the start of round 2 (tools/r02_sweep.sh ->
+profiles/r02_sweep_summary.txt).  The ones that were bit-equal AND faster are now the defaults (NAME=0 switches one off): PDL,
+packed-pair epilogues, the ConvTranspose2d fast path (> 64 input channels), the super-tile on the MODE_CONV3 layers, the 4-pixel
+input conversion, the register-resident wgrad loops, the 32-bit copy / activation-backward kernels and the separable SSIM sums.
+These tests keep proving the equalities the promotion rests on: every variant against the round-1 kernel it replaced (all
+switches forced to 0 by the fixture below), bit for bit where the arithmetic is the same.
 
 * PNNP_CONV_SUPER=1|2 — super-tile conv kernel (conv_tc.cu, template parameter SUP): two M = 128 tiles per pipeline stage.  Every
-  output pixel sees the same MMAs in the same order as in the default kernel, so the two must agree BIT FOR BIT — outputs,
-  fused max-pool, fused 1x1 head and the masked data-gradient epilogue alike.  (Checked on the CPU tensor-core model first,
-  tests/test_device_tc_on_cpu.py: the variant is only taken where its taller boxes keep the plan's K chunk.)
-* PNNP_CONVT_FAST=1 — ConvTranspose2d layers: compile-time specialised pixel-shuffle epilogue, weights resident in shared memory
-  when 4 * cout <= 256, two CTAs per SM for the K = 64 layer.  Bit-identical to the default.
-* PNNP_IN_V2=1 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.  Bit-identical to the default.
-* PNNP_CONV_F32X2=1 — the specialised 3x3 epilogues' fp32 arithmetic in packed pairs (FADD2 / FFMA2: the same IEEE operations, 16-20 %
-  fewer epilogue instructions by SASS count).  Bit-identical to the default.  Built alone and together with SUPER + PDL.
-* PNNP_WGRAD_V2=1 — weight-gradient kernel with the producer / MMA warps' loop-invariant state in registers (per-stage loops 352 -> ~100
-  and 139 -> ~80 executed SASS instructions).  Same loads and MMAs: checked against autograd like the default kernel.
-* PNNP_E2E_ZERO_COPY=1 — HostSynthPipeline as ONE launch that reads / writes the pinned host buffers directly over PCIe.  Same result as
-  the chunked copy -> kernel -> copy pipeline, bit for bit (draws are keyed on global element indices).
-* PNNP_COPY_V2=1 — weight-packing / gradient re-layout copy with 32-bit index arithmetic (the kernel source is run on the CPU against NumPy
-  in tests/test_device_kernels_on_cpu.py); on the device: a training step gives the same loss and parameters.
-* PNNP_ACTBWD_V2=1 — activation backward + bias gradient with 32-bit item indices and no per-item modulo (csrc/actbwd_core.cuh; its phases
-  are run on the CPU against torch's bf16 arithmetic).  In-place gradient bit-identical to the default kernel, bias sums equal to
-  fp32 summation order.
-* PNNP_SSIM_V2=1 — separable 7x7 window sums in the eval epilogue (csrc/ssim_core.cuh; the same source is run phase by phase on the
-  CPU against the oracle in tests/test_device_kernels_on_cpu.py).  Equal to the default kernel's sums to float64 summation order.
-* PNNP_CONV_PDL=1 — conv layers launched with programmatic stream serialization (the kernel's prologue overlaps the previous
-  layer's tail; `griddepcontrol.wait` before the first global access).  Bit-identical to the default."""
+  output pixel sees the same MMAs in the same order as in the round-1 kernel, so the two must agree BIT FOR BIT — outputs,
+  fused max-pool, fused 1x1 head and the masked data-gradient epilogue alike.
+* PNNP_CONVT_FAST — ConvTranspose2d layers: compile-time specialised pixel-shuffle epilogue, weights resident in shared memory.
+* PNNP_IN_V2 — NCHW fp32 -> NHWC16 bf16 input conversion, four pixels per thread.
+* PNNP_CONV_F32X2 — the specialised 3x3 epilogues' fp32 arithmetic in packed pairs (FADD2 / FFMA2: the same IEEE operations).
+* PNNP_WGRAD_V2 — weight-gradient kernel with the producer / MMA warps' loop-invariant state in registers.
+* PNNP_E2E_ZERO_COPY=1 (still opt-in: measured slower, 9 854 against 10 314 MP/s) — HostSynthPipeline as ONE launch that reads /
+  writes the pinned host buffers directly over PCIe.
+* PNNP_COPY_V2 / PNNP_ACTBWD_V2 — 32-bit index arithmetic in the weight-packing copy / activation backward + bias gradient.
+* PNNP_SSIM_V2 — separable 7x7 window sums in the eval epilogue (equal to float64 summation order).
+* PNNP_CONV_PDL — conv layers launched with programmatic stream serialization (`griddepcontrol.wait` before the first global
+  access)."""
 import os
 
 import pytest
@@ -32,8 +26,18 @@ import torch
 import pnnp_b200 as P
 from pnnp_b200 import _lib, archs
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PNNP_TEST_EXPERIMENTAL") != "1", reason="experimental kernel variant: opt-in")]
+pytestmark = pytest.mark.gpu
+
+VARIANT_SWITCHES = ("PNNP_CONV_SUPER", "PNNP_CONVT_FAST", "PNNP_IN_V2", "PNNP_CONV_PDL", "PNNP_CONV_F32X2", "PNNP_WGRAD_V2",
+                    "PNNP_COPY_V2", "PNNP_ACTBWD_V2", "PNNP_SSIM_V2")
+
+
+@pytest.fixture(autouse=True)
+def _round1_kernels_as_baseline(monkeypatch):
+    """Every test starts from the round-1 kernels (all switches 0) and turns on what it examines."""
+    for name in VARIANT_SWITCHES:
+        monkeypatch.setenv(name, "0")
+    yield
 
 
 def _nhwc(t):
@@ -57,7 +61,7 @@ def _run(monkeypatch, sup, fn):
     if sup:
         monkeypatch.setenv("PNNP_CONV_SUPER", str(sup))
     else:
-        monkeypatch.delenv("PNNP_CONV_SUPER", raising=False)
+        monkeypatch.setenv("PNNP_CONV_SUPER", "0")
     out = fn()
     torch.cuda.synchronize()
     assert _lib.lib().pnnp_conv_pipeline_error() == 0, "tcgen05/TMA pipeline wait timed out"
@@ -126,7 +130,7 @@ def _run_env(monkeypatch, name, value, fn):
     if value:
         monkeypatch.setenv(name, str(value))
     else:
-        monkeypatch.delenv(name, raising=False)
+        monkeypatch.setenv(name, "0")
     out = fn()
     torch.cuda.synchronize()
     assert _lib.lib().pnnp_conv_pipeline_error() == 0, "tcgen05/TMA pipeline wait timed out"
@@ -199,8 +203,8 @@ def test_programmatic_dependent_launch_leaves_both_networks_unchanged(monkeypatc
             if sup:
                 monkeypatch.setenv("PNNP_CONV_SUPER", str(sup))
             got = [net(x).clone() for x in xs]
-            monkeypatch.delenv("PNNP_CONV_PDL")
-            monkeypatch.delenv("PNNP_CONV_SUPER", raising=False)
+            monkeypatch.setenv("PNNP_CONV_PDL", "0")
+            monkeypatch.setenv("PNNP_CONV_SUPER", "0")
         torch.cuda.synchronize()
         assert _lib.lib().pnnp_conv_pipeline_error() == 0
         assert all(torch.equal(a, b) for a, b in zip(got, want))
@@ -237,7 +241,7 @@ def test_packed_pair_epilogue_is_bit_identical(monkeypatch, combo):
             full = [net(frame).clone() for net in nets]
         return [out.view(torch.int16), pooled.view(torch.int16), hout, out2.view(torch.int16)] + full
     for k in ("PNNP_CONV_F32X2", "PNNP_CONV_SUPER", "PNNP_CONV_PDL"):
-        monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv(k, "0")
     want = call()
     for k, v in combo.items():
         monkeypatch.setenv(k, v)
@@ -253,7 +257,7 @@ def test_separable_ssim_equals_default_kernel(monkeypatch, shape, scale, correct
     g = torch.Generator(device="cuda").manual_seed(9)
     hr = torch.rand(shape, device="cuda", generator=g)
     dn = ((hr + 0.07 * torch.randn(shape, device="cuda", generator=g)) / scale).contiguous()
-    monkeypatch.delenv("PNNP_SSIM_V2", raising=False)
+    monkeypatch.setenv("PNNP_SSIM_V2", "0")
     want = eval_partial_sums(dn, hr, scale, correct).clone()
     monkeypatch.setenv("PNNP_SSIM_V2", "1")
     got = eval_partial_sums(dn, hr, scale, correct)
@@ -302,7 +306,7 @@ def test_copy_v2_training_step_is_unchanged(monkeypatch):
         if v2:
             monkeypatch.setenv("PNNP_COPY_V2", "1")
         else:
-            monkeypatch.delenv("PNNP_COPY_V2", raising=False)
+            monkeypatch.setenv("PNNP_COPY_V2", "0")
         torch.manual_seed(13)
         net = P.UNetSeeInDark({"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}).cuda()
         P.initialize_weights(net)
@@ -331,7 +335,7 @@ def test_act_backward_v2_equals_the_default_kernel(monkeypatch, act_kind):
             if v2:
                 monkeypatch.setenv("PNNP_ACTBWD_V2", "1")
             else:
-                monkeypatch.delenv("PNNP_ACTBWD_V2", raising=False)
+                monkeypatch.setenv("PNNP_ACTBWD_V2", "0")
             g = g0.clone()
             db = torch.full((c,), 0.25, device="cuda")
             _lib.check(L.pnnp_act_bwd_bias(g.data_ptr(), out.data_ptr(), db.data_ptr(), pixels, c, act_kind, _lib.stream_ptr(g.device)),

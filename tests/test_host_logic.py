@@ -189,3 +189,55 @@ def test_built_library_uses_tcgen05_tma_and_packed_fp32():
     assert re.search(r"LDG\.E\S*\.128", noise) and re.search(r"STG\.E\S*\.128", noise)      # 128-bit coalesced HBM loads and stores
     packed = [k for k in conv if k.endswith("ELi4EEEv14CUtensorMap_stS1_S1_NS_10ConvParamsE")]
     assert packed and all("FADD2" in conv[k] and "FFMA2" in conv[k] for k in packed)
+
+
+def test_bayer2rggb_rggb2bayer_true_rggb_order_and_round_trip():
+    """P3 (utils/isp_ops.py:57-63): HWC pack in TRUE RGGB order — R (0,0), G1 (0,1), G2 (1,0), B (1,1) — which differs from
+    raw2bayer's plane order R, G1, B, G2 (isp_ops.py:87-90); rggb2bayer is its inverse.  Checked against the index definition,
+    the oracle, and (build container) the live reference."""
+    import oracle_np as O
+    import ref_harness as rh
+    rs = np.random.RandomState(11)
+    for H, W, dt in ((4, 6, np.uint16), (64, 96, np.float32), (2, 2, np.int32)):
+        bayer = (rs.rand(H, W) * 16383).astype(dt)
+        rggb = P.bayer2rggb(bayer)
+        assert rggb.shape == (H // 2, W // 2, 4) and rggb.dtype == dt
+        for k, (dy, dx) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+            assert np.array_equal(rggb[..., k], bayer[dy::2, dx::2])
+        assert np.array_equal(P.rggb2bayer(rggb), bayer)
+        assert np.array_equal(rggb, O.bayer2rggb(bayer)) and np.array_equal(O.rggb2bayer(rggb), bayer)
+        if rh.available():
+            ISP = rh.load().isp_ops
+            assert np.array_equal(rggb, ISP.bayer2rggb(bayer)) and np.array_equal(P.rggb2bayer(rggb), ISP.rggb2bayer(rggb))
+    # not the same channel order as the packed planes raw2bayer produces: planes 2 and 3 are swapped
+    bayer = np.arange(16, dtype=np.float32).reshape(4, 4)
+    planes = O.raw2bayer(bayer, wp=1, bl=0, norm=False)
+    assert np.array_equal(planes[[0, 1, 3, 2]].transpose(1, 2, 0), P.bayer2rggb(bayer))
+
+
+def test_lr_of_the_kth_trained_epoch_matches_the_reference_scheduler_with_nonzero_last_epoch():
+    """trainer_SID.py:57,75,127 + base_trainer.py:131-138: LambdaScheduler (a LambdaLR whose get_lr returns lmbda(last_epoch)
+    itself) starts at -1 whatever hyper['last_epoch'] is.  With the reference PNNP.yml's resume settings (last_epoch 1200,
+    stop_epoch 1600, T 2) the first trained epoch must run at get_cos_lr(1), not get_cos_lr(1201) (cycle 6, lr / 64)."""
+    import torch
+    from torch.optim.lr_scheduler import LambdaLR
+    from pnnp_b200.utils import lr_for_epoch, lr_lambda_from_hyper
+
+    class LambdaScheduler(LambdaLR):                       # the reference's class, restated for the test
+        def get_lr(self):
+            return [lmbda(self.last_epoch) for lmbda, _ in zip(self.lr_lambdas, self.base_lrs)]
+
+    for last_epoch, stop_epoch, sched in ((1200, 1600, "WarmupCosine"), (0, 1600, "WarmupCosine"), (300, 700, "MultiStep")):
+        hyper = {"lr_scheduler": sched, "learning_rate": 1e-4, "last_epoch": last_epoch, "stop_epoch": stop_epoch,
+                 "step_size": 10, "T": 2}
+        lam = lr_lambda_from_hyper(hyper)
+        opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=hyper["learning_rate"])
+        sch = LambdaScheduler(opt, lam)
+        sch.step()                                         # top of train()
+        for epoch in range(last_epoch + 1, last_epoch + 260):
+            assert lr_for_epoch(lam, epoch, last_epoch) == sch.get_last_lr()[0], (sched, epoch)
+            opt.step()
+            sch.step()                                     # after each trained epoch
+    hyper = {"lr_scheduler": "WarmupCosine", "learning_rate": 1e-4, "last_epoch": 1200, "stop_epoch": 1600, "step_size": 10, "T": 2}
+    lam = lr_lambda_from_hyper(hyper)
+    assert lr_for_epoch(lam, 1201, 1200) == lam(1) and lam(1) > 32 * lam(1201)

@@ -173,6 +173,12 @@ def test_psnr_ssim_against_independent_implementations():
     assert O.ssim(a, b) == pytest.approx(np.mean(via_cv), abs=1e-12)
     assert O.ssim(a, b) == pytest.approx(np.mean(by_definition), abs=1e-10)
     assert 0.5 < O.ssim(a, b) < 0.9999
+    # the library's own float32 execution path (scikit-image keeps float32 images in float32) moves SSIM by far less than the
+    # four decimals the reference logs (trainer_SID.py:309-312)
+    assert abs(O.ssim(a, b) - O.ssim_float32_path(a, b)) < 5e-5
+    big_a = np.clip(rs.rand(256, 384, 4).astype(np.float32) * 255, 0, 255)
+    big_b = np.clip(big_a * 0.97 + rs.randn(256, 384, 4).astype(np.float32) * 3, 0, 255)
+    assert abs(O.ssim(big_a, big_b) - O.ssim_float32_path(big_a, big_b)) < 5e-5
 
 
 def test_eval_tiling_oracle_matches_reference_goldens(golden):
