@@ -4,8 +4,15 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
 Workloads (BASELINE.json configs; raw MP = Bayer samples = packed elements / 1e6):
-  synth64      configs[1] (DEFAULT, the headline): SonyA7S2 P-G/ELD noise synthesis 'pgrq' on 64
-               synthetic 4x512x512 packed crops per GPU; one step = one fused-kernel pass. HBM roofline.
+  path64       DEFAULT — the metric BASELINE.json names, "noise-synth + UNet denoise": configs[1]'s 64 synthetic 4x512x512
+               packed crops per GPU go through the fused SonyA7S2 'pgrq' noise synthesis AND the UNetSeeInDark forward
+               (PNNP.yml arch, reference init) that consumes them; one step = both.  `roofline` = the dominant kernel (the
+               tcgen05 conv kernel, tensor-core bound), `roofline_parts` = every part with its own CUDA-event time taken inside
+               the timed region (synth: HBM; unet: tensor) plus configs[2]'s training step (incl. the DDP gradient all-reduce
+               at N > 1) timed right after it.  e2e = pinned uint16 RAW crops in -> pack -> synthesis -> UNet -> PSNR/SSIM sums
+               out (+ the eval all-reduce of the sums at N > 1).
+  synth64      configs[1] alone: SonyA7S2 P-G/ELD noise synthesis 'pgrq' on 64 synthetic 4x512x512 packed crops per GPU;
+               one step = one fused-kernel pass. HBM roofline.
   unet_sony    configs[0] on the GPU: UNetSeeInDark (PNNP.yml arch, reference init) eval forward on one
                synthetic 4x1424x2128 frame per GPU per step. Tensor-core roofline.
   imx686_eval  configs[3]: UNetSeeInDark eval on synthetic 4x1736x2312 frames, reflect-pad 4 -> net ->
@@ -34,6 +41,11 @@ ARCH = dict(name="UNetSeeInDark", in_nc=4, out_nc=4, nf=32, nframes=1, use_dpsv=
             cascade=False, add=False, lock_wb=False)       # runfiles/SonyA7S2/PNNP.yml: arch
 
 WORKLOADS = {
+    "path64": dict(metric="raw megapixels/sec (noise synthesis + UNetSeeInDark denoise, 64x4x512x512 crops per GPU)", n=64, c=4,
+                   h=512, w=512, bound="tensor", dtype="bf16 tcgen05 (fp32 accumulate) UNet + f64 NumPy-chain synthesis",
+                   desc="path64 (BASELINE metric 'noise-synth+UNet denoise' on configs[1]'s crops): per GPU 64 crops of 4x512x512 "
+                        "-> fused SonyA7S2 'pgrq' noise synthesis (numpy float64 chain, Philox4x32-10) -> UNetSeeInDark nf=32 "
+                        "forward (configs[0]'s network, reference init, bf16 tcgen05)"),
     "synth64": dict(metric="raw megapixels/sec (noise synthesis, 64x4x512x512 crops per GPU)", n=64, c=4, h=512, w=512,
                     bound="hbm", dtype="f64",
                     desc="synth64 (BASELINE configs[1]): SonyA7S2 'pgrq' noise synthesis, 64 crops of 4x512x512 per GPU, "
@@ -199,8 +211,41 @@ def _cpu_train_steps(steps, threads, crops=2):
     return time.perf_counter() - t0, crops
 
 
+def _cpu_path_crops(crops, threads):
+    """The reference's CPU path for `crops` crops: per-crop generate_noisy_obs (NumPy, one thread) then the fp32 UNet forward
+    of the batch on `threads` torch threads.  Returns (synthesis seconds, forward seconds)."""
+    import numpy as np
+    import torch
+    O = _oracle()
+    import pnnp_b200 as P
+    torch.set_num_threads(threads)
+    torch.manual_seed(1997)
+    net = P.UNetSeeInDark(ARCH)
+    P.initialize_weights(net)
+    sd = net.state_dict()
+    rs = np.random.RandomState(7)
+    hr = rs.rand(crops, 4, 512, 512).astype(np.float32) ** 2
+    np.random.seed(3)
+    t0 = time.perf_counter()
+    lr = np.stack([np.clip(O.generate_noisy_obs(hr[i], param=O.sample_params("SonyA7S2"), noise_code=NOISE_CODE), None, 1.0)
+                   for i in range(crops)])
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(crops):
+            O.unet_forward(torch.from_numpy(lr[i:i + 1]), sd)
+    return t1 - t0, time.perf_counter() - t1
+
+
 def cpu_baseline(name, wl):
     cores = os.cpu_count() or 1
+    if name == "path64":
+        k = 4
+        _cpu_path_crops(1, cores)                                # warm-up (thread pools, oneDNN primitives)
+        ts, tu = _cpu_path_crops(k, cores)
+        return {"value": k * 4 * 512 * 512 / 1e6 / (ts + tu), "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{k} of 64 crops (4x512x512): oracle_np.generate_noisy_obs one crop after the other (NumPy / SciPy are "
+                          f"single-threaded: {ts / k * 1e3:.0f} ms per crop) + oracle_np.unet_forward on torch CPU fp32 with {cores} "
+                          f"threads ({tu / k * 1e3:.0f} ms per crop)"}
     if name == "synth64":
         t_start, n, busy = time.perf_counter(), 0, 0.0
         while n < 64 and (time.perf_counter() - t_start) < 12.0:
@@ -225,7 +270,40 @@ def run_reference_arm(args, name, wl):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    if name == "synth64":
+    if name == "path64":
+        # all host cores on both halves: synthesis of `workers` crops in `workers` processes (NumPy is single-threaded, this is the
+        # reference's DataLoader(num_workers) arrangement), then their fp32 UNet forwards on `cores` torch threads
+        import multiprocessing as mp
+        workers = max(1, min(cores, 16))
+        pool = mp.get_context("fork").Pool(workers)                # forked before torch starts its thread pools
+        import torch
+        O = _oracle()
+        import pnnp_b200 as P
+        torch.set_num_threads(cores)
+        torch.manual_seed(1997)
+        net = P.UNetSeeInDark(ARCH)
+        P.initialize_weights(net)
+        sd = net.state_dict()
+        x = torch.rand((1, 4, 512, 512))
+
+        def one_step(seed0):
+            pool.map(_cpu_synth_one_crop, [seed0 + i for i in range(workers)])
+            with torch.no_grad():
+                for _ in range(workers):
+                    O.unet_forward(x, sd)
+        for w in range(min(args.warmup, 1)):
+            one_step(w * workers)
+        steps = min(args.steps, 4)
+        t0 = time.perf_counter()
+        for s_ in range(steps):
+            one_step(5000 + s_ * workers)
+        dt = (time.perf_counter() - t0) * args.steps / steps
+        pool.close()
+        mp_step = workers * 4 * 512 * 512 / 1e6
+        sample = (f"{workers} of 64 crops per step ({steps} steps timed, scaled to {args.steps}): oracle port of generate_noisy_obs on "
+                  f"{workers} worker processes, then oracle_np.unet_forward per crop on torch CPU fp32 with {cores} threads")
+        used = cores
+    elif name == "synth64":
         import multiprocessing as mp
         workers = max(1, min(cores, 64))
         per_step = workers                                     # bounded sample: one crop per worker per step
@@ -258,7 +336,8 @@ def run_reference_arm(args, name, wl):
     print(json.dumps({
         "impl": "reference", "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64" if name == "synth64" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64" if name == "synth64" else ("f64 synthesis + f32 UNet" if name == "path64" else "f32"),
+        "data": "synthetic",
         "config": {"workload": wl["desc"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
@@ -319,7 +398,32 @@ def run_gpu_arm(args, name, wl):
     elems = n * c * h * w
     gen = P.PhiloxGenerator(1997)
     g = torch.Generator(device=device).manual_seed(1997 + rank)
-    if name == "synth64":
+    marks = []                                                                 # path64: per-step (start, after synthesis, after UNet) events
+    if name == "path64":
+        torch.manual_seed(1997)
+        net = P.UNetSeeInDark(ARCH).to(device).eval()
+        P.initialize_weights(net)
+        clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2      # dark-scene distribution
+        np.random.seed(1997 + rank)
+        params = [P.sample_params("SonyA7S2") for _ in range(n)]
+        table = P.ParamTable(params, device)
+        noisy = torch.empty_like(clean)
+        crop0 = rank * n
+
+        def step():
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            P.synthesize_batch(clean, None, NOISE_CODE, _lib.CHAIN_NUMPY, post_clip=(-float("inf"), 1.0),
+                               generator=gen, crop_id0=crop0, out=noisy, table=table)
+            ev[1].record()
+            with torch.no_grad():
+                net(noisy)
+            ev[2].record()
+            marks.append(ev)
+        algo = UNET_FLOP_PER_PIXEL * elems                                     # the dominant kernel's work: the UNet's FLOPs
+        l2_note = "no flush: 268 MB of crops in, 268 MB noisy out, 1.07 GB per full-resolution activation tensor: all exceed the 126 MB L2"
+        kernel = "conv_gemm_tc_kernel (the 23 conv launches of the UNet forward; share of the step in profiles/)"
+    elif name == "synth64":
         clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2      # dark-scene distribution
         np.random.seed(1997 + rank)
         params = [P.sample_params("SonyA7S2") for _ in range(n)]
@@ -399,6 +503,7 @@ def run_gpu_arm(args, name, wl):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    marks.clear()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = _lib.launch_count()
@@ -415,7 +520,35 @@ def run_gpu_arm(args, name, wl):
 
     # ---- end-to-end through the public host-buffer API (pinned host in, host result out)
     e2e_steps = max(3, min(args.steps, 20))
-    if name == "synth64":
+    parts = None
+    if name == "path64":
+        # per-part times taken INSIDE the timed region above (events between the synthesis launch and the UNet's launches)
+        synth_ms = allmax(sum(a.elapsed_time(b) for a, b, _ in marks) / len(marks))
+        unet_ms = allmax(sum(b.elapsed_time(c_) for _, b, c_ in marks) / len(marks))
+        parts = {"synth_ms": synth_ms, "unet_ms": unet_ms}
+        from pnnp_b200.pipeline import SynthDenoisePipeline
+        from pnnp_b200 import distributed as D
+        from pnnp_b200.metrics import finish_metrics
+        raw_dev = (512 + clean.reshape(n, c, h, w) * (16383 - 512)).round().clamp(0, 16383)       # sensor codes of the same crops
+        raw_host = torch.empty((n, 2 * h, 2 * w), dtype=torch.int16).pin_memory()
+        mosaic = torch.empty((n, 2 * h, 2 * w), device=device)
+        mosaic[:, 0::2, 0::2], mosaic[:, 0::2, 1::2] = raw_dev[:, 0], raw_dev[:, 1]              # R G1 / G2 B (isp_ops.py:87-90)
+        mosaic[:, 1::2, 1::2], mosaic[:, 1::2, 0::2] = raw_dev[:, 2], raw_dev[:, 3]
+        raw_host.copy_(mosaic.to(torch.int16).cpu())
+        del mosaic, raw_dev
+        pipe = SynthDenoisePipeline(net, n, 2 * h, 2 * w, 16383, 512, NOISE_CODE, device, chunk=int(os.environ.get("PNNP_E2E_CHUNK", "16")))
+        e2e_metrics = {}
+
+        def e2e_step():
+            sums = pipe.run(raw_host, table=table, generator=gen, crop_id0=crop0)
+            torch.cuda.current_stream().synchronize()            # the metric sums are on the host: the step's result
+            rows = finish_metrics(sums, c, h, w)
+            ps, ss = sum(r["PSNR"] for r in rows), sum(r["SSIM"] for r in rows)
+            e2e_metrics["psnr"], e2e_metrics["ssim"], e2e_metrics["crops"] = D.reduce_metric_sums(ps, ss, n, device)   # eval all-reduce
+        h2d, d2h = n * 2 * h * 2 * w * 2, n * 7 * 8
+        api = ("pnnp_b200.pipeline.SynthDenoisePipeline.run: pinned uint16 RAW crops in -> pack -> synthesis -> UNetSeeInDark -> "
+               "PSNR/SSIM partial sums out (+ one all-reduce of [sum PSNR, sum SSIM, count] per step at N > 1)")
+    elif name == "synth64":
         pipe = HostSynthPipeline(n, c, h, w, device, chunk=int(os.environ.get("PNNP_E2E_CHUNK", "8")),
                                  n_streams=int(os.environ.get("PNNP_E2E_STREAMS", "3")))
         host_in = torch.empty((n, c, h, w), dtype=torch.float32).pin_memory()
@@ -475,14 +608,53 @@ def run_gpu_arm(args, name, wl):
     torch.cuda.synchronize()
     e2e_value = world * elems / 1e6 / (allmax(time.perf_counter() - t0) / e2e_steps)
 
+    train_part = None
+    if name == "path64" and not args.no_parts:
+        # configs[2] right behind it: synthetic-pair training step on 8 of the crops per GPU (64 global at N = 8), CUDA-graph replay,
+        # the DDP gradient all-reduce inside the step at N > 1
+        from pnnp_b200.train import UNetTrainStep
+        torch.manual_seed(1997)
+        tnet = P.UNetSeeInDark(ARCH).to(device)
+        P.initialize_weights(tnet)
+        trainer = UNetTrainStep(tnet, lr=1e-4)
+        trainer.use_graph = os.environ.get("PNNP_TRAIN_GRAPH", "1") != "0"
+        tc_, tn_ = clean[:8].contiguous(), torch.empty((8, c, h, w), device=device)
+        t_losses = []
+
+        def train_step():
+            P.synthesize_batch(tc_, None, NOISE_CODE, _lib.CHAIN_NUMPY, post_clip=(-float("inf"), 1.0), generator=gen,
+                               crop_id0=crop0, out=tn_, table=table)
+            t_losses.append(trainer.step(tn_, tc_))
+        for _ in range(4):                                       # eager step, graph capture, replays
+            train_step()
+        barrier()
+        t_steps = max(5, min(args.steps, 20))
+        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        te0.record()
+        for _ in range(t_steps):
+            train_step()
+        te1.record()
+        barrier()
+        train_part = {"ms_per_step": allmax(te0.elapsed_time(te1)) / t_steps, "steps": t_steps, "crops_per_gpu": 8,
+                      "loss_first_last": [float(t_losses[0]), float(t_losses[-1])]}
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        if wl["bound"] == "hbm":
+        burst, sustained = float(peaks["bf16_tflops"]), float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        if name == "path64":
+            # the dominant kernel's own time inside the timed region; burst peak for a short timed region, sustained for a long one
+            timed_s = ms_step * args.steps / 1e3
+            peak, which = (sustained, "sustained cuBLAS bf16 (timed region >= 1 s)") if timed_s >= 1.0 else \
+                          (burst, f"burst cuBLAS bf16 (timed region {timed_s:.2f} s < 1 s)")
+            achieved, unit = algo / (parts["unet_ms"] / 1e3) / 1e12, "TFLOP/s"
+        elif wl["bound"] == "hbm":
             achieved, peak, unit = algo / (ms_step / 1e3) / 1e9, float(peaks["hbm_gbs"]), "GB/s"
             which = "burst copy"
         else:
             achieved, unit = algo / (ms_step / 1e3) / 1e12, "TFLOP/s"
-            peak, which = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), "sustained cuBLAS bf16 (kernels timed inside a multi-kernel step)"
+            timed_s = ms_step * args.steps / 1e3
+            peak, which = (sustained, "sustained cuBLAS bf16 (timed region >= 1 s)") if timed_s >= 1.0 else \
+                          (burst, f"burst cuBLAS bf16 (timed region {timed_s:.2f} s < 1 s)")
         line = {
             "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -495,6 +667,32 @@ def run_gpu_arm(args, name, wl):
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if unit == "TFLOP/s":
+            line["roofline"].update(frac_of_burst=achieved / burst, frac_of_sustained=achieved / sustained)
+        if name == "path64":
+            hbm = float(peaks["hbm_gbs"])
+            sy = elems * 8.0 / (parts["synth_ms"] / 1e3) / 1e9
+            tr = ncu_traffic("path64_parts") or {}
+            line["roofline"].update(frac_of_burst=achieved / burst, frac_of_sustained=achieved / sustained,
+                                    kernel_ms_per_step=parts["unet_ms"], traffic=tr.get("unet"))
+            line["roofline_parts"] = {
+                "synth": {"bound": "hbm", "kernel": "noise_synth_fast_kernel", "ms_per_step": parts["synth_ms"], "achieved": sy,
+                          "peak": hbm, "unit": "GB/s", "frac": sy / hbm, "algorithmic_work_per_step": elems * 8.0,
+                          "traffic": tr.get("synth")},
+                "unet": {"bound": "tensor", "kernel": "conv_gemm_tc_kernel x 23", "ms_per_step": parts["unet_ms"], "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "frac_of_burst": achieved / burst,
+                         "frac_of_sustained": achieved / sustained, "algorithmic_work_per_step": algo, "traffic": tr.get("unet")},
+            }
+            if train_part:
+                ta = UNET_TRAIN_FLOP_PER_PIXEL * 8 * c * h * w / (train_part["ms_per_step"] / 1e3) / 1e12
+                line["roofline_parts"]["train_step"] = dict(
+                    train_part, bound="tensor", kernel="conv_gemm_tc_kernel (fwd + dgrad) + wgrad_nhwc_kernel", achieved=ta, peak=burst,
+                    unit="TFLOP/s", frac=ta / burst, frac_of_sustained=ta / sustained,
+                    value_mp_s=world * 8 * c * h * w / 1e6 / (train_part["ms_per_step"] / 1e3),
+                    note="BASELINE configs[2]: synthesis + UNet fwd/bwd + Adam, CUDA-graph replay"
+                         + (f", DDP gradient all-reduce over {world} ranks inside the step" if world > 1 else ""))
+            line["e2e"]["eval_allreduce"] = {"ranks": world, "avg_psnr": e2e_metrics.get("psnr"), "avg_ssim": e2e_metrics.get("ssim"),
+                                             "crops": e2e_metrics.get("crops")}
         if name == "train_step":
             line["config"]["global_batch"] = world * n
             line["loss_first_last"] = [float(losses[0]), float(losses[-1])]
@@ -502,6 +700,8 @@ def run_gpu_arm(args, name, wl):
             line["cpu_baseline"] = cpu_baseline(name, wl)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if name == "path64" and train_part is not None:
+            name = "train_step"                                  # same teardown as the training workload (captured all-reduce)
         if name == "train_step":
             # A process group whose all-reduce was captured into live CUDA graphs did not shut down cleanly in the r01 8-GPU run
             # (destroy_process_group never returned after the JSON line was out): drop the graphs, meet at a barrier, and leave
@@ -522,8 +722,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pnnp_b200", choices=["pnnp_b200", "reference"])
-    ap.add_argument("--workload", default="synth64", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="path64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parts", action="store_true", help="path64: skip the training-step part")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -114,3 +114,59 @@ class EvalPipeline:
             sums = eval_partial_sums(dn, hr, scale, self.correct)
             self.h_sums[k].copy_(sums, non_blocking=True)
         return self.h_sums[k]
+
+
+class SynthDenoisePipeline:
+    """Host-buffer entry of the WHOLE hot path for a batch of crops — what one training / evaluation item of the reference
+    costs on the CPU side of its DataLoader plus its network call (data_process/syn_datasets.py:296-347 -> trainer_SID.py:221-248):
+
+        pinned uint16 RAW crops  --H2D-->  P1 raw2bayer(norm, clip)  ->  S2 + N1-N3 fused noise synthesis (+ the D1 post-clip)
+        ->  UNetSeeInDark / ResUnet forward (tcgen05)  ->  clamp + PSNR / SSIM partial sums against the clean crops
+        --D2H-->  (3 + c) float64 per crop in pinned host memory.
+
+    Only sensor codes go in (2 B per raw pixel) and only metric sums come out, so the PCIe bytes per raw pixel are a quarter of
+    HostSynthPipeline's float32 round trip.  The crops are processed in chunks: the H2D copy of chunk i + 1 (copy stream) overlaps the
+    kernels of chunk i.  bench.py times this call as `e2e` of the default workload."""
+
+    def __init__(self, net, n, H, W, wp, bl, noise_code, device=None, chunk=16, post_clip=(-float("inf"), 1.0), depth=2):
+        self.net, self.n, self.H, self.W, self.wp, self.bl = net, n, H, W, wp, bl
+        self.noise_code, self.post_clip = noise_code, post_clip
+        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.chunk = min(chunk, n)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.d_raw = [torch.empty((self.chunk, H, W), dtype=torch.int16, device=self.device) for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [torch.cuda.Event() for _ in range(depth)]
+        self.h_sums = torch.empty((n, 7), dtype=torch.float64).pin_memory()
+        self.slot = 0
+
+    def run(self, host_raw_i16, params=None, table=None, generator=None, crop_id0=0, seed_offset=None):
+        """host_raw_i16: pinned CPU int16 tensor (n, H, W) holding the uint16 sensor codes of n RAW crops; params: n reference-style
+        parameter dicts (or a ParamTable).  Returns the pinned (n, 3 + c) float64 tensor of partial sums (metrics.finish_metrics turns
+        a row into PSNR / SSIM), valid once the current stream has been synchronised."""
+        from .isp_ops import raw2bayer
+        from .metrics import eval_partial_sums
+        n = self.n
+        assert tuple(host_raw_i16.shape) == (n, self.H, self.W)
+        if table is None:
+            table = ParamTable(params, self.device)
+        if seed_offset is None:
+            seed_offset = (default_generator if generator is None else generator).next()
+        cur = torch.cuda.current_stream(self.device)
+        with torch.no_grad():
+            for s0 in range(0, n, self.chunk):
+                m = min(self.chunk, n - s0)
+                k = self.slot
+                self.slot = (self.slot + 1) % len(self.d_raw)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(self.consumed[k])            # the previous user of this slot has packed it
+                    self.d_raw[k][:m].copy_(host_raw_i16[s0:s0 + m], non_blocking=True)
+                    self.ready[k].record(self.copy_stream)
+                cur.wait_event(self.ready[k])
+                hr = raw2bayer(self.d_raw[k][:m], wp=self.wp, bl=self.bl, norm=True, clip=True)
+                self.consumed[k].record(cur)
+                lr = synthesize_batch(hr, None, self.noise_code, post_clip=self.post_clip, crop_id0=crop_id0 + s0, table=table,
+                                      table_row0=s0, seed_offset=seed_offset)
+                dn = self.net(lr)
+                self.h_sums[s0:s0 + m].copy_(eval_partial_sums(dn, hr, 1.0, False), non_blocking=True)
+        return self.h_sums
