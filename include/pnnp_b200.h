@@ -176,6 +176,13 @@ int pnnp_conv_pipeline_error(void);
 /* network input: NCHW fp32 (c <= 16) * scale -> NHWC bf16 zero-padded to 16 channels */
 int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, float scale,
                         void* stream);
+/* First layer fused with the pack boundary (archs/Unet.py:55 conv1_1, archs/ResUnet.py conv_in, fed by the packed planes that
+ * data_process/process.py:625-631 / utils/isp_ops.py:84-96 produce): NCHW fp32 input with cin <= 4 channels -> conv3x3 pad 1
+ * (weight: the module's own fp32 [cout][cin][3][3], rounded to bf16 in the kernel) + bias + activation (act: 0 none, 1 LeakyReLU
+ * 0.2, 2 ReLU) -> NHWC bf16 with cout in {16, 32, 48, 64} channels.  One launch instead of pnnp_nchw_to_nhwc16 + a 16-channel conv. */
+int pnnp_conv_first_nchw(const float* in, const float* weight, const float* bias, void* out, int n, int cin, int h, int w,
+                         int cout, int act, void* stream);
+int pnnp_conv_first_pipeline_error(void);
 /* nn.MaxPool2d(2) on NHWC bf16 (Unet.py:57) */
 int pnnp_maxpool2x2_nhwc(const void* in, void* out, int n, int h, int w, int c, void* stream);
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     "pnnp_conv2d_tc_ex": (_i, [C.POINTER(ConvDesc), _vp]),
     "pnnp_conv_pipeline_error": (_i, []),
     "pnnp_nchw_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "pnnp_conv_first_nchw": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pnnp_conv_first_pipeline_error": (_i, []),
     "pnnp_maxpool2x2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "pnnp_l1_loss": (_i, [_vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "pnnp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

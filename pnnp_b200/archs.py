@@ -119,6 +119,26 @@ def _to_nhwc16(x, out, scale=1.0):
     return out
 
 
+def _first_conv(x, module, out, act):
+    """First layer fused with the pack boundary (csrc/conv_first.cu): NCHW fp32 packed planes (<= 4 channels) -> conv3x3 + bias +
+    activation -> NHWC bf16, reading the module's own fp32 parameters (rounded to bf16 in the kernel, like the packed layers)."""
+    n, c, h, w = x.shape
+    wt, b = module.weight.detach(), module.bias
+    if wt.dtype != torch.float32 or not wt.is_contiguous():
+        wt = wt.float().contiguous()
+    b = None if b is None else b.detach().float().contiguous()
+    _lib.check(_lib.lib().pnnp_conv_first_nchw(x.data_ptr(), wt.data_ptr(), _lib.ptr(b), out.data_ptr(), n, c, h, w, wt.shape[0], act,
+                                               _lib.stream_ptr(x.device)), "conv_first_nchw")
+    return out
+
+
+_FUSED_FIRST = os.environ.get("PNNP_NO_FUSED_FIRST") is None
+
+
+def _use_first_conv(c, cout):
+    return _FUSED_FIRST and os.environ.get("PNNP_FUSED_FIRST", "1") != "0" and c <= 4 and cout % 16 == 0 and 16 <= cout <= 64
+
+
 class _TCNet(nn.Module):
     def _check_input(self, x):
         _lib.require_cuda(x, "network input")
@@ -189,12 +209,16 @@ class UNetSeeInDark(_TCNet):
         buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev)
         L = _lib.ACT_LEAKY
         with torch.cuda.device(dev):
-            cur = _to_nhwc16(x, buf("x16", h, w, 16))
+            fused_first = _use_first_conv(c, nf)                   # conv1_1 straight from the packed fp32 planes (csrc/conv_first.cu)
+            cur = None if fused_first else _to_nhwc16(x, buf("x16", h, w, 16))
             skips = []
             hh, ww = h, w
             for i in range(1, 6):                                  # encoder (Unet.py:55-69)
                 co = nf * 2 ** (i - 1)
-                t = self._conv3(f"conv{i}_1", cur, buf(f"c{i}a", hh, ww, co), co, L)
+                if i == 1 and fused_first:
+                    t = _first_conv(x, self.conv1_1, buf("c1a", hh, ww, co), L)
+                else:
+                    t = self._conv3(f"conv{i}_1", cur, buf(f"c{i}a", hh, ww, co), co, L)
                 if i < 5:                                          # conv + LeakyReLU + MaxPool2d(2) in one epilogue
                     pooled = buf(f"p{i}", hh // 2, ww // 2, co)
                     skips.append(self._conv3(f"conv{i}_2", t, buf(f"c{i}", hh, ww, co), co, L, pool_out=pooled))
@@ -300,9 +324,12 @@ class ResUnet(_TCNet):
             return _conv(_lib.CONV3, t, w2, None, buf(f"b{i}", hh, ww, co), co, _lib.ACT_NONE, resid=shortcut)
 
         with torch.cuda.device(dev):
-            x16 = _to_nhwc16(x, buf("x16", h, w, 16))
-            wi, bi = self._packed("conv_in")
-            cur = _conv(_lib.CONV3, x16, wi, bi, buf("cin", h, w, nf), nf, _lib.ACT_RELU)
+            if _use_first_conv(c, nf):                             # conv_in straight from the packed fp32 planes
+                cur = _first_conv(x, self.conv_in, buf("cin", h, w, nf), _lib.ACT_RELU)
+            else:
+                x16 = _to_nhwc16(x, buf("x16", h, w, 16))
+                wi, bi = self._packed("conv_in")
+                cur = _conv(_lib.CONV3, x16, wi, bi, buf("cin", h, w, nf), nf, _lib.ACT_RELU)
             skips, hh, ww = [], h, w
             for i in range(1, 6):
                 co = nf * 2 ** (i - 1)

@@ -158,7 +158,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #define PNNP_SWZ_K (kCt ? 32 * K16S : p.swz)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x stage_bytes] [barriers] [tmem slot] [bias]
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by POINTER arithmetic on the __shared__ array (not through an integer cast): the compiler keeps the
+    // shared address space of everything carved from it, so plain loads / stores of these pointers are LDS / STS instead of
+    // generic LD / ST (which go through the global-memory instruction queue: stall reason lg_throttle in the r02 capture)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_bres = smem + (size_t)p.stages * p.stage_bytes;          // resident weights (1024-aligned), may be empty
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bres + p.b_res_bytes);
     uint64_t* full_bar = bars;                       // [stages]

@@ -84,6 +84,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols));
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+// generic-proxy shared-memory writes (st.shared by threads) -> visible to the async proxy (tcgen05.mma / TMA reading shared memory)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // programmatic dependent launch: wait for the previous grid of the stream, then let the next one be scheduled
 __device__ __forceinline__ void pdl_wait_then_release() {

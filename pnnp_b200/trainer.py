@@ -29,7 +29,7 @@ from .datasets import Raw_Dataset, Synthetic_ELD_Dataset, Synthetic_IMX686_Datas
 from .metrics import eval_partial_sums, finish_metrics
 from .noise import synthesize_batch
 from .noise_params import HALF_CLIP, sample_params_max
-from .utils import AverageMeter, load_weights, log, lr_for_epoch, lr_lambda_from_hyper, tensor_dim5to4
+from .utils import AverageMeter, PhaseTimer, load_weights, log, lr_for_epoch, lr_lambda_from_hyper, tensor_dim5to4
 
 
 class BaseParser():
@@ -261,6 +261,7 @@ class SID_Trainer(Base_Trainer):
         step = UNetTrainStep(self.net, lr=lr_lambda(1))
         self.train_psnr = AverageMeter('PSNR', ':2f')
         bs = int(self.hyper['batch_size'])
+        phases = PhaseTimer(self.device)          # dataloader / preprocess / net+bp, as trainer_SID.py:81-123 splits a step
         for epoch in range(self.hyper['last_epoch'] + 1, self.hyper['stop_epoch'] + 1):
             self.net.train()
             self.train_psnr.reset()
@@ -273,12 +274,16 @@ class SID_Trainer(Base_Trainer):
             per_rank = -(-len(batches) // self.world_size)             # every rank takes the same number of steps (the
             for j in range(per_rank):                                   # gradient all-reduce is collective); wrap around
                 k = (self.rank * per_rank + j) % len(batches)
+                phases.start('dataloader')                              # device-built items: pack + crop/aug (+ CPU-route synthesis)
                 items = [self.dst_train[int(i)] for i in batches[k]]
                 imgs_lr = torch.cat([it['lr'] for it in items]).contiguous()
                 imgs_hr = torch.cat([it['hr'] for it in items]).contiguous()
+                phases.start('preprocess')                              # GPU-route synthesis + clamps (trainer_SID.py:449-485)
                 if dst_args['gpu_preprocess'] is not False:
                     imgs_lr, imgs_hr = self.preprocess_train(imgs_lr, imgs_hr, dst_args)
+                phases.start('net+bp')                                  # forward, L1, backward, all-reduce, Adam: one graph replay
                 losses.append(step.step(imgs_lr, imgs_hr))
+                phases.stop()
             if losses:
                 with torch.no_grad():                                   # PSNR of the last batch, as the progress bar shows
                     mse = (step.scr.bufs['pred'].clamp(0, 1) - imgs_hr.clamp(0, 1)).pow(2).mean()
@@ -286,6 +291,10 @@ class SID_Trainer(Base_Trainer):
             if self.rank == 0:
                 mean_loss = float(torch.stack(losses).mean()) if losses else float('nan')
                 log(f"Epoch {epoch}: lr={step.lr:.2e}, L1={mean_loss:.5f}, PSNR={self.train_psnr.avg:.2f}", log=self.logfile)
+            rt = phases.summary()                                       # every rank: summary() synchronises the device
+            if self.rank == 0 and rt:
+                log("runtime (device ms | host ms): " + ", ".join(f"{k}={d:.1f}|{h:.1f}" for k, (d, h) in rt.items()),
+                    log=self.logfile)
             if epoch % self.hyper['save_freq'] == 0 and self.rank == 0:
                 epoch_id = epoch // self.hyper['plot_freq'] * self.hyper['plot_freq']
                 torch.save(_detached_state(self.net), os.path.join(self.model_dir, '%s_e%04d.pth' % (self.model_name, epoch_id)))

@@ -106,3 +106,48 @@ def lr_for_epoch(lr_lambda, epoch, last_epoch):
     its constructor, once at the top of train() (trainer_SID.py:75) and once after every trained epoch (:127), and returns
     lmbda(last_epoch) itself: the k-th trained epoch runs at lr_lambda(k), k = epoch - hyper['last_epoch']."""
     return lr_lambda(epoch - last_epoch)
+
+
+class PhaseTimer:
+    """The reference's per-step split `dataloader / preprocess / net / bp` (trainer_SID.py:81-123: wall-clock stamps without a
+    synchronize, so its GPU phases are launch-side only) with device time: every phase is an NVTX range (visible in Nsight Systems /
+    `ncu --nvtx`) bracketed by CUDA events on the current stream; `summary()` resolves the events once per epoch, so the loop itself
+    never synchronises.  Host-only phases (no kernels in between) read as ~0 device time and are reported by wall clock too."""
+
+    def __init__(self, device=None, enabled=True):
+        import torch
+        self.torch, self.device, self.enabled = torch, device, enabled and torch.cuda.is_available()
+        self.events, self.wall, self._open = {}, {}, None
+
+    def start(self, name):
+        import time as _t
+        self.stop()
+        if not self.enabled:
+            return
+        t = self.torch
+        t.cuda.nvtx.range_push(name)
+        e0 = t.cuda.Event(enable_timing=True)
+        e0.record()
+        self._open = (name, e0, _t.perf_counter())
+
+    def stop(self):
+        import time as _t
+        if self._open is None:
+            return
+        name, e0, w0 = self._open
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.torch.cuda.nvtx.range_pop()
+        self.events.setdefault(name, []).append((e0, e1))
+        self.wall[name] = self.wall.get(name, 0.0) + (_t.perf_counter() - w0)
+        self._open = None
+
+    def summary(self):
+        """{phase: (device ms, host wall ms)} accumulated since the last call; clears the accumulators."""
+        self.stop()
+        if not self.enabled:
+            return {}
+        self.torch.cuda.synchronize(self.device)
+        out = {k: (sum(a.elapsed_time(b) for a, b in v), self.wall.get(k, 0.0) * 1e3) for k, v in self.events.items()}
+        self.events, self.wall = {}, {}
+        return out

@@ -213,6 +213,7 @@ static inline void tc_fence_after() {}
 static inline void tc_ld_wait() {}
 static inline void prefetch_tensormap(const CUtensorMap*) {}
 static inline void fence_mbarrier_init() {}
+static inline void fence_proxy_async() {}
 static inline void pdl_wait_then_release() {}
 static inline void tmem_alloc(uint32_t slot, uint32_t cols) {
     if (cols < 32 || cols > 512 || (cols & (cols - 1))) tc_model_fail("tcgen05.alloc: column count must be a power of two in [32, 512]");

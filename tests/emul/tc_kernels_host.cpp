@@ -20,6 +20,7 @@ void count_launch(uint64_t n) { g_launches += n; }
 
 #include "../../pnnp_b200/csrc/conv_tc.cu"
 #include "../../pnnp_b200/csrc/wgrad_nhwc_tc.cu"
+#include "../../pnnp_b200/csrc/conv_first.cu"
 
 extern "C" {
 int emul_conv2d_tc_ex(const pnnp_conv_desc* d) { return pnnp::conv_layer_launch(*d, nullptr); }
@@ -30,6 +31,10 @@ int emul_wgrad_nhwc(int mode, const void* g, int co, int co_stride, const void* 
     return pnnp_wgrad_nhwc(mode, g, co, co_stride, x, ci, ci_stride, n, h, w, dw, ci_off, ci_total, co_pad, nullptr);
 }
 int emul_wgrad_pipeline_error(void) { return pnnp_wgrad_nhwc_pipeline_error(); }
+int emul_conv_first_nchw(const float* in, const float* w, const float* b, void* out, int n, int cin, int h, int wd, int cout, int act) {
+    return pnnp_conv_first_nchw(in, w, b, out, n, cin, h, wd, cout, act, nullptr);
+}
+int emul_conv_first_pipeline_error(void) { return pnnp_conv_first_pipeline_error(); }
 // counters of the model since the last call: [mma instructions, TMA loads, zero-filled elements, mbarrier waits]
 unsigned long emul_tc_trailing_commits(void) { const unsigned long v = pnnp::g_trailing_commits; pnnp::g_trailing_commits = 0; return v; }
 void emul_tc_stats(unsigned long* out4) {

@@ -51,7 +51,7 @@ def libs():
         pytest.skip("g++ not available")
     shim = [os.path.join(EMUL, f) for f in ("cuda_host_shim.h", "simt_host.h", "tc_host_model.h")]
     tc = _build("libtc_kernels_host.so", "tc_kernels_host.cpp",
-                shim + [os.path.join(CSRC, f) for f in ("conv_tc.cu", "tc_common.cuh", "abi_common.h")] + [os.path.join(ROOT, "include", "pnnp_b200.h")])
+                shim + [os.path.join(CSRC, f) for f in ("conv_tc.cu", "conv_first.cu", "tc_common.cuh", "abi_common.h")] + [os.path.join(ROOT, "include", "pnnp_b200.h")])
     tc.emul_tc_last_error.restype = C.c_char_p
     k = _build("libkernels_host.so", "kernels_host.cpp", shim[:1] + [os.path.join(CSRC, f) for f in ("layout_kernels.cuh", "copy_kernels.cuh")])
     sk = _build("libsimt_kernels_host.so", "simt_kernels_host.cpp", shim[:2] + [os.path.join(CSRC, f) for f in ("train_kernels.cuh", "actbwd_core.cuh", "noise_kernels.cuh", "eval_kernels.cuh", "hbr_kernels.cuh")])
@@ -176,6 +176,10 @@ class _EmulatedLibrary:
         self.launches += 1
         return self.k.emul_wb_gains(C.c_void_p(data), n, c, h, w, C.c_float(rgb_gain), kind, gain, 3, 128)
 
+    def pnnp_conv_first_nchw(self, src, wt, b, dst, n, cin, h, w, cout, act, stream):
+        self.launches += 1
+        return self.tc.emul_conv_first_nchw(C.c_void_p(src), C.c_void_p(wt), C.c_void_p(b), C.c_void_p(dst), n, cin, h, w, cout, act)
+
     def pnnp_nchw_to_nhwc16(self, src, dst, n, c, h, w, scale, stream):
         v2 = int(os.environ.get("PNNP_IN_V2", "1") != "0" and (h * w) % 4 == 0)
         return self.k.emul_nchw_to_nhwc16(C.c_void_p(src), C.c_void_p(dst), n, c, h, w, C.c_float(scale), v2, 3, 256)
@@ -254,6 +258,41 @@ def test_conv3x3_layer_vs_torch(emu, cin, cout, h, w, n, act):
     ref = F.conv2d(_bf(x), _bf(wt), b, padding=1)
     ref = F.leaky_relu(ref, 0.2) if act == 1 else (F.relu(ref) if act == 2 else ref)
     assert (_nchw(out) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n,act", [(4, 32, 16, 32, 1, 1), (4, 32, 21, 45, 2, 2), (3, 16, 9, 17, 1, 0), (4, 64, 24, 16, 1, 1), (1, 48, 8, 40, 1, 1)])
+def test_fused_first_layer_vs_torch(emu, cin, cout, h, w, n, act):
+    """csrc/conv_first.cu (NCHW fp32 packed planes -> im2col in shared memory -> three K16 MMAs -> bias + activation -> NHWC bf16)
+    against torch on bf16-rounded operands: ragged tile edges, 1..4 input channels, every output width, every activation; and
+    the whole-network forwards (UNetSeeInDark conv1_1, ResUnet conv_in) equal the unfused path's to bf16 rounding."""
+    g = torch.Generator().manual_seed(cin * 100 + cout + h)
+    x = torch.randn((n, cin, h, w), generator=g)
+    m = torch.nn.Conv2d(cin, cout, 3, padding=1)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn((cout, cin, 3, 3), generator=g) / (3 * cin ** 0.5))
+        m.bias.copy_(torch.randn((cout,), generator=g) * 0.1)
+    out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16)
+    archs._first_conv(x.contiguous(), m, out, act)
+    ref = F.conv2d(_bf(x), _bf(m.weight.detach()), m.bias.detach(), padding=1)
+    ref = F.leaky_relu(ref, 0.2) if act == 1 else (F.relu(ref) if act == 2 else ref)
+    assert not torch.isnan(out.float()).any()
+    assert (_nchw(out) - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_fused_first_layer_leaves_the_network_forwards_unchanged(emu, monkeypatch):
+    import pnnp_b200 as P
+    torch.manual_seed(8)
+    arch = {"in_nc": 4, "out_nc": 4, "nf": 32, "nframes": 1, "res": False}
+    x = torch.rand((1, 4, 48, 64))
+    for cls in (P.UNetSeeInDark, P.ResUnet):
+        net = cls(arch).eval()
+        P.initialize_weights(net)
+        with torch.no_grad():
+            monkeypatch.setenv("PNNP_FUSED_FIRST", "0")
+            want = net(x).clone()
+            monkeypatch.setenv("PNNP_FUSED_FIRST", "1")
+            got = net(x).clone()
+        assert (got - want).abs().max().item() < 2e-4 * max(1e-2, want.abs().max().item()), cls.__name__
 
 
 def test_two_sources_transposed_1x1_stride2_and_residual_modes_vs_torch(emu):

@@ -39,6 +39,7 @@ def _pack(w, kind="conv"):
 def _no_pipeline_error():
     torch.cuda.synchronize()
     assert _lib.lib().pnnp_conv_pipeline_error() == 0, "tcgen05/TMA pipeline wait timed out"
+    assert _lib.lib().pnnp_conv_first_pipeline_error() == 0, "first-layer kernel: MMA completion wait timed out"
 
 
 @pytest.mark.parametrize("cin,cout,h,w,n", [(16, 32, 16, 32, 1), (32, 32, 24, 40, 2), (64, 64, 32, 48, 1),
@@ -303,3 +304,42 @@ def test_full_frame_forward_vs_cpu_fp32_oracle(arch_name, shape, reflect):
     target = torch.rand(want.shape, generator=torch.Generator().manual_seed(3))
     psnr = lambda a: 10 * torch.log10(1.0 / ((a.clamp(0, 1) - target) ** 2).mean())
     assert abs(psnr(got.cpu()).item() - psnr(want).item()) < 0.01           # PSNR +- 0.01 dB on the same inputs
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n,act", [(4, 32, 16, 32, 1, _lib.ACT_LEAKY), (4, 32, 21, 45, 2, _lib.ACT_RELU), (3, 16, 9, 17, 1, _lib.ACT_NONE),
+                                                (4, 64, 24, 16, 1, _lib.ACT_LEAKY), (1, 48, 8, 40, 1, _lib.ACT_LEAKY),
+                                                (4, 32, 512, 512, 3, _lib.ACT_LEAKY), (4, 32, 1424, 2128, 1, _lib.ACT_LEAKY)])
+def test_fused_first_layer(cin, cout, h, w, n, act):
+    """csrc/conv_first.cu — packed NCHW fp32 planes -> conv3x3 + bias + activation -> NHWC bf16 in one launch (the pack boundary
+    fused into the first layer: process.py:625-631 -> Unet.py:55) — against torch on the bf16-rounded operands, ragged tile edges
+    and the BASELINE crop / frame shapes included."""
+    g = torch.Generator(device="cuda").manual_seed(cin * 100 + cout + h)
+    x = torch.randn((n, cin, h, w), device="cuda", generator=g)
+    m = torch.nn.Conv2d(cin, cout, 3, padding=1).cuda()
+    with torch.no_grad():
+        m.weight.copy_(torch.randn((cout, cin, 3, 3), device="cuda", generator=g) / (3 * cin ** 0.5))
+        m.bias.copy_(torch.randn((cout,), device="cuda", generator=g) * 0.1)
+    out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    archs._first_conv(x, m, out, act)
+    _no_pipeline_error()
+    ref = F.conv2d(_bf(x), _bf(m.weight.detach()), m.bias.detach(), padding=1)
+    ref = F.leaky_relu(ref, 0.2) if act == _lib.ACT_LEAKY else (F.relu(ref) if act == _lib.ACT_RELU else ref)
+    assert not torch.isnan(out.float()).any()
+    assert (_nchw(out) - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_fused_first_layer_equals_the_two_kernel_path(monkeypatch):
+    """Same operands, same products: the fused first layer and input conversion + general conv kernel agree to the accumulation
+    order of 36 fp32 terms (bf16 outputs equal except for isolated last-bit roundings), and so do the network outputs."""
+    torch.manual_seed(8)
+    x = torch.rand((2, 4, 208, 272), device="cuda")
+    for cls in (P.UNetSeeInDark, P.ResUnet):
+        net = cls(_arch()).cuda().eval()
+        P.initialize_weights(net)
+        with torch.no_grad():
+            monkeypatch.setenv("PNNP_FUSED_FIRST", "0")
+            want = net(x).clone()
+            monkeypatch.setenv("PNNP_FUSED_FIRST", "1")
+            got = net(x).clone()
+        _no_pipeline_error()
+        assert (got - want).abs().max().item() < 2e-3 * want.abs().max().item(), cls.__name__      # bf16 rounding flips of the first layer, propagated

@@ -10,7 +10,7 @@ arch = dict(name="UNetSeeInDark", in_nc=4, out_nc=4, nf=32, nframes=1, use_dpsv=
 net = P.UNetSeeInDark(arch).cuda().eval(); P.initialize_weights(net)
 x = torch.rand(shape, device="cuda")
 records = []
-orig_conv, orig_pool, orig_in = archs._conv, archs._pool, archs._to_nhwc16
+orig_conv, orig_pool, orig_in, orig_first = archs._conv, archs._pool, archs._to_nhwc16, archs._first_conv
 def timed(fn, label):
     def w(*a, **k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,12 +30,14 @@ with torch.no_grad():
     archs._conv = timed(orig_conv, conv_label)
     archs._pool = timed(orig_pool, lambda a, k: ("pool", f"{a[0].shape[3]} @{a[0].shape[1]}x{a[0].shape[2]}", 0.0))
     archs._to_nhwc16 = timed(orig_in, lambda a, k: ("in", "", 0.0))
+    archs._first_conv = timed(orig_first, lambda a, k: ("first", f"{a[0].shape[1]}->{a[1].weight.shape[0]} @{a[0].shape[2]}x{a[0].shape[3]} (fused in+conv)",
+                                                        2.0 * a[0].shape[0] * a[0].shape[2] * a[0].shape[3] * a[0].shape[1] * a[1].weight.shape[0] * 9))
     net(x); torch.cuda.synchronize()
     tot = 0.0
     for (kind, desc, fl), e0, e1 in records:
         ms = e0.elapsed_time(e1); tot += ms
-        print(f"{kind:6s} {desc:28s} {ms*1e3:9.1f} us  {fl/ms/1e9 if ms>0 else 0:8.1f} TFLOP/s")
-    archs._conv, archs._pool, archs._to_nhwc16 = orig_conv, orig_pool, orig_in
+        print(f"{kind:6s} {desc:44s} {ms*1e3:9.1f} us  {fl/ms/1e9 if ms>0 else 0:8.1f} TFLOP/s")
+    archs._conv, archs._pool, archs._to_nhwc16, archs._first_conv = orig_conv, orig_pool, orig_in, orig_first
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10): net(x)
