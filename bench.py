@@ -443,8 +443,8 @@ def run_gpu_arm(args, name, wl):
         net = P.UNetSeeInDark(ARCH).to(device)
         P.initialize_weights(net)
         trainer = UNetTrainStep(net, lr=1e-4)
-        trainer.use_graph = os.environ.get("PNNP_TRAIN_GRAPH", "1") != "0"     # CUDA-graph replay of the step at every N (8 ranks
-        clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2     # launching eagerly from one host: 6.4 ms; replayed: 5.2)
+        clean = torch.rand((n, c, h, w), device=device, generator=g) ** 2     # (CUDA-graph replay at every N: 8 ranks launching eagerly
+                                                                              # from one host take 6.4 ms per step, replayed 5.2)
         np.random.seed(1997 + rank)
         params = [P.sample_params("SonyA7S2") for _ in range(n)]
         table = P.ParamTable(params, device)
@@ -617,7 +617,6 @@ def run_gpu_arm(args, name, wl):
         tnet = P.UNetSeeInDark(ARCH).to(device)
         P.initialize_weights(tnet)
         trainer = UNetTrainStep(tnet, lr=1e-4)
-        trainer.use_graph = os.environ.get("PNNP_TRAIN_GRAPH", "1") != "0"
         tc_, tn_ = clean[:8].contiguous(), torch.empty((8, c, h, w), device=device)
         t_losses = []
 
@@ -700,20 +699,20 @@ def run_gpu_arm(args, name, wl):
             line["cpu_baseline"] = cpu_baseline(name, wl)
         print(json.dumps(line), flush=True)
     if world > 1:
-        if name == "path64" and train_part is not None:
-            name = "train_step"                                  # same teardown as the training workload (captured all-reduce)
-        if name == "train_step":
-            # A process group whose all-reduce was captured into live CUDA graphs did not shut down cleanly in the r01 8-GPU run
-            # (destroy_process_group never returned after the JSON line was out): drop the graphs, meet at a barrier, and leave
-            # without the NCCL teardown.
-            trainer._graphs.clear()
-            torch.cuda.synchronize()
-            sys.stdout.flush()
-            sys.stderr.flush()
-            dist.barrier()
-            torch.cuda.synchronize()
-            os._exit(0)
+        # Teardown.  Graphs that captured all-reduces go first (r01: destroy_process_group() never returned with them alive; r02,
+        # tools/ddp_check.py: 0.5 s once they are dropped); a watchdog still ends the process if NCCL hangs, after the JSON line.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if "trainer" in locals():
+            trainer.close()
+        torch.cuda.synchronize()
+        watchdog = threading.Timer(60.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def main():

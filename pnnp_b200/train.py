@@ -87,11 +87,10 @@ class UNetTrainStep:
         # learning rate and step count in device memory: the whole step is replayed as one CUDA graph (see step())
         self.adam_state = torch.tensor([float(lr), 0.0], dtype=torch.float32, device=self.device)
         self._lr = float(lr)
-        # CUDA-graph replay of the step: on by default for a single process; under torch.distributed the captured all-reduce works
-        # (r01, 8 GPUs: 5.2 ms against 6.4 ms eager) but the process group then has to be left without destroy_process_group
-        # (bench.py does), so multi-rank callers opt in with PNNP_TRAIN_GRAPH=1 or `step.use_graph = True`
-        env = os.environ.get("PNNP_TRAIN_GRAPH")
-        self.use_graph = (env != "0") if env is not None else (D.world()[1] == 1)
+        # CUDA-graph replay of the step, single process and DDP alike (the bucketed all-reduces are captured with it).  Before the
+        # process group is destroyed the graphs have to go (close()): r01's destroy_process_group() never returned with captured
+        # all-reduces alive; with the graphs dropped first it returns in 0.5 s (r02, tools/ddp_check.py).  PNNP_TRAIN_GRAPH=0: eager.
+        self.use_graph = os.environ.get("PNNP_TRAIN_GRAPH", "1") != "0"
         self._graphs = {}
         # flat fp32 parameter / gradient / moment buffers; the module's parameters become views of the flat buffer
         params = list(net.named_parameters())
@@ -109,20 +108,50 @@ class UNetTrainStep:
         self.sync_parameters()
         self.scr = _Scratch(self.device)
         self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
-        # weight-gradient scratch of every layer ([taps][ci_pad16][co] fp32, the layout the wgrad kernel adds into with
-        # coalesced reds) carved out of ONE buffer: a single memset per step
-        self.dw, total_dw = {}, 0
-        for name, m in net.named_modules():
+        # Gradient scratch of every layer, carved out of ONE buffer (a single memset per step) IN BACKWARD ORDER, so that what the
+        # backward pass finishes first lies first: [taps][ci_pad16][co] fp32 weight gradient (the layout the wgrad kernel adds into
+        # with coalesced reds) followed by the layer's [co] bias gradient; the 1x1 head (weight [out_nc][nf] + bias) leads.  Under
+        # DDP the buffer is all-reduced in contiguous BUCKETS while the rest of the backward pass still runs (SURVEY 8e:
+        # "bucketed and overlapped with backward"); `unpack` then scatters it into the parameters' own layout in flat_g.
+        mods = dict(net.named_modules())
+        order = ["conv10_1"]
+        for i in range(9, 5, -1):
+            order += [f"conv{i}_2", f"conv{i}_1", f"upv{i}"]
+        for i in range(5, 0, -1):
+            order += [f"conv{i}_2", f"conv{i}_1"]
+        self.dw, self.db, total_dw = {}, {}, 0
+        for name in order:
+            m = mods[name]
             if isinstance(m, torch.nn.ConvTranspose2d):
                 shape = (4, m.weight.shape[0], m.weight.shape[1])
-            elif isinstance(m, torch.nn.Conv2d) and m.kernel_size == (3, 3):
+            elif m.kernel_size == (3, 3):
                 shape = (9, _pad16(m.weight.shape[1]), m.weight.shape[0])
             else:
-                continue
+                shape = (1, m.weight.shape[0], m.weight.shape[1])                 # conv10_1: [1][out_nc][nf], the parameter's own layout
             self.dw[name] = (total_dw, shape)
             total_dw += shape[0] * shape[1] * shape[2]
+            if m.bias is not None:
+                self.db[name] = (total_dw, m.bias.numel())
+                total_dw += (m.bias.numel() + 3) // 4 * 4                         # keep every region 16-byte aligned
         self.dw_flat = torch.zeros(total_dw, dtype=torch.float32, device=self.device)
+        # bucket = contiguous slice of dw_flat closed by the layer whose gradients complete it (~5-9 MB each; the last, tiny one is
+        # the only part of the reduction that cannot overlap with anything)
+        closers = ("conv6_2", "upv6", "conv5_2", "conv4_1", "conv1_1")
+        self.buckets, start = {}, 0
+        for name in order:
+            if name in closers:
+                end = (self.db[name][0] + (self.db[name][1] + 3) // 4 * 4) if name in self.db else self.dw[name][0] + \
+                    self.dw[name][1][0] * self.dw[name][1][1] * self.dw[name][1][2]
+                self.buckets[name] = (start, end)
+                start = end
+        assert start == total_dw
+        self.comm_stream = torch.cuda.Stream(self.device) if D.world()[1] > 1 else None
         self._build_copy_tables()
+
+    def close(self):
+        """Drop the captured graphs (they hold NCCL work under DDP) — call before torch.distributed.destroy_process_group()."""
+        self._graphs.clear()
+        torch.cuda.synchronize(self.device)
 
     def sync_parameters(self, src=0):
         """Every rank starts from (and, after a checkpoint reload, continues from) rank `src`'s parameters, as the
@@ -186,6 +215,12 @@ class UNetTrainStep:
                                           (buf.shape[1] * buf.shape[2], buf.shape[2], 1)))
                     self.wd[(name, k)] = buf
                     c_off += ck
+        for layer, (off, nb) in self.db.items():            # bias gradients: reduce buffer -> flat gradient buffer
+            src = self.dw_flat.data_ptr() + 4 * off
+            unpack.append(_desc(src, self.flat_g.data_ptr() + 4 * self.slices[layer + ".bias"][0], 0, (nb,), (1,), (1,)))
+        n10 = self.slices["conv10_1.weight"][1]              # 1x1 head weight gradient: same layout on both sides
+        unpack.append(_desc(self._dw_view("conv10_1").data_ptr(), gp("conv10_1"), 0, (n10,), (1,), (1,)))
+
         def table(descs):
             arr = (_lib.CopyDesc * len(descs))(*descs)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -206,8 +241,27 @@ class UNetTrainStep:
 
     # ---------------------------------------------------------------- small wrappers over the C ABI
     def _grad_view(self, name):
+        """Where the backward kernels write the gradient of parameter `name`: bias gradients and the 1x1 head's weight gradient
+        go straight into the reduce buffer (same layout as the parameter); 3x3 / transposed-conv weights use _dw_view."""
+        layer, kind = name.rsplit(".", 1)
+        if kind == "bias" and layer in self.db:
+            off, n = self.db[layer]
+            return self.dw_flat[off:off + n]
+        if name == "conv10_1.weight":
+            return self._dw_view("conv10_1").view(self.slices[name][2])
         off, n, shape = self.slices[name]
         return self.flat_g[off:off + n].view(shape)
+
+    def _bucket_done(self, layer, grad_allreduce):
+        """DDP: `layer` completes a bucket of the reduce buffer -> all-reduce(SUM) it on the communication stream while the current
+        stream goes on with the backward pass (the 1 / world factor is folded into Adam)."""
+        if not grad_allreduce or self.comm_stream is None or layer not in self.buckets:
+            return
+        a, b = self.buckets[layer]
+        cur = torch.cuda.current_stream(self.device)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            torch.distributed.all_reduce(self.dw_flat[a:b], op=torch.distributed.ReduceOp.SUM)
 
     def _dw_view(self, name):
         off, shape = self.dw[name]
@@ -245,6 +299,7 @@ class UNetTrainStep:
         for s in srcs:
             self._wgrad_nhwc(0, g, co, s, dw, c_off, ci_total)
             c_off += s.shape[-1]
+        self._bucket_done(name, getattr(self, "_ar", False))  # this layer's gradients are complete: the data gradient overlaps the reduce
         gxs = []
         if need_dx:
             for k, s in enumerate(srcs):                  # data gradient: the forward kernel on the transposed + flipped weights
@@ -265,6 +320,7 @@ class UNetTrainStep:
         self._act_bwd(g_up, None, self._grad_view(name + ".bias"), _lib.ACT_NONE)
         dw = self._dw_view(name)
         self._wgrad_nhwc(1, g_up, co, x_in, dw, 0, ci)
+        self._bucket_done(name, getattr(self, "_ar", False))
         gx = self.scr.get("gx_" + name, (n, h, w, ci))
         _conv(_lib.CONV2S2, g_up, self.wd[name], None, gx, ci, _lib.ACT_NONE, mask=x_in)      # [a*2+b][ci][co] = W[ci][co][a][b]
         return gx
@@ -307,8 +363,9 @@ class UNetTrainStep:
         s["pred"] = pred
         return pred, s
 
-    def backward(self, gpred, s):
+    def backward(self, gpred, s, grad_allreduce=False):
         net, nf = self.net, self.net.nf
+        self._ar = grad_allreduce
         n, _, h, w = gpred.shape
         LK = _lib.ACT_LEAKY
         self.flat_g.zero_()
@@ -322,6 +379,7 @@ class UNetTrainStep:
                                       self._grad_view("conv10_1.bias").data_ptr(), self._grad_view("conv9_2.bias").data_ptr(),
                                       n, h, w, nf, net.out_nc, LK,
                                       self._stream()), "head_bwd")
+        self._bucket_done("conv10_1", self._ar)
         # decoder (every data gradient that lands on an activation output carries that activation's derivative: `mask`)
         g_skip = {}
         for i in range(9, 5, -1):
@@ -341,7 +399,9 @@ class UNetTrainStep:
             res = self._conv3_bwd(f"conv{i}_1", g, [s[f"in{i}_1"]], i > 1)
             if i > 1:
                 g = res[0]
-        tab, nd = self._unpack_tab                           # wgrad scratch -> the parameters' gradient layout (one launch)
+        if self._ar and self.comm_stream is not None:        # every bucket's all-reduce has to land before the scatter
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        tab, nd = self._unpack_tab                           # reduce buffer -> the parameters' gradient layout (one launch)
         L.check(L.lib().pnnp_strided_copy_batch(tab.data_ptr(), nd, 48, self._stream()), "unpack gradients")
 
     @property
@@ -359,8 +419,9 @@ class UNetTrainStep:
         gpred = self.scr.get("gpred", tuple(pred.shape), torch.float32)
         L.check(L.lib().pnnp_l1_loss(pred.data_ptr(), hr.data_ptr(), gpred.data_ptr(), pred.numel(), self.loss_sum.data_ptr(),
                                      self._stream()), "l1_loss")
-        self.backward(gpred, saved)
-        gscale = D.allreduce_mean_(self.flat_g) if grad_allreduce else 1.0   # DDP: average of the per-rank mean losses
+        ddp = bool(grad_allreduce) and D.world()[1] > 1
+        self.backward(gpred, saved, ddp)                                 # DDP: bucketed all-reduce(SUM) overlapped with the backward pass
+        gscale = 1.0 / D.world()[1] if ddp else 1.0                      # average of the per-rank mean losses, folded into Adam
         L.check(L.lib().pnnp_adam_step_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                            self.flat_p.numel(), self.adam_state.data_ptr(), self.betas[0], self.betas[1], self.eps,
                                            gscale, self._stream()), "adam_step")

@@ -318,6 +318,7 @@ class SID_Trainer(Base_Trainer):
                         log(f'Successfully reload best model (Eval PSNR:{self.best_psnr})', log=self.logfile)
         if self.rank == 0:
             torch.save(_detached_state(self.net), f'{self.fast_ckpt}/{self.model_name}_last_model.pth')
+        step.close()                                                    # captured all-reduces must not outlive the process group
         if self.world_size > 1:
             torch.distributed.barrier()
         return step
