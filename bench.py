@@ -640,6 +640,8 @@ def run_gpu_arm(args, name, wl):
     if rank == 0:
         peaks, peak_src = measured_peaks()
         burst, sustained = float(peaks["bf16_tflops"]), float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        if args.precision == "tf32":                            # dense tf32 = half the bf16 rate (1.1 vs 2.25 PFLOP/s nominal)
+            burst, sustained = burst / 2, sustained / 2
         if name == "path64":
             # the dominant kernel's own time inside the timed region; burst peak for a short timed region, sustained for a long one
             timed_s = ms_step * args.steps / 1e3
@@ -724,8 +726,14 @@ def main():
     ap.add_argument("--workload", default="path64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parts", action="store_true", help="path64: skip the training-step part")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="network accuracy class: bf16 storage + kind::f16 MMAs (default) or fp32 storage + kind::tf32 MMAs")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.precision == "tf32":
+        os.environ["PNNP_UNET_PRECISION"] = "tf32"
+        wl = dict(wl, dtype="tf32 tcgen05 (fp32 storage, fp32 accumulate)" + (" UNet + f64 NumPy-chain synthesis" if args.workload == "path64" else ""),
+                  desc=wl["desc"] + " [fp32-storage / kind::tf32 variant: the roofline peak is half the measured bf16 peak]")
     if args.impl == "reference":
         return run_reference_arm(args, args.workload, wl)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

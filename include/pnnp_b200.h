@@ -168,6 +168,10 @@ typedef struct pnnp_conv_desc {
     const float* head_w; const float* head_b; float* head_out; int head_cout;
     const void* mask; float mask_slope;   /* NHWC bf16 activation shaped like the output: out *= (mask > 0 ? 1 : mask_slope) — the
                                            * activation derivative fused into a data-gradient conv (training); NULL = off */
+    int io_f32;                           /* 1: fp32-storage variant — in0 / in1 / weight / out / resid / pool_out are fp32 (same NHWC /
+                                           * [tap][rows][cin] layouts), the MMAs are tcgen05 kind::tf32.  The north_star's "fp32" accuracy
+                                           * class (bf16 reported separately); inference layers of UNetSeeInDark (3x3, x-mode, transposed,
+                                           * 1x1, fused pool / head, two sources).  0: bf16 storage (default). */
 } pnnp_conv_desc;
 int pnnp_conv2d_tc_ex(const pnnp_conv_desc* desc, void* stream);
 /* Non-zero if a tcgen05/TMA pipeline wait timed out since the last call (the kernels terminate
@@ -176,6 +180,8 @@ int pnnp_conv_pipeline_error(void);
 /* network input: NCHW fp32 (c <= 16) * scale -> NHWC bf16 zero-padded to 16 channels */
 int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int h, int w, float scale,
                         void* stream);
+/* the same conversion with fp32 output (input of the fp32-storage / tf32 variant) */
+int pnnp_nchw_to_nhwc16_f32(const float* in, float* out, int n, int c, int h, int w, void* stream);
 /* First layer fused with the pack boundary (archs/Unet.py:55 conv1_1, archs/ResUnet.py conv_in, fed by the packed planes that
  * data_process/process.py:625-631 / utils/isp_ops.py:84-96 produce): NCHW fp32 input with cin <= 4 channels -> conv3x3 pad 1
  * (weight: the module's own fp32 [cout][cin][3][3], rounded to bf16 in the kernel) + bias + activation (act: 0 none, 1 LeakyReLU

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
                 ("out", C.c_void_p), ("cout", C.c_int), ("cout_stride", C.c_int),
                 ("resid", C.c_void_p), ("resid_nchw", C.c_void_p), ("pool_out", C.c_void_p),
                 ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_cout", C.c_int),
-                ("mask", C.c_void_p), ("mask_slope", C.c_float)]
+                ("mask", C.c_void_p), ("mask_slope", C.c_float), ("io_f32", C.c_int)]
 
 CODE_P, CODE_G, CODE_R, CODE_Q, CODE_D, CODE_B = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 CODE_UNIFORM_F64 = 0x100
@@ -62,6 +62,7 @@ SIGNATURES = {
     "pnnp_nchw_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "pnnp_conv_first_nchw": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pnnp_conv_first_pipeline_error": (_i, []),
+    "pnnp_nchw_to_nhwc16_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "pnnp_maxpool2x2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "pnnp_l1_loss": (_i, [_vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "pnnp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

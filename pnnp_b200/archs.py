@@ -39,8 +39,8 @@ class _PackedLayer:
     """bf16 weights in the kernel's [taps][rows][cin] layout + fp32 bias, rebuilt when the
     underlying parameters change (tracked by tensor._version / data_ptr)."""
 
-    def __init__(self, module, kind):
-        self.module, self.kind, self.key = module, kind, None
+    def __init__(self, module, kind, dtype=torch.bfloat16):
+        self.module, self.kind, self.key, self.dtype = module, kind, None, dtype
         self.weight = self.bias = None
 
     def get(self, device):
@@ -59,8 +59,8 @@ class _PackedLayer:
                 cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
                 packed = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)
             rows, cin_p = _pad16(packed.shape[1]), _pad16(packed.shape[2])
-            buf = torch.zeros((packed.shape[0], rows, cin_p), dtype=torch.bfloat16, device=device)
-            buf[:, :packed.shape[1], :packed.shape[2]] = packed.to(torch.bfloat16)
+            buf = torch.zeros((packed.shape[0], rows, cin_p), dtype=self.dtype, device=device)
+            buf[:, :packed.shape[1], :packed.shape[2]] = packed.to(self.dtype)
             self.weight = buf.contiguous()
             self.bias = None if m.bias is None else m.bias.detach().to(device=device, dtype=torch.float32).contiguous()
             self.key = key
@@ -73,12 +73,12 @@ class _Workspace:
     def __init__(self):
         self.bufs, self.sig = {}, None
 
-    def get(self, sig, name, shape, device):
+    def get(self, sig, name, shape, device, dtype=torch.bfloat16):
         if sig != self.sig:
             self.bufs, self.sig = {}, sig
         t = self.bufs.get(name)
         if t is None:
-            t = torch.empty(shape, dtype=torch.bfloat16, device=device)
+            t = torch.empty(shape, dtype=dtype, device=device)
             self.bufs[name] = t
         return t
 
@@ -91,6 +91,9 @@ def _conv(mode, x0, w, b, out, cout, act, x1=None, resid=None, out_mode=_lib.OUT
     n, h, wd, c0 = x0.shape
     d = _lib.ConvDesc()
     d.mode, d.act, d.out_mode, d.n, d.h, d.w = mode, act, out_mode, n, h, wd
+    d.io_f32 = int(x0.dtype == torch.float32)              # fp32-storage variant (tcgen05 kind::tf32): operands and outputs fp32
+    if d.io_f32 and (w.dtype != torch.float32 or (x1 is not None and x1.dtype != torch.float32)):
+        raise RuntimeError("pnnp_b200: fp32-storage conv needs fp32 activations and fp32 packed weights")
     d.in0, d.cin0 = x0.data_ptr(), c0
     d.in1, d.cin1 = (None, 0) if x1 is None else (x1.data_ptr(), x1.shape[3])
     d.weight, d.w_rows, d.bias = w.data_ptr(), w.shape[1], _lib.ptr(b)
@@ -114,6 +117,12 @@ def _pool(x, out):
 
 def _to_nhwc16(x, out, scale=1.0):
     n, c, h, w = x.shape
+    if out.dtype == torch.float32:
+        if scale != 1.0:
+            raise RuntimeError("pnnp_b200: the fp32 input conversion has no scale")
+        _lib.check(_lib.lib().pnnp_nchw_to_nhwc16_f32(x.data_ptr(), out.data_ptr(), n, c, h, w, _lib.stream_ptr(x.device)),
+                   "nchw_to_nhwc16_f32")
+        return out
     _lib.check(_lib.lib().pnnp_nchw_to_nhwc16(x.data_ptr(), out.data_ptr(), n, c, h, w, float(scale),
                                               _lib.stream_ptr(x.device)), "nchw_to_nhwc16")
     return out
@@ -153,11 +162,26 @@ class _TCNet(nn.Module):
             raise RuntimeError("pnnp_b200: at most 16 input channels")
         return x.float().contiguous()
 
+    # Accuracy class of the forward (north_star: "within 1e-3 max-abs in fp32 (bf16 variant reported separately)"):
+    #   "bf16" (default)  activations / weights bf16 in HBM, tcgen05 kind::f16, fp32 accumulation — the fast path;
+    #   "tf32"            activations / weights fp32 in HBM, tcgen05 kind::tf32 (fp32 operands, 10-bit mantissa products, fp32
+    #                     accumulation) — UNetSeeInDark inference; twice the bytes, for runs that need the fp32 tolerance under any init.
+    # Set per network (`net.precision = "tf32"`), by the YAML arch dict (`precision: tf32`) or PNNP_UNET_PRECISION.
+    precision = None
+
+    def _dtype(self):
+        p = self.precision or (self.args or {}).get("precision") or os.environ.get("PNNP_UNET_PRECISION", "bf16")
+        if p not in ("bf16", "tf32"):
+            raise RuntimeError(f"pnnp_b200: precision {p!r} (bf16 or tf32)")
+        return torch.float32 if p == "tf32" else torch.bfloat16
+
     def _packed(self, name, kind="conv"):
         cache = self.__dict__.setdefault("_pack_cache", {})
-        if (name, kind) not in cache:
-            cache[(name, kind)] = _PackedLayer(self.get_submodule(name), kind)
-        return cache[(name, kind)].get(next(self.parameters()).device)
+        dt = self._dtype()
+        key = (name, kind) if dt == torch.bfloat16 else (name, kind, "f32")
+        if key not in cache:
+            cache[key] = _PackedLayer(self.get_submodule(name), kind, dt)
+        return cache[key].get(next(self.parameters()).device)
 
     def _conv3(self, name, x0, out, cout, act, **kw):
         """3x3 stride-1 conv layer `name`: the x-shift-in-N kernel mode for narrow layers (Cout <= 64, where a
@@ -205,11 +229,12 @@ class UNetSeeInDark(_TCNet):
         x = self._check_input(x)
         n, c, h, w = x.shape
         dev, ws, nf = x.device, self._ws(), self.nf
-        sig = (n, h, w, str(dev))
-        buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev)
+        dt = self._dtype()
+        sig = (n, h, w, str(dev), dt)
+        buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev, dt)
         L = _lib.ACT_LEAKY
         with torch.cuda.device(dev):
-            fused_first = _use_first_conv(c, nf)                   # conv1_1 straight from the packed fp32 planes (csrc/conv_first.cu)
+            fused_first = dt == torch.bfloat16 and _use_first_conv(c, nf)   # conv1_1 straight from the packed fp32 planes (csrc/conv_first.cu)
             cur = None if fused_first else _to_nhwc16(x, buf("x16", h, w, 16))
             skips = []
             hh, ww = h, w
@@ -308,8 +333,9 @@ class ResUnet(_TCNet):
         x = self._check_input(x)
         n, c, h, w = x.shape
         dev, ws, nf = x.device, self._ws(), self.nf
-        sig = (n, h, w, str(dev))
-        buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev)
+        dt = self._dtype()
+        sig = (n, h, w, str(dev), dt)
+        buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev, dt)
 
         def block(i, src0, src1, hh, ww, co):
             """ResidualBlock i on (src0 [, src1]) -> NHWC bf16 (modules.py:176-197)."""
@@ -324,7 +350,7 @@ class ResUnet(_TCNet):
             return _conv(_lib.CONV3, t, w2, None, buf(f"b{i}", hh, ww, co), co, _lib.ACT_NONE, resid=shortcut)
 
         with torch.cuda.device(dev):
-            if _use_first_conv(c, nf):                             # conv_in straight from the packed fp32 planes
+            if dt == torch.bfloat16 and _use_first_conv(c, nf):    # conv_in straight from the packed fp32 planes
                 cur = _first_conv(x, self.conv_in, buf("cin", h, w, nf), _lib.ACT_RELU)
             else:
                 x16 = _to_nhwc16(x, buf("x16", h, w, 16))

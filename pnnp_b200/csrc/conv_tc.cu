@@ -112,7 +112,7 @@ struct TileIter {
 
 // All MMAs of one pipeline stage: TPS taps x K16S K-slices, fully unrolled; descriptors advance by adding
 // to the 14-bit start-address field (no carry out of the field: shared memory is < 256 KB).
-template <int TPS, int K16S>
+template <int TPS, int K16S, bool F32 = false>
 __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc0, uint64_t bdesc0, uint32_t a_tap_stride,
                                                  uint32_t b_tap_stride, uint32_t idesc, bool accumulate_first) {
 #pragma unroll
@@ -121,7 +121,8 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
         for (int k = 0; k < K16S; ++k) {
             const uint64_t ad = adesc0 + (uint64_t)(dy * a_tap_stride + k * 2);     // k * 32 B
             const uint64_t bd = bdesc0 + (uint64_t)(dy * b_tap_stride + k * 2);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || dy != 0 || k != 0) ? 1u : 0u);
+            if constexpr (F32) tc_mma_tf32(d_tmem, ad, bd, idesc, (accumulate_first || dy != 0 || k != 0) ? 1u : 0u);   // 32 bytes = 8 fp32 per slice
+            else tc_mma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || dy != 0 || k != 0) ? 1u : 0u);
         }
     }
 }
@@ -148,6 +149,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     constexpr int SUP = VAR & 1;
     constexpr bool kPdl = (VAR & 2) != 0;
     constexpr bool kX2 = (VAR & 4) != 0;
+    // VAR bit 3 = F32: the fp32-storage variant (north_star: "within 1e-3 in fp32, bf16 variant reported separately") — activations and
+    // weights are fp32 in HBM and shared memory, the MMAs are kind::tf32 (K = 8 per 32-byte slice, so the same slice / swizzle /
+    // descriptor arithmetic applies with kc = span / 4 channels per chunk), the epilogue stores fp32 NHWC.  Generic epilogue only.
+    constexpr bool kF32 = (VAR & 8) != 0;
     // Opt-in variants (VAR != 0) with a specialised epilogue are never launched with debug switches, so their mode (bits 0 / 4 of
     // EPI), the debug word and the swizzle span (32 bytes per K16 slice) are compile-time constants: the serial loops of the
     // producer and MMA warps — whose instruction count IS the tile rate of the small-K layers — lose their run-time selects.
@@ -279,7 +284,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int groups = p.groups;
         const bool b_res = p.b_resident != 0;
         int* const err = p.err;
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | ((kF32 ? 2u : 1u) << 7) | ((kF32 ? 2u : 1u) << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);   // A/B format: 1 = bf16, 2 = tf32
         const uint64_t dhi = umma_desc_hi(PNNP_SWZ_K);
         const uint32_t a_tap_stride = (uint32_t)(kTileW * PNNP_SWZ_K) >> 4;      // descriptor units (16 B)
         const uint32_t b_tap_stride = (uint32_t)p.b_tap_stride >> 4;
@@ -310,9 +315,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 // (chunk * taps_total + dx) * tap bytes: +1 tap per stage, +taps_total per chunk
                 if (++dx == dxc) { dx = 0; sb_res += (uint32_t)(taps_total - dxc + 1) * b_tap_bytes; } else sb_res += b_tap_bytes;
                 if (elect_one()) {
-                    if (!(dbg & 2)) issue_stage_mmas<TPS, K16S>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
+                    if (!(dbg & 2)) issue_stage_mmas<TPS, K16S, kF32>(d_tmem, adesc0, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
                     if (SUP && !(dbg & 2))
-                        issue_stage_mmas<TPS, K16S>(d_tmem + (uint32_t)umma_n, adesc0 + a_half, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
+                        issue_stage_mmas<TPS, K16S, kF32>(d_tmem + (uint32_t)umma_n, adesc0 + a_half, bdesc0, a_tap_stride, b_stride_eff, idesc, ks != 0);
                     if (dbg & 16) mbar_arrive(eb);
                     else tc_commit(eb);                                    // frees the smem slot when these MMAs retire
                 }
@@ -454,7 +459,42 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         f[i] = fmaxf(a, fmaf(a, slope, 0.0f));
                     }
                 }
-                if (out_nhwc) {
+                if (kF32 && out_nhwc) {
+                    // fp32-storage variant: residual, output and fused max-pool in fp32 NHWC (the accumulators are never rounded)
+                    if (has_resid && valid) {
+                        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + opix * p.cout_stride + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const float4 r = rp[i]; f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w; }
+                    }
+                    if (p.out && valid) {
+                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.cout_stride + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    }
+                    if (has_pool) {
+                        float m[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float o1 = xmode ? __shfl_down_sync(0xffffffffu, f[i], 1) : __shfl_xor_sync(0xffffffffu, f[i], 1);
+                            const float a = fmaxf(f[i], o1);
+                            m[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
+                        }
+                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16)) {
+                            const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
+                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.pool_out) + pp * p.cout_stride + c0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) op[i] = make_float4(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
+                        }
+                    }
+                    if (has_head) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(&s_head_w[(c0 + i) * 4]);
+                            head[0] = fmaf(f[i], w4.x, head[0]); head[1] = fmaf(f[i], w4.y, head[1]);
+                            head[2] = fmaf(f[i], w4.z, head[2]); head[3] = fmaf(f[i], w4.w, head[3]);
+                        }
+                    }
+                } else if (out_nhwc) {
                     if (has_resid && valid) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.resid + opix * p.cout_stride + c0);
                         const uint4 r0 = rp[0], r1 = rp[1];
@@ -595,29 +635,29 @@ static CUtensorMapSwizzle swz_enum(int swz) {
 }
 // activation map: NHWC bf16 viewed as (C, W, H, N); box (kc, 16, box_h, 1)
 static int make_act_map(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c, int kc, int box_h, int swz,
-                        int stride = 1) {
+                        int stride = 1, int esz = 2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)c * esz, (cuuint64_t)w * c * esz, (cuuint64_t)h * w * c * esz};
     // with a traversal stride s the TMA unit loads boxDim/s elements per dimension
     cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(kTileW * stride), (cuuint32_t)(box_h * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+    CUresult r = enc(tm, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return fail(b); }
     return 0;
 }
 // weight map: [taps][rows][cin] bf16 viewed as (cin, rows, taps); box (kc, umma_n, 1)
-static int make_w_map(CUtensorMap* tm, const void* ptr, int taps, int rows, int cin, int kc, int umma_n, int swz) {
+static int make_w_map(CUtensorMap* tm, const void* ptr, int taps, int rows, int cin, int kc, int umma_n, int swz, int esz = 2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)rows, (cuuint64_t)taps};
-    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)rows * cin * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * esz, (cuuint64_t)rows * cin * esz};
     cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)umma_n, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+    CUresult r = enc(tm, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { char b[128]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r); return fail(b); }
@@ -636,7 +676,12 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (!in0 || !weight || (!out && !d.head_out)) return fail("conv: null pointer");
     if (cin0 % 16 || cin1 % 16) return fail("conv: channel counts must be multiples of 16");
     const int nsrc = in1 ? 2 : 1;
-    int kc = 64;
+    // fp32-storage variant (kind::tf32): 4-byte elements, so a 128-byte swizzle span holds 32 channels
+    const bool f32 = d.io_f32 != 0;
+    const int esz = f32 ? 4 : 2;
+    if (f32 && (d.mask || mode == MODE_CONV2S2))
+        return fail("conv: the fp32-storage (tf32) variant covers the inference layers only (no activation mask, no dgrad modes)");
+    int kc = f32 ? 32 : 64;
     while (kc > 16 && ((cin0 % kc) || (nsrc > 1 && (cin1 % kc)))) kc >>= 1;
     int umma_n, n_tiles;
     if (mode == MODE_CONVT) {
@@ -684,10 +729,10 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
     const int dbg_env = getenv("PNNP_CONV_DBG") ? atoi(getenv("PNNP_CONV_DBG")) : 0;
     int epi = EPI_GENERIC;
-    if (!no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && !dbg_env &&
+    if (!f32 && !no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && !dbg_env &&
         !(d.pool_out && d.head_out) && !(d.mask && (mode == MODE_CONV3X || d.pool_out || d.head_out)))
         epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
-    if (convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
+    if (!f32 && convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
         act == ACT_NONE && !no_spec && !dbg_env)
         epi = EPI_CONVT;
     // K chunk the shared-memory plan below ends up with for a given A-box height.  The super-tile variant is taken only where its
@@ -697,16 +742,16 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     auto plan_kc = [&](int box_rows) {
         const int budget = 227 * 1024 - 4096 - cout * 20, cin_all = cin0 + (nsrc > 1 ? cin1 : 0);
         int k = kc;
-        const int bts = (umma_n * k * 2 + 1023) / 1024 * 1024;
-        const int res_bytes = (cin_all / k) * (mode == MODE_CONVT ? 1 : taps) * bts, a_only = (box_rows * kTileW * k * 2 + 1023) / 1024 * 1024;
+        const int bts = (umma_n * k * esz + 1023) / 1024 * 1024;
+        const int res_bytes = (cin_all / k) * (mode == MODE_CONVT ? 1 : taps) * bts, a_only = (box_rows * kTileW * k * esz + 1023) / 1024 * 1024;
         const bool res = (mode != MODE_CONVT || convt_fast) && n_tiles == 1 && res_bytes + 3 * a_only <= budget && !getenv("PNNP_NO_RESIDENT_W");
         for (;; k >>= 1) {
-            const int a_b = box_rows * kTileW * k * 2, b_ts = (umma_n * k * 2 + 1023) / 1024 * 1024;
+            const int a_b = box_rows * kTileW * k * esz, b_ts = (umma_n * k * esz + 1023) / 1024 * 1024;
             const int st_b = ((res ? a_b : a_b + tps * b_ts) + 1023) / 1024 * 1024;
             if ((budget - (res ? res_bytes : 0)) / st_b >= 3 || k == 16 || res) return k;
         }
     };
-    const bool sup_wanted = super_env > 0 && mode != MODE_CONVT && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
+    const bool sup_wanted = !f32 && super_env > 0 && mode != MODE_CONVT && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH;
     const bool sup = sup_wanted && plan_kc(2 * kTileH + 2) == plan_kc(kTileH + 2);
     const int tile_rows = sup ? 2 * kTileH : kTileH;
     const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? tile_rows + 2 : kTileH;
@@ -716,7 +761,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     const int cin_total = cin0 + (nsrc > 1 ? cin1 : 0);
     {
         // weights resident in smem when all taps x chunks fit beside >= 3 A-only stages (single N tile, not convT)
-        const int swz_r = kc * 2, bts = (umma_n * swz_r + 1023) / 1024 * 1024;
+        const int swz_r = kc * esz, bts = (umma_n * swz_r + 1023) / 1024 * 1024;
         const int res_bytes = (cin_total / kc) * (mode == MODE_CONVT ? 1 : taps) * bts;   // convT: the four taps are N columns of one block
         const int a_only = (box_h * kTileW * swz_r + 1023) / 1024 * 1024;
         // ConvTranspose2d layers with a single N tile (4 * cout <= 256) can keep their weights resident too: opt-in
@@ -726,12 +771,12 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         }
     }
     for (;; kc >>= 1) {
-        swz = kc * 2;
+        swz = kc * esz;
         a_bytes = box_h * kTileW * swz;
         b_tap_stride = (umma_n * swz + 1023) / 1024 * 1024;
         stage_bytes = ((b_resident ? a_bytes : a_bytes + tps * b_tap_stride) + 1023) / 1024 * 1024;
         stages = std::min(kMaxStages, (smem_budget - b_res_bytes) / stage_bytes);
-        if (stages >= 3 || kc == 16 || b_resident) break;
+        if (stages >= 3 || swz == 32 || b_resident) break;
     }
     if (stages < 2) return fail("conv: tile does not fit in shared memory");
     ConvParams p{};
@@ -751,8 +796,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         const int half_budget = 110 * 1024 - 2048 - cout * 20;
         const int st2 = std::min(stages, (half_budget - b_res_bytes) / stage_bytes);
         if (st2 >= 3) stages = st2;
-        else if (sup) two_ctas = false;                      // the 18-row stages of a super-tile may not fit twice: one CTA per SM then
-        else return fail("conv: two-CTA configuration does not fit (internal)");
+        else two_ctas = false;                               // taller (super-tile) or wider (fp32) stages may not fit twice: one CTA per SM then
     }
     const int groups = two_ctas ? 2 : ((umma_n <= 128 && !getenv("PNNP_CONV_2GROUPS")) ? 4 : 2);
     p.stages = stages;
@@ -767,11 +811,11 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
     p.err = g_err_dev;
     CUtensorMap tmA0, tmA1, tmB;
-    if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, s2 ? 2 : 1)) return e;
-    if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz)) return e; }
+    if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, s2 ? 2 : 1, esz)) return e;
+    if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz, 1, esz)) return e; }
     else tmA1 = tmA0;
-    if (mode == MODE_CONVT) { if (int e = make_w_map(&tmB, weight, 1, 4 * cout, cin0, kc, umma_n, swz)) return e; }
-    else if (int e = make_w_map(&tmB, weight, taps, w_rows, cin0 + (nsrc > 1 ? cin1 : 0), kc, umma_n, swz)) return e;
+    if (mode == MODE_CONVT) { if (int e = make_w_map(&tmB, weight, 1, 4 * cout, cin0, kc, umma_n, swz, esz)) return e; }
+    else if (int e = make_w_map(&tmB, weight, taps, w_rows, cin0 + (nsrc > 1 ? cin1 : 0), kc, umma_n, swz, esz)) return e;
     int dev = 0, sms = 0;
     PNNP_CUDA(cudaGetDevice(&dev));
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -815,7 +859,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 #undef X
         attr_optin_done = true;
     }
-    const int k16s = kc / 16;
+    const int k16s = swz / 32;                    // 32-byte MMA slices per K chunk (16 bf16 or 8 tf32 elements each)
     // Programmatic dependent launch (opt-in until measured): the kernel waits (griddepcontrol.wait) before its first global access
     cudaLaunchAttribute pdl_attr[1];
     pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -824,6 +868,27 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     pdl_cfg.gridDim = dim3((unsigned)grid); pdl_cfg.blockDim = dim3((unsigned)(64 + 128 * groups)); pdl_cfg.dynamicSmemBytes = smem;
     pdl_cfg.stream = st; pdl_cfg.attrs = pdl_attr; pdl_cfg.numAttrs = 1;
     bool launched = false;
+    if (f32) {
+#ifdef PNNP_HOST_EMUL
+        return fail("conv: the fp32-storage (tf32) variant is not modelled on the host");
+#else
+        static bool attr_f32_done = false;
+#define PNNP_FOR_EACH_F32_VARIANT(X) X(3, 1, -1) X(3, 2, -1) X(3, 4, -1) X(1, 1, -1) X(1, 2, -1) X(1, 4, -1)
+        if (!attr_f32_done) {
+#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            PNNP_FOR_EACH_F32_VARIANT(X)
+#undef X
+            attr_f32_done = true;
+        }
+#define X(T, K, E) if (!launched && tps == T && k16s == K) { PNNP_CONV_KLAUNCH(T, K, E, 8); launched = true; }
+        PNNP_FOR_EACH_F32_VARIANT(X)
+#undef X
+        if (!launched) return fail("conv: no fp32-storage kernel variant for this (taps per stage, K chunk)");
+        count_launch();
+        PNNP_CUDA(cudaGetLastError());
+        return 0;
+#endif
+    }
     if (sup && (groups & 1)) return fail("conv: the super-tile variant needs an even number of accumulator buffers (internal)");
     if (x2) {
 #define X(T, K, E) if (!launched && tps == T && k16s == K && epi == E) { \
@@ -894,6 +959,16 @@ extern "C" int pnnp_nchw_to_nhwc16(const float* in, void* out, int n, int c, int
     }
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     nchw_f32_to_nhwc16_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, static_cast<__nv_bfloat16*>(out), n, c, h, w, scale);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_nchw_to_nhwc16_f32(const float* in, float* out, int n, int c, int h, int w, void* stream) {
+    if (!in || !out || c > 16) return fail("nchw_to_nhwc16_f32: bad arguments");
+    const size_t total = (size_t)n * h * w;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    nchw_f32_to_nhwc16_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, c, h, w);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

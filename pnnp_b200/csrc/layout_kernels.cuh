@@ -31,6 +31,20 @@ __global__ void nchw_f32_to_nhwc16_bf16_kernel(const float* __restrict__ in, __n
     }
 }
 
+// NCHW fp32 -> NHWC fp32 zero-padded to 16 channels (input of the fp32-storage / tf32 variant of the network)
+__global__ void nchw_f32_to_nhwc16_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int c, int h, int w) {
+    const size_t plane = (size_t)h * w, total = (size_t)n * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t img = i / plane, pix = i - img * plane;
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = k < c ? in[(img * c + k) * plane + pix] : 0.f;
+        float4* o = reinterpret_cast<float4*>(out + i * 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+}
+
 // Same conversion, four pixels per thread (h * w % 4 == 0): one 128-bit load per plane (all issued before the first use) and a
 // contiguous 128-byte store per thread.  OPT-IN (PNNP_IN_V2=1) until measured: the one-pixel kernel above takes 53 us for a Sony
 // frame (146 MB of traffic: 2.7 TB/s).

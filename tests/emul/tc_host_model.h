@@ -35,7 +35,7 @@ typedef int CUresult;
 constexpr CUresult CUDA_SUCCESS = 0;
 typedef uint32_t cuuint32_t;
 typedef uint64_t cuuint64_t;
-enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 = 9 };
+enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 = 9 };
 enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
 enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_128B };
 enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_NONE = 0, CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B };
@@ -271,6 +271,7 @@ static inline void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, 
         }
     });
 }
+static inline void tc_mma_tf32(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { tc_model_fail("tcgen05.mma.kind::tf32 is not modelled (the fp32-storage variant is checked on the GPU only)"); }
 static inline void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     const unsigned tid = simt::g_cta->cur, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFFu;

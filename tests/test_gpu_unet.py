@@ -343,3 +343,58 @@ def test_fused_first_layer_equals_the_two_kernel_path(monkeypatch):
             got = net(x).clone()
         _no_pipeline_error()
         assert (got - want).abs().max().item() < 2e-3 * want.abs().max().item(), cls.__name__      # bf16 rounding flips of the first layer, propagated
+
+
+@pytest.mark.parametrize("cin,cout,h,w,two,xmode", [(16, 32, 16, 32, False, False), (32, 64, 24, 40, False, False), (128, 128, 16, 16, False, False),
+                                                    (256, 512, 8, 16, False, False), (64, 64, 24, 32, True, False), (32, 32, 24, 44, False, True),
+                                                    (32, 32, 16, 30, True, True)])
+def test_conv3x3_layer_tf32_variant(cin, cout, h, w, two, xmode):
+    """The fp32-storage variant (tcgen05 kind::tf32, fp32 NHWC in and out): against an fp32 reference the error is that of 10-bit
+    mantissa products — far below the bf16 variant's."""
+    g = torch.Generator(device="cuda").manual_seed(cin * 13 + cout)
+    x = torch.randn((1, cin, h, w), device="cuda", generator=g)
+    x2 = torch.randn((1, cin, h, w), device="cuda", generator=g) if two else None
+    ct = cin * (2 if two else 1)
+    wt = torch.randn((cout, ct, 3, 3), device="cuda", generator=g) / (3 * ct ** 0.5)
+    b = torch.randn((cout,), device="cuda", generator=g) * 0.1
+
+    class M:
+        pass
+    m = M()
+    m.weight, m.bias = wt, None
+    wp = archs._PackedLayer(m, "conv3x" if xmode else "conv", torch.float32).get(wt.device)[0]
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((1, h, w, cout), float("nan"), dtype=torch.float32, device="cuda")
+    pooled = torch.empty((1, h // 2, w // 2, cout), dtype=torch.float32, device="cuda")
+    archs._conv(_lib.CONV3X if xmode else _lib.CONV3, nhwc(x), wp, b, out, cout, _lib.ACT_LEAKY, x1=None if x2 is None else nhwc(x2),
+                pool_out=pooled)
+    _no_pipeline_error()
+    xin = x if x2 is None else torch.cat([x, x2], 1)
+    ref = F.leaky_relu(F.conv2d(xin, wt, b, padding=1), 0.2)
+    got = out.permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err                       # tf32: 2^-11 relative per product
+    assert torch.equal(pooled.permute(0, 3, 1, 2), F.max_pool2d(got, 2))
+
+
+@pytest.mark.parametrize("arch_name", ["UNetSeeInDark", "ResUnet"])
+def test_forward_tf32_variant_meets_the_fp32_bound_under_any_init(arch_name):
+    """north_star: "UNet output within 1e-3 max-abs in fp32 (bf16 variant reported separately)".  With PyTorch's DEFAULT init the
+    outputs are O(0.1-1) — there the bf16 variant's absolute error grows with them, the fp32-storage / tf32 variant stays inside
+    1e-3; with the reference's initialiser both do.  Both variants are reported (printed) against the CPU fp32 oracle."""
+    oracle_fwd = O.unet_forward if arch_name == "UNetSeeInDark" else O.resunet_forward
+    x = torch.rand((1, 4, 256, 384), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    for init in ("default", "reference"):
+        torch.manual_seed(3)
+        net = getattr(P, arch_name)(_arch()).cuda().eval()
+        if init == "reference":
+            P.initialize_weights(net)
+        with torch.no_grad():
+            want = oracle_fwd(x.cpu(), _cpu_state(net))
+            net.precision = "bf16"
+            e_bf16 = (net(x).cpu() - want).abs().max().item()
+            net.precision = "tf32"
+            e_tf32 = (net(x).cpu() - want).abs().max().item()
+        _no_pipeline_error()
+        print(f"{arch_name} init={init}: out absmax {want.abs().max().item():.3e}; max-abs error bf16 {e_bf16:.3e}, tf32 {e_tf32:.3e}")
+        assert e_tf32 <= 1e-3 and e_tf32 < e_bf16, (init, e_tf32, e_bf16)
