@@ -36,6 +36,7 @@ struct FirstParams {
     const float* in; const float* w; const float* bias; __nv_bfloat16* out;
     int n, cin, H, W, cout, tiles_x, tiles_y;
     float slope;                 // activation as max(v, v * slope): LeakyReLU 0.2 / ReLU 0 / identity 1
+    int dbg;                     // timing experiments only (PNNP_FIRST_DBG): 1 no MMA round trip, 2 no global loads, 4 no stores, 8 no im2col
     int* err;
 };
 
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
     // everything the loop needs in registers: the asm statements carry "memory" clobbers, so p.field would be re-read per tile
     const int H = p.H, W = p.W, cin = p.cin, cout = p.cout, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
     const float slope = p.slope;
+    const int dbg = p.dbg;
     const float* const in = p.in;
     __nv_bfloat16* const out = p.out;
     int* const err = p.err;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
     auto prefetch = [&]() {
         const int y0 = n_ty * kFirstTileH - 1, x0 = n_tx * kFirstTileW - 1;
         const float* base = in + ((size_t)n_img * cin + warp) * plane + (long long)y0 * W + x0;
-        if (!ch_on) {
+        if (!ch_on || (dbg & 2)) {
 #pragma unroll
             for (int j = 0; j < 6; ++j) pre[j] = 0.f;
         } else if (y0 >= 0 && x0 >= 0 && y0 + kFirstHaloH <= H && x0 + kFirstHaloW <= W) {      // interior tile: no bounds tests
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
         if (t + 1 < t_end) prefetch();                                       // in flight while this tile is built, multiplied, stored
         // ---- im2col: this pixel's 9 taps x 4 channels -> bf16 -> its row of the three K16 blocks
         uint32_t pk[9][2];
+        if (!(dbg & 8)) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -164,10 +167,11 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
             *reinterpret_cast<uint4*>(sA + (ch >> 1) * kFirstABlock + swz32((uint32_t)tid, (uint32_t)(ch & 1))) =
                 make_uint4(pk[2 * ch][0], pk[2 * ch][1], pk[2 * ch + 1][0], pk[2 * ch + 1][1]);
         *reinterpret_cast<uint4*>(sA + 2 * kFirstABlock + swz32((uint32_t)tid, 0u)) = make_uint4(pk[8][0], pk[8][1], 0u, 0u);
-        fence_proxy_async();                                                 // generic-proxy writes -> visible to the tensor core
+        }
+        if (!(dbg & 1)) fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && !(dbg & 1)) {
             tc_fence_after();
 #pragma unroll
             for (int kb = 0; kb < 3; ++kb)
@@ -179,13 +183,15 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
         const bool valid = y < H && x < W;
         __nv_bfloat16* op = out + (((size_t)c_img * H + y) * (size_t)W + x) * cout;
         if (++c_tx == tiles_x) { c_tx = 0; if (++c_ty == tiles_y) { c_ty = 0; ++c_img; } }
-        mbar_wait(bar, phase, err, 301);
-        phase ^= 1;
+        if (!(dbg & 1)) { mbar_wait(bar, phase, err, 301); phase ^= 1; }
         tc_fence_after();
         for (int j = 0; j < cout / 16; ++j) {
             uint32_t v[16];
-            tc_ld16(taddr + j * 16, v);
-            tc_ld_wait();
+            if (!(dbg & 1)) { tc_ld16(taddr + j * 16, v); tc_ld_wait(); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(pre[i % 6]);
+            }
             uint32_t o[8];
             const float4* b4 = reinterpret_cast<const float4*>(s_bias + j * 16);
 #pragma unroll
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
                 o[2 * i] = bf2(fmaxf(a0_, m0), fmaxf(a1_, m1));
                 o[2 * i + 1] = bf2(fmaxf(a2_, m2), fmaxf(a3_, m3));
             }
-            if (valid) {
+            if (valid && !(dbg & 4)) {
                 reinterpret_cast<uint4*>(op + j * 16)[0] = make_uint4(o[0], o[1], o[2], o[3]);
                 reinterpret_cast<uint4*>(op + j * 16)[1] = make_uint4(o[4], o[5], o[6], o[7]);
             }
@@ -210,6 +216,212 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)tmem_cols); }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Warp-specialised form (the default).  The single-role kernel above runs load -> im2col -> MMA -> drain -> store as ONE dependency
+// chain per CTA; its r02 timing experiments (PNNP_FIRST_DBG, 64 crops: 558 us; no stores 387; no im2col 387; no loads 490; no MMA
+// round trip 490; all four off 148) show the parts simply ADD.  Here they overlap inside a CTA:
+//   warps 0-3  producers: halo-tile loads (prefetched one tile ahead) -> shared fp32 tile (double-buffered) -> im2col rows of A
+//              (double-buffered) -> fence.proxy.async -> arrive a_full[b];
+//   warp  8    MMA issuer: waits a_full[b] and t_empty[b], three tcgen05.mma into accumulator b, commits to a_empty[b] and t_full[b];
+//   warps 4-7  epilogue: wait t_full[b] -> tcgen05.ld -> release the accumulator -> bias + activation -> 64-byte stores.
+// Same arithmetic, same operand layouts, same results bit for bit as the single-role kernel (tested).
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int kWsThreads = 288;
+constexpr int kWsSmem = 1024 + 2 * 3 * kFirstABlock + 3 * kFirstBBlock + 2 * 768 * 4 + 64 * 4 + 16 * 8 + 16;
+
+__global__ void __launch_bounds__(kWsThreads, 3) conv_first_ws_kernel(const FirstParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* sA = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // [2][3 x 4 KB]
+    uint8_t* sB = sA + 2 * 3 * kFirstABlock;                                        // [3 x 2 KB]
+    float* s_in = reinterpret_cast<float*>(sB + 3 * kFirstBBlock);                  // [2][768]
+    float* s_bias = s_in + 2 * 768;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);                      // a_full[2] a_empty[2] t_full[2] t_empty[2] pbar
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = p.H, W = p.W, cin = p.cin, cout = p.cout, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+    int* const err = p.err;
+    const int tmem_cols = cout <= 16 ? 32 : (cout <= 32 ? 64 : 128);                // two accumulators
+
+    for (int i = tid; i < 3 * kFirstBBlock / 16; i += kWsThreads) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 2 * kFirstABlock / 16; i += kWsThreads) {                 // K block 2 of both A buffers: taps 9..11 stay zero
+        const int b = i / (kFirstABlock / 16), r = i - b * (kFirstABlock / 16);
+        reinterpret_cast<uint4*>(sA + b * 3 * kFirstABlock + 2 * kFirstABlock)[r] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    for (int i = tid; i < cout * 36; i += kWsThreads) {
+        const int nrow = i / 36, k = i - nrow * 36, c = k & 3, tap = k >> 2;
+        if (c < cin) {
+            const int kb = k >> 4, kk = k & 15;
+            *reinterpret_cast<__nv_bfloat16*>(sB + kb * kFirstBBlock + swz32((uint32_t)nrow, (uint32_t)(kk >> 3)) + (kk & 7) * 2) =
+                __float2bfloat16_rn(p.w[(nrow * cin + c) * 9 + tap]);
+        }
+    }
+    for (int i = tid; i < 64; i += kWsThreads) s_bias[i] = (i < cout && p.bias) ? p.bias[i] : 0.f;
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bars[0 + b]), 128); mbar_init(smem_u32(&bars[2 + b]), 1);
+            mbar_init(smem_u32(&bars[4 + b]), 1);   mbar_init(smem_u32(&bars[6 + b]), 4);
+        }
+        mbar_init(smem_u32(&bars[8]), 128);
+        fence_mbarrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(s_tmem), (uint32_t)tmem_cols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[2]), t_full = smem_u32(&bars[4]), t_empty = smem_u32(&bars[6]),
+                   pbar = smem_u32(&bars[8]);
+    const int total = p.n * tiles_y * tiles_x;
+    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_begin = min(total, (int)blockIdx.x * per), t_end = min(total, t_begin + per);
+    int t_img = t_begin / (tiles_y * tiles_x), t_ty, t_tx;
+    { const int r = t_begin - t_img * (tiles_y * tiles_x); t_ty = r / tiles_x; t_tx = r - t_ty * tiles_x; }
+
+    if (warp < 4) {
+        // ============================== producers ==============================
+        const float* const in = p.in;
+        const size_t plane = (size_t)H * W;
+        int e_off[6], e_row[6], e_col[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int idx = lane + 32 * j;
+            e_row[j] = idx / kFirstHaloW;
+            e_col[j] = idx - e_row[j] * kFirstHaloW;
+            e_off[j] = e_row[j] * W + e_col[j];
+        }
+        const bool ch_on = warp < cin, last_on = lane + 160 < kFirstPlane;
+        float pre[6];
+        auto prefetch = [&]() {
+            const int y0 = t_ty * kFirstTileH - 1, x0 = t_tx * kFirstTileW - 1;
+            const float* base = in + ((size_t)t_img * cin + warp) * plane + (long long)y0 * W + x0;
+            if (!ch_on) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) pre[j] = 0.f;
+            } else if (y0 >= 0 && x0 >= 0 && y0 + kFirstHaloH <= H && x0 + kFirstHaloW <= W) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) pre[j] = __ldg(base + e_off[j]);
+                pre[5] = last_on ? __ldg(base + e_off[5]) : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int gy = y0 + e_row[j], gx = x0 + e_col[j];
+                    const bool ok = (j < 5 || last_on) && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    pre[j] = ok ? __ldg(base + e_off[j]) : 0.f;
+                }
+            }
+            if (++t_tx == tiles_x) { t_tx = 0; if (++t_ty == tiles_y) { t_ty = 0; ++t_img; } }
+        };
+        if (t_begin < t_end) prefetch();
+        const int my = tid >> 4, mx = tid & 15;
+        for (int t = t_begin, k = 0; t < t_end; ++t, ++k) {
+            const int b = k & 1;
+            float* const s_mine = s_in + b * 768 + warp * kFirstPlane + lane;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) s_mine[32 * j] = pre[j];
+            if (last_on) s_mine[160] = pre[5];
+            mbar_arrive(pbar);                                               // producer-group barrier: the fp32 tile is complete
+            if (t + 1 < t_end) prefetch();                                   // next tile's loads fly during the im2col and the waits
+            mbar_wait(pbar, (uint32_t)(k & 1), err, 311);
+            mbar_wait(a_empty + 8 * b, (uint32_t)(((k >> 1) & 1) ^ 1), err, 312);      // the MMAs that read A[b] two tiles ago are done
+            const float* const q0 = s_in + b * 768 + my * kFirstHaloW + mx;
+            uint8_t* const a = sA + b * 3 * kFirstABlock;
+            uint32_t pk[9][2];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* q = q0 + ky * kFirstHaloW + kx;
+                    pk[ky * 3 + kx][0] = bf2(q[0], q[kFirstPlane]);
+                    pk[ky * 3 + kx][1] = bf2(q[2 * kFirstPlane], q[3 * kFirstPlane]);
+                }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                *reinterpret_cast<uint4*>(a + (ch >> 1) * kFirstABlock + swz32((uint32_t)tid, (uint32_t)(ch & 1))) =
+                    make_uint4(pk[2 * ch][0], pk[2 * ch][1], pk[2 * ch + 1][0], pk[2 * ch + 1][1]);
+            *reinterpret_cast<uint4*>(a + 2 * kFirstABlock + swz32((uint32_t)tid, 0u)) = make_uint4(pk[8][0], pk[8][1], 0u, 0u);
+            fence_proxy_async();
+            mbar_arrive(a_full + 8 * b);
+        }
+    } else if (warp == 8) {
+        // ============================== MMA issuer ==============================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t dhi = umma_desc_hi(32);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        for (int t = t_begin, k = 0; t < t_end; ++t, ++k) {
+            const int b = k & 1;
+            const uint32_t par = (uint32_t)((k >> 1) & 1);
+            mbar_wait(t_empty + 8 * b, par ^ 1, err, 313);                   // the epilogue has drained accumulator b
+            mbar_wait(a_full + 8 * b, par, err, 314);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int kb = 0; kb < 3; ++kb)
+                    tc_mma_bf16(tmem_base + (uint32_t)(b * cout), umma_desc(dhi, a0 + (b * 3 + kb) * kFirstABlock),
+                                umma_desc(dhi, b0 + kb * kFirstBBlock), idesc, kb ? 1u : 0u);
+                tc_commit(a_empty + 8 * b);
+                tc_commit(t_full + 8 * b);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ============================== epilogue (warps 4..7) ==============================
+        const float slope = p.slope;
+        __nv_bfloat16* const out = p.out;
+        const int e = tid - 128, my = e >> 4, mx = e & 15;                   // accumulator row == pixel inside the tile
+        const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint64_t slope2 = f2_pack(slope, slope), zero2 = f2_pack(0.0f, 0.0f);
+        for (int t = t_begin, k = 0; t < t_end; ++t, ++k) {
+            const int b = k & 1;
+            const int y = t_ty * kFirstTileH + my, x = t_tx * kFirstTileW + mx;
+            const bool valid = y < H && x < W;
+            __nv_bfloat16* op = out + (((size_t)t_img * H + y) * (size_t)W + x) * cout;
+            if (++t_tx == tiles_x) { t_tx = 0; if (++t_ty == tiles_y) { t_ty = 0; ++t_img; } }
+            mbar_wait(t_full + 8 * b, (uint32_t)((k >> 1) & 1), err, 315);
+            tc_fence_after();
+            const uint32_t taddr = taddr0 + (uint32_t)(b * cout);
+            for (int j = 0; j < cout / 16; j += 2) {                         // two 16-column chunks per TMEM wait
+                uint32_t v[2][16];
+                const int nj = min(2, cout / 16 - j);
+                tc_ld16(taddr + j * 16, v[0]);
+                if (nj > 1) tc_ld16(taddr + (j + 1) * 16, v[1]);
+                tc_ld_wait();
+                if (j + 2 >= cout / 16) {                                    // all columns read: hand the accumulator back before the math
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + 8 * b);
+                }
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    if (h2 < nj) {
+                        uint32_t o[8];
+                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + (j + h2) * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 bb = b4[i];
+                            const uint64_t a01 = f2_add(f2_pack(__uint_as_float(v[h2][4 * i]), __uint_as_float(v[h2][4 * i + 1])), f2_pack(bb.x, bb.y));
+                            const uint64_t a23 = f2_add(f2_pack(__uint_as_float(v[h2][4 * i + 2]), __uint_as_float(v[h2][4 * i + 3])), f2_pack(bb.z, bb.w));
+                            float a0_, a1_, a2_, a3_, m0, m1, m2, m3;
+                            f2_unpack(a01, a0_, a1_); f2_unpack(a23, a2_, a3_);
+                            f2_unpack(f2_fma(a01, slope2, zero2), m0, m1); f2_unpack(f2_fma(a23, slope2, zero2), m2, m3);
+                            o[2 * i] = bf2(fmaxf(a0_, m0), fmaxf(a1_, m1));
+                            o[2 * i + 1] = bf2(fmaxf(a2_, m2), fmaxf(a3_, m3));
+                        }
+                        if (valid) {
+                            reinterpret_cast<uint4*>(op + (j + h2) * 16)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                            reinterpret_cast<uint4*>(op + (j + h2) * 16)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)tmem_cols); }
+}
+
 static int* g_first_err = nullptr;
 
 }  // namespace pnnp
@@ -218,8 +430,10 @@ using namespace pnnp;
 
 #ifdef PNNP_HOST_EMUL
 #define PNNP_FIRST_KLAUNCH(grid) emul_launch_1d(grid, kFirstThreads, [&]() { conv_first_kernel(p); })
+#define PNNP_FIRST_WS_KLAUNCH(grid) emul_launch_1d(grid, kWsThreads, [&]() { conv_first_ws_kernel(p); })
 #else
 #define PNNP_FIRST_KLAUNCH(grid) conv_first_kernel<<<grid, kFirstThreads, kFirstSmem, (cudaStream_t)stream>>>(p)
+#define PNNP_FIRST_WS_KLAUNCH(grid) conv_first_ws_kernel<<<grid, kWsThreads, kWsSmem, (cudaStream_t)stream>>>(p)
 #endif
 
 extern "C" int pnnp_conv_first_nchw(const float* in, const float* weight, const float* bias, void* out, int n, int cin, int h, int w,
@@ -235,13 +449,23 @@ extern "C" int pnnp_conv_first_nchw(const float* in, const float* weight, const 
     p.slope = act == 1 ? 0.2f : (act == 2 ? 0.f : 1.f);                      // ACT_LEAKY / ACT_RELU / ACT_NONE of the conv kernels
     if (!g_first_err) { PNNP_CUDA(cudaMalloc(&g_first_err, sizeof(int))); PNNP_CUDA(cudaMemset(g_first_err, 0, sizeof(int))); }
     p.err = g_first_err;
+    p.dbg = getenv("PNNP_FIRST_DBG") ? atoi(getenv("PNNP_FIRST_DBG")) : 0;
     int dev = 0, sms = 0;
     PNNP_CUDA(cudaGetDevice(&dev));
     PNNP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long total = (long long)n * p.tiles_y * p.tiles_x;
     if (total > 0x7FFFFFFFll) return fail("conv_first: too many tiles");
-    const int grid = (int)std::min<long long>(total, (long long)sms * 8);
-    PNNP_FIRST_KLAUNCH(grid);
+    if (variant_on("PNNP_FIRST_WS") && !p.dbg) {                           // warp-specialised form (default); =0: the single-role kernel
+#ifndef PNNP_HOST_EMUL
+        static bool attr_done = false;
+        if (!attr_done) { PNNP_CUDA(cudaFuncSetAttribute(conv_first_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem)); attr_done = true; }
+#endif
+        const int grid_ws = (int)std::min<long long>(total, (long long)sms * 3);
+        PNNP_FIRST_WS_KLAUNCH(grid_ws);
+    } else {
+        const int grid = (int)std::min<long long>(total, (long long)sms * 8);
+        PNNP_FIRST_KLAUNCH(grid);
+    }
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

@@ -250,15 +250,17 @@ class SID_Trainer(Base_Trainer):
         the device by Raw_Dataset: P1 -> D2 -> S2 -> fused N1-N3) -> UNetTrainStep (forward, L1 on pred.clamp(0,1), explicit
         backward, DDP gradient all-reduce, Adam).  Ranks take disjoint items of every epoch (same permutation on every rank)."""
         from .train import UNetTrainStep
-        if not isinstance(self.net, UNetSeeInDark):
-            raise RuntimeError("pnnp_b200: the explicit training step is built for UNetSeeInDark (runfiles/*/PNNP.yml)")
+        from .train_resunet import ResUnetTrainStep
+        if not isinstance(self.net, (UNetSeeInDark, ResUnet)):
+            raise RuntimeError("pnnp_b200: the explicit training step is built for UNetSeeInDark and ResUnet")
+        TrainStep = UNetTrainStep if isinstance(self.net, UNetSeeInDark) else ResUnetTrainStep
         dst_args = dict(self.args['dst_train'])
         if dst_args.get('ori'):
             raise RuntimeError("pnnp_b200: training with ori=True (pred * ratio inside the loss) is not built")
         self.dst_train = globals()[dst_args['dataset']](dst_args)       # trainer_SID.py:48
         self.change_eval_dst('eval')
         lr_lambda = self.get_lr_lambda_func()
-        step = UNetTrainStep(self.net, lr=lr_lambda(1))
+        step = TrainStep(self.net, lr=lr_lambda(1))
         self.train_psnr = AverageMeter('PSNR', ':2f')
         bs = int(self.hyper['batch_size'])
         phases = PhaseTimer(self.device)          # dataloader / preprocess / net+bp, as trainer_SID.py:81-123 splits a step
@@ -286,7 +288,7 @@ class SID_Trainer(Base_Trainer):
                 phases.stop()
             if losses:
                 with torch.no_grad():                                   # PSNR of the last batch, as the progress bar shows
-                    mse = (step.scr.bufs['pred'].clamp(0, 1) - imgs_hr.clamp(0, 1)).pow(2).mean()
+                    mse = (step.scr.bufs['pred'].clamp(0, 1) - imgs_hr.clamp(0, 1)).pow(2).mean()   # both steps keep `pred` there
                     self.train_psnr.update(float(-10.0 * torch.log10(mse)))
             if self.rank == 0:
                 mean_loss = float(torch.stack(losses).mean()) if losses else float('nan')

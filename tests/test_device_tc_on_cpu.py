@@ -279,6 +279,22 @@ def test_fused_first_layer_vs_torch(emu, cin, cout, h, w, n, act):
     assert (_nchw(out) - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
 
 
+def test_fused_first_layer_warp_specialised_equals_single_role_kernel(emu, monkeypatch):
+    """conv_first_ws_kernel (producers / MMA issuer / epilogue warps, double-buffered) == conv_first_kernel bit for bit."""
+    g = torch.Generator().manual_seed(77)
+    for cin, cout, h, w, n in ((4, 32, 40, 52, 2), (3, 64, 17, 33, 1), (4, 16, 8, 16, 3)):
+        x = torch.randn((n, cin, h, w), generator=g)
+        m = torch.nn.Conv2d(cin, cout, 3, padding=1)
+        outs = []
+        for ws in ("0", "1"):
+            monkeypatch.setenv("PNNP_FIRST_WS", ws)
+            out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16)
+            archs._first_conv(x.contiguous(), m, out, 1)
+            outs.append(out)
+        monkeypatch.delenv("PNNP_FIRST_WS")
+        assert torch.equal(_bits(outs[0]), _bits(outs[1])), (cin, cout, h, w, n)
+
+
 def test_fused_first_layer_leaves_the_network_forwards_unchanged(emu, monkeypatch):
     import pnnp_b200 as P
     torch.manual_seed(8)

@@ -328,6 +328,24 @@ def test_fused_first_layer(cin, cout, h, w, n, act):
     assert (_nchw(out) - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
 
 
+def test_fused_first_layer_warp_specialised_equals_single_role_kernel(monkeypatch):
+    """conv_first_ws_kernel (producer / MMA / epilogue warps, double-buffered operands and accumulators) is bit-identical to the
+    single-role conv_first_kernel: same operand layouts, same MMAs, same epilogue arithmetic."""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    for cin, cout, h, w, n in ((4, 32, 40, 52, 2), (3, 64, 17, 33, 1), (4, 16, 8, 16, 3), (4, 32, 512, 512, 5), (4, 32, 1424, 2128, 1)):
+        x = torch.randn((n, cin, h, w), device="cuda", generator=g)
+        m = torch.nn.Conv2d(cin, cout, 3, padding=1).cuda()
+        outs = []
+        for ws in ("0", "1"):
+            monkeypatch.setenv("PNNP_FIRST_WS", ws)
+            out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            archs._first_conv(x, m, out, _lib.ACT_LEAKY)
+            outs.append(out)
+        monkeypatch.delenv("PNNP_FIRST_WS")
+        _no_pipeline_error()
+        assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16)), (cin, cout, h, w, n)
+
+
 def test_fused_first_layer_equals_the_two_kernel_path(monkeypatch):
     """Same operands, same products: the fused first layer and input conversion + general conv kernel agree to the accumulation
     order of 36 fp32 terms (bf16 outputs equal except for isolated last-bit roundings), and so do the network outputs."""
