@@ -205,10 +205,7 @@ __global__ void __launch_bounds__(kFirstThreads, 8) conv_first_kernel(const Firs
                 o[2 * i] = bf2(fmaxf(a0_, m0), fmaxf(a1_, m1));
                 o[2 * i + 1] = bf2(fmaxf(a2_, m2), fmaxf(a3_, m3));
             }
-            if (valid && !(dbg & 4)) {
-                reinterpret_cast<uint4*>(op + j * 16)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                reinterpret_cast<uint4*>(op + j * 16)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            }
+            if (valid && !(dbg & 4)) st_global_256(op + j * 16, o);
         }
         tc_fence_before();                                                   // the next MMA overwrites the accumulator: ordered by the barrier
     }
@@ -408,10 +405,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_first_ws_kernel(const Firs
                             o[2 * i] = bf2(fmaxf(a0_, m0), fmaxf(a1_, m1));
                             o[2 * i + 1] = bf2(fmaxf(a2_, m2), fmaxf(a3_, m3));
                         }
-                        if (valid) {
-                            reinterpret_cast<uint4*>(op + (j + h2) * 16)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                            reinterpret_cast<uint4*>(op + (j + h2) * 16)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                        }
+                        if (valid) st_global_256(op + (j + h2) * 16, o);
                     }
                 }
             }

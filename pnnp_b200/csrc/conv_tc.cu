@@ -467,9 +467,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         for (int i = 0; i < 4; ++i) { const float4 r = rp[i]; f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w; }
                     }
                     if (p.out && valid) {
-                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.cout_stride + c0);
+                        float* op = reinterpret_cast<float*>(p.out) + opix * p.cout_stride + c0;
+                        uint32_t w0[8], w1[8];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                        for (int i = 0; i < 8; ++i) { w0[i] = __float_as_uint(f[i]); w1[i] = __float_as_uint(f[8 + i]); }
+                        st_global_256(op, w0);
+                        st_global_256(op + 8, w1);
                     }
                     if (has_pool) {
                         float m[16];
@@ -496,9 +499,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     }
                 } else if (out_nhwc) {
                     if (has_resid && valid) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + opix * p.cout_stride + c0);
-                        const uint4 r0 = rp[0], r1 = rp[1];
-                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        uint32_t rw[8];
+                        ld_global_256(p.resid + opix * p.cout_stride + c0, rw);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             f[2 * i] += __uint_as_float(rw[i] << 16);
@@ -507,9 +509,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     }
                     if (has_mask && valid) {
                         // backward of the producing layer's activation, fused: g_pre = g * act'(out), out > 0 ? 1 : slope
-                        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + opix * p.cout_stride + c0);
-                        const uint4 m0 = mp[0], m1 = mp[1];
-                        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                        uint32_t mw[8];
+                        ld_global_256(p.mask + opix * p.cout_stride + c0, mw);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             f[2 * i] *= __uint_as_float(mw[i] << 16) > 0.f ? 1.f : p.mask_slope;
@@ -522,11 +523,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                         pk[i] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    if (p.out && valid && !(PNNP_DBG_K & 1)) {
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0);
-                        op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    }
+                    if (p.out && valid && !(PNNP_DBG_K & 1))
+                        st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0, pk);     // one whole sector
                     if (has_pool) {
                         // fused nn.MaxPool2d(2): lanes l^1 hold the x-neighbour, l^16 the y-neighbour of the same tile
                         // (a warp owns two 16-pixel tile rows); max of bf16-rounded values == rounding of the max
@@ -542,9 +540,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         }
                         if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16) && !(PNNP_DBG_K & 1)) {
                             const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
-                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pp * p.cout_stride + c0);
-                            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pp * p.cout_stride + c0, pk);
                         }
                     }
                     if (has_head) {
@@ -722,7 +718,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // layers with N <= 128 take it (decided below, once the epilogue specialisation is known).
     // ConvTranspose2d fast path (specialised pixel-shuffle epilogue, resident weights): 31 -> 25, 39 -> 35, 62 -> 50 us on the Sony
     // frame's 512 / 256 / 128-channel layers, but 89 -> 95-99 us on the 64-channel full-resolution one, which keeps the generic path
-    const bool convt_fast = variant_on("PNNP_CONVT_FAST") && cin0 > 64;
+    const bool convt_fast = variant_on("PNNP_CONVT_FAST") && (cin0 > 64 || (getenv("PNNP_CONVT_FAST") && atoi(getenv("PNNP_CONVT_FAST")) > 1));
     // super-tile: measured faster on the MODE_CONV3 layers it applies to (64->64 @712x1064: 86 -> 70 us, 32->64: 64 -> 58) and
     // slower on the x-shift-in-N layers (16->32: 99 -> 109, 64->32: 134 -> 146), which therefore stay on single tiles
     const int super_env = getenv("PNNP_CONV_SUPER") ? atoi(getenv("PNNP_CONV_SUPER")) : (mode == MODE_CONV3 ? 1 : 0);

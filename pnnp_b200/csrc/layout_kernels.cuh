@@ -68,8 +68,13 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc16_bf16_x4_kernel(const f
                 const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
                 pk[k] = *reinterpret_cast<const uint32_t*>(&hh);
             }
+#ifndef PNNP_HOST_EMUL
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"       // one whole 32-byte sector per instruction
+                         ::"l"(o + 2 * px), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+#else
             o[2 * px] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             o[2 * px + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#endif
         }
     }
 }

@@ -223,7 +223,20 @@ struct FastC {                              // per-crop constants
 // Three CTAs (24 warps) per SM at 79 registers without spills.  Measured alternatives (r01): four CTAs at 64 registers spill and
 // run 15 % slower; reading the Poisson table through L1 instead of a per-CTA shared-memory copy (41 KB instead of 65 KB of
 // shared memory) is 12 % slower at equal occupancy.
-template <bool DEBUG>
+// EXP: timing experiments only (PNNP_SYNTH_EXP, never part of a result): bit 0 no Poisson samplers (count = round(rate)), bit 1 no
+// Tukey-lambda quantile, bit 2 no sorting by sampler (queue slot = own slot), bit 3 no Philox rounds (counter mixed with two
+// multiplies).  EXP = 0 is the product kernel; the others measure what each part costs ("measured floor").
+template <int EXP>
+__device__ __forceinline__ uint4 exp_block(const RngCtx& rng, uint64_t index, uint32_t stream, uint32_t sub) {
+    if constexpr ((EXP & 8) != 0) {
+        const uint32_t x = (uint32_t)index * 0x9E3779B9u + sub * 0x85EBCA6Bu + stream;
+        return make_uint4(x, x * 0xC2B2AE35u, x ^ 0x27D4EB2Fu, x * 0x165667B1u);
+    } else {
+        return rng.block(index, stream, sub);
+    }
+}
+
+template <bool DEBUG, int EXP = 0>
 __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const SynthArgs a) {
     // dynamic shared memory (kFastSmemBytes > 48 KB): [warps][512] uint2 queue | [warps][512] uint16 positions | Poisson table
     extern __shared__ __align__(16) uint8_t s_fast[];
@@ -296,7 +309,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
             const bool valid = x < a.w;
             const unsigned m_valid = __ballot_sync(0xffffffffu, valid);
             const float4 yv = j == 0 ? ybuf[0] : (j == 1 ? ybuf[1] : (j == 2 ? ybuf[2] : ybuf[3]));
-            const uint4 b0 = rng.block((g_base + x) >> 2, kStreamElem, 0u);      // (g_base + x) % 4 == 0 on this path
+            const uint4 b0 = exp_block<EXP>(rng, (g_base + x) >> 2, kStreamElem, 0u);      // (g_base + x) % 4 == 0 on this path
             const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
             const uint32_t ws[4] = {b0.x, b0.y, b0.z, b0.w};
             uint32_t pq[4];
@@ -304,6 +317,11 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
             for (int e = 0; e < 4; ++e) {
                 const float ysc = div_rn_by_const(__fmul_rn(ys[e], f.span32), f.ratio32, f.rratio32);
                 const float lam = ysc * f.invK32;
+                if constexpr ((EXP & 4) != 0) {                               // experiment: no sorting, every entry in its own slot
+                    pq[e] = (uint32_t)((j * 32 + lane) * 4 + e);
+                    if (valid) q[pq[e]] = make_uint2(__float_as_uint(lam), ws[e]);
+                    n_small = kFastUnit;
+                } else {
                 const bool small = lam < kPoissonSwitch;
                 const unsigned m_small = __ballot_sync(0xffffffffu, small && valid);
                 const unsigned m_large = m_valid & ~m_small;
@@ -313,6 +331,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
                 if (valid) q[pq[e]] = make_uint2(__float_as_uint(lam), ws[e]);
                 n_small += __popc(m_small);
                 n_large += __popc(m_large);
+                }
             }
             *reinterpret_cast<uint2*>(qpos + (j * 32 + lane) * 4) = make_uint2(pq[0] | (pq[1] << 16), pq[2] | (pq[3] << 16));
         }
@@ -320,11 +339,14 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
         // ---- phase 2: each sampler over its part of the queue, all lanes busy; the count replaces the rate in place
         for (int i = lane; i < n_small; i += 32) {
             const uint2 en = q[i];
-            q[i].x = __float_as_uint(poisson_small_table(__uint_as_float(en.x), en.y, s_pois));
+            if constexpr ((EXP & 1) != 0) q[i].x = __float_as_uint(rintf(__uint_as_float(en.x)) + (float)(en.y >> 31));
+            else if constexpr ((EXP & 4) != 0) q[i].x = __float_as_uint(poisson_sample(__uint_as_float(en.x), en.y, s_pois));
+            else q[i].x = __float_as_uint(poisson_small_table(__uint_as_float(en.x), en.y, s_pois));
         }
         for (int i = lane; i < n_large; i += 32) {
             const uint2 en = q[kFastUnit - 1 - i];
-            q[kFastUnit - 1 - i].x = __float_as_uint(poisson_large(__uint_as_float(en.x), en.y));
+            if constexpr ((EXP & 1) != 0) q[kFastUnit - 1 - i].x = __float_as_uint(rintf(__uint_as_float(en.x)) + (float)(en.y >> 31));
+            else q[kFastUnit - 1 - i].x = __float_as_uint(poisson_large(__uint_as_float(en.x), en.y));
         }
         __syncwarp();
         // ---- phase 3: read noise + quantisation + tail (needs the counts, not the clean pixels)
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
             const int x = x0 + (j * 32 + lane) * 4;
             if (x < a.w) {
                 const uint64_t grp = (g_base + x) >> 2;
-                const uint4 b1 = rng.block(grp, kStreamElem, 1u);
+                const uint4 b1 = exp_block<EXP>(rng, grp, kStreamElem, 1u);
                 const uint32_t mix[4] = {b1.x, b1.y, b1.z, b1.w};
                 const uint2 pp = *reinterpret_cast<const uint2*>(qpos + (j * 32 + lane) * 4);
                 const uint32_t pq[4] = {pp.x & 0xFFFFu, pp.x >> 16, pp.y & 0xFFFFu, pp.y >> 16};
@@ -344,6 +366,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
                     const uint32_t rf[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) d_read[e] = tukey_lambda_ppf(read_word(mix[e], rf[e]), f.lam_tl, f.inv_lam_tl) * f.sigTL32;
+                } else if constexpr ((EXP & 2) != 0) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d_read[e] = (__uint_as_float(0x3F800000u | (mix[e] >> 9)) - 1.5f) * f.sigTL32;
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) d_read[e] = tukey_lambda_ppf_body(mix[e], f.lam_tl, f.inv_lam_tl) * f.sigTL32;

@@ -76,7 +76,18 @@ static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
             PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
             attr_done = true;
         }
-        noise_synth_fast_kernel<DEBUG><<<(int)std::min<long long>(fwant, (long long)sms * 3), kFastThreads, kFastSmemBytes, st>>>(b);
+        const int fgrid = (int)std::min<long long>(fwant, (long long)sms * 3);
+        const int exp_sw = DEBUG ? 0 : (getenv("PNNP_SYNTH_EXP") ? atoi(getenv("PNNP_SYNTH_EXP")) : 0);     // timing experiments only
+        if (exp_sw) {
+#define PNNP_EXP_CASE(E) case E: PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<false, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes)); \
+                                 noise_synth_fast_kernel<false, E><<<fgrid, kFastThreads, kFastSmemBytes, st>>>(b); break;
+            switch (exp_sw) {
+                PNNP_EXP_CASE(1) PNNP_EXP_CASE(2) PNNP_EXP_CASE(3) PNNP_EXP_CASE(5) PNNP_EXP_CASE(7) PNNP_EXP_CASE(8) PNNP_EXP_CASE(15)
+                default: return fail("noise_synth: unknown PNNP_SYNTH_EXP combination");
+            }
+#undef PNNP_EXP_CASE
+        } else
+        noise_synth_fast_kernel<DEBUG><<<fgrid, kFastThreads, kFastSmemBytes, st>>>(b);
     }
     else if (chain == PNNP_CHAIN_NUMPY) { if (vec) PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 4); else PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 1); }
     else                                { if (vec) PNNP_LAUNCH(PNNP_CHAIN_TORCH, 4); else PNNP_LAUNCH(PNNP_CHAIN_TORCH, 1); }

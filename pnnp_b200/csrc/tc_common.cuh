@@ -103,6 +103,18 @@ __device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm(
 __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+// 256-bit global accesses (sm_100: LDG / STG.E.ENL2.256): one whole 32-byte sector per lane and instruction.  The NHWC epilogues write 32
+// bytes (16 bf16 channels) per thread and chunk; as two 128-bit stores every warp instruction put 16 bytes into each of 32 sectors and the
+// L2 slices saw two byte-masked requests per sector (r02 capture: lts throughput 55-74 % on the store-heavy layers at 20-45 % DRAM).
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
 __device__ __forceinline__ uint64_t umma_desc_hi(int swz) {

@@ -280,6 +280,9 @@ static inline void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = g_tmem[lane0 + lane][col + i];
 }
 
+static inline void st_global_256(void* p, const uint32_t (&v)[8]) { std::memcpy(p, v, 32); }
+static inline void ld_global_256(const void* p, uint32_t (&v)[8]) { std::memcpy(v, p, 32); }
+
 // packed fp32 pairs
 static inline uint64_t f2_pack(float a, float b) { return (uint64_t)__float_as_uint(a) | ((uint64_t)__float_as_uint(b) << 32); }
 static inline void f2_unpack(uint64_t v, float& a, float& b) { a = __uint_as_float((uint32_t)v); b = __uint_as_float((uint32_t)(v >> 32)); }
