@@ -151,7 +151,8 @@ class UNetTrainStep:
     def close(self):
         """Drop the captured graphs (they hold NCCL work under DDP) — call before torch.distributed.destroy_process_group()."""
         self._graphs.clear()
-        torch.cuda.synchronize(self.device)
+        if torch.device(self.device).type == "cuda":
+            torch.cuda.synchronize(self.device)
 
     def sync_parameters(self, src=0):
         """Every rank starts from (and, after a checkpoint reload, continues from) rank `src`'s parameters, as the

@@ -99,7 +99,8 @@ class ResUnetTrainStep:
 
     # ---------------------------------------------------------------- helpers
     def close(self):
-        torch.cuda.synchronize(self.device)
+        if torch.device(self.device).type == "cuda":
+            torch.cuda.synchronize(self.device)
 
     def _stream(self):
         return _lib.stream_ptr(self.device)
