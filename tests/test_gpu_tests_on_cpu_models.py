@@ -110,3 +110,10 @@ def test_experimental_act_backward_v2(cuda_is_the_host, monkeypatch, act_kind):
 def test_experimental_wgrad_v2(cuda_is_the_host, monkeypatch):
     import test_gpu_variants as E
     E.test_wgrad_v2_matches_autograd_like_the_default_kernel(monkeypatch)
+
+
+def test_resunet_backward_on_the_cpu_models(cuda_is_the_host):
+    """train_resunet.ResUnetTrainStep (round 2): residual blocks, 1x1 shortcuts, stride-2 convs through zero-inserted gradients —
+    the product's host code with every launch on the CPU models, against fp32 autograd through the oracle's functional ResUnet."""
+    import test_gpu_train_resunet as R
+    R.test_resunet_backward_matches_fp32_autograd()
