@@ -540,7 +540,7 @@ def run_gpu_arm(args, name, wl):
         e2e_metrics = {}
 
         def e2e_step():
-            sums = pipe.run(raw_host, table=table, generator=gen, crop_id0=crop0)
+            sums = pipe.run(raw_host, table=table, generator=gen, crop_id0=crop0, next_host=raw_host)      # batches arrive one ahead
             torch.cuda.current_stream().synchronize()            # the metric sums are on the host: the step's result
             rows = finish_metrics(sums, c, h, w)
             ps, ss = sum(r["PSNR"] for r in rows), sum(r["SSIM"] for r in rows)

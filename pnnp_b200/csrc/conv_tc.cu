@@ -398,6 +398,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             if (PNNP_DBG_K & 8) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc])); acc_phase ^= 1; continue; }
             const int col_tile0 = n_tile * p.umma_n;     // first GEMM column of this tile
             const size_t pix_in = ((size_t)img * p.H + y) * (size_t)p.W + x;
+            // per-tile addresses hoisted out of the chunk loop (the asm statements' memory clobbers make the compiler re-read the
+            // parameter bank and redo the 64-bit products per 16-channel chunk otherwise)
+            const size_t pool_off = has_pool ? (((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1)) * (size_t)p.cout_stride : 0;
+            const size_t out_off = pix_in * (size_t)p.cout_stride;
             float head[4] = {0.f, 0.f, 0.f, 0.f};
             // specialised ConvTranspose2d epilogue: (tap, channel block) of chunk j kept as a running pair — one division per tile
             constexpr bool kCtT = EPI >= 0 && (EPI & EPI_CONVT) != 0;
@@ -550,7 +554,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         pk[i] = *reinterpret_cast<const uint32_t*>(&h);
                     }
                     if (p.out && valid && !(PNNP_DBG_K & 1))
-                        st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.cout_stride + c0, pk);     // one whole sector
+                        st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + (is_convt ? opix * p.cout_stride : out_off) + c0, pk);     // one whole sector
                     if (has_pool) {
                         // fused nn.MaxPool2d(2): lanes l^1 hold the x-neighbour, l^16 the y-neighbour of the same tile
                         // (a warp owns two 16-pixel tile rows); max of bf16-rounded values == rounding of the max
@@ -565,8 +569,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             pk[i] = *reinterpret_cast<uint32_t*>(&a);
                         }
                         if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16) && !(PNNP_DBG_K & 1)) {
-                            const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
-                            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pp * p.cout_stride + c0, pk);
+                            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pool_off + c0, pk);
                         }
                     }
                     if (has_head) {

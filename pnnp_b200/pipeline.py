@@ -80,7 +80,7 @@ class EvalPipeline:
         import torch.nn.functional as F  # noqa: F401
         self.net, self.H, self.W, self.wp, self.bl = net, H, W, wp, bl
         self.noise_code, self.ori, self.correct = noise_code, ori, brightness_correct
-        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.copy_stream = torch.cuda.Stream(self.device)
         self.d_raw = [torch.empty((H, W), dtype=torch.int16, device=self.device) for _ in range(depth)]
         self.h_sums = [torch.empty((1, 7), dtype=torch.float64).pin_memory() for _ in range(depth)]
@@ -131,7 +131,7 @@ class SynthDenoisePipeline:
     def __init__(self, net, n, H, W, wp, bl, noise_code, device=None, chunk=16, post_clip=(-float("inf"), 1.0), depth=2):
         self.net, self.n, self.H, self.W, self.wp, self.bl = net, n, H, W, wp, bl
         self.noise_code, self.post_clip = noise_code, post_clip
-        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.chunk = min(chunk, n)
         self.copy_stream = torch.cuda.Stream(self.device)
         self.d_raw = [torch.empty((self.chunk, H, W), dtype=torch.int16, device=self.device) for _ in range(depth)]
@@ -140,10 +140,12 @@ class SynthDenoisePipeline:
         self.h_sums = torch.empty((n, 7), dtype=torch.float64).pin_memory()
         self.slot = 0
 
-    def run(self, host_raw_i16, params=None, table=None, generator=None, crop_id0=0, seed_offset=None):
+    def run(self, host_raw_i16, params=None, table=None, generator=None, crop_id0=0, seed_offset=None, next_host=None):
         """host_raw_i16: pinned CPU int16 tensor (n, H, W) holding the uint16 sensor codes of n RAW crops; params: n reference-style
         parameter dicts (or a ParamTable).  Returns the pinned (n, 3 + c) float64 tensor of partial sums (metrics.finish_metrics turns
-        a row into PSNR / SSIM), valid once the current stream has been synchronised."""
+        a row into PSNR / SSIM), valid once the current stream has been synchronised.
+        next_host: the batch the NEXT call will be given (a DataLoader hands batches over one ahead): its first chunk's H2D copy is
+        issued behind this batch's last one, so it overlaps this batch's kernels instead of opening the next call."""
         from .isp_ops import raw2bayer
         from .metrics import eval_partial_sums
         n = self.n
@@ -153,15 +155,25 @@ class SynthDenoisePipeline:
         if seed_offset is None:
             seed_offset = (default_generator if generator is None else generator).next()
         cur = torch.cuda.current_stream(self.device)
+        pre = getattr(self, "_prefetched", None)
+        self._prefetched = None
         with torch.no_grad():
             for s0 in range(0, n, self.chunk):
                 m = min(self.chunk, n - s0)
                 k = self.slot
                 self.slot = (self.slot + 1) % len(self.d_raw)
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_event(self.consumed[k])            # the previous user of this slot has packed it
-                    self.d_raw[k][:m].copy_(host_raw_i16[s0:s0 + m], non_blocking=True)
-                    self.ready[k].record(self.copy_stream)
+                if not (s0 == 0 and pre == (host_raw_i16.data_ptr(), k)):    # else: already on its way (prefetched by the previous call)
+                    with torch.cuda.stream(self.copy_stream):
+                        self.copy_stream.wait_event(self.consumed[k])        # the previous user of this slot has packed it
+                        self.d_raw[k][:m].copy_(host_raw_i16[s0:s0 + m], non_blocking=True)
+                        self.ready[k].record(self.copy_stream)
+                if s0 + self.chunk >= n and next_host is not None:           # last chunk issued: start on the next batch
+                    kn = self.slot
+                    with torch.cuda.stream(self.copy_stream):
+                        self.copy_stream.wait_event(self.consumed[kn])
+                        self.d_raw[kn][:min(self.chunk, n)].copy_(next_host[0:min(self.chunk, n)], non_blocking=True)
+                        self.ready[kn].record(self.copy_stream)
+                    self._prefetched = (next_host.data_ptr(), kn)
                 cur.wait_event(self.ready[k])
                 hr = raw2bayer(self.d_raw[k][:m], wp=self.wp, bl=self.bl, norm=True, clip=True)
                 self.consumed[k].record(cur)
