@@ -29,6 +29,7 @@ def initialize_weights(net):
 
 import os
 _X_MODE = os.environ.get("PNNP_NO_XMODE") is None
+_XMODE_MAX_COUT = int(os.environ.get("PNNP_XMODE_MAX_COUT", "32"))     # single-source layers up to this width take the x-shift-in-N mode
 
 
 def _pad16(c):
@@ -188,7 +189,7 @@ class _TCNet(nn.Module):
         128 x Cout MMA cannot amortise its A-operand read), the per-tap mode otherwise."""
         # measured on B200 (profiles/): x-mode wins when 3*Cout <= 128 (four TMEM accumulators / epilogue groups
         # stay available) or when K is long (two-source decoder convs); otherwise the per-tap mode does.
-        narrow = cout <= 32 or (cout <= 64 and kw.get("x1") is not None)
+        narrow = cout <= _XMODE_MAX_COUT or (cout <= 64 and kw.get("x1") is not None)
         if narrow and cout % 16 == 0 and kw.get("resid") is None and _X_MODE:
             w, b = self._packed(name, "conv3x")
             return _conv(_lib.CONV3X, x0, w, b, out, cout, act, **kw)
