@@ -19,6 +19,8 @@ run memcheck pack_crops_eval 300 tests/test_gpu_pack.py tests/test_gpu_crops.py 
 run memcheck noise 400 tests/test_gpu_noise.py -k "replay_bit_exact_vs_reference or philox_kernel_uses or shard_independence or row_noise or reference_signatures or tail_refinement"
 run memcheck unet 400 tests/test_gpu_unet.py -k "$SEL"
 run memcheck train 400 tests/test_gpu_train.py -k "act_backward or adam or conv_transpose_backward or head_backward or l1_loss or maxpool_backward or wgrad_nhwc"
+run memcheck round2_kernels 500 tests/test_gpu_unet.py tests/test_gpu_pipeline.py tests/test_gpu_train_resunet.py -k "fused_first and not 1424 and not 512 or tf32 and not under_any_init or pipeline_equals or resunet_backward"
+run racecheck first_layer 400 tests/test_gpu_unet.py -k "fused_first and not 1424 and not 512"
 run racecheck noise_eval 400 tests/test_gpu_noise.py tests/test_gpu_eval.py -k "philox_kernel_uses or shard_independence or psnr_ssim or identical"
 run racecheck unet_train 400 tests/test_gpu_unet.py tests/test_gpu_train.py -k "conv3x3_layer or fused_pool or x_shift or head_backward or maxpool_backward or l1_loss or act_backward"
 cat "$OUT/summary.txt"
