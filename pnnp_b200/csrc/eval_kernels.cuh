@@ -107,19 +107,29 @@ __global__ void __launch_bounds__(256) ssim_mse_kernel(const float* __restrict__
     if (threadIdx.x == 0) { atomicAdd(&sums[frame * stride + 2], se); atomicAdd(&sums[frame * stride + 3 + ch], ssum); }
 }
 
-// pass 2, separable form (ssim_core.cuh): one block = one 32 x 16 tile of window centres of one (frame, channel) plane
+// pass 2, separable form (ssim_core.cuh): one block = kS2TilesPerCta vertically adjacent 32 x 16 tiles of window centres of one
+// (frame, channel) plane.  The two partial sums stay in registers across the block's tiles and are reduced and added to the frame's
+// accumulators ONCE per block: with one tile per block every block ended in two float64 atomics on the same two addresses per frame
+// (65 536 same-address atomics per 16 crops serialise in L2 — the whole kernel's 291 us in r02, whatever the arithmetic cost).
+constexpr int kS2TilesPerCta = 8;
 __global__ void __launch_bounds__(kS2Threads) ssim_mse_v2_kernel(Ssim2Args g, double* sums, int stride) {
     extern __shared__ __align__(16) uint8_t s2_raw[];
     Ssim2Tile& t = *reinterpret_cast<Ssim2Tile*>(s2_raw);
     PNNP_SMEM double s_red[8];
     const int plane_id = blockIdx.z, frame = plane_id / g.c, ch = plane_id - frame * g.c;
     if (g.use_gain) g.gain = (float)sums[frame * stride + 0] / (float)sums[frame * stride + 1];   // num / den in float32 like torch
-    const int x0 = blockIdx.x * kS2TileX, y0 = blockIdx.y * kS2TileY;
-    double se = ssim2_load(threadIdx.x, g, plane_id, x0, y0, t);
-    __syncthreads();
-    ssim2_hsum(threadIdx.x, t);
-    __syncthreads();
-    double ssum = ssim2_vsum(threadIdx.x, g, x0, y0, t);
+    const int x0 = blockIdx.x * kS2TileX;
+    double se = 0.0, ssum = 0.0;
+    for (int k = 0; k < kS2TilesPerCta; ++k) {
+        const int y0 = (blockIdx.y * kS2TilesPerCta + k) * kS2TileY;
+        if (y0 >= g.h) break;
+        se += ssim2_load(threadIdx.x, g, plane_id, x0, y0, t);
+        __syncthreads();
+        ssim2_hsum(threadIdx.x, t);
+        __syncthreads();
+        ssum += ssim2_vsum(threadIdx.x, g, x0, y0, t);
+        __syncthreads();                            // the tile buffers are reused by the next tile
+    }
     se = block_reduce_sum(se, s_red);
     ssum = block_reduce_sum(ssum, s_red);
     if (threadIdx.x == 0) { atomicAdd(&sums[frame * stride + 2], se); atomicAdd(&sums[frame * stride + 3 + ch], ssum); }

@@ -39,7 +39,7 @@ extern "C" int pnnp_eval_epilogue(const float* dn, const float* hr, int n, int c
             attr_done = true;
         }
         Ssim2Args a{dn, hr, c, h, w, scale, 1.0f, brightness_correct};
-        dim3 gv((w + kS2TileX - 1) / kS2TileX, (h + kS2TileY - 1) / kS2TileY, n * c);
+        dim3 gv((w + kS2TileX - 1) / kS2TileX, ((h + kS2TileY - 1) / kS2TileY + kS2TilesPerCta - 1) / kS2TilesPerCta, n * c);
         ssim_mse_v2_kernel<<<gv, kS2Threads, sizeof(Ssim2Tile), st>>>(a, sums, stride);
         count_launch();
         PNNP_CUDA(cudaGetLastError());

@@ -1,4 +1,4 @@
-// Separable form of the SSIM / squared-error pass of eval_metrics.cu (OPT-IN, PNNP_SSIM_V2=1, until measured on a B200).
+// Separable form of the SSIM / squared-error pass of eval_metrics.cu (the default since r02; PNNP_SSIM_V2=0: the first form).
 //
 // The 7x7 uniform-window sums of skimage's structural_similarity (utils/visualization.py:29-30) are separable: for each of the
 // five quantities (a, b, a^2, b^2, ab) a horizontal 7-sum per patch row, then a vertical 7-sum per window centre — 2 x 7 float64
@@ -59,41 +59,76 @@ __device__ __forceinline__ double ssim2_load(int tid, const Ssim2Args& g, int pl
     return se;
 }
 
-// phase 2: horizontal 7-sums, one (patch row, centre column) per item
+// Four adjacent 7-sums w_k = v[k] + ... + v[k + 6] (k = 0..3) of ten values share their terms: the core v[3..6] is common to all
+// four, v[1] + v[2] to w0 and w1, v[7] + v[8] to w2 and w3 — 13 additions instead of 24, only additions (no running-sum subtraction,
+// hence no cancellation), each w_k still the sum of its own seven values in a fixed association.
+__device__ __forceinline__ void ssim2_sums4(const double (&v)[10], double (&w)[4]) {
+    const double core = (v[3] + v[4]) + (v[5] + v[6]);
+    const double p12 = v[1] + v[2], p78 = v[7] + v[8];
+    w[0] = core + (v[0] + p12);
+    w[1] = core + (p12 + v[7]);
+    w[2] = core + (v[2] + p78);
+    w[3] = core + (p78 + v[9]);
+}
+
+// four consecutive doubles as two 16-byte stores (lanes are 32 bytes apart: 16-byte stores are conflict-free, 8-byte ones 8-way)
+__device__ __forceinline__ void ssim2_store4(double* p, const double (&w)[4]) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(w[0], w[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(w[2], w[3]);
+}
+
+// phase 2: horizontal 7-sums; one item = (patch row, group of FOUR adjacent centre columns): ten pixels loaded, converted and multiplied
+// once (the first form loaded, converted and multiplied every pixel seven times: 70 float64 operations per output, 29 now)
 __device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t) {
-    for (int i = tid; i < kS2PatchY * kS2TileX; i += kS2Threads) {
-        const int py = i / kS2TileX, lx = i - py * kS2TileX;
-        double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+    constexpr int kGroups = kS2TileX / 4;
+    for (int i = tid; i < kS2PatchY * kGroups; i += kS2Threads) {
+        const int py = i / kGroups, lx = (i - py * kGroups) * 4;
+        double a[10], b[10], aa[10], bb[10], ab[10], w[4];
 #pragma unroll
-        for (int dx = 0; dx < kS2Win; ++dx) {
-            const double a = t.a[py][lx + dx], b = t.b[py][lx + dx];
-            sa += a; sb += b; saa += a * a; sbb += b * b; sab += a * b;
+        for (int k = 0; k < 10; ++k) {
+            a[k] = t.a[py][lx + k]; b[k] = t.b[py][lx + k];
+            aa[k] = a[k] * a[k]; bb[k] = b[k] * b[k]; ab[k] = a[k] * b[k];
         }
-        t.hs[0][py][lx] = sa; t.hs[1][py][lx] = sb; t.hs[2][py][lx] = saa; t.hs[3][py][lx] = sbb; t.hs[4][py][lx] = sab;
+        ssim2_sums4(a, w);
+        ssim2_store4(&t.hs[0][py][lx], w);
+        ssim2_sums4(b, w);
+        ssim2_store4(&t.hs[1][py][lx], w);
+        ssim2_sums4(aa, w);
+        ssim2_store4(&t.hs[2][py][lx], w);
+        ssim2_sums4(bb, w);
+        ssim2_store4(&t.hs[3][py][lx], w);
+        ssim2_sums4(ab, w);
+        ssim2_store4(&t.hs[4][py][lx], w);
     }
 }
 
-// phase 3: vertical 7-sums + the SSIM map value per valid window centre; returns this thread's share of the map's sum
+// phase 3: vertical 7-sums + the SSIM map value; one item = (centre column, group of FOUR adjacent centre rows): ten rows of horizontal
+// sums loaded once per quantity; returns this thread's share of the map's sum
 __device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Tile& t) {
     const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
     const double inv_np = 1.0 / 49.0, cov_norm = 49.0 / 48.0;
     double ssum = 0.0;
-    for (int i = tid; i < kS2TileY * kS2TileX; i += kS2Threads) {
-        const int ly = i / kS2TileX, lx = i - ly * kS2TileX;
-        const int cx = x0 + lx, cy = y0 + ly;
-        if (cx < kS2Pad || cx >= g.w - kS2Pad || cy < kS2Pad || cy >= g.h - kS2Pad) continue;
-        double s[5];
+    for (int i = tid; i < (kS2TileY / 4) * kS2TileX; i += kS2Threads) {
+        const int lg = i / kS2TileX, lx = i - lg * kS2TileX, ly0 = lg * 4;
+        const int cx = x0 + lx;
+        if (cx < kS2Pad || cx >= g.w - kS2Pad) continue;
+        double s[5][4];
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            double v = 0.0;
+            double v[10];
 #pragma unroll
-            for (int dy = 0; dy < kS2Win; ++dy) v += t.hs[q][ly + dy][lx];
-            s[q] = v;
+            for (int k = 0; k < 10; ++k) v[k] = t.hs[q][ly0 + k][lx];
+            ssim2_sums4(v, s[q]);
         }
-        const double ux = s[0] * inv_np, uy = s[1] * inv_np;
-        const double vx = cov_norm * (s[2] * inv_np - ux * ux), vy = cov_norm * (s[3] * inv_np - uy * uy);
-        const double vxy = cov_norm * (s[4] * inv_np - ux * uy);
-        ssum += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cy = y0 + ly0 + k;
+            if (cy < kS2Pad || cy >= g.h - kS2Pad) continue;
+            const double ux = s[0][k] * inv_np, uy = s[1][k] * inv_np;
+            const double vx = cov_norm * (s[2][k] * inv_np - ux * ux), vy = cov_norm * (s[3][k] * inv_np - uy * uy);
+            const double vxy = cov_norm * (s[4][k] * inv_np - ux * uy);
+            ssum += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+        }
     }
     return ssum;
 }

@@ -40,6 +40,8 @@ static inline double __dsqrt_rn(double a) { return sqrt(a); }
 static inline double __drcp_rn(double a) { return 1.0 / a; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline float __double2float_rn(double a) { return (float)a; }
+struct alignas(16) double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }

@@ -120,7 +120,8 @@ int emul_eval_epilogue(const float* dn, const float* hr, int n, int c, int h, in
     if (brightness_correct) SIMT_LAUNCH3(dots_blocks, n, 1, 256, (illum_dots_kernel(dn, hr, per_frame, scale, sums, stride)));
     if (v2) {
         const Ssim2Args a{dn, hr, c, h, w, scale, 1.0f, brightness_correct};
-        SIMT_LAUNCH3((w + kS2TileX - 1) / kS2TileX, (h + kS2TileY - 1) / kS2TileY, n * c, kS2Threads, (ssim_mse_v2_kernel(a, sums, stride)));
+        SIMT_LAUNCH3((w + kS2TileX - 1) / kS2TileX, ((h + kS2TileY - 1) / kS2TileY + kS2TilesPerCta - 1) / kS2TilesPerCta, n * c, kS2Threads,
+                     (ssim_mse_v2_kernel(a, sums, stride)));
     } else {
         SIMT_LAUNCH3((w + kTileX - 1) / kTileX, (h + kTileY - 1) / kTileY, n * c, 256,
                      (ssim_mse_kernel(dn, hr, c, h, w, scale, brightness_correct, sums, stride)));
