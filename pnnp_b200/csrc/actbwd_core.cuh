@@ -1,4 +1,4 @@
-// act_bwd_bias, second form (OPT-IN, PNNP_ACTBWD_V2=1, until measured): the same in-place  g *= act'(out)  and per-channel bias
+// act_bwd_bias, second form (the default since r02; PNNP_ACTBWD_V2=0 for the first form): the same in-place  g *= act'(out)  and per-channel bias
 // gradient as act_bwd_bias_kernel (train_kernels.cu), without the 64-bit `i % (c/8)` per 16-byte item that makes up more than half of
 // that kernel's executed instructions: c/8 is a power of two and the grid stride is a multiple of it, so a thread's channel group
 // is  start & (c/8 - 1)  once and for all; item indices are 32-bit.

@@ -158,7 +158,7 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
 // 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
 // the narrow full-resolution layers are bound by the epilogue's instruction count, and most of it was run-time feature tests.
 constexpr int EPI_GENERIC = -1, EPI_X = 1, EPI_POOL = 2, EPI_HEAD = 4, EPI_MASK = 8;   // bit 3: activation-derivative mask (training dgrad)
-constexpr int EPI_CONVT = 16;           // bit 4: ConvTranspose2d pixel-shuffle store (bf16 NHWC, bias only) — opt-in, see conv_layer_launch
+constexpr int EPI_CONVT = 16;           // bit 4: ConvTranspose2d pixel-shuffle store (bf16 NHWC, bias only) — default for > 64 input channels since r02, see conv_layer_launch
 // SUP: super-tile.  One pipeline stage carries a 16-row box (8 + 8 + 2 halo rows, ONE TMA load) and feeds TWO M = 128 tiles —
 // rows 0-7 into accumulator buffer a, rows 8-15 (A descriptor start + 128 pixel rows) into buffer a + 1 — so the producer <-> MMA
 // hand-shake, which bounds the small-K full-resolution layers, is paid once per 256 pixels, and a tile's halo
@@ -167,7 +167,7 @@ constexpr int EPI_CONVT = 16;           // bit 4: ConvTranspose2d pixel-shuffle 
 // grid of the stream before its first global-memory access (see the top of the body).  Both are compile-time so that the
 // default instantiations (VAR = 0) keep exactly the machine code that was measured in round 1.
 // VAR bit 2 = X2: the epilogue's fp32 arithmetic (x-mode partial-sum combine, bias + activation, fused 1x1 head) in packed pairs —
-// the same IEEE additions / FMAs, half the instructions (opt-in, PNNP_CONV_F32X2=1).
+// the same IEEE additions / FMAs, half the instructions (default since r02; PNNP_CONV_F32X2=0 switches it off).
 template <int TPS, int K16S, int EPI, int VAR = 0>
 __global__ void __launch_bounds__(kConvThreadsMax, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -179,10 +179,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // weights are fp32 in HBM and shared memory, the MMAs are kind::tf32 (K = 8 per 32-byte slice, so the same slice / swizzle /
     // descriptor arithmetic applies with kc = span / 4 channels per chunk), the epilogue stores fp32 NHWC.  Generic epilogue only.
     constexpr bool kF32 = (VAR & 8) != 0;
-    // Opt-in variants (VAR != 0) with a specialised epilogue are never launched with debug switches, so their mode (bits 0 / 4 of
+    // Variant instantiations (VAR != 0; the defaults since r02) with a specialised epilogue are never launched with debug switches, so their mode (bits 0 / 4 of
     // EPI), the debug word and the swizzle span (32 bytes per K16 slice) are compile-time constants: the serial loops of the
     // producer and MMA warps — whose instruction count IS the tile rate of the small-K layers — lose their run-time selects.
-    constexpr bool kCt = VAR != 0 && EPI >= 0;       // every opt-in instantiation with a specialised epilogue (the launcher never
+    constexpr bool kCt = VAR != 0 && EPI >= 0;       // every variant instantiation with a specialised epilogue (the launcher never
     constexpr int kCtMode = (EPI >= 0 && (EPI & EPI_CONVT)) ? MODE_CONVT : ((EPI >= 0 && (EPI & EPI_X)) ? MODE_CONV3X : MODE_CONV3);   // pairs those with debug switches)
 #define PNNP_MODE_K (kCt ? kCtMode : p.mode)        /* expressions, not locals: the default instantiations must compile exactly as before */
 #define PNNP_DBG_K (kCt ? 0 : p.dbg)
@@ -214,7 +214,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int taps_total = PNNP_MODE_K == MODE_CONV3 ? 9 : (PNNP_MODE_K == MODE_CONV3S2 ? 9 : (PNNP_MODE_K == MODE_CONV3X ? 3 : (PNNP_MODE_K == MODE_CONV2S2 ? 4 : 1)));
 
     if constexpr (kPdl) {
-        // Programmatic dependent launch (opt-in, PNNP_CONV_PDL=1): this grid may have been scheduled while the previous kernel of
+        // Programmatic dependent launch (default since r02; PNNP_CONV_PDL=0 switches it off): this grid may have been scheduled while the previous kernel of
         // the stream was still draining.  Nothing above touches global memory; every thread waits here for the previous grid to
         // complete and flush, then lets the next conv layer's CTAs be scheduled as ours retire.
         pdl_wait_then_release();
@@ -741,7 +741,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     const int in_h = h, in_w = w;
     if (s2) { h /= 2; w /= 2; }        // tile over the OUTPUT grid
     const int tps = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? 3 : 1;
-    // Super-tile variant (two M = 128 tiles per pipeline stage, see the kernel's SUP parameter).  OPT-IN until it has been measured
+    // Super-tile variant (two M = 128 tiles per pipeline stage, see the kernel's SUP parameter).  Measured in r02 (tools/r02_sweep.sh): on by default for the MODE_CONV3 layers only; originally written as opt-in until measured
     // on a B200: PNNP_CONV_SUPER=1 -> one CTA per SM, four accumulators (two super-tiles in flight); =2 -> keeps two CTAs per SM
     // for the small-K resident-weight layers (one super-tile in flight per CTA).  Only the compile-time specialised NHWC 3x3
     // layers with N <= 128 take it (decided below, once the epilogue specialisation is known).
@@ -789,8 +789,8 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         const int swz_r = kc * esz, bts = (umma_n * swz_r + 1023) / 1024 * 1024;
         const int res_bytes = (cin_total / kc) * (mode == MODE_CONVT ? 1 : taps) * bts;   // convT: the four taps are N columns of one block
         const int a_only = (box_h * kTileW * swz_r + 1023) / 1024 * 1024;
-        // ConvTranspose2d layers with a single N tile (4 * cout <= 256) can keep their weights resident too: opt-in
-        // (PNNP_CONVT_FAST=1) until measured — it also lets the K = 64 layer run two CTAs per SM
+        // ConvTranspose2d layers with a single N tile (4 * cout <= 256) can keep their weights resident too: the ConvTranspose fast path
+        // (PNNP_CONVT_FAST; default for > 64 input channels since r02 — the K = 64 layer measured slower with it)
         if ((mode != MODE_CONVT || convt_fast) && n_tiles == 1 && res_bytes + 3 * a_only <= smem_budget && !getenv("PNNP_NO_RESIDENT_W")) {
             b_resident = 1; b_res_bytes = res_bytes;
         }
@@ -861,7 +861,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
 #undef X
         attr_done = true;
     }
-    // the opt-in instantiations are touched only once one of their switches is on: a default run loads and configures exactly
+    // the variant instantiations are configured on first use (with every switch forced to 0 a run loads and configures exactly
     // the kernels it did when it was measured
     const bool pdl = variant_on("PNNP_CONV_PDL");
     // packed-pair epilogue arithmetic: built for the specialised 3x3 epilogues, alone (VAR 4), with PDL (VAR 6) or with both other
@@ -885,7 +885,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         attr_optin_done = true;
     }
     const int k16s = swz / 32;                    // 32-byte MMA slices per K chunk (16 bf16 or 8 tf32 elements each)
-    // Programmatic dependent launch (opt-in until measured): the kernel waits (griddepcontrol.wait) before its first global access
+    // Programmatic dependent launch (default since r02): the kernel waits (griddepcontrol.wait) before its first global access
     cudaLaunchAttribute pdl_attr[1];
     pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -32,7 +32,7 @@ extern "C" int pnnp_eval_epilogue(const float* dn, const float* hr, int n, int c
         illum_dots_kernel<<<g, 256, 0, st>>>(dn, hr, per_frame, scale, sums, stride);
         count_launch();
     }
-    if (variant_on("PNNP_SSIM_V2")) {          // opt-in separable form (ssim_core.cuh)
+    if (variant_on("PNNP_SSIM_V2")) {          // separable form (ssim_core.cuh), the default since r02
         static bool attr_done = false;
         if (!attr_done) {
             PNNP_CUDA(cudaFuncSetAttribute(ssim_mse_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ssim2Tile)));

@@ -46,7 +46,7 @@ __global__ void nchw_f32_to_nhwc16_f32_kernel(const float* __restrict__ in, floa
 }
 
 // Same conversion, four pixels per thread (h * w % 4 == 0): one 128-bit load per plane (all issued before the first use) and a
-// contiguous 128-byte store per thread.  OPT-IN (PNNP_IN_V2=1) until measured: the one-pixel kernel above takes 53 us for a Sony
+// contiguous 128-byte store per thread.  The default since r02 (55 -> 50 us per Sony frame; PNNP_IN_V2=0 for the first form): the one-pixel kernel above takes 53 us for a Sony
 // frame (146 MB of traffic: 2.7 TB/s).
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc16_bf16_x4_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                                          int n, int c, int h, int w, float scale) {

@@ -48,7 +48,8 @@ extern "C" int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t 
     // grid * 256 is a multiple of c/8 (c/8 is a power of two <= 128 for this network family): a thread keeps its channel group.
     // Every block ends with c global atomics, so small tensors get few blocks (>= 8 items per thread) instead of 1184 x c atomics.
     const size_t items = pixels * (size_t)(c / 8);
-    int blocks = (int)std::max<size_t>(1, std::min<size_t>(items / (256 * 8), 148 * 8));
+    static const int max_blocks = getenv("PNNP_ACTBWD_BLOCKS") ? atoi(getenv("PNNP_ACTBWD_BLOCKS")) : 148 * 4;   // r02: 592 blocks 4.32 ms per step, 1184 4.38, 148 4.47 (every block ends in c same-address atomics)
+    int blocks = (int)std::max<size_t>(1, std::min<size_t>(items / (256 * 8), (size_t)max_blocks));
     const int quantum = std::max(1, (c / 8) / 256);                  // keep grid * 256 a multiple of c / 8
     blocks = std::max(quantum, blocks / quantum * quantum);
     const int c8 = c / 8;

@@ -71,7 +71,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_hi(int swz, int lbo_bytes) {
     return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-// VAR 1 (OPT-IN, PNNP_WGRAD_V2=1, until measured): the producer and MMA warps — one warp each, so the instruction count of their
+// VAR 1 (the default since r02: 4.88 -> 4.82 ms per step; PNNP_WGRAD_V2=0 for the first form): the producer and MMA warps — one warp each, so the instruction count of their
 // per-stage loops is the stage rate (352 and 139 SASS instructions in VAR 0: two integer divisions and a walk over the box / MMA
 // tables in the kernel-parameter bank per stage) — keep everything that does not change from stage to stage in registers: the
 // boxes' coordinates offsets, shared-memory offsets and tensor maps, the MMAs' descriptors, the (image, tile row, tile column) of the
