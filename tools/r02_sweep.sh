@@ -1,4 +1,7 @@
 #!/bin/bash
+# (Historical: this is the script as it ran at the start of round 2, against the round-1 defaults.  The variants it timed are defaults
+# now, tests/test_gpu_variants.py became tests/test_gpu_variants.py and runs in the normal -m gpu suite; results:
+# profiles/r02_sweep_summary.txt.  To re-run it against today's tree, set every PNNP_* variant switch to 0 for the "default" label.)
 # Round-2 first GPU call: correctness of the opt-in kernel variants written without a GPU at the end of round 1, then their timing.
 #   gpurun --timeout 1500 -- 'bash tools/r02_sweep.sh'      (about 13 minutes of box time)
 # Everything lands in gpurun_out/r02_sweep/.  Order: cheap correctness first, so a hang / failure is seen before time is spent.
@@ -8,7 +11,7 @@ mkdir -p "$OUT"
 # hand-shake micro-benchmarks (seconds): what one trip through the producer/consumer mbarrier ring costs, per signalling scheme
 if [[ -x tools/_bin/ubench_pipeline ]]; then timeout 120 tools/_bin/ubench_pipeline > "$OUT/ubench_pipeline.txt" 2>&1; echo "ubench rc=$?" | tee -a "$OUT/summary.txt"; fi
 export PNNP_TEST_EXPERIMENTAL=1
-timeout 300 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_wb_jitter.py tests/test_gpu_preprocess_route.py -q > "$OUT/pytest_experimental.log" 2>&1
+timeout 300 python -m pytest tests/test_gpu_variants.py tests/test_gpu_wb_jitter.py tests/test_gpu_preprocess_route.py -q > "$OUT/pytest_experimental.log" 2>&1
 echo "experimental tests rc=$?" | tee -a "$OUT/summary.txt"
 unset PNNP_TEST_EXPERIMENTAL
 run() {  # label, env assignments...
