@@ -755,7 +755,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     const int dbg_env = getenv("PNNP_CONV_DBG") ? atoi(getenv("PNNP_CONV_DBG")) : 0;
     int epi = EPI_GENERIC;
     if (!f32 && !no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && !dbg_env &&
-        !(d.pool_out && d.head_out) && !(d.mask && (mode == MODE_CONV3X || d.pool_out || d.head_out)))
+        !(d.pool_out && d.head_out) && !(d.mask && (d.pool_out || d.head_out)))
         epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
     if (!f32 && convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
         act == ACT_NONE && !no_spec && !dbg_env)
@@ -852,9 +852,10 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     // (taps per stage, K16 slices, epilogue specialisation); specialised epilogues exist for the 3-taps-per-stage shapes
 #define PNNP_SPEC_EPI(X, T, K) X(T, K, 0) X(T, K, 1) X(T, K, 2) X(T, K, 3) X(T, K, 4) X(T, K, 5)
 #define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1, -1) X(3, 2, -1) X(3, 4, -1) X(1, 1, -1) X(1, 2, -1) X(1, 4, -1) \
-    PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8) \
+    PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8) X(3, 1, 9) X(3, 2, 9) X(3, 4, 9) \
     X(1, 1, 16) X(1, 2, 16) X(1, 4, 16)
-#define PNNP_FOR_EACH_SUPER_VARIANT(X) PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8)
+#define PNNP_FOR_EACH_SUPER_VARIANT(X) PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8) \
+    X(3, 1, 9) X(3, 2, 9) X(3, 4, 9)        /* 9 = x-mode + activation mask: the data gradients of the 32-channel layers (r02) */
     if (!attr_done) {
 #define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PNNP_FOR_EACH_CONV_VARIANT(X)
