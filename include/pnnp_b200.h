@@ -34,7 +34,8 @@ extern "C" {
 #define PNNP_CODE_D 0x10u /* 'd' per-channel bias                                     */
 #define PNNP_CODE_B 0x20u /* 'b' black frame: read/row/q/bias all zero                */
 /* hint (not a reference letter): every table row has flags == PNNP_F_K64|PNNP_F_SIG64, i.e. all
- * crops use sample_params-style np.float64 parameters; lets the launcher pick the branch-free kernel */
+ * crops use sample_params-style np.float64 parameters, and |lam| >= 1e-3 (every camera of the
+ * reference: process.py:215-309); lets the launcher pick the branch-free kernel */
 #define PNNP_CODE_UNIFORM_F64 0x100u
 
 /* arithmetic chain (which reference function's rounding sequence is reproduced) */

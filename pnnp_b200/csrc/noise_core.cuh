@@ -140,6 +140,54 @@ __device__ __forceinline__ float normal_icdf(uint32_t w) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Shot words.  The Poisson samplers read only the top 23 bits of their 32-bit word: the low 9 bits are NOT part of the draw
+// (every sampler entry point replaces them by the cell centre 0x100), which leaves room for the specialised kernel to carry an
+// element's position inside its 512-element unit through the sampler queue.  2^-23 is the float32 resolution of a uniform in
+// [0.5, 1) anyway, and no conversion instruction is needed to form it: 0x3F800000 | bits is 1 + bits / 2^23.
+// Conversions (I2F / F2I / F2F / FRND), POPC and MUFU all issue on the XU pipe, four lanes per SM sub-partition and clock:
+// the r02 capture of the specialised kernel showed 14.7 of them per element = 38 % of the kernel's cycles on that pipe
+// alone, so the samplers below avoid them (floor by an add rounding towards -inf into 2^23 + x, counts as integers).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kShotPosMask = 0x1FFu;
+__device__ __forceinline__ uint32_t shot_word(uint32_t w) { return (w & ~kShotPosMask) | 0x100u; }
+// floor(x) for 0 <= x < 2^23 as an integer and as a float, without F2I / FRND: the sum 2^23 + x has unit spacing
+__device__ __forceinline__ float floor_bias23(float x) { return __fadd_rd(x, 8388608.0f); }
+__device__ __forceinline__ int bias23_int(float t) { return (int)(__float_as_uint(t) & 0x7FFFFFu); }
+
+// z = Phi^-1 of the 23-bit cell of a shot word (already through shot_word): sign bit + the 22 bits below it.  Same
+// polynomials as normal_icdf; the central branch forms 2p = ((m >> 8) + 0.5) / 2^23 from the bit pattern, the tail branch
+// (p < 8e-4) takes the integer conversion for its relative precision.
+__device__ __forceinline__ float normal_icdf_cell23(uint32_t w) {
+    const bool lower = w < 0x80000000u;
+    const uint32_t m = lower ? w : ~w;
+    const float p2 = __uint_as_float(0x3F800000u | (m >> 8)) - 0.99999994f;            // 2p in (0, 1), exact
+    const float t = -lg2_approx(p2 * (2.0f - p2));
+    float q = 2.674857846e-08f;
+    q = fmaf(q, t, -1.025935489e-06f);
+    q = fmaf(q, t, 1.418562169e-05f);
+    q = fmaf(q, t, -4.943624299e-05f);
+    q = fmaf(q, t, -7.453467697e-04f);
+    q = fmaf(q, t, 5.522758700e-03f);
+    q = fmaf(q, t, 1.608277857e-01f);
+    q = fmaf(q, t, 8.862264752e-01f);
+    float e = q * (1.0f - p2);
+    if (t >= 8.25f) {                       // p < 8e-4: the straight-line body above is discarded (two independent entries interleave)
+        const float p = fmaf((float)m, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        const float s = sqrtf(-lg2_approx(4.0f * p * (1.0f - p)));
+        q = 7.718497727e-06f;
+        q = fmaf(q, s, -2.602138266e-04f);
+        q = fmaf(q, s, 3.719373606e-03f);
+        q = fmaf(q, s, -2.902236022e-02f);
+        q = fmaf(q, s, 1.309477687e-01f);
+        q = fmaf(q, s, 5.167053342e-01f);
+        q = fmaf(q, s, 1.426639557e-01f);
+        e = q;
+    }
+    const float z = 1.4142135623730951f * e;
+    return lower ? -z : z;
+}
+
+// ------------------------------------------------------------------------------------------
 // Tukey-lambda quantile  Q(u) = (u^lam - (1-u)^lam) / lam   (lam -> 0: logit)
 // u and 1-u are formed separately from the word so both tails keep relative precision.
 // ------------------------------------------------------------------------------------------
@@ -149,6 +197,11 @@ __device__ __forceinline__ float tukey_lambda_from_uv(float a, float b, float la
 __device__ __forceinline__ float tukey_lambda_ppf_body(uint32_t mix, float lam, float inv_lam) {
     const float a = __uint_as_float(0x3F800000u | ((mix >> 12) << 3) | 4u) - 1.0f;
     return tukey_lambda_from_uv(a, 1.0f - a, lam, inv_lam);
+}
+// power form only (|lam| >= 1e-3, which PNNP_CODE_UNIFORM_F64 promises): the specialised kernel's body cells
+__device__ __forceinline__ float tukey_lambda_ppf_body_pow(uint32_t mix, float lam, float inv_lam) {
+    const float a = __uint_as_float(0x3F800000u | ((mix >> 12) << 3) | 4u) - 1.0f;
+    return (ex2_approx(lam * lg2_approx(a)) - ex2_approx(lam * lg2_approx(1.0f - a))) * inv_lam;
 }
 __device__ __forceinline__ float tukey_lambda_ppf(uint32_t w, float lam, float inv_lam) {
     if (!read_cell_is_tail(w >> 12)) return tukey_lambda_ppf_body(w, lam, inv_lam);
@@ -188,14 +241,16 @@ __constant__ float c_inv_k[kInvTab] = {
     1.f / 57, 1.f / 58, 1.f / 59, 1.f / 60, 1.f / 61, 1.f / 62, 1.f / 63};
 constexpr float kPoissonSwitch = 10.0f;
 
-__device__ __forceinline__ float poisson_large(float lam, uint32_t w) {
-    const float z = normal_icdf(w);
+// w: a shot word that has been through shot_word().  Counts saturate at 2^23 - 1 (rates of millions of electrons per pixel:
+// three orders of magnitude beyond any sensor's full well).
+__device__ __forceinline__ int poisson_large_k(float lam, uint32_t w) {
+    const float z = normal_icdf_cell23(w);
     const float rs = rsqrt_approx(lam), s = lam * rs, z2 = z * z;
     float x = fmaf(s, z, lam);
     x += fmaf(z2, 0.16666667f, 0.33333334f);
     x = fmaf(-z * fmaf(z2, 0.013888889f, 0.027777778f), rs, x);
     x = fmaf(fmaf(z2, fmaf(z2, 0.0037037036f, 0.008641975f), -0.019753087f), rs * rs, x);
-    return fmaxf(floorf(x), 0.f);
+    return bias23_int(floor_bias23(fminf(fmaxf(x, 0.f), 8388607.0f)));            // fmaxf also turns a NaN rate into 0
 }
 
 __device__ __forceinline__ float poisson_small(float lam, uint32_t w) {
@@ -231,34 +286,48 @@ __device__ __forceinline__ float poisson_small(float lam, uint32_t w) {
 constexpr int kPoisRows = 161, kPoisCols = 32, kPoisPad = 5, kPoisStride = kPoisCols + kPoisPad;   // 37 floats per row
 constexpr int kPoisTableFloats = kPoisRows * kPoisStride;
 
-__device__ __forceinline__ float poisson_small_table(float lam, uint32_t w, const float* __restrict__ T) {
-    lam = fmaxf(lam, 0.f);
-    const float u = fminf(u01_32(w), 0.99999994f);
-    const int i = (int)(lam * 16.0f);
-    const float delta = fmaf(-0.0625f, (float)i, lam);                        // exact
-    const float* row = T + i * kPoisStride + kPoisPad;
+// w: a shot word (its low 9 bits are ignored: u has 23 bits).  Two steps, so that a caller can run the straight-line first
+// step of several entries side by side (their shared-memory probes are a chain of five dependent loads each) before the
+// data-dependent second step.
+struct PoisSmall { const float* row; float delta, c2, c3, c4, ue, t1, t2, t3, t4; int k; };
+__device__ __forceinline__ PoisSmall poisson_small_search(float lam, uint32_t w, const float* __restrict__ T) {
+    PoisSmall s;
+    lam = fminf(fmaxf(lam, 0.f), 9.999999f);                                   // also keeps the row index inside the table
+    const float u = __uint_as_float(0x3F800000u | (w >> 9)) - 0.99999994f;     // ((w >> 9) + 0.5) / 2^23 in (0, 1), exact
+    const float ti = floor_bias23(lam * 16.0f);                                // 2^23 + floor(16 lam)
+    s.delta = fmaf(-0.0625f, ti - 8388608.0f, lam);                            // exact
+    s.row = T + bias23_int(ti) * kPoisStride + kPoisPad;
     int k = 0;
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) k += (row[k + s - 1] < u) ? s : 0;     // entries 0..30 that are < u
-    const float c2 = 0.5f * delta * delta, c3 = c2 * delta * 0.33333334f, c4 = c3 * delta * 0.25f;
+    for (int st = 16; st >= 1; st >>= 1) k += (s.row[k + st - 1] < u) ? st : 0;   // entries 0..30 that are < u
+    s.k = k;
+    s.c2 = 0.5f * s.delta * s.delta; s.c3 = s.c2 * s.delta * 0.33333334f; s.c4 = s.c3 * s.delta * 0.25f;
     // u * e^delta (delta < 1/16: degree-5 Taylor, relative error 1e-10)
-    const float ed = fmaf(delta, fmaf(delta, fmaf(delta, fmaf(delta, fmaf(delta, 8.3333333e-3f, 4.1666667e-2f), 0.16666667f), 0.5f), 1.0f), 1.0f);
-    const float ue = u * ed;
-    float t1 = row[k - 1], t2 = row[k - 2], t3 = row[k - 3], t4 = row[k - 4];
+    const float d = s.delta;
+    s.ue = u * fmaf(d, fmaf(d, fmaf(d, fmaf(d, fmaf(d, 8.3333333e-3f, 4.1666667e-2f), 0.16666667f), 0.5f), 1.0f), 1.0f);
+    s.t1 = s.row[k - 1]; s.t2 = s.row[k - 2]; s.t3 = s.row[k - 3]; s.t4 = s.row[k - 4];
+    return s;
+}
+__device__ __forceinline__ int poisson_small_finish(PoisSmall& s, float lam, uint32_t w) {
 #pragma unroll 1
     while (true) {
-        if (k >= kPoisCols) return poisson_small(lam, w);                      // probability < 1e-8: sequential search
-        const float t0 = row[k];
-        if (fmaf(c4, t4, fmaf(c3, t3, fmaf(c2, t2, fmaf(delta, t1, t0)))) >= ue) break;
-        t4 = t3; t3 = t2; t2 = t1; t1 = t0; ++k;
+        if (s.k >= kPoisCols) return (int)poisson_small(fminf(fmaxf(lam, 0.f), 9.999999f), shot_word(w));   // probability < 1e-8: sequential search
+        const float t0 = s.row[s.k];
+        if (fmaf(s.c4, s.t4, fmaf(s.c3, s.t3, fmaf(s.c2, s.t2, fmaf(s.delta, s.t1, t0)))) >= s.ue) break;
+        s.t4 = s.t3; s.t3 = s.t2; s.t2 = s.t1; s.t1 = t0; ++s.k;
     }
-    return (float)k;
+    return s.k;
+}
+__device__ __forceinline__ int poisson_small_table_k(float lam, uint32_t w, const float* __restrict__ T) {
+    PoisSmall s = poisson_small_search(lam, w, T);
+    return poisson_small_finish(s, lam, w);
 }
 
 // T: the shared-memory copy of the table above
 __device__ __forceinline__ float poisson_sample(float lam, uint32_t w, const float* __restrict__ T) {
     if (!(lam > 0.f)) return 0.f;
-    return lam < kPoissonSwitch ? poisson_small_table(lam, w, T) : poisson_large(lam, w);
+    w = shot_word(w);
+    return (float)(lam < kPoissonSwitch ? poisson_small_table_k(lam, w, T) : poisson_large_k(lam, w));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -371,20 +440,41 @@ __device__ __forceinline__ double div_rn_by_const(double a, double b, double r) 
     return __fma_rn(__fma_rn(-b, q, a), r, q);
 }
 
-// Per-unit constants of the specialised ("fast") NumPy-chain path: noise_code 'p','g','r','q' only,
+// Per-crop constants of the specialised ("fast") NumPy-chain path: noise_code 'p','g','r','q' only,
 // K / sigR np.float64 and ratio a python float (what sample_params returns), ori=False, clip=False.
-struct FastP {
-    float span32, ratio32, rratio32, invK32, sigTL32, lam_tl, inv_lam_tl;
-    double K, span, rspan, lo, ratio, row64;
+struct FastC {
+    float span32, ratio32, rratio32, invK32, sigTL32, lam_tl, inv_lam_tl, out_lo, out_hi;
+    double K, span, rspan, ratio, sigR;
 };
-__device__ __forceinline__ float tail_numpy_fast(const FastP& f, float cnt, float d_read, double d_q) {
-    double A = __dmul_rn((double)cnt, f.K);
+__device__ __forceinline__ FastC fast_constants(const pnnp_noise_params* t, float post_lo, float post_hi) {
+    FastC f;
+    f.K = t->K; f.span = t->span; f.ratio = t->ratio; f.sigR = t->sigR;
+    f.rspan = __drcp_rn(f.span);
+    f.span32 = (float)f.span; f.ratio32 = (float)f.ratio; f.rratio32 = __frcp_rn(f.ratio32);
+    f.invK32 = (float)(1.0 / f.K); f.sigTL32 = (float)t->sigTL; f.lam_tl = (float)t->lam;
+    f.inv_lam_tl = f.lam_tl != 0.f ? 1.0f / f.lam_tl : 0.f;
+    // np.clip(z, lo, 1) * ratio -> float32 -> post-clip is a composition of monotone maps of z, so both clips commute with the
+    // multiplication and the final rounding: float32(clip(z, lo, 1) * ratio) == clamp(float32(z * ratio), float32(lo * ratio),
+    // float32(1 * ratio)), and a clamp followed by the post-clip clamp is ONE clamp whose bounds are the post-clipped bounds.
+    // Two FMNMX per element instead of two float64 compare + select pairs and two FMNMX.  (A negative ratio swaps the bounds.)
+    const float a = (float)__dmul_rn(t->clip_lo, f.ratio), b = (float)__dmul_rn(1.0, f.ratio);
+    f.out_lo = fminf(fmaxf(fminf(a, b), post_lo), post_hi);
+    f.out_hi = fminf(fmaxf(fmaxf(a, b), post_lo), post_hi);
+    return f;
+}
+// Poisson rate of a clean pixel (scale-in + 1.0*y/K rounded to float32 for the samplers)
+__device__ __forceinline__ float fast_rate(const FastC& f, float y) {
+    return div_rn_by_const(__fmul_rn(y, f.span32), f.ratio32, f.rratio32) * f.invK32;
+}
+// count -> float64 exactly, without the conversion instruction: 2^52 + cnt has unit spacing (0 <= cnt < 2^31)
+__device__ __forceinline__ double count_to_f64(int cnt) { return __dadd_rn(__hiloint2double(0x43300000, cnt), -4503599627370496.0); }
+__device__ __forceinline__ float fast_tail(const FastC& f, int cnt, float d_read, double row64, double d_q) {
+    double A = __dmul_rn(count_to_f64(cnt), f.K);
     A = __dadd_rn(A, (double)d_read);
-    A = __dadd_rn(A, f.row64);
+    A = __dadd_rn(A, row64);
     A = __dadd_rn(A, d_q);
-    double z = div_rn_by_const(A, f.span, f.rspan);
-    z = fmin(fmax(z, f.lo), 1.0);
-    return (float)__dmul_rn(z, f.ratio);
+    const float v = (float)__dmul_rn(div_rn_by_const(A, f.span, f.rspan), f.ratio);
+    return fminf(fmaxf(v, f.out_lo), f.out_hi);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ struct SynthArgs {
     float* d_shot; float* d_read; float* d_rowz; double* d_q;
 };
 
-// Poisson CDF table (noise_core.cuh: poisson_small_table), filled once per process by the host
+// Poisson CDF table (noise_core.cuh: poisson_small_table_k), filled once per process by the host
 __device__ float g_pois_table[kPoisTableFloats];
 // the table's contents (host side; noise_synth.cu copies it to g_pois_table once per device)
 inline void build_poisson_table(float* host) {
@@ -198,31 +198,34 @@ __global__ void __launch_bounds__(kThreads, 4) noise_synth_kernel(const SynthArg
 // test_specialised_kernel_is_bit_identical_to_replay_at_scale), organised around what the generic kernel wastes:
 //
 //  * The two Poisson samplers (exact CDF search below rate 10, Cornish-Fisher inversion above) are data-dependent branches
-//    that a warp pays for one after the other whenever its 32 lanes disagree — and with per-pixel rates they always do;
-//    inside the search every lane also waits for the slowest one.  Here a warp owns 512 consecutive elements of a row and
-//    first *sorts them by sampler* through a 4 KB shared-memory queue (ballot + popc compaction: low-rate entries fill the
-//    queue from the bottom, high-rate entries from the top), then runs each sampler over its part of the queue 32 entries at
-//    a time with every lane active, and writes the count back in place.  Each lane keeps the queue positions of its 16
-//    elements in registers and collects the counts afterwards.
-//  * Per-crop constants (reciprocals for the Markstein divisions, float32 copies) are rebuilt only when the warp moves to
-//    another crop; the row-noise draws of a warp's next 32 rows are generated in one go, one row per lane, and handed out
-//    by shuffle (row noise is keyed on the global row index, so the value does not depend on who computes it).
+//    that a warp pays for one after the other whenever its 32 lanes disagree — and with per-pixel rates they always do.
+//    Here a warp owns 512 consecutive elements of a row and first *sorts them by sampler* through a 4 KB shared-memory queue
+//    (low-rate entries fill it from the bottom, high-rate entries from the top), then runs each sampler over its part of the
+//    queue 32 entries at a time with every lane active.  An entry is (rate, shot word); the 9 low bits of the word, which no
+//    sampler reads (noise_core.cuh: shot_word), carry the element's position in the unit, so the count goes straight to
+//    the element's slot of a 2 KB count array and phase 3 fetches its four counts with one conflict-free 128-bit load.
+//  * Queue positions come from ONE warp scan per unit: a lane counts the low-rate elements among its 16 (a bit mask), the
+//    packed (low, high) counts go through five shuffle steps, and the lane's entries then take consecutive slots.  (Round 1
+//    used a ballot and four POPC per element; POPC, the conversions and MUFU share the XU pipe — four lanes per SM
+//    sub-partition and clock — which that kernel kept 38 % busy.)
+//  * Per-crop constants (reciprocals for the Markstein divisions, float32 copies, the folded clip bounds) are rebuilt only
+//    when the warp moves to another crop; row / crop indices advance incrementally (no integer division per unit); the
+//    row-noise draws of a warp's next 32 rows are generated in one go, one row per lane, and handed out by shuffle (row
+//    noise is keyed on the global row index, so the value does not depend on who computes it).
 //  * Phase 3 (read noise, quantisation, float64 tail, 128-bit streaming stores) needs only the counts, not the clean pixels.
 // ------------------------------------------------------------------------------------------
 constexpr int kFastUnit = 512;              // elements per warp work unit (16 per lane, four float4 groups)
 constexpr int kFastThreads = 256;
+static_assert(kFastUnit - 1 <= (int)kShotPosMask, "an element's position in the unit travels in the unused low bits of its shot word");
 
-constexpr int kFastQueueBytes = (kFastThreads / 32) * kFastUnit * 8, kFastPosBytes = (kFastThreads / 32) * kFastUnit * 2;
-constexpr int kFastSmemBytes = kFastQueueBytes + kFastPosBytes + kPoisTableFloats * 4;
+constexpr int fast_queue_bytes(int threads) { return (threads / 32) * kFastUnit * 8; }
+constexpr int fast_count_bytes(int threads) { return (threads / 32) * kFastUnit * 4; }
+constexpr int fast_smem_bytes(int threads) { return fast_queue_bytes(threads) + fast_count_bytes(threads) + kPoisTableFloats * 4; }
+constexpr int kFastSmemBytes = fast_smem_bytes(kFastThreads);
 
-struct FastC {                              // per-crop constants
-    float span32, ratio32, rratio32, invK32, sigTL32, lam_tl, inv_lam_tl;
-    double K, span, rspan, lo, ratio, sigR;
-};
-
-// Three CTAs (24 warps) per SM at 79 registers without spills.  Measured alternatives (r01): four CTAs at 64 registers spill and
-// run 15 % slower; reading the Poisson table through L1 instead of a per-CTA shared-memory copy (41 KB instead of 65 KB of
-// shared memory) is 12 % slower at equal occupancy.
+// Three CTAs (24 warps) per SM.  Measured alternatives: four CTAs at 64 registers spill and run 15 % slower (r01); two CTAs of 448
+// threads at 72 registers (28 warps) 6 % slower (r02: 575 against 544 us); reading the Poisson table through L1 instead of a
+// per-CTA shared-memory copy is 12 % slower at equal occupancy (r01).
 // EXP: timing experiments only (PNNP_SYNTH_EXP, never part of a result): bit 0 no Poisson samplers (count = round(rate)), bit 1 no
 // Tukey-lambda quantile, bit 2 no sorting by sampler (queue slot = own slot), bit 3 no Philox rounds (counter mixed with two
 // multiplies).  EXP = 0 is the product kernel; the others measure what each part costs ("measured floor").
@@ -236,129 +239,201 @@ __device__ __forceinline__ uint4 exp_block(const RngCtx& rng, uint64_t index, ui
     }
 }
 
-template <bool DEBUG, int EXP = 0>
-__global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const SynthArgs a) {
-    // dynamic shared memory (kFastSmemBytes > 48 KB): [warps][512] uint2 queue | [warps][512] uint16 positions | Poisson table
+// Queue stores of phase 1.  `sp` / `lp` are shared-memory byte addresses; an entry goes to the low-rate end (and moves `sp` up)
+// or to the high-rate end (and moves `lp` down): one predicate, one select, two predicated adds and the store.
+#ifndef PNNP_HOST_EMUL
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void queue_put_at(uint32_t addr, float lam, uint32_t word) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_uint(lam)), "r"(word) : "memory");
+}
+__device__ __forceinline__ void queue_put(uint32_t& sp, uint32_t& lp, float lam, uint32_t word) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 a;\n\t"
+        "setp.lt.f32 p, %2, 0f41200000;\n\t"          // lam < 10
+        "selp.b32 a, %0, %1, p;\n\t"
+        "st.shared.v2.b32 [a], {%3, %4};\n\t"
+        "@p add.u32 %0, %0, 8;\n\t"
+        "@!p sub.u32 %1, %1, 8;\n\t}"
+        : "+r"(sp), "+r"(lp) : "f"(lam), "r"(__float_as_uint(lam)), "r"(word) : "memory");
+}
+#else
+extern uint8_t s_fast[];              // the emulated CTA's dynamic shared memory (tests/emul/simt_kernels_host.cpp)
+inline uint32_t smem_addr(const void* p) { return (uint32_t)(uintptr_t)((const uint8_t*)p - s_fast); }
+inline void queue_put_at(uint32_t addr, float lam, uint32_t word) { *reinterpret_cast<uint2*>(s_fast + addr) = make_uint2(__float_as_uint(lam), word); }
+inline void queue_put(uint32_t& sp, uint32_t& lp, float lam, uint32_t word) {
+    const bool small = lam < kPoissonSwitch;
+    queue_put_at(small ? sp : lp, lam, word);
+    if (small) sp += 8; else lp -= 8;
+}
+#endif
+
+template <bool DEBUG, int EXP = 0, int THREADS = kFastThreads, int CTAS = 3>
+__global__ void __launch_bounds__(THREADS, CTAS) noise_synth_fast_kernel(const SynthArgs a) {
+    // dynamic shared memory (fast_smem_bytes(THREADS) > 48 KB): [warps][512] uint2 queue | [warps][512] int counts | Poisson table
     extern __shared__ __align__(16) uint8_t s_fast[];
-    float* s_pois = reinterpret_cast<float*>(s_fast + kFastQueueBytes + kFastPosBytes);
+    constexpr int kFastWarps = THREADS / 32, kFastQueueBytes = fast_queue_bytes(THREADS), kFastCountBytes = fast_count_bytes(THREADS);
+    float* s_pois = reinterpret_cast<float*>(s_fast + kFastQueueBytes + kFastCountBytes);
     load_poisson_table(s_pois);
     const int lane = threadIdx.x & 31;
     uint2* q = reinterpret_cast<uint2*>(s_fast) + (threadIdx.x >> 5) * kFastUnit;
-    uint16_t* qpos = reinterpret_cast<uint16_t*>(s_fast + kFastQueueBytes) + (threadIdx.x >> 5) * kFastUnit;   // queue position of every element
-    const unsigned lt = (1u << lane) - 1u;
+    int* cnt_s = reinterpret_cast<int*>(s_fast + kFastQueueBytes) + (threadIdx.x >> 5) * kFastUnit;   // counts, element order
     // 32-bit index arithmetic (the launcher takes this kernel only below 2^31 elements): registers are what limits occupancy
-    const int warps_total = (int)gridDim.x * (kFastThreads / 32);
-    const int warp_id = (int)blockIdx.x * (kFastThreads / 32) + (int)(threadIdx.x >> 5);
+    const int warps_total = (int)gridDim.x * kFastWarps;
+    const int warp_id = (int)blockIdx.x * kFastWarps + (int)(threadIdx.x >> 5);
     const int nseg = (a.w + kFastUnit - 1) / kFastUnit;
     const int rows_per_crop = a.c * a.h;
     const int units = a.n * rows_per_crop * nseg;
     const RngCtx rng{a.rk, (uint32_t)a.offset, (uint32_t)(a.offset >> 32)};
+    // Philox group index (global element index / 4) of the tensor's first element; opaque to the compiler, which otherwise
+    // re-derives the 64-bit product in every trip of the loops below instead of keeping two registers
+    uint64_t group0 = (a.crop_id0 * (uint64_t)rows_per_crop * (uint64_t)a.w) >> 2;          // the product is a multiple of 4 on this path
+#ifndef PNNP_HOST_EMUL
+    asm volatile("" : "+l"(group0));
+#endif
+    // A warp owns a CONTIGUOUS range of units (rows follow each other, so the per-crop constants below are rebuilt once or
+    // twice per warp — with a grid-stride walk and more warps than rows per crop EVERY unit was in another crop: ~100
+    // instructions and a float64 reciprocal per unit); (row, segment, crop, row inside the crop) advance by increment and carry.
+    const int u_begin = (int)((long long)units * warp_id / warps_total), u_end = (int)((long long)units * (warp_id + 1) / warps_total);
+    int row = u_begin / nseg, seg = u_begin - row * nseg;
+    int crop = row / rows_per_crop, crop_row = row - crop * rows_per_crop;
 
     FastC f = {};
     int cur_crop = -1;
     float rowz_batch = 0.f;
     int it = 0;
-    for (int u = warp_id; u < units; u += warps_total, ++it) {
+    for (int u = u_begin; u < u_end; ++u, ++it) {
         if ((it & 31) == 0) {
             // row draws of this warp's next 32 units, one per lane
-            const long long uu = (long long)u + (long long)lane * warps_total;
-            if (uu < units) rowz_batch = normal_icdf(rng.block(a.crop_id0 * (uint64_t)rows_per_crop + (uint64_t)(uu / nseg), kStreamRow, 0u).x);
+            const int uu = u + lane;
+            if (uu < u_end) rowz_batch = normal_icdf(rng.block(a.crop_id0 * (uint64_t)rows_per_crop + (uint64_t)(uu / nseg), kStreamRow, 0u).x);
         }
         const float rowz = __shfl_sync(0xffffffffu, rowz_batch, it & 31);
-        const int row = u / nseg;
-        const int seg = u - row * nseg;
-        const int crop = row / rows_per_crop;
         if (crop != cur_crop) {
-            const pnnp_noise_params* t = a.table + crop;
-            f.K = t->K; f.span = t->span; f.lo = t->clip_lo; f.ratio = t->ratio; f.sigR = t->sigR;
-            f.rspan = __drcp_rn(f.span);
-            f.span32 = (float)f.span; f.ratio32 = (float)f.ratio; f.rratio32 = __frcp_rn(f.ratio32);
-            f.invK32 = (float)(1.0 / f.K); f.sigTL32 = (float)t->sigTL; f.lam_tl = (float)t->lam;
-            f.inv_lam_tl = f.lam_tl != 0.f ? 1.0f / f.lam_tl : 0.f;
+            f = fast_constants(a.table + crop, a.post_lo, a.post_hi);
             cur_crop = crop;
         }
         if (DEBUG && a.d_rowz && seg == 0 && lane == 0) a.d_rowz[row] = rowz;
         const double row64 = __dmul_rn((double)rowz, f.sigR);
         const uint32_t row_base = (uint32_t)row * (uint32_t)a.w;
-        const uint64_t g_base = a.crop_id0 * (uint64_t)rows_per_crop * (uint64_t)a.w + (uint64_t)row_base;
         const int x0 = seg * kFastUnit;
+        const uint64_t group_u = group0 + (uint64_t)((row_base + (uint32_t)x0) >> 2) + (uint64_t)lane;   // group of this lane's first float4
 
-        // ---- phase 1: rates + shot words -> queue, sorted by sampler.  The j loops are deliberately NOT unrolled: the
-        // kernel is latency-bound, not issue-bound, and a 4x unrolled body (4 Philox blocks per phase) overflows the
-        // instruction cache once the warps of an SM spread over the three phases.
-        int n_small = 0, n_large = 0;
-        // all four 128-bit loads of the unit are issued before the first use (one exposed memory latency per unit instead of
-        // four: the first multiply of a freshly loaded pixel was 13 % of all stall samples), and the next unit's lines are
-        // requested into L2 while this unit computes
+        // ---- phase 1: rates, sampler of every element, ONE scan for the queue positions, shot words -> queue.
+        // All four 128-bit loads of the unit are issued before the first use (one exposed memory latency per unit), and the
+        // next unit's lines are requested into L2 while this unit computes.
         float4 ybuf[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = x0 + (j * 32 + lane) * 4;
             ybuf[j] = x < a.w ? __ldcs(reinterpret_cast<const float4*>(a.clean + row_base + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (u + warps_total < units) {
-            const int un = u + warps_total, rown = un / nseg, xn0 = (un - rown * nseg) * kFastUnit;
-            const float* nb = a.clean + (size_t)rown * a.w + xn0 + lane * 4;
+        if (u + 1 < u_end) {
+            int rown = row, segn = seg + 1;
+            if (segn >= nseg) { segn = 0; ++rown; }
+            const float* nb = a.clean + (size_t)rown * a.w + segn * kFastUnit + lane * 4;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (xn0 + (j * 32 + lane) * 4 < a.w) prefetch_l2(nb + j * 128);
+                if (segn * kFastUnit + (j * 32 + lane) * 4 < a.w) prefetch_l2(nb + j * 128);
         }
-#pragma unroll 1
+        // rates: counted by sampler here and parked in the (still unused) count array, so that no 16 values stay in registers
+        // across the scan and the Philox blocks below
+        int ns_own = 0, n_own = 0;            // low-rate / valid elements of this lane
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool valid = x0 + (j * 32 + lane) * 4 < a.w;
+            n_own += valid ? 4 : 0;
+            float4 l;
+            l.x = fast_rate(f, ybuf[j].x); l.y = fast_rate(f, ybuf[j].y); l.z = fast_rate(f, ybuf[j].z); l.w = fast_rate(f, ybuf[j].w);
+            ns_own += (valid && l.x < kPoissonSwitch) ? 1 : 0;
+            ns_own += (valid && l.y < kPoissonSwitch) ? 1 : 0;
+            ns_own += (valid && l.z < kPoissonSwitch) ? 1 : 0;
+            ns_own += (valid && l.w < kPoissonSwitch) ? 1 : 0;
+            *reinterpret_cast<float4*>(cnt_s + (j * 32 + lane) * 4) = l;
+        }
+        int n_small, n_large;
+        uint32_t sp, lp;                      // next low-rate slot (upwards) / high-rate slot (downwards) of this lane, as shared-memory byte addresses
+        const uint32_t q_addr = smem_addr(q);
+        if constexpr ((EXP & 4) != 0) {       // experiment: no sorting, every entry in its own slot, one sampler loop with both samplers
+            n_small = kFastUnit; n_large = 0; sp = q_addr; lp = q_addr;
+        } else {
+            const uint32_t own = (uint32_t)ns_own | ((uint32_t)(n_own - ns_own) << 16);
+            uint32_t incl = own;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                incl += lane >= d ? up : 0u;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            n_small = (int)(tot & 0xFFFFu); n_large = (int)(tot >> 16);
+            sp = q_addr + 8u * ((incl - own) & 0xFFFFu);
+            lp = q_addr + 8u * (uint32_t)(kFastUnit - 1 - (int)((incl - own) >> 16));
+        }
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = x0 + (j * 32 + lane) * 4;
-            const bool valid = x < a.w;
-            const unsigned m_valid = __ballot_sync(0xffffffffu, valid);
-            const float4 yv = j == 0 ? ybuf[0] : (j == 1 ? ybuf[1] : (j == 2 ? ybuf[2] : ybuf[3]));
-            const uint4 b0 = exp_block<EXP>(rng, (g_base + x) >> 2, kStreamElem, 0u);      // (g_base + x) % 4 == 0 on this path
-            const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
-            const uint32_t ws[4] = {b0.x, b0.y, b0.z, b0.w};
-            uint32_t pq[4];
+            if (x < a.w) {
+                const uint4 b0 = exp_block<EXP>(rng, group_u + (uint64_t)(j * 32), kStreamElem, 0u);
+                const uint32_t ws[4] = {b0.x, b0.y, b0.z, b0.w};
+                const float4 l4 = *reinterpret_cast<const float4*>(cnt_s + (j * 32 + lane) * 4);      // own store: no barrier needed
+                const float lam[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float ysc = div_rn_by_const(__fmul_rn(ys[e], f.span32), f.ratio32, f.rratio32);
-                const float lam = ysc * f.invK32;
-                if constexpr ((EXP & 4) != 0) {                               // experiment: no sorting, every entry in its own slot
-                    pq[e] = (uint32_t)((j * 32 + lane) * 4 + e);
-                    if (valid) q[pq[e]] = make_uint2(__float_as_uint(lam), ws[e]);
-                    n_small = kFastUnit;
-                } else {
-                const bool small = lam < kPoissonSwitch;
-                const unsigned m_small = __ballot_sync(0xffffffffu, small && valid);
-                const unsigned m_large = m_valid & ~m_small;
-                const int p_small = n_small + __popc(m_small & lt);
-                const int p_large = kFastUnit - 1 - (n_large + __popc(m_large & lt));
-                pq[e] = (uint32_t)(small ? p_small : p_large);
-                if (valid) q[pq[e]] = make_uint2(__float_as_uint(lam), ws[e]);
-                n_small += __popc(m_small);
-                n_large += __popc(m_large);
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t pos_in_unit = (uint32_t)(lane * 4) | (uint32_t)(j * 128 + e);
+                    const uint32_t word = (ws[e] & ~kShotPosMask) | pos_in_unit;
+                    if constexpr ((EXP & 4) != 0) queue_put_at(q_addr + 8u * pos_in_unit, lam[e], word);
+                    else queue_put(sp, lp, lam[e], word);
                 }
             }
-            *reinterpret_cast<uint2*>(qpos + (j * 32 + lane) * 4) = make_uint2(pq[0] | (pq[1] << 16), pq[2] | (pq[3] << 16));
         }
         __syncwarp();
-        // ---- phase 2: each sampler over its part of the queue, all lanes busy; the count replaces the rate in place
-        for (int i = lane; i < n_small; i += 32) {
-            const uint2 en = q[i];
-            if constexpr ((EXP & 1) != 0) q[i].x = __float_as_uint(rintf(__uint_as_float(en.x)) + (float)(en.y >> 31));
-            else if constexpr ((EXP & 4) != 0) q[i].x = __float_as_uint(poisson_sample(__uint_as_float(en.x), en.y, s_pois));
-            else q[i].x = __float_as_uint(poisson_small_table(__uint_as_float(en.x), en.y, s_pois));
-        }
-        for (int i = lane; i < n_large; i += 32) {
-            const uint2 en = q[kFastUnit - 1 - i];
-            if constexpr ((EXP & 1) != 0) q[kFastUnit - 1 - i].x = __float_as_uint(rintf(__uint_as_float(en.x)) + (float)(en.y >> 31));
-            else q[kFastUnit - 1 - i].x = __float_as_uint(poisson_large(__uint_as_float(en.x), en.y));
+        // ---- phase 2: each sampler over its part of the queue, all lanes busy; the count goes to the element's slot
+        // Two entries per lane and trip: the samplers are chains of dependent shared-memory loads / special-function results and
+        // the kernel runs 6 warps per scheduler, so a second independent chain fills the slots the first one waits in (an odd
+        // last trip repeats its entry: same count to the same slot).
+        if constexpr ((EXP & 5) != 0) {
+            for (int i = lane; i < n_small; i += 32) {
+                const uint2 en = q[i];
+                const float l = __uint_as_float(en.x);
+                int k;
+                if constexpr ((EXP & 1) != 0) k = (int)(rintf(l) + (float)(en.y >> 31));
+                else k = (int)poisson_sample(l, en.y, s_pois);
+                cnt_s[en.y & kShotPosMask] = k;
+            }
+            for (int i = lane; i < n_large; i += 32) {
+                const uint2 en = q[kFastUnit - 1 - i];
+                cnt_s[en.y & kShotPosMask] = (int)(rintf(__uint_as_float(en.x)) + (float)(en.y >> 31));
+            }
+        } else {
+            for (int i = lane; i < n_small; i += 64) {
+                const uint2 e0 = q[i], e1 = q[i + 32 < n_small ? i + 32 : i];
+                PoisSmall s0 = poisson_small_search(__uint_as_float(e0.x), e0.y, s_pois);
+                PoisSmall s1 = poisson_small_search(__uint_as_float(e1.x), e1.y, s_pois);
+                const int k0 = poisson_small_finish(s0, __uint_as_float(e0.x), e0.y);
+                const int k1 = poisson_small_finish(s1, __uint_as_float(e1.x), e1.y);
+                cnt_s[e0.y & kShotPosMask] = k0;
+                cnt_s[e1.y & kShotPosMask] = k1;
+            }
+            for (int i = lane; i < n_large; i += 64) {
+                const uint2 e0 = q[kFastUnit - 1 - i], e1 = q[kFastUnit - 1 - (i + 32 < n_large ? i + 32 : i)];
+                const int k0 = poisson_large_k(__uint_as_float(e0.x), shot_word(e0.y));
+                const int k1 = poisson_large_k(__uint_as_float(e1.x), shot_word(e1.y));
+                cnt_s[e0.y & kShotPosMask] = k0;
+                cnt_s[e1.y & kShotPosMask] = k1;
+            }
         }
         __syncwarp();
-        // ---- phase 3: read noise + quantisation + tail (needs the counts, not the clean pixels)
+        // ---- phase 3: read noise + quantisation + tail (needs the counts, not the clean pixels).  Deliberately NOT unrolled:
+        // a 4x unrolled body (4 Philox blocks + 16 tails) overflows the instruction cache once the warps of an SM spread over
+        // the three phases.
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             const int x = x0 + (j * 32 + lane) * 4;
             if (x < a.w) {
-                const uint64_t grp = (g_base + x) >> 2;
+                const uint64_t grp = group_u + (uint64_t)(j * 32);
                 const uint4 b1 = exp_block<EXP>(rng, grp, kStreamElem, 1u);
                 const uint32_t mix[4] = {b1.x, b1.y, b1.z, b1.w};
-                const uint2 pp = *reinterpret_cast<const uint2*>(qpos + (j * 32 + lane) * 4);
-                const uint32_t pq[4] = {pp.x & 0xFFFFu, pp.x >> 16, pp.y & 0xFFFFu, pp.y >> 16};
+                const uint4 c4 = *reinterpret_cast<const uint4*>(cnt_s + (j * 32 + lane) * 4);
+                const int cnt[4] = {(int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w};
                 float d_read[4];
                 if (read_cell_is_tail(b1.x >> 12) | read_cell_is_tail(b1.y >> 12) | read_cell_is_tail(b1.z >> 12) | read_cell_is_tail(b1.w >> 12)) {
                     // rare (2^-9 per group): some draw lies in the outer cells -> refinement block, general sampler
@@ -371,22 +446,16 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
                     for (int e = 0; e < 4; ++e) d_read[e] = (__uint_as_float(0x3F800000u | (mix[e] >> 9)) - 1.5f) * f.sigTL32;
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) d_read[e] = tukey_lambda_ppf_body(mix[e], f.lam_tl, f.inv_lam_tl) * f.sigTL32;
+                    for (int e = 0; e < 4; ++e) d_read[e] = tukey_lambda_ppf_body_pow(mix[e], f.lam_tl, f.inv_lam_tl) * f.sigTL32;
                 }
                 float o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float cnt = __uint_as_float(q[pq[e]].x);
                     const double dq = quant_draw_f64(mix[e]);
-                    double A = __dmul_rn((double)cnt, f.K);
-                    A = __dadd_rn(A, (double)d_read[e]);
-                    A = __dadd_rn(A, row64);
-                    A = __dadd_rn(A, dq);
-                    const double z = clip_f64(div_rn_by_const(A, f.span, f.rspan), f.lo, 1.0);
-                    o[e] = fminf(fmaxf((float)__dmul_rn(z, f.ratio), a.post_lo), a.post_hi);
+                    o[e] = fast_tail(f, cnt[e], d_read[e], row64, dq);
                     if (DEBUG) {
                         const size_t lidx = (size_t)row_base + x + e;
-                        if (a.d_shot) a.d_shot[lidx] = cnt;
+                        if (a.d_shot) a.d_shot[lidx] = (float)cnt[e];
                         if (a.d_read) a.d_read[lidx] = d_read[e];
                         if (a.d_q) a.d_q[lidx] = dq;
                     }
@@ -394,7 +463,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) noise_synth_fast_kernel(const
                 __stcs(reinterpret_cast<float4*>(a.noisy + row_base + x), make_float4(o[0], o[1], o[2], o[3]));
             }
         }
-        __syncwarp();                       // the queue is reused by the next unit
+        __syncwarp();                       // the queue and the count array are reused by the next unit
+        // next unit of this warp
+        if (++seg >= nseg) { seg = 0; ++row; if (++crop_row >= rows_per_crop) { crop_row = 0; ++crop; } }
     }
 }
 

@@ -70,15 +70,10 @@ static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
 #define PNNP_LAUNCH(CH, V) noise_synth_kernel<CH, DEBUG, V><<<blocks, kThreads, 0, st>>>(b)
     if (fast) {
         const long long funits = (long long)a.n * a.c * a.h * ((a.w + kFastUnit - 1) / kFastUnit);
-        const long long fwant = (funits + (kFastThreads / 32) - 1) / (kFastThreads / 32);
-        static bool attr_done = false;
-        if (!attr_done) {
-            PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
-            attr_done = true;
-        }
-        const int fgrid = (int)std::min<long long>(fwant, (long long)sms * 3);
         const int exp_sw = DEBUG ? 0 : (getenv("PNNP_SYNTH_EXP") ? atoi(getenv("PNNP_SYNTH_EXP")) : 0);     // timing experiments only
         if (exp_sw) {
+            const long long fwant = (funits + (kFastThreads / 32) - 1) / (kFastThreads / 32);
+            const int fgrid = (int)std::min<long long>(fwant, (long long)sms * 3);
 #define PNNP_EXP_CASE(E) case E: PNNP_CUDA(cudaFuncSetAttribute(noise_synth_fast_kernel<false, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes)); \
                                  noise_synth_fast_kernel<false, E><<<fgrid, kFastThreads, kFastSmemBytes, st>>>(b); break;
             switch (exp_sw) {
@@ -86,8 +81,16 @@ static int launch_synth(const SynthArgs& a, int chain, cudaStream_t st) {
                 default: return fail("noise_synth: unknown PNNP_SYNTH_EXP combination");
             }
 #undef PNNP_EXP_CASE
-        } else
-        noise_synth_fast_kernel<DEBUG><<<fgrid, kFastThreads, kFastSmemBytes, st>>>(b);
+        } else {
+            auto kern = noise_synth_fast_kernel<DEBUG>;
+            const long long fwant = (funits + (kFastThreads / 32) - 1) / (kFastThreads / 32);
+            static bool attr_done = false;
+            if (!attr_done) {
+                PNNP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
+                attr_done = true;
+            }
+            kern<<<(int)std::min<long long>(fwant, (long long)sms * 3), kFastThreads, kFastSmemBytes, st>>>(b);
+        }
     }
     else if (chain == PNNP_CHAIN_NUMPY) { if (vec) PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 4); else PNNP_LAUNCH(PNNP_CHAIN_NUMPY, 1); }
     else                                { if (vec) PNNP_LAUNCH(PNNP_CHAIN_TORCH, 4); else PNNP_LAUNCH(PNNP_CHAIN_TORCH, 1); }

@@ -220,7 +220,9 @@ class ParamTable:
         self.host = host
         self.device = host.to(device, non_blocking=True)
         self.ratios = [float(r.ratio) for r in rows]
-        self.uniform_f64 = all(r.flags == (_lib.F_K64 | _lib.F_SIG64) for r in rows)
+        # hint for the launcher (PNNP_CODE_UNIFORM_F64): sample_params-style float64 parameters in every row AND a Tukey-lambda
+        # shape away from 0 (the specialised kernel has only the power form of the quantile; |lam| < 1e-3 needs the series)
+        self.uniform_f64 = all(r.flags == (_lib.F_K64 | _lib.F_SIG64) and abs(r.lam) >= 1e-3 for r in rows)
 
     def data_ptr(self):
         return self.device.data_ptr()

@@ -24,6 +24,15 @@ static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
+#include <cfenv>
+static inline float __fadd_rd(float a, float b) {                 // add rounding towards -inf (FADD.RM)
+    const int r = fegetround();
+    fesetround(FE_DOWNWARD);
+    volatile float va = a, vb = b;
+    volatile float s = va + vb;
+    fesetround(r);
+    return s;
+}
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -62,19 +62,11 @@ void emul_replay(const float* clean, float* noisy, const pnnp_noise_params* row,
 // Markstein divisions instead of IEEE divisions; must equal emul_replay bit for bit for 'pgrq' with float64 K / sigR
 void emul_fast_tail(const float* clean, float* noisy, float* rate_out, const pnnp_noise_params* t, int n, const float* cnt,
                     const float* d_read, float rowz, const double* d_q, float post_lo, float post_hi) {
-    const double K = t->K, span = t->span, lo = t->clip_lo, ratio = t->ratio, sigR = t->sigR;
-    const double rspan = __drcp_rn(span);
-    const float span32 = (float)span, ratio32 = (float)ratio, rratio32 = __frcp_rn(ratio32), invK32 = (float)(1.0 / K);
-    const double row64 = __dmul_rn((double)rowz, sigR);
+    const FastC f = fast_constants(t, post_lo, post_hi);
+    const double row64 = __dmul_rn((double)rowz, f.sigR);
     for (int i = 0; i < n; ++i) {
-        const float ysc = div_rn_by_const(__fmul_rn(clean[i], span32), ratio32, rratio32);
-        rate_out[i] = ysc * invK32;
-        double A = __dmul_rn((double)cnt[i], K);
-        A = __dadd_rn(A, (double)d_read[i]);
-        A = __dadd_rn(A, row64);
-        A = __dadd_rn(A, d_q[i]);
-        const double z = clip_f64(div_rn_by_const(A, span, rspan), lo, 1.0);
-        noisy[i] = fminf(fmaxf((float)__dmul_rn(z, ratio), post_lo), post_hi);
+        rate_out[i] = fast_rate(f, clean[i]);
+        noisy[i] = fast_tail(f, (int)cnt[i], d_read[i], row64, d_q[i]);
     }
 }
 

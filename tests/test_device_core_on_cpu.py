@@ -125,6 +125,13 @@ def test_specialised_kernel_arithmetic_equals_the_generic_tail_and_the_oracle(co
                             _p(cnt, _f32p), _p(read, _f32p), C.c_float(float(d["row_z"].reshape(-1)[0])), _p(q, _f64p),
                             C.c_float(-np.inf), C.c_float(np.inf))
         assert fast.tobytes() == want.tobytes()
+        # the specialised kernel folds np.clip(z, lo, 1) * ratio and the caller's post-clip into ONE float32 clamp (noise_core.cuh:
+        # fast_constants): equal to clipping the reference's output, also where the two clips cut into each other
+        for lo, hi in ((-np.inf, 1.0), (0.0, 0.5), (-0.01, 250.0), (float(want.max()) * 2, np.inf), (-np.inf, float(want.min()) - 1)):
+            core.emul_fast_tail(_p(np.ascontiguousarray(y.reshape(-1)), _f32p), _p(fast, _f32p), _p(rate, _f32p), C.byref(r), 4096,
+                                _p(cnt, _f32p), _p(read, _f32p), C.c_float(float(d["row_z"].reshape(-1)[0])), _p(q, _f64p),
+                                C.c_float(lo), C.c_float(hi))
+            assert fast.tobytes() == np.clip(want.reshape(-1), np.float32(lo), np.float32(hi)).tobytes(), (lo, hi)
         ysc = (y.reshape(-1) * np.float32(p["wp"] - p["bl"])) / np.float32(p["ratio"])
         assert np.allclose(rate, ysc.astype(np.float64) / p["K"], rtol=3e-7)           # invK32 multiply: 2 roundings from the exact rate
 

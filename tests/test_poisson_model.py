@@ -86,7 +86,7 @@ def _table():
 def _table_sampler(lam, words, t):
     f32 = np.float32
     lam = lam.astype(f32)
-    u = np.minimum((words.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(f32), f32(0.99999994))   # fmaf, one rounding
+    u = (((words >> np.uint64(9)).astype(np.float64) + 0.5) * 2.0 ** -23).astype(f32)                  # top 23 bits, exact in float32
     i = (lam * f32(16)).astype(np.int64)
     delta = (lam.astype(np.float64) - 0.0625 * i).astype(f32)                                          # exact
     k = np.zeros(lam.shape, dtype=np.int64)

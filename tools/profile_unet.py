@@ -5,9 +5,11 @@ import torch
 import pnnp_b200 as P
 from pnnp_b200 import archs, _lib
 
-shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,4,1424,2128").split(","))
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+shape = tuple(int(v) for v in (args[0] if args else "1,4,1424,2128").split(","))
+RES = "--resunet" in sys.argv
 arch = dict(name="UNetSeeInDark", in_nc=4, out_nc=4, nf=32, nframes=1, use_dpsv=False, res=False, cascade=False, add=False, lock_wb=False)
-net = P.UNetSeeInDark(arch).cuda().eval(); P.initialize_weights(net)
+net = (P.ResUnet if RES else P.UNetSeeInDark)(arch).cuda().eval(); P.initialize_weights(net)
 x = torch.rand(shape, device="cuda")
 records = []
 orig_conv, orig_pool, orig_in, orig_first = archs._conv, archs._pool, archs._to_nhwc16, archs._first_conv
@@ -22,8 +24,9 @@ def conv_label(a, k):
     n, h, w, c0 = x0.shape
     c1 = 0 if k.get("x1") is None else k["x1"].shape[3]
     cout = a[5]; taps = {0: 9, 1: 1, 2: 4, 3: 9, 4: 9}[mode]
-    flops = 2.0 * n * h * w * (c0 + c1) * cout * taps
-    return ({0: "conv", 1: "1x1", 2: "convT", 3: "convS2", 4: "convX"}[mode], f"{c0+c1}->{cout} @{h}x{w}", flops)
+    flops = 2.0 * n * h * w * (c0 + c1) * cout * taps / (4 if mode == 3 else 1)
+    extra = ("+resid" if k.get("resid") is not None else "") + ("+pool" if k.get("pool_out") is not None else "") + ("+head" if k.get("head") is not None else "")
+    return ({0: "conv", 1: "1x1", 2: "convT", 3: "convS2", 4: "convX"}[mode], f"{c0+c1}->{cout} @{h}x{w}{extra}", flops)
 with torch.no_grad():
     for _ in range(3): net(x)
     torch.cuda.synchronize()
@@ -44,4 +47,4 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     px = shape[0] * shape[1] * shape[2] * shape[3]
-    print(f"sum of layers {tot:.3f} ms; whole forward {ms:.3f} ms; {px/1e6/ms*1e3:.0f} MP/s; {92288*px/ms/1e9:.1f} TFLOP/s effective")
+    print(f"sum of layers {tot:.3f} ms; whole forward {ms:.3f} ms; {px/1e6/ms*1e3:.0f} MP/s; {(119424 if RES else 92288)*px/ms/1e9:.1f} TFLOP/s effective")

@@ -21,6 +21,9 @@ def run(label):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
     print(f"{label:60s} {ms*1e3:8.1f} us   {n*c*h*w*8/ms/1e6:8.1f} GB/s", flush=True)
+if os.environ.get("PNNP_SYNTH_ONLY"):
+    run("product kernel")
+    sys.exit(0)
 for e, label in ((0, "product kernel"), (1, "no Poisson samplers"), (2, "no Tukey-lambda quantile"), (3, "no Poisson, no Tukey"),
                  (5, "no Poisson, no sorting"), (7, "no Poisson, no Tukey, no sorting"), (8, "no Philox rounds"),
                  (15, "none of them: loads, rates, queue traffic, f64 tail, stores")):
