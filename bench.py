@@ -135,13 +135,70 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU side: the oracle port of the reference algorithms (the reference is Python; /root/reference is
-# not on the GPU box).  Used ONLY as the reported baseline.
+# CPU side.  The reference is Python and /root/reference is not on the GPU box, so the CPU legs run
+#   * the UNMODIFIED reference from the git-ignored copy `oracle/_ref/` (oracle/build_ref.py, made by __graft_entry__.build() in the
+#     build container; SHA-256 manifest checked before use)            -> cpu_baseline.kind == "reference"
+#   * else the oracle port oracle/oracle_np.py                           -> cpu_baseline.kind == "port"
+# Used ONLY as the reported baseline, never by the product path.
 # ----------------------------------------------------------------------------------------------
+class _RefImpl:
+    """The reference's own functions behind the names the CPU legs call (same names as oracle_np)."""
+    kind = "reference"
+    what = "the unmodified reference (oracle/_ref: data_process/process.py generate_noisy_obs, archs/Unet.py, archs/ResUnet.py)"
+
+    def __init__(self, ns):
+        self.ns, self._mods = ns, {}
+        self.sample_params = ns.process.sample_params
+        self.sample_params_max = ns.process.sample_params_max
+
+    def generate_noisy_obs(self, y, param=None, noise_code="p"):
+        return self.ns.process.generate_noisy_obs(y, param=param, noise_code=noise_code)
+
+    def _module(self, name):
+        if name not in self._mods:
+            arch = dict(ARCH, name=name)
+            self._mods[name] = getattr(self.ns.archs, name)(arch).eval()
+        return self._mods[name]
+
+    def unet_forward(self, x, sd):
+        import torch
+        return torch.func.functional_call(self._module("UNetSeeInDark"), dict(sd), (x,))
+
+    def resunet_forward(self, x, sd):
+        import torch
+        return torch.func.functional_call(self._module("ResUnet"), dict(sd), (x,))
+
+
+_CPU_IMPL = None
+
+
 def _oracle():
+    """The CPU implementation the baseline legs time: the reference itself when oracle/_ref is intact, else the oracle port."""
+    global _CPU_IMPL
+    if _CPU_IMPL is not None:
+        return _CPU_IMPL
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if os.environ.get("PNNP_BENCH_CPU_PORT", "0") != "1" and os.path.isdir(os.path.join(ref_root, "data_process")):
+        try:
+            import build_ref
+            if build_ref.verify(ref_root):
+                os.environ["PNNP_REFERENCE_ROOT"] = ref_root
+                import ref_harness
+                if os.path.realpath(ref_harness.REFERENCE_ROOT) == os.path.realpath(ref_root):
+                    _CPU_IMPL = _RefImpl(ref_harness.load())
+                    return _CPU_IMPL
+        except Exception as e:                                         # a broken copy must not take the bench down
+            print(f"bench: oracle/_ref unusable ({type(e).__name__}: {e}); CPU legs use the oracle port", file=sys.stderr)
     import oracle_np as O
+    O.kind, O.what = "port", "the oracle port (oracle/oracle_np.py restatement of generate_noisy_obs / Unet.py / ResUnet.py)"
+    _CPU_IMPL = O
     return O
+
+
+def _cpu_impl_warm(_):
+    _oracle()
+    return 0
 
 
 def _cpu_synth_one_crop(seed):
@@ -242,27 +299,27 @@ def cpu_baseline(name, wl):
         k = 4
         _cpu_path_crops(1, cores)                                # warm-up (thread pools, oneDNN primitives)
         ts, tu = _cpu_path_crops(k, cores)
-        return {"value": k * 4 * 512 * 512 / 1e6 / (ts + tu), "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{k} of 64 crops (4x512x512): oracle_np.generate_noisy_obs one crop after the other (NumPy / SciPy are "
-                          f"single-threaded: {ts / k * 1e3:.0f} ms per crop) + oracle_np.unet_forward on torch CPU fp32 with {cores} "
-                          f"threads ({tu / k * 1e3:.0f} ms per crop)"}
+        return {"value": k * 4 * 512 * 512 / 1e6 / (ts + tu), "unit": UNIT, "cores": cores, "kind": _oracle().kind,
+                "sample": f"{k} of 64 crops (4x512x512): generate_noisy_obs one crop after the other (NumPy / SciPy are "
+                          f"single-threaded: {ts / k * 1e3:.0f} ms per crop) + the UNetSeeInDark forward on torch CPU fp32 with {cores} "
+                          f"threads ({tu / k * 1e3:.0f} ms per crop) — {_oracle().what}"}
     if name == "synth64":
         t_start, n, busy = time.perf_counter(), 0, 0.0
         while n < 64 and (time.perf_counter() - t_start) < 12.0:
             busy += _cpu_synth_one_crop(1000 + n)
             n += 1
-        return {"value": n * 4 * 512 * 512 / 1e6 / busy, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"{n} of 64 crops (4x512x512, '{NOISE_CODE}'), sequential, oracle_np.generate_noisy_obs "
-                          "(NumPy/SciPy are single-threaded)"}
+        return {"value": n * 4 * 512 * 512 / 1e6 / busy, "unit": UNIT, "cores": 1, "kind": _oracle().kind,
+                "sample": f"{n} of 64 crops (4x512x512, '{NOISE_CODE}'), sequential generate_noisy_obs "
+                          f"(NumPy/SciPy are single-threaded) — {_oracle().what}"}
     if name == "train_step":
         dt, k = _cpu_train_steps(1, cores)
-        return {"value": k * 4 * 512 * 512 / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"1 step on {k} of 8 crops (4x512x512): oracle generate_noisy_obs + torch CPU fp32 autograd of "
-                          f"oracle_np.unet_forward + Adam, {cores} threads"}
+        return {"value": k * 4 * 512 * 512 / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": _oracle().kind,
+                "sample": f"1 step on {k} of 8 crops (4x512x512): generate_noisy_obs + torch CPU fp32 autograd of "
+                          f"the UNetSeeInDark forward + Adam, {cores} threads — {_oracle().what}"}
     dt = _cpu_unet_frames(wl, 1, cores, resunet=(name == "sony_evaltest"))
     what = "generate_noisy_obs + resunet_forward (metrics excluded)" if name == "sony_evaltest" else "unet_forward"
-    return {"value": wl["c"] * wl["h"] * wl["w"] / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 frame 4x{wl['h']}x{wl['w']}, torch CPU fp32, {cores} threads, oracle_np.{what}"}
+    return {"value": wl["c"] * wl["h"] * wl["w"] / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": _oracle().kind,
+            "sample": f"1 frame 4x{wl['h']}x{wl['w']}, torch CPU fp32, {cores} threads, {what} — {_oracle().what}"}
 
 
 def run_reference_arm(args, name, wl):
@@ -276,6 +333,7 @@ def run_reference_arm(args, name, wl):
         import multiprocessing as mp
         workers = max(1, min(cores, 16))
         pool = mp.get_context("fork").Pool(workers)                # forked before torch starts its thread pools
+        pool.map(_cpu_impl_warm, range(workers))                   # every worker imports the CPU implementation outside the timed region
         import torch
         O = _oracle()
         import pnnp_b200 as P
@@ -300,14 +358,15 @@ def run_reference_arm(args, name, wl):
         dt = (time.perf_counter() - t0) * args.steps / steps
         pool.close()
         mp_step = workers * 4 * 512 * 512 / 1e6
-        sample = (f"{workers} of 64 crops per step ({steps} steps timed, scaled to {args.steps}): oracle port of generate_noisy_obs on "
-                  f"{workers} worker processes, then oracle_np.unet_forward per crop on torch CPU fp32 with {cores} threads")
+        sample = (f"{workers} of 64 crops per step ({steps} steps timed, scaled to {args.steps}): generate_noisy_obs on "
+                  f"{workers} worker processes, then the UNetSeeInDark forward per crop on torch CPU fp32 with {cores} threads")
         used = cores
     elif name == "synth64":
         import multiprocessing as mp
         workers = max(1, min(cores, 64))
         per_step = workers                                     # bounded sample: one crop per worker per step
         with mp.get_context("fork").Pool(workers) as pool:
+            pool.map(_cpu_impl_warm, range(workers))
             for w in range(args.warmup):
                 pool.map(_cpu_synth_one_crop, [w * per_step + i for i in range(per_step)])
             t0 = time.perf_counter()
@@ -315,7 +374,7 @@ def run_reference_arm(args, name, wl):
                 pool.map(_cpu_synth_one_crop, [5000 + s * per_step + i for i in range(per_step)])
             dt = time.perf_counter() - t0
         mp_step = per_step * 4 * 512 * 512 / 1e6
-        sample = f"{per_step} crops per step on {workers} worker processes (oracle port of generate_noisy_obs)"
+        sample = f"{per_step} crops per step on {workers} worker processes (generate_noisy_obs)"
         used = workers
     elif name == "train_step":
         steps = min(args.steps, 2)
@@ -339,7 +398,7 @@ def run_reference_arm(args, name, wl):
         "vs_baseline": None, "dtype": "f64" if name == "synth64" else ("f64 synthesis + f32 UNet" if name == "path64" else "f32"),
         "data": "synthetic",
         "config": {"workload": wl["desc"], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": _oracle().kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
 
 

@@ -3,7 +3,9 @@
 Imports the *unmodified* fenghansen/PNNP sources from /root/reference so that the
 restatement in ``oracle/oracle_np.py`` can be validated against them and golden vectors
 can be generated (``oracle/make_golden.py``).  /root/reference only exists in the build
-container; nothing under ``tests -m gpu``, ``smoke()`` or ``bench.py`` may call this.
+container; nothing under ``tests -m gpu`` or ``smoke()`` may call this.  ``bench.py``'s CPU legs
+(``--impl reference``, ``cpu_baseline``) load the unmodified copy that ``oracle/build_ref.py`` puts
+under the git-ignored ``oracle/_ref/`` (PNNP_REFERENCE_ROOT), never /root/reference itself.
 
 Nine third-party modules the reference imports at module top but never touches on the hot
 path are absent from this image; they are replaced by empty stubs.
@@ -13,7 +15,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PNNP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the unmodified copy under oracle/_ref (oracle/build_ref.py)."""
+    if os.path.isdir("/root/reference/data_process"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("PNNP_REFERENCE_ROOT") or _default_root()
 
 _STUBS = {
     "matplotlib": {},

@@ -241,3 +241,30 @@ def test_lr_of_the_kth_trained_epoch_matches_the_reference_scheduler_with_nonzer
     hyper = {"lr_scheduler": "WarmupCosine", "learning_rate": 1e-4, "last_epoch": 1200, "stop_epoch": 1600, "step_size": 10, "T": 2}
     lam = lr_lambda_from_hyper(hyper)
     assert lr_for_epoch(lam, 1201, 1200) == lam(1) and lam(1) > 32 * lam(1201)
+
+
+def test_reference_copy_recipe_is_verbatim_and_the_bench_baseline_uses_it(tmp_path):
+    """oracle/build_ref.py copies the reference packages byte for byte into a (git-ignored) directory with a SHA-256 manifest;
+    bench.py's CPU legs run that copy (`cpu_baseline.kind == "reference"`) and fall back to the oracle port when it is absent or
+    has been touched."""
+    import build_ref
+    src = "/root/reference"
+    if not os.path.isdir(os.path.join(src, "data_process")):
+        pytest.skip("reference tree not present")
+    dest = build_ref.build(src, str(tmp_path / "_ref"), quiet=True)
+    assert build_ref.verify(dest)
+    n = 0
+    for root, _d, files in os.walk(dest):
+        for f in files:
+            if f.endswith(".py"):
+                rel = os.path.relpath(os.path.join(root, f), dest)
+                assert open(os.path.join(root, f), "rb").read() == open(os.path.join(src, rel), "rb").read(), rel
+                n += 1
+    assert n >= 20
+    with open(os.path.join(dest, "archs", "Unet.py"), "a") as f:
+        f.write("\n# edited\n")
+    assert not build_ref.verify(dest)                                   # an edited copy is refused
+    gi = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in gi                                         # never part of the history
+    ig = os.path.join(ROOT, ".gpurunignore")
+    assert not os.path.exists(ig) or "oracle/_ref" not in open(ig).read()   # but it travels to the GPU box
