@@ -43,6 +43,10 @@ struct FirstParams {
 // byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_32B block whose base is 256-byte aligned
 __device__ __forceinline__ uint32_t swz32(uint32_t r, uint32_t c) { return r * 32u + ((c ^ ((r >> 2) & 1u)) << 4); }
 
+__device__ __forceinline__ uint16_t bf1(float a) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(a);
+    return *reinterpret_cast<const uint16_t*>(&h);
+}
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -314,24 +318,27 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_first_ws_kernel(const Firs
         const int my = tid >> 4, mx = tid & 15;
         for (int t = t_begin, k = 0; t < t_end; ++t, ++k) {
             const int b = k & 1;
-            float* const s_mine = s_in + b * 768 + warp * kFirstPlane + lane;
+            // staging tile: bf16, channel-interleaved ([pixel][4 channels] = 8 bytes per pixel), converted by the loading thread —
+            // the im2col below then reads a tap's four channels with ONE 8-byte load that already is the packed pair of words of
+            // the A row (36 scalar loads + 18 conversions per pixel before: the kernel is bound by load / store-unit work)
+            uint16_t* const s_mine = reinterpret_cast<uint16_t*>(s_in + b * 768) + lane * 4 + warp;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) s_mine[32 * j] = pre[j];
-            if (last_on) s_mine[160] = pre[5];
+            for (int j = 0; j < 5; ++j) s_mine[128 * j] = bf1(pre[j]);
+            if (last_on) s_mine[640] = bf1(pre[5]);
             mbar_arrive(pbar);                                               // producer-group barrier: the fp32 tile is complete
             if (t + 1 < t_end) prefetch();                                   // next tile's loads fly during the im2col and the waits
             mbar_wait(pbar, (uint32_t)(k & 1), err, 311);
             mbar_wait(a_empty + 8 * b, (uint32_t)(((k >> 1) & 1) ^ 1), err, 312);      // the MMAs that read A[b] two tiles ago are done
-            const float* const q0 = s_in + b * 768 + my * kFirstHaloW + mx;
+            const uint2* const q0 = reinterpret_cast<const uint2*>(s_in + b * 768) + my * kFirstHaloW + mx;
             uint8_t* const a = sA + b * 3 * kFirstABlock;
             uint32_t pk[9][2];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const float* q = q0 + ky * kFirstHaloW + kx;
-                    pk[ky * 3 + kx][0] = bf2(q[0], q[kFirstPlane]);
-                    pk[ky * 3 + kx][1] = bf2(q[2 * kFirstPlane], q[3 * kFirstPlane]);
+                    const uint2 q = q0[ky * kFirstHaloW + kx];               // channels (0, 1) | (2, 3) of the tap's pixel
+                    pk[ky * 3 + kx][0] = q.x;
+                    pk[ky * 3 + kx][1] = q.y;
                 }
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
