@@ -193,6 +193,9 @@ class _EmulatedLibrary:
     def pnnp_conv_pipeline_error(self):
         return self.tc.emul_conv_pipeline_error()
 
+    def pnnp_conv_first_pipeline_error(self):
+        return self.tc.emul_conv_first_pipeline_error()
+
 
 @pytest.fixture
 def emu(monkeypatch, libs):

@@ -316,3 +316,22 @@ def test_reference_signatures_roundtrip():
     assert z.shape == yt.shape and z.is_cuda and float(z.min()) >= 0.0
     z2 = P.generate_noisy_obs(yt, param=p, noise_code="pgr")
     assert z2.is_cuda and z2.dtype == torch.float32
+
+
+def test_tiny_tukey_lambda_withholds_the_specialised_kernel_hint():
+    """The specialised kernel has only the power form of the Tukey-lambda quantile; PNNP_CODE_UNIFORM_F64 therefore also promises
+    |lam| >= 1e-3 (include/pnnp_b200.h).  A table with a smaller shape parameter goes through the generic kernel (series form) and
+    still equals the replay of its own draws; the read noise is the logistic-like limit, finite and centred."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    y = torch.rand((2, 4, 64, 512), device="cuda", generator=g) ** 2
+    np.random.seed(4)
+    params = [P.sample_params("SonyA7S2") for _ in range(2)]
+    assert P.ParamTable(params, y.device).uniform_f64
+    params[1]["lam"] = 5e-4
+    tab = P.ParamTable(params, y.device)
+    assert not tab.uniform_f64
+    out, d = P.synthesize_batch(y, None, "pgrq", generator=P.PhiloxGenerator(5), debug=True, table=tab)
+    rep = P.replay_batch(y, params, "pgrq", {"shot": d["shot"], "read": d["read"], "row_z": d["row_z"], "q": d["q"]})
+    assert torch.equal(out, rep)
+    r = d["read"][1].double()
+    assert torch.isfinite(r).all() and abs(float(r.mean())) < 0.05 * float(r.std())
