@@ -380,7 +380,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const bool has_head = kSpec ? (EPI & EPI_HEAD) != 0 : p.head_out != nullptr;
         // activation as max(v, v * slope + 0): LeakyReLU 0.2 / ReLU (slope 0; the +0 turns -0 into +0) / identity (slope 1)
         const float slope = p.act == ACT_LEAKY ? 0.2f : (p.act == ACT_RELU ? 0.f : 1.f);
-        const int chunks16 = (xmode ? p.cout : p.umma_n) / 16;
+        // Every parameter the tile loop reads, copied out of the parameter bank once: the asm statements carry "memory" clobbers, so each
+        // p.field inside the loop was re-read per tile (the r02 capture of conv9_2 + head shows LDCU -> compare -> branch chains on the
+        // critical path of every tile: 15 % of the epilogue warps' stall samples were per-tile set-up)
+        const int eH = p.H, eW = p.W, e_cout = p.cout, e_umma_n = p.umma_n, e_n_tiles = p.n_tiles, e_tiles_x = p.tiles_x, e_tiles_y = p.tiles_y;
+        const int e_cout_stride = p.cout_stride, e_groups = p.groups;
+        int* const e_err = p.err;
+        void* const e_out = p.out;
+        void* const e_pool_out = p.pool_out;
+        const __nv_bfloat16* const e_resid = p.resid;
+        const __nv_bfloat16* const e_mask = p.mask;
+        const float e_mask_slope = p.mask_slope;
+        const int chunks16 = (xmode ? e_cout : e_umma_n) / 16;
         // fused head: its four biases once per thread (they were four global loads per pixel and tile — 13 % of the stall
         // samples of conv9_2 + head in the r02 capture, each addition waiting for its own load)
         float head_bias[4] = {0.f, 0.f, 0.f, 0.f};
@@ -392,39 +403,39 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         float* const head_out = p.head_out;
         const float* const head_resid = p.resid_nchw;
         TileIter ti;
-        ti.init(total_tiles, p.n_tiles, p.tiles_x, p.tiles_y);
+        ti.init(total_tiles, e_n_tiles, e_tiles_x, e_tiles_y);
         if (PNNP_DBG_K & 32) ti.t = ti.t_end;
-        const int slot = SUP ? group >> 1 : group, n_slots = SUP ? p.groups >> 1 : p.groups;     // SUP: two groups share a super-tile
+        const int slot = SUP ? group >> 1 : group, n_slots = SUP ? e_groups >> 1 : e_groups;     // SUP: two groups share a super-tile
         const int y_in = SUP ? (group & 1) * kTileH + ty_in : ty_in, tile_rows = SUP ? 2 * kTileH : kTileH;
-        for (int g = 0; g < slot && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);   // slot s: every n_slots-th tile
+        for (int g = 0; g < slot && ti.valid(); ++g) ti.next(e_n_tiles, e_tiles_x, e_tiles_y);   // slot s: every n_slots-th tile
         for (; ti.valid(); ) {
             const int n_tile = ti.n_tile, tx = ti.tx, ty = ti.ty, img = ti.img;
-            for (int g = 0; g < n_slots && ti.valid(); ++g) ti.next(p.n_tiles, p.tiles_x, p.tiles_y);
+            for (int g = 0; g < n_slots && ti.valid(); ++g) ti.next(e_n_tiles, e_tiles_x, e_tiles_y);
             const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTileW + tx_in, y = ty * tile_rows + y_in;
-            const bool valid = x < p.W && y < p.H && (!xmode || (tx_in >= 1 && tx_in <= kTileWX));
-            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);
+            const bool valid = x < eW && y < eH && (!xmode || (tx_in >= 1 && tx_in <= kTileWX));
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, e_err, 104);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * (uint32_t)p.umma_n + ((uint32_t)(quad * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * (uint32_t)e_umma_n + ((uint32_t)(quad * 32) << 16);
             if (PNNP_DBG_K & 8) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc])); acc_phase ^= 1; continue; }
-            const int col_tile0 = n_tile * p.umma_n;     // first GEMM column of this tile
-            const size_t pix_in = ((size_t)img * p.H + y) * (size_t)p.W + x;
+            const int col_tile0 = n_tile * e_umma_n;     // first GEMM column of this tile
+            const size_t pix_in = ((size_t)img * eH + y) * (size_t)eW + x;
             // per-tile addresses hoisted out of the chunk loop (the asm statements' memory clobbers make the compiler re-read the
             // parameter bank and redo the 64-bit products per 16-channel chunk otherwise)
-            const size_t pool_off = has_pool ? (((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1)) * (size_t)p.cout_stride : 0;
-            const size_t out_off = pix_in * (size_t)p.cout_stride;
+            const size_t pool_off = has_pool ? (((size_t)img * (eH >> 1) + (y >> 1)) * (size_t)(eW >> 1) + (x >> 1)) * (size_t)e_cout_stride : 0;
+            const size_t out_off = pix_in * (size_t)e_cout_stride;
             float head[4] = {0.f, 0.f, 0.f, 0.f};
             // specialised ConvTranspose2d epilogue: (tap, channel block) of chunk j kept as a running pair — one division per tile
             constexpr bool kCtT = EPI >= 0 && (EPI & EPI_CONVT) != 0;
             int t_cpt = 1, t_tap = 0, t_rem = 0;
-            if constexpr (kCtT) { t_cpt = p.cout >> 4; t_tap = (col_tile0 >> 4) / t_cpt; t_rem = (col_tile0 >> 4) - t_tap * t_cpt; }
+            if constexpr (kCtT) { t_cpt = e_cout >> 4; t_tap = (col_tile0 >> 4) / t_cpt; t_rem = (col_tile0 >> 4) - t_tap * t_cpt; }
             for (int j = 0; j < chunks16; ++j) {
                 uint32_t v[16];
                 tc_ld16(taddr + j * 16, v);
                 if (xmode) {
                     // columns are (dx, co): out(j) = P[j-1, dx=0] + P[j, dx=1] + P[j+1, dx=2] along the 16-lane tile row
                     uint32_t v0[16], v2[16];
-                    tc_ld16(taddr + p.cout + j * 16, v0);          // dx = 1 block (own column)
-                    tc_ld16(taddr + 2 * p.cout + j * 16, v2);      // dx = 2 block
+                    tc_ld16(taddr + e_cout + j * 16, v0);          // dx = 1 block (own column)
+                    tc_ld16(taddr + 2 * e_cout + j * 16, v2);      // dx = 2 block
                     tc_ld_wait();
                     if constexpr (kX2) {
 #pragma unroll
@@ -454,13 +465,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const int tap = t_tap;
                     c0 = t_rem << 4;
                     if (++t_rem == t_cpt) { t_rem = 0; ++t_tap; }
-                    opix = ((size_t)img * (2 * p.H) + (2 * y + (tap >> 1))) * (size_t)(2 * p.W) + (2 * x + (tap & 1));
+                    opix = ((size_t)img * (2 * eH) + (2 * y + (tap >> 1))) * (size_t)(2 * eW) + (2 * x + (tap & 1));
                 } else if (is_convt) {                    // GEMM column = (a*2+b)*cout + co  ->  pixel (2y+a, 2x+b)
-                    const int tap = c0 / p.cout;
-                    c0 -= tap * p.cout;
-                    opix = ((size_t)img * (2 * p.H) + (2 * y + (tap >> 1))) * (size_t)(2 * p.W) + (2 * x + (tap & 1));
+                    const int tap = c0 / e_cout;
+                    c0 -= tap * e_cout;
+                    opix = ((size_t)img * (2 * eH) + (2 * y + (tap >> 1))) * (size_t)(2 * eW) + (2 * x + (tap & 1));
                 }
-                if (c0 >= p.cout) continue;               // zero-padded weight rows (warp-uniform)
+                if (c0 >= e_cout) continue;               // zero-padded weight rows (warp-uniform)
                 float f[16];
                 if constexpr (kCtT) {                     // bias only: the launcher takes this epilogue for act == NONE (identity) alone
 #pragma unroll
@@ -495,19 +506,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float a = __uint_as_float(v[i]) + s_bias[min(c0 + i, p.cout - 1)];
+                        const float a = __uint_as_float(v[i]) + s_bias[min(c0 + i, e_cout - 1)];
                         f[i] = fmaxf(a, fmaf(a, slope, 0.0f));
                     }
                 }
                 if (kF32 && out_nhwc) {
                     // fp32-storage variant: residual, output and fused max-pool in fp32 NHWC (the accumulators are never rounded)
                     if (has_resid && valid) {
-                        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + opix * p.cout_stride + c0);
+                        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e_resid) + opix * e_cout_stride + c0);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { const float4 r = rp[i]; f[4 * i] += r.x; f[4 * i + 1] += r.y; f[4 * i + 2] += r.z; f[4 * i + 3] += r.w; }
                     }
-                    if (p.out && valid) {
-                        float* op = reinterpret_cast<float*>(p.out) + opix * p.cout_stride + c0;
+                    if (e_out && valid) {
+                        float* op = reinterpret_cast<float*>(e_out) + opix * e_cout_stride + c0;
                         uint32_t w0[8], w1[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { w0[i] = __float_as_uint(f[i]); w1[i] = __float_as_uint(f[8 + i]); }
@@ -523,8 +534,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             m[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
                         }
                         if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16)) {
-                            const size_t pp = ((size_t)img * (p.H >> 1) + (y >> 1)) * (size_t)(p.W >> 1) + (x >> 1);
-                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.pool_out) + pp * p.cout_stride + c0);
+                            const size_t pp = ((size_t)img * (eH >> 1) + (y >> 1)) * (size_t)(eW >> 1) + (x >> 1);
+                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e_pool_out) + pp * e_cout_stride + c0);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) op[i] = make_float4(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
                         }
@@ -540,7 +551,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 } else if (out_nhwc) {
                     if (has_resid && valid) {
                         uint32_t rw[8];
-                        ld_global_256(p.resid + opix * p.cout_stride + c0, rw);
+                        ld_global_256(e_resid + opix * e_cout_stride + c0, rw);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             f[2 * i] += __uint_as_float(rw[i] << 16);
@@ -550,11 +561,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     if (has_mask && valid) {
                         // backward of the producing layer's activation, fused: g_pre = g * act'(out), out > 0 ? 1 : slope
                         uint32_t mw[8];
-                        ld_global_256(p.mask + opix * p.cout_stride + c0, mw);
+                        ld_global_256(e_mask + opix * e_cout_stride + c0, mw);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            f[2 * i] *= __uint_as_float(mw[i] << 16) > 0.f ? 1.f : p.mask_slope;
-                            f[2 * i + 1] *= __uint_as_float(mw[i] & 0xFFFF0000u) > 0.f ? 1.f : p.mask_slope;
+                            f[2 * i] *= __uint_as_float(mw[i] << 16) > 0.f ? 1.f : e_mask_slope;
+                            f[2 * i + 1] *= __uint_as_float(mw[i] & 0xFFFF0000u) > 0.f ? 1.f : e_mask_slope;
                         }
                     }
                     uint32_t pk[8];
@@ -563,8 +574,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                         pk[i] = *reinterpret_cast<const uint32_t*>(&h);
                     }
-                    if (p.out && valid && !(PNNP_DBG_K & 1))
-                        st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + (is_convt ? opix * p.cout_stride : out_off) + c0, pk);     // one whole sector
+                    if (e_out && valid && !(PNNP_DBG_K & 1))
+                        st_global_256(reinterpret_cast<__nv_bfloat16*>(e_out) + (is_convt ? opix * e_cout_stride : out_off) + c0, pk);     // one whole sector
                     if (has_pool) {
                         // fused nn.MaxPool2d(2): lanes l^1 hold the x-neighbour, l^16 the y-neighbour of the same tile
                         // (a warp owns two 16-pixel tile rows); max of bf16-rounded values == rounding of the max
@@ -579,7 +590,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             pk[i] = *reinterpret_cast<uint32_t*>(&a);
                         }
                         if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16) && !(PNNP_DBG_K & 1)) {
-                            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.pool_out) + pool_off + c0, pk);
+                            st_global_256(reinterpret_cast<__nv_bfloat16*>(e_pool_out) + pool_off + c0, pk);
                         }
                     }
                     if (has_head) {
@@ -607,20 +618,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         }
                     }
                 } else if (valid) {
-                    float* o = reinterpret_cast<float*>(p.out);
-                    const size_t plane = (size_t)p.H * p.W;
+                    float* o = reinterpret_cast<float*>(e_out);
+                    const size_t plane = (size_t)eH * eW;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {           // static indices keep f[] in registers
-                        if (c0 + i < p.cout) {
-                            const size_t oi = ((size_t)img * p.cout + (c0 + i)) * plane + (size_t)y * p.W + x;
-                            o[oi] = f[i] + (p.resid_nchw ? p.resid_nchw[oi] : 0.f);
+                        if (c0 + i < e_cout) {
+                            const size_t oi = ((size_t)img * e_cout + (c0 + i)) * plane + (size_t)y * eW + x;
+                            o[oi] = f[i] + (head_resid ? head_resid[oi] : 0.f);
                         }
                     }
                 }
             }
             if (has_head && valid) {
-                const size_t plane = (size_t)p.H * p.W;
-                size_t oi = (size_t)img * head_cout * plane + (size_t)y * p.W + x;       // output 0; one plane further per output
+                const size_t plane = (size_t)eH * eW;
+                size_t oi = (size_t)img * head_cout * plane + (size_t)y * eW + x;       // output 0; one plane further per output
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
                     if (o < head_cout) {
