@@ -190,7 +190,7 @@ class _TCNet(nn.Module):
         # measured on B200 (profiles/): x-mode wins when 3*Cout <= 128 (four TMEM accumulators / epilogue groups
         # stay available) or when K is long (two-source decoder convs); otherwise the per-tap mode does.
         narrow = cout <= _XMODE_MAX_COUT or (cout <= 64 and kw.get("x1") is not None)
-        if narrow and cout % 16 == 0 and kw.get("resid") is None and _X_MODE:
+        if narrow and cout % 16 == 0 and _X_MODE:
             w, b = self._packed(name, "conv3x")
             return _conv(_lib.CONV3X, x0, w, b, out, cout, act, **kw)
         w, b = self._packed(name)
@@ -338,17 +338,21 @@ class ResUnet(_TCNet):
         sig = (n, h, w, str(dev), dt)
         buf = lambda name, hh, ww, cc: ws.get(sig, name, (n, hh, ww, cc), dev, dt)
 
-        def block(i, src0, src1, hh, ww, co):
-            """ResidualBlock i on (src0 [, src1]) -> NHWC bf16 (modules.py:176-197)."""
-            w1, _ = self._packed(f"conv{i}.block.0.conv.conv")
-            w2, _ = self._packed(f"conv{i}.block.1.conv.conv")
-            t = _conv(_lib.CONV3, src0, w1, None, buf(f"b{i}a", hh, ww, co), co, _lib.ACT_RELU, x1=src1)
+        def block(i, src0, src1, hh, ww, co, head=None):
+            """ResidualBlock i on (src0 [, src1]) -> NHWC bf16 (modules.py:176-197).  Narrow layers take the x-shift-in-N kernel
+            mode like the UNet's (`_conv3`); the second conv adds the shortcut in its (specialised) epilogue, and the last block
+            also applies conv10 there (`head`: the block's output then never reaches HBM)."""
+            conv3 = self._conv3 if dt == torch.bfloat16 else (
+                lambda name, x0, out_, cout, act, **kw: _conv(_lib.CONV3, x0, self._packed(name)[0], None, out_, cout, act, **kw))
+            t = conv3(f"conv{i}.block.0.conv.conv", src0, buf(f"b{i}a", hh, ww, co), co, _lib.ACT_RELU, x1=src1)
             if src1 is None:
                 shortcut = src0                                        # identity (in_c == out_c)
             else:
                 wsc, _ = self._packed(f"conv{i}.short_cut.0.conv.conv")
                 shortcut = _conv(_lib.CONV1, src0, wsc, None, buf(f"b{i}s", hh, ww, co), co, _lib.ACT_NONE, x1=src1)
-            return _conv(_lib.CONV3, t, w2, None, buf(f"b{i}", hh, ww, co), co, _lib.ACT_NONE, resid=shortcut)
+            if head is not None:
+                return conv3(f"conv{i}.block.1.conv.conv", t, None, co, _lib.ACT_NONE, resid=shortcut, head=head[:3], resid_nchw=head[3])
+            return conv3(f"conv{i}.block.1.conv.conv", t, buf(f"b{i}", hh, ww, co), co, _lib.ACT_NONE, resid=shortcut)
 
         with torch.cuda.device(dev):
             if dt == torch.bfloat16 and _use_first_conv(c, nf):    # conv_in straight from the packed fp32 planes
@@ -366,14 +370,25 @@ class ResUnet(_TCNet):
                     wp, bp = self._packed(f"pool{i}.conv")
                     cur = _conv(_lib.CONV3S2, cur, wp, bp, buf(f"d{i}", hh // 2, ww // 2, co * 2), co * 2, _lib.ACT_NONE)
                     hh, ww = hh // 2, ww // 2
+            out = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=dev)
+            # conv10 (1x1, ResUnet.py:88) inside the last block's second conv: x-mode + residual + head epilogue (fp32 head weights)
+            fuse_head = dt == torch.bfloat16 and _X_MODE and nf <= _XMODE_MAX_COUT and nf % 16 == 0 and self.out_nc <= 4 \
+                and os.environ.get("PNNP_RESUNET_FUSED_HEAD", "1") != "0"
+            if fuse_head:
+                hw10 = self.conv10.weight.detach().reshape(self.out_nc, nf)
+                hb10 = self.conv10.bias.detach()
+                if hw10.dtype != torch.float32 or not hw10.is_contiguous():
+                    hw10, hb10 = hw10.float().contiguous(), hb10.float().contiguous()
             for i in range(6, 10):
                 co = nf * 2 ** (9 - i)
                 wu, bu = self._packed(f"upv{i}", "convT")
                 up = _conv(_lib.CONVT, cur, wu, bu, buf(f"u{i}", hh * 2, ww * 2, co), co, _lib.ACT_NONE)
                 hh, ww = hh * 2, ww * 2
+                if i == 9 and fuse_head:
+                    block(i, up, skips[9 - i], hh, ww, co, head=(hw10, hb10, out, x if self.res else None))
+                    return out
                 cur = block(i, up, skips[9 - i], hh, ww, co)
             w10, b10 = self._packed("conv10")
-            out = torch.empty((n, self.out_nc, h, w), dtype=torch.float32, device=dev)
             _conv(_lib.CONV1, cur, w10, b10, out, self.out_nc, _lib.ACT_NONE, out_mode=_lib.OUT_NCHW_F32,
                   resid_nchw=x if self.res else None)
         return out

@@ -158,6 +158,7 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
 // 3x3 layers (no residual, no transposed conv), bit 0 = x-shift-in-N mode, bit 1 = fused 2x2 max-pool, bit 2 = fused 1x1 head:
 // the narrow full-resolution layers are bound by the epilogue's instruction count, and most of it was run-time feature tests.
 constexpr int EPI_GENERIC = -1, EPI_X = 1, EPI_POOL = 2, EPI_HEAD = 4, EPI_MASK = 8;   // bit 3: activation-derivative mask (training dgrad)
+constexpr int EPI_RESID = 32;          // bit 5: NHWC bf16 residual added after the activation (the second conv of a ResUnet residual block; r02: those layers ran the generic epilogue, 217 us against 135 for the same conv without the residual)
 constexpr int EPI_CONVT = 16;           // bit 4: ConvTranspose2d pixel-shuffle store (bf16 NHWC, bias only) — default for > 64 input channels since r02, see conv_layer_launch
 // SUP: super-tile.  One pipeline stage carries a 16-row box (8 + 8 + 2 halo rows, ONE TMA load) and feeds TWO M = 128 tiles —
 // rows 0-7 into accumulator buffer a, rows 8-15 (A descriptor start + 128 pixel rows) into buffer a + 1 — so the producer <-> MMA
@@ -374,7 +375,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const bool xmode = kSpec ? (EPI & EPI_X) != 0 : p.mode == MODE_CONV3X;
         const bool is_convt = kSpec ? (EPI & EPI_CONVT) != 0 : p.mode == MODE_CONVT;
         const bool out_nhwc = kSpec ? true : p.out_mode == OUT_NHWC_BF16;
-        const bool has_resid = kSpec ? false : p.resid != nullptr;
+        const bool has_resid = kSpec ? (EPI & EPI_RESID) != 0 : p.resid != nullptr;
         const bool has_mask = kSpec ? (EPI & EPI_MASK) != 0 : p.mask != nullptr;
         const bool has_pool = kSpec ? (EPI & EPI_POOL) != 0 : p.pool_out != nullptr;
         const bool has_head = kSpec ? (EPI & EPI_HEAD) != 0 : p.head_out != nullptr;
@@ -756,7 +757,6 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         return fail("conv: fused 1x1 head needs a single N tile, cout <= 64 and 1..4 head channels");
     if (out_mode == OUT_NHWC_BF16 && (cout % 16)) return fail("conv: NHWC output needs cout % 16 == 0");
     if (mode == MODE_CONVT ? (w_rows != cout) : (w_rows < n_tiles * umma_n)) return fail("conv: weight tensor has the wrong number of rows");
-    if (mode == MODE_CONV3X && d.resid) return fail("conv3x: residual add is not supported in this mode");
     const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : ((mode == MODE_CONVT || mode == MODE_CONV2S2) ? 4 : (mode == MODE_CONV3X ? 3 : 1));
     const bool s2 = mode == MODE_CONV3S2 || mode == MODE_CONV2S2;
     if (s2 && (nsrc > 1 || (h & 1) || (w & 1))) return fail("stride-2 conv: single source, even h and w");
@@ -776,9 +776,13 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
     const int dbg_env = getenv("PNNP_CONV_DBG") ? atoi(getenv("PNNP_CONV_DBG")) : 0;
     int epi = EPI_GENERIC;
-    if (!f32 && !no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !d.resid && !dbg_env &&
-        !(d.pool_out && d.head_out) && !(d.mask && (d.pool_out || d.head_out)))
+    if (!f32 && !no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !dbg_env &&
+        !(d.pool_out && d.head_out) && !(d.mask && (d.pool_out || d.head_out))) {
         epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
+        // residual: built alone (32), with the x-shift-in-N mode (33) and with x-mode + fused head (37: the last residual block of the
+        // ResUnet + conv10); every other combination runs the generic epilogue
+        if (d.resid) epi = (d.pool_out || d.mask || (d.head_out && mode != MODE_CONV3X)) ? EPI_GENERIC : (epi | EPI_RESID);
+    }
     if (!f32 && convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
         act == ACT_NONE && !no_spec && !dbg_env)
         epi = EPI_CONVT;
@@ -872,7 +876,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (smem > 227 * 1024) return fail("conv: shared memory budget exceeded");
     static bool attr_done = false;
     // (taps per stage, K16 slices, epilogue specialisation); specialised epilogues exist for the 3-taps-per-stage shapes
-#define PNNP_SPEC_EPI(X, T, K) X(T, K, 0) X(T, K, 1) X(T, K, 2) X(T, K, 3) X(T, K, 4) X(T, K, 5)
+#define PNNP_SPEC_EPI(X, T, K) X(T, K, 0) X(T, K, 1) X(T, K, 2) X(T, K, 3) X(T, K, 4) X(T, K, 5) X(T, K, 32) X(T, K, 33) X(T, K, 37)
 #define PNNP_FOR_EACH_CONV_VARIANT(X) X(3, 1, -1) X(3, 2, -1) X(3, 4, -1) X(1, 1, -1) X(1, 2, -1) X(1, 4, -1) \
     PNNP_SPEC_EPI(X, 3, 1) PNNP_SPEC_EPI(X, 3, 2) PNNP_SPEC_EPI(X, 3, 4) X(3, 1, 8) X(3, 2, 8) X(3, 4, 8) X(3, 1, 9) X(3, 2, 9) X(3, 4, 9) \
     X(1, 1, 16) X(1, 2, 16) X(1, 4, 16)
