@@ -595,7 +595,7 @@ def run_gpu_arm(args, name, wl):
         mosaic[:, 1::2, 1::2], mosaic[:, 1::2, 0::2] = raw_dev[:, 2], raw_dev[:, 3]
         raw_host.copy_(mosaic.to(torch.int16).cpu())
         del mosaic, raw_dev
-        pipe = SynthDenoisePipeline(net, n, 2 * h, 2 * w, 16383, 512, NOISE_CODE, device, chunk=int(os.environ.get("PNNP_E2E_CHUNK", "16")))
+        pipe = SynthDenoisePipeline(net, n, 2 * h, 2 * w, 16383, 512, NOISE_CODE, device, chunk=int(os.environ.get("PNNP_E2E_CHUNK", "64")))
         e2e_metrics = {}
 
         def e2e_step():

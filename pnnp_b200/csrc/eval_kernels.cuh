@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) ssim_mse_kernel(const float* __restrict__
 // accumulators ONCE per block: with one tile per block every block ended in two float64 atomics on the same two addresses per frame
 // (65 536 same-address atomics per 16 crops serialise in L2 — the whole kernel's 291 us in r02, whatever the arithmetic cost).
 constexpr int kS2TilesPerCta = 8;
-__global__ void __launch_bounds__(kS2Threads) ssim_mse_v2_kernel(Ssim2Args g, double* sums, int stride) {
+__global__ void __launch_bounds__(kS2Threads, 4) ssim_mse_v2_kernel(Ssim2Args g, double* sums, int stride) {
     extern __shared__ __align__(16) uint8_t s2_raw[];
     Ssim2Tile& t = *reinterpret_cast<Ssim2Tile*>(s2_raw);
     PNNP_SMEM double s_red[8];
@@ -120,10 +120,13 @@ __global__ void __launch_bounds__(kS2Threads) ssim_mse_v2_kernel(Ssim2Args g, do
     if (g.use_gain) g.gain = (float)sums[frame * stride + 0] / (float)sums[frame * stride + 1];   // num / den in float32 like torch
     const int x0 = blockIdx.x * kS2TileX;
     double se = 0.0, ssum = 0.0;
+    Ssim2Regs nxt;                                      // the next tile's pixels: loaded while the current tile is summed
+    ssim2_fetch(threadIdx.x, g, plane_id, x0, blockIdx.y * kS2TilesPerCta * kS2TileY, nxt);
     for (int k = 0; k < kS2TilesPerCta; ++k) {
         const int y0 = (blockIdx.y * kS2TilesPerCta + k) * kS2TileY;
         if (y0 >= g.h) break;
-        se += ssim2_load(threadIdx.x, g, plane_id, x0, y0, t);
+        se += ssim2_stage(threadIdx.x, g, x0, y0, nxt, t);
+        if (k + 1 < kS2TilesPerCta && y0 + kS2TileY < g.h) ssim2_fetch(threadIdx.x, g, plane_id, x0, y0 + kS2TileY, nxt);
         __syncthreads();
         ssim2_hsum(threadIdx.x, t);
         __syncthreads();

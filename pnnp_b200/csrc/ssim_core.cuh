@@ -34,20 +34,39 @@ struct Ssim2Tile {
     double hs[5][kS2PatchY][kS2TileX];                         // horizontal 7-sums per patch row and centre column: 28 KB
 };
 
-// phase 1: load + tensor2im of the (22 x 38) patch of plane `plane`; returns this thread's share of the squared error
-__device__ __forceinline__ double ssim2_load(int tid, const Ssim2Args& g, int plane, int x0, int y0, Ssim2Tile& t) {
+// phase 1, split in two so that the kernel can keep the NEXT tile's global loads in flight while it computes the current one (r02
+// capture: the pass spent 4.3 of its 14 warp cycles per issue waiting for these loads and 4.5 at the barriers behind them):
+//   ssim2_fetch  the thread's (up to) four pixels of both planes into registers, zero outside the image;
+//   ssim2_stage  tensor2im of those registers into the shared tile; returns this thread's share of the squared error.
+constexpr int kS2Slots = (kS2PatchY * kS2PatchX + kS2Threads - 1) / kS2Threads;        // 4
+struct Ssim2Regs { float d[kS2Slots], r[kS2Slots]; };
+__device__ __forceinline__ void ssim2_fetch(int tid, const Ssim2Args& g, int plane, int x0, int y0, Ssim2Regs& v) {
     const float* d = g.dn + (size_t)plane * g.h * g.w;
     const float* r = g.hr + (size_t)plane * g.h * g.w;
+#pragma unroll
+    for (int k = 0; k < kS2Slots; ++k) {
+        const int i = tid + k * kS2Threads;
+        const int py = i / kS2PatchX, px = i - py * kS2PatchX;
+        const int gx = x0 + px - kS2Pad, gy = y0 + py - kS2Pad;
+        const bool in = i < kS2PatchY * kS2PatchX && gx >= 0 && gx < g.w && gy >= 0 && gy < g.h;
+        v.d[k] = in ? d[(size_t)gy * g.w + gx] : 0.f;
+        v.r[k] = in ? r[(size_t)gy * g.w + gx] : 0.f;
+    }
+}
+__device__ __forceinline__ double ssim2_stage(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Regs& v, Ssim2Tile& t) {
     double se = 0.0;
-    for (int i = tid; i < kS2PatchY * kS2PatchX; i += kS2Threads) {
+#pragma unroll
+    for (int k = 0; k < kS2Slots; ++k) {
+        const int i = tid + k * kS2Threads;
+        if (i >= kS2PatchY * kS2PatchX) break;
         const int py = i / kS2PatchX, px = i - py * kS2PatchX;
         const int gx = x0 + px - kS2Pad, gy = y0 + py - kS2Pad;
         float a = 0.f, b = 0.f;
         if (gx >= 0 && gx < g.w && gy >= 0 && gy < g.h) {
-            float p = fminf(fmaxf(d[(size_t)gy * g.w + gx] * g.scale, 0.f), 1.f);
+            float p = fminf(fmaxf(v.d[k] * g.scale, 0.f), 1.f);
             if (g.use_gain) p = g.gain * p;
             a = fminf(fmaxf(p * 255.0f, 0.f), 255.f);
-            b = fminf(fmaxf(r[(size_t)gy * g.w + gx] * 255.0f, 0.f), 255.f);
+            b = fminf(fmaxf(v.r[k] * 255.0f, 0.f), 255.f);
             if (px >= kS2Pad && px < kS2TileX + kS2Pad && py >= kS2Pad && py < kS2TileY + kS2Pad) {
                 const double e = (double)b - (double)a;
                 se += e * e;
@@ -57,6 +76,12 @@ __device__ __forceinline__ double ssim2_load(int tid, const Ssim2Args& g, int pl
         t.b[py][px] = b;
     }
     return se;
+}
+// both halves in one call (the CPU suite's phase-by-phase driver)
+__device__ __forceinline__ double ssim2_load(int tid, const Ssim2Args& g, int plane, int x0, int y0, Ssim2Tile& t) {
+    Ssim2Regs v;
+    ssim2_fetch(tid, g, plane, x0, y0, v);
+    return ssim2_stage(tid, g, x0, y0, v, t);
 }
 
 // Four adjacent 7-sums w_k = v[k] + ... + v[k + 6] (k = 0..3) of ten values share their terms: the core v[3..6] is common to all
@@ -102,26 +127,30 @@ __device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t) {
     }
 }
 
-// phase 3: vertical 7-sums + the SSIM map value; one item = (centre column, group of FOUR adjacent centre rows): ten rows of horizontal
-// sums loaded once per quantity; returns this thread's share of the map's sum
+// phase 3: vertical 7-sums + the SSIM map value; one item = (centre column, TWO adjacent centre rows) = one per thread (the first
+// form's items of four rows kept half of the block idle during the pass's heaviest phase: barrier stalls 4.5 warp cycles per issue
+// in the r02 capture); eight rows of horizontal sums per quantity, their six common rows summed once; returns this thread's share
+// of the map's sum
 __device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Tile& t) {
     const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
     const double inv_np = 1.0 / 49.0, cov_norm = 49.0 / 48.0;
     double ssum = 0.0;
-    for (int i = tid; i < (kS2TileY / 4) * kS2TileX; i += kS2Threads) {
-        const int lg = i / kS2TileX, lx = i - lg * kS2TileX, ly0 = lg * 4;
+    for (int i = tid; i < (kS2TileY / 2) * kS2TileX; i += kS2Threads) {
+        const int lg = i / kS2TileX, lx = i - lg * kS2TileX, ly0 = lg * 2;
         const int cx = x0 + lx;
         if (cx < kS2Pad || cx >= g.w - kS2Pad) continue;
-        double s[5][4];
+        double s[5][2];
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            double v[10];
+            double v[8];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) v[k] = t.hs[q][ly0 + k][lx];
-            ssim2_sums4(v, s[q]);
+            for (int k = 0; k < 8; ++k) v[k] = t.hs[q][ly0 + k][lx];
+            const double core = ((v[1] + v[2]) + (v[3] + v[4])) + (v[5] + v[6]);
+            s[q][0] = core + v[0];
+            s[q][1] = core + v[7];
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 2; ++k) {
             const int cy = y0 + ly0 + k;
             if (cy < kS2Pad || cy >= g.h - kS2Pad) continue;
             const double ux = s[0][k] * inv_np, uy = s[1][k] * inv_np;

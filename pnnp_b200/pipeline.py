@@ -126,9 +126,14 @@ class SynthDenoisePipeline:
 
     Only sensor codes go in (2 B per raw pixel) and only metric sums come out, so the PCIe bytes per raw pixel are a quarter of
     HostSynthPipeline's float32 round trip.  The crops are processed in chunks: the H2D copy of chunk i + 1 (copy stream) overlaps the
-    kernels of chunk i.  bench.py times this call as `e2e` of the default workload."""
+    kernels of chunk i, and the first chunk of the NEXT batch is copied behind the last one of this batch (`next_host`).  Measured
+    (r02, 64 crops of 4x512x512, one B200): chunks of 8 / 16 / 32 / 64 crops -> 7 000 / 7 390 / 7 560 / 7 610 raw MP/s end to end — the
+    deep layers of the network fill the GPU better on larger batches, and with the next batch prefetched nothing is left to overlap
+    inside a batch — so the default is one chunk of up to 64 crops.  (Running the metric pass of chunk i on a second stream under the
+    convolutions of chunk i + 1 gained nothing: the persistent conv CTAs leave it no SM.)  bench.py times this call as `e2e` of the
+    default workload."""
 
-    def __init__(self, net, n, H, W, wp, bl, noise_code, device=None, chunk=16, post_clip=(-float("inf"), 1.0), depth=2):
+    def __init__(self, net, n, H, W, wp, bl, noise_code, device=None, chunk=64, post_clip=(-float("inf"), 1.0), depth=2):
         self.net, self.n, self.H, self.W, self.wp, self.bl = net, n, H, W, wp, bl
         self.noise_code, self.post_clip = noise_code, post_clip
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
