@@ -31,8 +31,14 @@ struct Ssim2Args {
 
 struct Ssim2Tile {
     float a[kS2PatchY][kS2PatchX + 1], b[kS2PatchY][kS2PatchX + 1];
-    double hs[5][kS2PatchY][kS2TileX];                         // horizontal 7-sums per patch row and centre column: 28 KB
+    // horizontal 7-sums per patch row and centre column: 28 KB.  Columns are stored permuted (ssim2_col): the four sums a thread of the
+    // horizontal pass produces go out as two 16-byte stores, and with the natural order neighbouring lanes were 32 bytes apart — a
+    // quarter-warp's 128-bit store then spans 256 bytes, two wavefronts instead of one (r02 capture: 35 M store bank conflicts, the
+    // pass bound by shared-memory wavefronts at 62 % of the LSU pipe).  Sums 0-1 of column group g sit at [2g, 2g + 1], sums 2-3 at
+    // [16 + 2g, 16 + 2g + 1]: lanes 16 bytes apart in both stores; the vertical pass walks the columns in the stored order.
+    double hs[5][kS2PatchY][kS2TileX];
 };
+__device__ __forceinline__ int ssim2_col(int lx) { return ((lx >> 1) & 1) * 16 + (lx >> 2) * 2 + (lx & 1); }
 
 // phase 1, split in two so that the kernel can keep the NEXT tile's global loads in flight while it computes the current one (r02
 // capture: the pass spent 4.3 of its 14 warp cycles per issue waiting for these loads and 4.5 at the barriers behind them):
@@ -96,10 +102,10 @@ __device__ __forceinline__ void ssim2_sums4(const double (&v)[10], double (&w)[4
     w[3] = core + (p78 + v[9]);
 }
 
-// four consecutive doubles as two 16-byte stores (lanes are 32 bytes apart: 16-byte stores are conflict-free, 8-byte ones 8-way)
-__device__ __forceinline__ void ssim2_store4(double* p, const double (&w)[4]) {
-    reinterpret_cast<double2*>(p)[0] = make_double2(w[0], w[1]);
-    reinterpret_cast<double2*>(p)[1] = make_double2(w[2], w[3]);
+// the four sums of column group g = lx / 4 of one patch row as two 16-byte stores in the permuted column order
+__device__ __forceinline__ void ssim2_store4(double* row, int g, const double (&w)[4]) {
+    reinterpret_cast<double2*>(row)[g] = make_double2(w[0], w[1]);
+    reinterpret_cast<double2*>(row)[8 + g] = make_double2(w[2], w[3]);
 }
 
 // phase 2: horizontal 7-sums; one item = (patch row, group of FOUR adjacent centre columns): ten pixels loaded, converted and multiplied
@@ -115,15 +121,15 @@ __device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t) {
             aa[k] = a[k] * a[k]; bb[k] = b[k] * b[k]; ab[k] = a[k] * b[k];
         }
         ssim2_sums4(a, w);
-        ssim2_store4(&t.hs[0][py][lx], w);
+        ssim2_store4(t.hs[0][py], lx >> 2, w);
         ssim2_sums4(b, w);
-        ssim2_store4(&t.hs[1][py][lx], w);
+        ssim2_store4(t.hs[1][py], lx >> 2, w);
         ssim2_sums4(aa, w);
-        ssim2_store4(&t.hs[2][py][lx], w);
+        ssim2_store4(t.hs[2][py], lx >> 2, w);
         ssim2_sums4(bb, w);
-        ssim2_store4(&t.hs[3][py][lx], w);
+        ssim2_store4(t.hs[3][py], lx >> 2, w);
         ssim2_sums4(ab, w);
-        ssim2_store4(&t.hs[4][py][lx], w);
+        ssim2_store4(t.hs[4][py], lx >> 2, w);
     }
 }
 
@@ -136,15 +142,17 @@ __device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0
     const double inv_np = 1.0 / 49.0, cov_norm = 49.0 / 48.0;
     double ssum = 0.0;
     for (int i = tid; i < (kS2TileY / 2) * kS2TileX; i += kS2Threads) {
-        const int lg = i / kS2TileX, lx = i - lg * kS2TileX, ly0 = lg * 2;
-        const int cx = x0 + lx;
+        // consecutive lanes take columns that are consecutive IN THE STORED ORDER (a half-warp's 64-bit load is one 128-byte run);
+        // lx = ssim2_col^-1(col) is the centre column those sums belong to
+        const int lg = i / kS2TileX, col = i - lg * kS2TileX, ly0 = lg * 2;
+        const int lx = ((col & 15) >> 1) * 4 + (col >> 4) * 2 + (col & 1), cx = x0 + lx;
         if (cx < kS2Pad || cx >= g.w - kS2Pad) continue;
         double s[5][2];
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
             double v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = t.hs[q][ly0 + k][lx];
+            for (int k = 0; k < 8; ++k) v[k] = t.hs[q][ly0 + k][col];
             const double core = ((v[1] + v[2]) + (v[3] + v[4])) + (v[5] + v[6]);
             s[q][0] = core + v[0];
             s[q][1] = core + v[7];
