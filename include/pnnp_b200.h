@@ -134,6 +134,7 @@ int pnnp_noise_synth_replay(const float* clean, float* noisy, const pnnp_noise_p
 /* 3x3 s1 p1 with the x-shift folded into N: weights [ky][kx*cout + co][cin], MMA N = 3*cout, the three
  * kx partial sums are combined across neighbouring pixels in the epilogue (cout <= 80) */
 #define PNNP_CONV3X 4
+#define PNNP_CONV3B 6 /* nn.Conv2d(k=3, p=1), single narrow source: all nine taps from ONE haloed TMA box (8 x 16 tiles, taps as descriptor offsets); weights [ky*3+kx][cout][cin] like PNNP_CONV3 */
 #define PNNP_CONV2S2 5 /* nn.Conv2d(k=2, s=2, p=0): the data gradient of ConvTranspose2d(2, stride 2); weights [a*2+b][cout][cin] */
 #define PNNP_ACT_NONE 0
 #define PNNP_ACT_LEAKY02 1 /* nn.LeakyReLU(0.2)  Unet.py:52    */

@@ -87,7 +87,7 @@ class CopyDesc(C.Structure):
                 ("sstride", C.c_longlong * 4), ("dstride", C.c_longlong * 4)]
 
 
-CONV3, CONV1, CONVT, CONV3S2, CONV3X, CONV2S2 = 0, 1, 2, 3, 4, 5
+CONV3, CONV1, CONVT, CONV3S2, CONV3X, CONV2S2, CONV3B = 0, 1, 2, 3, 4, 5, 6
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 OUT_NHWC_BF16, OUT_NCHW_F32 = 0, 1
 

@@ -29,6 +29,10 @@ def initialize_weights(net):
 
 import os
 _X_MODE = os.environ.get("PNNP_NO_XMODE") is None
+_ONE_BOX = os.environ.get("PNNP_CONV3B", "1") != "0" and os.environ.get("PNNP_CONV_NOSPEC") is None and os.environ.get("PNNP_CONV_DBG") is None
+_ONEBOX_MAX_COUT = int(os.environ.get("PNNP_CONV3B_MAX_COUT", "64"))
+_ONEBOX_TWO_SRC = os.environ.get("PNNP_CONV3B_TWO_SRC", "0") == "1"
+_ONEBOX_CIN = tuple(int(v) for v in os.environ.get("PNNP_CONV3B_CIN", "32,64").split(","))
 _XMODE_MAX_COUT = int(os.environ.get("PNNP_XMODE_MAX_COUT", "32"))     # single-source layers up to this width take the x-shift-in-N mode
 
 
@@ -190,6 +194,12 @@ class _TCNet(nn.Module):
         # measured on B200 (profiles/): x-mode wins when 3*Cout <= 128 (four TMEM accumulators / epilogue groups
         # stay available) or when K is long (two-source decoder convs); otherwise the per-tap mode does.
         narrow = cout <= _XMODE_MAX_COUT or (cout <= 64 and kw.get("x1") is not None)
+        # one-box mode (csrc/conv_tc.cu MODE_CONV3B, r02): single 32-channel source, cout <= _ONEBOX_MAX_COUT, plain / pool / head / residual epilogue
+        if (_ONE_BOX and x0.dtype == torch.bfloat16 and (kw.get("x1") is None or _ONEBOX_TWO_SRC) and x0.shape[3] in _ONEBOX_CIN and cout % 16 == 0
+                and cout <= _ONEBOX_MAX_COUT and kw.get("mask") is None and not (kw.get("pool_out") is not None and kw.get("head") is not None)
+                and not (kw.get("resid") is not None and kw.get("pool_out") is not None)):
+            w, b = self._packed(name)
+            return _conv(_lib.CONV3B, x0, w, b, out, cout, act, **kw)
         if narrow and cout % 16 == 0 and _X_MODE:
             w, b = self._packed(name, "conv3x")
             return _conv(_lib.CONV3X, x0, w, b, out, cout, act, **kw)

@@ -47,7 +47,15 @@ constexpr int kMaxGroups = 4;            // epilogue groups == TMEM accumulator 
 constexpr int kConvThreadsMax = 64 + 128 * kMaxGroups;   // warp 0 TMA, warp 1 MMA, then 4 epilogue warps per group
 constexpr int kMaxStages = 8;
 
-enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2, MODE_CONV3S2 = 3, MODE_CONV3X = 4, MODE_CONV2S2 = 5 };
+enum { MODE_CONV3 = 0, MODE_CONV1 = 1, MODE_CONVT = 2, MODE_CONV3S2 = 3, MODE_CONV3X = 4, MODE_CONV2S2 = 5, MODE_CONV3B = 6 };
+// MODE_CONV3B ("one box"): all NINE taps of a 3x3 conv from ONE haloed TMA box.  The tile is 8 pixels wide x 16 tall, so a tile row
+// is exactly one 8-row core-matrix group of the K-major operand and the stride between groups (SBO) is the box's row pitch, 10 pixels;
+// tap (dy, dx) is the start-address offset (dy * 10 + dx) pixel rows.  tcgen05.mma applies the shared-memory swizzle to the ABSOLUTE
+// address (tools/ubench_umma_offset.cu, measured on a B200 in r02: any start offset in whole rows and any SBO read exactly the rows
+// of the linear-address model, base-offset field 0), which is also how TMA wrote them.  Against the x-shift-in-N mode: the
+// accumulator has Cout columns instead of 3 Cout (a third of the TMEM drain, which at 64 B per clock was 768 of a tile's ~1 200
+// cycles), no cross-lane combine, no halo lanes; against the per-tap mode: one box and one hand-shake per tile instead of three.
+constexpr int kTileWB = 8, kTileHB = 16, kBoxWB = kTileWB + 2, kBoxHB = kTileHB + 2;
 constexpr int kTileWX = 14;             // output columns per tile in MODE_CONV3X (16 partial-sum columns, 1 halo each side)
 enum { OUT_NHWC_BF16 = 0, OUT_NCHW_F32 = 1 };
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
@@ -141,6 +149,22 @@ struct TileIter {
 template <int TPS, int K16S, bool F32 = false>
 __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc0, uint64_t bdesc0, uint32_t a_tap_stride,
                                                  uint32_t b_tap_stride, uint32_t idesc, bool accumulate_first) {
+    if constexpr (TPS == 9) {
+        // MODE_CONV3B: a_tap_stride = one pixel row of the box in descriptor units; tap (dy, dx) starts (dy * kBoxWB + dx) rows in.
+        // Taps in the per-tap mode's order (dx outer, dy inner, K slices innermost), so the fp32 accumulators — not only the rounded
+        // outputs — are bit-identical to MODE_CONV3's.
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int dx = t / 3, dy = t % 3;
+#pragma unroll
+            for (int k = 0; k < K16S; ++k) {
+                const uint64_t ad = adesc0 + (uint64_t)((dy * kBoxWB + dx) * a_tap_stride + k * 2);
+                const uint64_t bd = bdesc0 + (uint64_t)((dy * 3 + dx) * b_tap_stride + k * 2);
+                tc_mma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || t != 0 || k != 0) ? 1u : 0u);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int dy = 0; dy < TPS; ++dy) {
 #pragma unroll
@@ -184,7 +208,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // EPI), the debug word and the swizzle span (32 bytes per K16 slice) are compile-time constants: the serial loops of the
     // producer and MMA warps — whose instruction count IS the tile rate of the small-K layers — lose their run-time selects.
     constexpr bool kCt = VAR != 0 && EPI >= 0;       // every variant instantiation with a specialised epilogue (the launcher never
-    constexpr int kCtMode = (EPI >= 0 && (EPI & EPI_CONVT)) ? MODE_CONVT : ((EPI >= 0 && (EPI & EPI_X)) ? MODE_CONV3X : MODE_CONV3);   // pairs those with debug switches)
+    constexpr bool kB = TPS == 9;                    // MODE_CONV3B: 8 x 16 tiles, one box, nine taps by descriptor offset
+    constexpr int kTW = kB ? kTileWB : kTileW, kTH = kB ? kTileHB : kTileH;
+    constexpr int kCtMode = kB ? MODE_CONV3B : ((EPI >= 0 && (EPI & EPI_CONVT)) ? MODE_CONVT : ((EPI >= 0 && (EPI & EPI_X)) ? MODE_CONV3X : MODE_CONV3));   // pairs those with debug switches)
 #define PNNP_MODE_K (kCt ? kCtMode : p.mode)        /* expressions, not locals: the default instantiations must compile exactly as before */
 #define PNNP_DBG_K (kCt ? 0 : p.dbg)
 #define PNNP_SWZ_K (kCt ? 32 * K16S : p.swz)
@@ -212,7 +238,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int ksteps = (chunks0 + chunks1) * dx_count;
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles;
     const uint32_t stage_tx = (uint32_t)(p.a_bytes + (p.b_resident ? 0 : taps_per_stage * p.umma_n * PNNP_SWZ_K));
-    const int taps_total = PNNP_MODE_K == MODE_CONV3 ? 9 : (PNNP_MODE_K == MODE_CONV3S2 ? 9 : (PNNP_MODE_K == MODE_CONV3X ? 3 : (PNNP_MODE_K == MODE_CONV2S2 ? 4 : 1)));
+    const int taps_total = (PNNP_MODE_K == MODE_CONV3 || PNNP_MODE_K == MODE_CONV3B) ? 9 : (PNNP_MODE_K == MODE_CONV3S2 ? 9 : (PNNP_MODE_K == MODE_CONV3X ? 3 : (PNNP_MODE_K == MODE_CONV2S2 ? 4 : 1)));
 
     if constexpr (kPdl) {
         // Programmatic dependent launch (default since r02; PNNP_CONV_PDL=0 switches it off): this grid may have been scheduled while the previous kernel of
@@ -253,9 +279,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const bool b_res = p.b_resident != 0;
         int* const err = p.err;
         const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
-        const int halo = mode == MODE_CONV3 ? 1 : 0;
-        const int yhalo = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? 1 : 0;
-        const int tile_w = mode == MODE_CONV3X ? kTileWX : kTileW, x_first = mode == MODE_CONV3X ? -1 : 0;
+        const int halo = (mode == MODE_CONV3 || mode == MODE_CONV3B) ? 1 : 0;
+        const int yhalo = (mode == MODE_CONV3 || mode == MODE_CONV3X || mode == MODE_CONV3B) ? 1 : 0;
+        const int tile_w = mode == MODE_CONV3X ? kTileWX : kTW, x_first = mode == MODE_CONV3X ? -1 : 0;
         const bool plain = mode != MODE_CONV2S2 && mode != MODE_CONV3S2;
         if (b_res && elect_one()) {
             // weights for every (K chunk, tap) once per CTA: layout [chunk][tap][umma_n rows x swz bytes]
@@ -272,7 +298,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint32_t stage = 0, phase = 0, sa = smem0, fb = full0, eb = empty0;
         for (; ti.valid(); ti.next(n_tiles, tiles_x, tiles_y)) {
             const int img = ti.img;
-            const int x0 = ti.tx * tile_w + x_first, y0 = ti.ty * (SUP ? 2 * kTileH : kTileH);
+            const int x0 = ti.tx * tile_w + x_first, y0 = ti.ty * (SUP ? 2 * kTileH : kTH);
             const int n_off = ti.n_tile * umma_n;
             const bool skip_loads = (dbg & 4) && ti.t != first_tile;
             int chunk = 0, dx = 0;
@@ -293,7 +319,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const int cin_off = (src ? cin0 : 0) + cc * kc;
                         for (int dy = 0; dy < taps_per_stage; ++dy) {
                             const int tap = mode == MODE_CONV3 ? dy * 3 + dx
-                                          : ((mode == MODE_CONV3S2 || mode == MODE_CONV2S2) ? dx : (mode == MODE_CONV3X ? dy : 0));
+                                          : ((mode == MODE_CONV3S2 || mode == MODE_CONV2S2) ? dx : ((mode == MODE_CONV3X || mode == MODE_CONV3B) ? dy : 0));
                             tma_load_3d(sa + a_bytes + dy * b_tap_bytes, &tmB, fb, cin_off, n_off, tap);
                         }
                     }
@@ -313,7 +339,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         int* const err = p.err;
         const uint32_t idesc = (1u << 4) | ((kF32 ? 2u : 1u) << 7) | ((kF32 ? 2u : 1u) << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);   // A/B format: 1 = bf16, 2 = tf32
         const uint64_t dhi = umma_desc_hi(PNNP_SWZ_K);
-        const uint32_t a_tap_stride = (uint32_t)(kTileW * PNNP_SWZ_K) >> 4;      // descriptor units (16 B)
+        // MODE_CONV3B: the A operand's 8-row groups are kBoxWB pixel rows apart (SBO), and a tap advances by whole pixel rows
+        const uint64_t dhi_a = kB ? ((dhi & ~(0x3FFFull << 32)) | ((uint64_t)((kBoxWB * PNNP_SWZ_K) >> 4) << 32)) : dhi;
+        const uint32_t a_tap_stride = kB ? (uint32_t)PNNP_SWZ_K >> 4 : (uint32_t)(kTileW * PNNP_SWZ_K) >> 4;      // descriptor units (16 B)
         const uint32_t b_tap_stride = (uint32_t)p.b_tap_stride >> 4;
         const uint32_t b_tap_bytes = (uint32_t)p.b_tap_stride;
         const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
@@ -336,7 +364,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             for (int ks = 0; ks < ksteps; ++ks) {
                 mbar_wait(fb, phase, err, 103);
                 if (!(dbg & 64)) tc_fence_after();
-                const uint64_t adesc0 = dhi | (uint64_t)((sa >> 4) & 0x3FFFu);
+                const uint64_t adesc0 = dhi_a | (uint64_t)((sa >> 4) & 0x3FFFu);
                 const uint32_t sb = b_res ? sb_res : sa + (uint32_t)a_bytes;
                 const uint64_t bdesc0 = dhi | (uint64_t)((sb >> 4) & 0x3FFFu);
                 // (chunk * taps_total + dx) * tap bytes: +1 tap per stage, +taps_total per chunk
@@ -368,7 +396,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int group = (warp - 2) >> 2;
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
         const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
-        const int ty_in = m / kTileW, tx_in = m % kTileW;
+        const int ty_in = m / kTW, tx_in = m % kTW;
         const uint32_t acc = (uint32_t)group;
         uint32_t acc_phase = 0;
         constexpr bool kSpec = EPI >= 0;
@@ -407,12 +435,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         ti.init(total_tiles, e_n_tiles, e_tiles_x, e_tiles_y);
         if (PNNP_DBG_K & 32) ti.t = ti.t_end;
         const int slot = SUP ? group >> 1 : group, n_slots = SUP ? e_groups >> 1 : e_groups;     // SUP: two groups share a super-tile
-        const int y_in = SUP ? (group & 1) * kTileH + ty_in : ty_in, tile_rows = SUP ? 2 * kTileH : kTileH;
+        const int y_in = SUP ? (group & 1) * kTileH + ty_in : ty_in, tile_rows = SUP ? 2 * kTileH : kTH;
         for (int g = 0; g < slot && ti.valid(); ++g) ti.next(e_n_tiles, e_tiles_x, e_tiles_y);   // slot s: every n_slots-th tile
         for (; ti.valid(); ) {
             const int n_tile = ti.n_tile, tx = ti.tx, ty = ti.ty, img = ti.img;
             for (int g = 0; g < n_slots && ti.valid(); ++g) ti.next(e_n_tiles, e_tiles_x, e_tiles_y);
-            const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTileW + tx_in, y = ty * tile_rows + y_in;
+            const int x = xmode ? tx * kTileWX - 1 + tx_in : tx * kTW + tx_in, y = ty * tile_rows + y_in;
             const bool valid = x < eW && y < eH && (!xmode || (tx_in >= 1 && tx_in <= kTileWX));
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, e_err, 104);
             tc_fence_after();
@@ -532,9 +560,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         for (int i = 0; i < 16; ++i) {
                             const float o1 = xmode ? __shfl_down_sync(0xffffffffu, f[i], 1) : __shfl_xor_sync(0xffffffffu, f[i], 1);
                             const float a = fmaxf(f[i], o1);
-                            m[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
+                            m[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, kTW));
                         }
-                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16)) {
+                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & kTW)) {
                             const size_t pp = ((size_t)img * (eH >> 1) + (y >> 1)) * (size_t)(eW >> 1) + (x >> 1);
                             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e_pool_out) + pp * e_cout_stride + c0);
 #pragma unroll
@@ -586,11 +614,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             uint32_t o1 = xmode ? __shfl_down_sync(0xffffffffu, pk[i], 1) : __shfl_xor_sync(0xffffffffu, pk[i], 1);
                             a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o1));
                             uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
-                            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, 16);
+                            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, kTW);
                             a = __hmax2(a, *reinterpret_cast<__nv_bfloat162*>(&o2));
                             pk[i] = *reinterpret_cast<uint32_t*>(&a);
                         }
-                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & 16) && !(PNNP_DBG_K & 1)) {
+                        if (valid && ((lane & 1) == (xmode ? 1 : 0)) && !(lane & kTW) && !(PNNP_DBG_K & 1)) {
                             st_global_256(reinterpret_cast<__nv_bfloat16*>(e_pool_out) + pool_off + c0, pk);
                         }
                     }
@@ -683,13 +711,13 @@ static CUtensorMapSwizzle swz_enum(int swz) {
 }
 // activation map: NHWC bf16 viewed as (C, W, H, N); box (kc, 16, box_h, 1)
 static int make_act_map(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c, int kc, int box_h, int swz,
-                        int stride = 1, int esz = 2) {
+                        int stride = 1, int esz = 2, int box_w = kTileW) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)c * esz, (cuuint64_t)w * c * esz, (cuuint64_t)h * w * c * esz};
     // with a traversal stride s the TMA unit loads boxDim/s elements per dimension
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(kTileW * stride), (cuuint32_t)(box_h * stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = enc(tm, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -757,12 +785,15 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         return fail("conv: fused 1x1 head needs a single N tile, cout <= 64 and 1..4 head channels");
     if (out_mode == OUT_NHWC_BF16 && (cout % 16)) return fail("conv: NHWC output needs cout % 16 == 0");
     if (mode == MODE_CONVT ? (w_rows != cout) : (w_rows < n_tiles * umma_n)) return fail("conv: weight tensor has the wrong number of rows");
-    const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2) ? 9 : ((mode == MODE_CONVT || mode == MODE_CONV2S2) ? 4 : (mode == MODE_CONV3X ? 3 : 1));
+    const bool mode_b = mode == MODE_CONV3B;
+    if (mode_b && (f32 || cout > 64 || cout % 16 || out_mode != OUT_NHWC_BF16))
+        return fail("conv3b: bf16 sources, NHWC bf16 output, cout a multiple of 16 up to 64");
+    const int taps = (mode == MODE_CONV3 || mode == MODE_CONV3S2 || mode_b) ? 9 : ((mode == MODE_CONVT || mode == MODE_CONV2S2) ? 4 : (mode == MODE_CONV3X ? 3 : 1));
     const bool s2 = mode == MODE_CONV3S2 || mode == MODE_CONV2S2;
     if (s2 && (nsrc > 1 || (h & 1) || (w & 1))) return fail("stride-2 conv: single source, even h and w");
     const int in_h = h, in_w = w;
     if (s2) { h /= 2; w /= 2; }        // tile over the OUTPUT grid
-    const int tps = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? 3 : 1;
+    const int tps = mode_b ? 9 : ((mode == MODE_CONV3 || mode == MODE_CONV3X) ? 3 : 1);
     // Super-tile variant (two M = 128 tiles per pipeline stage, see the kernel's SUP parameter).  Measured in r02 (tools/r02_sweep.sh): on by default for the MODE_CONV3 layers only; originally written as opt-in until measured
     // on a B200: PNNP_CONV_SUPER=1 -> one CTA per SM, four accumulators (two super-tiles in flight); =2 -> keeps two CTAs per SM
     // for the small-K resident-weight layers (one super-tile in flight per CTA).  Only the compile-time specialised NHWC 3x3
@@ -776,13 +807,17 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     static const bool no_spec = getenv("PNNP_CONV_NOSPEC") != nullptr;
     const int dbg_env = getenv("PNNP_CONV_DBG") ? atoi(getenv("PNNP_CONV_DBG")) : 0;
     int epi = EPI_GENERIC;
-    if (!f32 && !no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X) && out_mode == OUT_NHWC_BF16 && !dbg_env &&
+    if (!f32 && !no_spec && (mode == MODE_CONV3 || mode == MODE_CONV3X || mode_b) && out_mode == OUT_NHWC_BF16 && !dbg_env &&
         !(d.pool_out && d.head_out) && !(d.mask && (d.pool_out || d.head_out))) {
         epi = (mode == MODE_CONV3X ? EPI_X : 0) | (d.pool_out ? EPI_POOL : 0) | (d.head_out ? EPI_HEAD : 0) | (d.mask ? EPI_MASK : 0);
         // residual: built alone (32), with the x-shift-in-N mode (33) and with x-mode + fused head (37: the last residual block of the
         // ResUnet + conv10); every other combination runs the generic epilogue
-        if (d.resid) epi = (d.pool_out || d.mask || (d.head_out && mode != MODE_CONV3X)) ? EPI_GENERIC : (epi | EPI_RESID);
+        if (d.resid) epi = (d.pool_out || d.mask || (d.head_out && mode != MODE_CONV3X && !mode_b)) ? EPI_GENERIC : (epi | EPI_RESID);
     }
+    // MODE_CONV3B exists with the specialised epilogues 0 / pool / head / residual / head + residual only (the callers fall back to the
+    // x-shift-in-N mode for everything else)
+    if (mode_b && !(epi == 0 || epi == EPI_POOL || epi == EPI_HEAD || epi == EPI_RESID || epi == (EPI_HEAD | EPI_RESID)))
+        return fail("conv3b: no kernel for this epilogue (generic / masked epilogues take MODE_CONV3 or MODE_CONV3X)");
     if (!f32 && convt_fast && mode == MODE_CONVT && out_mode == OUT_NHWC_BF16 && !d.resid && !d.mask && !d.pool_out && !d.head_out &&
         act == ACT_NONE && !no_spec && !dbg_env)
         epi = EPI_CONVT;
@@ -803,10 +838,11 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         }
     };
     // (not with the residual epilogue: 64->64 + residual @712x1064 82 us on single tiles, 97 us on super-tiles; 128 channels equal)
-    const bool sup_wanted = !f32 && super_env > 0 && mode != MODE_CONVT && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH && !d.resid;
+    const bool sup_wanted = !f32 && super_env > 0 && mode != MODE_CONVT && !mode_b && epi != EPI_GENERIC && umma_n <= 128 && h > kTileH && !d.resid;
     const bool sup = sup_wanted && plan_kc(2 * kTileH + 2) == plan_kc(kTileH + 2);
-    const int tile_rows = sup ? 2 * kTileH : kTileH;
-    const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X) ? tile_rows + 2 : kTileH;
+    const int tile_rows = mode_b ? kTileHB : (sup ? 2 * kTileH : kTileH);
+    const int box_h = (mode == MODE_CONV3 || mode == MODE_CONV3X || mode_b) ? tile_rows + 2 : kTileH;
+    const int box_w = mode_b ? kBoxWB : kTileW;
     // shrink the K chunk until at least 3 pipeline stages fit
     int swz, a_bytes, b_tap_stride, stage_bytes, stages, b_resident = 0, b_res_bytes = 0;
     const int smem_budget = 227 * 1024 - 4096 - cout * 20;
@@ -815,7 +851,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         // weights resident in smem when all taps x chunks fit beside >= 3 A-only stages (single N tile, not convT)
         const int swz_r = kc * esz, bts = (umma_n * swz_r + 1023) / 1024 * 1024;
         const int res_bytes = (cin_total / kc) * (mode == MODE_CONVT ? 1 : taps) * bts;   // convT: the four taps are N columns of one block
-        const int a_only = (box_h * kTileW * swz_r + 1023) / 1024 * 1024;
+        const int a_only = (box_h * box_w * swz_r + 1023) / 1024 * 1024;
         // ConvTranspose2d layers with a single N tile (4 * cout <= 256) can keep their weights resident too: the ConvTranspose fast path
         // (PNNP_CONVT_FAST; default for > 64 input channels since r02 — the K = 64 layer measured slower with it)
         if ((mode != MODE_CONVT || convt_fast) && n_tiles == 1 && res_bytes + 3 * a_only <= smem_budget && !getenv("PNNP_NO_RESIDENT_W")) {
@@ -824,7 +860,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     }
     for (;; kc >>= 1) {
         swz = kc * esz;
-        a_bytes = box_h * kTileW * swz;
+        a_bytes = box_h * box_w * swz;
         b_tap_stride = (umma_n * swz + 1023) / 1024 * 1024;
         stage_bytes = ((b_resident ? a_bytes : a_bytes + tps * b_tap_stride) + 1023) / 1024 * 1024;
         stages = std::min(kMaxStages, (smem_budget - b_res_bytes) / stage_bytes);
@@ -833,7 +869,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (stages < 2) return fail("conv: tile does not fit in shared memory");
     ConvParams p{};
     p.mode = mode; p.n_img = n; p.H = h; p.W = w;
-    p.tiles_x = mode == MODE_CONV3X ? (w + kTileWX - 1) / kTileWX : (w + kTileW - 1) / kTileW;
+    p.tiles_x = mode == MODE_CONV3X ? (w + kTileWX - 1) / kTileWX : (mode_b ? (w + kTileWB - 1) / kTileWB : (w + kTileW - 1) / kTileW);
     p.tiles_y = (h + tile_rows - 1) / tile_rows; p.n_tiles = n_tiles;
     p.umma_n = umma_n; p.nsrc = nsrc; p.cin0 = cin0; p.cin1 = nsrc > 1 ? cin1 : 0; p.kc = kc; p.swz = swz;
     p.cout = cout; p.cout_stride = cout_stride; p.act = act; p.out_mode = out_mode;
@@ -863,8 +899,8 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     if (!g_err_dev) { PNNP_CUDA(cudaMalloc(&g_err_dev, sizeof(int))); PNNP_CUDA(cudaMemset(g_err_dev, 0, sizeof(int))); }
     p.err = g_err_dev;
     CUtensorMap tmA0, tmA1, tmB;
-    if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, s2 ? 2 : 1, esz)) return e;
-    if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz, 1, esz)) return e; }
+    if (int e = make_act_map(&tmA0, in0, n, in_h, in_w, cin0, kc, box_h, swz, s2 ? 2 : 1, esz, box_w)) return e;
+    if (nsrc > 1) { if (int e = make_act_map(&tmA1, in1, n, h, w, cin1, kc, box_h, swz, 1, esz, box_w)) return e; }
     else tmA1 = tmA0;
     if (mode == MODE_CONVT) { if (int e = make_w_map(&tmB, weight, 1, 4 * cout, cin0, kc, umma_n, swz, esz)) return e; }
     else if (int e = make_w_map(&tmB, weight, taps, w_rows, cin0 + (nsrc > 1 ? cin1 : 0), kc, umma_n, swz, esz)) return e;
@@ -941,6 +977,35 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
         PNNP_CUDA(cudaGetLastError());
         return 0;
 #endif
+    }
+    if (mode_b) {
+        // MODE_CONV3B instantiations: (9 taps per stage, K16 slices 1 / 2 / 4, epilogue 0 / pool / head / residual / head + residual), plain,
+        // with PDL, with packed-pair arithmetic, with both (the default)
+#define PNNP_FOR_EACH_B_VARIANT(X) X(9, 1, 0) X(9, 1, 2) X(9, 1, 4) X(9, 1, 32) X(9, 1, 36) X(9, 2, 0) X(9, 2, 2) X(9, 2, 4) X(9, 2, 32) X(9, 2, 36) \
+                                   X(9, 4, 0) X(9, 4, 2) X(9, 4, 4) X(9, 4, 32) X(9, 4, 36)
+        static bool attr_b_done = false;
+        if (!attr_b_done) {
+#define X(T, K, E) PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                   PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                   PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                   PNNP_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<T, K, E, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            PNNP_FOR_EACH_B_VARIANT(X)
+#undef X
+            attr_b_done = true;
+        }
+        const bool x2b = variant_on("PNNP_CONV_F32X2");
+#define X(T, K, E) if (!launched && k16s == K && epi == E) { \
+        if (x2b && pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 6>, tmA0, tmA1, tmB, p)); \
+        else if (x2b) PNNP_CONV_KLAUNCH(T, K, E, 4); \
+        else if (pdl) PNNP_CUDA(cudaLaunchKernelEx(&pdl_cfg, conv_gemm_tc_kernel<T, K, E, 2>, tmA0, tmA1, tmB, p)); \
+        else PNNP_CONV_KLAUNCH(T, K, E, 0); \
+        launched = true; }
+        PNNP_FOR_EACH_B_VARIANT(X)
+#undef X
+        if (!launched) return fail("conv3b: no kernel variant for this (K chunk, epilogue)");
+        count_launch();
+        PNNP_CUDA(cudaGetLastError());
+        return 0;
     }
     if (sup && (groups & 1)) return fail("conv: the super-tile variant needs an even number of accumulator buffers (internal)");
     if (x2) {

@@ -745,7 +745,7 @@ def test_results_do_not_depend_on_which_asynchronous_agent_lags(emu, libs, monke
 
 # ------------------------------------------------------------------------------------------ the model has teeth
 _WAITS = {"mma_full": "                mbar_wait(fb, phase, err, 103);",                                   # MMA issuer: stage loaded?
-          "epilogue_tfull": "            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 104);",     # epilogue: accumulator complete?
+          "epilogue_tfull": "            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, e_err, 104);",     # epilogue: accumulator complete?
           "producer_empty": "                mbar_wait(eb, phase ^ 1, err, 101);"}                          # producer: stage free again?
 
 

@@ -416,3 +416,54 @@ def test_forward_tf32_variant_meets_the_fp32_bound_under_any_init(arch_name):
         _no_pipeline_error()
         print(f"{arch_name} init={init}: out absmax {want.abs().max().item():.3e}; max-abs error bf16 {e_bf16:.3e}, tf32 {e_tf32:.3e}")
         assert e_tf32 <= 1e-3 and e_tf32 < e_bf16, (init, e_tf32, e_bf16)
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n", [(32, 32, 16, 8, 1), (32, 32, 24, 44, 2), (32, 32, 19, 29, 1), (32, 64, 40, 72, 1), (16, 32, 34, 18, 1),
+                                            (64, 32, 20, 36, 1)])
+def test_conv3x3_one_box_mode(cin, cout, h, w, n):
+    """MODE_CONV3B: all nine taps from ONE haloed TMA box (8 x 16 tiles; tap = descriptor start offset of (dy * 10 + dx) pixel rows, SBO =
+    the box's row pitch — tools/ubench_umma_offset.cu shows tcgen05.mma reading exactly those rows).  Bit-equal to the per-tap mode (same
+    products accumulated in the same tap / channel order), for ragged sizes, 32 / 64 / 128-byte rows, and with the pool, head, residual
+    and head + residual epilogues."""
+    g = torch.Generator(device="cuda").manual_seed(cin * 1000 + cout + h)
+    x = torch.randn((n, cin, h, w), device="cuda", generator=g)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) / (3 * cin ** 0.5)
+    b = torch.randn((cout,), device="cuda", generator=g) * 0.1
+    xs, wp = _nhwc(x), _pack(wt)
+    outs = {}
+    for mode in (_lib.CONV3, _lib.CONV3B):
+        o = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device="cuda")
+        archs._conv(mode, xs, wp, b, o, cout, _lib.ACT_LEAKY)
+        _no_pipeline_error()
+        outs[mode] = o
+    ref = F.leaky_relu(F.conv2d(_bf(x), _bf(wt), b, padding=1), 0.2)
+    assert (_nchw(outs[_lib.CONV3B]) - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.equal(outs[_lib.CONV3], outs[_lib.CONV3B])
+    # residual epilogue
+    r = torch.randn((n, h, w, cout), device="cuda", generator=g).to(torch.bfloat16)
+    o3, ob = torch.empty_like(r), torch.empty_like(r)
+    archs._conv(_lib.CONV3, xs, wp, b, o3, cout, _lib.ACT_NONE, resid=r)
+    archs._conv(_lib.CONV3B, xs, wp, b, ob, cout, _lib.ACT_NONE, resid=r)
+    _no_pipeline_error()
+    assert torch.equal(o3, ob)
+    if h % 2 == 0 and w % 2 == 0:                                   # fused 2x2 max-pool
+        pooled = torch.empty((n, h // 2, w // 2, cout), dtype=torch.bfloat16, device="cuda")
+        o = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device="cuda")
+        archs._conv(_lib.CONV3B, xs, wp, b, o, cout, _lib.ACT_LEAKY, pool_out=pooled)
+        _no_pipeline_error()
+        assert torch.equal(o, outs[_lib.CONV3]) and torch.equal(_nchw(pooled), F.max_pool2d(_nchw(o), 2))
+    # fused 1x1 head, with and without the residual
+    hw = torch.randn((4, cout), device="cuda", generator=g) / 6
+    hb = torch.randn((4,), device="cuda", generator=g) * 0.1
+    res = torch.randn((n, 4, h, w), device="cuda", generator=g)
+    for resid in (None, r):
+        h3 = torch.empty((n, 4, h, w), dtype=torch.float32, device="cuda")
+        hbm = torch.empty_like(h3)
+        kw = dict(head=(hw, hb, h3), resid_nchw=res)
+        if resid is not None:
+            kw["resid"] = resid
+        archs._conv(_lib.CONV3, xs, wp, b, None, cout, _lib.ACT_LEAKY, **kw)
+        kw["head"] = (hw, hb, hbm)
+        archs._conv(_lib.CONV3B, xs, wp, b, None, cout, _lib.ACT_LEAKY, **kw)
+        _no_pipeline_error()
+        assert torch.equal(h3, hbm)

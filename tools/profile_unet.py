@@ -23,10 +23,10 @@ def conv_label(a, k):
     mode, x0, wt = a[0], a[1], a[2]
     n, h, w, c0 = x0.shape
     c1 = 0 if k.get("x1") is None else k["x1"].shape[3]
-    cout = a[5]; taps = {0: 9, 1: 1, 2: 4, 3: 9, 4: 9}[mode]
+    cout = a[5]; taps = {0: 9, 1: 1, 2: 4, 3: 9, 4: 9, 6: 9}[mode]
     flops = 2.0 * n * h * w * (c0 + c1) * cout * taps / (4 if mode == 3 else 1)
     extra = ("+resid" if k.get("resid") is not None else "") + ("+pool" if k.get("pool_out") is not None else "") + ("+head" if k.get("head") is not None else "")
-    return ({0: "conv", 1: "1x1", 2: "convT", 3: "convS2", 4: "convX"}[mode], f"{c0+c1}->{cout} @{h}x{w}{extra}", flops)
+    return ({0: "conv", 1: "1x1", 2: "convT", 3: "convS2", 4: "convX", 6: "convB"}[mode], f"{c0+c1}->{cout} @{h}x{w}{extra}", flops)
 with torch.no_grad():
     for _ in range(3): net(x)
     torch.cuda.synchronize()
