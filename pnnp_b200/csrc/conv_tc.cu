@@ -158,8 +158,13 @@ __device__ __forceinline__ void issue_stage_mmas(uint32_t d_tmem, uint64_t adesc
             const int dx = t / 3, dy = t % 3;
 #pragma unroll
             for (int k = 0; k < K16S; ++k) {
-                const uint64_t ad = adesc0 + (uint64_t)((dy * kBoxWB + dx) * a_tap_stride + k * 2);
-                const uint64_t bd = bdesc0 + (uint64_t)((dy * 3 + dx) * b_tap_stride + k * 2);
+                // both offsets are compile-time constants (a pixel row of the box is 32 K16S bytes; the launcher lays the weights of
+                // a tap out 64 rows apart whatever Cout is), so a descriptor is ONE 64-bit add with an immediate: the MMA warp's
+                // instruction stream is what bounds this mode (r02 capture: 186 instructions per tile, a third of them zero-extending
+                // and adding run-time tap strides)
+                constexpr uint32_t kARow = (32u * K16S) >> 4, kBTap = (64u * 32u * K16S) >> 4;
+                const uint64_t ad = adesc0 + (uint64_t)((dy * kBoxWB + dx) * kARow + k * 2);
+                const uint64_t bd = bdesc0 + (uint64_t)((dy * 3 + dx) * kBTap + k * 2);
                 tc_mma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || t != 0 || k != 0) ? 1u : 0u);
             }
         }
@@ -849,7 +854,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     const int cin_total = cin0 + (nsrc > 1 ? cin1 : 0);
     {
         // weights resident in smem when all taps x chunks fit beside >= 3 A-only stages (single N tile, not convT)
-        const int swz_r = kc * esz, bts = (umma_n * swz_r + 1023) / 1024 * 1024;
+        const int swz_r = kc * esz, bts = mode_b ? 64 * swz_r : (umma_n * swz_r + 1023) / 1024 * 1024;   // MODE_CONV3B: fixed tap stride, see issue_stage_mmas
         const int res_bytes = (cin_total / kc) * (mode == MODE_CONVT ? 1 : taps) * bts;   // convT: the four taps are N columns of one block
         const int a_only = (box_h * box_w * swz_r + 1023) / 1024 * 1024;
         // ConvTranspose2d layers with a single N tile (4 * cout <= 256) can keep their weights resident too: the ConvTranspose fast path
@@ -861,7 +866,7 @@ int conv_layer_launch(const pnnp_conv_desc& d, cudaStream_t st) {
     for (;; kc >>= 1) {
         swz = kc * esz;
         a_bytes = box_h * box_w * swz;
-        b_tap_stride = (umma_n * swz + 1023) / 1024 * 1024;
+        b_tap_stride = mode_b ? 64 * swz : (umma_n * swz + 1023) / 1024 * 1024;
         stage_bytes = ((b_resident ? a_bytes : a_bytes + tps * b_tap_stride) + 1023) / 1024 * 1024;
         stages = std::min(kMaxStages, (smem_budget - b_res_bytes) / stage_bytes);
         if (stages >= 3 || swz == 32 || b_resident) break;
