@@ -121,16 +121,23 @@ __global__ void __launch_bounds__(kS2Threads, 4) ssim_mse_v2_kernel(Ssim2Args g,
     const int x0 = blockIdx.x * kS2TileX;
     double se = 0.0, ssum = 0.0;
     Ssim2Regs nxt;                                      // the next tile's pixels: loaded while the current tile is summed
-    ssim2_fetch(threadIdx.x, g, plane_id, x0, blockIdx.y * kS2TilesPerCta * kS2TileY, nxt);
+    const int y_first = blockIdx.y * kS2TilesPerCta * kS2TileY;
+    ssim2_fetch(threadIdx.x, g, plane_id, x0, y_first, nxt);
     for (int k = 0; k < kS2TilesPerCta; ++k) {
-        const int y0 = (blockIdx.y * kS2TilesPerCta + k) * kS2TileY;
+        const int y0 = y_first + k * kS2TileY;
         if (y0 >= g.h) break;
-        se += ssim2_stage(threadIdx.x, g, x0, y0, nxt, t);
-        if (k + 1 < kS2TilesPerCta && y0 + kS2TileY < g.h) ssim2_fetch(threadIdx.x, g, plane_id, x0, y0 + kS2TileY, nxt);
+        // from the second tile on only the 16 new patch rows are loaded, converted and summed horizontally: rows 0-5 are the previous
+        // tile's rows 16-21, still in the ring of horizontal sums
+        const int py0 = k == 0 ? 0 : 2 * kS2Pad, ring0 = (k * kS2TileY) & (kS2Ring - 1);
+        const bool more = k + 1 < kS2TilesPerCta && y0 + kS2TileY < g.h;
+        // squared error: every image row of the block's range exactly once, by the tile that stages it (staged rows: y0 - 3 + [py0, 22))
+        const int se_lo = max(y_first, y0 - kS2Pad + py0), se_hi = more ? y0 + kS2TileY + kS2Pad : y0 + kS2TileY;
+        se += ssim2_stage(threadIdx.x, g, x0, y0, nxt, t, py0, se_lo, se_hi);
+        if (more) ssim2_fetch(threadIdx.x, g, plane_id, x0, y0 + kS2TileY, nxt, 2 * kS2Pad);
         __syncthreads();
-        ssim2_hsum(threadIdx.x, t);
+        ssim2_hsum(threadIdx.x, t, py0, ring0);
         __syncthreads();
-        ssum += ssim2_vsum(threadIdx.x, g, x0, y0, t);
+        ssum += ssim2_vsum(threadIdx.x, g, x0, y0, t, ring0);
         __syncthreads();                            // the tile buffers are reused by the next tile
     }
     se = block_reduce_sum(se, s_red);

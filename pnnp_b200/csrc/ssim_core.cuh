@@ -21,6 +21,11 @@ constexpr int kS2Win = 7, kS2Pad = 3;
 constexpr int kS2TileX = 32, kS2TileY = 16;                     // window centres per block
 constexpr int kS2PatchX = kS2TileX + 2 * kS2Pad, kS2PatchY = kS2TileY + 2 * kS2Pad;   // 38 x 22 pixels
 constexpr int kS2Threads = 256;
+// A block walks kS2TilesPerCta vertically adjacent tiles.  The bottom six patch rows of a tile are the top six of the next one, so
+// from the second tile on only the 16 NEW rows are loaded and summed horizontally (22 before: 27 % of the load, conversion,
+// multiplication and horizontal-sum work); the horizontal sums live in a ring of kS2Ring rows indexed by the row's distance from
+// the block's first patch row (a power of two: the slot is an AND).
+constexpr int kS2Ring = 32;
 
 struct Ssim2Args {
     const float* dn; const float* hr;
@@ -36,7 +41,7 @@ struct Ssim2Tile {
     // quarter-warp's 128-bit store then spans 256 bytes, two wavefronts instead of one (r02 capture: 35 M store bank conflicts, the
     // pass bound by shared-memory wavefronts at 62 % of the LSU pipe).  Sums 0-1 of column group g sit at [2g, 2g + 1], sums 2-3 at
     // [16 + 2g, 16 + 2g + 1]: lanes 16 bytes apart in both stores; the vertical pass walks the columns in the stored order.
-    double hs[5][kS2PatchY][kS2TileX];
+    double hs[5][kS2Ring][kS2TileX];
 };
 __device__ __forceinline__ int ssim2_col(int lx) { return ((lx >> 1) & 1) * 16 + (lx >> 2) * 2 + (lx & 1); }
 
@@ -46,12 +51,13 @@ __device__ __forceinline__ int ssim2_col(int lx) { return ((lx >> 1) & 1) * 16 +
 //   ssim2_stage  tensor2im of those registers into the shared tile; returns this thread's share of the squared error.
 constexpr int kS2Slots = (kS2PatchY * kS2PatchX + kS2Threads - 1) / kS2Threads;        // 4
 struct Ssim2Regs { float d[kS2Slots], r[kS2Slots]; };
-__device__ __forceinline__ void ssim2_fetch(int tid, const Ssim2Args& g, int plane, int x0, int y0, Ssim2Regs& v) {
+// py0: first patch row to load (0 for a block's first tile, 6 for the following ones: rows 0-5 were the previous tile's rows 16-21)
+__device__ __forceinline__ void ssim2_fetch(int tid, const Ssim2Args& g, int plane, int x0, int y0, Ssim2Regs& v, int py0 = 0) {
     const float* d = g.dn + (size_t)plane * g.h * g.w;
     const float* r = g.hr + (size_t)plane * g.h * g.w;
 #pragma unroll
     for (int k = 0; k < kS2Slots; ++k) {
-        const int i = tid + k * kS2Threads;
+        const int i = tid + k * kS2Threads + py0 * kS2PatchX;
         const int py = i / kS2PatchX, px = i - py * kS2PatchX;
         const int gx = x0 + px - kS2Pad, gy = y0 + py - kS2Pad;
         const bool in = i < kS2PatchY * kS2PatchX && gx >= 0 && gx < g.w && gy >= 0 && gy < g.h;
@@ -59,11 +65,15 @@ __device__ __forceinline__ void ssim2_fetch(int tid, const Ssim2Args& g, int pla
         v.r[k] = in ? r[(size_t)gy * g.w + gx] : 0.f;
     }
 }
-__device__ __forceinline__ double ssim2_stage(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Regs& v, Ssim2Tile& t) {
+// se_lo / se_hi: image rows [se_lo, se_hi) whose squared error this call accounts for (a block's first tile: its own 16 centre rows
+// and, like every tile, the three rows below them when another tile of the block follows — those rows are not staged again)
+__device__ __forceinline__ double ssim2_stage(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Regs& v, Ssim2Tile& t, int py0 = 0,
+                                              int se_lo = -1, int se_hi = -1) {
+    if (se_lo < 0) { se_lo = y0; se_hi = y0 + kS2TileY; }
     double se = 0.0;
 #pragma unroll
     for (int k = 0; k < kS2Slots; ++k) {
-        const int i = tid + k * kS2Threads;
+        const int i = tid + k * kS2Threads + py0 * kS2PatchX;
         if (i >= kS2PatchY * kS2PatchX) break;
         const int py = i / kS2PatchX, px = i - py * kS2PatchX;
         const int gx = x0 + px - kS2Pad, gy = y0 + py - kS2Pad;
@@ -73,7 +83,7 @@ __device__ __forceinline__ double ssim2_stage(int tid, const Ssim2Args& g, int x
             if (g.use_gain) p = g.gain * p;
             a = fminf(fmaxf(p * 255.0f, 0.f), 255.f);
             b = fminf(fmaxf(v.r[k] * 255.0f, 0.f), 255.f);
-            if (px >= kS2Pad && px < kS2TileX + kS2Pad && py >= kS2Pad && py < kS2TileY + kS2Pad) {
+            if (px >= kS2Pad && px < kS2TileX + kS2Pad && gy >= se_lo && gy < se_hi) {
                 const double e = (double)b - (double)a;
                 se += e * e;
             }
@@ -110,10 +120,11 @@ __device__ __forceinline__ void ssim2_store4(double* row, int g, const double (&
 
 // phase 2: horizontal 7-sums; one item = (patch row, group of FOUR adjacent centre columns): ten pixels loaded, converted and multiplied
 // once (the first form loaded, converted and multiplied every pixel seven times: 70 float64 operations per output, 29 now)
-__device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t) {
+// py0: first patch row to sum (see ssim2_fetch); ring0: ring slot of patch row 0 of this tile
+__device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t, int py0 = 0, int ring0 = 0) {
     constexpr int kGroups = kS2TileX / 4;
-    for (int i = tid; i < kS2PatchY * kGroups; i += kS2Threads) {
-        const int py = i / kGroups, lx = (i - py * kGroups) * 4;
+    for (int i = tid + py0 * kGroups; i < kS2PatchY * kGroups; i += kS2Threads) {
+        const int py = i / kGroups, lx = (i - py * kGroups) * 4, slot = (ring0 + py) & (kS2Ring - 1);
         double a[10], b[10], aa[10], bb[10], ab[10], w[4];
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
@@ -121,15 +132,15 @@ __device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t) {
             aa[k] = a[k] * a[k]; bb[k] = b[k] * b[k]; ab[k] = a[k] * b[k];
         }
         ssim2_sums4(a, w);
-        ssim2_store4(t.hs[0][py], lx >> 2, w);
+        ssim2_store4(t.hs[0][slot], lx >> 2, w);
         ssim2_sums4(b, w);
-        ssim2_store4(t.hs[1][py], lx >> 2, w);
+        ssim2_store4(t.hs[1][slot], lx >> 2, w);
         ssim2_sums4(aa, w);
-        ssim2_store4(t.hs[2][py], lx >> 2, w);
+        ssim2_store4(t.hs[2][slot], lx >> 2, w);
         ssim2_sums4(bb, w);
-        ssim2_store4(t.hs[3][py], lx >> 2, w);
+        ssim2_store4(t.hs[3][slot], lx >> 2, w);
         ssim2_sums4(ab, w);
-        ssim2_store4(t.hs[4][py], lx >> 2, w);
+        ssim2_store4(t.hs[4][slot], lx >> 2, w);
     }
 }
 
@@ -137,7 +148,7 @@ __device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t) {
 // form's items of four rows kept half of the block idle during the pass's heaviest phase: barrier stalls 4.5 warp cycles per issue
 // in the r02 capture); eight rows of horizontal sums per quantity, their six common rows summed once; returns this thread's share
 // of the map's sum
-__device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Tile& t) {
+__device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Tile& t, int ring0 = 0) {
     const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
     const double inv_np = 1.0 / 49.0, cov_norm = 49.0 / 48.0;
     double ssum = 0.0;
@@ -152,7 +163,7 @@ __device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0
         for (int q = 0; q < 5; ++q) {
             double v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = t.hs[q][ly0 + k][col];
+            for (int k = 0; k < 8; ++k) v[k] = t.hs[q][(ring0 + ly0 + k) & (kS2Ring - 1)][col];
             const double core = ((v[1] + v[2]) + (v[3] + v[4])) + (v[5] + v[6]);
             s[q][0] = core + v[0];
             s[q][1] = core + v[7];
