@@ -28,13 +28,14 @@ static int pack_impl(const T* raw, float* out, int n, int H, int W, double wp, c
                      int clip, void* stream) {
     if (!raw || !out || !black4) return fail("pack_norm: null pointer");
     if (n <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return fail("pack_norm: H and W must be positive and even");
-    PackArgs a{raw, out, n, H, W, wp, {black4[0], black4[1], black4[2], black4[3]}, norm, clip};
+    const PackArgs a = make_pack_args(raw, out, n, H, W, wp, black4, norm, clip);
     const int w = W / 2;
     const size_t row_bytes = (size_t)W * sizeof(T);
     const bool vec = (w % 4 == 0) && (reinterpret_cast<uintptr_t>(raw) % 16 == 0) && (row_bytes % 16 == 0) &&
                      (reinterpret_cast<uintptr_t>(out) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec) pack_norm_kernel<T, true><<<grid_for((size_t)n * (H / 2) * (w / 4)), 256, 0, st>>>(a);
+    if (vec && a.use_rcp) pack_norm_kernel<T, true, true><<<grid_for((size_t)n * (H / 2) * (w / 4)), 256, 0, st>>>(a);
+    else if (vec) pack_norm_kernel<T, true><<<grid_for((size_t)n * (H / 2) * (w / 4)), 256, 0, st>>>(a);
     else pack_norm_kernel<T, false><<<grid_for((size_t)n * H * W), 256, 0, st>>>(a);
     count_launch();
     PNNP_CUDA(cudaGetLastError());

@@ -13,11 +13,38 @@ namespace pnnp {
 
 struct PackArgs {
     const void* raw; float* out; int n, H, W; double wp; double black[4]; int norm, clip;
+    double span[4], rcp[4]; int use_rcp;         // wp - black per plane, its correctly rounded reciprocal (norm_one_d), both from the host
 };
+
+// host side: the per-plane divisor and its reciprocal; use_rcp only when the reciprocal form is proven equal to the division
+inline PackArgs make_pack_args(const void* raw, float* out, int n, int H, int W, double wp, const double* black4, int norm, int clip) {
+    PackArgs a{raw, out, n, H, W, wp, {black4[0], black4[1], black4[2], black4[3]}, norm, clip, {0, 0, 0, 0}, {0, 0, 0, 0}, 1};
+    for (int c = 0; c < 4; ++c) {
+        a.span[c] = wp - black4[c];
+        a.rcp[c] = 1.0 / a.span[c];
+        uint64_t bits;
+        static_assert(sizeof(bits) == sizeof(double), "double is 64 bits");
+        __builtin_memcpy(&bits, &a.span[c], 8);
+        const uint64_t mant = bits & 0xFFFFFFFFFFFFFull, expo = (bits >> 52) & 0x7FF;
+        // normal, finite divisor and reciprocal, significand not all ones, magnitudes far from the over- / underflow thresholds
+        if (expo < 1023 - 400 || expo > 1023 + 400 || mant == 0xFFFFFFFFFFFFFull) a.use_rcp = 0;
+    }
+    return a;
+}
 
 
 template <typename T> struct Load8;
 template <> struct Load8<uint16_t> {
+    // the eight codes as doubles without a conversion instruction: 2^52 + n is the bit pattern (0x43300000, n); minus 2^52 is exact
+    static __device__ __forceinline__ void ldd(const uint16_t* p, double (&v)[8]) {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __dsub_rn(__hiloint2double(0x43300000, (int)(w[i] & 0xFFFFu)), 4503599627370496.0);
+            v[2 * i + 1] = __dsub_rn(__hiloint2double(0x43300000, (int)(w[i] >> 16)), 4503599627370496.0);
+        }
+    }
     static __device__ __forceinline__ void ld(const uint16_t* p, float (&v)[8]) {
         const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p));
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -26,6 +53,12 @@ template <> struct Load8<uint16_t> {
     }
 };
 template <> struct Load8<float> {
+    static __device__ __forceinline__ void ldd(const float* p, double (&v)[8]) {
+        float f[8];
+        ld(p, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (double)f[i];
+    }
     static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
         const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
         const float4 b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
@@ -33,7 +66,8 @@ template <> struct Load8<float> {
     }
 };
 
-template <typename T, bool VEC>
+// RCP: the reciprocal form of the normalisation (norm_one_d; the launcher passes a.use_rcp) — vector path only
+template <typename T, bool VEC, bool RCP = false>
 __global__ void __launch_bounds__(256) pack_norm_kernel(const PackArgs a) {
     const T* raw = static_cast<const T*>(a.raw);
     const int h = a.H / 2, w = a.W / 2;
@@ -47,18 +81,17 @@ __global__ void __launch_bounds__(256) pack_norm_kernel(const PackArgs a) {
             const int y = (int)(t % h);
             const int f = (int)(t / h);
             const T* r0 = raw + ((size_t)f * a.H + 2 * y) * a.W + 8 * x4;
-            float e[8], o[8];
-            Load8<T>::ld(r0, e);
-            Load8<T>::ld(r0 + a.W, o);
+            double e[8], o[8];
+            Load8<T>::ldd(r0, e);
+            Load8<T>::ldd(r0 + a.W, o);
+            // plane order R(0,0) G1(0,1) B(1,1) G2(1,0): even row -> R (even columns), G1 (odd); odd row -> G2 (even), B (odd)
+#define PNNP_NORM(v, c) norm_one_d<RCP>(v, a.black[c], a.wp, a.span[c], a.rcp[c], a.norm, a.clip)
             float4 R, G1, B, G2;
-            R.x = norm_one(e[0], a.black[0], a.wp, a.norm, a.clip); R.y = norm_one(e[2], a.black[0], a.wp, a.norm, a.clip);
-            R.z = norm_one(e[4], a.black[0], a.wp, a.norm, a.clip); R.w = norm_one(e[6], a.black[0], a.wp, a.norm, a.clip);
-            G1.x = norm_one(e[1], a.black[1], a.wp, a.norm, a.clip); G1.y = norm_one(e[3], a.black[1], a.wp, a.norm, a.clip);
-            G1.z = norm_one(e[5], a.black[1], a.wp, a.norm, a.clip); G1.w = norm_one(e[7], a.black[1], a.wp, a.norm, a.clip);
-            B.x = norm_one(o[1], a.black[2], a.wp, a.norm, a.clip); B.y = norm_one(o[3], a.black[2], a.wp, a.norm, a.clip);
-            B.z = norm_one(o[5], a.black[2], a.wp, a.norm, a.clip); B.w = norm_one(o[7], a.black[2], a.wp, a.norm, a.clip);
-            G2.x = norm_one(o[0], a.black[3], a.wp, a.norm, a.clip); G2.y = norm_one(o[2], a.black[3], a.wp, a.norm, a.clip);
-            G2.z = norm_one(o[4], a.black[3], a.wp, a.norm, a.clip); G2.w = norm_one(o[6], a.black[3], a.wp, a.norm, a.clip);
+            R.x = PNNP_NORM(e[0], 0); R.y = PNNP_NORM(e[2], 0); R.z = PNNP_NORM(e[4], 0); R.w = PNNP_NORM(e[6], 0);
+            G1.x = PNNP_NORM(e[1], 1); G1.y = PNNP_NORM(e[3], 1); G1.z = PNNP_NORM(e[5], 1); G1.w = PNNP_NORM(e[7], 1);
+            B.x = PNNP_NORM(o[1], 2); B.y = PNNP_NORM(o[3], 2); B.z = PNNP_NORM(o[5], 2); B.w = PNNP_NORM(o[7], 2);
+            G2.x = PNNP_NORM(o[0], 3); G2.y = PNNP_NORM(o[2], 3); G2.z = PNNP_NORM(o[4], 3); G2.w = PNNP_NORM(o[6], 3);
+#undef PNNP_NORM
             float* ob = a.out + (size_t)f * 4 * plane + (size_t)y * w + 4 * x4;
             __stcs(reinterpret_cast<float4*>(ob), R);
             __stcs(reinterpret_cast<float4*>(ob + plane), G1);

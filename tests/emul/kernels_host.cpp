@@ -17,15 +17,23 @@ extern "C" {
 // grid x block are free parameters: results must not depend on them
 int emul_pack_norm_u16(const uint16_t* raw, float* out, int n, int H, int W, double wp, const double* black4, int norm, int clip,
                        int vec, int grid, int block) {
-    PackArgs a{raw, out, n, H, W, wp, {black4[0], black4[1], black4[2], black4[3]}, norm, clip};
-    if (vec) { if ((W / 2) % 4) return 1; EMUL_LAUNCH(grid, block, (pack_norm_kernel<uint16_t, true>(a))); }
+    const PackArgs a = make_pack_args(raw, out, n, H, W, wp, black4, norm, clip);
+    if (vec) {
+        if ((W / 2) % 4) return 1;
+        if (a.use_rcp) EMUL_LAUNCH(grid, block, (pack_norm_kernel<uint16_t, true, true>(a)));      // as pack.cu selects
+        else EMUL_LAUNCH(grid, block, (pack_norm_kernel<uint16_t, true>(a)));
+    }
     else EMUL_LAUNCH(grid, block, (pack_norm_kernel<uint16_t, false>(a)));
     return 0;
 }
 int emul_pack_norm_f32(const float* raw, float* out, int n, int H, int W, double wp, const double* black4, int norm, int clip,
                        int vec, int grid, int block) {
-    PackArgs a{raw, out, n, H, W, wp, {black4[0], black4[1], black4[2], black4[3]}, norm, clip};
-    if (vec) { if ((W / 2) % 4) return 1; EMUL_LAUNCH(grid, block, (pack_norm_kernel<float, true>(a))); }
+    const PackArgs a = make_pack_args(raw, out, n, H, W, wp, black4, norm, clip);
+    if (vec) {
+        if ((W / 2) % 4) return 1;
+        if (a.use_rcp) EMUL_LAUNCH(grid, block, (pack_norm_kernel<float, true, true>(a)));
+        else EMUL_LAUNCH(grid, block, (pack_norm_kernel<float, true>(a)));
+    }
     else EMUL_LAUNCH(grid, block, (pack_norm_kernel<float, false>(a)));
     return 0;
 }

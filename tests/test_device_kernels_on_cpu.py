@@ -81,6 +81,31 @@ def test_pack_kernels_vs_reference_goldens_and_oracle(K, golden):
         assert _pack(K, rf, 1023, 64, shape=(3, 32)).tobytes() == O.raw2bayer(rf, 1023, 64, True, False).tobytes()
 
 
+def test_pack_reciprocal_form_equals_the_division_on_every_code(K):
+    """pack_core.cuh norm_one_d<RCP>: q = x r, q + (x - span q) r against the reference's float64 division (utils/isp_ops.py:92-96)
+    on EVERY sensor code of both cameras through the vector kernel (the form pack.cu launches), with per-plane bias offsets, on
+    float32 samples including infinities / NaN, and the fallback to the division for a divisor whose significand is all ones."""
+    for wp, bl, ncodes in ((16383, 512, 16384), (1023, 64, 1024), (65535, 0, 65536), (4095, 240, 4096)):
+        codes = np.arange(ncodes, dtype=np.uint16)
+        raw = np.concatenate([codes, codes[::-1]]).reshape(2, -1)                   # every code on an even and on an odd row
+        raw = np.concatenate([raw, np.roll(raw, 1, axis=1)], axis=0)                # ... and in even and odd columns
+        assert (raw.shape[1] // 2) % 4 == 0
+        for bias in ((0, 0, 0, 0), (1, -2, 3, 0), (7, 7, -7, 11)):
+            for clip in (False, True):
+                want = O.raw2bayer(raw, wp, bl, True, clip, np.array(bias))
+                assert _pack(K, raw, wp, bl, clip=clip, bias=bias, vec=True, shape=(3, 64)).tobytes() == want.tobytes(), (wp, bl, bias, clip)
+    rs = np.random.RandomState(7)
+    rf = (rs.rand(8, 64).astype(np.float32) * 70000 - 2000).astype(np.float32)
+    rf[0, :6] = [np.inf, -np.inf, np.nan, 0.0, -0.0, 3.4e38]
+    with np.errstate(invalid="ignore"):
+        want = O.raw2bayer(rf, 16383, 512, True, False)
+    got = _pack(K, rf, 16383, 512, vec=True, shape=(2, 32))
+    assert got.tobytes() == want.tobytes() or (np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]))
+    wp_ones = float(np.nextafter(np.float64(2.0), 0)) * 8192            # wp - 0 = 1.11...1b x 2^13: the launcher falls back to the division
+    fin = np.ascontiguousarray(rf[2:4])
+    assert _pack(K, fin, wp_ones, 0, vec=True, shape=(2, 32)).tobytes() == O.raw2bayer(fin, wp_ones, 0, True, False).tobytes()
+
+
 def test_unpack_kernel_vs_reference_golden_and_roundtrip(K, golden):
     g = golden("pack")
     u = np.ascontiguousarray(g["unpack_in"], np.float32).reshape(-1, 4, *g["unpack_in"].shape[-2:])
