@@ -1,7 +1,7 @@
 // Separable form of the SSIM / squared-error pass of eval_metrics.cu (the default since r02; PNNP_SSIM_V2=0: the first form).
 //
 // The 7x7 uniform-window sums of skimage's structural_similarity (utils/visualization.py:29-30) are separable: for each of the
-// five quantities (a, b, a^2, b^2, ab) a horizontal 7-sum per patch row, then a vertical 7-sum per window centre — 2 x 7 float64
+// window quantities (a, b, a^2 + b^2, ab; five with a^2 and b^2 apart in the first version) a horizontal 7-sum per patch row, then a vertical 7-sum per window centre — 2 x 7 float64
 // additions per quantity and centre instead of 49.  The first version (ssim_mse_kernel) spends ~440 float64-heavy instructions
 // per pixel, about 1 ms of the 3.8 ms evaltest frame.
 //
@@ -41,7 +41,9 @@ struct Ssim2Tile {
     // quarter-warp's 128-bit store then spans 256 bytes, two wavefronts instead of one (r02 capture: 35 M store bank conflicts, the
     // pass bound by shared-memory wavefronts at 62 % of the LSU pipe).  Sums 0-1 of column group g sit at [2g, 2g + 1], sums 2-3 at
     // [16 + 2g, 16 + 2g + 1]: lanes 16 bytes apart in both stores; the vertical pass walks the columns in the stored order.
-    double hs[5][kS2Ring][kS2TileX];
+    // FOUR quantities: sum a, sum b, sum (a^2 + b^2), sum ab — the SSIM map needs the two variances only as their sum, so a^2 and b^2
+    // share one window sum (a fifth of the additions, shared-memory stores and loads of both passes; the first form kept five)
+    double hs[4][kS2Ring][kS2TileX];
 };
 __device__ __forceinline__ int ssim2_col(int lx) { return ((lx >> 1) & 1) * 16 + (lx >> 2) * 2 + (lx & 1); }
 
@@ -125,23 +127,35 @@ __device__ __forceinline__ void ssim2_hsum(int tid, Ssim2Tile& t, int py0 = 0, i
     constexpr int kGroups = kS2TileX / 4;
     for (int i = tid + py0 * kGroups; i < kS2PatchY * kGroups; i += kS2Threads) {
         const int py = i / kGroups, lx = (i - py * kGroups) * 4, slot = (ring0 + py) & (kS2Ring - 1);
-        double a[10], b[10], aa[10], bb[10], ab[10], w[4];
+        double a[10], b[10], pp[10], ab[10], w[4];
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
             a[k] = t.a[py][lx + k]; b[k] = t.b[py][lx + k];
-            aa[k] = a[k] * a[k]; bb[k] = b[k] * b[k]; ab[k] = a[k] * b[k];
+            pp[k] = fma(a[k], a[k], b[k] * b[k]); ab[k] = a[k] * b[k];      // a^2, b^2 are exact (24-bit significands): one rounding
         }
         ssim2_sums4(a, w);
         ssim2_store4(t.hs[0][slot], lx >> 2, w);
         ssim2_sums4(b, w);
         ssim2_store4(t.hs[1][slot], lx >> 2, w);
-        ssim2_sums4(aa, w);
+        ssim2_sums4(pp, w);
         ssim2_store4(t.hs[2][slot], lx >> 2, w);
-        ssim2_sums4(bb, w);
-        ssim2_store4(t.hs[3][slot], lx >> 2, w);
         ssim2_sums4(ab, w);
-        ssim2_store4(t.hs[4][slot], lx >> 2, w);
+        ssim2_store4(t.hs[3][slot], lx >> 2, w);
     }
+}
+
+// 1 / d for the map's denominator (d >= C1 C2 > 0) without the division subroutine: the hardware's 2^-23 seed and two Newton steps
+// (2^-46, then the float64 rounding level); a handful of FMAs against ~15 instructions and a slow-path test per pixel
+__device__ __forceinline__ double ssim2_rcp(double d) {
+#ifdef PNNP_HOST_EMUL
+    return 1.0 / d;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+#endif
 }
 
 // phase 3: vertical 7-sums + the SSIM map value; one item = (centre column, TWO adjacent centre rows) = one per thread (the first
@@ -158,9 +172,9 @@ __device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0
         const int lg = i / kS2TileX, col = i - lg * kS2TileX, ly0 = lg * 2;
         const int lx = ((col & 15) >> 1) * 4 + (col >> 4) * 2 + (col & 1), cx = x0 + lx;
         if (cx < kS2Pad || cx >= g.w - kS2Pad) continue;
-        double s[5][2];
+        double s[4][2];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
+        for (int q = 0; q < 4; ++q) {
             double v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = t.hs[q][(ring0 + ly0 + k) & (kS2Ring - 1)][col];
@@ -173,9 +187,10 @@ __device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0
             const int cy = y0 + ly0 + k;
             if (cy < kS2Pad || cy >= g.h - kS2Pad) continue;
             const double ux = s[0][k] * inv_np, uy = s[1][k] * inv_np;
-            const double vx = cov_norm * (s[2][k] * inv_np - ux * ux), vy = cov_norm * (s[3][k] * inv_np - uy * uy);
-            const double vxy = cov_norm * (s[4][k] * inv_np - ux * uy);
-            ssum += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+            const double uxuy = ux * uy, m2 = fma(ux, ux, uy * uy);
+            const double vxvy = cov_norm * (s[2][k] * inv_np - m2);            // var a + var b (sample variances)
+            const double vxy = cov_norm * (s[3][k] * inv_np - uxuy);
+            ssum += ((2 * uxuy + C1) * (2 * vxy + C2)) * ssim2_rcp((m2 + C1) * (vxvy + C2));
         }
     }
     return ssum;
