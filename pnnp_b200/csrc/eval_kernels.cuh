@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) ssim_mse_kernel(const float* __restrict__
 // accumulators ONCE per block: with one tile per block every block ended in two float64 atomics on the same two addresses per frame
 // (65 536 same-address atomics per 16 crops serialise in L2 — the whole kernel's 291 us in r02, whatever the arithmetic cost).
 constexpr int kS2TilesPerCta = 8;
-__global__ void __launch_bounds__(kS2Threads, 4) ssim_mse_v2_kernel(Ssim2Args g, double* sums, int stride) {
+__global__ void __launch_bounds__(kS2Threads, kS2Threads == 128 ? 5 : 4) ssim_mse_v2_kernel(Ssim2Args g, double* sums, int stride) {
     extern __shared__ __align__(16) uint8_t s2_raw[];
     Ssim2Tile& t = *reinterpret_cast<Ssim2Tile*>(s2_raw);
     PNNP_SMEM double s_red[8];

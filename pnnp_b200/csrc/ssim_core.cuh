@@ -20,7 +20,20 @@ namespace pnnp {
 constexpr int kS2Win = 7, kS2Pad = 3;
 constexpr int kS2TileX = 32, kS2TileY = 16;                     // window centres per block
 constexpr int kS2PatchX = kS2TileX + 2 * kS2Pad, kS2PatchY = kS2TileY + 2 * kS2Pad;   // 38 x 22 pixels
-constexpr int kS2Threads = 256;
+// 128 threads: both summing passes then have exactly one item per thread and tile — 16 new patch rows x 8 column groups in the
+// horizontal pass (with 256 threads half of the block idled there), 4 row groups x 32 columns in the vertical pass, whose items
+// cover FOUR centre rows (ten rows of horizontal sums per quantity for four outputs instead of eight for two: 2.5 instead of 4
+// 8-byte shared-memory loads per output and quantity; the pass is bound by shared-memory bytes — ~180 per output before, r02).
+// PNNP_S2_THREADS=256 / PNNP_S2_VROWS=2 rebuild the earlier form (same-box comparisons).
+#ifndef PNNP_S2_THREADS
+#define PNNP_S2_THREADS 128
+#endif
+#ifndef PNNP_S2_VROWS
+#define PNNP_S2_VROWS 4
+#endif
+constexpr int kS2Threads = PNNP_S2_THREADS;
+constexpr int kS2VRows = PNNP_S2_VROWS;
+static_assert(kS2VRows == 2 || kS2VRows == 4, "vertical-pass items cover two or four centre rows");
 // A block walks kS2TilesPerCta vertically adjacent tiles.  The bottom six patch rows of a tile are the top six of the next one, so
 // from the second tile on only the 16 NEW rows are loaded and summed horizontally (22 before: 27 % of the load, conversion,
 // multiplication and horizontal-sum work); the horizontal sums live in a ring of kS2Ring rows indexed by the row's distance from
@@ -158,32 +171,41 @@ __device__ __forceinline__ double ssim2_rcp(double d) {
 #endif
 }
 
-// phase 3: vertical 7-sums + the SSIM map value; one item = (centre column, TWO adjacent centre rows) = one per thread (the first
-// form's items of four rows kept half of the block idle during the pass's heaviest phase: barrier stalls 4.5 warp cycles per issue
-// in the r02 capture); eight rows of horizontal sums per quantity, their six common rows summed once; returns this thread's share
-// of the map's sum
+// phase 3: vertical 7-sums + the SSIM map value; one item = (centre column, kS2VRows adjacent centre rows) = one per thread (an
+// earlier form's items of four rows in a 256-thread block kept half of the block idle during the pass's heaviest phase: barrier
+// stalls 4.5 warp cycles per issue in the r02 capture); ten (eight) rows of horizontal sums per quantity, their common rows summed
+// once; returns this thread's share of the map's sum
 __device__ __forceinline__ double ssim2_vsum(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Tile& t, int ring0 = 0) {
     const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
     const double inv_np = 1.0 / 49.0, cov_norm = 49.0 / 48.0;
     double ssum = 0.0;
-    for (int i = tid; i < (kS2TileY / 2) * kS2TileX; i += kS2Threads) {
+    for (int i = tid; i < (kS2TileY / kS2VRows) * kS2TileX; i += kS2Threads) {
         // consecutive lanes take columns that are consecutive IN THE STORED ORDER (a half-warp's 64-bit load is one 128-byte run);
         // lx = ssim2_col^-1(col) is the centre column those sums belong to
-        const int lg = i / kS2TileX, col = i - lg * kS2TileX, ly0 = lg * 2;
+        const int lg = i / kS2TileX, col = i - lg * kS2TileX, ly0 = lg * kS2VRows;
         const int lx = ((col & 15) >> 1) * 4 + (col >> 4) * 2 + (col & 1), cx = x0 + lx;
         if (cx < kS2Pad || cx >= g.w - kS2Pad) continue;
-        double s[4][2];
+        double s[4][kS2VRows];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            double v[8];
+            if constexpr (kS2VRows == 4) {
+                double v[10], w[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = t.hs[q][(ring0 + ly0 + k) & (kS2Ring - 1)][col];
-            const double core = ((v[1] + v[2]) + (v[3] + v[4])) + (v[5] + v[6]);
-            s[q][0] = core + v[0];
-            s[q][1] = core + v[7];
+                for (int k = 0; k < 10; ++k) v[k] = t.hs[q][(ring0 + ly0 + k) & (kS2Ring - 1)][col];
+                ssim2_sums4(v, w);                          // the horizontal pass's sharing of terms, down a column
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s[q][k] = w[k];
+            } else {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = t.hs[q][(ring0 + ly0 + k) & (kS2Ring - 1)][col];
+                const double core = ((v[1] + v[2]) + (v[3] + v[4])) + (v[5] + v[6]);
+                s[q][0] = core + v[0];
+                s[q][1] = core + v[7];
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < kS2VRows; ++k) {
             const int cy = y0 + ly0 + k;
             if (cy < kS2Pad || cy >= g.h - kS2Pad) continue;
             const double ux = s[0][k] * inv_np, uy = s[1][k] * inv_np;
