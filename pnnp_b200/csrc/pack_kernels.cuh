@@ -33,38 +33,92 @@ inline PackArgs make_pack_args(const void* raw, float* out, int n, int H, int W,
 }
 
 
+#ifndef PNNP_PACK_ST
+#define PNNP_PACK_ST __stcs                    // tools/ubench_pack.cu rebuilds the kernel with other store / load flavours
+#endif
+#ifndef PNNP_PACK_LD
+#define PNNP_PACK_LD __ldcs
+#endif
+// Eight raw samples of one row: the load (kept apart from the conversion so that a thread can have several rows in flight) and
+// the samples as doubles.
 template <typename T> struct Load8;
 template <> struct Load8<uint16_t> {
+    struct Raw { uint4 q; };
+    static __device__ __forceinline__ Raw ldraw(const uint16_t* p) { return Raw{PNNP_PACK_LD(reinterpret_cast<const uint4*>(p))}; }
     // the eight codes as doubles without a conversion instruction: 2^52 + n is the bit pattern (0x43300000, n); minus 2^52 is exact
-    static __device__ __forceinline__ void ldd(const uint16_t* p, double (&v)[8]) {
-        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    static __device__ __forceinline__ void cvt(const Raw& r, double (&v)[8]) {
+        const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             v[2 * i] = __dsub_rn(__hiloint2double(0x43300000, (int)(w[i] & 0xFFFFu)), 4503599627370496.0);
             v[2 * i + 1] = __dsub_rn(__hiloint2double(0x43300000, (int)(w[i] >> 16)), 4503599627370496.0);
         }
     }
-    static __device__ __forceinline__ void ld(const uint16_t* p, float (&v)[8]) {
-        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { v[2 * i] = (float)(w[i] & 0xFFFFu); v[2 * i + 1] = (float)(w[i] >> 16); }
-    }
 };
 template <> struct Load8<float> {
-    static __device__ __forceinline__ void ldd(const float* p, double (&v)[8]) {
-        float f[8];
-        ld(p, f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (double)f[i];
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw ldraw(const float* p) {
+        return Raw{PNNP_PACK_LD(reinterpret_cast<const float4*>(p)), PNNP_PACK_LD(reinterpret_cast<const float4*>(p) + 1)};
     }
-    static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
-        const float4 a = __ldcs(reinterpret_cast<const float4*>(p));
-        const float4 b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    static __device__ __forceinline__ void cvt(const Raw& r, double (&v)[8]) {
+        v[0] = (double)r.a.x; v[1] = (double)r.a.y; v[2] = (double)r.a.z; v[3] = (double)r.a.w;
+        v[4] = (double)r.b.x; v[5] = (double)r.b.y; v[6] = (double)r.b.z; v[7] = (double)r.b.w;
     }
 };
+
+// One vector item = 8 samples of an even raw row and the 8 below them -> one float4 in each of the four planes.
+template <typename T, bool RCP, typename I>
+struct PackItem {
+    I f, y, x4;
+    typename Load8<T>::Raw e, o;
+    __device__ __forceinline__ void load(const PackArgs& a, I i, I w4, I h) {
+        x4 = i % w4;
+        const I t = i / w4;
+        y = t % h;
+        f = t / h;
+        const T* r0 = static_cast<const T*>(a.raw) + ((size_t)f * a.H + 2 * (size_t)y) * a.W + 8 * (size_t)x4;
+        e = Load8<T>::ldraw(r0);
+        o = Load8<T>::ldraw(r0 + a.W);
+    }
+    __device__ __forceinline__ void finish(const PackArgs& a, size_t plane, int w) const {
+        double ev[8], ov[8];
+        Load8<T>::cvt(e, ev);
+        Load8<T>::cvt(o, ov);
+        // plane order R(0,0) G1(0,1) B(1,1) G2(1,0): even row -> R (even columns), G1 (odd); odd row -> G2 (even), B (odd)
+#define PNNP_NORM(v, c) norm_one_d<RCP>(v, a.black[c], a.wp, a.span[c], a.rcp[c], a.norm, a.clip)
+        float4 R, G1, B, G2;
+        R.x = PNNP_NORM(ev[0], 0); R.y = PNNP_NORM(ev[2], 0); R.z = PNNP_NORM(ev[4], 0); R.w = PNNP_NORM(ev[6], 0);
+        G1.x = PNNP_NORM(ev[1], 1); G1.y = PNNP_NORM(ev[3], 1); G1.z = PNNP_NORM(ev[5], 1); G1.w = PNNP_NORM(ev[7], 1);
+        B.x = PNNP_NORM(ov[1], 2); B.y = PNNP_NORM(ov[3], 2); B.z = PNNP_NORM(ov[5], 2); B.w = PNNP_NORM(ov[7], 2);
+        G2.x = PNNP_NORM(ov[0], 3); G2.y = PNNP_NORM(ov[2], 3); G2.z = PNNP_NORM(ov[4], 3); G2.w = PNNP_NORM(ov[6], 3);
+#undef PNNP_NORM
+        float* ob = a.out + (size_t)f * 4 * plane + (size_t)y * w + 4 * (size_t)x4;
+        PNNP_PACK_ST(reinterpret_cast<float4*>(ob), R);
+        PNNP_PACK_ST(reinterpret_cast<float4*>(ob + plane), G1);
+        PNNP_PACK_ST(reinterpret_cast<float4*>(ob + 2 * plane), B);
+        PNNP_PACK_ST(reinterpret_cast<float4*>(ob + 3 * plane), G2);
+    }
+};
+
+// Two items per trip: both items' four 128-bit loads are issued before the first conversion (one item per trip kept 32 bytes per
+// thread in flight: 3.6 TB/s); I = index type (32-bit whenever the item count allows: the two divisions per item were 64-bit).
+template <typename T, bool RCP, typename I>
+__device__ __forceinline__ void pack_vec_loop(const PackArgs& a, I total, I w4, I h, size_t plane, int w) {
+    const I stride = (I)gridDim.x * (I)blockDim.x;
+    I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x;
+    for (; i < total && total - i > stride; i += 2 * stride) {
+        PackItem<T, RCP, I> p0, p1;
+        p0.load(a, i, w4, h);
+        p1.load(a, i + stride, w4, h);
+        p0.finish(a, plane, w);
+        p1.finish(a, plane, w);
+    }
+    if (i < total) {
+        PackItem<T, RCP, I> p0;
+        p0.load(a, i, w4, h);
+        p0.finish(a, plane, w);
+    }
+}
 
 // RCP: the reciprocal form of the normalisation (norm_one_d; the launcher passes a.use_rcp) — vector path only
 template <typename T, bool VEC, bool RCP = false>
@@ -75,29 +129,8 @@ __global__ void __launch_bounds__(256) pack_norm_kernel(const PackArgs a) {
     if (VEC) {
         const int w4 = w / 4;                                  // float4 groups per packed row
         const size_t total = (size_t)a.n * h * w4;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-            const int x4 = (int)(i % w4);
-            const size_t t = i / w4;
-            const int y = (int)(t % h);
-            const int f = (int)(t / h);
-            const T* r0 = raw + ((size_t)f * a.H + 2 * y) * a.W + 8 * x4;
-            double e[8], o[8];
-            Load8<T>::ldd(r0, e);
-            Load8<T>::ldd(r0 + a.W, o);
-            // plane order R(0,0) G1(0,1) B(1,1) G2(1,0): even row -> R (even columns), G1 (odd); odd row -> G2 (even), B (odd)
-#define PNNP_NORM(v, c) norm_one_d<RCP>(v, a.black[c], a.wp, a.span[c], a.rcp[c], a.norm, a.clip)
-            float4 R, G1, B, G2;
-            R.x = PNNP_NORM(e[0], 0); R.y = PNNP_NORM(e[2], 0); R.z = PNNP_NORM(e[4], 0); R.w = PNNP_NORM(e[6], 0);
-            G1.x = PNNP_NORM(e[1], 1); G1.y = PNNP_NORM(e[3], 1); G1.z = PNNP_NORM(e[5], 1); G1.w = PNNP_NORM(e[7], 1);
-            B.x = PNNP_NORM(o[1], 2); B.y = PNNP_NORM(o[3], 2); B.z = PNNP_NORM(o[5], 2); B.w = PNNP_NORM(o[7], 2);
-            G2.x = PNNP_NORM(o[0], 3); G2.y = PNNP_NORM(o[2], 3); G2.z = PNNP_NORM(o[4], 3); G2.w = PNNP_NORM(o[6], 3);
-#undef PNNP_NORM
-            float* ob = a.out + (size_t)f * 4 * plane + (size_t)y * w + 4 * x4;
-            __stcs(reinterpret_cast<float4*>(ob), R);
-            __stcs(reinterpret_cast<float4*>(ob + plane), G1);
-            __stcs(reinterpret_cast<float4*>(ob + 2 * plane), B);
-            __stcs(reinterpret_cast<float4*>(ob + 3 * plane), G2);
-        }
+        if (total < 0x40000000u) pack_vec_loop<T, RCP, uint32_t>(a, (uint32_t)total, (uint32_t)w4, (uint32_t)h, plane, w);
+        else pack_vec_loop<T, RCP, size_t>(a, total, (size_t)w4, (size_t)h, plane, w);
     } else {
         const size_t total = (size_t)a.n * 4 * plane;
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
