@@ -3,11 +3,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
-#include "../pnnp_b200/csrc/pack_kernels.cuh"
-using namespace pnnp;
-__device__ __forceinline__ void st_plain(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ void st_plain(float4* p, float4 v) { *p = v; }       // -DPNNP_PACK_ST=st_plain -DPNNP_PACK_LD=ld_plain
 __device__ __forceinline__ uint4 ld_plain(const uint4* p) { return *p; }
 __device__ __forceinline__ float4 ld_plain(const float4* p) { return *p; }
+#include "../pnnp_b200/csrc/pack_kernels.cuh"
+using namespace pnnp;
 int main(int argc, char** argv) {
     const int n = 64, H = 1024, W = 1024;
     const int bps = argc > 1 ? atoi(argv[1]) : 8, threads = argc > 2 ? atoi(argv[2]) : 256;
