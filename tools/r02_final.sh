@@ -1,6 +1,6 @@
 #!/bin/bash
 # Final measurement pass of round 2 (run under gpurun; outputs under gpurun_out/r02_final/)
-O=gpurun_out/r02_final; mkdir -p $O
+O=gpurun_out/${R02_OUT:-r02_final}; mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
 python bench.py --steps 20 --warmup 5 > $O/bench_path64.json 2> $O/bench_path64.err
 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_reference.json 2> $O/bench_reference.err
