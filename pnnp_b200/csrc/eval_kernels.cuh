@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(kS2Threads, kS2Threads == 128 ? 5 : 4) ssim_ms
     double se = 0.0, ssum = 0.0;
     Ssim2Regs nxt;                                      // the next tile's pixels: loaded while the current tile is summed
     const int y_first = blockIdx.y * kS2TilesPerCta * kS2TileY;
-    ssim2_fetch(threadIdx.x, g, plane_id, x0, y_first, nxt);
+    if (ssim2_inside(g, x0, y_first, 0)) ssim2_fetch<true>(threadIdx.x, g, plane_id, x0, y_first, nxt);
+    else ssim2_fetch(threadIdx.x, g, plane_id, x0, y_first, nxt);
     for (int k = 0; k < kS2TilesPerCta; ++k) {
         const int y0 = y_first + k * kS2TileY;
         if (y0 >= g.h) break;
@@ -132,8 +133,12 @@ __global__ void __launch_bounds__(kS2Threads, kS2Threads == 128 ? 5 : 4) ssim_ms
         const bool more = k + 1 < kS2TilesPerCta && y0 + kS2TileY < g.h;
         // squared error: every image row of the block's range exactly once, by the tile that stages it (staged rows: y0 - 3 + [py0, 22))
         const int se_lo = max(y_first, y0 - kS2Pad + py0), se_hi = more ? y0 + kS2TileY + kS2Pad : y0 + kS2TileY;
-        se += ssim2_stage(threadIdx.x, g, x0, y0, nxt, t, py0, se_lo, se_hi);
-        if (more) ssim2_fetch(threadIdx.x, g, plane_id, x0, y0 + kS2TileY, nxt, 2 * kS2Pad);
+        if (ssim2_inside(g, x0, y0, py0)) se += ssim2_stage<true>(threadIdx.x, g, x0, y0, nxt, t, py0, se_lo, se_hi);
+        else se += ssim2_stage(threadIdx.x, g, x0, y0, nxt, t, py0, se_lo, se_hi);
+        if (more) {
+            if (ssim2_inside(g, x0, y0 + kS2TileY, 2 * kS2Pad)) ssim2_fetch<true>(threadIdx.x, g, plane_id, x0, y0 + kS2TileY, nxt, 2 * kS2Pad);
+            else ssim2_fetch(threadIdx.x, g, plane_id, x0, y0 + kS2TileY, nxt, 2 * kS2Pad);
+        }
         __syncthreads();
         ssim2_hsum(threadIdx.x, t, py0, ring0);
         __syncthreads();

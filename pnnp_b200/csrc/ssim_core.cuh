@@ -67,6 +67,10 @@ __device__ __forceinline__ int ssim2_col(int lx) { return ((lx >> 1) & 1) * 16 +
 constexpr int kS2Slots = (kS2PatchY * kS2PatchX + kS2Threads - 1) / kS2Threads;        // 4
 struct Ssim2Regs { float d[kS2Slots], r[kS2Slots]; };
 // py0: first patch row to load (0 for a block's first tile, 6 for the following ones: rows 0-5 were the previous tile's rows 16-21)
+// INSIDE: the whole patch (rows py0 .. 21, all 38 columns) lies inside the image — the caller's block-uniform test — so the four
+// per-pixel bounds comparisons of both halves go away (r02 capture: 16 ISETP per output, most of them these; four tiles in five of
+// a 512 x 512 crop are interior).
+template <bool INSIDE = false>
 __device__ __forceinline__ void ssim2_fetch(int tid, const Ssim2Args& g, int plane, int x0, int y0, Ssim2Regs& v, int py0 = 0) {
     const float* d = g.dn + (size_t)plane * g.h * g.w;
     const float* r = g.hr + (size_t)plane * g.h * g.w;
@@ -75,13 +79,17 @@ __device__ __forceinline__ void ssim2_fetch(int tid, const Ssim2Args& g, int pla
         const int i = tid + k * kS2Threads + py0 * kS2PatchX;
         const int py = i / kS2PatchX, px = i - py * kS2PatchX;
         const int gx = x0 + px - kS2Pad, gy = y0 + py - kS2Pad;
-        const bool in = i < kS2PatchY * kS2PatchX && gx >= 0 && gx < g.w && gy >= 0 && gy < g.h;
+        const bool in = i < kS2PatchY * kS2PatchX && (INSIDE || (gx >= 0 && gx < g.w && gy >= 0 && gy < g.h));
         v.d[k] = in ? d[(size_t)gy * g.w + gx] : 0.f;
         v.r[k] = in ? r[(size_t)gy * g.w + gx] : 0.f;
     }
 }
+__device__ __forceinline__ bool ssim2_inside(const Ssim2Args& g, int x0, int y0, int py0) {
+    return x0 - kS2Pad >= 0 && x0 + kS2TileX + kS2Pad <= g.w && y0 - kS2Pad + py0 >= 0 && y0 + kS2TileY + kS2Pad <= g.h;
+}
 // se_lo / se_hi: image rows [se_lo, se_hi) whose squared error this call accounts for (a block's first tile: its own 16 centre rows
 // and, like every tile, the three rows below them when another tile of the block follows — those rows are not staged again)
+template <bool INSIDE = false>
 __device__ __forceinline__ double ssim2_stage(int tid, const Ssim2Args& g, int x0, int y0, const Ssim2Regs& v, Ssim2Tile& t, int py0 = 0,
                                               int se_lo = -1, int se_hi = -1) {
     if (se_lo < 0) { se_lo = y0; se_hi = y0 + kS2TileY; }
@@ -93,7 +101,7 @@ __device__ __forceinline__ double ssim2_stage(int tid, const Ssim2Args& g, int x
         const int py = i / kS2PatchX, px = i - py * kS2PatchX;
         const int gx = x0 + px - kS2Pad, gy = y0 + py - kS2Pad;
         float a = 0.f, b = 0.f;
-        if (gx >= 0 && gx < g.w && gy >= 0 && gy < g.h) {
+        if (INSIDE || (gx >= 0 && gx < g.w && gy >= 0 && gy < g.h)) {
             float p = fminf(fmaxf(v.d[k] * g.scale, 0.f), 1.f);
             if (g.use_gain) p = g.gain * p;
             a = fminf(fmaxf(p * 255.0f, 0.f), 255.f);
