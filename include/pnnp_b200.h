@@ -250,6 +250,11 @@ int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t pixels, int
  * the result is also multiplied by act'(cfull) (cfull is the activated output whose pooling this undoes) */
 int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c,
                      int act_kind, void* stream);
+/* the same with the bias gradient of the conv that produced cfull in the same pass: dbias[ch] += sum over pixels of gc (fp32
+ * sums of the stored bf16 values — what pnnp_act_bwd_bias(gc, NULL, dbias, ..., act none) computes in a second pass over gc;
+ * torch.autograd's conv bias gradient, /root/reference/trainer_SID.py:93-101 `loss.backward()`); c / 8 has to divide 256 */
+int pnnp_maxpool_bwd_bias(const void* gp, const void* cfull, const void* gskip, void* gc, float* dbias, int n, int h, int w, int c,
+                          int act_kind, void* stream);
 /* Weight gradients straight from the NHWC bf16 activations (tcgen05, MN-major operands via TMA; no transposed copies):
  *   mode 0 (3x3 s1 p1 conv):      dw[ky*3+kx][ci_off + ci][co] += sum_p x[p + (ky-1, kx-1)][ci] * g[p][co]
  *   mode 1 (ConvTranspose2d 2x2): dw[a*2+b][ci_off + ci][co]   += sum_p x[p][ci] * g[2p + (a, b)][co]

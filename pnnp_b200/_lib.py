@@ -68,6 +68,7 @@ SIGNATURES = {
     "pnnp_head_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pnnp_act_bwd_bias": (_i, [_vp, _vp, _vp, C.c_size_t, _i, _i, _vp]),
     "pnnp_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pnnp_maxpool_bwd_bias": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pnnp_wgrad_nhwc": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "pnnp_wgrad_nhwc_pipeline_error": (_i, []),
     "pnnp_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _f, _f, _f, _f, _vp]),

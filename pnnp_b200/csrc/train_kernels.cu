@@ -72,9 +72,24 @@ extern "C" int pnnp_act_bwd_bias(void* g, const void* out, float* dbias, size_t 
 extern "C" int pnnp_maxpool_bwd(const void* gp, const void* cfull, const void* gskip, void* gc, int n, int h, int w, int c, int act_kind,
                                 void* stream) {
     if (!gp || !cfull || !gc || (h & 1) || (w & 1) || (c & 7)) return fail("maxpool_bwd: bad arguments (even h, w; c % 8 == 0)");
-    maxpool_bwd_kernel<<<blocks_for((size_t)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+    maxpool_bwd_kernel<false><<<blocks_for((size_t)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
         static_cast<const __nv_bfloat16*>(gp), static_cast<const __nv_bfloat16*>(cfull), static_cast<const __nv_bfloat16*>(gskip),
-        static_cast<__nv_bfloat16*>(gc), n, h, w, c, act_kind);
+        static_cast<__nv_bfloat16*>(gc), nullptr, n, h, w, c, act_kind);
+    count_launch();
+    PNNP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pnnp_maxpool_bwd_bias(const void* gp, const void* cfull, const void* gskip, void* gc, float* dbias, int n, int h, int w,
+                                     int c, int act_kind, void* stream) {
+    if (!gp || !cfull || !gc || !dbias || (h & 1) || (w & 1) || (c & 7) || c > 2048 || (256 % (c / 8)))
+        return fail("maxpool_bwd_bias: bad arguments (even h, w; c / 8 a divisor of 256)");
+    // every block ends in c same-address atomics: at least four items per thread on small tensors (as pnnp_act_bwd_bias)
+    const size_t items = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(items / (256 * 4), 148 * 8));
+    maxpool_bwd_kernel<true><<<blocks, 256, sizeof(float) * c, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(gp), static_cast<const __nv_bfloat16*>(cfull), static_cast<const __nv_bfloat16*>(gskip),
+        static_cast<__nv_bfloat16*>(gc), dbias, n, h, w, c, act_kind);
     count_launch();
     PNNP_CUDA(cudaGetLastError());
     return 0;

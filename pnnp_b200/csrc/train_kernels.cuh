@@ -25,15 +25,24 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ pred, const float* __restrict__ hr,
                                                       float* __restrict__ gpred, size_t total, float inv_total, double* loss_sum) {
     double acc = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const float p = pred[i], t = hr[i];
+    // d|x|/dx = sign(x) (0 at 0, as torch); clamp passes the gradient only for 0 <= p <= 1 (torch.clamp semantics)
+    auto one = [&](float p, float t) -> float {
         const float pc = fminf(fmaxf(p, 0.f), 1.f);
         const float d = pc - t;
         acc += (double)fabsf(d);
-        // d|x|/dx = sign(x) (0 at 0, as torch); clamp passes the gradient only for 0 <= p <= 1 (torch.clamp semantics)
         const float s = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-        gpred[i] = (p >= 0.f && p <= 1.f) ? s * inv_total : 0.f;
+        return (p >= 0.f && p <= 1.f) ? s * inv_total : 0.f;
+    };
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(gpred)) & 15) == 0;
+    const size_t quads = vec ? total / 4 : 0;                                // 16-byte items; the (< 4 element) rest goes one by one
+    for (size_t q = tid; q < quads; q += nthr) {
+        const float4 p = reinterpret_cast<const float4*>(pred)[q], t = reinterpret_cast<const float4*>(hr)[q];
+        float4 g;
+        g.x = one(p.x, t.x); g.y = one(p.y, t.y); g.z = one(p.z, t.z); g.w = one(p.w, t.w);
+        reinterpret_cast<float4*>(gpred)[q] = g;
     }
+    for (size_t i = quads * 4 + tid; i < total; i += nthr) gpred[i] = one(pred[i], hr[i]);
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum, acc);
 }
@@ -54,9 +63,11 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     for (int i = threadIdx.x; i < co * cin + co + cin; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
     const int groups = cin / 8;                      // 1, 2, 4 or 8: divides 32, so a warp holds whole pixels
-    const size_t plane = (size_t)h * w, total = (size_t)n * plane * groups;
+    int sh = 0;
+    while ((1 << sh) < groups) ++sh;
+    const size_t plane = (size_t)h * w, npix = (size_t)n * plane;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int grp = (int)(tid % groups), c = grp * 8;
+    const int grp = (int)(tid & (size_t)(groups - 1)), c = grp * 8;
     float wv[4][8], adw[4][8], adb[4] = {0.f, 0.f, 0.f, 0.f}, abp[8];
 #pragma unroll
     for (int o = 0; o < 4; ++o)
@@ -65,13 +76,19 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
     for (int k = 0; k < 8; ++k) abp[k] = 0.f;
     const float slope = act_kind == 1 ? 0.2f : (act_kind == 2 ? 0.f : 1.f);
-    for (size_t i = tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t pix = i / groups;
-        const size_t img = pix / plane, off = pix - img * plane;
-        float gp[4] = {0.f, 0.f, 0.f, 0.f};
+    // A thread's items are ps pixels apart (grid * 256 is a multiple of the group count), so (image, offset inside the plane) advance
+    // by increment and carry: the two 64-bit divisions per item of the first form were more than half of its executed instructions
+    // (r02 launch list: 157 us for 302 MB).  Two items per trip, loads first; the additions keep their order (same results bit for bit).
+    const size_t ps = ((size_t)gridDim.x * blockDim.x) >> sh;
+    size_t pix = tid >> sh;
+    size_t img = pix / plane, off = pix - img * plane;
+    auto advance = [&]() { pix += ps; off += ps; while (off >= plane) { off -= plane; ++img; } };
+    auto fetch = [&](float (&gp)[4], uint4& av) {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) if (o < co) gp[o] = gpred[(img * co + o) * plane + off];
-        const uint4 av = *reinterpret_cast<const uint4*>(act + pix * cin + c);
+        for (int o = 0; o < 4; ++o) gp[o] = o < co ? gpred[(img * co + o) * plane + off] : 0.f;
+        av = *reinterpret_cast<const uint4*>(act + pix * cin + c);
+    };
+    auto item = [&](size_t at, const float (&gp)[4], const uint4& av) {
         const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
         uint32_t gw[4];
 #pragma unroll
@@ -92,7 +109,23 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
             for (int o = 0; o < 4; ++o) adb[o] += gp[o];
         }
-        *reinterpret_cast<uint4*>(gact + pix * cin + c) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+        *reinterpret_cast<uint4*>(gact + at * cin + c) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+    };
+    constexpr int kInFlight = 2;                     // items whose loads are issued before the first one is used (1 and two divisions per item: 157 us; 2: 113; 4 at 128 registers: 111)
+    while (pix < npix) {
+        float gpv[kInFlight][4];
+        uint4 avv[kInFlight];
+        size_t at[kInFlight];
+        bool on[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            at[u] = pix;
+            on[u] = pix < npix;
+            if (on[u]) { fetch(gpv[u], avv[u]); advance(); }
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+            if (on[u]) item(at[u], gpv[u], avv[u]);
     }
     // lanes l, l + groups, l + 2 groups, ... hold the same channel group: combine them
     for (int o = groups; o < 32; o <<= 1) {
@@ -166,12 +199,22 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(__nv_bfloat16* __rest
 // ---------------------------------------------------------------- 2x2 max-pool backward (+ skip-connection gradient)
 // gc[n,h,w,c] = (gskip ? gskip : 0) + gp[n,h/2,w/2,c] at the first arg-max of each window (row-major scan order, as torch),
 // optionally times act'(cfull).  Work item = (pooled pixel, 8 channels): 16-byte loads / stores throughout.
+// kBias: dbias[ch] += sum over pixels of the values written to gc (the bias gradient of the conv whose pre-activation gradient gc is) —
+// the tensor is in registers here, the separate read-only pass (act_bwd_bias with act none) read it back from HBM / L2.  Needs
+// grid * 256 to be a multiple of c / 8 (a thread keeps its channel group) and c floats of dynamic shared memory.
+template <bool kBias>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ gp, const __nv_bfloat16* __restrict__ cfull,
                                                           const __nv_bfloat16* __restrict__ gskip, __nv_bfloat16* __restrict__ gc,
-                                                          int n, int h, int w, int c, int act_kind) {
+                                                          float* dbias, int n, int h, int w, int c, int act_kind) {
+    extern __shared__ float s_pool_bias[];
     const int ho = h / 2, wo = w / 2, c8 = c / 8;
     const size_t total = (size_t)n * ho * wo * c8;
     const float sl = act_kind == 1 ? 0.2f : 0.f;
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (kBias) {
+        for (int i = threadIdx.x; i < c; i += blockDim.x) s_pool_bias[i] = 0.f;
+        __syncthreads();
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int cc = (int)(i % c8);
         size_t r = i / c8;
@@ -209,10 +252,21 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
                 if (act_kind)           // fused act'(cfull): the sum is rounded to bf16 first, as when the two steps were separate kernels
                     o = __floats2bfloat162_rn(__low2float(o) * (v0[k] > 0.f ? 1.f : sl), __high2float(o) * (v1[k] > 0.f ? 1.f : sl));
                 ow[k][q] = *reinterpret_cast<const uint32_t*>(&o);
+                if (kBias) { bsum[2 * q] += __low2float(o); bsum[2 * q + 1] += __high2float(o); }   // the stored (bf16) values, as the separate pass summed
             }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(gc + idx[k]) = make_uint4(ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
+    }
+    if (kBias) {
+        const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int cc = (int)(tid % (size_t)c8);                // the channel group of every item of this thread
+        if (tid < total) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&s_pool_bias[cc * 8 + k], bsum[k]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&dbias[i], s_pool_bias[i]);
     }
 }
 

@@ -10,7 +10,7 @@
 
 namespace pnnp {                                     // the kernels' dynamic shared memory (`extern __shared__` arrays)
 alignas(16) uint8_t s_fast[kFastSmemBytes];
-float s_acc[4 * 64 + 4 + 64], s_b[1024], s_b2[2048];
+float s_acc[4 * 64 + 4 + 64], s_b[1024], s_b2[2048], s_pool_bias[2048];
 alignas(16) uint8_t s2_raw[sizeof(Ssim2Tile)];
 }
 
@@ -85,9 +85,17 @@ int emul_act_bwd_bias_v2_kernel(uint16_t* g, const uint16_t* out, float* dbias, 
 int emul_maxpool_bwd(const uint16_t* gp, const uint16_t* cfull, const uint16_t* gskip, uint16_t* gc, int n, int h, int w, int c,
                      int act_kind, int blocks) {
     if ((h & 1) || (w & 1) || (c & 7)) return 1;
-    SIMT_LAUNCH(blocks, 256, (maxpool_bwd_kernel(reinterpret_cast<const __nv_bfloat16*>(gp), reinterpret_cast<const __nv_bfloat16*>(cfull),
-                                                 reinterpret_cast<const __nv_bfloat16*>(gskip), reinterpret_cast<__nv_bfloat16*>(gc), n, h, w, c,
-                                                 act_kind)));
+    SIMT_LAUNCH(blocks, 256, (maxpool_bwd_kernel<false>(reinterpret_cast<const __nv_bfloat16*>(gp), reinterpret_cast<const __nv_bfloat16*>(cfull),
+                                                        reinterpret_cast<const __nv_bfloat16*>(gskip), reinterpret_cast<__nv_bfloat16*>(gc), nullptr,
+                                                        n, h, w, c, act_kind)));
+    return 0;
+}
+int emul_maxpool_bwd_bias(const uint16_t* gp, const uint16_t* cfull, const uint16_t* gskip, uint16_t* gc, float* dbias, int n, int h, int w,
+                          int c, int act_kind, int blocks) {
+    if ((h & 1) || (w & 1) || (c & 7) || (256 % (c / 8))) return 1;
+    SIMT_LAUNCH(blocks, 256, (maxpool_bwd_kernel<true>(reinterpret_cast<const __nv_bfloat16*>(gp), reinterpret_cast<const __nv_bfloat16*>(cfull),
+                                                       reinterpret_cast<const __nv_bfloat16*>(gskip), reinterpret_cast<__nv_bfloat16*>(gc), dbias,
+                                                       n, h, w, c, act_kind)));
     return 0;
 }
 int emul_adam(float* p, const float* g, float* m, float* v, size_t total, float lr, float b1, float b2, float eps, int step, float gscale,

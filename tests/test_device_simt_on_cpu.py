@@ -254,6 +254,29 @@ def test_maxpool_backward_kernel_vs_torch_autograd(S, act_kind, skip):
         assert torch.equal(got + 0.0, ref + 0.0)                         # +0.0: -0 and +0 compare equal either way; kept explicit
 
 
+@pytest.mark.parametrize("act_kind,skip,c", [(1, True, 32), (0, False, 64), (1, True, 256)])
+def test_maxpool_backward_with_bias_sums_kernel(S, act_kind, skip, c):
+    """The fused form (pnnp_maxpool_bwd_bias): the routed gradient is bit-identical to the plain kernel's, and dbias receives the
+    per-channel sums of the stored bf16 values on top of what it held (the separate read-only pass it replaces)."""
+    import torch
+    g = torch.Generator().manual_seed(5 + c)
+    n, h, w = 2, 6, 10
+    cfull = (torch.randint(-3, 4, (n, c, h, w), generator=g).float() * 0.25).to(torch.bfloat16)
+    gp = torch.randn((n, c, h // 2, w // 2), generator=g).to(torch.bfloat16)
+    gskip = torch.randn((n, c, h, w), generator=g).to(torch.bfloat16) if skip else None
+    nhwc = lambda t: _bf16_bits(t.permute(0, 2, 3, 1))
+    args = (_p(nhwc(gp), _u16p), _p(nhwc(cfull), _u16p), _p(nhwc(gskip), _u16p) if skip else None)
+    ref = np.zeros((n, h, w, c), np.uint16)
+    assert S.emul_maxpool_bwd(*args, _p(ref, _u16p), n, h, w, c, act_kind, 2) == 0
+    want = _from_bits(ref).double().reshape(-1, c).sum(0).numpy()
+    for blocks in (1, 2, 3):
+        gc, db = np.zeros((n, h, w, c), np.uint16), np.full(c, 0.5, np.float32)
+        assert S.emul_maxpool_bwd_bias(*args, _p(gc, _u16p), _p(db, _f32p), n, h, w, c, act_kind, blocks) == 0
+        assert np.array_equal(gc, ref)
+        assert np.allclose(db - 0.5, want, rtol=1e-5, atol=1e-4)
+    assert S.emul_maxpool_bwd_bias(*args, _p(gc, _u16p), _p(db, _f32p), n, h, w, 24, act_kind, 1) == 1      # 3 channel groups do not divide 256
+
+
 @pytest.mark.parametrize("on_device_state", [0, 1])
 def test_adam_kernels_vs_torch_optim(S, on_device_state):
     """torch.optim.Adam defaults (betas 0.9 / 0.999, eps 1e-8, no weight decay), three steps; `gscale` = the 1 / world factor of the

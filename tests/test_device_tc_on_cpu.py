@@ -82,6 +82,10 @@ class _EmulatedLibrary:
     def pnnp_maxpool_bwd(self, gp, cfull, gskip, gc, n, h, w, c, act, stream):
         return self.sk.emul_maxpool_bwd(C.c_void_p(gp), C.c_void_p(cfull), C.c_void_p(gskip), C.c_void_p(gc), n, h, w, c, act, 2)
 
+    def pnnp_maxpool_bwd_bias(self, gp, cfull, gskip, gc, dbias, n, h, w, c, act, stream):
+        return self.sk.emul_maxpool_bwd_bias(C.c_void_p(gp), C.c_void_p(cfull), C.c_void_p(gskip), C.c_void_p(gc), C.c_void_p(dbias),
+                                             n, h, w, c, act, 2)
+
     def pnnp_l1_loss(self, pred, hr, gpred, total, loss_sum, stream):
         return self.sk.emul_l1_loss(C.c_void_p(pred), C.c_void_p(hr), C.c_void_p(gpred), C.c_size_t(total), C.c_void_p(loss_sum), 2)
 

@@ -106,6 +106,27 @@ def test_maxpool_backward_with_skip():
     assert torch.equal(_nchw(gc), _bf(_bf(x.grad + gs) * torch.where(x.detach() > 0, 1.0, 0.2)))
 
 
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 32, 32), (8, 64, 64, 256), (3, 38, 52, 64)])
+def test_maxpool_backward_with_bias_sums(n, h, w, c):
+    """pnnp_maxpool_bwd_bias: gradient bit-identical to pnnp_maxpool_bwd, bias sums equal to the separate pass (pnnp_act_bwd_bias, act none)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = _nhwc(_bf(torch.randn((n, c, h, w), device="cuda", generator=g)))
+    gp = _nhwc(_bf(torch.randn((n, c, h // 2, w // 2), device="cuda", generator=g)))
+    gs = _nhwc(_bf(torch.randn((n, c, h, w), device="cuda", generator=g)))
+    ref, gc = torch.empty_like(x), torch.empty_like(x)
+    L.check(L.lib().pnnp_maxpool_bwd(gp.data_ptr(), x.data_ptr(), gs.data_ptr(), ref.data_ptr(), n, h, w, c, L.ACT_LEAKY, _sp()), "pool_bwd")
+    want = torch.full((c,), 0.25, device="cuda")
+    L.check(L.lib().pnnp_act_bwd_bias(ref.data_ptr(), None, want.data_ptr(), n * h * w, c, L.ACT_NONE, _sp()), "bias sums")
+    db = torch.full((c,), 0.25, device="cuda")
+    L.check(L.lib().pnnp_maxpool_bwd_bias(gp.data_ptr(), x.data_ptr(), gs.data_ptr(), gc.data_ptr(), db.data_ptr(),
+                                          n, h, w, c, L.ACT_LEAKY, _sp()), "pool_bwd_bias")
+    torch.cuda.synchronize()
+    assert torch.equal(gc, ref)
+    exact = ref.double().reshape(-1, c).sum(0) + 0.25
+    tol = 1e-5 * ref.double().abs().reshape(-1, c).sum(0) + 1e-4
+    assert ((db.double() - exact).abs() <= tol).all() and ((want.double() - exact).abs() <= tol).all()
+
+
 @pytest.mark.parametrize("ci,co,h,w,n", [(16, 32, 16, 32, 1), (32, 32, 24, 40, 2), (32, 64, 20, 36, 1), (64, 64, 16, 48, 2),
                                          (64, 128, 16, 16, 2), (128, 64, 16, 32, 1), (128, 128, 24, 16, 1), (256, 256, 8, 16, 1),
                                          (512, 256, 8, 8, 1), (256, 512, 4, 6, 2)])
