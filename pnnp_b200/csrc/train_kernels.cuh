@@ -216,11 +216,19 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
         __syncthreads();
     }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int cc = (int)(i % c8);
-        size_t r = i / c8;
-        const int xo = (int)(r % wo); r /= wo;
-        const int yo = (int)(r % ho);
-        const int img = (int)(r / ho);
+        int cc, xo, yo, img;
+        if (total <= 0xFFFFFFFFull) {                         // 32-bit index arithmetic (the 64-bit divisions were most of the kernel's instructions)
+            uint32_t r = (uint32_t)i;
+            const uint32_t q0 = r / (uint32_t)c8; cc = (int)(r - q0 * (uint32_t)c8); r = q0;
+            const uint32_t q1 = r / (uint32_t)wo; xo = (int)(r - q1 * (uint32_t)wo); r = q1;
+            const uint32_t q2 = r / (uint32_t)ho; yo = (int)(r - q2 * (uint32_t)ho); img = (int)q2;
+        } else {
+            size_t r = i / c8;
+            cc = (int)(i % c8);
+            xo = (int)(r % wo); r /= wo;
+            yo = (int)(r % ho);
+            img = (int)(r / ho);
+        }
         const size_t base = (((size_t)img * h + 2 * yo) * w + 2 * xo) * c + cc * 8;
         const size_t idx[4] = {base, base + c, base + (size_t)w * c, base + (size_t)w * c + c};
         uint4 cv[4], sv[4];
