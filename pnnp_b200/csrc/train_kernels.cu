@@ -36,8 +36,9 @@ extern "C" int pnnp_head_bwd(const float* gpred, const void* act, const float* W
     if (!gpred || !act || !W || !gact || !dW || !db || co < 1 || co > 4 || (cin != 8 && cin != 16 && cin != 32 && cin != 64))
         return fail("head_bwd: bad arguments (1..4 outputs, 8/16/32/64 input channels)");
     const size_t smem = sizeof(float) * (size_t)(co * cin + co + cin);
-    // every block ends in co * cin + co + cin same-address atomics: few, long-lived blocks (PNNP_HEADBWD_BLOCKS: timing experiments)
-    static const int hb_max = getenv("PNNP_HEADBWD_BLOCKS") ? atoi(getenv("PNNP_HEADBWD_BLOCKS")) : 148 * 8;
+    // every block ends in 132 shuffles per thread and co * cin + co + cin same-address atomics: few, long-lived blocks — two per SM,
+    // what 127 registers keep resident (r02, 8 crops: 296 blocks 100 us, 592 104, 1184 112, 2368 112; PNNP_HEADBWD_BLOCKS: timing experiments)
+    static const int hb_max = getenv("PNNP_HEADBWD_BLOCKS") ? atoi(getenv("PNNP_HEADBWD_BLOCKS")) : 148 * 2;
     head_bwd_kernel<<<std::min(blocks_for((size_t)n * h * w * (cin / 8)), hb_max), 256, smem, (cudaStream_t)stream>>>(
         gpred, static_cast<const __nv_bfloat16*>(act), W, static_cast<__nv_bfloat16*>(gact), dW, db, dbias_prev, n, h, w, cin, co, act_kind);
     count_launch();

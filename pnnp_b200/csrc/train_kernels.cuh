@@ -79,14 +79,26 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     // A thread's items are ps pixels apart (grid * 256 is a multiple of the group count), so (image, offset inside the plane) advance
     // by increment and carry: the two 64-bit divisions per item of the first form were more than half of its executed instructions
     // (r02 launch list: 157 us for 302 MB).  Two items per trip, loads first; the additions keep their order (same results bit for bit).
-    const size_t ps = ((size_t)gridDim.x * blockDim.x) >> sh;
-    size_t pix = tid >> sh;
-    size_t img = pix / plane, off = pix - img * plane;
-    auto advance = [&]() { pix += ps; off += ps; while (off >= plane) { off -= plane; ++img; } };
+    // Pointers advance with the items (one add each; a carry adds the co - 1 planes between two images): the first form of this loop
+    // rebuilt (img * co + o) * plane + off and pix * cin + c in 64 bits for every load and store — 87 of its 250 instructions per item.
+    const size_t ps = ((size_t)gridDim.x * blockDim.x) >> sh, pe = ps * (size_t)cin, nelem = npix * (size_t)cin;
+    size_t off, eo;                                   // offset inside the image plane; element offset of the item in act / gact
+    const float* gptr;                                // gpred of (image, output 0, off)
+    {
+        const size_t pix = tid >> sh, img = pix / plane;
+        off = pix - img * plane;
+        eo = pix * (size_t)cin + (size_t)c;
+        gptr = gpred + img * (size_t)co * plane + off;
+    }
+    const size_t carry = (size_t)(co - 1) * plane;
+    auto advance = [&]() {
+        eo += pe; off += ps; gptr += ps;
+        while (off >= plane) { off -= plane; gptr += carry; }
+    };
     auto fetch = [&](float (&gp)[4], uint4& av) {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) gp[o] = o < co ? gpred[(img * co + o) * plane + off] : 0.f;
-        av = *reinterpret_cast<const uint4*>(act + pix * cin + c);
+        for (int o = 0; o < 4; ++o) gp[o] = o < co ? gptr[(size_t)o * plane] : 0.f;
+        av = *reinterpret_cast<const uint4*>(act + eo);
     };
     auto item = [&](size_t at, const float (&gp)[4], const uint4& av) {
         const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
@@ -109,18 +121,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
             for (int o = 0; o < 4; ++o) adb[o] += gp[o];
         }
-        *reinterpret_cast<uint4*>(gact + at * cin + c) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+        *reinterpret_cast<uint4*>(gact + at) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
     };
     constexpr int kInFlight = 2;                     // items whose loads are issued before the first one is used (1 and two divisions per item: 157 us; 2: 113; 4 at 128 registers: 111)
-    while (pix < npix) {
+    while (eo < nelem) {
         float gpv[kInFlight][4];
         uint4 avv[kInFlight];
         size_t at[kInFlight];
         bool on[kInFlight];
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) {
-            at[u] = pix;
-            on[u] = pix < npix;
+            at[u] = eo;
+            on[u] = eo < nelem;
             if (on[u]) { fetch(gpv[u], avv[u]); advance(); }
         }
 #pragma unroll
