@@ -47,6 +47,19 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
     if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum, acc);
 }
 
+// packed pairs of fp32 (FFMA2: the same IEEE fma on both halves, half the issue slots)
+#ifndef PNNP_HOST_EMUL
+__device__ __forceinline__ uint64_t hb_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void hb_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t hb_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#else
+static inline uint64_t hb_pack(float a, float b) { return (uint64_t)__float_as_uint(a) | ((uint64_t)__float_as_uint(b) << 32); }
+static inline void hb_unpack(uint64_t v, float& a, float& b) { a = __uint_as_float((uint32_t)v); b = __uint_as_float((uint32_t)(v >> 32)); }
+static inline uint64_t hb_fma(uint64_t x, uint64_t y, uint64_t z) {
+    float a, b, c, d, e, f; hb_unpack(x, a, b); hb_unpack(y, c, d); hb_unpack(z, e, f); return hb_pack(fmaf(a, c, e), fmaf(b, d, f));
+}
+#endif
+
 // ---------------------------------------------------------------- 1x1 head backward (out_nc <= 4, cin <= 64)
 // gpred: NCHW fp32 [n][co][h][w]; act: NHWC bf16 [n,h,w,cin] = LeakyReLU output feeding the head;
 // gact (out): NHWC bf16 gradient w.r.t. the PRE-activation of that layer (already multiplied by act');
@@ -68,11 +81,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const size_t plane = (size_t)h * w, npix = (size_t)n * plane;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int grp = (int)(tid & (size_t)(groups - 1)), c = grp * 8;
-    float wv[4][8], adw[4][8], adb[4] = {0.f, 0.f, 0.f, 0.f}, abp[8];
+    float adb[4] = {0.f, 0.f, 0.f, 0.f}, abp[8];
+    uint64_t wv2[4][4], adw2[4][4];                   // channel pairs (2 k2, 2 k2 + 1): weights and the dW accumulators
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { wv[o][k] = o < co ? W[o * cin + c + k] : 0.f; adw[o][k] = 0.f; }
+        for (int k2 = 0; k2 < 4; ++k2) {
+            wv2[o][k2] = o < co ? hb_pack(W[o * cin + c + 2 * k2], W[o * cin + c + 2 * k2 + 1]) : hb_pack(0.f, 0.f);
+            adw2[o][k2] = hb_pack(0.f, 0.f);
+        }
 #pragma unroll
     for (int k = 0; k < 8; ++k) abp[k] = 0.f;
     const float slope = act_kind == 1 ? 0.2f : (act_kind == 2 ? 0.f : 1.f);
@@ -103,15 +120,21 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     auto item = [&](size_t at, const float (&gp)[4], const uint4& av) {
         const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
         uint32_t gw[4];
+        uint64_t gp2[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) gp2[o] = hb_pack(gp[o], gp[o]);
 #pragma unroll
         for (int k2 = 0; k2 < 4; ++k2) {
             const float a0 = __uint_as_float(aw[k2] << 16), a1 = __uint_as_float(aw[k2] & 0xFFFF0000u);
-            float g0 = 0.f, g1 = 0.f;
+            const uint64_t a2 = hb_pack(a0, a1);
+            uint64_t g2 = hb_pack(0.f, 0.f);
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                g0 = fmaf(gp[o], wv[o][2 * k2], g0); g1 = fmaf(gp[o], wv[o][2 * k2 + 1], g1);
-                adw[o][2 * k2] = fmaf(gp[o], a0, adw[o][2 * k2]); adw[o][2 * k2 + 1] = fmaf(gp[o], a1, adw[o][2 * k2 + 1]);
+            for (int o = 0; o < 4; ++o) {             // the fmas of the scalar form, two channels per instruction (same order: same bits)
+                g2 = hb_fma(gp2[o], wv2[o][k2], g2);
+                adw2[o][k2] = hb_fma(gp2[o], a2, adw2[o][k2]);
             }
+            float g0, g1;
+            hb_unpack(g2, g0, g1);
             g0 *= a0 > 0.f ? 1.f : slope; g1 *= a1 > 0.f ? 1.f : slope;
             abp[2 * k2] += g0; abp[2 * k2 + 1] += g1;      // pre-activation gradient: what the previous conv's bias gradient sums
             const __nv_bfloat162 hb = __floats2bfloat162_rn(g0, g1);
@@ -139,6 +162,11 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         for (int u = 0; u < kInFlight; ++u)
             if (on[u]) item(at[u], gpv[u], avv[u]);
     }
+    float adw[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) hb_unpack(adw2[o][k2], adw[o][2 * k2], adw[o][2 * k2 + 1]);
     // lanes l, l + groups, l + 2 groups, ... hold the same channel group: combine them
     for (int o = groups; o < 32; o <<= 1) {
 #pragma unroll
