@@ -291,8 +291,12 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
                 s0[k] = __uint_as_float(sw << 16); s1[k] = __uint_as_float(sw & 0xFFFF0000u);
             }
             int a0 = 0, a1 = 0;
+            float m0 = v0[0], m1 = v1[0];                     // the running maxima in registers (v0[a0] was a local-memory access)
 #pragma unroll
-            for (int k = 1; k < 4; ++k) { if (v0[k] > v0[a0]) a0 = k; if (v1[k] > v1[a1]) a1 = k; }
+            for (int k = 1; k < 4; ++k) {
+                if (v0[k] > m0) { m0 = v0[k]; a0 = k; }
+                if (v1[k] > m1) { m1 = v1[k]; a1 = k; }
+            }
             const float g0 = __uint_as_float(gw[q] << 16), g1 = __uint_as_float(gw[q] & 0xFFFF0000u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
